@@ -1,0 +1,67 @@
+"""Build helpers: compile the CUDA plugin (sm_100a) and the GPU-less model.
+
+``python -m acts_b200.build`` builds everything in-tree so that the shared
+objects travel with the repository snapshot to the GPU box.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "acts_b200", "csrc")
+PLUGIN_SO = os.path.join(ROOT, "acts_b200", "libacts_b200_seeding.so")
+MODEL_SO = os.path.join(ROOT, "tests", "model", "libgpu_model.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++20",
+    # exact binary32 replay of the reference: no FMA contraction, IEEE div/sqrt
+    "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall",
+    "-shared",
+]
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def plugin_sources():
+    names = ["seeding_plugin.cu", "host_plan.cpp", "seeding_kernels.cuh", "seed_math.h", "host_plan.hpp"]
+    return [os.path.join(CSRC, n) for n in names] + [os.path.join(ROOT, "include", "acts_b200_seeding.h")]
+
+
+def build_plugin(force: bool = False, verbose: bool = False) -> str:
+    srcs = plugin_sources()
+    if force or _stale(PLUGIN_SO, srcs):
+        cmd = ["nvcc", *NVCC_FLAGS, "-Xptxas", "-v" if verbose else "-warn-spills", "-o", PLUGIN_SO,
+               os.path.join(CSRC, "seeding_plugin.cu"), os.path.join(CSRC, "host_plan.cpp")]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed building the seeding plugin")
+    return PLUGIN_SO
+
+
+def build_model(force: bool = False) -> str:
+    src = os.path.join(ROOT, "tests", "model", "gpu_model.cpp")
+    srcs = [src, os.path.join(CSRC, "seed_math.h")]
+    if force or _stale(MODEL_SO, srcs):
+        cmd = [os.environ.get("CXX", "g++"), "-O2", "-g", "-std=gnu++20", "-fPIC", "-ffp-contract=off", "-Wall",
+               "-shared", "-o", MODEL_SO, src]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("g++ failed building the GPU-less model")
+    return MODEL_SO
+
+
+if __name__ == "__main__":
+    print(build_plugin(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_model(force="--force" in sys.argv))

@@ -1,0 +1,281 @@
+"""ctypes mirror of ``include/acts_b200_seeding.h`` and the canonical configurations.
+
+The field names are the reference's ``GridTripletSeedingAlgorithm::Config``
+(Examples/Algorithms/TrackFinding/include/ActsExamples/TrackFinding/
+GridTripletSeedingAlgorithm.hpp:34-244).  This module is pure host-side
+marshalling; it never computes anything the engine computes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+ABI_VERSION = 1
+
+# status codes (acts_b200_seeding.h)
+OK, ERR_INVALID_ARGUMENT, ERR_RUNTIME, ERR_DOMAIN, ERR_UNSUPPORTED, ERR_CUDA, ERR_CAPACITY, ERR_OVERFLOW = range(8)
+
+# Acts::UnitConstants (Core/include/Acts/Definitions/Units.hpp:85,143,149,168)
+mm = 1.0
+GeV = 1.0
+MeV = 1e-3
+T = 0.000299792458
+
+
+class SeedConfirmationRange(C.Structure):
+    _fields_ = [
+        ("zMinSeedConf", C.c_float),
+        ("zMaxSeedConf", C.c_float),
+        ("rMaxSeedConf", C.c_float),
+        ("nTopForLargeR", C.c_uint64),
+        ("nTopForSmallR", C.c_uint64),
+        ("seedConfMinBottomRadius", C.c_float),
+        ("seedConfMaxZOrigin", C.c_float),
+        ("minImpactSeedConf", C.c_float),
+    ]
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_uint32),
+        ("struct_size", C.c_uint32),
+        ("bFieldInZ", C.c_float),
+        ("minPt", C.c_float),
+        ("cotThetaMax", C.c_float),
+        ("impactMax", C.c_float),
+        ("deltaRMin", C.c_float),
+        ("deltaRMax", C.c_float),
+        ("deltaRMinTop", C.c_float),
+        ("deltaRMaxTop", C.c_float),
+        ("deltaRMinBottom", C.c_float),
+        ("deltaRMaxBottom", C.c_float),
+        ("rMin", C.c_float),
+        ("rMax", C.c_float),
+        ("zMin", C.c_float),
+        ("zMax", C.c_float),
+        ("phiMin", C.c_float),
+        ("phiMax", C.c_float),
+        ("phiBinDeflectionCoverage", C.c_int32),
+        ("maxPhiBins", C.c_int32),
+        ("zBinNeighborsTop", C.POINTER(C.c_int32)),
+        ("nZBinNeighborsTop", C.c_uint32),
+        ("zBinNeighborsBottom", C.POINTER(C.c_int32)),
+        ("nZBinNeighborsBottom", C.c_uint32),
+        ("numPhiNeighbors", C.c_int32),
+        ("zBinEdges", C.POINTER(C.c_float)),
+        ("nZBinEdges", C.c_uint32),
+        ("zBinsCustomLooping", C.POINTER(C.c_uint64)),
+        ("nZBinsCustomLooping", C.c_uint32),
+        ("rMinMiddle", C.c_float),
+        ("rMaxMiddle", C.c_float),
+        ("useVariableMiddleSPRange", C.c_uint8),
+        ("rRangeMiddleSP", C.POINTER(C.c_float)),
+        ("nRRangeMiddleSP", C.c_uint32),
+        ("deltaRMiddleMinSPRange", C.c_float),
+        ("deltaRMiddleMaxSPRange", C.c_float),
+        ("deltaZMin", C.c_float),
+        ("deltaZMax", C.c_float),
+        ("interactionPointCut", C.c_uint8),
+        ("collisionRegionMin", C.c_float),
+        ("collisionRegionMax", C.c_float),
+        ("helixCutTolerance", C.c_float),
+        ("sigmaScattering", C.c_float),
+        ("radLengthPerSeed", C.c_float),
+        ("toleranceParam", C.c_float),
+        ("deltaInvHelixDiameter", C.c_float),
+        ("compatSeedWeight", C.c_float),
+        ("impactWeightFactor", C.c_float),
+        ("zOriginWeightFactor", C.c_float),
+        ("maxSeedsPerSpM", C.c_uint32),
+        ("compatSeedLimit", C.c_uint64),
+        ("seedWeightIncrement", C.c_float),
+        ("numSeedIncrement", C.c_float),
+        ("seedConfirmation", C.c_uint8),
+        ("centralSeedConfirmationRange", SeedConfirmationRange),
+        ("forwardSeedConfirmationRange", SeedConfirmationRange),
+        ("maxSeedsPerSpMConf", C.c_uint32),
+        ("maxQualitySeedsPerSpMConf", C.c_uint32),
+        ("useDeltaRinsteadOfTopRadius", C.c_uint8),
+        ("useExtraCuts", C.c_uint8),
+        ("relaxedFloat", C.c_uint8),
+    ]
+
+    # python-side keep-alives for the (pointer, count) members
+    _ARRAYS = {
+        "zBinNeighborsTop": (C.c_int32, "nZBinNeighborsTop", 2),
+        "zBinNeighborsBottom": (C.c_int32, "nZBinNeighborsBottom", 2),
+        "zBinEdges": (C.c_float, "nZBinEdges", 1),
+        "zBinsCustomLooping": (C.c_uint64, "nZBinsCustomLooping", 1),
+        "rRangeMiddleSP": (C.c_float, "nRRangeMiddleSP", 2),
+    }
+
+    def set_array(self, name, values):
+        """Set a vector member; ``values`` is a flat list or a list of pairs."""
+        ctype, count_name, width = self._ARRAYS[name]
+        flat = []
+        for v in values:
+            if width == 2:
+                flat.extend(v)
+            else:
+                flat.append(v)
+        if not hasattr(self, "_keep"):
+            self._keep = {}
+        arr = (ctype * max(len(flat), 1))(*flat)
+        self._keep[name] = arr
+        setattr(self, name, C.cast(arr, C.POINTER(ctype)))
+        setattr(self, count_name, len(flat) // width)
+
+    def update(self, **kw):
+        for k, v in kw.items():
+            if k in self._ARRAYS:
+                self.set_array(k, v)
+            elif k in ("centralSeedConfirmationRange", "forwardSeedConfirmationRange"):
+                rng = getattr(self, k)
+                for rk, rv in v.items():
+                    setattr(rng, rk, rv)
+            else:
+                if not any(k == f[0] for f in self._fields_):
+                    raise AttributeError(f"unknown config field {k}")
+                setattr(self, k, v)
+        return self
+
+
+class Seeds(C.Structure):
+    _fields_ = [
+        ("bottom", C.c_void_p),
+        ("middle", C.c_void_p),
+        ("top", C.c_void_p),
+        ("quality", C.c_void_p),
+        ("vertexZ", C.c_void_p),
+        ("capacity", C.c_uint64),
+        ("size", C.c_uint64),
+    ]
+
+
+class Info(C.Structure):
+    _fields_ = [
+        ("phiBins", C.c_int32),
+        ("zBins", C.c_int32),
+        ("rBins", C.c_int32),
+        ("nGlobalBins", C.c_int32),
+        ("minHelixDiameter2", C.c_float),
+        ("highland", C.c_float),
+        ("sigmapT2perRadius", C.c_float),
+        ("multipleScattering2", C.c_float),
+        ("deltaRMinBottom", C.c_float),
+        ("deltaRMaxBottom", C.c_float),
+        ("deltaRMinTop", C.c_float),
+        ("deltaRMaxTop", C.c_float),
+        ("smCount", C.c_int32),
+        ("ccMajor", C.c_int32),
+        ("ccMinor", C.c_int32),
+    ]
+
+
+class Counters(C.Structure):
+    _fields_ = [
+        ("nSpacePoints", C.c_uint64),
+        ("nInGrid", C.c_uint64),
+        ("nMiddles", C.c_uint64),
+        ("nBottomDoublets", C.c_uint64),
+        ("nTopDoublets", C.c_uint64),
+        ("nTripletTests", C.c_uint64),
+        ("nCandidates", C.c_uint64),
+        ("nSeeds", C.c_uint64),
+        ("nTieMiddles", C.c_uint64),
+        ("nKernelLaunches", C.c_uint64),
+    ]
+
+    def as_dict(self):
+        return {f[0]: int(getattr(self, f[0])) for f in self._fields_}
+
+
+class Doublets(C.Structure):
+    _fields_ = [
+        ("nMiddles", C.c_uint64),
+        ("nDoublets", C.c_uint64),
+        ("middlePos", C.c_void_p),
+        ("firstDoublet", C.c_void_p),
+        ("nBottom", C.c_void_p),
+        ("otherPos", C.c_void_p),
+        ("cotTheta", C.c_void_p),
+        ("iDeltaR", C.c_void_p),
+        ("er", C.c_void_p),
+        ("u", C.c_void_p),
+        ("v", C.c_void_p),
+        ("xNew", C.c_void_p),
+        ("yNew", C.c_void_p),
+        ("middleCapacity", C.c_uint64),
+        ("doubletCapacity", C.c_uint64),
+    ]
+
+
+def f32(v: float) -> float:
+    """Round a python float to binary32 (what assigning to a C float does)."""
+    return C.c_float(v).value
+
+
+def seeding_py_config(init) -> Config:
+    """Config 1 of BASELINE.json: Examples/Scripts/Python/seeding.py:117-134 verbatim.
+
+    ``init`` is a ``*_config_init(Config*)`` function (product or oracle).
+    """
+    cfg = Config()
+    init(C.byref(cfg))
+    cfg.update(
+        rMax=200 * mm,
+        deltaRMin=1 * mm,
+        deltaRMax=300 * mm,
+        deltaRMinTop=1 * mm,
+        deltaRMaxTop=300 * mm,
+        deltaRMinBottom=1 * mm,
+        deltaRMaxBottom=300 * mm,
+        collisionRegionMin=-250 * mm,
+        collisionRegionMax=250 * mm,
+        zMin=-2000 * mm,
+        zMax=2000 * mm,
+        maxSeedsPerSpM=1,
+        sigmaScattering=50,
+        radLengthPerSeed=0.1,
+        minPt=500 * MeV,
+        impactMax=3 * mm,
+        bFieldInZ=2 * T,
+    )
+    return cfg
+
+
+def pu200_config(init) -> Config:
+    """Configs 2-5 of BASELINE.json: the reference's own <mu>=200 cut set,
+    CI/physmon/workflows/physmon_trackfinding_ttbar_pu200.py:104-114
+    (identical to seeding.py except sigmaScattering=5; rMin=33 is ignored by the
+    grid, GridTripletSeedingAlgorithm.cpp:133-134)."""
+    cfg = seeding_py_config(init)
+    cfg.update(sigmaScattering=5, rMin=33 * mm)
+    return cfg
+
+
+def itk_like_config(init) -> Config:
+    """A non-uniform z-binned configuration exercising zBinEdges,
+    zBinNeighbors{Top,Bottom}, zBinsCustomLooping and rRangeMiddleSP
+    (shape of Python/Examples/python/itk.py:300-560 scaled to the generic
+    detector; used by parity tests only)."""
+    cfg = pu200_config(init)
+    edges = [-2000.0, -1000.0, -500.0, -200.0, 0.0, 200.0, 500.0, 1000.0, 2000.0]
+    n = len(edges) - 1
+    cfg.update(
+        zBinEdges=edges,
+        zBinNeighborsTop=[(0, 0), (-1, 0), (-1, 0), (-1, 0), (0, 1), (0, 1), (0, 1), (0, 0)],
+        zBinNeighborsBottom=[(0, 1), (0, 1), (0, 1), (0, 1), (-1, 0), (-1, 0), (-1, 0), (-1, 0)],
+        zBinsCustomLooping=[1, 8, 2, 7, 3, 6, 4, 5],
+        rRangeMiddleSP=[(60.0, 130.0)] * 2 + [(50.0, 120.0)] * (n - 4) + [(60.0, 130.0)] * 2,
+        numPhiNeighbors=1,
+        maxSeedsPerSpM=4,
+        deltaRMinTop=6.0,
+        deltaRMaxTop=280.0,
+        deltaRMinBottom=6.0,
+        deltaRMaxBottom=150.0,
+    )
+    return cfg
+
+
+NAN = math.nan

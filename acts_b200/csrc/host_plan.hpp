@@ -1,0 +1,50 @@
+// host_plan.hpp -- host-side planning of the B200 seeding engine.
+//
+// Replaces the constructor chain of the reference algorithm:
+//   GridTripletSeedingAlgorithm ctor      GridTripletSeedingAlgorithm.cpp:101-178
+//   CylindricalSpacePointGrid ctor        Core/src/Seeding/CylindricalSpacePointGrid.cpp:15-99
+//   computeSpacePointGridPhiBins          Core/src/Seeding/detail/SpacePointGridPhiBinning.cpp:20-95
+//   DoubletSeedFinder::DerivedConfig      Core/src/Seeding/DoubletSeedFinder.cpp:351-357
+//   TripletSeedFinder::DerivedConfig      Core/src/Seeding/TripletSeedFinder.cpp:456-481
+//   BinnedGroup / GridBinFinder tables    BinnedGroup.ipp:32-62, GridBinFinder.ipp:42-76
+// All derived constants are computed here, on the host, with the reference's
+// exact expressions and types, and handed to the device as plain numbers.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/acts_b200_seeding.h"
+#include "seed_math.h"
+
+namespace b200seed {
+
+struct PlanError {
+  int code = B200SEED_OK;
+  std::string message;
+};
+
+struct HostPlan {
+  DeviceConfig dev{};
+  b200seed_info info{};
+  // middle bins in the reference's visiting order (phi outermost, z in
+  // zBinsCustomLooping order, r) as global bin indices
+  std::vector<uint32_t> navBins;
+  // neighbour bins of every navigation entry, flattened; empty (under/overflow)
+  // bins are kept so that the emission order is literally the reference's
+  std::vector<uint32_t> botOffsets, botBins, topOffsets, topBins;
+  uint32_t maxNeighborBins = 0;
+  // per-middle output slots: min(maxSeedsPerSpM + 1, maxSeedsPerSpMConf)
+  uint32_t seedsPerMiddle = 0;
+  bool relaxedFloat = false;
+};
+
+// Validates like the reference (same exception classes mapped to status codes)
+// and fills the plan.  Returns false and sets err on failure.
+bool make_host_plan(const b200seed_config& cfg, HostPlan& plan, PlanError& err);
+
+// Reference defaults (GridTripletSeedingAlgorithm.hpp:34-244).
+void config_defaults(b200seed_config& cfg);
+
+}  // namespace b200seed

@@ -1,0 +1,637 @@
+// seed_math.h -- exact-arithmetic building blocks of the B200 seeding engine.
+//
+// Everything in this header is `host + device`: the CUDA kernels
+// (seeding_kernels.cu) use it on the GPU and tests/model/ compiles the very same
+// functions with g++ to check them against the CPU oracle without a GPU.
+//
+// Exactness contract: the reference evaluates every cut
+// in IEEE-754 binary32, round-to-nearest, one rounding per operation, no FMA.
+// All float arithmetic below therefore goes through fmul/fadd/fsub/fdiv/fsqrt,
+// which map to __fmul_rn & co. on the device (never contracted into FMA by
+// ptxas, IEEE-correct division and square root) and to plain operators on the
+// host (compiled with -ffp-contract=off, no -march).
+//
+// Reference lines are cited per function (paths relative to the ACTS tree).
+#pragma once
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define B2S_HD __host__ __device__ __forceinline__
+#else
+#define B2S_HD inline
+#endif
+
+#if !defined(__CUDA_ARCH__)
+#include <cmath>
+#include <cstring>
+#endif
+
+namespace b200seed {
+
+// ---------------------------------------------------------------------------
+// IEEE binary32 primitives
+// ---------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+B2S_HD float fmul(float a, float b) { return __fmul_rn(a, b); }
+B2S_HD float fadd(float a, float b) { return __fadd_rn(a, b); }
+B2S_HD float fsub(float a, float b) { return __fsub_rn(a, b); }
+B2S_HD float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+B2S_HD float fsqrt(float a) { return __fsqrt_rn(a); }
+B2S_HD double dadd(double a, double b) { return __dadd_rn(a, b); }
+B2S_HD double dsub(double a, double b) { return __dsub_rn(a, b); }
+B2S_HD double dmul(double a, double b) { return __dmul_rn(a, b); }
+B2S_HD double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+B2S_HD uint32_t f2u(float f) { return __float_as_uint(f); }
+B2S_HD float u2f(uint32_t u) { return __uint_as_float(u); }
+B2S_HD float fabs_(float a) { return fabsf(a); }
+B2S_HD double dfloor(double a) { return floor(a); }
+#else
+B2S_HD float fmul(float a, float b) { return a * b; }
+B2S_HD float fadd(float a, float b) { return a + b; }
+B2S_HD float fsub(float a, float b) { return a - b; }
+B2S_HD float fdiv(float a, float b) { return a / b; }
+B2S_HD float fsqrt(float a) { return std::sqrt(a); }
+B2S_HD double dadd(double a, double b) { return a + b; }
+B2S_HD double dsub(double a, double b) { return a - b; }
+B2S_HD double dmul(double a, double b) { return a * b; }
+B2S_HD double ddiv(double a, double b) { return a / b; }
+B2S_HD uint32_t f2u(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+B2S_HD float u2f(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+B2S_HD float fabs_(float a) { return std::fabs(a); }
+B2S_HD double dfloor(double a) { return std::floor(a); }
+#endif
+
+// ---------------------------------------------------------------------------
+// atan2f exactly as glibc 2.39 (x86-64, generic fdlibm-derived
+// sysdeps/ieee754/flt-32/e_atan2f.c + s_atanf.c) computes it.  The reference
+// bins space points with std::atan2(float, float)
+// (GridTripletSeedingAlgorithm.cpp:219) and glibc's result is NOT correctly
+// rounded, so the device must replay the same operation sequence.  Validated
+// bit-for-bit against the host libm in tests/ (2e8 samples, zero mismatches).
+// ---------------------------------------------------------------------------
+B2S_HD float glibc_atanf(float x) {
+  // atanhi[] / atanlo[] of s_atanf.c, selected by `id` below
+  const float hi0 = 4.6364760399e-01f, hi1 = 7.8539812565e-01f,
+              hi2 = 9.8279368877e-01f, hi3 = 1.5707962513e+00f;
+  const float lo0 = 5.0121582440e-09f, lo1 = 3.7748947079e-08f,
+              lo2 = 3.4473217170e-08f, lo3 = 7.5497894159e-08f;
+  const float aT0 = 3.3333334327e-01f, aT1 = -2.0000000298e-01f,
+              aT2 = 1.4285714924e-01f, aT3 = -1.1111110449e-01f,
+              aT4 = 9.0908870101e-02f, aT5 = -7.6918758452e-02f,
+              aT6 = 6.6610731184e-02f, aT7 = -5.8335702866e-02f,
+              aT8 = 4.9768779427e-02f, aT9 = -3.6531571299e-02f,
+              aT10 = 1.6285819933e-02f;
+  const int32_t hx = (int32_t)f2u(x);
+  const int32_t ix = hx & 0x7fffffff;
+  int id;
+  if (ix >= 0x4c000000) {  // |x| >= 2^25
+    if (ix > 0x7f800000) return fadd(x, x);
+    if (hx > 0) return fadd(hi3, lo3);
+    return fsub(-hi3, lo3);
+  }
+  if (ix < 0x3ee00000) {  // |x| < 0.4375
+    if (ix < 0x31000000) return x;  // |x| < 2^-29
+    id = -1;
+  } else {
+    x = fabs_(x);
+    if (ix < 0x3f980000) {    // |x| < 1.1875
+      if (ix < 0x3f300000) {  // 7/16 <= |x| < 11/16
+        id = 0;
+        x = fdiv(fsub(fmul(2.0f, x), 1.0f), fadd(2.0f, x));
+      } else {  // 11/16 <= |x| < 19/16
+        id = 1;
+        x = fdiv(fsub(x, 1.0f), fadd(x, 1.0f));
+      }
+    } else {
+      if (ix < 0x401c0000) {  // |x| < 2.4375
+        id = 2;
+        x = fdiv(fsub(x, 1.5f), fadd(1.0f, fmul(1.5f, x)));
+      } else {  // 2.4375 <= |x| < 2^25
+        id = 3;
+        x = fdiv(-1.0f, x);
+      }
+    }
+  }
+  const float z = fmul(x, x);
+  const float w = fmul(z, z);
+  float s1 = fadd(aT8, fmul(w, aT10));
+  s1 = fadd(aT6, fmul(w, s1));
+  s1 = fadd(aT4, fmul(w, s1));
+  s1 = fadd(aT2, fmul(w, s1));
+  s1 = fadd(aT0, fmul(w, s1));
+  s1 = fmul(z, s1);
+  float s2 = fadd(aT7, fmul(w, aT9));
+  s2 = fadd(aT5, fmul(w, s2));
+  s2 = fadd(aT3, fmul(w, s2));
+  s2 = fadd(aT1, fmul(w, s2));
+  s2 = fmul(w, s2);
+  if (id < 0) return fsub(x, fmul(x, fadd(s1, s2)));
+  const float ahi = id == 0 ? hi0 : (id == 1 ? hi1 : (id == 2 ? hi2 : hi3));
+  const float alo = id == 0 ? lo0 : (id == 1 ? lo1 : (id == 2 ? lo2 : lo3));
+  const float r = fsub(ahi, fsub(fsub(fmul(x, fadd(s1, s2)), alo), x));
+  return (hx < 0) ? -r : r;
+}
+
+B2S_HD float glibc_atan2f(float y, float x) {
+  const float tiny = 1.0e-30f, pi_o_4 = 7.8539818525e-01f,
+              pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f,
+              pi_lo = -8.7422776573e-08f;
+  const int32_t hx = (int32_t)f2u(x), hy = (int32_t)f2u(y);
+  const int32_t ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
+  if (ix > 0x7f800000 || iy > 0x7f800000) return fadd(x, y);
+  if (hx == 0x3f800000) return glibc_atanf(y);
+  const int32_t m = ((hy >> 31) & 1) | ((hx >> 30) & 2);
+  if (iy == 0) {
+    switch (m) {
+      case 0:
+      case 1: return y;
+      case 2: return fadd(pi, tiny);
+      default: return fsub(-pi, tiny);
+    }
+  }
+  if (ix == 0) return (hy < 0) ? fsub(-pi_o_2, tiny) : fadd(pi_o_2, tiny);
+  if (ix == 0x7f800000) {
+    if (iy == 0x7f800000) {
+      switch (m) {
+        case 0: return fadd(pi_o_4, tiny);
+        case 1: return fsub(-pi_o_4, tiny);
+        case 2: return fadd(fmul(3.0f, pi_o_4), tiny);
+        default: return fsub(fmul(-3.0f, pi_o_4), tiny);
+      }
+    } else {
+      switch (m) {
+        case 0: return 0.0f;
+        case 1: return -0.0f;
+        case 2: return fadd(pi, tiny);
+        default: return fsub(-pi, tiny);
+      }
+    }
+  }
+  if (iy == 0x7f800000) return (hy < 0) ? fsub(-pi_o_2, tiny) : fadd(pi_o_2, tiny);
+  const int32_t k = (iy - ix) >> 23;
+  float z;
+  if (k > 60) {
+    z = fadd(pi_o_2, fmul(0.5f, pi_lo));
+  } else if (hx < 0 && k < -60) {
+    z = 0.0f;
+  } else {
+    z = glibc_atanf(fabs_(fdiv(y, x)));
+  }
+  switch (m) {
+    case 0: return z;
+    case 1: return u2f(f2u(z) ^ 0x80000000u);
+    case 2: return fsub(pi, fsub(z, pi_lo));
+    default: return fsub(fsub(z, pi_lo), pi);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Device-side constants (derived on the host with the reference's expressions)
+// ---------------------------------------------------------------------------
+constexpr int kMaxZEdges = 64;        // z bins + 1 supported on the device
+constexpr int kMaxNeighborBins = 32;  // neighbour bins per side per middle bin
+constexpr int kMaxZWindows = 32;      // VertexZCuts windows per event
+constexpr int kMaxCompatSeedLimit = 8;
+constexpr int kMaxHeap = 16;          // maxSeedsPerSpMConf supported
+
+enum DoubletCutKind : int { kCutsNone = 0, kCutsItk = 1, kCutsVertexZ = 2 };
+
+struct DeviceConfig {
+  // grid axes (Axis.hpp, doubles like the reference)
+  double phiMin, phiMax, phiWidth;
+  double zEdges[kMaxZEdges];
+  double rAxisMin, rAxisMax;
+  int32_t phiBins, nZ, nR, nGlobalBins;
+  // space point selector + doublet experiment cuts
+  int32_t useExtraCuts;
+  int32_t doubletCuts;  // DoubletCutKind
+  // doublet finder (DoubletSeedFinder::DerivedConfig)
+  float dRMinB, dRMaxB, dRMinT, dRMaxT;
+  float deltaZMin, deltaZMax;
+  float collisionRegionMin, collisionRegionMax;
+  float cotThetaMax, impactMax;
+  float minHelixDiameter2Doublet;
+  int32_t interactionPointCut;
+  // triplet finder (TripletSeedFinder::DerivedConfig)
+  float minHelixDiameter2, sigmapT2perRadius, multipleScattering2;
+  // filter (BroadTripletSeedFilter::Config)
+  float deltaInvHelixDiameter, filterDeltaRMin, compatSeedWeight,
+      impactWeightFactor, seedWeightIncrement, numSeedIncrement;
+  uint32_t compatSeedLimit;  // clamped to kMaxCompatSeedLimit (checked on host)
+  uint32_t maxSeedsPerSpM;
+  uint32_t maxSeedsPerSpMConf;  // heap capacity nLow
+  int32_t useDeltaRinsteadOfTopRadius;
+  // middle r range
+  int32_t useVariableMiddleSPRange;
+  float rMinMiddle, rMaxMiddle;
+  float deltaRMiddleMinSPRange, deltaRMiddleMaxSPRange;
+  int32_t nRRangeMiddleSP;  // 0 = use (rMinMiddle, rMaxMiddle)
+  float rRangeMiddleSP[2 * kMaxZEdges];
+  int32_t nZBinEdgesF;  // user zBinEdges as float (lower_bound in .cpp:415)
+  float zBinEdgesF[kMaxZEdges];
+};
+
+// ---------------------------------------------------------------------------
+// Grid lookup: SpacePointGridBase.hpp:67-87, Axis.hpp:216-235,296,497-539,598-600,
+// MultiAxisHelper.hpp:230-245.  Returns -1 when the point is outside the grid.
+// ---------------------------------------------------------------------------
+B2S_HD int32_t grid_bin_index(const DeviceConfig& c, float phiF, float zF, float rF) {
+  const double phi = (double)phiF, z = (double)zF, r = (double)rF;
+  if (!((c.phiMin <= phi) && (phi < c.phiMax))) return -1;
+  if (!((c.zEdges[0] <= z) && (z < c.zEdges[c.nZ]))) return -1;
+  if (!((c.rAxisMin <= r) && (r < c.rAxisMax))) return -1;
+  const int raw = (int)(dadd(dfloor(ddiv(dsub(phi, c.phiMin), c.phiWidth)), 1.0));
+  const int w = c.phiBins;
+  const int phiBin = 1 + (w + ((raw - 1) % w)) % w;
+  // std::upper_bound over the edges: first edge > z
+  int lo = 0, hi = c.nZ + 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (c.zEdges[mid] > z) hi = mid; else lo = mid + 1;
+  }
+  int zBin = lo;
+  if (zBin > c.nZ + 1) zBin = c.nZ + 1;
+  // r axis has the two edges {rAxisMin, rAxisMax}: inside => bin 1
+  const int rBin = 1;
+  return (phiBin * (c.nZ + 2) + zBin) * (c.nR + 2) + rBin;
+}
+
+// itkFastTrackingSPselect, GridTripletSeedingAlgorithm.cpp:46-62
+B2S_HD bool itk_sp_select(float r, float z) {
+  const float zabs = fabs_(z);
+  if ((double)zabs > 200. && (double)r < 45.) return false;
+  const float cotTheta = 27.2899f;
+  if (dsub((double)zabs, 150.) > (double)fmul(cotTheta, r)) return false;
+  return true;
+}
+
+// ---------------------------------------------------------------------------
+// Doublets: DoubletSeedFinder.cpp:41-273,359-368
+// ---------------------------------------------------------------------------
+struct MiddleSp {
+  float x, y, z, r, varZ, varR;
+  float uIP, uIP2, cosPhiM, sinPhiM;
+};
+
+B2S_HD void middle_info(MiddleSp& m) {  // :359-368
+  m.uIP = fdiv(-1.0f, m.r);
+  m.cosPhiM = fmul(-m.x, m.uIP);
+  m.sinPhiM = fmul(-m.y, m.uIP);
+  m.uIP2 = fmul(m.uIP, m.uIP);
+}
+
+B2S_HD bool outside_range(float v, float lo, float hi) { return (v < lo) | (v > hi); }
+
+// Cuts that only need (z, r) of the other space point (:104-165 for
+// interactionPointCut == false; the cotTheta cut moves after the IP cut when
+// it is true).  deltaR is assumed to be inside [deltaRMin, deltaRMax] already
+// (the r window is found by binary search).
+template <bool kBottom>
+B2S_HD bool doublet_zr_cuts(const DeviceConfig& c, const MiddleSp& m, float zO, float rO,
+                            float& deltaR, float& deltaZ) {
+  deltaR = kBottom ? fsub(m.r, rO) : fsub(rO, m.r);
+  deltaZ = kBottom ? fsub(m.z, zO) : fsub(zO, m.z);
+  if (outside_range(deltaZ, c.deltaZMin, c.deltaZMax)) return false;
+  const float zOriginTimesDeltaR = fsub(fmul(m.z, deltaR), fmul(m.r, deltaZ));
+  if (outside_range(zOriginTimesDeltaR, fmul(c.collisionRegionMin, deltaR),
+                    fmul(c.collisionRegionMax, deltaR))) {
+    return false;
+  }
+  if (!c.interactionPointCut) {
+    if (outside_range(deltaZ, fmul(-c.cotThetaMax, deltaR), fmul(c.cotThetaMax, deltaR))) {
+      return false;
+    }
+  }
+  return true;
+}
+
+struct DoubletRec {
+  float cotTheta, iDeltaR, er, u, v, xNew, yNew;
+};
+
+// Second half (:168-201 resp. :205-271): coordinate transform, optional IP /
+// curvature cut, experiment cuts, error term.
+template <bool kBottom>
+B2S_HD bool doublet_finish(const DeviceConfig& c, const MiddleSp& m, float deltaR, float deltaZ,
+                           float xO, float yO, float rO, float varZO, float varRO,
+                           const float* zWinLo, const float* zWinHi, int nZWin,
+                           DoubletRec& out) {
+  const float deltaX = fsub(xO, m.x);
+  const float deltaY = fsub(yO, m.y);
+  const float xNewFrame = fadd(fmul(deltaX, m.cosPhiM), fmul(deltaY, m.sinPhiM));
+  const float yNewFrame = fsub(fmul(deltaY, m.cosPhiM), fmul(deltaX, m.sinPhiM));
+  const float deltaR2 = fadd(fmul(deltaX, deltaX), fmul(deltaY, deltaY));
+  const float iDeltaR2 = fdiv(1.0f, deltaR2);
+  const float uT = fmul(xNewFrame, iDeltaR2);
+  const float vT = fmul(yNewFrame, iDeltaR2);
+  if (c.interactionPointCut) {
+    const float impactMax = kBottom ? -c.impactMax : c.impactMax;
+    const float vIPAbs = fmul(impactMax, m.uIP2);
+    if (fabs_(fmul(m.r, yNewFrame)) > fmul(impactMax, xNewFrame)) {
+      const float vIP = (yNewFrame > 0) ? -vIPAbs : vIPAbs;
+      const float aCoef = fdiv(fsub(vT, vIP), fsub(uT, m.uIP));
+      const float bCoef = fsub(vIP, fmul(aCoef, m.uIP));
+      if (fmul(fmul(bCoef, bCoef), c.minHelixDiameter2Doublet) >
+          fadd(1.0f, fmul(aCoef, aCoef))) {
+        return false;
+      }
+    }
+    if (outside_range(deltaZ, fmul(-c.cotThetaMax, deltaR), fmul(c.cotThetaMax, deltaR))) {
+      return false;
+    }
+  }
+  const float iDeltaR = fsqrt(iDeltaR2);
+  const float cotTheta = fmul(deltaZ, iDeltaR);
+  if (c.doubletCuts == kCutsItk) {  // itkFastTrackingCuts, .cpp:33-44
+    if (kBottom && rO < 45.0f && (cotTheta > 1.5f || cotTheta < -1.5f)) return false;
+  } else if (c.doubletCuts == kCutsVertexZ && nZWin > 0) {  // VertexZCuts, .cpp:78-96
+    const float zOrigin = fsub(m.z, fmul(m.r, cotTheta));
+    bool inside = false;
+    for (int k = 0; k < nZWin; ++k) {
+      if (zOrigin >= zWinLo[k] && zOrigin <= zWinHi[k]) { inside = true; break; }
+    }
+    if (!inside) return false;
+  }
+  // calculateError :67-71
+  out.er = fmul(iDeltaR2, fadd(fadd(m.varZ, varZO),
+                               fmul(fmul(cotTheta, cotTheta), fadd(m.varR, varRO))));
+  out.cotTheta = cotTheta;
+  out.iDeltaR = iDeltaR;
+  out.u = uT;
+  out.v = vT;
+  out.xNew = xNewFrame;
+  out.yNew = yNewFrame;
+  return true;
+}
+
+// ---------------------------------------------------------------------------
+// Triplets: TripletSeedFinder.cpp:34-162 (pixel path)
+// ---------------------------------------------------------------------------
+struct BottomCtx {
+  float cotThetaB, erB, iDeltaRB, Ub, Vb;
+  float sigmaSquaredPtDependent, scatteringInRegion2;
+};
+B2S_HD void bottom_ctx(const DeviceConfig& c, BottomCtx& b) {  // :54-65
+  const float iSinTheta2 = fadd(1.0f, fmul(b.cotThetaB, b.cotThetaB));
+  b.sigmaSquaredPtDependent = fmul(iSinTheta2, c.sigmapT2perRadius);
+  b.scatteringInRegion2 = fmul(c.multipleScattering2, iSinTheta2);
+}
+
+enum PairClass : int {
+  kPairFailA = 0,  // slope cut with the min-pT scattering term  (:96-107)
+  kPairFailB = 1,  // slope cut with the measured-pT term        (:135-143)
+  kPairSkip = 2,   // dU == 0, helix diameter or impact cut      (:109-125,148-151)
+  kPairEmit = 3    // candidate {top, curvature, impact}         (:155)
+};
+
+B2S_HD int eval_pair(const DeviceConfig& c, float rM, float varZM, float varRM,
+                     const BottomCtx& b, float cotThetaT, float erT, float iDeltaRT,
+                     float uT, float vT, float& curvature, float& impact) {
+  const float cotThetaAvg2 = fmul(b.cotThetaB, cotThetaT);
+  // erT + erB + ((2 * (cotAvg2*varRM + varZM)) * iDeltaRB) * iDeltaRT, left to right
+  const float corr = fmul(fmul(fmul(2.0f, fadd(fmul(cotThetaAvg2, varRM), varZM)), b.iDeltaRB), iDeltaRT);
+  const float error2 = fadd(fadd(erT, b.erB), corr);
+  const float deltaCotTheta = fsub(b.cotThetaB, cotThetaT);
+  const float deltaCotTheta2 = fmul(deltaCotTheta, deltaCotTheta);
+  if (deltaCotTheta2 > fadd(error2, b.scatteringInRegion2)) return kPairFailA;
+  const float dU = fsub(uT, b.Ub);
+  if (dU == 0) return kPairSkip;
+  const float A = fdiv(fsub(vT, b.Vb), dU);
+  const float S2 = fadd(1.0f, fmul(A, A));
+  const float B = fsub(b.Vb, fmul(A, b.Ub));
+  const float B2 = fmul(B, B);
+  if (S2 < fmul(B2, c.minHelixDiameter2)) return kPairSkip;
+  const float iHelixDiameter2 = fdiv(B2, S2);
+  const float p2scatterSigma = fmul(iHelixDiameter2, b.sigmaSquaredPtDependent);
+  if (deltaCotTheta2 > fadd(error2, p2scatterSigma)) return kPairFailB;
+  const float im = fabs_(fmul(fsub(A, fmul(B, rM)), rM));
+  if (im > c.impactMax) return kPairSkip;
+  curvature = fdiv(B, fsqrt(S2));
+  impact = im;
+  return kPairEmit;
+}
+
+// ---------------------------------------------------------------------------
+// Seed filter: BroadTripletSeedFilter.cpp:96-322 (seedConfirmation == false).
+// The candidates of one (middle, bottom) pair are given in curvature-sorted
+// order (curv[], topR[], impact[] indexed by sorted rank).  The weight of
+// candidate `k` only depends on the other candidates (the reference's
+// beginCompTopIndex is an exact monotone skip), so every candidate can be
+// weighted independently.
+// ---------------------------------------------------------------------------
+template <typename CurvAt, typename TopRAt>
+B2S_HD float filter_weight(const DeviceConfig& c, int n, int k, float impact, CurvAt curvAt,
+                           TopRAt topRAt) {
+  const float invHelixDiameter = curvAt(k);
+  const float lowerLimitCurv = fsub(invHelixDiameter, c.deltaInvHelixDiameter);
+  const float upperLimitCurv = fadd(invHelixDiameter, c.deltaInvHelixDiameter);
+  const float currentTopR = topRAt(k);
+  float weight = fmul(-impact, c.impactWeightFactor);
+  float compatR[kMaxCompatSeedLimit];
+  uint32_t nCompat = 0;
+  for (int o = 0; o < n; ++o) {
+    if (o == k) continue;
+    const float curvO = curvAt(o);
+    if (curvO < lowerLimitCurv) continue;
+    if (curvO > upperLimitCurv) break;
+    const float otherTopR = topRAt(o);
+    const float deltaR = fsub(currentTopR, otherTopR);
+    if (fabs_(deltaR) < c.filterDeltaRMin) continue;
+    bool newCompSeed = true;
+    for (uint32_t q = 0; q < nCompat; ++q) {
+      if (fabs_(fsub(compatR[q], otherTopR)) < c.filterDeltaRMin) {
+        newCompSeed = false;
+        break;
+      }
+    }
+    if (newCompSeed) {
+      if (nCompat < (uint32_t)kMaxCompatSeedLimit) compatR[nCompat] = otherTopR;
+      ++nCompat;
+      weight = fadd(weight, c.compatSeedWeight);
+    }
+    if (nCompat >= c.compatSeedLimit) break;
+  }
+  if ((float)nCompat > c.numSeedIncrement) {
+    weight = fadd(weight, c.seedWeightIncrement);
+  }
+  return weight;
+}
+
+// ---------------------------------------------------------------------------
+// libstdc++ (GCC 13, bits/stl_heap.h) binary-heap primitives, restated so that
+// the bounded candidate heap of CandidatesForMiddleSp.cpp:44-93 behaves
+// identically on ties.  `comp(a, b)` is the std comparator (a.first > b.first
+// for the reference's min-heap on weight).
+// ---------------------------------------------------------------------------
+struct WeightIndex {
+  float weight;
+  uint32_t index;
+};
+B2S_HD bool heap_comp(const WeightIndex& a, const WeightIndex& b) { return a.weight > b.weight; }
+
+template <typename T, typename Comp>
+B2S_HD void std_push_heap_impl(T* first, int holeIndex, int topIndex, T value, Comp comp) {
+  int parent = (holeIndex - 1) / 2;
+  while (holeIndex > topIndex && comp(first[parent], value)) {
+    first[holeIndex] = first[parent];
+    holeIndex = parent;
+    parent = (holeIndex - 1) / 2;
+  }
+  first[holeIndex] = value;
+}
+template <typename T, typename Comp>
+B2S_HD void std_adjust_heap(T* first, int holeIndex, int len, T value, Comp comp) {
+  const int topIndex = holeIndex;
+  int secondChild = holeIndex;
+  while (secondChild < (len - 1) / 2) {
+    secondChild = 2 * (secondChild + 1);
+    if (comp(first[secondChild], first[secondChild - 1])) secondChild--;
+    first[holeIndex] = first[secondChild];
+    holeIndex = secondChild;
+  }
+  if ((len & 1) == 0 && secondChild == (len - 2) / 2) {
+    secondChild = 2 * (secondChild + 1);
+    first[holeIndex] = first[secondChild - 1];
+    holeIndex = secondChild - 1;
+  }
+  std_push_heap_impl(first, holeIndex, topIndex, value, comp);
+}
+// std::push_heap(first, first + n): the new element is first[n-1]
+template <typename T, typename Comp>
+B2S_HD void std_push_heap(T* first, int n, Comp comp) {
+  std_push_heap_impl(first, n - 1, 0, first[n - 1], comp);
+}
+// std::pop_heap(first, first + n): moves the top to first[n-1]
+template <typename T, typename Comp>
+B2S_HD void std_pop_heap(T* first, int n, Comp comp) {
+  if (n > 1) {
+    const T value = first[n - 1];
+    first[n - 1] = first[0];
+    std_adjust_heap(first, 0, n - 1, value, comp);
+  }
+}
+template <typename T, typename Comp>
+B2S_HD void std_sort_heap(T* first, int n, Comp comp) {
+  while (n > 1) {
+    std_pop_heap(first, n, comp);
+    --n;
+  }
+}
+template <typename T, typename Comp>
+B2S_HD void std_make_heap(T* first, int len, Comp comp) {
+  if (len < 2) return;
+  int parent = (len - 2) / 2;
+  while (true) {
+    const T value = first[parent];
+    std_adjust_heap(first, parent, len, value, comp);
+    if (parent == 0) return;
+    parent--;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// libstdc++ std::sort (GCC 13 bits/stl_algo.h: introsort with median-of-3,
+// depth limit 2*floor(log2 n), heap-sort fallback, final insertion sort with
+// threshold 16) restated with an explicit stack.  Used wherever the reference
+// calls the UNSTABLE std::ranges::sort and the keys contain ties, so that tie
+// order -- and with it window / heap decisions -- match the reference
+// (GridTripletSeedingAlgorithm.cpp:224, DoubletSeedFinder.hpp:101,
+// BroadTripletSeedFilter.cpp:145).  `less(a, b)` compares two elements.
+// ---------------------------------------------------------------------------
+template <typename T, typename Less>
+B2S_HD void std_unguarded_linear_insert(T* a, int last, Less less) {
+  const T val = a[last];
+  int next = last - 1;
+  while (less(val, a[next])) {
+    a[last] = a[next];
+    last = next;
+    --next;
+  }
+  a[last] = val;
+}
+template <typename T, typename Less>
+B2S_HD void std_insertion_sort(T* a, int first, int last, Less less) {
+  if (first == last) return;
+  for (int i = first + 1; i != last; ++i) {
+    if (less(a[i], a[first])) {
+      const T val = a[i];
+      for (int k = i; k > first; --k) a[k] = a[k - 1];
+      a[first] = val;
+    } else {
+      std_unguarded_linear_insert(a, i, less);
+    }
+  }
+}
+template <typename T, typename Less>
+B2S_HD void std_sort(T* a, int n, Less less) {
+  if (n <= 0) return;
+  constexpr int kThreshold = 16;
+  int lg = 0;
+  for (unsigned v = (unsigned)n; v > 1; v >>= 1) ++lg;
+  // explicit stack of (first, last, depth); sub-ranges are disjoint so the
+  // processing order does not change the result
+  int stackFirst[64], stackLast[64], stackDepth[64];
+  int sp = 0;
+  stackFirst[0] = 0; stackLast[0] = n; stackDepth[0] = 2 * lg; sp = 1;
+  while (sp > 0) {
+    --sp;
+    int first = stackFirst[sp], last = stackLast[sp], depth = stackDepth[sp];
+    while (last - first > kThreshold) {
+      if (depth == 0) {
+        // std::__partial_sort(first, last, last): make_heap + sort_heap
+        std_make_heap(a + first, last - first, less);
+        std_sort_heap(a + first, last - first, less);
+        break;
+      }
+      --depth;
+      // __unguarded_partition_pivot
+      const int mid = first + (last - first) / 2;
+      {  // __move_median_to_first(first, first + 1, mid, last - 1)
+        const int ia = first + 1, ib = mid, ic = last - 1;
+        int pick;
+        if (less(a[ia], a[ib])) {
+          if (less(a[ib], a[ic])) pick = ib;
+          else if (less(a[ia], a[ic])) pick = ic;
+          else pick = ia;
+        } else if (less(a[ia], a[ic])) pick = ia;
+        else if (less(a[ib], a[ic])) pick = ic;
+        else pick = ib;
+        const T t = a[first]; a[first] = a[pick]; a[pick] = t;
+      }
+      int lo = first + 1, hi = last;
+      while (true) {  // __unguarded_partition(first + 1, last, pivot = first)
+        while (less(a[lo], a[first])) ++lo;
+        --hi;
+        while (less(a[first], a[hi])) --hi;
+        if (!(lo < hi)) break;
+        const T t = a[lo]; a[lo] = a[hi]; a[hi] = t;
+        ++lo;
+      }
+      const int cut = lo;
+      // recurse on [cut, last), loop on [first, cut)
+      stackFirst[sp] = cut; stackLast[sp] = last; stackDepth[sp] = depth; ++sp;
+      last = cut;
+    }
+  }
+  // __final_insertion_sort
+  if (n > kThreshold) {
+    std_insertion_sort(a, 0, kThreshold, less);
+    for (int i = kThreshold; i != n; ++i) std_unguarded_linear_insert(a, i, less);
+  } else {
+    std_insertion_sort(a, 0, n, less);
+  }
+}
+
+// Monotone (non-decreasing in the key) bucket of a cot(theta) key for the
+// in-block bucket sort.  Keys are expected inside [-cotThetaMax, cotThetaMax]
+// but any value is clamped.
+B2S_HD int cot_bucket(float cot, float cotMax, float scale, int nBuckets) {
+  float t = fmul(fadd(cot, cotMax), scale);
+  if (!(t > 0.0f)) t = 0.0f;
+  int b = (int)t;
+  if (b >= nBuckets) b = nBuckets - 1;
+  return b;
+}
+
+}  // namespace b200seed

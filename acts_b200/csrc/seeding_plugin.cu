@@ -1,0 +1,650 @@
+// seeding_plugin.cu -- C ABI of the B200 seeding plugin (include/acts_b200_seeding.h).
+//
+// Host side: validates the configuration (host_plan.cpp), owns the device
+// workspaces and enqueues the kernel sequence of seeding_kernels.cuh on one
+// stream.  There is no CPU implementation of any stage in this library: without
+// a CUDA device every computing entry point fails with B200SEED_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/acts_b200_seeding.h"
+#include "host_plan.hpp"
+#include "seeding_kernels.cuh"
+
+using namespace b200seed;
+
+namespace {
+
+thread_local std::string g_lastError;
+
+int fail(int code, const std::string& msg) {
+  g_lastError = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t err__ = (expr);                                                          \
+    if (err__ != cudaSuccess) {                                                          \
+      return fail(B200SEED_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__)); \
+    }                                                                                    \
+  } while (0)
+
+struct DevBuf {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (ptr != nullptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+    const size_t want = need + need / 4 + 256;
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e == cudaSuccess) bytes = want;
+    return e;
+  }
+  void release() {
+    if (ptr != nullptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+  template <typename T>
+  T* as() const { return static_cast<T*>(ptr); }
+};
+
+uint32_t env_u32(const char* name, uint32_t def) {
+  const char* v = std::getenv(name);
+  if (v == nullptr || *v == 0) return def;
+  return static_cast<uint32_t>(std::strtoul(v, nullptr, 10));
+}
+
+}  // namespace
+
+struct b200seed_handle {
+  HostPlan plan;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int smCount = 0, ccMajor = 0, ccMinor = 0;
+  // engine tunables
+  uint32_t capB = 2048, capT = 1024, capPool = 1024, nBuckets = 2048;
+  uint32_t sortSmemCap = 4096;
+  int exactTies = 1;
+  int seedBlocksPerSM = 1;
+  size_t seedSmemBytes = 0;
+  // constant tables
+  DevBuf navBins, botOffsets, botBins, topOffsets, topBins;
+  // per-batch workspaces
+  DevBuf inOffsets, inX, inY, inZ, inR, inVarZ, inVarR;  // staging of host inputs
+  DevBuf binOf, binCount, binStart, binCursor, tmpIdx, pIdx, pXY, pZR, pVar, sortScratch;
+  DevBuf midLo, midCount, workStart, workPos, workEG, workCounter;
+  DevBuf slotB, slotM, slotT, slotQ, slotZ, slotCount, seedStart, tileSums, tilePrefix;
+  DevBuf outB, outM, outT, outQ, outZ, seedOffsets;  // device outputs of the host API
+  DevBuf counters, status, zWin;
+  // pinned host mirrors
+  unsigned long long* hCounters = nullptr;  // [kCntSlots]
+  int* hStatus = nullptr;
+  unsigned long long* hSeedTotal = nullptr;
+  // state of the last call
+  uint32_t lastEvents = 0, lastTotal = 0;
+  unsigned long long lastCapacity = 0;
+  const unsigned long long* lastSeedOffsets = nullptr;
+  b200seed_counters lastCounters{};
+  bool pending = false;
+  uint64_t launches = 0;
+};
+
+namespace {
+
+int upload(DevBuf& buf, const std::vector<uint32_t>& v, cudaStream_t s) {
+  CUDA_TRY(buf.reserve(std::max<size_t>(4, v.size() * 4)));
+  if (!v.empty()) CUDA_TRY(cudaMemcpyAsync(buf.ptr, v.data(), v.size() * 4, cudaMemcpyHostToDevice, s));
+  return B200SEED_OK;
+}
+
+int ensure_workspace(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal) {
+  const size_t nBinsAll = (size_t)nEvents * (size_t)h->plan.dev.nGlobalBins;
+  const size_t nNavAll = (size_t)nEvents * h->plan.navBins.size();
+  const size_t nT = std::max<size_t>(nTotal, 1);
+  const size_t K = std::max<uint32_t>(h->plan.seedsPerMiddle, 1);
+  CUDA_TRY(h->binOf.reserve(nT * 4));
+  CUDA_TRY(h->binCount.reserve((nBinsAll + 1) * 4));
+  CUDA_TRY(h->binStart.reserve((nBinsAll + 1) * 4));
+  CUDA_TRY(h->binCursor.reserve((nBinsAll + 1) * 4));
+  CUDA_TRY(h->tmpIdx.reserve(nT * 4));
+  CUDA_TRY(h->pIdx.reserve(nT * 4));
+  CUDA_TRY(h->pXY.reserve(nT * 8));
+  CUDA_TRY(h->pZR.reserve(nT * 8));
+  CUDA_TRY(h->pVar.reserve(nT * 8));
+  CUDA_TRY(h->sortScratch.reserve(nT * 16));
+  CUDA_TRY(h->midLo.reserve((nNavAll + 1) * 4));
+  CUDA_TRY(h->midCount.reserve((nNavAll + 1) * 4));
+  CUDA_TRY(h->workStart.reserve((nNavAll + 1) * 4));
+  CUDA_TRY(h->workPos.reserve(nT * 4));
+  CUDA_TRY(h->workEG.reserve(nT * 4));
+  CUDA_TRY(h->workCounter.reserve(16));
+  CUDA_TRY(h->slotB.reserve(nT * K * 4));
+  CUDA_TRY(h->slotM.reserve(nT * K * 4));
+  CUDA_TRY(h->slotT.reserve(nT * K * 4));
+  CUDA_TRY(h->slotQ.reserve(nT * K * 4));
+  CUDA_TRY(h->slotZ.reserve(nT * K * 4));
+  CUDA_TRY(h->slotCount.reserve(nT * 4));
+  CUDA_TRY(h->seedStart.reserve((nT + 1) * 4));
+  const size_t nTiles = (nT + kTile - 1) / kTile;
+  CUDA_TRY(h->tileSums.reserve((nTiles + 1) * 4));
+  CUDA_TRY(h->tilePrefix.reserve((nTiles + 1) * 4));
+  CUDA_TRY(h->counters.reserve(kCntSlots * 8));
+  CUDA_TRY(h->status.reserve(16));
+  CUDA_TRY(h->zWin.reserve(2 * kMaxZWindows * 4));
+  return B200SEED_OK;
+}
+
+// Enqueue the whole pipeline for a batch whose inputs already live on the device.
+int enqueue(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal, const uint32_t* dOffsets,
+            const float* x, const float* y, const float* z, const float* r, const float* varZ,
+            const float* varR, const float* dPhi, int nZWin, uint32_t* outB, uint32_t* outM,
+            uint32_t* outT, float* outQ, float* outZ, unsigned long long outCapacity,
+            unsigned long long* dSeedOffsets, cudaStream_t s) {
+  int rc = ensure_workspace(h, nEvents, nTotal);
+  if (rc != B200SEED_OK) return rc;
+  const HostPlan& plan = h->plan;
+  const uint32_t nBins = (uint32_t)plan.dev.nGlobalBins;
+  const uint32_t nNav = (uint32_t)plan.navBins.size();
+  const uint32_t nBinsAll = nEvents * nBins, nNavAll = nEvents * nNav;
+  uint64_t launches = 0;
+
+  CUDA_TRY(cudaMemsetAsync(h->binCount.ptr, 0, ((size_t)nBinsAll + 1) * 4, s));
+  CUDA_TRY(cudaMemsetAsync(h->binCursor.ptr, 0, ((size_t)nBinsAll + 1) * 4, s));
+  CUDA_TRY(cudaMemsetAsync(h->workCounter.ptr, 0, 16, s));
+  CUDA_TRY(cudaMemsetAsync(h->counters.ptr, 0, kCntSlots * 8, s));
+  CUDA_TRY(cudaMemsetAsync(h->status.ptr, 0, 16, s));
+
+  GridParams gp{};
+  gp.cfg = plan.dev;
+  gp.nEvents = nEvents; gp.nTotal = nTotal; gp.nBins = nBins;
+  gp.spOffsets = dOffsets;
+  gp.x = x; gp.y = y; gp.z = z; gp.r = r; gp.varZ = varZ; gp.varR = varR;
+  gp.phi = dPhi;
+  gp.binOf = h->binOf.as<uint32_t>();
+  gp.binCount = h->binCount.as<uint32_t>();
+  gp.binStart = h->binStart.as<uint32_t>();
+  gp.binCursor = h->binCursor.as<uint32_t>();
+  gp.tmpIdx = h->tmpIdx.as<uint32_t>();
+  gp.pIdx = h->pIdx.as<uint32_t>();
+  gp.pXY = h->pXY.as<float2>();
+  gp.pZR = h->pZR.as<float2>();
+  gp.pVar = h->pVar.as<float2>();
+  gp.sortScratch = h->sortScratch.as<unsigned long long>();
+  gp.sortSmemCap = h->sortSmemCap;
+  gp.exactTies = h->exactTies;
+  gp.status = h->status.as<int>();
+  gp.counters = h->counters.as<unsigned long long>();
+
+  const int elemBlocks = std::max(1, std::min<int>((int)((nTotal + 255) / 256), h->smCount * 8));
+  if (nTotal > 0) {
+    k_bin_count<<<elemBlocks, 256, 0, s>>>(gp);
+    ++launches;
+  }
+  k_scan<<<1, kScanThreads, 0, s>>>(gp.binCount, gp.binStart, nBinsAll);
+  ++launches;
+  if (nTotal > 0) {
+    k_scatter<<<elemBlocks, 256, 0, s>>>(gp);
+    k_sort_bins<<<nBinsAll, kSortThreads, (size_t)h->sortSmemCap * 8, s>>>(gp);
+    launches += 2;
+  }
+
+  WorkParams wp{};
+  wp.cfg = plan.dev;
+  wp.nEvents = nEvents; wp.nBins = nBins; wp.nNav = nNav;
+  wp.binStart = gp.binStart;
+  wp.pZR = gp.pZR;
+  wp.navBins = h->navBins.as<uint32_t>();
+  wp.midLo = h->midLo.as<uint32_t>();
+  wp.midCount = h->midCount.as<uint32_t>();
+  wp.workStart = h->workStart.as<uint32_t>();
+  wp.workPos = h->workPos.as<uint32_t>();
+  wp.workEG = h->workEG.as<uint32_t>();
+  k_middle_ranges<<<nEvents, 256, 0, s>>>(wp);
+  k_scan<<<1, kScanThreads, 0, s>>>(wp.midCount, wp.workStart, nNavAll);
+  k_fill_work<<<(nNavAll * 32 + 255) / 256, 256, 0, s>>>(wp);
+  launches += 3;
+
+  SeedParams sp{};
+  sp.cfg = plan.dev;
+  if (nZWin > 0) sp.cfg.doubletCuts = kCutsVertexZ;  // takes the experimentCuts slot, .cpp:291-296
+  sp.pXY = gp.pXY; sp.pZR = gp.pZR; sp.pVar = gp.pVar;
+  sp.binStart = gp.binStart;
+  sp.navBins = h->navBins.as<uint32_t>();
+  sp.botOffsets = h->botOffsets.as<uint32_t>();
+  sp.botBins = h->botBins.as<uint32_t>();
+  sp.topOffsets = h->topOffsets.as<uint32_t>();
+  sp.topBins = h->topBins.as<uint32_t>();
+  sp.workPos = wp.workPos; sp.workEG = wp.workEG;
+  sp.nWorkPtr = wp.workStart + nNavAll;
+  sp.nNav = nNav; sp.nBins = nBins;
+  sp.zWinLo = h->zWin.as<float>();
+  sp.zWinHi = h->zWin.as<float>() + kMaxZWindows;
+  sp.nZWin = nZWin;
+  sp.workCounter = h->workCounter.as<uint32_t>();
+  sp.slotB = h->slotB.as<uint32_t>(); sp.slotM = h->slotM.as<uint32_t>(); sp.slotT = h->slotT.as<uint32_t>();
+  sp.slotQ = h->slotQ.as<float>(); sp.slotZ = h->slotZ.as<float>();
+  sp.slotCount = h->slotCount.as<uint32_t>();
+  sp.seedsPerMiddle = std::max<uint32_t>(plan.seedsPerMiddle, 1);
+  sp.capB = h->capB; sp.capT = h->capT; sp.capPool = h->capPool; sp.nBuckets = h->nBuckets;
+  sp.counters = gp.counters;
+  sp.status = gp.status;
+  k_seed_middles<<<h->smCount * h->seedBlocksPerSM, kSeedThreads, h->seedSmemBytes, s>>>(sp);
+  ++launches;
+
+  CompactParams cp{};
+  cp.nWorkPtr = sp.nWorkPtr;
+  cp.slotCount = sp.slotCount;
+  cp.tileSums = h->tileSums.as<uint32_t>();
+  cp.tilePrefix = h->tilePrefix.as<uint32_t>();
+  cp.slotB = sp.slotB; cp.slotM = sp.slotM; cp.slotT = sp.slotT; cp.slotQ = sp.slotQ; cp.slotZ = sp.slotZ;
+  cp.seedsPerMiddle = sp.seedsPerMiddle;
+  cp.pIdx = gp.pIdx;
+  cp.outB = outB; cp.outM = outM; cp.outT = outT; cp.outQ = outQ; cp.outZ = outZ;
+  cp.outCapacity = outCapacity;
+  cp.seedOffsets = dSeedOffsets;
+  cp.workStart = wp.workStart;
+  cp.seedStart = h->seedStart.as<uint32_t>();
+  cp.nEvents = nEvents; cp.nNav = nNav;
+  cp.counters = gp.counters;
+  const uint32_t nTiles = std::max<uint32_t>(1, (nTotal + kTile - 1) / kTile);
+  k_tile_sums<<<nTiles, 256, 0, s>>>(cp);
+  k_scan<<<1, kScanThreads, 0, s>>>(cp.tileSums, cp.tilePrefix, nTiles);
+  k_compact_seeds<<<nTiles, 256, 0, s>>>(cp);
+  k_event_offsets<<<1, 256, 0, s>>>(cp);
+  launches += 4;
+  CUDA_TRY(cudaGetLastError());
+
+  // results the host needs after the sync
+  CUDA_TRY(cudaMemcpyAsync(h->hCounters, h->counters.ptr, kCntSlots * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h->hStatus, h->status.ptr, 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h->hSeedTotal, dSeedOffsets + nEvents, 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h->hCounters + kCntSlots, h->binStart.as<uint32_t>() + nBinsAll, 4, cudaMemcpyDeviceToHost, s));
+  h->lastEvents = nEvents;
+  h->lastTotal = nTotal;
+  h->lastCapacity = outCapacity;
+  h->launches = launches;
+  h->pending = true;
+  return B200SEED_OK;
+}
+
+int finish(b200seed_handle* h, cudaStream_t s, b200seed_seeds* out) {
+  CUDA_TRY(cudaStreamSynchronize(s));
+  h->pending = false;
+  b200seed_counters& c = h->lastCounters;
+  c.nSpacePoints = h->lastTotal;
+  c.nInGrid = *reinterpret_cast<uint32_t*>(h->hCounters + kCntSlots);
+  c.nMiddles = h->hCounters[kCntMiddles];
+  c.nBottomDoublets = h->hCounters[kCntBottomDoublets];
+  c.nTopDoublets = h->hCounters[kCntTopDoublets];
+  c.nTripletTests = h->hCounters[kCntTripletTests];
+  c.nCandidates = h->hCounters[kCntCandidates];
+  c.nSeeds = *h->hSeedTotal;
+  c.nTieMiddles = h->hCounters[kCntTieMiddles];
+  c.nKernelLaunches = h->launches;
+  if (out != nullptr) out->size = *h->hSeedTotal;
+  const int st = *h->hStatus;
+  if (st & (kStatusOverflowDoublets | kStatusOverflowPool)) {
+    return fail(B200SEED_ERR_OVERFLOW,
+                "per-middle scratch exhausted (doublets > " + std::to_string(h->capB) + "/" +
+                    std::to_string(h->capT) + " or candidates > " + std::to_string(h->capPool) +
+                    "); raise B200SEED_CAPB / B200SEED_CAPT / B200SEED_CAPPOOL");
+  }
+  if (*h->hSeedTotal > h->lastCapacity) {
+    return fail(B200SEED_ERR_CAPACITY, "seed buffers too small: need " + std::to_string(*h->hSeedTotal));
+  }
+  return B200SEED_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200seed_last_error(void) { return g_lastError.c_str(); }
+
+int b200seed_config_init(b200seed_config* cfg) {
+  if (cfg == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "cfg is NULL");
+  config_defaults(*cfg);
+  return B200SEED_OK;
+}
+
+// Host-only planning, usable without a GPU (validation + derived constants).
+int b200seed_plan_info(const b200seed_config* cfg, b200seed_info* info) {
+  if (cfg == nullptr || info == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL argument");
+  HostPlan plan;
+  PlanError err;
+  if (!make_host_plan(*cfg, plan, err)) return fail(err.code, err.message);
+  *info = plan.info;
+  return B200SEED_OK;
+}
+
+// Host-only: device constants + navigation / neighbour tables of a config
+// (used by the GPU-less model tests).  Arrays may be NULL to query the sizes:
+// sizes[0] = nNav, sizes[1] = #bottom bins, sizes[2] = #top bins,
+// sizes[3] = sizeof(DeviceConfig), sizes[4] = seeds per middle.
+int b200seed_plan_tables(const b200seed_config* cfg, void* deviceConfig, uint64_t deviceConfigBytes,
+                         uint32_t* navBins, uint32_t* botOffsets, uint32_t* botBins,
+                         uint32_t* topOffsets, uint32_t* topBins, uint64_t* sizes) {
+  if (cfg == nullptr || sizes == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL argument");
+  HostPlan plan;
+  PlanError err;
+  if (!make_host_plan(*cfg, plan, err)) return fail(err.code, err.message);
+  sizes[0] = plan.navBins.size();
+  sizes[1] = plan.botBins.size();
+  sizes[2] = plan.topBins.size();
+  sizes[3] = sizeof(DeviceConfig);
+  sizes[4] = plan.seedsPerMiddle;
+  if (deviceConfig != nullptr) {
+    if (deviceConfigBytes != sizeof(DeviceConfig)) return fail(B200SEED_ERR_INVALID_ARGUMENT, "DeviceConfig size mismatch");
+    std::memcpy(deviceConfig, &plan.dev, sizeof(DeviceConfig));
+  }
+  auto copy = [](uint32_t* dst, const std::vector<uint32_t>& v) {
+    if (dst != nullptr && !v.empty()) std::memcpy(dst, v.data(), v.size() * 4);
+  };
+  copy(navBins, plan.navBins);
+  copy(botOffsets, plan.botOffsets);
+  copy(botBins, plan.botBins);
+  copy(topOffsets, plan.topOffsets);
+  copy(topBins, plan.topBins);
+  return B200SEED_OK;
+}
+
+int b200seed_create(const b200seed_config* cfg, int device, b200seed_handle** out) {
+  if (cfg == nullptr || out == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL argument");
+  *out = nullptr;
+  auto* h = new b200seed_handle;
+  PlanError err;
+  if (!make_host_plan(*cfg, h->plan, err)) {
+    delete h;
+    return fail(err.code, err.message);
+  }
+  if (h->plan.relaxedFloat) {
+    delete h;
+    return fail(B200SEED_ERR_UNSUPPORTED, "relaxedFloat fast path is not built yet; only the exact binary32 path exists");
+  }
+  int nDev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&nDev);
+  if (ce != cudaSuccess || nDev <= 0) {
+    delete h;
+    return fail(B200SEED_ERR_CUDA, std::string("no CUDA device available: ") + cudaGetErrorString(ce));
+  }
+  if (device < 0 || device >= nDev) {
+    delete h;
+    return fail(B200SEED_ERR_INVALID_ARGUMENT, "device index out of range");
+  }
+  h->device = device;
+  auto cleanup = [&](int code) {
+    b200seed_destroy(h);
+    return code;
+  };
+#define CREATE_TRY(expr)                                                                       \
+  do {                                                                                         \
+    cudaError_t err__ = (expr);                                                                \
+    if (err__ != cudaSuccess) {                                                                \
+      return cleanup(fail(B200SEED_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__))); \
+    }                                                                                          \
+  } while (0)
+  CREATE_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop{};
+  CREATE_TRY(cudaGetDeviceProperties(&prop, device));
+  h->smCount = prop.multiProcessorCount;
+  h->ccMajor = prop.major;
+  h->ccMinor = prop.minor;
+  h->plan.info.smCount = h->smCount;
+  h->plan.info.ccMajor = h->ccMajor;
+  h->plan.info.ccMinor = h->ccMinor;
+  CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CREATE_TRY(cudaMallocHost(&h->hCounters, (kCntSlots + 2) * 8));
+  CREATE_TRY(cudaMallocHost(&h->hStatus, 16));
+  CREATE_TRY(cudaMallocHost(&h->hSeedTotal, 16));
+
+  h->capB = env_u32("B200SEED_CAPB", h->capB);
+  h->capT = env_u32("B200SEED_CAPT", h->capT);
+  h->capPool = env_u32("B200SEED_CAPPOOL", h->capPool);
+  h->nBuckets = env_u32("B200SEED_BUCKETS", h->nBuckets);
+  h->exactTies = (int)env_u32("B200SEED_EXACT_TIES", 1);
+  if (h->capB > 65535 || h->capT > 65535 || h->capPool > 65534) {
+    return cleanup(fail(B200SEED_ERR_INVALID_ARGUMENT, "B200SEED_CAP* must stay below 65535"));
+  }
+  h->seedSmemBytes = seed_smem_bytes(h->capB, h->capT, h->capPool, h->nBuckets);
+  if (h->seedSmemBytes > (size_t)prop.sharedMemPerBlockOptin) {
+    return cleanup(fail(B200SEED_ERR_INVALID_ARGUMENT, "per-middle scratch does not fit shared memory"));
+  }
+  CREATE_TRY(cudaFuncSetAttribute(k_seed_middles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seedSmemBytes));
+  CREATE_TRY(cudaFuncSetAttribute(k_sort_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->sortSmemCap * 8)));
+  int blocksPerSM = 0;
+  CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_seed_middles, kSeedThreads, h->seedSmemBytes));
+  h->seedBlocksPerSM = std::max(1, blocksPerSM);
+
+  int rc = upload(h->navBins, h->plan.navBins, h->stream);
+  if (rc == B200SEED_OK) rc = upload(h->botOffsets, h->plan.botOffsets, h->stream);
+  if (rc == B200SEED_OK) rc = upload(h->botBins, h->plan.botBins, h->stream);
+  if (rc == B200SEED_OK) rc = upload(h->topOffsets, h->plan.topOffsets, h->stream);
+  if (rc == B200SEED_OK) rc = upload(h->topBins, h->plan.topBins, h->stream);
+  if (rc != B200SEED_OK) return cleanup(rc);
+  CREATE_TRY(cudaStreamSynchronize(h->stream));
+#undef CREATE_TRY
+  *out = h;
+  return B200SEED_OK;
+}
+
+void b200seed_destroy(b200seed_handle* h) {
+  if (h == nullptr) return;
+  cudaSetDevice(h->device);
+  if (h->stream != nullptr) {
+    cudaStreamSynchronize(h->stream);
+    cudaStreamDestroy(h->stream);
+  }
+  for (DevBuf* b : {&h->navBins, &h->botOffsets, &h->botBins, &h->topOffsets, &h->topBins, &h->inOffsets,
+                    &h->inX, &h->inY, &h->inZ, &h->inR, &h->inVarZ, &h->inVarR, &h->binOf, &h->binCount,
+                    &h->binStart, &h->binCursor, &h->tmpIdx, &h->pIdx, &h->pXY, &h->pZR, &h->pVar,
+                    &h->sortScratch, &h->midLo, &h->midCount, &h->workStart, &h->workPos, &h->workEG,
+                    &h->workCounter, &h->slotB, &h->slotM, &h->slotT, &h->slotQ, &h->slotZ, &h->slotCount,
+                    &h->seedStart, &h->tileSums, &h->tilePrefix, &h->outB, &h->outM, &h->outT, &h->outQ,
+                    &h->outZ, &h->seedOffsets, &h->counters, &h->status, &h->zWin}) {
+    b->release();
+  }
+  if (h->hCounters != nullptr) cudaFreeHost(h->hCounters);
+  if (h->hStatus != nullptr) cudaFreeHost(h->hStatus);
+  if (h->hSeedTotal != nullptr) cudaFreeHost(h->hSeedTotal);
+  delete h;
+}
+
+int b200seed_get_info(const b200seed_handle* h, b200seed_info* info) {
+  if (h == nullptr || info == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL argument");
+  *info = h->plan.info;
+  return B200SEED_OK;
+}
+
+int b200seed_get_counters(const b200seed_handle* h, b200seed_counters* c) {
+  if (h == nullptr || c == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL argument");
+  *c = h->lastCounters;
+  return B200SEED_OK;
+}
+
+int b200seed_run_batch_device(b200seed_handle* h, uint32_t nEvents, uint32_t nSpacePointsTotal,
+                              const uint32_t* spOffsets, const float* x, const float* y, const float* z,
+                              const float* r, const float* varZ, const float* varR, uint64_t* seedOffsets,
+                              b200seed_seeds* out, void* cudaStream) {
+  if (h == nullptr || out == nullptr || spOffsets == nullptr || seedOffsets == nullptr || nEvents == 0) {
+    return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL argument or empty batch");
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = cudaStream != nullptr ? static_cast<cudaStream_t>(cudaStream) : h->stream;
+  h->lastSeedOffsets = reinterpret_cast<const unsigned long long*>(seedOffsets);
+  return enqueue(h, nEvents, nSpacePointsTotal, spOffsets, x, y, z, r, varZ, varR, nullptr, 0,
+                 out->bottom, out->middle, out->top, out->quality, out->vertexZ, out->capacity,
+                 reinterpret_cast<unsigned long long*>(seedOffsets), s);
+}
+
+int b200seed_sync(b200seed_handle* h, b200seed_seeds* out) {
+  if (h == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  // the stream of the last call is ordered with the handle's stream through
+  // the device-wide synchronisation below (the caller may have used its own)
+  CUDA_TRY(cudaDeviceSynchronize());
+  return finish(h, h->stream, out);
+}
+
+static int run_host_batch(b200seed_handle* h, uint32_t nEvents, const uint32_t* spOffsets, const float* x,
+                          const float* y, const float* z, const float* r, const float* varZ,
+                          const float* varR, const float* phi, uint32_t nZWin, const float* zLo,
+                          const float* zHi, uint64_t* seedOffsets, b200seed_seeds* out) {
+  if (h == nullptr || out == nullptr || spOffsets == nullptr || nEvents == 0) {
+    return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL argument or empty batch");
+  }
+  if (nZWin > (uint32_t)kMaxZWindows) {
+    return fail(B200SEED_ERR_UNSUPPORTED, "more than " + std::to_string(kMaxZWindows) + " vertex z windows");
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const uint32_t nTotal = spOffsets[nEvents] - spOffsets[0];
+  if (spOffsets[0] != 0) return fail(B200SEED_ERR_INVALID_ARGUMENT, "spOffsets[0] must be 0");
+  const size_t colBytes = std::max<size_t>(4, (size_t)nTotal * 4);
+  CUDA_TRY(h->inOffsets.reserve(((size_t)nEvents + 1) * 4));
+  DevBuf* cols[6] = {&h->inX, &h->inY, &h->inZ, &h->inR, &h->inVarZ, &h->inVarR};
+  const float* src[6] = {x, y, z, r, varZ, varR};
+  for (int i = 0; i < 6; ++i) {
+    CUDA_TRY(cols[i]->reserve(colBytes));
+    if (nTotal > 0) {
+      if (src[i] == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL space point column");
+      CUDA_TRY(cudaMemcpyAsync(cols[i]->ptr, src[i], (size_t)nTotal * 4, cudaMemcpyHostToDevice, s));
+    }
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->inOffsets.ptr, spOffsets, ((size_t)nEvents + 1) * 4, cudaMemcpyHostToDevice, s));
+  float* dPhi = nullptr;
+  if (phi != nullptr && nTotal > 0) {
+    CUDA_TRY(h->binOf.reserve(colBytes));  // make sure workspaces exist before aliasing
+    CUDA_TRY(h->tmpIdx.reserve(colBytes));
+    // phi staging shares no workspace with the pipeline: use sortScratch's tail
+    CUDA_TRY(h->sortScratch.reserve((size_t)nTotal * 16 + colBytes));
+    dPhi = reinterpret_cast<float*>(h->sortScratch.as<unsigned char>() + (size_t)nTotal * 16);
+    CUDA_TRY(cudaMemcpyAsync(dPhi, phi, (size_t)nTotal * 4, cudaMemcpyHostToDevice, s));
+  }
+  int rc = ensure_workspace(h, nEvents, nTotal);
+  if (rc != B200SEED_OK) return rc;
+  if (nZWin > 0) {
+    CUDA_TRY(cudaMemcpyAsync(h->zWin.ptr, zLo, nZWin * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->zWin.as<float>() + kMaxZWindows, zHi, nZWin * 4, cudaMemcpyHostToDevice, s));
+  }
+  const size_t K = std::max<uint32_t>(h->plan.seedsPerMiddle, 1);
+  const size_t maxSeeds = std::max<size_t>(1, (size_t)nTotal * K);
+  CUDA_TRY(h->outB.reserve(maxSeeds * 4));
+  CUDA_TRY(h->outM.reserve(maxSeeds * 4));
+  CUDA_TRY(h->outT.reserve(maxSeeds * 4));
+  CUDA_TRY(h->outQ.reserve(maxSeeds * 4));
+  CUDA_TRY(h->outZ.reserve(maxSeeds * 4));
+  CUDA_TRY(h->seedOffsets.reserve(((size_t)nEvents + 1) * 8));
+  rc = enqueue(h, nEvents, nTotal, h->inOffsets.as<uint32_t>(), h->inX.as<float>(), h->inY.as<float>(),
+               h->inZ.as<float>(), h->inR.as<float>(), h->inVarZ.as<float>(), h->inVarR.as<float>(), dPhi,
+               (int)nZWin, h->outB.as<uint32_t>(), h->outM.as<uint32_t>(), h->outT.as<uint32_t>(),
+               h->outQ.as<float>(), h->outZ.as<float>(), maxSeeds, h->seedOffsets.as<unsigned long long>(), s);
+  if (rc != B200SEED_OK) return rc;
+  b200seed_seeds tmp{};
+  rc = finish(h, s, &tmp);
+  out->size = tmp.size;
+  if (rc != B200SEED_OK) return rc;
+  if (tmp.size > out->capacity) {
+    return fail(B200SEED_ERR_CAPACITY, "seed buffers too small: need " + std::to_string(tmp.size));
+  }
+  if (tmp.size > 0) {
+    CUDA_TRY(cudaMemcpyAsync(out->bottom, h->outB.ptr, tmp.size * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out->middle, h->outM.ptr, tmp.size * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out->top, h->outT.ptr, tmp.size * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out->quality, h->outQ.ptr, tmp.size * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out->vertexZ, h->outZ.ptr, tmp.size * 4, cudaMemcpyDeviceToHost, s));
+  }
+  if (seedOffsets != nullptr) {
+    CUDA_TRY(cudaMemcpyAsync(seedOffsets, h->seedOffsets.ptr, ((size_t)nEvents + 1) * 8, cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return B200SEED_OK;
+}
+
+int b200seed_run(b200seed_handle* h, uint32_t nSpacePoints, const float* x, const float* y, const float* z,
+                 const float* r, const float* varZ, const float* varR, uint32_t nZWindows,
+                 const float* zWindowLo, const float* zWindowHi, b200seed_seeds* out) {
+  const uint32_t offsets[2] = {0, nSpacePoints};
+  return run_host_batch(h, 1, offsets, x, y, z, r, varZ, varR, nullptr, nZWindows, zWindowLo, zWindowHi, nullptr, out);
+}
+
+// b200seed_run with a caller-provided phi column (optional precomputed
+// azimuth, SURVEY.md section 7 "atan2f parity"; used by tests to separate the
+// atan2f replay from the rest of the path).
+int b200seed_run_with_phi(b200seed_handle* h, uint32_t nSpacePoints, const float* x, const float* y,
+                          const float* z, const float* r, const float* varZ, const float* varR,
+                          const float* phi, b200seed_seeds* out) {
+  const uint32_t offsets[2] = {0, nSpacePoints};
+  return run_host_batch(h, 1, offsets, x, y, z, r, varZ, varR, phi, 0, nullptr, nullptr, nullptr, out);
+}
+
+int b200seed_run_batch(b200seed_handle* h, uint32_t nEvents, const uint32_t* spOffsets, const float* x,
+                       const float* y, const float* z, const float* r, const float* varZ, const float* varR,
+                       uint64_t* seedOffsets, b200seed_seeds* out) {
+  return run_host_batch(h, nEvents, spOffsets, x, y, z, r, varZ, varR, nullptr, 0, nullptr, nullptr, seedOffsets, out);
+}
+
+int b200seed_debug_grid(b200seed_handle* h, uint64_t capacity, uint32_t* copiedFromIndex, float* x, float* y,
+                        float* z, float* r, float* varZ, float* varR, uint64_t binCapacity,
+                        uint32_t* binBegin, uint32_t* binEnd) {
+  if (h == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  const size_t n = h->lastCounters.nInGrid;
+  const size_t nBinsAll = (size_t)h->lastEvents * (size_t)h->plan.dev.nGlobalBins;
+  if (capacity < n || binCapacity < nBinsAll) return fail(B200SEED_ERR_CAPACITY, "debug_grid buffers too small");
+  std::vector<float2> xy(n), zr(n), var(n);
+  std::vector<uint32_t> starts(nBinsAll + 1);
+  if (n > 0) {
+    CUDA_TRY(cudaMemcpy(copiedFromIndex, h->pIdx.ptr, n * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(xy.data(), h->pXY.ptr, n * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(zr.data(), h->pZR.ptr, n * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(var.data(), h->pVar.ptr, n * 8, cudaMemcpyDeviceToHost));
+  }
+  CUDA_TRY(cudaMemcpy(starts.data(), h->binStart.ptr, (nBinsAll + 1) * 4, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; ++i) {
+    x[i] = xy[i].x; y[i] = xy[i].y; z[i] = zr[i].x; r[i] = zr[i].y; varZ[i] = var[i].x; varR[i] = var[i].y;
+  }
+  for (size_t b = 0; b < nBinsAll; ++b) {
+    binBegin[b] = starts[b];
+    binEnd[b] = starts[b + 1];
+  }
+  return B200SEED_OK;
+}
+
+int b200seed_debug_doublets(b200seed_handle* h, b200seed_doublets* out) {
+  (void)h;
+  (void)out;
+  return fail(B200SEED_ERR_UNSUPPORTED, "materialised doublet dump is not built yet");
+}
+
+int b200seed_debug_atan2f(b200seed_handle* h, uint64_t n, const float* y, const float* x, float* phi) {
+  if (h == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL handle");
+  if (n == 0) return B200SEED_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  float *dy = nullptr, *dx = nullptr, *dp = nullptr;
+  CUDA_TRY(cudaMalloc(&dy, n * 4));
+  CUDA_TRY(cudaMalloc(&dx, n * 4));
+  CUDA_TRY(cudaMalloc(&dp, n * 4));
+  cudaMemcpy(dy, y, n * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dx, x, n * 4, cudaMemcpyHostToDevice);
+  k_atan2f<<<h->smCount * 8, 256, 0, h->stream>>>(dy, dx, dp, n);
+  cudaStreamSynchronize(h->stream);
+  cudaError_t e = cudaMemcpy(phi, dp, n * 4, cudaMemcpyDeviceToHost);
+  cudaFree(dy);
+  cudaFree(dx);
+  cudaFree(dp);
+  if (e != cudaSuccess) return fail(B200SEED_ERR_CUDA, cudaGetErrorString(e));
+  return B200SEED_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,142 @@
+"""Synthetic Generic-detector-like space point events (numpy, deterministic).
+
+There is no Fatras in this image, so the benchmark events are generated from
+ideal helices through a pixel layout that follows the reference's Generic
+detector (Examples/Detectors/GenericDetector/src/GenericDetectorBuilder.cpp
+:328-335,364-368,405-406): barrel cylinders at r = 32/72/116/172 mm with
+|z| <= 490 mm and a +-1 mm radial stagger (tilted modules), end-cap discs at
+|z| = 600/700/820/960 mm with r in [30, 176] mm.  2 T solenoid field, pile-up
+vertices z ~ N(0, 55.5 mm) like CI/physmon/workflows/
+physmon_trackfinding_ttbar_pu200.py:60-63, Gaussian smearing sigma = 0.0144338 mm
+(Examples/Configs/generic-digi-smearing-config.json).  Columns are binary32
+exactly like the reference's SpacePointContainer (SpacePointMaker.cpp:260-264).
+
+RNG: Philox counter-based, key = 42 + event number (the reference's seed
+convention, Examples/Scripts/Python/seeding.py:69).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+BARREL_R = np.array([32.0, 72.0, 116.0, 172.0])
+BARREL_HALF_Z = 490.0
+ENDCAP_Z = np.array([600.0, 700.0, 820.0, 960.0])
+ENDCAP_R = (30.0, 176.0)
+SIGMA = 0.0144338
+B_FIELD_T = 2.0
+PT_PER_RADIUS = B_FIELD_T * 0.000299792458  # GeV / mm
+
+
+def _helix_hits(rng, zv, pt, eta, phi0, q):
+    """Intersections of helices from (0, 0, zv) with all layers (vectorised).
+
+    Returns x, y, z (float64), is_barrel for every hit."""
+    R = pt / PT_PER_RADIUS  # mm
+    sinh_eta = np.sinh(eta)
+    xs, ys, zs, barrel = [], [], [], []
+    # barrel: solve r = 2 R sin(alpha / 2)
+    for r0 in BARREL_R:
+        r = r0 + rng.uniform(-1.0, 1.0, size=pt.shape)
+        ok = r < 2.0 * R * 0.999
+        alpha = 2.0 * np.arcsin(np.where(ok, r / (2.0 * R), 0.0))
+        z = zv + R * alpha * sinh_eta
+        ok &= np.abs(z) <= BARREL_HALF_Z
+        phi = phi0 - q * 0.5 * alpha
+        # smear r-phi and z
+        phi = phi + rng.normal(0.0, SIGMA, size=pt.shape) / r
+        z = z + rng.normal(0.0, SIGMA, size=pt.shape)
+        xs.append((r * np.cos(phi))[ok])
+        ys.append((r * np.sin(phi))[ok])
+        zs.append(z[ok])
+        barrel.append(np.ones(int(ok.sum()), dtype=bool))
+    # end-caps: solve z = z_disc
+    for zd0 in ENDCAP_Z:
+        for side in (-1.0, 1.0):
+            zd = side * zd0 + rng.uniform(-2.0, 2.0, size=pt.shape)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                s = (zd - zv) / sinh_eta
+            alpha = s / R
+            ok = np.isfinite(s) & (s > 0) & (alpha < np.pi)
+            r = 2.0 * R * np.abs(np.sin(0.5 * np.where(ok, alpha, 0.0)))
+            ok &= (r >= ENDCAP_R[0]) & (r <= ENDCAP_R[1])
+            r = r + rng.normal(0.0, SIGMA, size=pt.shape)
+            phi = phi0 - q * 0.5 * alpha + rng.normal(0.0, SIGMA, size=pt.shape) / np.maximum(r, 1.0)
+            xs.append((r * np.cos(phi))[ok])
+            ys.append((r * np.sin(phi))[ok])
+            zs.append(zd[ok])
+            barrel.append(np.zeros(int(ok.sum()), dtype=bool))
+    return (np.concatenate(xs), np.concatenate(ys), np.concatenate(zs), np.concatenate(barrel))
+
+
+def _finish(rng, x, y, z, barrel, noise_fraction):
+    n = x.size
+    n_noise = int(round(noise_fraction * n))
+    if n_noise > 0:
+        nb = n_noise // 2
+        rb = rng.choice(BARREL_R, size=nb) + rng.uniform(-1.0, 1.0, size=nb)
+        pb = rng.uniform(-np.pi, np.pi, size=nb)
+        zb = rng.uniform(-BARREL_HALF_Z, BARREL_HALF_Z, size=nb)
+        ne = n_noise - nb
+        re = rng.uniform(ENDCAP_R[0], ENDCAP_R[1], size=ne)
+        pe = rng.uniform(-np.pi, np.pi, size=ne)
+        ze = rng.choice(ENDCAP_Z, size=ne) * rng.choice([-1.0, 1.0], size=ne) + rng.uniform(-2.0, 2.0, size=ne)
+        x = np.concatenate([x, rb * np.cos(pb), re * np.cos(pe)])
+        y = np.concatenate([y, rb * np.sin(pb), re * np.sin(pe)])
+        z = np.concatenate([z, zb, ze])
+        barrel = np.concatenate([barrel, np.ones(nb, dtype=bool), np.zeros(ne, dtype=bool)])
+    perm = rng.permutation(x.size)
+    x, y, z, barrel = x[perm], y[perm], z[perm], barrel[perm]
+    r = np.hypot(x, y)
+    var_hit = np.float32(SIGMA * SIGMA)
+    varZ = np.where(barrel, var_hit, np.float32(0.0)).astype(np.float32)
+    varR = np.where(barrel, np.float32(4e-6), var_hit).astype(np.float32)
+    return {
+        "x": x.astype(np.float32),
+        "y": y.astype(np.float32),
+        "z": z.astype(np.float32),
+        "r": r.astype(np.float32),
+        "varZ": varZ,
+        "varR": varR,
+    }
+
+
+def pileup_event(event: int, mu: float = 200.0, sp_per_vertex: float = 500.0,
+                 noise_fraction: float = 0.10, seed: int = 42) -> dict:
+    """<mu> pile-up vertices of soft charged pions (configs 2-5).
+
+    ``sp_per_vertex`` tunes the multiplicity so that <mu>=200 gives ~1e5 space
+    points per event (BASELINE.json configs[2])."""
+    rng = np.random.Generator(np.random.Philox(key=seed + event))
+    n_vtx = max(1, int(rng.poisson(mu)))
+    # ~4.5 hits per generated particle on this layout (measured)
+    n_part = rng.poisson(sp_per_vertex / (1.0 + noise_fraction) / 4.5, size=n_vtx)
+    zv = np.repeat(rng.normal(0.0, 55.5, size=n_vtx), n_part)
+    n = zv.size
+    pt = 0.1 + rng.gamma(2.0, 0.3, size=n)  # falling spectrum, GeV
+    eta = rng.uniform(-2.7, 2.7, size=n)
+    phi0 = rng.uniform(-np.pi, np.pi, size=n)
+    q = rng.choice([-1.0, 1.0], size=n)
+    x, y, z, barrel = _helix_hits(rng, zv, pt, eta, phi0, q)
+    return _finish(rng, x, y, z, barrel, noise_fraction)
+
+
+def muon_gun_event(event: int, n_muons: int = 100, seed: int = 42) -> dict:
+    """Config 1: particle gun, 100 muons/event, pT 1-10 GeV, |eta| < 2.5
+    (Examples/Scripts/Python/seeding.py:76-92), single vertex, no noise."""
+    rng = np.random.Generator(np.random.Philox(key=seed + event))
+    zv = np.full(n_muons, rng.normal(0.0, 55.5))
+    pt = rng.uniform(1.0, 10.0, size=n_muons)
+    eta = rng.uniform(-2.5, 2.5, size=n_muons)
+    phi0 = rng.uniform(-np.pi, np.pi, size=n_muons)
+    q = rng.choice([-1.0, 1.0], size=n_muons)
+    x, y, z, barrel = _helix_hits(rng, zv, pt, eta, phi0, q)
+    return _finish(rng, x, y, z, barrel, 0.0)
+
+
+def concat_events(events: list[dict]) -> tuple[dict, np.ndarray]:
+    """Concatenate events into the batch layout of ``b200seed_run_batch``."""
+    offsets = np.zeros(len(events) + 1, dtype=np.uint32)
+    for i, e in enumerate(events):
+        offsets[i + 1] = offsets[i] + e["x"].size
+    cols = {k: np.ascontiguousarray(np.concatenate([e[k] for e in events])) for k in ("x", "y", "z", "r", "varZ", "varR")}
+    return cols, offsets

@@ -1,0 +1,225 @@
+"""ctypes binding of the C ABI in ``include/acts_b200_seeding.h``.
+
+This is what a host application does across the FFI boundary: fill a
+``b200seed_config`` (same fields as ``GridTripletSeedingAlgorithm::Config``),
+create a handle, pass raw column pointers, receive seed columns.  There is no
+CPU fallback: if the CUDA library is missing or no device is present the calls
+raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import config as cfgmod
+from .config import Config, Counters, Info, Seeds
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libacts_b200_seeding.so")
+
+# every symbol include/acts_b200_seeding.h declares
+EXPORTED_SYMBOLS = [
+    "b200seed_config_init", "b200seed_plan_info", "b200seed_plan_tables", "b200seed_create",
+    "b200seed_destroy", "b200seed_last_error", "b200seed_get_info", "b200seed_get_counters",
+    "b200seed_run", "b200seed_run_with_phi", "b200seed_run_batch", "b200seed_run_batch_device",
+    "b200seed_sync", "b200seed_debug_grid", "b200seed_debug_doublets", "b200seed_debug_atan2f",
+]
+
+
+class SeedingError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"b200seed error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+_lib = None
+
+
+def lib():
+    """Load the plugin (built in-tree by ``acts_b200.build``); fail loudly if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SeedingError(cfgmod.ERR_CUDA, f"{LIB_PATH} is missing: run `python -m acts_b200.build` (nvcc, sm_100a)")
+        L = C.CDLL(LIB_PATH)
+        vp, u32, u64, f32p = C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p
+        L.b200seed_last_error.restype = C.c_char_p
+        L.b200seed_config_init.argtypes = [C.POINTER(Config)]
+        L.b200seed_plan_info.argtypes = [C.POINTER(Config), C.POINTER(Info)]
+        L.b200seed_plan_tables.argtypes = [C.POINTER(Config), vp, u64, vp, vp, vp, vp, vp, vp]
+        L.b200seed_create.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(vp)]
+        L.b200seed_destroy.argtypes = [vp]
+        L.b200seed_get_info.argtypes = [vp, C.POINTER(Info)]
+        L.b200seed_get_counters.argtypes = [vp, C.POINTER(Counters)]
+        L.b200seed_run.argtypes = [vp, u32] + [f32p] * 6 + [u32, f32p, f32p, C.POINTER(Seeds)]
+        L.b200seed_run_with_phi.argtypes = [vp, u32] + [f32p] * 7 + [C.POINTER(Seeds)]
+        L.b200seed_run_batch.argtypes = [vp, u32, vp] + [f32p] * 6 + [vp, C.POINTER(Seeds)]
+        L.b200seed_run_batch_device.argtypes = [vp, u32, u32, vp] + [f32p] * 6 + [vp, C.POINTER(Seeds), vp]
+        L.b200seed_sync.argtypes = [vp, C.POINTER(Seeds)]
+        L.b200seed_debug_grid.argtypes = [vp, u64] + [vp] * 7 + [u64, vp, vp]
+        L.b200seed_debug_doublets.argtypes = [vp, vp]
+        L.b200seed_debug_atan2f.argtypes = [vp, u64, vp, vp, vp]
+        _lib = L
+    return _lib
+
+
+def config_init(cfg_ref):
+    lib().b200seed_config_init(cfg_ref)
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise SeedingError(rc, lib().b200seed_last_error().decode())
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def plan_info(cfg: Config) -> Info:
+    """Host-only validation + derived constants (no GPU needed)."""
+    info = Info()
+    _check(lib().b200seed_plan_info(C.byref(cfg), C.byref(info)))
+    return info
+
+
+def plan_tables(cfg: Config) -> dict:
+    """Host-only: device constant block + navigation / neighbour tables."""
+    sizes = np.zeros(8, dtype=np.uint64)
+    _check(lib().b200seed_plan_tables(C.byref(cfg), None, 0, None, None, None, None, None, _p(sizes)))
+    n_nav, n_bot, n_top, dc_bytes, k = (int(v) for v in sizes[:5])
+    out = {
+        "deviceConfig": np.zeros(dc_bytes, dtype=np.uint8),
+        "navBins": np.zeros(n_nav, dtype=np.uint32),
+        "botOffsets": np.zeros(n_nav + 1, dtype=np.uint32),
+        "botBins": np.zeros(max(n_bot, 1), dtype=np.uint32),
+        "topOffsets": np.zeros(n_nav + 1, dtype=np.uint32),
+        "topBins": np.zeros(max(n_top, 1), dtype=np.uint32),
+        "seedsPerMiddle": k,
+    }
+    _check(lib().b200seed_plan_tables(C.byref(cfg), _p(out["deviceConfig"]), dc_bytes, _p(out["navBins"]),
+                                      _p(out["botOffsets"]), _p(out["botBins"]), _p(out["topOffsets"]),
+                                      _p(out["topBins"]), _p(sizes)))
+    out["botBins"] = out["botBins"][:n_bot]
+    out["topBins"] = out["topBins"][:n_top]
+    return out
+
+
+class SeedingEngine:
+    """One handle = one device + one stream (see the header's threading contract)."""
+
+    def __init__(self, cfg: Config, device: int = 0):
+        self._h = C.c_void_p()
+        self.cfg = cfg
+        _check(lib().b200seed_create(C.byref(cfg), device, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().b200seed_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> Info:
+        i = Info()
+        _check(lib().b200seed_get_info(self._h, C.byref(i)))
+        return i
+
+    def counters(self) -> dict:
+        c = Counters()
+        _check(lib().b200seed_get_counters(self._h, C.byref(c)))
+        return c.as_dict()
+
+    @staticmethod
+    def _cols(ev):
+        return [np.ascontiguousarray(ev[k], dtype=np.float32) for k in ("x", "y", "z", "r", "varZ", "varR")]
+
+    @staticmethod
+    def _alloc(capacity):
+        out = {
+            "bottom": np.zeros(capacity, np.uint32), "middle": np.zeros(capacity, np.uint32),
+            "top": np.zeros(capacity, np.uint32), "quality": np.zeros(capacity, np.float32),
+            "vertexZ": np.zeros(capacity, np.float32),
+        }
+        s = Seeds()
+        s.bottom, s.middle, s.top = _p(out["bottom"]), _p(out["middle"]), _p(out["top"])
+        s.quality, s.vertexZ = _p(out["quality"]), _p(out["vertexZ"])
+        s.capacity = capacity
+        return out, s
+
+    def run(self, ev: dict, z_windows=None, phi=None, capacity=None) -> dict:
+        """One event through ``b200seed_run`` (host buffers in, host seeds out)."""
+        cols = self._cols(ev)
+        n = cols[0].size
+        cap = capacity if capacity is not None else max(16, n * 6)
+        out, s = self._alloc(cap)
+        if phi is not None:
+            phi = np.ascontiguousarray(phi, dtype=np.float32)
+            rc = lib().b200seed_run_with_phi(self._h, n, *[_p(c) for c in cols], _p(phi), C.byref(s))
+        else:
+            lo = hi = None
+            nzw = 0
+            if z_windows is not None and len(z_windows) > 0:
+                lo = np.ascontiguousarray([w[0] for w in z_windows], dtype=np.float32)
+                hi = np.ascontiguousarray([w[1] for w in z_windows], dtype=np.float32)
+                nzw = lo.size
+            rc = lib().b200seed_run(self._h, n, *[_p(c) for c in cols], nzw, _p(lo), _p(hi), C.byref(s))
+        _check(rc)
+        k = int(s.size)
+        return {name: arr[:k] for name, arr in out.items()}
+
+    def run_batch(self, cols: dict, offsets: np.ndarray, capacity=None) -> list[dict]:
+        """A batch of events through ``b200seed_run_batch``; returns one dict per event."""
+        arrs = self._cols(cols)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+        n_events = offsets.size - 1
+        cap = capacity if capacity is not None else max(16, int(offsets[-1]) * 6)
+        out, s = self._alloc(cap)
+        seed_offsets = np.zeros(n_events + 1, dtype=np.uint64)
+        _check(lib().b200seed_run_batch(self._h, n_events, _p(offsets), *[_p(a) for a in arrs], _p(seed_offsets), C.byref(s)))
+        res = []
+        for e in range(n_events):
+            a, b = int(seed_offsets[e]), int(seed_offsets[e + 1])
+            res.append({name: arr[a:b] for name, arr in out.items()})
+        return res
+
+    def debug_grid(self, n_events: int = 1) -> dict:
+        n = self.counters()["nInGrid"]
+        nb = self.info().nGlobalBins * n_events
+        g = {"copiedFromIndex": np.zeros(n, np.uint32)}
+        for k in ("x", "y", "z", "r", "varZ", "varR"):
+            g[k] = np.zeros(n, np.float32)
+        g["binBegin"] = np.zeros(nb, np.uint32)
+        g["binEnd"] = np.zeros(nb, np.uint32)
+        _check(lib().b200seed_debug_grid(self._h, n, *[_p(g[k]) for k in ("copiedFromIndex", "x", "y", "z", "r", "varZ", "varR")],
+                                         nb, _p(g["binBegin"]), _p(g["binEnd"])))
+        return g
+
+    def device_atan2f(self, y: np.ndarray, x: np.ndarray) -> np.ndarray:
+        y = np.ascontiguousarray(y, dtype=np.float32)
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.zeros_like(y)
+        _check(lib().b200seed_debug_atan2f(self._h, y.size, _p(y), _p(x), _p(out)))
+        return out
+
+    # ---- device-resident path (inputs already in HBM) -------------------------
+    def run_batch_device(self, n_events, n_total, d_offsets, d_cols, d_seed_offsets, d_out, capacity, stream=None):
+        """Raw device pointers (ints); asynchronous, see ``b200seed_run_batch_device``."""
+        s = Seeds()
+        s.bottom, s.middle, s.top, s.quality, s.vertexZ = d_out
+        s.capacity = capacity
+        _check(lib().b200seed_run_batch_device(self._h, n_events, n_total, d_offsets, *d_cols, d_seed_offsets, C.byref(s), stream))
+        return s
+
+    def sync(self, seeds: Seeds | None = None) -> int:
+        s = seeds if seeds is not None else Seeds()
+        _check(lib().b200seed_sync(self._h, C.byref(s)))
+        return int(s.size)

@@ -1,0 +1,382 @@
+// gpu_model.cpp -- sequential CPU model of the GPU algorithm (TEST INFRASTRUCTURE).
+//
+// The CUDA kernels do not run the reference's loops literally: r windows are
+// found by binary search, doublets are ordered by (cotTheta, emission index),
+// every bottom doublet derives its top window independently (prefix-max
+// formulation) and heap pushes are replayed from a
+// compacted candidate list.  This file executes exactly that restructured
+// algorithm, single threaded, with the SAME arithmetic (acts_b200/csrc/seed_math.h)
+// so that its equivalence with the oracle can be tested on a machine without a
+// GPU.  It is never part of the product library.
+#include "../../acts_b200/csrc/seed_math.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <random>
+#include <utility>
+#include <vector>
+
+using namespace b200seed;
+
+namespace {
+
+struct Packed {
+  const uint32_t* copiedFrom;
+  const float *x, *y, *z, *r, *varZ, *varR;
+};
+
+struct SortItem {
+  float key;
+  uint32_t val;
+};
+inline bool sortItemLess(const SortItem& a, const SortItem& b) { return a.key < b.key; }
+
+struct SeedOut {
+  uint32_t b, m, t;
+  float q, z;
+};
+
+// first position in [lo, hi) where pred is true (pred monotone false..true)
+template <typename Pred>
+uint32_t firstTrue(uint32_t lo, uint32_t hi, Pred pred) {
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (pred(mid)) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+struct Window {
+  uint32_t begin, end;
+};
+
+struct Doublet {
+  DoubletRec rec;
+  uint32_t pos;  // packed position of the other space point
+  uint32_t seq;  // emission index in the reference's order
+};
+
+// One middle space point, restructured algorithm.  tieMode: 0 canonical
+// (key, seq) order, 1 replay libstdc++ std::sort from the emission order.
+void processMiddle(const DeviceConfig& c, const Packed& p, uint32_t m, uint32_t firstMiddleInBin,
+                   const std::vector<Window>& bottomBins, const std::vector<Window>& topBins,
+                   const float* zLo, const float* zHi, int nZWin, int tieMode,
+                   std::vector<SeedOut>& out, uint64_t* stats) {
+  MiddleSp mid{p.x[m], p.y[m], p.z[m], p.r[m], p.varZ[m], p.varR[m], 0, 0, 0, 0};
+  middle_info(mid);
+  const float firstMiddleR = p.r[firstMiddleInBin];
+
+  auto collect = [&](bool bottom, const std::vector<Window>& bins, std::vector<Doublet>& dst) {
+    uint32_t seq = 0;
+    for (const Window& bin : bins) {
+      uint32_t start, end;
+      if (bottom) {
+        // TripletSeeder.cpp:157-170 pre-trim + DoubletSeedFinder.cpp:73-93,105-113
+        const float trimValue = fsub(firstMiddleR, c.dRMaxB);
+        const uint32_t trim = firstTrue(bin.begin, bin.end, [&](uint32_t i) { return !(p.r[i] < trimValue); });
+        start = firstTrue(trim, bin.end, [&](uint32_t i) { return fsub(mid.r, p.r[i]) <= c.dRMaxB; });
+        end = firstTrue(start, bin.end, [&](uint32_t i) { return fsub(mid.r, p.r[i]) < c.dRMinB; });
+      } else {
+        const float trimValue = fadd(firstMiddleR, c.dRMinT);
+        const uint32_t trim = firstTrue(bin.begin, bin.end, [&](uint32_t i) { return !(p.r[i] < trimValue); });
+        start = firstTrue(trim, bin.end, [&](uint32_t i) { return fsub(p.r[i], mid.r) >= c.dRMinT; });
+        end = firstTrue(start, bin.end, [&](uint32_t i) { return fsub(p.r[i], mid.r) > c.dRMaxT; });
+      }
+      for (uint32_t o = start; o < end; ++o, ++seq) {
+        float dR, dZ;
+        const bool ok = bottom ? doublet_zr_cuts<true>(c, mid, p.z[o], p.r[o], dR, dZ)
+                               : doublet_zr_cuts<false>(c, mid, p.z[o], p.r[o], dR, dZ);
+        if (!ok) continue;
+        Doublet d;
+        const bool ok2 = bottom ? doublet_finish<true>(c, mid, dR, dZ, p.x[o], p.y[o], p.r[o], p.varZ[o], p.varR[o], zLo, zHi, nZWin, d.rec)
+                                : doublet_finish<false>(c, mid, dR, dZ, p.x[o], p.y[o], p.r[o], p.varZ[o], p.varR[o], zLo, zHi, nZWin, d.rec);
+        if (!ok2) continue;
+        d.pos = o;
+        d.seq = seq;
+        dst.push_back(d);
+      }
+    }
+  };
+
+  std::vector<Doublet> tops, bottoms;
+  collect(false, topBins, tops);
+  if (tops.empty()) return;
+  collect(true, bottomBins, bottoms);
+  if (bottoms.empty()) return;
+  stats[0] += bottoms.size();
+  stats[1] += tops.size();
+
+  auto sortList = [&](std::vector<Doublet>& v) {
+    if (tieMode == 0) {
+      // GPU canonical order: (cotTheta, emission index); the kernel gets there
+      // with a bucket sort, any correct sort gives the same unique order
+      std::sort(v.begin(), v.end(), [](const Doublet& a, const Doublet& b) {
+        if (a.rec.cotTheta != b.rec.cotTheta) return a.rec.cotTheta < b.rec.cotTheta;
+        return a.seq < b.seq;
+      });
+    } else {
+      // exact replay: v is in emission order, sort {index, cotTheta} like
+      // DoubletSeedFinder.hpp:94-104 with the libstdc++ algorithm
+      std::vector<SortItem> items(v.size());
+      for (uint32_t i = 0; i < v.size(); ++i) items[i] = {v[i].rec.cotTheta, i};
+      std_sort(items.data(), (int)items.size(), sortItemLess);
+      std::vector<Doublet> sorted(v.size());
+      for (uint32_t i = 0; i < v.size(); ++i) sorted[i] = v[items[i].val];
+      v.swap(sorted);
+    }
+  };
+  sortList(bottoms);
+  sortList(tops);
+
+  const int nT = (int)tops.size(), nB = (int)bottoms.size();
+
+  // --- per bottom, independent of the others: H_j, brk_j --------------------
+  std::vector<int> H(nB), brk(nB), ub(nB);
+  std::vector<BottomCtx> ctx(nB);
+  for (int j = 0; j < nB; ++j) {
+    BottomCtx& b = ctx[j];
+    b.cotThetaB = bottoms[j].rec.cotTheta; b.erB = bottoms[j].rec.er;
+    b.iDeltaRB = bottoms[j].rec.iDeltaR; b.Ub = bottoms[j].rec.u; b.Vb = bottoms[j].rec.v;
+    bottom_ctx(c, b);
+    // |P_j| = number of tops with cotT <= cotB  (i.e. !(cotB < cotT))
+    int lo = 0, hi = nT;
+    while (lo < hi) {
+      const int mid2 = (lo + hi) >> 1;
+      if (b.cotThetaB < tops[mid2].rec.cotTheta) hi = mid2; else lo = mid2 + 1;
+    }
+    ub[j] = lo;
+    float cu, im;
+    int h = 0;
+    for (int t = lo - 1; t >= 0; --t) {  // last failing top of the prefix
+      const DoubletRec& T = tops[t].rec;
+      const int cls = eval_pair(c, mid.r, mid.varZ, mid.varR, b, T.cotTheta, T.er, T.iDeltaR, T.u, T.v, cu, im);
+      if (cls == kPairFailA) { h = t + 1; break; }
+      if (cls == kPairFailB) { h = t; break; }
+    }
+    H[j] = h;
+    int k = lo;
+    for (; k < nT; ++k) {  // first failing top beyond the prefix
+      const DoubletRec& T = tops[k].rec;
+      const int cls = eval_pair(c, mid.r, mid.varZ, mid.varR, b, T.cotTheta, T.er, T.iDeltaR, T.u, T.v, cu, im);
+      if (cls == kPairFailA || cls == kPairFailB) break;
+    }
+    brk[j] = k;
+  }
+
+  // --- window starts: exclusive prefix max of H ------------------------------
+  std::vector<int> start(nB);
+  {
+    int run = 0;
+    for (int j = 0; j < nB; ++j) {
+      start[j] = run;
+      run = std::max(run, H[j]);
+    }
+  }
+
+  // --- candidates, filter, bounded heap -------------------------------------
+  struct Cand { float curv, impact, topR; uint32_t topPos; };
+  const int nLow = (int)c.maxSeedsPerSpMConf;
+  std::vector<WeightIndex> heap;  // size <= nLow
+  struct Stored { uint32_t b, t; float w, z; };
+  std::vector<Stored> storage;
+  std::vector<Cand> cands;
+  std::vector<SortItem> order;
+  for (int j = 0; j < nB; ++j) {
+    cands.clear();
+    const BottomCtx& b = ctx[j];
+    for (int t = start[j]; t < brk[j]; ++t) {
+      const DoubletRec& T = tops[t].rec;
+      float cu, im;
+      stats[2]++;
+      const int cls = eval_pair(c, mid.r, mid.varZ, mid.varR, b, T.cotTheta, T.er, T.iDeltaR, T.u, T.v, cu, im);
+      if (cls != kPairEmit) continue;
+      const uint32_t tp = tops[t].pos;
+      float topR = p.r[tp];
+      if (c.useDeltaRinsteadOfTopRadius) {
+        const float dr = fsub(p.r[tp], mid.r), dz = fsub(p.z[tp], mid.z);
+        topR = fsqrt(fadd(fmul(dr, dr), fmul(dz, dz)));
+      }
+      cands.push_back({cu, im, topR, tp});
+    }
+    const int n = (int)cands.size();
+    if (n < 1) continue;
+    stats[3] += n;
+    const float zOrigin = fsub(mid.z, fmul(mid.r, b.cotThetaB));
+    order.resize(n);
+    for (int i = 0; i < n; ++i) order[i] = {cands[i].curv, (uint32_t)i};
+    std_sort(order.data(), n, sortItemLess);  // BroadTripletSeedFilter.cpp:143-148
+    for (int k = 0; k < n; ++k) {
+      const Cand& cd = cands[order[k].val];
+      const float w = filter_weight(
+          c, n, k, cd.impact, [&](int i) { return cands[order[i].val].curv; },
+          [&](int i) { return cands[order[i].val].topR; });
+      // CandidatesForMiddleSp::push, detail/CandidatesForMiddleSp.cpp:44-75
+      if (nLow == 0) continue;
+      if ((int)heap.size() < nLow) {
+        storage.push_back({bottoms[j].pos, cd.topPos, w, zOrigin});
+        heap.push_back({w, (uint32_t)storage.size() - 1});
+        std_push_heap(heap.data(), (int)heap.size(), heap_comp);
+        continue;
+      }
+      const WeightIndex smallest = heap[0];
+      if (w <= smallest.weight) continue;
+      storage[smallest.index] = {bottoms[j].pos, cd.topPos, w, zOrigin};
+      std_pop_heap(heap.data(), (int)heap.size(), heap_comp);
+      heap.back() = {w, smallest.index};
+      std_push_heap(heap.data(), (int)heap.size(), heap_comp);
+    }
+  }
+  // toSortedCandidates + filterTripletsMiddleFixed (BroadTripletSeedFilter.cpp:324-393)
+  std_sort_heap(heap.data(), (int)heap.size(), heap_comp);
+  size_t maxSeeds = heap.size();
+  if (maxSeeds > c.maxSeedsPerSpM) maxSeeds = c.maxSeedsPerSpM + 1;
+  for (size_t i = 0; i < heap.size() && i < maxSeeds; ++i) {
+    const Stored& s = storage[heap[i].index];
+    out.push_back({p.copiedFrom[s.b], p.copiedFrom[m], p.copiedFrom[s.t], s.w, s.z});
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+// Runs the restructured algorithm on an already built grid (packed arrays +
+// per-bin ranges).  Neighbour bins are passed per middle bin as index lists
+// into binBegin/binEnd: nbrOffsets has nMiddleBins+1 entries for each side.
+// middleBins lists the middle bins in navigation order with their r range.
+int64_t model_run(const DeviceConfig* cfg, const uint32_t* copiedFrom, const float* x,
+                  const float* y, const float* z, const float* r, const float* varZ,
+                  const float* varR, const uint32_t* binBegin, const uint32_t* binEnd,
+                  uint32_t nMiddleBins, const uint32_t* middleBins, const float* rangeMin,
+                  const float* rangeMax, const uint32_t* botOffsets, const uint32_t* botBins,
+                  const uint32_t* topOffsets, const uint32_t* topBins, uint32_t nZWin,
+                  const float* zLo, const float* zHi, int tieMode, uint64_t capacity,
+                  uint32_t* ob, uint32_t* om, uint32_t* ot, float* oq, float* oz,
+                  uint64_t* stats) {
+  Packed p{copiedFrom, x, y, z, r, varZ, varR};
+  std::vector<SeedOut> out;
+  for (int i = 0; i < 8; ++i) stats[i] = 0;
+  for (uint32_t g = 0; g < nMiddleBins; ++g) {
+    const uint32_t mb = middleBins[g];
+    if (binBegin[mb] == binEnd[mb]) continue;
+    std::vector<Window> bot, top;
+    for (uint32_t k = botOffsets[g]; k < botOffsets[g + 1]; ++k) bot.push_back({binBegin[botBins[k]], binEnd[botBins[k]]});
+    for (uint32_t k = topOffsets[g]; k < topOffsets[g + 1]; ++k) top.push_back({binBegin[topBins[k]], binEnd[topBins[k]]});
+    // TripletSeeder.cpp:183-195 as a predicate-defined contiguous range
+    const uint32_t mlo = firstTrue(binBegin[mb], binEnd[mb], [&](uint32_t i) { return !(r[i] < rangeMin[g]); });
+    const uint32_t mhi = firstTrue(mlo, binEnd[mb], [&](uint32_t i) { return r[i] > rangeMax[g]; });
+    for (uint32_t m = mlo; m < mhi; ++m) {
+      processMiddle(*cfg, p, m, binBegin[mb], bot, top, zLo, zHi, (int)nZWin, tieMode, out, stats);
+    }
+  }
+  if (out.size() <= capacity) {
+    for (size_t i = 0; i < out.size(); ++i) {
+      ob[i] = out[i].b; om[i] = out[i].m; ot[i] = out[i].t; oq[i] = out[i].q; oz[i] = out[i].z;
+    }
+  }
+  return (int64_t)out.size();
+}
+
+// grid stage of the model: bin index with the replayed atan2f, per-SP
+int32_t model_bin_index(const DeviceConfig* cfg, float x, float y, float z, float r) {
+  if (cfg->useExtraCuts && !itk_sp_select(r, z)) return -1;
+  return grid_bin_index(*cfg, glibc_atan2f(y, x), z, r);
+}
+float model_atan2f(float y, float x) { return glibc_atan2f(y, x); }
+
+// ---- self checks of the libstdc++ replays against the real libstdc++ -------
+// returns the number of trials whose result differs from std::sort
+int64_t model_check_std_sort(uint64_t seed, int maxN, int trials, int keyRange) {
+  std::mt19937_64 rng(seed);
+  int64_t bad = 0;
+  for (int t = 0; t < trials; ++t) {
+    const int n = (int)(rng() % (uint64_t)(maxN + 1));
+    std::vector<SortItem> a(n), b;
+    const int mode = (int)(rng() % 5);
+    for (int i = 0; i < n; ++i) {
+      float key;
+      switch (mode) {
+        case 0: key = (float)(rng() % (uint64_t)keyRange); break;              // heavy ties
+        case 1: key = (float)i; break;                                          // sorted
+        case 2: key = (float)(n - i); break;                                    // reversed
+        case 3: key = (float)((i * 7919) % std::max(1, n / 3)); break;          // patterned ties
+        default: key = (float)(rng() % 1000003) * 1e-3f; break;                 // mostly distinct
+      }
+      a[i] = {key, (uint32_t)i};
+    }
+    b = a;
+    std_sort(a.data(), n, sortItemLess);
+    std::sort(b.begin(), b.end(), sortItemLess);
+    for (int i = 0; i < n; ++i) {
+      if (a[i].val != b[i].val) { ++bad; break; }
+    }
+  }
+  return bad;
+}
+
+// adversarial input for median-of-3 quicksort (forces the heap-sort fallback)
+int64_t model_check_std_sort_killer(int n) {
+  // Musser's median-of-3 killer sequence
+  std::vector<SortItem> a(n);
+  const int k = n / 2;
+  for (int i = 0; i < n; ++i) a[i] = {0.f, (uint32_t)i};
+  for (int i = 1; i <= k; ++i) {
+    if (i % 2 == 1) { a[i - 1].key = (float)i; a[i].key = (float)(k + i); }
+    a[k + i - 1].key = (float)(2 * i);
+  }
+  std::vector<SortItem> b = a;
+  std_sort(a.data(), n, sortItemLess);
+  std::sort(b.begin(), b.end(), sortItemLess);
+  int64_t bad = 0;
+  for (int i = 0; i < n; ++i) bad += a[i].val != b[i].val;
+  return bad;
+}
+
+int64_t model_check_heap(uint64_t seed, int trials) {
+  std::mt19937_64 rng(seed);
+  int64_t bad = 0;
+  auto comp = [](const std::pair<float, uint32_t>& a, const std::pair<float, uint32_t>& b) { return a.first > b.first; };
+  for (int t = 0; t < trials; ++t) {
+    const int cap = 1 + (int)(rng() % 8);
+    const int nPush = (int)(rng() % 64);
+    std::vector<std::pair<float, uint32_t>> ref;
+    std::vector<WeightIndex> mine;
+    for (int i = 0; i < nPush; ++i) {
+      const float w = (float)(rng() % 6);
+      if ((int)ref.size() < cap) {
+        ref.emplace_back(w, (uint32_t)i); std::push_heap(ref.begin(), ref.end(), comp);
+        mine.push_back({w, (uint32_t)i}); std_push_heap(mine.data(), (int)mine.size(), heap_comp);
+      } else if (!(w <= ref.front().first)) {
+        std::pop_heap(ref.begin(), ref.end(), comp); ref.back() = {w, (uint32_t)i}; std::push_heap(ref.begin(), ref.end(), comp);
+        std_pop_heap(mine.data(), (int)mine.size(), heap_comp); mine.back() = {w, (uint32_t)i}; std_push_heap(mine.data(), (int)mine.size(), heap_comp);
+      }
+    }
+    std::sort_heap(ref.begin(), ref.end(), comp);
+    std_sort_heap(mine.data(), (int)mine.size(), heap_comp);
+    for (size_t i = 0; i < ref.size(); ++i) {
+      if (ref[i].second != mine[i].index) { ++bad; break; }
+    }
+  }
+  return bad;
+}
+
+int64_t model_check_atan2f(uint64_t seed, int64_t n) {
+  uint64_t s = seed | 1;
+  int64_t bad = 0;
+  auto next = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+  for (int64_t i = 0; i < n; ++i) {
+    float x = ((int64_t)(next() & 0xffffff) - 0x800000) * (200.f / 0x800000);
+    float y = ((int64_t)(next() & 0xffffff) - 0x800000) * (200.f / 0x800000);
+    if (i % 7 == 0) x = u2f((uint32_t)(next() >> 32));
+    if (i % 11 == 0) y = u2f((uint32_t)(next() >> 20));
+    const float a = std::atan2(y, x), b = glibc_atan2f(y, x);
+    if (f2u(a) != f2u(b) && !(a != a && b != b)) ++bad;
+  }
+  return bad;
+}
+
+uint64_t model_sizeof_device_config() { return sizeof(DeviceConfig); }
+
+}  // extern "C"
