@@ -222,11 +222,17 @@ void build(const b200seed_config& c, HostPlan& plan) {
       zFirst = zNb[2 * (zLoc - 1)];
       zSecond = zNb[2 * (zLoc - 1) + 1];
     }
+    // Under-/overflow bins of the open z and r axes are legal neighbours in the
+    // reference (Axis.hpp:413-423) but can never hold a space point because
+    // insert() requires isInside on every axis (SpacePointGridBase.hpp:67-87):
+    // dropping them keeps the emission order of everything that can exist.
     std::vector<uint32_t> out;
     for (int p : closedNeighbors(phiLoc, -c.numPhiNeighbors, c.numPhiNeighbors, d.phiBins))
       for (int z : openNeighbors(zLoc, zFirst, zSecond, d.nZ))
-        for (int r : openNeighbors(rLoc, 0, 0, d.nR))
+        for (int r : openNeighbors(rLoc, 0, 0, d.nR)) {
+          if (z < 1 || z > d.nZ || r < 1 || r > d.nR) continue;
           out.push_back(static_cast<uint32_t>((p * (d.nZ + 2) + z) * (d.nR + 2) + r));
+        }
     return out;
   };
 

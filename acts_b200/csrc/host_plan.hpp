@@ -31,8 +31,8 @@ struct HostPlan {
   // middle bins in the reference's visiting order (phi outermost, z in
   // zBinsCustomLooping order, r) as global bin indices
   std::vector<uint32_t> navBins;
-  // neighbour bins of every navigation entry, flattened; empty (under/overflow)
-  // bins are kept so that the emission order is literally the reference's
+  // neighbour bins of every navigation entry, flattened, in the reference's
+  // order (never-fillable under/overflow bins removed)
   std::vector<uint32_t> botOffsets, botBins, topOffsets, topBins;
   uint32_t maxNeighborBins = 0;
   // per-middle output slots: min(maxSeedsPerSpM + 1, maxSeedsPerSpMConf)

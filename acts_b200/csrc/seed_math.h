@@ -190,7 +190,7 @@ B2S_HD float glibc_atan2f(float y, float x) {
 // Device-side constants (derived on the host with the reference's expressions)
 // ---------------------------------------------------------------------------
 constexpr int kMaxZEdges = 64;        // z bins + 1 supported on the device
-constexpr int kMaxNeighborBins = 32;  // neighbour bins per side per middle bin
+constexpr int kMaxNeighborBins = 64;  // non-empty-able neighbour bins per side per middle bin
 constexpr int kMaxZWindows = 32;      // VertexZCuts windows per event
 constexpr int kMaxCompatSeedLimit = 8;
 constexpr int kMaxHeap = 16;          // maxSeedsPerSpMConf supported
@@ -620,6 +620,72 @@ B2S_HD void std_sort(T* a, int n, Less less) {
     for (int i = kThreshold; i != n; ++i) std_unguarded_linear_insert(a, i, less);
   } else {
     std_insertion_sort(a, 0, n, less);
+  }
+}
+
+// Pruned replay of libstdc++ std::sort that only resolves TIE ORDER.
+//
+// For an element whose key is unique the final position is forced (number of
+// smaller keys), whatever the algorithm does.  What the unstable introsort
+// decides is the internal order of every group of equal keys.  That order can
+// be obtained by replaying the introsort partitions only on ranges that still
+// contain at least two flagged (tied) elements: a range without two tied
+// elements cannot change any tie order, elements never leave their range, and
+// the final insertion sort is stable (it never swaps equal keys).  After the
+// pruned replay the left-to-right order of the flagged elements in `a` IS their
+// order in the reference's std::sort output.
+//
+// `a` must hold the n elements in the reference's INPUT order; `flagged(e)`
+// tells whether an element belongs to a tie group.  Cost ~2-3 n element visits
+// for a few tie groups instead of n log n.
+template <typename T, typename Less, typename Flagged>
+B2S_HD void std_sort_replay_ties(T* a, int n, Less less, Flagged flagged) {
+  if (n <= 16) return;  // plain insertion sort: stable, input order decides
+  constexpr int kThreshold = 16;
+  int lg = 0;
+  for (unsigned v = (unsigned)n; v > 1; v >>= 1) ++lg;
+  int stackFirst[64], stackLast[64], stackDepth[64];
+  int sp = 0;
+  stackFirst[0] = 0; stackLast[0] = n; stackDepth[0] = 2 * lg; sp = 1;
+  while (sp > 0) {
+    --sp;
+    int first = stackFirst[sp], last = stackLast[sp], depth = stackDepth[sp];
+    while (last - first > kThreshold) {
+      int nFlagged = 0;
+      for (int i = first; i < last && nFlagged < 2; ++i) nFlagged += flagged(a[i]) ? 1 : 0;
+      if (nFlagged < 2) break;  // nothing left to decide in this range
+      if (depth == 0) {
+        std_make_heap(a + first, last - first, less);
+        std_sort_heap(a + first, last - first, less);
+        break;
+      }
+      --depth;
+      const int mid = first + (last - first) / 2;
+      {
+        const int ia = first + 1, ib = mid, ic = last - 1;
+        int pick;
+        if (less(a[ia], a[ib])) {
+          if (less(a[ib], a[ic])) pick = ib;
+          else if (less(a[ia], a[ic])) pick = ic;
+          else pick = ia;
+        } else if (less(a[ia], a[ic])) pick = ia;
+        else if (less(a[ib], a[ic])) pick = ic;
+        else pick = ib;
+        const T t = a[first]; a[first] = a[pick]; a[pick] = t;
+      }
+      int lo = first + 1, hi = last;
+      while (true) {
+        while (less(a[lo], a[first])) ++lo;
+        --hi;
+        while (less(a[first], a[hi])) --hi;
+        if (!(lo < hi)) break;
+        const T t = a[lo]; a[lo] = a[hi]; a[hi] = t;
+        ++lo;
+      }
+      const int cut = lo;
+      stackFirst[sp] = cut; stackLast[sp] = last; stackDepth[sp] = depth; ++sp;
+      last = cut;
+    }
   }
 }
 

@@ -28,7 +28,7 @@
 namespace b200seed {
 
 constexpr uint32_t kInvalidBin = 0xFFFFFFFFu;
-constexpr int kSeedThreads = 256;
+constexpr int kSeedThreads = 512;
 constexpr int kSortThreads = 256;
 constexpr int kScanThreads = 1024;
 constexpr int kTile = 2048;  // elements per block in the tiled scan
@@ -91,7 +91,10 @@ struct SeedParams {
   const uint32_t* binStart;
   const uint32_t *navBins, *botOffsets, *botBins, *topOffsets, *topBins;
   const uint32_t *workPos, *workEG;
-  const uint32_t* nWorkPtr;
+  const uint32_t* nWorkPtr;   // number of items of THIS launch
+  const uint32_t* workList;   // NULL: items are 0..n-1; else indices into workPos/workEG
+  uint32_t* overflowList;     // middles that did not fit this launch's scratch (NULL: error)
+  uint32_t* overflowCount;
   uint32_t nNav, nBins;
   const float *zWinLo, *zWinHi;
   int nZWin;
@@ -101,6 +104,7 @@ struct SeedParams {
   uint32_t* slotCount;
   uint32_t seedsPerMiddle;
   uint32_t capB, capT, capPool, nBuckets;
+  int exactTies;  // replay libstdc++ std::sort inside groups of equal cotTheta
   unsigned long long* counters;
   int* status;
 };
@@ -431,7 +435,7 @@ struct SeedShared {
   MiddleSp mid;
   uint32_t w, m, eg;
   uint32_t nB, nT, poolCount;
-  uint32_t tie, bad;
+  uint32_t tie, tieTmp, bad;
   uint32_t carry;
   uint32_t nBotWin, nTopWin;
   uint32_t winBs[kMaxNeighborBins], winBe[kMaxNeighborBins], winBp[kMaxNeighborBins + 1];
@@ -450,29 +454,38 @@ __device__ __forceinline__ uint32_t seq_to_pos(uint32_t seq, const uint32_t* pre
   return start[k] + (seq - prefix[k]);
 }
 
-// Shared-memory carve-up (all sizes multiples of 16 bytes)
+// Shared-memory carve-up.  Persistent arrays first, then one arena whose
+// content changes with the phase of a middle:
+//   phases 1-2 : tCot, tSeq, tSorted (tops before their records exist)
+//   tie replay : W + two u16 arrays -- for the tops inside the (not yet written)
+//                sorted-top arrays, for the bottoms inside the arena
+//   phase 3    : pool (+ links) and pool2
 struct SeedSmem {
   SeedShared* sh;
   float* bCot; uint32_t* bSeq; uint16_t* bSorted;       // bottoms, unsorted + rank -> index
-  float* tCot; uint32_t* tSeq; uint16_t* tSorted;       // tops, unsorted + rank -> index
   float *sCot, *sIDR, *sEr, *sU, *sV; uint32_t* sPos;   // tops in sorted order
   uint32_t* buckets;                                    // [nBuckets + 1]
-  Cand* pool; uint16_t* poolNext;                       // emission order, linked per owner
-  Cand* pool2;                                          // contiguous per owner
+  unsigned char* arena;
+  float* tCot; uint32_t* tSeq; uint16_t* tSorted;       // arena, phases 1-2
+  Cand* pool; uint16_t* poolNext; Cand* pool2;          // arena, phase 3
 };
 
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
+__host__ __device__ inline size_t seed_arena_bytes(uint32_t capB, uint32_t capT, uint32_t capPool) {
+  const size_t tops = align16(4ull * capT) * 2 + align16(2ull * capT);
+  const size_t pools = align16(sizeof(Cand) * (size_t)capPool) * 2 + align16(2ull * capPool);
+  const size_t tieB = align16(8ull * capB) + align16(2ull * capB) * 2;  // W + seqSorted + grpOf (bottoms)
+  size_t a = tops > pools ? tops : pools;
+  return a > tieB ? a : tieB;
+}
+
 __host__ __device__ inline size_t seed_smem_bytes(uint32_t capB, uint32_t capT, uint32_t capPool, uint32_t nBuckets) {
   size_t s = align16(sizeof(SeedShared));
   s += align16(4ull * capB) * 2 + align16(2ull * capB);
-  // region A: tops unsorted (cot, seq) + buckets, later reused by the linked pool
-  size_t a = align16(4ull * capT) * 2 + align16(4ull * (nBuckets + 1));
-  size_t a2 = align16(sizeof(Cand) * (size_t)capPool) + align16(2ull * capPool);
-  s += a > a2 ? a : a2;
-  s += align16(2ull * capT);
   s += align16(4ull * capT) * 6;
-  s += align16(sizeof(Cand) * (size_t)capPool);
+  s += align16(4ull * (nBuckets + 1));
+  s += seed_arena_bytes(capB, capT, capPool);
   return s;
 }
 
@@ -483,23 +496,21 @@ __device__ __forceinline__ SeedSmem carve_seed_smem(unsigned char* base, uint32_
   s.bCot = reinterpret_cast<float*>(q); q += align16(4ull * capB);
   s.bSeq = reinterpret_cast<uint32_t*>(q); q += align16(4ull * capB);
   s.bSorted = reinterpret_cast<uint16_t*>(q); q += align16(2ull * capB);
-  unsigned char* regionA = q;
-  s.tCot = reinterpret_cast<float*>(q); q += align16(4ull * capT);
-  s.tSeq = reinterpret_cast<uint32_t*>(q); q += align16(4ull * capT);
-  s.buckets = reinterpret_cast<uint32_t*>(q); q += align16(4ull * (nBuckets + 1));
-  const size_t a = (size_t)(q - regionA);
-  s.pool = reinterpret_cast<Cand*>(regionA);
-  s.poolNext = reinterpret_cast<uint16_t*>(regionA + align16(sizeof(Cand) * (size_t)capPool));
-  const size_t a2 = align16(sizeof(Cand) * (size_t)capPool) + align16(2ull * capPool);
-  q = regionA + (a > a2 ? a : a2);
-  s.tSorted = reinterpret_cast<uint16_t*>(q); q += align16(2ull * capT);
   s.sCot = reinterpret_cast<float*>(q); q += align16(4ull * capT);
   s.sIDR = reinterpret_cast<float*>(q); q += align16(4ull * capT);
   s.sEr = reinterpret_cast<float*>(q); q += align16(4ull * capT);
   s.sU = reinterpret_cast<float*>(q); q += align16(4ull * capT);
   s.sV = reinterpret_cast<float*>(q); q += align16(4ull * capT);
   s.sPos = reinterpret_cast<uint32_t*>(q); q += align16(4ull * capT);
-  s.pool2 = reinterpret_cast<Cand*>(q);
+  s.buckets = reinterpret_cast<uint32_t*>(q); q += align16(4ull * (nBuckets + 1));
+  s.arena = q;
+  s.tCot = reinterpret_cast<float*>(q); q += align16(4ull * capT);
+  s.tSeq = reinterpret_cast<uint32_t*>(q); q += align16(4ull * capT);
+  s.tSorted = reinterpret_cast<uint16_t*>(q);
+  q = s.arena;
+  s.pool = reinterpret_cast<Cand*>(q); q += align16(sizeof(Cand) * (size_t)capPool);
+  s.pool2 = reinterpret_cast<Cand*>(q); q += align16(sizeof(Cand) * (size_t)capPool);
+  s.poolNext = reinterpret_cast<uint16_t*>(q);
   return s;
 }
 
@@ -534,17 +545,36 @@ __device__ __forceinline__ void find_doublets(const SeedParams& p, SeedShared& s
   }
 }
 
-// Bucket sort of n (cot, seq) pairs: sorted[rank] = index, ordered by
-// (cot, seq).  Sets *tie when two neighbours have the same cot.
-__device__ __forceinline__ void block_sort_cot(const SeedParams& p, uint32_t n, const float* cot, const uint32_t* seq,
-                                               uint16_t* sorted, uint32_t* buckets, uint32_t* scratch, uint32_t* tie) {
-  const uint32_t nBk = p.nBuckets;
-  const float scale = (float)nBk / (2.0f * p.cfg.cotThetaMax);
+// Keys of the in-block bucket sort.  bucket() must be monotone in the order
+// and after(u, v) tells whether element u sorts strictly after element v.
+struct CotKey {  // order by (cotTheta, emission index)
+  const float* cot;
+  const uint32_t* seq;
+  float cotMax, scale;
+  int nBk;
+  __device__ __forceinline__ int bucket(uint32_t i) const { return cot_bucket(cot[i], cotMax, scale, nBk); }
+  __device__ __forceinline__ bool after(uint32_t u, uint32_t v) const {
+    const float cu = cot[u], cv = cot[v];
+    return cu > cv || (cu == cv && seq[u] > seq[v]);
+  }
+};
+struct SeqKey {  // order by emission index (unique)
+  const uint32_t* seq;
+  uint32_t total;
+  int nBk;
+  __device__ __forceinline__ int bucket(uint32_t i) const {
+    return (int)(((unsigned long long)seq[i] * (unsigned long long)nBk) / (unsigned long long)total);
+  }
+  __device__ __forceinline__ bool after(uint32_t u, uint32_t v) const { return seq[u] > seq[v]; }
+};
+
+// Bucket sort of n elements: sorted[rank] = element index.
+template <typename Key>
+__device__ __forceinline__ void block_bucket_sort(uint32_t n, const Key key, uint16_t* sorted, uint32_t* buckets,
+                                                  uint32_t nBk, uint32_t* scratch) {
   for (uint32_t i = threadIdx.x; i <= nBk; i += blockDim.x) buckets[i] = 0;
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-    atomicAdd(buckets + cot_bucket(cot[i], p.cfg.cotThetaMax, scale, (int)nBk), 1u);
-  }
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(buckets + key.bucket(i), 1u);
   __syncthreads();
   // exclusive scan of the bucket counts (in place), blockDim.x buckets per pass
   __shared__ uint32_t runCarry;
@@ -563,38 +593,93 @@ __device__ __forceinline__ void block_sort_cot(const SeedParams& p, uint32_t n, 
   }
   // scatter: after this loop buckets[b] is the END of bucket b
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const uint32_t b = (uint32_t)cot_bucket(cot[i], p.cfg.cotThetaMax, scale, (int)nBk);
-    sorted[atomicAdd(buckets + b, 1u)] = (uint16_t)i;
+    sorted[atomicAdd(buckets + key.bucket(i), 1u)] = (uint16_t)i;
   }
   __syncthreads();
-  // order every bucket by (cot, seq); buckets hold O(1) entries
+  // order every bucket; buckets hold O(1) entries
   for (uint32_t b = threadIdx.x; b < nBk; b += blockDim.x) {
     const uint32_t s = b == 0 ? 0u : buckets[b - 1], e = buckets[b];
     for (uint32_t i = s + 1; i < e; ++i) {
       const uint16_t v = sorted[i];
-      const float cv = cot[v];
-      const uint32_t sv = seq[v];
       uint32_t j = i;
-      while (j > s) {
-        const uint16_t u = sorted[j - 1];
-        const float cu = cot[u];
-        if (cu > cv || (cu == cv && seq[u] > sv)) {
-          sorted[j] = u;
-          --j;
-        } else {
-          break;
-        }
+      while (j > s && key.after(sorted[j - 1], v)) {
+        sorted[j] = sorted[j - 1];
+        --j;
       }
       sorted[j] = v;
-    }
-    for (uint32_t i = s + 1; i < e; ++i) {
-      if (cot[sorted[i]] == cot[sorted[i - 1]]) *tie = 1u;
     }
   }
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kSeedThreads) k_seed_middles(const __grid_constant__ SeedParams p) {
+// true (block-uniform) when two neighbours of the sorted list have equal keys
+__device__ __forceinline__ bool block_has_ties(uint32_t n, const float* cot, const uint16_t* sorted, uint32_t* flag) {
+  if (threadIdx.x == 0) *flag = 0;
+  __syncthreads();
+  bool t = false;
+  for (uint32_t i = threadIdx.x + 1; i < n; i += blockDim.x) t |= cot[sorted[i]] == cot[sorted[i - 1]];
+  if (t) *flag = 1;
+  __syncthreads();
+  const bool r = *flag != 0;
+  __syncthreads();
+  return r;
+}
+
+struct TieItem {
+  float key;
+  uint32_t val;  // element index | tie group (first canonical rank) << 16; group 0xFFFF = unique key
+};
+__device__ __forceinline__ bool tie_less(const TieItem& a, const TieItem& b) { return a.key < b.key; }
+__device__ __forceinline__ bool tie_flagged(const TieItem& a) { return (a.val >> 16) != 0xFFFFu; }
+
+// Exact order inside groups of equal cotTheta: the reference sorts the doublets
+// with the unstable std::ranges::sort (DoubletSeedFinder.hpp:94-104) starting
+// from the emission order.  `sorted` holds the canonical (cot, seq) order; the
+// pruned replay of libstdc++'s introsort (seed_math.h) run by one thread on the
+// emission-ordered copy W decides which member of a tie group takes which of the
+// group's slots.  seqSorted / grpOf are n-entry u16 scratch arrays.
+__device__ __forceinline__ void block_fix_ties(uint32_t n, const float* cot, const uint32_t* seq, uint32_t totalCand,
+                                               uint16_t* sorted, TieItem* W, uint16_t* seqSorted, uint16_t* grpOf,
+                                               uint32_t* buckets, uint32_t nBk, uint32_t* scratch) {
+  SeqKey sk{seq, totalCand > 0 ? totalCand : 1u, (int)nBk};
+  block_bucket_sort(n, sk, seqSorted, buckets, nBk, scratch);
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint16_t e = sorted[i];
+    const float c = cot[e];
+    const bool tp = i > 0 && cot[sorted[i - 1]] == c;
+    const bool tn = i + 1 < n && cot[sorted[i + 1]] == c;
+    uint16_t g = 0xFFFFu;
+    if (tp || tn) {
+      uint32_t q = i;
+      while (q > 0 && cot[sorted[q - 1]] == c) --q;
+      g = (uint16_t)q;
+    }
+    grpOf[e] = g;
+  }
+  __syncthreads();
+  for (uint32_t r = threadIdx.x; r < n; r += blockDim.x) {
+    const uint16_t e = seqSorted[r];
+    TieItem it;
+    it.key = cot[e];
+    it.val = (uint32_t)e | ((uint32_t)grpOf[e] << 16);
+    W[r] = it;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) std_sort_replay_ties(W, (int)n, tie_less, tie_flagged);
+  __syncthreads();
+  // member k (in W order) of group q goes to canonical slot q + k
+  for (uint32_t r = threadIdx.x; r < n; r += blockDim.x) {
+    const TieItem it = W[r];
+    const uint32_t g = it.val >> 16;
+    if (g == 0xFFFFu) continue;
+    uint32_t before = 0;
+    for (uint32_t q = 0; q < r; ++q) before += (W[q].val >> 16) == g ? 1u : 0u;
+    sorted[g + before] = (uint16_t)(it.val & 0xFFFFu);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSeedThreads, 2) k_seed_middles(const __grid_constant__ SeedParams p) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const SeedSmem S = carve_seed_smem(smemRaw, p.capB, p.capT, p.capPool, p.nBuckets);
   SeedShared& sh = *S.sh;
@@ -606,10 +691,13 @@ __global__ void __launch_bounds__(kSeedThreads) k_seed_middles(const __grid_cons
 
   for (;;) {
     __syncthreads();
-    if (tid == 0) sh.w = atomicAdd(p.workCounter, 1u);
+    if (tid == 0) {
+      const uint32_t item = atomicAdd(p.workCounter, 1u);
+      sh.w = item < nWork ? (p.workList != nullptr ? p.workList[item] : item) : 0xFFFFFFFFu;
+    }
     __syncthreads();
     const uint32_t w = sh.w;
-    if (w >= nWork) break;
+    if (w == 0xFFFFFFFFu) break;
 
     // ---- phase 0: middle, r windows ------------------------------------
     const uint32_t m = __ldg(p.workPos + w);
@@ -642,8 +730,8 @@ __global__ void __launch_bounds__(kSeedThreads) k_seed_middles(const __grid_cons
         const uint32_t s = first_true(trim, b1, [&](uint32_t i) { return fsub(rM, ldg2(p.pZR + i).y) <= cfg.dRMaxB; });
         const uint32_t e = first_true(s, b1, [&](uint32_t i) { return fsub(rM, ldg2(p.pZR + i).y) < cfg.dRMinB; });
         sh.winBs[tid] = s; sh.winBe[tid] = e;
-      } else if (tid >= 32 && tid < 32 + nTop) {
-        const uint32_t k = tid - 32;
+      } else if (tid >= (uint32_t)kMaxNeighborBins && tid < (uint32_t)kMaxNeighborBins + nTop) {
+        const uint32_t k = tid - (uint32_t)kMaxNeighborBins;
         const uint32_t bin = __ldg(p.topBins + topBeg + k);
         const uint32_t b0 = bs[bin], b1 = bs[bin + 1];
         const float trimValue = fadd(firstMiddleR, cfg.dRMinT);
@@ -679,14 +767,32 @@ __global__ void __launch_bounds__(kSeedThreads) k_seed_middles(const __grid_cons
     if (nB == 0 || nT > p.capT || nB > p.capB) {
       if (tid == 0) {
         p.slotCount[w] = 0;
-        if (nB != 0) atomicOr(p.status, kStatusOverflowDoublets);
+        if (nB != 0) {  // does not fit this launch's scratch: hand over to the large-capacity launch
+          if (p.overflowList != nullptr) {
+            p.overflowList[atomicAdd(p.overflowCount, 1u)] = w;
+            sh.cnt[kCntMiddles] -= 1;  // counted again by the launch that completes it
+          } else {
+            atomicOr(p.status, kStatusOverflowDoublets);
+          }
+        }
       }
       continue;
     }
 
-    // ---- phase 2: order both lists by (cotTheta, emission index) ---------
-    block_sort_cot(p, nT, S.tCot, S.tSeq, S.tSorted, S.buckets, sh.scratch, &sh.tie);
-    block_sort_cot(p, nB, S.bCot, S.bSeq, S.bSorted, S.buckets, sh.scratch, &sh.tie);
+    // ---- phase 2: order both lists like DoubletSeedFinder.hpp:94-104 -------
+    const float bkScale = (float)p.nBuckets / (2.0f * cfg.cotThetaMax);
+    {
+      CotKey tk{S.tCot, S.tSeq, cfg.cotThetaMax, bkScale, (int)p.nBuckets};
+      block_bucket_sort(nT, tk, S.tSorted, S.buckets, p.nBuckets, sh.scratch);
+      const bool tieT = block_has_ties(nT, S.tCot, S.tSorted, &sh.tieTmp);
+      if (tieT && tid == 0) sh.tie = 1;
+      if (tieT && p.exactTies && nT > 16) {
+        // scratch inside the sorted-top arrays, which are written only after this
+        block_fix_ties(nT, S.tCot, S.tSeq, sh.winTp[nTop], S.tSorted, reinterpret_cast<TieItem*>(S.sCot),
+                       reinterpret_cast<uint16_t*>(S.sEr), reinterpret_cast<uint16_t*>(S.sU), S.buckets,
+                       p.nBuckets, sh.scratch);
+      }
+    }
     // tops: full records in sorted order (recomputed from the space points)
     for (uint32_t t = tid; t < nT; t += blockDim.x) {
       const uint32_t idx = S.tSorted[t];
@@ -699,7 +805,23 @@ __global__ void __launch_bounds__(kSeedThreads) k_seed_middles(const __grid_cons
       S.sCot[t] = rec.cotTheta; S.sIDR[t] = rec.iDeltaR; S.sEr[t] = rec.er; S.sU[t] = rec.u; S.sV[t] = rec.v;
       S.sPos[t] = pos;
     }
-    __syncthreads();  // region A (tCot/tSeq/buckets) is dead from here on: the pool lives there
+    __syncthreads();  // tCot / tSeq are dead from here on
+    {
+      CotKey bk{S.bCot, S.bSeq, cfg.cotThetaMax, bkScale, (int)p.nBuckets};
+      block_bucket_sort(nB, bk, S.bSorted, S.buckets, p.nBuckets, sh.scratch);
+      const bool tieB = block_has_ties(nB, S.bCot, S.bSorted, &sh.tieTmp);
+      if (tieB && tid == 0) sh.tie = 1;
+      if (tieB && p.exactTies && nB > 16) {
+        // scratch in the arena (tCot / tSeq / tSorted are dead, the pools not yet alive)
+        unsigned char* a = S.arena;
+        TieItem* W = reinterpret_cast<TieItem*>(a);
+        uint16_t* seqSorted = reinterpret_cast<uint16_t*>(a + align16(8ull * p.capB));
+        uint16_t* grpOf = reinterpret_cast<uint16_t*>(a + align16(8ull * p.capB) + align16(2ull * p.capB));
+        block_fix_ties(nB, S.bCot, S.bSeq, sh.winBp[nBot], S.bSorted, W, seqSorted, grpOf, S.buckets, p.nBuckets,
+                       sh.scratch);
+      }
+    }
+    __syncthreads();  // the arena now belongs to the candidate pools
 
     // ---- phase 3: triplets + filter, one thread per bottom ---------------
     const MiddleSp mid = sh.mid;
@@ -780,7 +902,15 @@ __global__ void __launch_bounds__(kSeedThreads) k_seed_middles(const __grid_cons
       __syncthreads();
       const uint32_t poolCount = sh.poolCount;
       if (poolCount > p.capPool) {
-        if (tid == 0) { atomicOr(p.status, kStatusOverflowPool); sh.bad = 1; }
+        if (tid == 0) {
+          sh.bad = 1;
+          if (p.overflowList != nullptr) {
+            p.overflowList[atomicAdd(p.overflowCount, 1u)] = w;
+            sh.cnt[kCntMiddles] -= 1;
+          } else {
+            atomicOr(p.status, kStatusOverflowPool);
+          }
+        }
         __syncthreads();
         break;
       }
@@ -870,7 +1000,7 @@ __global__ void __launch_bounds__(kSeedThreads) k_seed_middles(const __grid_cons
         t += __shfl_down_sync(0xffffffffu, t, d);
         c += __shfl_down_sync(0xffffffffu, c, d);
       }
-      if ((tid & 31) == 0) {
+      if ((tid & 31) == 0 && !sh.bad) {
         atomicAdd(&sh.cnt[kCntTripletTests], t);
         atomicAdd(&sh.cnt[kCntCandidates], c);
       }
@@ -896,10 +1026,12 @@ __global__ void __launch_bounds__(kSeedThreads) k_seed_middles(const __grid_cons
         }
       }
       p.slotCount[w] = nOut;
-      sh.cnt[kCntBottomDoublets] += nB;
-      sh.cnt[kCntTopDoublets] += nT;
-      sh.cnt[kCntSeeds] += nOut;
-      sh.cnt[kCntTieMiddles] += sh.tie;
+      if (!sh.bad) {
+        sh.cnt[kCntBottomDoublets] += nB;
+        sh.cnt[kCntTopDoublets] += nT;
+        sh.cnt[kCntSeeds] += nOut;
+        sh.cnt[kCntTieMiddles] += sh.tie;
+      }
     }
   }
   __syncthreads();

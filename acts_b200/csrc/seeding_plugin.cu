@@ -72,17 +72,20 @@ struct b200seed_handle {
   cudaStream_t stream = nullptr;
   int smCount = 0, ccMajor = 0, ccMinor = 0;
   // engine tunables
-  uint32_t capB = 2048, capT = 1024, capPool = 1024, nBuckets = 2048;
+  // per-middle shared-memory capacities: tier 0 takes every middle at 2 blocks
+  // per SM, middles that do not fit are re-queued to tier 1 (1 block per SM)
+  uint32_t capB[2] = {2304, 4608}, capT[2] = {1792, 3584}, capPool[2] = {896, 1792};
+  uint32_t nBuckets = 2048;
   uint32_t sortSmemCap = 4096;
   int exactTies = 1;
-  int seedBlocksPerSM = 1;
-  size_t seedSmemBytes = 0;
+  int seedBlocksPerSM[2] = {1, 1};
+  size_t seedSmemBytes[2] = {0, 0};
   // constant tables
   DevBuf navBins, botOffsets, botBins, topOffsets, topBins;
   // per-batch workspaces
   DevBuf inOffsets, inX, inY, inZ, inR, inVarZ, inVarR;  // staging of host inputs
   DevBuf binOf, binCount, binStart, binCursor, tmpIdx, pIdx, pXY, pZR, pVar, sortScratch;
-  DevBuf midLo, midCount, workStart, workPos, workEG, workCounter;
+  DevBuf midLo, midCount, workStart, workPos, workEG, workCounter, overflowList;
   DevBuf slotB, slotM, slotT, slotQ, slotZ, slotCount, seedStart, tileSums, tilePrefix;
   DevBuf outB, outM, outT, outQ, outZ, seedOffsets;  // device outputs of the host API
   DevBuf counters, status, zWin;
@@ -97,6 +100,9 @@ struct b200seed_handle {
   b200seed_counters lastCounters{};
   bool pending = false;
   uint64_t launches = 0;
+  // stage boundaries of the last call: start | grid | work list | seeding | compaction
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  float stageMs[4] = {0, 0, 0, 0};
 };
 
 namespace {
@@ -127,7 +133,8 @@ int ensure_workspace(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal) {
   CUDA_TRY(h->workStart.reserve((nNavAll + 1) * 4));
   CUDA_TRY(h->workPos.reserve(nT * 4));
   CUDA_TRY(h->workEG.reserve(nT * 4));
-  CUDA_TRY(h->workCounter.reserve(16));
+  CUDA_TRY(h->workCounter.reserve(32));
+  CUDA_TRY(h->overflowList.reserve(nT * 4));
   CUDA_TRY(h->slotB.reserve(nT * K * 4));
   CUDA_TRY(h->slotM.reserve(nT * K * 4));
   CUDA_TRY(h->slotT.reserve(nT * K * 4));
@@ -160,10 +167,11 @@ int enqueue(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal, const uint32_
 
   CUDA_TRY(cudaMemsetAsync(h->binCount.ptr, 0, ((size_t)nBinsAll + 1) * 4, s));
   CUDA_TRY(cudaMemsetAsync(h->binCursor.ptr, 0, ((size_t)nBinsAll + 1) * 4, s));
-  CUDA_TRY(cudaMemsetAsync(h->workCounter.ptr, 0, 16, s));
+  CUDA_TRY(cudaMemsetAsync(h->workCounter.ptr, 0, 32, s));
   CUDA_TRY(cudaMemsetAsync(h->counters.ptr, 0, kCntSlots * 8, s));
   CUDA_TRY(cudaMemsetAsync(h->status.ptr, 0, 16, s));
 
+  CUDA_TRY(cudaEventRecord(h->ev[0], s));
   GridParams gp{};
   gp.cfg = plan.dev;
   gp.nEvents = nEvents; gp.nTotal = nTotal; gp.nBins = nBins;
@@ -198,6 +206,7 @@ int enqueue(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal, const uint32_
     launches += 2;
   }
 
+  CUDA_TRY(cudaEventRecord(h->ev[1], s));
   WorkParams wp{};
   wp.cfg = plan.dev;
   wp.nEvents = nEvents; wp.nBins = nBins; wp.nNav = nNav;
@@ -214,6 +223,7 @@ int enqueue(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal, const uint32_
   k_fill_work<<<(nNavAll * 32 + 255) / 256, 256, 0, s>>>(wp);
   launches += 3;
 
+  CUDA_TRY(cudaEventRecord(h->ev[2], s));
   SeedParams sp{};
   sp.cfg = plan.dev;
   if (nZWin > 0) sp.cfg.doubletCuts = kCutsVertexZ;  // takes the experimentCuts slot, .cpp:291-296
@@ -230,17 +240,35 @@ int enqueue(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal, const uint32_
   sp.zWinLo = h->zWin.as<float>();
   sp.zWinHi = h->zWin.as<float>() + kMaxZWindows;
   sp.nZWin = nZWin;
-  sp.workCounter = h->workCounter.as<uint32_t>();
   sp.slotB = h->slotB.as<uint32_t>(); sp.slotM = h->slotM.as<uint32_t>(); sp.slotT = h->slotT.as<uint32_t>();
   sp.slotQ = h->slotQ.as<float>(); sp.slotZ = h->slotZ.as<float>();
   sp.slotCount = h->slotCount.as<uint32_t>();
   sp.seedsPerMiddle = std::max<uint32_t>(plan.seedsPerMiddle, 1);
-  sp.capB = h->capB; sp.capT = h->capT; sp.capPool = h->capPool; sp.nBuckets = h->nBuckets;
+  sp.nBuckets = h->nBuckets;
+  sp.exactTies = h->exactTies;
   sp.counters = gp.counters;
   sp.status = gp.status;
-  k_seed_middles<<<h->smCount * h->seedBlocksPerSM, kSeedThreads, h->seedSmemBytes, s>>>(sp);
-  ++launches;
+  // workCounter words: [0] tier-0 ticket, [1] overflow count, [2] tier-1 ticket
+  uint32_t* wc = h->workCounter.as<uint32_t>();
+  // tier 0: every middle
+  sp.workCounter = wc + 0;
+  sp.workList = nullptr;
+  sp.overflowList = h->overflowList.as<uint32_t>();
+  sp.overflowCount = wc + 1;
+  sp.capB = h->capB[0]; sp.capT = h->capT[0]; sp.capPool = h->capPool[0];
+  k_seed_middles<<<h->smCount * h->seedBlocksPerSM[0], kSeedThreads, h->seedSmemBytes[0], s>>>(sp);
+  // tier 1: the middles that did not fit, with the large scratch
+  sp.workCounter = wc + 2;
+  sp.workList = h->overflowList.as<uint32_t>();
+  sp.nWorkPtr = wc + 1;
+  sp.overflowList = nullptr;
+  sp.overflowCount = nullptr;
+  sp.capB = h->capB[1]; sp.capT = h->capT[1]; sp.capPool = h->capPool[1];
+  k_seed_middles<<<h->smCount * h->seedBlocksPerSM[1], kSeedThreads, h->seedSmemBytes[1], s>>>(sp);
+  sp.nWorkPtr = wp.workStart + nNavAll;
+  launches += 2;
 
+  CUDA_TRY(cudaEventRecord(h->ev[3], s));
   CompactParams cp{};
   cp.nWorkPtr = sp.nWorkPtr;
   cp.slotCount = sp.slotCount;
@@ -262,6 +290,7 @@ int enqueue(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal, const uint32_
   k_compact_seeds<<<nTiles, 256, 0, s>>>(cp);
   k_event_offsets<<<1, 256, 0, s>>>(cp);
   launches += 4;
+  CUDA_TRY(cudaEventRecord(h->ev[4], s));
   CUDA_TRY(cudaGetLastError());
 
   // results the host needs after the sync
@@ -280,6 +309,10 @@ int enqueue(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal, const uint32_
 int finish(b200seed_handle* h, cudaStream_t s, b200seed_seeds* out) {
   CUDA_TRY(cudaStreamSynchronize(s));
   h->pending = false;
+  for (int i = 0; i < 4; ++i) {
+    if (cudaEventElapsedTime(&h->stageMs[i], h->ev[i], h->ev[i + 1]) != cudaSuccess) h->stageMs[i] = 0.f;
+  }
+  (void)cudaGetLastError();
   b200seed_counters& c = h->lastCounters;
   c.nSpacePoints = h->lastTotal;
   c.nInGrid = *reinterpret_cast<uint32_t*>(h->hCounters + kCntSlots);
@@ -295,9 +328,9 @@ int finish(b200seed_handle* h, cudaStream_t s, b200seed_seeds* out) {
   const int st = *h->hStatus;
   if (st & (kStatusOverflowDoublets | kStatusOverflowPool)) {
     return fail(B200SEED_ERR_OVERFLOW,
-                "per-middle scratch exhausted (doublets > " + std::to_string(h->capB) + "/" +
-                    std::to_string(h->capT) + " or candidates > " + std::to_string(h->capPool) +
-                    "); raise B200SEED_CAPB / B200SEED_CAPT / B200SEED_CAPPOOL");
+                "per-middle scratch exhausted even in the large tier (doublets > " + std::to_string(h->capB[1]) +
+                    "/" + std::to_string(h->capT[1]) + " or candidates per round > " +
+                    std::to_string(h->capPool[1]) + "); raise B200SEED_CAP{B,T,POOL}_LARGE");
   }
   if (*h->hSeedTotal > h->lastCapacity) {
     return fail(B200SEED_ERR_CAPACITY, "seed buffers too small: need " + std::to_string(*h->hSeedTotal));
@@ -403,27 +436,38 @@ int b200seed_create(const b200seed_config* cfg, int device, b200seed_handle** ou
   h->plan.info.ccMajor = h->ccMajor;
   h->plan.info.ccMinor = h->ccMinor;
   CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 5; ++i) CREATE_TRY(cudaEventCreate(&h->ev[i]));
   CREATE_TRY(cudaMallocHost(&h->hCounters, (kCntSlots + 2) * 8));
   CREATE_TRY(cudaMallocHost(&h->hStatus, 16));
   CREATE_TRY(cudaMallocHost(&h->hSeedTotal, 16));
 
-  h->capB = env_u32("B200SEED_CAPB", h->capB);
-  h->capT = env_u32("B200SEED_CAPT", h->capT);
-  h->capPool = env_u32("B200SEED_CAPPOOL", h->capPool);
+  h->capB[0] = env_u32("B200SEED_CAPB", h->capB[0]);
+  h->capT[0] = env_u32("B200SEED_CAPT", h->capT[0]);
+  h->capPool[0] = env_u32("B200SEED_CAPPOOL", h->capPool[0]);
+  h->capB[1] = env_u32("B200SEED_CAPB_LARGE", h->capB[1]);
+  h->capT[1] = env_u32("B200SEED_CAPT_LARGE", h->capT[1]);
+  h->capPool[1] = env_u32("B200SEED_CAPPOOL_LARGE", h->capPool[1]);
   h->nBuckets = env_u32("B200SEED_BUCKETS", h->nBuckets);
   h->exactTies = (int)env_u32("B200SEED_EXACT_TIES", 1);
-  if (h->capB > 65535 || h->capT > 65535 || h->capPool > 65534) {
-    return cleanup(fail(B200SEED_ERR_INVALID_ARGUMENT, "B200SEED_CAP* must stay below 65535"));
+  size_t maxSmem = 0;
+  for (int t = 0; t < 2; ++t) {
+    if (h->capB[t] > 65534 || h->capT[t] > 65534 || h->capPool[t] > 65534 || h->capB[t] < 32 || h->capT[t] < 32 ||
+        h->capPool[t] < 32) {
+      return cleanup(fail(B200SEED_ERR_INVALID_ARGUMENT, "B200SEED_CAP* must lie in [32, 65534]"));
+    }
+    h->seedSmemBytes[t] = seed_smem_bytes(h->capB[t], h->capT[t], h->capPool[t], h->nBuckets);
+    if (h->seedSmemBytes[t] > (size_t)prop.sharedMemPerBlockOptin) {
+      return cleanup(fail(B200SEED_ERR_INVALID_ARGUMENT, "per-middle scratch does not fit shared memory"));
+    }
+    maxSmem = std::max(maxSmem, h->seedSmemBytes[t]);
   }
-  h->seedSmemBytes = seed_smem_bytes(h->capB, h->capT, h->capPool, h->nBuckets);
-  if (h->seedSmemBytes > (size_t)prop.sharedMemPerBlockOptin) {
-    return cleanup(fail(B200SEED_ERR_INVALID_ARGUMENT, "per-middle scratch does not fit shared memory"));
-  }
-  CREATE_TRY(cudaFuncSetAttribute(k_seed_middles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seedSmemBytes));
+  CREATE_TRY(cudaFuncSetAttribute(k_seed_middles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem));
   CREATE_TRY(cudaFuncSetAttribute(k_sort_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->sortSmemCap * 8)));
-  int blocksPerSM = 0;
-  CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_seed_middles, kSeedThreads, h->seedSmemBytes));
-  h->seedBlocksPerSM = std::max(1, blocksPerSM);
+  for (int t = 0; t < 2; ++t) {
+    int blocksPerSM = 0;
+    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_seed_middles, kSeedThreads, h->seedSmemBytes[t]));
+    h->seedBlocksPerSM[t] = std::max(1, blocksPerSM);
+  }
 
   int rc = upload(h->navBins, h->plan.navBins, h->stream);
   if (rc == B200SEED_OK) rc = upload(h->botOffsets, h->plan.botOffsets, h->stream);
@@ -448,10 +492,13 @@ void b200seed_destroy(b200seed_handle* h) {
                     &h->inX, &h->inY, &h->inZ, &h->inR, &h->inVarZ, &h->inVarR, &h->binOf, &h->binCount,
                     &h->binStart, &h->binCursor, &h->tmpIdx, &h->pIdx, &h->pXY, &h->pZR, &h->pVar,
                     &h->sortScratch, &h->midLo, &h->midCount, &h->workStart, &h->workPos, &h->workEG,
-                    &h->workCounter, &h->slotB, &h->slotM, &h->slotT, &h->slotQ, &h->slotZ, &h->slotCount,
+                    &h->workCounter, &h->overflowList, &h->slotB, &h->slotM, &h->slotT, &h->slotQ, &h->slotZ, &h->slotCount,
                     &h->seedStart, &h->tileSums, &h->tilePrefix, &h->outB, &h->outM, &h->outT, &h->outQ,
                     &h->outZ, &h->seedOffsets, &h->counters, &h->status, &h->zWin}) {
     b->release();
+  }
+  for (int i = 0; i < 5; ++i) {
+    if (h->ev[i] != nullptr) cudaEventDestroy(h->ev[i]);
   }
   if (h->hCounters != nullptr) cudaFreeHost(h->hCounters);
   if (h->hStatus != nullptr) cudaFreeHost(h->hStatus);
@@ -468,6 +515,15 @@ int b200seed_get_info(const b200seed_handle* h, b200seed_info* info) {
 int b200seed_get_counters(const b200seed_handle* h, b200seed_counters* c) {
   if (h == nullptr || c == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL argument");
   *c = h->lastCounters;
+  return B200SEED_OK;
+}
+
+// GPU time of the four stages of the last completed call, in milliseconds:
+// [0] grid (bin, scan, scatter, sort + packed copy), [1] middle work list,
+// [2] seeding kernel (both capacity tiers), [3] ordered seed compaction.
+int b200seed_get_stage_times(const b200seed_handle* h, float* ms) {
+  if (h == nullptr || ms == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL argument");
+  for (int i = 0; i < 4; ++i) ms[i] = h->stageMs[i];
   return B200SEED_OK;
 }
 

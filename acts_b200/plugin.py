@@ -23,6 +23,7 @@ LIB_PATH = os.path.join(_HERE, "libacts_b200_seeding.so")
 EXPORTED_SYMBOLS = [
     "b200seed_config_init", "b200seed_plan_info", "b200seed_plan_tables", "b200seed_create",
     "b200seed_destroy", "b200seed_last_error", "b200seed_get_info", "b200seed_get_counters",
+    "b200seed_get_stage_times",
     "b200seed_run", "b200seed_run_with_phi", "b200seed_run_batch", "b200seed_run_batch_device",
     "b200seed_sync", "b200seed_debug_grid", "b200seed_debug_doublets", "b200seed_debug_atan2f",
 ]
@@ -54,6 +55,7 @@ def lib():
         L.b200seed_destroy.argtypes = [vp]
         L.b200seed_get_info.argtypes = [vp, C.POINTER(Info)]
         L.b200seed_get_counters.argtypes = [vp, C.POINTER(Counters)]
+        L.b200seed_get_stage_times.argtypes = [vp, vp]
         L.b200seed_run.argtypes = [vp, u32] + [f32p] * 6 + [u32, f32p, f32p, C.POINTER(Seeds)]
         L.b200seed_run_with_phi.argtypes = [vp, u32] + [f32p] * 7 + [C.POINTER(Seeds)]
         L.b200seed_run_batch.argtypes = [vp, u32, vp] + [f32p] * 6 + [vp, C.POINTER(Seeds)]
@@ -137,6 +139,11 @@ class SeedingEngine:
         c = Counters()
         _check(lib().b200seed_get_counters(self._h, C.byref(c)))
         return c.as_dict()
+
+    def stage_times_ms(self) -> dict:
+        ms = np.zeros(4, dtype=np.float32)
+        _check(lib().b200seed_get_stage_times(self._h, _p(ms)))
+        return {"grid": float(ms[0]), "work": float(ms[1]), "seed": float(ms[2]), "compact": float(ms[3])}
 
     @staticmethod
     def _cols(ev):

@@ -1,0 +1,32 @@
+"""Event sharding across GPUs.
+
+Events are independent (one WhiteBoard per event in the reference's Sequencer,
+Examples/Framework/src/Framework/Sequencer.cpp:495-501), so an N-GPU job gives
+event ``e`` to rank ``e mod N``; every rank runs whole events on its own device
+and only the per-event results are gathered on the host.  No device collective
+is on the data path.
+"""
+from __future__ import annotations
+
+
+def events_of_rank(n_events: int, rank: int, world: int) -> list[int]:
+    return list(range(rank, n_events, world))
+
+
+def gather_seed_counts(local_counts: dict[int, int], n_events: int, group=None) -> list[int]:
+    """All ranks contribute {event: nSeeds}; returns the per-event list on every rank
+    (torch.distributed object gather over the host, gloo or nccl backend)."""
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        merged = dict(local_counts)
+    else:
+        parts = [None] * dist.get_world_size(group)
+        dist.all_gather_object(parts, local_counts, group=group)
+        merged = {}
+        for p in parts:
+            merged.update(p)
+    missing = [e for e in range(n_events) if e not in merged]
+    if missing:
+        raise RuntimeError(f"events without a result: {missing[:8]}")
+    return [merged[e] for e in range(n_events)]

@@ -279,6 +279,11 @@ int b200seed_run_batch_device(b200seed_handle* h, uint32_t nEvents,
 /* Wait for the last *_device call; fills out->size, returns deferred errors. */
 int b200seed_sync(b200seed_handle* h, b200seed_seeds* out);
 
+/* GPU time of the stages of the last completed call, milliseconds (CUDA events
+ * on the launching stream): ms[0] grid build, ms[1] middle work list,
+ * ms[2] seeding kernel, ms[3] ordered seed compaction. */
+int b200seed_get_stage_times(const b200seed_handle* h, float* ms);
+
 /* ---- stage-level introspection (parity tests of the grid / doublet stages) */
 
 /* After a run: the packed, bin-ordered, r-sorted space point copy of the LAST

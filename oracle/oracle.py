@@ -67,6 +67,7 @@ def lib():
         L.oracle_result_num_seeds.restype = C.c_uint64
         L.oracle_result_seeds.argtypes = [C.c_void_p] * 6
         L.oracle_result_counters.argtypes = [C.c_void_p, C.POINTER(OracleCounters)]
+        L.oracle_result_histograms.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_result_grid_size.argtypes = [C.c_void_p]
         L.oracle_result_grid_size.restype = C.c_uint64
         L.oracle_result_grid.argtypes = [C.c_void_p] * 10
@@ -75,7 +76,7 @@ def lib():
         L.oracle_result_dump_doublets.argtypes = [C.c_void_p]
         L.oracle_result_dump_doublets.restype = C.c_uint64
         L.oracle_result_dump.argtypes = [C.c_void_p] * 12
-        L.oracle_run_many.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p]
+        L.oracle_run_many.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 7 + [C.c_int, C.c_uint32, C.c_void_p]
         L.oracle_run_many.restype = C.c_int64
         _lib = L
     return _lib
@@ -163,6 +164,9 @@ class Oracle:
             cnt = OracleCounters()
             lib().oracle_result_counters(res, C.byref(cnt))
             out["counters"] = cnt.as_dict()
+            hist = np.zeros(96, np.uint64)
+            lib().oracle_result_histograms(res, _p(hist))
+            out["histograms"] = {"bottoms/128": hist[:32].copy(), "tops/128": hist[32:64].copy(), "candPerRound/32": hist[64:].copy()}
             if want_grid or dump_doublets:
                 ng = lib().oracle_result_grid_size(res)
                 nb = self.info().nGlobalBins
@@ -186,12 +190,13 @@ class Oracle:
         finally:
             lib().oracle_result_free(res)
 
-    def run_many(self, cols: dict, offsets: np.ndarray, n_threads: int = 1):
-        """Timed-baseline entry: returns per-event seed counts."""
+    def run_many(self, cols: dict, offsets: np.ndarray, n_threads: int = 1, nav_stride: int = 1):
+        """Timed-baseline entry: returns per-event seed counts.  ``nav_stride`` > 1
+        seeds only every nav_stride-th middle bin (bounded sample of the event)."""
         offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
         arrs = [np.ascontiguousarray(cols[k], dtype=np.float32) for k in ("x", "y", "z", "r", "varZ", "varR")]
         counts = np.zeros(offsets.size - 1, dtype=np.uint64)
-        tot = lib().oracle_run_many(self._h, offsets.size - 1, _p(offsets), *[_p(a) for a in arrs], n_threads, _p(counts))
+        tot = lib().oracle_run_many(self._h, offsets.size - 1, _p(offsets), *[_p(a) for a in arrs], n_threads, nav_stride, _p(counts))
         if tot < 0:
             raise OracleError(-1, "oracle_run_many failed")
         return counts

@@ -449,6 +449,8 @@ struct Counters {
                 nWeightTieMiddles = 0, maxBottoms = 0, maxTops = 0,
                 maxCandidatesPerBottom = 0, maxCandidatesPerMiddle = 0,
                 maxBinSize = 0;
+  // per-middle size histograms (bucket width 128, last bucket = overflow)
+  std::uint64_t histBottoms[32] = {0}, histTops[32] = {0}, histCandRound[32] = {0};
 };
 
 struct Seed {
@@ -477,6 +479,9 @@ struct Event {
   ZWindows zw;
   int sortMode = kFaithful;
   const float* phiOverride = nullptr;  // optional precomputed phi (tests)
+  // bounded sampling for the timed baseline: only navigation entries g with
+  // g % navStride == navPhase are seeded (the grid is always built in full)
+  std::uint32_t navStride = 1, navPhase = 0;
 
   Packed sp;
   Counters cnt;
@@ -1100,20 +1105,31 @@ void seedsForMiddle(Event& ev, DoubletCuts cuts, Index m,
     ev.cnt.nCotTieMiddles += tie ? 1 : 0;
   }
 
+  ev.cnt.histBottoms[std::min<std::size_t>(31, ev.bottomDoublets.size() / 128)]++;
+  ev.cnt.histTops[std::min<std::size_t>(31, ev.topDoublets.size() / 128)]++;
   std::size_t topBegin = 0;
   const std::size_t topEnd = ev.sortedTops.size();
   std::uint64_t candThisMiddle = 0;
+  std::uint64_t candThisRound = 0, bottomInRound = 0;
   for (const IndexAndCotTheta& b : ev.sortedBottoms) {
+    if (bottomInRound == 256) {
+      ev.cnt.histCandRound[std::min<std::uint64_t>(31, candThisRound / 32)]++;
+      bottomInRound = 0;
+      candThisRound = 0;
+    }
+    ++bottomInRound;
     if (topBegin == topEnd) break;
     ev.topCandidates.clear();
     createTripletTopCandidates(ev, m, b.index, topBegin, topEnd);
     ev.cnt.nCandidates += ev.topCandidates.size();
     candThisMiddle += ev.topCandidates.size();
+    candThisRound += ev.topCandidates.size();
     ev.cnt.maxCandidatesPerBottom =
         std::max<std::uint64_t>(ev.cnt.maxCandidatesPerBottom, ev.topCandidates.size());
     filterTripletTopCandidates(ev, m, b.index);
   }
   ev.cnt.maxCandidatesPerMiddle = std::max(ev.cnt.maxCandidatesPerMiddle, candThisMiddle);
+  ev.cnt.histCandRound[std::min<std::uint64_t>(31, candThisRound / 32)]++;
   filterTripletsMiddleFixed(ev);
 }
 
@@ -1160,11 +1176,13 @@ void runEvent(Event& ev) {
   ev.rMaxSeedConf = 0;
 
   std::vector<std::pair<Index, Index>> bottomRanges, topRanges;
+  std::uint32_t navIndex = 0;
   // BinnedGroupIterator (GridIterator.ipp:228-242): phi outermost, then z in
   // navigation order, then r; empty middle bins are skipped.
   for (std::size_t phiLoc : s.navPhi) {
     for (std::size_t zLoc : s.navZ) {
       for (std::size_t rLoc : s.navR) {
+        if ((navIndex++ % ev.navStride) != ev.navPhase) continue;
         const std::size_t middleBin = (phiLoc * (s.nZ + 2) + zLoc) * (s.nR + 2) + rLoc;
         const auto middleRange = p.binRange[middleBin];
         if (middleRange.first == middleRange.second) continue;
@@ -1421,6 +1439,15 @@ void oracle_result_counters(const oracle_event_result* r, oracle_counters* c) {
         k.nCotTieMiddles, k.nCurvTieGroups, k.nWeightTieMiddles, k.maxBottoms,
         k.maxTops, k.maxCandidatesPerBottom, k.maxCandidatesPerMiddle, k.maxBinSize};
 }
+// histograms: bottoms / tops per middle (bucket 128), candidates per round of
+// 256 cotTheta-sorted bottoms (bucket 32); 32 buckets each
+void oracle_result_histograms(const oracle_event_result* r, std::uint64_t* out) {
+  for (int i = 0; i < 32; ++i) {
+    out[i] = r->ev.cnt.histBottoms[i];
+    out[32 + i] = r->ev.cnt.histTops[i];
+    out[64 + i] = r->ev.cnt.histCandRound[i];
+  }
+}
 std::uint64_t oracle_result_grid_size(const oracle_event_result* r) { return r->ev.sp.copiedFrom.size(); }
 void oracle_result_grid(const oracle_event_result* r, std::uint32_t* copiedFrom, float* x,
                         float* y, float* z, float* rr, float* varZ, float* varR,
@@ -1465,11 +1492,13 @@ void oracle_result_dump(const oracle_event_result* r, std::uint32_t* middlePos,
 // events (Examples/Framework/src/Framework/Sequencer.cpp:472-475), each with
 // its own scratch.  Returns the total number of seeds (so the work cannot be
 // optimised away); per-event seed counts go to seedCounts when not NULL.
+// navStride > 1 seeds only every navStride-th middle bin of an event (a bounded
+// sample: 1/navStride of the event's seeding work, grid build in full).
 std::int64_t oracle_run_many(const oracle_handle* h, std::uint32_t nEvents,
                              const std::uint32_t* spOffsets, const float* x,
                              const float* y, const float* z, const float* r,
                              const float* varZ, const float* varR, int nThreads,
-                             std::uint64_t* seedCounts) {
+                             std::uint32_t navStride, std::uint64_t* seedCounts) {
   std::atomic<std::uint32_t> next{0};
   std::atomic<std::int64_t> total{0};
   std::atomic<bool> failed{false};
@@ -1484,6 +1513,8 @@ std::int64_t oracle_run_many(const oracle_handle* h, std::uint32_t nEvents,
         ev.x = x + o; ev.y = y + o; ev.z = z + o; ev.r = r + o;
         ev.varZ = varZ + o; ev.varR = varR + o;
         ev.n = spOffsets[e + 1] - o;
+        ev.navStride = navStride == 0 ? 1 : navStride;
+        ev.navPhase = e % ev.navStride;
         runEvent(ev);
         total += static_cast<std::int64_t>(ev.seeds.size());
         if (seedCounts != nullptr) seedCounts[e] = ev.seeds.size();

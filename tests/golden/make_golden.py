@@ -1,0 +1,50 @@
+"""Generates the committed golden vectors in tests/golden/ from the CPU oracle.
+
+The reference (ACTS) cannot be built or imported in the build container (needs
+Eigen / Boost / TBB / ROOT) and holds no golden vector
+for this path, so these fixtures are produced by the oracle restatement
+(oracle/seeding_oracle.cpp) -- "parity unpinned", see DESIGN.md.  They pin the
+oracle itself against accidental changes and travel to the GPU box, where the
+CUDA path is compared with them without running the oracle.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from acts_b200 import config, events  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+CASES = [
+    # name, config, generator, event id, mu
+    ("seeding_py_muons_ev0", "seeding_py", "muon", 0, 0.0),
+    ("seeding_py_muons_ev1", "seeding_py", "muon", 1, 0.0),
+    ("pu200_mu10_ev0", "pu200", "pileup", 0, 10.0),
+    ("pu200_mu20_ev3", "pu200", "pileup", 3, 20.0),
+    ("itk_like_mu10_ev1", "itk_like", "pileup", 1, 10.0),
+]
+
+MAKE = {"seeding_py": config.seeding_py_config, "pu200": config.pu200_config, "itk_like": config.itk_like_config}
+
+
+def main():
+    for name, cfg_name, gen, eid, mu in CASES:
+        ev = events.muon_gun_event(eid) if gen == "muon" else events.pileup_event(eid, mu=mu)
+        res = O.Oracle(MAKE[cfg_name](O.config_init)).run(ev, want_grid=True)
+        np.savez_compressed(
+            os.path.join(HERE, name + ".npz"), config=cfg_name,
+            x=ev["x"], y=ev["y"], z=ev["z"], r=ev["r"], varZ=ev["varZ"], varR=ev["varR"],
+            bottom=res["bottom"], middle=res["middle"], top=res["top"], quality=res["quality"],
+            vertexZ=res["vertexZ"], grid_copiedFromIndex=res["grid"]["copiedFromIndex"],
+            grid_binBegin=res["grid"]["binBegin"], grid_binEnd=res["grid"]["binEnd"],
+            counters=np.array([res["counters"][k] for k in ("nInGrid", "nMiddles", "nBottomDoublets", "nTopDoublets", "nCandidates", "nSeeds")], dtype=np.uint64))
+        print(name, ev["x"].size, "space points ->", res["quality"].size, "seeds")
+
+
+if __name__ == "__main__":
+    main()

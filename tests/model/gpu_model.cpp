@@ -116,7 +116,7 @@ void processMiddle(const DeviceConfig& c, const Packed& p, uint32_t m, uint32_t 
         if (a.rec.cotTheta != b.rec.cotTheta) return a.rec.cotTheta < b.rec.cotTheta;
         return a.seq < b.seq;
       });
-    } else {
+    } else if (tieMode == 1) {
       // exact replay: v is in emission order, sort {index, cotTheta} like
       // DoubletSeedFinder.hpp:94-104 with the libstdc++ algorithm
       std::vector<SortItem> items(v.size());
@@ -124,6 +124,44 @@ void processMiddle(const DeviceConfig& c, const Packed& p, uint32_t m, uint32_t 
       std_sort(items.data(), (int)items.size(), sortItemLess);
       std::vector<Doublet> sorted(v.size());
       for (uint32_t i = 0; i < v.size(); ++i) sorted[i] = v[items[i].val];
+      v.swap(sorted);
+    } else {
+      // what the kernel does: canonical order first, then the pruned replay of
+      // std::sort decides the order inside every group of equal cotTheta
+      const uint32_t n = (uint32_t)v.size();
+      std::vector<uint32_t> canon(n);
+      for (uint32_t i = 0; i < n; ++i) canon[i] = i;  // v is in emission order: index == seq rank
+      std::sort(canon.begin(), canon.end(), [&](uint32_t a, uint32_t b) {
+        if (v[a].rec.cotTheta != v[b].rec.cotTheta) return v[a].rec.cotTheta < v[b].rec.cotTheta;
+        return a < b;
+      });
+      std::vector<uint32_t> group(n, 0xFFFFu);
+      bool any = false;
+      for (uint32_t i = 0; i < n; ++i) {
+        const bool tp = i > 0 && v[canon[i]].rec.cotTheta == v[canon[i - 1]].rec.cotTheta;
+        const bool tn = i + 1 < n && v[canon[i]].rec.cotTheta == v[canon[i + 1]].rec.cotTheta;
+        if (tp || tn) {
+          uint32_t q = i;
+          while (q > 0 && v[canon[q - 1]].rec.cotTheta == v[canon[i]].rec.cotTheta) --q;
+          group[canon[i]] = q;
+          any = true;
+        }
+      }
+      if (any && n > 16) {
+        std::vector<SortItem> w(n);
+        for (uint32_t i = 0; i < n; ++i) w[i] = {v[i].rec.cotTheta, i | (group[i] << 16)};
+        std_sort_replay_ties(w.data(), (int)n, sortItemLess, [](const SortItem& e) { return (e.val >> 16) != 0xFFFFu; });
+        for (uint32_t i = 0; i < n; ++i) if (group[canon[i]] != 0xFFFFu) canon[i] = 0xFFFFFFFFu;
+        for (uint32_t i = 0; i < n; ++i) {
+          const uint32_t g = w[i].val >> 16;
+          if (g == 0xFFFFu) continue;
+          uint32_t s2 = g;
+          while (canon[s2] != 0xFFFFFFFFu) ++s2;
+          canon[s2] = w[i].val & 0xFFFFu;
+        }
+      }
+      std::vector<Doublet> sorted(n);
+      for (uint32_t i = 0; i < n; ++i) sorted[i] = v[canon[i]];
       v.swap(sorted);
     }
   };
@@ -311,6 +349,58 @@ int64_t model_check_std_sort(uint64_t seed, int maxN, int trials, int keyRange) 
     std::sort(b.begin(), b.end(), sortItemLess);
     for (int i = 0; i < n; ++i) {
       if (a[i].val != b[i].val) { ++bad; break; }
+    }
+  }
+  return bad;
+}
+
+// pruned tie replay: canonical order + replay must reproduce std::sort exactly
+int64_t model_check_tie_replay(uint64_t seed, int maxN, int trials, int nTieGroups) {
+  std::mt19937_64 rng(seed);
+  int64_t bad = 0;
+  for (int t = 0; t < trials; ++t) {
+    const int n = 2 + (int)(rng() % (uint64_t)(maxN - 1));
+    std::vector<SortItem> in(n);
+    for (int i = 0; i < n; ++i) in[i] = {(float)(rng() % 100000007ull), (uint32_t)i};
+    const int groups = (int)(rng() % (uint64_t)(nTieGroups + 1));
+    for (int gI = 0; gI < groups; ++gI) {  // plant tie groups of size 2..4
+      const int k = 2 + (int)(rng() % 3);
+      const float key = in[rng() % n].key;
+      for (int j = 0; j < k; ++j) in[rng() % n].key = key;
+    }
+    std::vector<SortItem> ref = in;
+    std::sort(ref.begin(), ref.end(), sortItemLess);
+    std::vector<uint32_t> canon(n);
+    for (int i = 0; i < n; ++i) canon[i] = i;
+    std::sort(canon.begin(), canon.end(), [&](uint32_t a, uint32_t b) {
+      if (in[a].key != in[b].key) return in[a].key < in[b].key;
+      return a < b;
+    });
+    std::vector<uint32_t> group(n, 0xFFFFu);
+    for (int i = 0; i < n; ++i) {
+      const bool tp = i > 0 && in[canon[i]].key == in[canon[i - 1]].key;
+      const bool tn = i + 1 < n && in[canon[i]].key == in[canon[i + 1]].key;
+      if (tp || tn) {
+        int q = i;
+        while (q > 0 && in[canon[q - 1]].key == in[canon[i]].key) --q;
+        group[canon[i]] = (uint32_t)q;
+      }
+    }
+    if (n > 16) {
+      std::vector<SortItem> w(n);
+      for (int i = 0; i < n; ++i) w[i] = {in[i].key, (uint32_t)i | (group[i] << 16)};
+      std_sort_replay_ties(w.data(), n, sortItemLess, [](const SortItem& e) { return (e.val >> 16) != 0xFFFFu; });
+      for (int i = 0; i < n; ++i) if (group[canon[i]] != 0xFFFFu) canon[i] = 0xFFFFFFFFu;
+      for (int i = 0; i < n; ++i) {
+        const uint32_t g = w[i].val >> 16;
+        if (g == 0xFFFFu) continue;
+        uint32_t s2 = g;
+        while (canon[s2] != 0xFFFFFFFFu) ++s2;
+        canon[s2] = w[i].val & 0xFFFFu;
+      }
+    }
+    for (int i = 0; i < n; ++i) {
+      if (canon[i] != ref[i].val) { ++bad; break; }
     }
   }
   return bad;

@@ -26,6 +26,8 @@ def lib():
         L.model_check_std_sort.restype = C.c_int64
         L.model_check_std_sort_killer.argtypes = [C.c_int]
         L.model_check_std_sort_killer.restype = C.c_int64
+        L.model_check_tie_replay.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int]
+        L.model_check_tie_replay.restype = C.c_int64
         L.model_check_heap.argtypes = [C.c_uint64, C.c_int]
         L.model_check_heap.restype = C.c_int64
         L.model_check_atan2f.argtypes = [C.c_uint64, C.c_int64]

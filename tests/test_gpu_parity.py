@@ -1,0 +1,279 @@
+"""GPU parity tests: the CUDA path through the C ABI against the CPU oracle.
+
+Bit-exact bar: identical (bottom, middle, top) triplets, bit-identical quality
+and vertexZ, and -- with the exact tie replay of the bin sort -- the same seed
+ORDER as the reference.
+"""
+import numpy as np
+import pytest
+
+from tests.conftest import make_config
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ("bottom", "middle", "top", "quality", "vertexZ")
+
+
+def _same_bits(a, b):
+    return all(np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)) for k in KEYS)
+
+
+@pytest.fixture(scope="module")
+def O(built):
+    from oracle import oracle
+
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def plugin(built):
+    from acts_b200 import plugin
+
+    return plugin
+
+
+def _event(kind, i, mu):
+    from acts_b200 import events
+
+    return events.muon_gun_event(i) if kind == "muon" else events.pileup_event(i, mu=mu)
+
+
+def test_device_atan2f_matches_host_libm(plugin, O):
+    """The device replays glibc's atan2f bit for bit (reference bins with
+    std::atan2(float, float), GridTripletSeedingAlgorithm.cpp:219)."""
+    rng = np.random.default_rng(7)
+    n = 4_000_000
+    x = rng.uniform(-200, 200, n).astype(np.float32)
+    y = rng.uniform(-200, 200, n).astype(np.float32)
+    # special values and raw bit patterns
+    x[:64] = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-30] * 8, dtype=np.float32)
+    y[:64] = np.repeat(np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-30], dtype=np.float32), 8)
+    x[64:100000] = rng.integers(0, 2**32, 100000 - 64, dtype=np.uint32).view(np.float32)
+    y[50000:150000] = rng.integers(0, 2**32, 100000, dtype=np.uint32).view(np.float32)
+    eng = plugin.SeedingEngine(make_config("pu200", plugin.config_init))
+    dev = eng.device_atan2f(y, x)
+    host = np.arctan2(y, x)  # numpy float32 atan2 -> libm atan2f? not guaranteed: use the oracle's libm call on a sample
+    sample = rng.choice(n, 200000, replace=False)
+    sample[:150] = np.arange(150)
+    ref = np.array([O.lib().oracle_atan2f(float(y[i]), float(x[i])) for i in sample], dtype=np.float32)
+    got = dev[sample]
+    nan = np.isnan(ref) & np.isnan(got)
+    assert np.array_equal(got.view(np.uint32)[~nan], ref.view(np.uint32)[~nan])
+    del host
+    eng.close()
+
+
+@pytest.mark.parametrize("name,kind,mu,ids", [
+    ("seeding_py", "muon", 0, (0, 1, 2)),
+    ("pu200", "pileup", 5, (0, 1)),
+    ("pu200", "pileup", 20, (0, 1, 2)),
+    ("pu200", "pileup", 60, (0, 1)),
+    ("itk_like", "pileup", 20, (0, 1)),
+    ("itk_like", "pileup", 60, (0,)),
+])
+def test_seeds_match_oracle(plugin, O, name, kind, mu, ids):
+    eng = plugin.SeedingEngine(make_config(name, plugin.config_init))
+    orc = O.Oracle(make_config(name, O.config_init))
+    for i in ids:
+        ev = _event(kind, i, mu)
+        got = eng.run(ev)
+        ref = orc.run(ev, want_grid=True)
+        assert O.seed_set(got) == O.seed_set(ref), f"{name} event {i}: seed set differs"
+        assert _same_bits(got, ref), f"{name} event {i}: seed order differs from the reference order"
+        cnt = eng.counters()
+        assert cnt["nInGrid"] == ref["counters"]["nInGrid"]
+        assert cnt["nMiddles"] == ref["counters"]["nMiddles"]
+        assert cnt["nBottomDoublets"] == ref["counters"]["nBottomDoublets"]
+        assert cnt["nTopDoublets"] == ref["counters"]["nTopDoublets"]
+        assert cnt["nCandidates"] == ref["counters"]["nCandidates"]
+        # grid stage: packed copy identical incl. the order inside every bin
+        g = eng.debug_grid()
+        for k in ("copiedFromIndex", "binBegin", "binEnd"):
+            assert np.array_equal(g[k], ref["grid"][k]), f"grid {k}"
+        for k in ("x", "y", "z", "r", "varZ", "varR"):
+            assert np.array_equal(g[k].view(np.uint32), ref["grid"][k].view(np.uint32)), f"grid {k}"
+    eng.close()
+
+
+def test_batch_equals_single_events(plugin, O):
+    from acts_b200 import events
+
+    eng = plugin.SeedingEngine(make_config("pu200", plugin.config_init))
+    orc = O.Oracle(make_config("pu200", O.config_init))
+    evs = [events.pileup_event(i, mu=m) for i, m in ((0, 20), (1, 5), (2, 40), (3, 1), (4, 20))]
+    empty = {k: np.zeros(0, np.float32) for k in ("x", "y", "z", "r", "varZ", "varR")}
+    evs.insert(2, empty)
+    cols, offsets = events.concat_events(evs)
+    res = eng.run_batch(cols, offsets)
+    assert len(res) == len(evs)
+    for ev, got in zip(evs, res):
+        ref = orc.run(ev)
+        assert _same_bits(got, ref)
+    eng.close()
+
+
+def test_full_size_event_mu200(plugin, O):
+    """BASELINE.json configs[2]: <mu>=200, ~1e5 space points, exact seed set and order."""
+    from acts_b200 import events
+
+    ev = events.pileup_event(0, mu=200)
+    assert 80_000 < ev["x"].size < 120_000
+    eng = plugin.SeedingEngine(make_config("pu200", plugin.config_init))
+    got = eng.run(ev)
+    ref = O.Oracle(make_config("pu200", O.config_init)).run(ev)
+    assert O.seed_set(got) == O.seed_set(ref)
+    assert _same_bits(got, ref)
+    cnt = eng.counters()
+    assert cnt["nCandidates"] == ref["counters"]["nCandidates"]
+    assert cnt["nTieMiddles"] == ref["counters"]["nCotTieMiddles"]
+    eng.close()
+
+
+@pytest.mark.parametrize("override", [
+    dict(interactionPointCut=1),
+    dict(useExtraCuts=1),
+    dict(useDeltaRinsteadOfTopRadius=1),
+    dict(useVariableMiddleSPRange=1),
+    dict(maxSeedsPerSpM=0),
+    dict(maxSeedsPerSpM=7, maxSeedsPerSpMConf=3),
+    dict(compatSeedLimit=0),
+    dict(compatSeedLimit=5, seedWeightIncrement=3.5, numSeedIncrement=1.0),
+    dict(numPhiNeighbors=2),
+    dict(numPhiNeighbors=40),
+    dict(phiMin=-1.0, phiMax=2.0),
+    dict(deltaZMin=-80.0, deltaZMax=120.0),
+    dict(impactMax=10.0, sigmaScattering=50),
+    dict(zBinEdges=[-2000.0, -300.0, 0.0, 300.0, 2000.0]),
+])
+def test_config_variants(plugin, O, override):
+    from acts_b200 import events
+
+    cfg = make_config("pu200", plugin.config_init).update(**override)
+    cfgo = make_config("pu200", O.config_init).update(**override)
+    eng = plugin.SeedingEngine(cfg)
+    orc = O.Oracle(cfgo)
+    for i, mu in ((0, 20), (5, 40)):
+        ev = events.pileup_event(i, mu=mu)
+        got = eng.run(ev)
+        ref = orc.run(ev)
+        assert _same_bits(got, ref), f"{override} event {i}"
+    eng.close()
+
+
+def test_vertex_z_windows(plugin, O):
+    """VertexZCuts (GridTripletSeedingAlgorithm.cpp:69-97) takes the experiment-cut slot."""
+    from acts_b200 import events
+
+    eng = plugin.SeedingEngine(make_config("pu200", plugin.config_init).update(useExtraCuts=1))
+    orc = O.Oracle(make_config("pu200", O.config_init).update(useExtraCuts=1))
+    ev = events.pileup_event(2, mu=30)
+    for windows in ([(-20.0, 15.0)], [(-100.0, -60.0), (-5.0, 5.0), (40.0, 90.0)]):
+        got = eng.run(ev, z_windows=windows)
+        ref = orc.run(ev, z_windows=windows)
+        assert ref["quality"].size > 0
+        assert _same_bits(got, ref)
+    # no windows again: back to the ITk cuts
+    assert _same_bits(eng.run(ev), orc.run(ev))
+    eng.close()
+
+
+def test_edge_cases(plugin, O):
+    from acts_b200 import events
+
+    eng = plugin.SeedingEngine(make_config("pu200", plugin.config_init))
+    orc = O.Oracle(make_config("pu200", O.config_init))
+    empty = {k: np.zeros(0, np.float32) for k in ("x", "y", "z", "r", "varZ", "varR")}
+    assert eng.run(empty)["quality"].size == 0
+    ev = events.pileup_event(9, mu=20)
+    # ragged / degenerate inputs: 1, 2, 3 space points
+    for n in (1, 2, 3, 17):
+        sub = {k: v[:n].copy() for k, v in ev.items()}
+        assert _same_bits(eng.run(sub), orc.run(sub))
+    # points outside the grid (r >= rMax, |z| >= zMax, NaN) are dropped like the reference does
+    bad = {k: v.copy() for k, v in ev.items()}
+    bad["r"][::7] = 250.0
+    bad["z"][::11] = 2500.0
+    bad["z"][::13] = -2000.0  # lower edge is inside
+    bad["r"][5] = np.nan
+    assert _same_bits(eng.run(bad), orc.run(bad))
+    # phi exactly on the closed-axis seam: y = +-0, x < 0 -> atan2f = +-pi
+    seam = {k: v.copy() for k, v in ev.items()}
+    seam["y"][:50] = 0.0
+    seam["y"][50:100] = -0.0
+    seam["x"][:100] = -np.abs(seam["x"][:100])
+    assert _same_bits(eng.run(seam), orc.run(seam))
+    # duplicated space points: equal r and equal cotTheta everywhere -> tie replay
+    dup = {k: np.concatenate([v[:3000], v[:3000]]) for k, v in ev.items()}
+    got, ref = eng.run(dup), orc.run(dup)
+    assert _same_bits(got, ref)
+    assert eng.counters()["nTieMiddles"] > 0
+    # caller buffer too small -> ERR_CAPACITY with the required size
+    from acts_b200 import config as C
+
+    with pytest.raises(plugin.SeedingError) as ei:
+        eng.run(ev, capacity=10)
+    assert ei.value.code == C.ERR_CAPACITY
+    eng.close()
+
+
+def test_canonical_tie_mode_gives_same_seed_set(plugin, O, monkeypatch):
+    """B200SEED_EXACT_TIES=0 (canonical (key, index) order): same seed SET on these events."""
+    from acts_b200 import events
+
+    monkeypatch.setenv("B200SEED_EXACT_TIES", "0")
+    eng = plugin.SeedingEngine(make_config("pu200", plugin.config_init))
+    orc = O.Oracle(make_config("pu200", O.config_init))
+    ev = events.pileup_event(1, mu=60)
+    assert O.seed_set(eng.run(ev)) == O.seed_set(orc.run(ev))
+    eng.close()
+
+
+def test_gpu_reproduces_committed_golden_vectors(plugin):
+    """The CUDA path against the committed fixtures (no oracle involved at run time)."""
+    import glob
+    import os
+
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+    assert len(files) >= 5
+    for f in files:
+        g = np.load(f)
+        ev = {k: g[k] for k in ("x", "y", "z", "r", "varZ", "varR")}
+        eng = plugin.SeedingEngine(make_config(str(g["config"]), plugin.config_init))
+        got = eng.run(ev)
+        for k in KEYS:
+            assert np.array_equal(got[k].view(np.uint32), g[k].view(np.uint32)), (f, k)
+        grid = eng.debug_grid()
+        assert np.array_equal(grid["copiedFromIndex"], g["grid_copiedFromIndex"])
+        assert np.array_equal(grid["binBegin"], g["grid_binBegin"]) and np.array_equal(grid["binEnd"], g["grid_binEnd"])
+        eng.close()
+
+
+def test_property_checks_at_full_size(plugin):
+    """Size-independent properties on a full <mu>=200 event (no oracle): per-middle seed cap,
+    permutation invariance of the seed SET under a shuffle of the input space points, and
+    idempotence (same call twice -> identical output)."""
+    from acts_b200 import events
+
+    cfg = make_config("pu200", plugin.config_init)
+    eng = plugin.SeedingEngine(cfg)
+    ev = events.pileup_event(11, mu=200)
+    a = eng.run(ev)
+    b = eng.run(ev)
+    assert _same_bits(a, b)
+    _, counts = np.unique(a["middle"], return_counts=True)
+    assert counts.max() <= cfg.maxSeedsPerSpM + 1
+    r = ev["r"]
+    assert np.all((r[a["middle"]] >= 60.0) & (r[a["middle"]] <= 120.0))
+    assert np.all(r[a["bottom"]] < r[a["middle"]]) and np.all(r[a["top"]] > r[a["middle"]])
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(ev["x"].size)
+    shuffled = {k: v[perm] for k, v in ev.items()}
+    c = eng.run(shuffled)
+    orig = {(int(perm[x]), int(perm[y]), int(perm[z])): (int(q), int(v)) for x, y, z, q, v in
+            zip(c["bottom"], c["middle"], c["top"], c["quality"].view(np.uint32), c["vertexZ"].view(np.uint32))}
+    ref = {(int(x), int(y), int(z)): (int(q), int(v)) for x, y, z, q, v in
+           zip(a["bottom"], a["middle"], a["top"], a["quality"].view(np.uint32), a["vertexZ"].view(np.uint32))}
+    # tie order depends on the input order (like in the reference), so allow a handful of differences
+    diff = set(orig.items()) ^ set(ref.items())
+    assert len(diff) <= 8, len(diff)
+    eng.close()

@@ -1,0 +1,79 @@
+"""The sequential CPU model of the GPU algorithm (tests/model) equals the oracle.
+
+This is where the exactness of the restructuring is established without a GPU:
+binary-searched r windows, (cotTheta, emission index) order + pruned libstdc++
+introsort replay for ties, per-bottom independent top windows (prefix-max
+formulation), independent filter weights, replayed bounded heap."""
+import numpy as np
+import pytest
+
+from tests.conftest import CONFIGS, make_config
+
+KEYS = ("bottom", "middle", "top", "quality", "vertexZ")
+
+
+@pytest.fixture(scope="module")
+def env(built):
+    from acts_b200 import events, plugin
+    from oracle import oracle as O
+    from tests.model import model as M
+
+    return events, plugin, O, M
+
+
+def test_libstdcxx_sort_replay_matches_std_sort(env):
+    M = env[3]
+    L = M.lib()
+    assert L.model_check_std_sort(1, 3000, 2000, 7) == 0
+    assert L.model_check_std_sort(2, 40, 20000, 3) == 0
+    assert L.model_check_std_sort(3, 100000, 10, 50) == 0
+    assert L.model_check_std_sort_killer(4096) == 0   # forces the heap-sort fallback
+
+
+def test_pruned_tie_replay_matches_std_sort(env):
+    L = env[3].lib()
+    assert L.model_check_tie_replay(1, 3000, 2000, 3) == 0
+    assert L.model_check_tie_replay(2, 60000, 50, 6) == 0
+    assert L.model_check_tie_replay(3, 40, 20000, 2) == 0
+    assert L.model_check_tie_replay(4, 2000, 2000, 40) == 0
+
+
+def test_heap_replay_matches_libstdcxx(env):
+    assert env[3].lib().model_check_heap(5, 200000) == 0
+
+
+def test_atan2f_replay_matches_host_libm(env):
+    """glibc's atan2f (what the reference calls, GridTripletSeedingAlgorithm.cpp:219) op for op."""
+    assert env[3].lib().model_check_atan2f(99, 30_000_000) == 0
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_model_equals_oracle(env, name):
+    events, plugin, O, M = env
+    cfg = make_config(name, plugin.config_init)
+    orc = O.Oracle(make_config(name, O.config_init))
+    for i, mu in ((0, 10), (2, 40)):
+        ev = events.muon_gun_event(i) if name == "seeding_py" else events.pileup_event(i, mu=mu)
+        ref = orc.run(ev, want_grid=True)
+        for tie_mode in (1, 2):   # full std::sort replay, canonical + pruned replay (what the kernel does)
+            got = M.run(cfg, ref["grid"], tie_mode=tie_mode)
+            for k in KEYS:
+                assert np.array_equal(got[k].view(np.uint32), ref[k].view(np.uint32)), (name, i, tie_mode, k)
+            assert got["stats"]["nCandidates"] == ref["counters"]["nCandidates"]
+        stable = orc.run(ev, sort_mode=O.Oracle.STABLE, want_grid=True)
+        got0 = M.run(cfg, stable["grid"], tie_mode=0)
+        for k in KEYS:
+            assert np.array_equal(got0[k].view(np.uint32), stable[k].view(np.uint32))
+
+
+def test_model_bin_index_equals_oracle(env):
+    events, plugin, O, M = env
+    for name in ("pu200", "itk_like"):
+        cfg = make_config(name, plugin.config_init)
+        orc = O.Oracle(make_config(name, O.config_init))
+        ev = events.pileup_event(7, mu=10)
+        n = 4000
+        got = M.bin_index(cfg, ev["x"][:n], ev["y"][:n], ev["z"][:n], ev["r"][:n])
+        ref = np.array([orc.bin_index(float(O.lib().oracle_atan2f(float(y), float(x))), float(z), float(r))
+                        for x, y, z, r in zip(ev["x"][:n], ev["y"][:n], ev["z"][:n], ev["r"][:n])])
+        assert np.array_equal(got, ref)

@@ -1,0 +1,189 @@
+"""CPU tests of the oracle (the restatement of the reference algorithm).
+
+The reference has no golden vector for this path, so the
+oracle is anchored on (i) the worked constants of the canonical configuration,
+(ii) the reference's own utility-layer known answers (GridBinFinderTests,
+BinnedGroupTests, SpacePointGridPhiBinningTests), (iii) hand-checkable micro
+cases, (iv) self-consistency properties and (v) the committed fixtures.
+"""
+import glob
+import math
+import os
+
+import numpy as np
+import pytest
+
+from tests.conftest import make_config
+
+
+@pytest.fixture(scope="module")
+def O(built):
+    from oracle import oracle
+
+    return oracle
+
+
+def test_worked_constants_of_canonical_config(O):
+    """SURVEY.md section 3.4 (computed there with g++ float from the reference's expressions)."""
+    i = O.Oracle(make_config("seeding_py", O.config_init)).info()
+    assert i.phiBins == 53 and i.zBins == 1 and i.rBins == 1 and i.nGlobalBins == 55 * 3 * 3
+    assert i.minHelixDiameter2 == np.float32(2781625.5)
+    assert i.highland == np.float32(3.92439403e-3)
+    assert i.sigmapT2perRadius == np.float32(428394.469)
+    assert i.multipleScattering2 == np.float32(0.154008687)
+    j = O.Oracle(make_config("pu200", O.config_init)).info()
+    assert j.phiBins == 53
+    assert abs(j.sigmapT2perRadius - 4283.94) < 0.01
+    assert j.multipleScattering2 == np.float32(1.54008687e-3) or abs(j.multipleScattering2 - 1.54008687e-3) < 1e-9
+
+
+def test_algorithm_default_config_has_26_phi_bins(O):
+    from acts_b200.config import Config
+    import ctypes as C
+
+    cfg = Config()
+    O.config_init(C.byref(cfg))
+    assert O.Oracle(cfg).info().phiBins == 26
+
+
+def test_phi_binning_reference_known_answers(O):
+    """Tests/UnitTests/Core/Seeding/SpacePointGridPhiBinningTests.cpp:44-86."""
+    from acts_b200 import config as cm
+
+    cfg = make_config("seeding_py", O.config_init).update(bFieldInZ=0.0, maxPhiBins=123)
+    assert O.Oracle(cfg).info().phiBins == 123          # zero field -> maxPhiBins
+    cfg = make_config("seeding_py", O.config_init).update(maxPhiBins=7)
+    assert O.Oracle(cfg).info().phiBins == 7             # cap
+    cfg = make_config("seeding_py", O.config_init).update(minPt=0.010)
+    with pytest.raises(O.OracleError) as ei:             # minPt = 10 MeV at rMax = 200 -> domain_error
+        O.Oracle(cfg)
+    assert ei.value.code == cm.ERR_DOMAIN
+
+
+def test_axis_neighbourhood_reference_known_answers(O):
+    """Tests/UnitTests/Core/Utilities/GridBinFinderTests.cpp:25-82, 10-bin axes, +-1."""
+    def closed(idx):
+        buf = np.zeros(64, np.uint64)
+        n = O.lib().oracle_neighbors_closed(idx, -1, 1, 10, buf.ctypes.data, 64)
+        return buf[:n].tolist()
+
+    def opened(idx):
+        buf = np.zeros(64, np.uint64)
+        n = O.lib().oracle_neighbors_open(idx, -1, 1, 10, buf.ctypes.data, 64)
+        return buf[:n].tolist()
+
+    assert closed(1) == [10, 1, 2]
+    assert closed(10) == [9, 10, 1]
+    assert closed(5) == [4, 5, 6]
+    assert opened(1) == [0, 1, 2]
+    assert opened(10) == [9, 10, 11]
+
+
+def test_navigation_validation(O):
+    """BinnedGroupTests.cpp:72-120: custom visit order, rejection of 0 / nBins+1 / duplicates."""
+    from acts_b200 import config as cm
+
+    edges = [-2000.0, -500.0, 0.0, 500.0, 2000.0]
+    ok = make_config("pu200", O.config_init).update(zBinEdges=edges, zBinsCustomLooping=[3, 4, 2, 1])
+    O.Oracle(ok)
+    for bad in ([0, 1, 2], [1, 2, 5 - 0], [1, 1, 2]):
+        cfg = make_config("pu200", O.config_init).update(zBinEdges=edges, zBinsCustomLooping=bad)
+        with pytest.raises(O.OracleError) as ei:
+            O.Oracle(cfg)
+        assert ei.value.code == cm.ERR_INVALID_ARGUMENT
+
+
+def _helix_points(radii, pt, phi0, z0, cot, q=1.0):
+    R = pt / (2 * 0.000299792458)
+    xs, ys, zs = [], [], []
+    for r in radii:
+        alpha = 2 * math.asin(r / (2 * R))
+        phi = phi0 - q * 0.5 * alpha
+        xs.append(r * math.cos(phi)); ys.append(r * math.sin(phi)); zs.append(z0 + R * alpha * cot)
+    x, y, z = (np.array(v, dtype=np.float32) for v in (xs, ys, zs))
+    return {"x": x, "y": y, "z": z, "r": np.hypot(x.astype(np.float64), y.astype(np.float64)).astype(np.float32),
+            "varZ": np.full(len(radii), 2e-4, np.float32), "varR": np.full(len(radii), 4e-6, np.float32)}
+
+
+def test_three_points_on_a_helix_give_exactly_one_seed(O):
+    """Hand-checkable micro case: a 2 GeV helix through the origin crossing r = 32, 72, 116:
+    one seed (bottom, middle, top) = (0, 1, 2), quality = -impact (no compatible
+    second top), vertexZ = zM - rM * cotTheta_bottom ~ z0."""
+    ev = _helix_points([32.0, 72.0, 116.0], pt=2.0, phi0=0.3, z0=12.0, cot=0.5)
+    res = O.Oracle(make_config("pu200", O.config_init)).run(ev)
+    assert res["quality"].size == 1
+    assert (int(res["bottom"][0]), int(res["middle"][0]), int(res["top"][0])) == (0, 1, 2)
+    assert -0.05 < float(res["quality"][0]) <= 0.0          # -impact, impact ~ 0 for a track from the origin
+    assert abs(float(res["vertexZ"][0]) - 12.0) < 0.5
+    # a fourth point on the same helix is a compatible top: the weights gain compatSeedWeight
+    ev4 = _helix_points([32.0, 72.0, 116.0, 172.0], pt=2.0, phi0=0.3, z0=12.0, cot=0.5)
+    res4 = O.Oracle(make_config("pu200", O.config_init)).run(ev4)
+    triplets = {(int(b), int(m), int(t)): float(q) for b, m, t, q in zip(res4["bottom"], res4["middle"], res4["top"], res4["quality"])}
+    assert (0, 1, 2) in triplets and (0, 1, 3) in triplets
+    assert 199.9 < triplets[(0, 1, 2)] <= 200.0 and 199.9 < triplets[(0, 1, 3)] <= 200.0
+
+
+def test_low_pt_helix_is_rejected(O):
+    ev = _helix_points([32.0, 72.0, 116.0], pt=0.2, phi0=-1.0, z0=0.0, cot=0.2)  # below minPt = 0.5
+    assert O.Oracle(make_config("pu200", O.config_init)).run(ev)["quality"].size == 0
+
+
+def test_seeds_satisfy_the_cuts_in_double_precision(O):
+    """Self-consistency: every emitted seed passes the r-window, collision-region,
+    cotTheta and helix/impact cuts when re-checked in float64 (with slack)."""
+    from acts_b200 import events
+
+    cfg = make_config("pu200", O.config_init)
+    ev = events.pileup_event(4, mu=20)
+    res = O.Oracle(cfg).run(ev)
+    assert res["quality"].size > 1000
+    x, y, z, r = (ev[k].astype(np.float64) for k in ("x", "y", "z", "r"))
+    b, m, t = res["bottom"], res["middle"], res["top"]
+    assert np.all((r[m] >= 60 - 1e-3) & (r[m] <= 120 + 1e-3))
+    for o, sign in ((b, -1.0), (t, 1.0)):
+        dR = sign * (r[o] - r[m])
+        dZ = sign * (z[o] - z[m])
+        assert np.all((dR >= 1 - 1e-3) & (dR <= 300 + 1e-3))
+        z0 = z[m] - r[m] * dZ / dR
+        assert np.all(np.abs(z0) <= 250 * (1 + 1e-4))
+        assert np.all(np.abs(dZ / dR) <= 10.01788 * (1 + 1e-4))
+    # circle through the three points: radius above minPt / (0.3 B), impact below impactMax
+    ax, ay, bx, by, cx, cy = x[b], y[b], x[m], y[m], x[t], y[t]
+    d = 2 * (ax * (by - cy) + bx * (cy - ay) + cx * (ay - by))
+    ux = ((ax**2 + ay**2) * (by - cy) + (bx**2 + by**2) * (cy - ay) + (cx**2 + cy**2) * (ay - by)) / d
+    uy = ((ax**2 + ay**2) * (cx - bx) + (bx**2 + by**2) * (ax - cx) + (cx**2 + cy**2) * (bx - ax)) / d
+    rad = np.hypot(ax - ux, ay - uy)
+    assert np.all(rad >= 0.5 / (2 * 0.000299792458) * 0.98)
+    assert np.all(np.abs(np.hypot(ux, uy) - rad) <= 3.0 * 1.05)
+    # per middle at most maxSeedsPerSpM + 1 seeds
+    _, counts = np.unique(m, return_counts=True)
+    assert counts.max() <= cfg.maxSeedsPerSpM + 1
+
+
+def test_stable_and_faithful_sort_orders_give_the_same_seed_set(O):
+    from acts_b200 import events
+
+    orc = O.Oracle(make_config("pu200", O.config_init))
+    ev = events.pileup_event(1, mu=40)
+    assert O.seed_set(orc.run(ev, sort_mode=O.Oracle.FAITHFUL)) == O.seed_set(orc.run(ev, sort_mode=O.Oracle.STABLE))
+
+
+def test_oracle_reproduces_committed_golden_vectors(O):
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+    assert len(files) >= 5
+    for f in files:
+        g = np.load(f)
+        ev = {k: g[k] for k in ("x", "y", "z", "r", "varZ", "varR")}
+        res = O.Oracle(make_config(str(g["config"]), O.config_init)).run(ev, want_grid=True)
+        for k in ("bottom", "middle", "top", "quality", "vertexZ"):
+            assert np.array_equal(res[k].view(np.uint32), g[k].view(np.uint32)), (f, k)
+        assert np.array_equal(res["grid"]["copiedFromIndex"], g["grid_copiedFromIndex"])
+
+
+def test_empty_and_out_of_grid_inputs(O):
+    orc = O.Oracle(make_config("pu200", O.config_init))
+    empty = {k: np.zeros(0, np.float32) for k in ("x", "y", "z", "r", "varZ", "varR")}
+    assert orc.run(empty)["quality"].size == 0
+    ev = _helix_points([32.0, 72.0, 116.0], pt=2.0, phi0=0.3, z0=12.0, cot=0.5)
+    ev["r"][2] = 250.0  # outside rMax = 200: dropped, no seed possible
+    assert orc.run(ev)["quality"].size == 0
