@@ -103,7 +103,6 @@ struct SeedParams {
   float *slotQ, *slotZ;
   uint32_t* slotCount;
   uint32_t seedsPerMiddle;
-  uint32_t capB, capT, capPool, nBuckets;
   int exactTies;  // replay libstdc++ std::sort inside groups of equal cotTheta
   unsigned long long* counters;
   int* status;
@@ -416,27 +415,45 @@ __global__ void __launch_bounds__(256) k_fill_work(const __grid_constant__ WorkP
 
 // ---------------------------------------------------------------------------
 // Seeding kernel: one block per middle space point (persistent blocks pulling
-// work items from an atomic counter).
+// work items from an atomic counter).  Per middle:
+//   phase 0  r windows of every neighbour bin (warp-parallel 32-ary searches)
+//   phase 1  doublet search, two passes per side: (z, r) cuts + compaction of the
+//            survivors, then the dense coordinate transform -> (cotTheta, seq)
+//   phase 2  order both lists like the reference's sortByCotTheta (bucket sort
+//            by (cotTheta, seq) + pruned libstdc++ introsort replay for ties);
+//            tops get their full records in sorted order
+//   phase 3  one thread per bottom doublet, no barrier inside the loops:
+//            a) H_j / brk_j scans; every pair is evaluated once and candidates
+//               are emitted on the spot          (TripletSeedFinder.cpp:34-162)
+//            b) window starts = exclusive prefix max of H
+//            c) the few pairs in [start_j, t*_j) the scans did not touch
+//            d) candidates grouped by bottom (counting sort), each group in
+//               curvature order                  (BroadTripletSeedFilter.cpp:143-148)
+//            e) one thread per candidate: weight  (BroadTripletSeedFilter.cpp:162-251)
+//            f) bounded heap replay in the reference's push order
+//               (CandidatesForMiddleSp.cpp:44-75)
+//   phase 4  sort_heap, keep min(n, maxSeedsPerSpM + 1), write the seed slots
 // ---------------------------------------------------------------------------
 struct Cand {
   float curv;
   float impactOrWeight;
   float topR;
-  uint32_t tOwner;  // sorted top rank | owner thread << 16
+  uint32_t tOwner;  // sorted top rank | sorted bottom rank << 16
 };
 __device__ __forceinline__ bool cand_less(const Cand& a, const Cand& b) { return a.curv < b.curv; }
 
 struct StoredSeed {
-  uint32_t bottomPos, topPos;
-  float weight, zOrigin;
+  uint32_t tOwner;  // candidate identity (sorted top rank | sorted bottom rank << 16)
+  float weight;
 };
 
 struct SeedShared {
   MiddleSp mid;
   uint32_t w, m, eg;
-  uint32_t nB, nT, poolCount;
+  uint32_t nB, nT, nSurv, poolCount, nValid;
   uint32_t tie, tieTmp, bad;
-  uint32_t carry;
+  uint32_t runCarry;
+  uint32_t nextChunkA, nextChunkC;
   uint32_t nBotWin, nTopWin;
   uint32_t winBs[kMaxNeighborBins], winBe[kMaxNeighborBins], winBp[kMaxNeighborBins + 1];
   uint32_t winTs[kMaxNeighborBins], winTe[kMaxNeighborBins], winTp[kMaxNeighborBins + 1];
@@ -448,101 +465,147 @@ struct SeedShared {
   unsigned long long cnt[kCntSlots];
 };
 
+// Static shared-memory layout of one block.  The sorted-top arrays double as
+// scratch (survivor list of phase 1, tie-replay work arrays of phase 2) until
+// they are written at the end of phase 2; the arena switches from the unsorted
+// doublet lists (phases 1-2) to the candidate pools (phase 3).
+template <int CAPB, int CAPT, int CAPPOOL, int NBK>
+struct SeedLayout {
+  static_assert(CAPB <= 2 * CAPT, "tie-replay scratch of the bottoms lives in the sorted-top arrays");
+  static_assert(CAPB + CAPT <= 6 * CAPT, "survivor list lives in the sorted-top arrays");
+  static_assert(CAPB < 65535 && CAPT < 65535 && CAPPOOL < 65535, "16-bit ranks");
+  SeedShared sh;
+  float bCot[CAPB];      // bottoms in sorted order (from phase 2 on)
+  uint32_t bSeq[CAPB];
+  float sCot[CAPT];      // tops in sorted order; contiguous block of 24 * CAPT bytes
+  float sIDR[CAPT];
+  float sEr[CAPT];
+  float sU[CAPT];
+  float sV[CAPT];
+  uint32_t sPos[CAPT];
+  uint32_t buckets[NBK + 1];
+  union Arena {
+    struct {
+      float uCotB[CAPB];
+      uint32_t uSeqB[CAPB];
+      float uCotT[CAPT];
+      uint32_t uSeqT[CAPT];
+      uint16_t rankB[CAPB];
+      uint16_t rankT[CAPT];
+    } a;
+    struct {
+      Cand pool[CAPPOOL];
+      Cand pool2[CAPPOOL];
+      uint32_t cnt[CAPB + 1];
+      uint16_t hval[CAPB];   // F value of the last failing top, later the window start
+      uint16_t tstar[CAPB];  // rank of the last failing top of the prefix
+    } b;
+  } u;
+};
+
 __device__ __forceinline__ uint32_t seq_to_pos(uint32_t seq, const uint32_t* prefix, const uint32_t* start, uint32_t nWin) {
   uint32_t k = 0;
   while (k + 1 < nWin && prefix[k + 1] <= seq) ++k;
   return start[k] + (seq - prefix[k]);
 }
 
-// Shared-memory carve-up.  Persistent arrays first, then one arena whose
-// content changes with the phase of a middle:
-//   phases 1-2 : tCot, tSeq, tSorted (tops before their records exist)
-//   tie replay : W + two u16 arrays -- for the tops inside the (not yet written)
-//                sorted-top arrays, for the bottoms inside the arena
-//   phase 3    : pool (+ links) and pool2
-struct SeedSmem {
-  SeedShared* sh;
-  float* bCot; uint32_t* bSeq; uint16_t* bSorted;       // bottoms, unsorted + rank -> index
-  float *sCot, *sIDR, *sEr, *sU, *sV; uint32_t* sPos;   // tops in sorted order
-  uint32_t* buckets;                                    // [nBuckets + 1]
-  unsigned char* arena;
-  float* tCot; uint32_t* tSeq; uint16_t* tSorted;       // arena, phases 1-2
-  Cand* pool; uint16_t* poolNext; Cand* pool2;          // arena, phase 3
-};
-
-__host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
-
-__host__ __device__ inline size_t seed_arena_bytes(uint32_t capB, uint32_t capT, uint32_t capPool) {
-  const size_t tops = align16(4ull * capT) * 2 + align16(2ull * capT);
-  const size_t pools = align16(sizeof(Cand) * (size_t)capPool) * 2 + align16(2ull * capPool);
-  const size_t tieB = align16(8ull * capB) + align16(2ull * capB) * 2;  // W + seqSorted + grpOf (bottoms)
-  size_t a = tops > pools ? tops : pools;
-  return a > tieB ? a : tieB;
+// First index in [lo, hi) where the monotone predicate holds (hi if none),
+// searched by a whole warp: 32 probes per step instead of one.
+template <typename Pred>
+__device__ __forceinline__ uint32_t warp_first_true(uint32_t lo, uint32_t hi, Pred pred) {
+  const uint32_t lane = threadIdx.x & 31;
+  while (hi - lo > 32) {
+    const uint32_t n = hi - lo;
+    const uint32_t step = (n + 31) / 32;
+    uint32_t q = lo + (lane + 1) * step - 1;
+    if (q > hi - 1) q = hi - 1;
+    const uint32_t mask = __ballot_sync(0xffffffffu, pred(q));
+    if (mask == 0u) return hi;  // the last probe is hi - 1
+    const int f = __ffs(mask) - 1;
+    const uint32_t qf = __shfl_sync(0xffffffffu, q, f);
+    const uint32_t qp = __shfl_sync(0xffffffffu, q, f > 0 ? f - 1 : 0);
+    lo = f > 0 ? qp + 1 : lo;
+    hi = qf;  // pred(qf) holds: the answer is qf unless an earlier index in [lo, qf) holds
+    if (hi == lo) return qf;
+    // search [lo, qf); if nothing is found there the answer is qf
+    uint32_t inner = hi;
+    {
+      uint32_t l2 = lo, h2 = hi;
+      while (h2 - l2 > 32) {
+        const uint32_t n2 = h2 - l2;
+        const uint32_t st2 = (n2 + 31) / 32;
+        uint32_t q2 = l2 + (lane + 1) * st2 - 1;
+        if (q2 > h2 - 1) q2 = h2 - 1;
+        const uint32_t m2 = __ballot_sync(0xffffffffu, pred(q2));
+        if (m2 == 0u) { l2 = h2; break; }
+        const int f2 = __ffs(m2) - 1;
+        const uint32_t qf2 = __shfl_sync(0xffffffffu, q2, f2);
+        const uint32_t qp2 = __shfl_sync(0xffffffffu, q2, f2 > 0 ? f2 - 1 : 0);
+        l2 = f2 > 0 ? qp2 + 1 : l2;
+        h2 = qf2;
+        inner = qf2;
+      }
+      if (l2 < h2) {
+        const uint32_t i = l2 + lane;
+        const uint32_t m3 = __ballot_sync(0xffffffffu, i < h2 && pred(i));
+        if (m3 != 0u) inner = l2 + (uint32_t)(__ffs(m3) - 1);
+      }
+    }
+    return inner;
+  }
+  const uint32_t i = lo + lane;
+  const uint32_t mask = __ballot_sync(0xffffffffu, i < hi && pred(i));
+  return mask != 0u ? lo + (uint32_t)(__ffs(mask) - 1) : hi;
 }
 
-__host__ __device__ inline size_t seed_smem_bytes(uint32_t capB, uint32_t capT, uint32_t capPool, uint32_t nBuckets) {
-  size_t s = align16(sizeof(SeedShared));
-  s += align16(4ull * capB) * 2 + align16(2ull * capB);
-  s += align16(4ull * capT) * 6;
-  s += align16(4ull * (nBuckets + 1));
-  s += seed_arena_bytes(capB, capT, capPool);
-  return s;
-}
-
-__device__ __forceinline__ SeedSmem carve_seed_smem(unsigned char* base, uint32_t capB, uint32_t capT, uint32_t capPool, uint32_t nBuckets) {
-  SeedSmem s;
-  unsigned char* q = base;
-  s.sh = reinterpret_cast<SeedShared*>(q); q += align16(sizeof(SeedShared));
-  s.bCot = reinterpret_cast<float*>(q); q += align16(4ull * capB);
-  s.bSeq = reinterpret_cast<uint32_t*>(q); q += align16(4ull * capB);
-  s.bSorted = reinterpret_cast<uint16_t*>(q); q += align16(2ull * capB);
-  s.sCot = reinterpret_cast<float*>(q); q += align16(4ull * capT);
-  s.sIDR = reinterpret_cast<float*>(q); q += align16(4ull * capT);
-  s.sEr = reinterpret_cast<float*>(q); q += align16(4ull * capT);
-  s.sU = reinterpret_cast<float*>(q); q += align16(4ull * capT);
-  s.sV = reinterpret_cast<float*>(q); q += align16(4ull * capT);
-  s.sPos = reinterpret_cast<uint32_t*>(q); q += align16(4ull * capT);
-  s.buckets = reinterpret_cast<uint32_t*>(q); q += align16(4ull * (nBuckets + 1));
-  s.arena = q;
-  s.tCot = reinterpret_cast<float*>(q); q += align16(4ull * capT);
-  s.tSeq = reinterpret_cast<uint32_t*>(q); q += align16(4ull * capT);
-  s.tSorted = reinterpret_cast<uint16_t*>(q);
-  q = s.arena;
-  s.pool = reinterpret_cast<Cand*>(q); q += align16(sizeof(Cand) * (size_t)capPool);
-  s.pool2 = reinterpret_cast<Cand*>(q); q += align16(sizeof(Cand) * (size_t)capPool);
-  s.poolNext = reinterpret_cast<uint16_t*>(q);
-  return s;
-}
-
-// Doublet search for one side (DoubletSeedFinder.cpp:41-273): every thread
-// strides over the r windows, survivors are appended as (cotTheta, seq).
+// Doublet search for one side (DoubletSeedFinder.cpp:41-273), two passes so that
+// the expensive transform runs on dense warps:
+//   pass 1: (z, r) cuts over the r windows, survivors appended as seq -> surv[]
+//   pass 2: coordinate transform / remaining cuts on the survivors -> (cot, seq)
 template <bool kBottom>
 __device__ __forceinline__ void find_doublets(const SeedParams& p, SeedShared& sh, uint32_t nWin, const uint32_t* winS,
-                                              const uint32_t* winE, const uint32_t* winP, float* cotOut, uint32_t* seqOut,
-                                              uint32_t* counter, uint32_t cap) {
+                                              const uint32_t* winE, const uint32_t* winP, uint32_t* surv, uint32_t survCap,
+                                              float* cotOut, uint32_t* seqOut, uint32_t* counter, uint32_t cap) {
   const MiddleSp mid = sh.mid;
+  if (threadIdx.x == 0) sh.nSurv = 0;
+  __syncthreads();
   for (uint32_t k = 0; k < nWin; ++k) {
     const uint32_t s = winS[k], e = winE[k], pre = winP[k];
     for (uint32_t base = s; base < e; base += blockDim.x) {
       const uint32_t o = base + threadIdx.x;
       bool pass = false;
-      DoubletRec rec;
       if (o < e) {
         const float2 zr = ldg2(p.pZR + o);
         float dR, dZ;
-        if (doublet_zr_cuts<kBottom>(p.cfg, mid, zr.x, zr.y, dR, dZ)) {
-          const float2 xy = ldg2(p.pXY + o);
-          const float2 var = ldg2(p.pVar + o);
-          pass = doublet_finish<kBottom>(p.cfg, mid, dR, dZ, xy.x, xy.y, zr.y, var.x, var.y, p.zWinLo, p.zWinHi, p.nZWin, rec);
-        }
+        pass = doublet_zr_cuts<kBottom>(p.cfg, mid, zr.x, zr.y, dR, dZ);
       }
-      const uint32_t slot = warp_append(counter, pass);
-      if (pass && slot < cap) {
-        cotOut[slot] = rec.cotTheta;
-        seqOut[slot] = pre + (o - s);
-      }
+      const uint32_t slot = warp_append(&sh.nSurv, pass);
+      if (pass && slot < survCap) surv[slot] = pre + (o - s);
     }
   }
+  __syncthreads();
+  const uint32_t nS = sh.nSurv < survCap ? sh.nSurv : survCap;
+  if (sh.nSurv > survCap && threadIdx.x == 0) *counter = cap + 1;  // forces the overflow path
+  for (uint32_t base = 0; base < nS; base += blockDim.x) {
+    const uint32_t i = base + threadIdx.x;
+    bool pass = false;
+    DoubletRec rec;
+    uint32_t seq = 0;
+    if (i < nS) {
+      seq = surv[i];
+      const uint32_t o = seq_to_pos(seq, winP, winS, nWin);
+      const float2 zr = ldg2(p.pZR + o), xy = ldg2(p.pXY + o), var = ldg2(p.pVar + o);
+      float dR, dZ;
+      doublet_zr_cuts<kBottom>(p.cfg, mid, zr.x, zr.y, dR, dZ);
+      pass = doublet_finish<kBottom>(p.cfg, mid, dR, dZ, xy.x, xy.y, zr.y, var.x, var.y, p.zWinLo, p.zWinHi, p.nZWin, rec);
+    }
+    const uint32_t slot = warp_append(counter, pass);
+    if (pass && slot < cap) {
+      cotOut[slot] = rec.cotTheta;
+      seqOut[slot] = seq;
+    }
+  }
+  __syncthreads();
 }
 
 // Keys of the in-block bucket sort.  bucket() must be monotone in the order
@@ -568,29 +631,44 @@ struct SeqKey {  // order by emission index (unique)
   __device__ __forceinline__ bool after(uint32_t u, uint32_t v) const { return seq[u] > seq[v]; }
 };
 
+// Exclusive scan (sum) of a shared array of n words in place; *carry gets the
+// total.  Every thread scans kItems consecutive words serially, one block scan
+// combines the per-thread sums.
+__device__ __forceinline__ void block_scan_array(uint32_t* a, uint32_t n, uint32_t* scratch, uint32_t* carry) {
+  constexpr uint32_t kItems = 4;
+  if (threadIdx.x == 0) *carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n; base += blockDim.x * kItems) {
+    const uint32_t i0 = base + threadIdx.x * kItems;
+    uint32_t v[kItems];
+    uint32_t sum = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < kItems; ++k) {
+      v[k] = (i0 + k) < n ? a[i0 + k] : 0u;
+      sum += v[k];
+    }
+    uint32_t total;
+    uint32_t run = block_scan_exclusive(sum, scratch, total, OpSum()) + *carry;
+#pragma unroll
+    for (uint32_t k = 0; k < kItems; ++k) {
+      if ((i0 + k) < n) a[i0 + k] = run;
+      run += v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *carry += total;
+    __syncthreads();
+  }
+}
+
 // Bucket sort of n elements: sorted[rank] = element index.
 template <typename Key>
 __device__ __forceinline__ void block_bucket_sort(uint32_t n, const Key key, uint16_t* sorted, uint32_t* buckets,
-                                                  uint32_t nBk, uint32_t* scratch) {
+                                                  uint32_t nBk, uint32_t* scratch, uint32_t* carry) {
   for (uint32_t i = threadIdx.x; i <= nBk; i += blockDim.x) buckets[i] = 0;
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(buckets + key.bucket(i), 1u);
   __syncthreads();
-  // exclusive scan of the bucket counts (in place), blockDim.x buckets per pass
-  __shared__ uint32_t runCarry;
-  if (threadIdx.x == 0) runCarry = 0;
-  __syncthreads();
-  for (uint32_t base = 0; base < nBk; base += blockDim.x) {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < nBk ? buckets[i] : 0u;
-    uint32_t total;
-    const uint32_t excl = block_scan_exclusive(v, scratch, total, OpSum());
-    const uint32_t c = runCarry;
-    if (i < nBk) buckets[i] = c + excl;
-    __syncthreads();
-    if (threadIdx.x == 0) runCarry = c + total;
-    __syncthreads();
-  }
+  block_scan_array(buckets, nBk, scratch, carry);
   // scatter: after this loop buckets[b] is the END of bucket b
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
     sorted[atomicAdd(buckets + key.bucket(i), 1u)] = (uint16_t)i;
@@ -640,9 +718,9 @@ __device__ __forceinline__ bool tie_flagged(const TieItem& a) { return (a.val >>
 // group's slots.  seqSorted / grpOf are n-entry u16 scratch arrays.
 __device__ __forceinline__ void block_fix_ties(uint32_t n, const float* cot, const uint32_t* seq, uint32_t totalCand,
                                                uint16_t* sorted, TieItem* W, uint16_t* seqSorted, uint16_t* grpOf,
-                                               uint32_t* buckets, uint32_t nBk, uint32_t* scratch) {
+                                               uint32_t* buckets, uint32_t nBk, uint32_t* scratch, uint32_t* carry) {
   SeqKey sk{seq, totalCand > 0 ? totalCand : 1u, (int)nBk};
-  block_bucket_sort(n, sk, seqSorted, buckets, nBk, scratch);
+  block_bucket_sort(n, sk, seqSorted, buckets, nBk, scratch, carry);
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
     const uint16_t e = sorted[i];
     const float c = cot[e];
@@ -679,13 +757,20 @@ __device__ __forceinline__ void block_fix_ties(uint32_t n, const float* cot, con
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kSeedThreads, 2) k_seed_middles(const __grid_constant__ SeedParams p) {
+template <int CAPB, int CAPT, int CAPPOOL, int NBK>
+__global__ void __launch_bounds__(kSeedThreads, (sizeof(SeedLayout<CAPB, CAPT, CAPPOOL, NBK>) <= 115712) ? 2 : 1)
+k_seed_middles(const __grid_constant__ SeedParams p) {
+  using Layout = SeedLayout<CAPB, CAPT, CAPPOOL, NBK>;
   extern __shared__ __align__(16) unsigned char smemRaw[];
-  const SeedSmem S = carve_seed_smem(smemRaw, p.capB, p.capT, p.capPool, p.nBuckets);
-  SeedShared& sh = *S.sh;
+  Layout& L = *reinterpret_cast<Layout*>(smemRaw);
+  SeedShared& sh = L.sh;
   const uint32_t tid = threadIdx.x;
+  const uint32_t lane = tid & 31, warp = tid >> 5, nWarps = blockDim.x >> 5;
   const DeviceConfig& cfg = p.cfg;
   const uint32_t nWork = *p.nWorkPtr;
+  // scratch overlays on the (not yet written) sorted-top arrays
+  uint32_t* surv = reinterpret_cast<uint32_t*>(L.sCot);
+  constexpr uint32_t kSurvCap = 6u * CAPT;
 
   if (tid < (uint32_t)kCntSlots) sh.cnt[tid] = 0ull;
 
@@ -715,30 +800,34 @@ __global__ void __launch_bounds__(kSeedThreads, 2) k_seed_middles(const __grid_c
       middle_info(mid);
       sh.mid = mid;
       sh.m = m;
-      sh.nB = 0; sh.nT = 0; sh.tie = 0; sh.bad = 0; sh.carry = 0; sh.heapSize = 0; sh.poolCount = 0;
+      sh.nB = 0; sh.nT = 0; sh.tie = 0; sh.bad = 0; sh.heapSize = 0; sh.poolCount = 0;
+      sh.nextChunkA = 0; sh.nextChunkC = 0;
       sh.nBotWin = nBot; sh.nTopWin = nTop;
     }
     {
-      // first middle space point of the bin (TripletSeeder.cpp:157-181 pre-trim)
+      // first middle space point of the bin (TripletSeeder.cpp:157-181 pre-trim);
+      // one warp per neighbour bin, 32-ary searches
       const uint32_t mb0 = bs[__ldg(p.navBins + g)];
       const float firstMiddleR = ldg2(p.pZR + mb0).y;
-      if (tid < nBot) {
-        const uint32_t bin = __ldg(p.botBins + botBeg + tid);
-        const uint32_t b0 = bs[bin], b1 = bs[bin + 1];
-        const float trimValue = fsub(firstMiddleR, cfg.dRMaxB);
-        const uint32_t trim = first_true(b0, b1, [&](uint32_t i) { return !(ldg2(p.pZR + i).y < trimValue); });
-        const uint32_t s = first_true(trim, b1, [&](uint32_t i) { return fsub(rM, ldg2(p.pZR + i).y) <= cfg.dRMaxB; });
-        const uint32_t e = first_true(s, b1, [&](uint32_t i) { return fsub(rM, ldg2(p.pZR + i).y) < cfg.dRMinB; });
-        sh.winBs[tid] = s; sh.winBe[tid] = e;
-      } else if (tid >= (uint32_t)kMaxNeighborBins && tid < (uint32_t)kMaxNeighborBins + nTop) {
-        const uint32_t k = tid - (uint32_t)kMaxNeighborBins;
-        const uint32_t bin = __ldg(p.topBins + topBeg + k);
-        const uint32_t b0 = bs[bin], b1 = bs[bin + 1];
-        const float trimValue = fadd(firstMiddleR, cfg.dRMinT);
-        const uint32_t trim = first_true(b0, b1, [&](uint32_t i) { return !(ldg2(p.pZR + i).y < trimValue); });
-        const uint32_t s = first_true(trim, b1, [&](uint32_t i) { return fsub(ldg2(p.pZR + i).y, rM) >= cfg.dRMinT; });
-        const uint32_t e = first_true(s, b1, [&](uint32_t i) { return fsub(ldg2(p.pZR + i).y, rM) > cfg.dRMaxT; });
-        sh.winTs[k] = s; sh.winTe[k] = e;
+      for (uint32_t k = warp; k < nBot + nTop; k += nWarps) {
+        if (k < nBot) {
+          const uint32_t bin = __ldg(p.botBins + botBeg + k);
+          const uint32_t b0 = bs[bin], b1 = bs[bin + 1];
+          const float trimValue = fsub(firstMiddleR, cfg.dRMaxB);
+          const uint32_t trim = warp_first_true(b0, b1, [&](uint32_t i) { return !(ldg2(p.pZR + i).y < trimValue); });
+          const uint32_t s = warp_first_true(trim, b1, [&](uint32_t i) { return fsub(rM, ldg2(p.pZR + i).y) <= cfg.dRMaxB; });
+          const uint32_t e = warp_first_true(s, b1, [&](uint32_t i) { return fsub(rM, ldg2(p.pZR + i).y) < cfg.dRMinB; });
+          if (lane == 0) { sh.winBs[k] = s; sh.winBe[k] = e; }
+        } else {
+          const uint32_t kt = k - nBot;
+          const uint32_t bin = __ldg(p.topBins + topBeg + kt);
+          const uint32_t b0 = bs[bin], b1 = bs[bin + 1];
+          const float trimValue = fadd(firstMiddleR, cfg.dRMinT);
+          const uint32_t trim = warp_first_true(b0, b1, [&](uint32_t i) { return !(ldg2(p.pZR + i).y < trimValue); });
+          const uint32_t s = warp_first_true(trim, b1, [&](uint32_t i) { return fsub(ldg2(p.pZR + i).y, rM) >= cfg.dRMinT; });
+          const uint32_t e = warp_first_true(s, b1, [&](uint32_t i) { return fsub(ldg2(p.pZR + i).y, rM) > cfg.dRMaxT; });
+          if (lane == 0) { sh.winTs[kt] = s; sh.winTe[kt] = e; }
+        }
       }
     }
     __syncthreads();
@@ -754,17 +843,15 @@ __global__ void __launch_bounds__(kSeedThreads, 2) k_seed_middles(const __grid_c
     __syncthreads();
 
     // ---- phase 1: doublets (tops first, TripletSeeder.cpp:52-82) ---------
-    find_doublets<false>(p, sh, nTop, sh.winTs, sh.winTe, sh.winTp, S.tCot, S.tSeq, &sh.nT, p.capT);
-    __syncthreads();
+    find_doublets<false>(p, sh, nTop, sh.winTs, sh.winTe, sh.winTp, surv, kSurvCap, L.u.a.uCotT, L.u.a.uSeqT, &sh.nT, CAPT);
     const uint32_t nT = sh.nT;
     if (nT == 0) {
       if (tid == 0) p.slotCount[w] = 0;
       continue;
     }
-    find_doublets<true>(p, sh, nBot, sh.winBs, sh.winBe, sh.winBp, S.bCot, S.bSeq, &sh.nB, p.capB);
-    __syncthreads();
+    find_doublets<true>(p, sh, nBot, sh.winBs, sh.winBe, sh.winBp, surv, kSurvCap, L.u.a.uCotB, L.u.a.uSeqB, &sh.nB, CAPB);
     const uint32_t nB = sh.nB;
-    if (nB == 0 || nT > p.capT || nB > p.capB) {
+    if (nB == 0 || nT > (uint32_t)CAPT || nB > (uint32_t)CAPB) {
       if (tid == 0) {
         p.slotCount[w] = 0;
         if (nB != 0) {  // does not fit this launch's scratch: hand over to the large-capacity launch
@@ -780,258 +867,280 @@ __global__ void __launch_bounds__(kSeedThreads, 2) k_seed_middles(const __grid_c
     }
 
     // ---- phase 2: order both lists like DoubletSeedFinder.hpp:94-104 -------
-    const float bkScale = (float)p.nBuckets / (2.0f * cfg.cotThetaMax);
+    const float bkScale = (float)NBK / (2.0f * cfg.cotThetaMax);
+    TieItem* tieW = reinterpret_cast<TieItem*>(L.sCot);
+    uint16_t* tieSeqSorted = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(L.sCot) + 8u * CAPB);
+    uint16_t* tieGrpOf = tieSeqSorted + CAPB;
     {
-      CotKey tk{S.tCot, S.tSeq, cfg.cotThetaMax, bkScale, (int)p.nBuckets};
-      block_bucket_sort(nT, tk, S.tSorted, S.buckets, p.nBuckets, sh.scratch);
-      const bool tieT = block_has_ties(nT, S.tCot, S.tSorted, &sh.tieTmp);
-      if (tieT && tid == 0) sh.tie = 1;
-      if (tieT && p.exactTies && nT > 16) {
-        // scratch inside the sorted-top arrays, which are written only after this
-        block_fix_ties(nT, S.tCot, S.tSeq, sh.winTp[nTop], S.tSorted, reinterpret_cast<TieItem*>(S.sCot),
-                       reinterpret_cast<uint16_t*>(S.sEr), reinterpret_cast<uint16_t*>(S.sU), S.buckets,
-                       p.nBuckets, sh.scratch);
+      CotKey bk{L.u.a.uCotB, L.u.a.uSeqB, cfg.cotThetaMax, bkScale, NBK};
+      block_bucket_sort(nB, bk, L.u.a.rankB, L.buckets, NBK, sh.scratch, &sh.runCarry);
+      const bool tieB = block_has_ties(nB, L.u.a.uCotB, L.u.a.rankB, &sh.tieTmp);
+      if (tieB && tid == 0) sh.tie = 1;
+      if (tieB && p.exactTies && nB > 16) {
+        block_fix_ties(nB, L.u.a.uCotB, L.u.a.uSeqB, sh.winBp[nBot], L.u.a.rankB, tieW, tieSeqSorted, tieGrpOf, L.buckets,
+                       NBK, sh.scratch, &sh.runCarry);
+      }
+      for (uint32_t j = tid; j < nB; j += blockDim.x) {
+        const uint32_t idx = L.u.a.rankB[j];
+        L.bCot[j] = L.u.a.uCotB[idx];
+        L.bSeq[j] = L.u.a.uSeqB[idx];
       }
     }
-    // tops: full records in sorted order (recomputed from the space points)
+    {
+      CotKey tk{L.u.a.uCotT, L.u.a.uSeqT, cfg.cotThetaMax, bkScale, NBK};
+      block_bucket_sort(nT, tk, L.u.a.rankT, L.buckets, NBK, sh.scratch, &sh.runCarry);
+      const bool tieT = block_has_ties(nT, L.u.a.uCotT, L.u.a.rankT, &sh.tieTmp);
+      if (tieT && tid == 0) sh.tie = 1;
+      if (tieT && p.exactTies && nT > 16) {
+        block_fix_ties(nT, L.u.a.uCotT, L.u.a.uSeqT, sh.winTp[nTop], L.u.a.rankT, tieW, tieSeqSorted, tieGrpOf, L.buckets,
+                       NBK, sh.scratch, &sh.runCarry);
+      }
+    }
+    // tops: full records in sorted order (recomputed from the space points);
+    // from here on the sorted-top arrays hold what their names say
     for (uint32_t t = tid; t < nT; t += blockDim.x) {
-      const uint32_t idx = S.tSorted[t];
-      const uint32_t pos = seq_to_pos(S.tSeq[idx], sh.winTp, sh.winTs, nTop);
+      const uint32_t idx = L.u.a.rankT[t];
+      const uint32_t pos = seq_to_pos(L.u.a.uSeqT[idx], sh.winTp, sh.winTs, nTop);
       const float2 zr = ldg2(p.pZR + pos), xy = ldg2(p.pXY + pos), var = ldg2(p.pVar + pos);
       float dR, dZ;
       DoubletRec rec;
       doublet_zr_cuts<false>(cfg, sh.mid, zr.x, zr.y, dR, dZ);
       doublet_finish<false>(cfg, sh.mid, dR, dZ, xy.x, xy.y, zr.y, var.x, var.y, p.zWinLo, p.zWinHi, p.nZWin, rec);
-      S.sCot[t] = rec.cotTheta; S.sIDR[t] = rec.iDeltaR; S.sEr[t] = rec.er; S.sU[t] = rec.u; S.sV[t] = rec.v;
-      S.sPos[t] = pos;
+      // all reads of the arena / scratch for this t are done before the writes below
+      L.sCot[t] = rec.cotTheta; L.sIDR[t] = rec.iDeltaR; L.sEr[t] = rec.er; L.sU[t] = rec.u; L.sV[t] = rec.v;
+      L.sPos[t] = pos;
     }
-    __syncthreads();  // tCot / tSeq are dead from here on
-    {
-      CotKey bk{S.bCot, S.bSeq, cfg.cotThetaMax, bkScale, (int)p.nBuckets};
-      block_bucket_sort(nB, bk, S.bSorted, S.buckets, p.nBuckets, sh.scratch);
-      const bool tieB = block_has_ties(nB, S.bCot, S.bSorted, &sh.tieTmp);
-      if (tieB && tid == 0) sh.tie = 1;
-      if (tieB && p.exactTies && nB > 16) {
-        // scratch in the arena (tCot / tSeq / tSorted are dead, the pools not yet alive)
-        unsigned char* a = S.arena;
-        TieItem* W = reinterpret_cast<TieItem*>(a);
-        uint16_t* seqSorted = reinterpret_cast<uint16_t*>(a + align16(8ull * p.capB));
-        uint16_t* grpOf = reinterpret_cast<uint16_t*>(a + align16(8ull * p.capB) + align16(2ull * p.capB));
-        block_fix_ties(nB, S.bCot, S.bSeq, sh.winBp[nBot], S.bSorted, W, seqSorted, grpOf, S.buckets, p.nBuckets,
-                       sh.scratch);
-      }
-    }
-    __syncthreads();  // the arena now belongs to the candidate pools
+    __syncthreads();  // the arena now belongs to phase 3
 
-    // ---- phase 3: triplets + filter, one thread per bottom ---------------
+    // ---- phase 3a: H_j / brk_j scans, candidates emitted on the spot ------
     const MiddleSp mid = sh.mid;
-    unsigned long long myTests = 0, myCands = 0;
-    for (uint32_t base = 0; base < nB; base += blockDim.x) {
-      const uint32_t j = base + tid;
-      const bool valid = j < nB;
+    unsigned long long myTests = 0;
+    auto bottomCtx = [&](uint32_t j, BottomCtx& bc) {
+      const uint32_t pos = seq_to_pos(L.bSeq[j], sh.winBp, sh.winBs, nBot);
+      const float2 zr = ldg2(p.pZR + pos), xy = ldg2(p.pXY + pos), var = ldg2(p.pVar + pos);
+      float dR, dZ;
+      DoubletRec rec;
+      doublet_zr_cuts<true>(cfg, mid, zr.x, zr.y, dR, dZ);
+      doublet_finish<true>(cfg, mid, dR, dZ, xy.x, xy.y, zr.y, var.x, var.y, p.zWinLo, p.zWinHi, p.nZWin, rec);
+      bc.cotThetaB = rec.cotTheta; bc.erB = rec.er; bc.iDeltaRB = rec.iDeltaR; bc.Ub = rec.u; bc.Vb = rec.v;
+      bottom_ctx(cfg, bc);
+    };
+    auto emit = [&](uint32_t j, uint32_t t, float cu, float im) {
+      const uint32_t slot = atomicAdd(&sh.poolCount, 1u);
+      if (slot < (uint32_t)CAPPOOL) {
+        const float2 tzr = ldg2(p.pZR + L.sPos[t]);
+        float topR = tzr.y;
+        if (cfg.useDeltaRinsteadOfTopRadius) {
+          const float dr = fsub(tzr.y, mid.r), dz = fsub(tzr.x, mid.z);
+          topR = fsqrt(fadd(fmul(dr, dr), fmul(dz, dz)));
+        }
+        Cand c;
+        c.curv = cu; c.impactOrWeight = im; c.topR = topR; c.tOwner = t | (j << 16);
+        L.u.b.pool[slot] = c;
+      }
+    };
+    for (;;) {  // warps pull chunks of 32 consecutive bottoms: balances uneven windows
+      uint32_t chunk = 0;
+      if (lane == 0) chunk = atomicAdd(&sh.nextChunkA, 32u);
+      chunk = __shfl_sync(0xffffffffu, chunk, 0);
+      if (chunk >= nB) break;
+      const uint32_t j = chunk + lane;
+      if (j >= nB) continue;
       BottomCtx bc;
-      uint32_t H = 0, brk = 0;
-      if (valid) {
-        const uint32_t idx = S.bSorted[j];
-        const uint32_t pos = seq_to_pos(S.bSeq[idx], sh.winBp, sh.winBs, nBot);
-        const float2 zr = ldg2(p.pZR + pos), xy = ldg2(p.pXY + pos), var = ldg2(p.pVar + pos);
-        float dR, dZ;
-        DoubletRec rec;
-        doublet_zr_cuts<true>(cfg, mid, zr.x, zr.y, dR, dZ);
-        doublet_finish<true>(cfg, mid, dR, dZ, xy.x, xy.y, zr.y, var.x, var.y, p.zWinLo, p.zWinHi, p.nZWin, rec);
-        bc.cotThetaB = rec.cotTheta; bc.erB = rec.er; bc.iDeltaRB = rec.iDeltaR; bc.Ub = rec.u; bc.Vb = rec.v;
-        bottom_ctx(cfg, bc);
-        // |P_j|: tops with cotT <= cotB
-        uint32_t lo = 0, hi = nT;
-        while (lo < hi) {
-          const uint32_t md = (lo + hi) >> 1;
-          if (bc.cotThetaB < S.sCot[md]) hi = md; else lo = md + 1;
-        }
-        float cu, im;
-        for (int t = (int)lo - 1; t >= 0; --t) {  // last failing top of the prefix -> H_j
-          const int cls = eval_pair(cfg, mid.r, mid.varZ, mid.varR, bc, S.sCot[t], S.sEr[t], S.sIDR[t], S.sU[t], S.sV[t], cu, im);
-          if (cls == kPairFailA) { H = (uint32_t)t + 1; break; }
-          if (cls == kPairFailB) { H = (uint32_t)t; break; }
-        }
-        uint32_t k = lo;
-        for (; k < nT; ++k) {  // first failing top beyond the prefix -> brk_j
-          const int cls = eval_pair(cfg, mid.r, mid.varZ, mid.varR, bc, S.sCot[k], S.sEr[k], S.sIDR[k], S.sU[k], S.sV[k], cu, im);
-          if (cls == kPairFailA || cls == kPairFailB) break;
-        }
-        brk = k;
+      bottomCtx(j, bc);
+      uint32_t lo = 0, hi = nT;  // |P_j|: tops with cotT <= cotB
+      while (lo < hi) {
+        const uint32_t md = (lo + hi) >> 1;
+        if (bc.cotThetaB < L.sCot[md]) hi = md; else lo = md + 1;
       }
-      // window start = running max of H over the preceding bottoms
-      uint32_t blockMax;
-      const uint32_t exclMax = block_scan_exclusive(H, sh.scratch, blockMax, OpMax());
-      const uint32_t carry = sh.carry;
-      const uint32_t start = exclMax > carry ? exclMax : carry;
-      __syncthreads();
-      if (tid == 0) {
-        sh.carry = blockMax > carry ? blockMax : carry;
-        sh.poolCount = 0;
+      uint32_t H = 0, ts = 0;
+      float cu, im;
+      for (int t = (int)lo - 1; t >= 0; --t) {  // down to the last failing top of the prefix
+        ++myTests;
+        const int cls = eval_pair(cfg, mid.r, mid.varZ, mid.varR, bc, L.sCot[t], L.sEr[t], L.sIDR[t], L.sU[t], L.sV[t], cu, im);
+        if (cls == kPairFailA) { H = (uint32_t)t + 1; ts = (uint32_t)t; break; }
+        if (cls == kPairFailB) { H = (uint32_t)t; ts = (uint32_t)t; break; }
+        if (cls == kPairEmit) emit(j, (uint32_t)t, cu, im);
       }
-      __syncthreads();
+      for (uint32_t k = lo; k < nT; ++k) {  // up to the first failing top beyond the prefix
+        ++myTests;
+        const int cls = eval_pair(cfg, mid.r, mid.varZ, mid.varR, bc, L.sCot[k], L.sEr[k], L.sIDR[k], L.sU[k], L.sV[k], cu, im);
+        if (cls == kPairFailA || cls == kPairFailB) break;
+        if (cls == kPairEmit) emit(j, k, cu, im);
+      }
+      L.u.b.hval[j] = (uint16_t)H;
+      L.u.b.tstar[j] = (uint16_t)ts;
+    }
+    __syncthreads();
 
-      // emission into the linked pool
-      uint32_t nMine = 0, head = 0xFFFFu, tail = 0xFFFFu;
-      if (valid) {
-        for (uint32_t t = start; t < brk; ++t) {
-          float cu, im;
-          ++myTests;
-          const int cls = eval_pair(cfg, mid.r, mid.varZ, mid.varR, bc, S.sCot[t], S.sEr[t], S.sIDR[t], S.sU[t], S.sV[t], cu, im);
-          if (cls != kPairEmit) continue;
-          const uint32_t slot = atomicAdd(&sh.poolCount, 1u);
-          ++nMine;
-          if (slot < p.capPool) {
-            const uint32_t tp = S.sPos[t];
-            const float2 tzr = ldg2(p.pZR + tp);
-            float topR = tzr.y;
-            if (cfg.useDeltaRinsteadOfTopRadius) {
-              const float dr = fsub(tzr.y, mid.r), dz = fsub(tzr.x, mid.z);
-              topR = fsqrt(fadd(fmul(dr, dr), fmul(dz, dz)));
-            }
-            Cand c;
-            c.curv = cu; c.impactOrWeight = im; c.topR = topR; c.tOwner = t | (tid << 16);
-            S.pool[slot] = c;
-            S.poolNext[slot] = 0xFFFFu;
-            if (tail != 0xFFFFu) S.poolNext[tail] = (uint16_t)slot; else head = slot;
-            tail = slot;
-          }
-        }
-      }
-      __syncthreads();
-      const uint32_t poolCount = sh.poolCount;
-      if (poolCount > p.capPool) {
-        if (tid == 0) {
-          sh.bad = 1;
-          if (p.overflowList != nullptr) {
-            p.overflowList[atomicAdd(p.overflowCount, 1u)] = w;
-            sh.cnt[kCntMiddles] -= 1;
-          } else {
-            atomicOr(p.status, kStatusOverflowPool);
-          }
-        }
-        __syncthreads();
-        break;
-      }
-      uint32_t totalCands;
-      const uint32_t seg = block_scan_exclusive(nMine, sh.scratch, totalCands, OpSum());
-      if (poolCount == 0) continue;  // uniform
-      myCands += nMine;
-      if (nMine > 0) {
-        uint32_t cur = head;
-        for (uint32_t i = 0; i < nMine; ++i) {
-          S.pool2[seg + i] = S.pool[cur];
-          cur = S.poolNext[cur];
-        }
-        // BroadTripletSeedFilter.cpp:143-148: sort by curvature (libstdc++ replay)
-        Cand* mine = S.pool2 + seg;
-        if (nMine > 1) std_sort(mine, (int)nMine, cand_less);
-        for (uint32_t k = 0; k < nMine; ++k) {
-          const float wgt = filter_weight(
-              cfg, (int)nMine, (int)k, mine[k].impactOrWeight, [&](int i) { return mine[i].curv; },
-              [&](int i) { return mine[i].topR; });
-          mine[k].impactOrWeight = wgt;
-        }
-      }
-      __syncthreads();
-      // bounded heap pushes in the reference's order (bottom-major, curvature
-      // order): CandidatesForMiddleSp.cpp:44-75
-      if (tid < 32) {
-        const int nLow = (int)cfg.maxSeedsPerSpMConf;
-        for (uint32_t c0 = 0; c0 < poolCount && nLow > 0; c0 += 32) {
-          const uint32_t i = c0 + tid;
-          const int hs = sh.heapSize;
-          const float hmin = sh.heapMin;
-          float wgt = 0.f;
-          bool want = false;
-          if (i < poolCount) {
-            wgt = S.pool2[i].impactOrWeight;
-            want = (hs < nLow) || (wgt > hmin);
-          }
-          uint32_t mask = __ballot_sync(0xffffffffu, want);
-          if (tid == 0) {
-            while (mask != 0u) {
-              const uint32_t q = c0 + (uint32_t)(__ffs(mask) - 1);
-              mask &= mask - 1u;
-              const Cand c = S.pool2[q];
-              const float wq = c.impactOrWeight;
-              const uint32_t owner = c.tOwner >> 16, tRank = c.tOwner & 0xFFFFu;
-              const uint32_t bIdx = S.bSorted[base + owner];
-              if (sh.heapSize < nLow) {
-                StoredSeed sd;
-                sd.bottomPos = seq_to_pos(S.bSeq[bIdx], sh.winBp, sh.winBs, nBot);
-                sd.topPos = S.sPos[tRank];
-                sd.weight = wq;
-                sd.zOrigin = fsub(mid.z, fmul(mid.r, S.bCot[bIdx]));
-                const int slotI = sh.heapSize;
-                sh.storage[slotI] = sd;
-                sh.heap[slotI].weight = wq;
-                sh.heap[slotI].index = (uint32_t)slotI;
-                sh.heapSize = slotI + 1;
-                std_push_heap(sh.heap, sh.heapSize, heap_comp);
-              } else {
-                const WeightIndex smallest = sh.heap[0];
-                if (wq <= smallest.weight) continue;
-                StoredSeed sd;
-                sd.bottomPos = seq_to_pos(S.bSeq[bIdx], sh.winBp, sh.winBs, nBot);
-                sd.topPos = S.sPos[tRank];
-                sd.weight = wq;
-                sd.zOrigin = fsub(mid.z, fmul(mid.r, S.bCot[bIdx]));
-                sh.storage[smallest.index] = sd;
-                std_pop_heap(sh.heap, sh.heapSize, heap_comp);
-                sh.heap[sh.heapSize - 1].weight = wq;
-                sh.heap[sh.heapSize - 1].index = smallest.index;
-                std_push_heap(sh.heap, sh.heapSize, heap_comp);
-              }
-              sh.heapMin = sh.heap[0].weight;
-            }
-          }
-          __syncwarp();
-        }
-      }
-      __syncthreads();
-    }  // rounds over bottoms
-
-    // per-thread counters -> block counters
+    // ---- phase 3b: window start = exclusive running max of H --------------
     {
-      unsigned long long t = myTests, c = myCands;
-      for (int d = 16; d > 0; d >>= 1) {
-        t += __shfl_down_sync(0xffffffffu, t, d);
-        c += __shfl_down_sync(0xffffffffu, c, d);
+      const uint32_t chunk = (nB + blockDim.x - 1) / blockDim.x;
+      const uint32_t c0 = tid * chunk, c1 = (c0 + chunk < nB) ? c0 + chunk : nB;
+      uint32_t localMax = 0;
+      for (uint32_t j = c0; j < c1; ++j) localMax = localMax > L.u.b.hval[j] ? localMax : (uint32_t)L.u.b.hval[j];
+      uint32_t blockMax;
+      uint32_t run = block_scan_exclusive(localMax, sh.scratch, blockMax, OpMax());
+      for (uint32_t j = c0; j < c1; ++j) {
+        const uint32_t h = L.u.b.hval[j];
+        L.u.b.hval[j] = (uint16_t)run;
+        run = run > h ? run : h;
       }
-      if ((tid & 31) == 0 && !sh.bad) {
-        atomicAdd(&sh.cnt[kCntTripletTests], t);
-        atomicAdd(&sh.cnt[kCntCandidates], c);
+    }
+    __syncthreads();
+
+    // ---- phase 3c: pairs in [start_j, t*_j) that the scans did not touch --
+    for (;;) {
+      uint32_t chunk = 0;
+      if (lane == 0) chunk = atomicAdd(&sh.nextChunkC, 32u);
+      chunk = __shfl_sync(0xffffffffu, chunk, 0);
+      if (chunk >= nB) break;
+      const uint32_t j = chunk + lane;
+      if (j >= nB) continue;
+      const uint32_t s = L.u.b.hval[j], te = L.u.b.tstar[j];
+      if (s >= te) continue;
+      BottomCtx bc;
+      bottomCtx(j, bc);
+      float cu, im;
+      for (uint32_t t = s; t < te; ++t) {
+        ++myTests;
+        const int cls = eval_pair(cfg, mid.r, mid.varZ, mid.varR, bc, L.sCot[t], L.sEr[t], L.sIDR[t], L.sU[t], L.sV[t], cu, im);
+        if (cls == kPairEmit) emit(j, t, cu, im);
       }
+    }
+    for (uint32_t j = tid; j <= nB; j += blockDim.x) L.u.b.cnt[j] = 0;
+    __syncthreads();
+    const uint32_t poolCount = sh.poolCount;
+    if (poolCount > (uint32_t)CAPPOOL) {
+      if (tid == 0) {
+        p.slotCount[w] = 0;
+        if (p.overflowList != nullptr) {
+          p.overflowList[atomicAdd(p.overflowCount, 1u)] = w;
+          sh.cnt[kCntMiddles] -= 1;
+        } else {
+          atomicOr(p.status, kStatusOverflowPool);
+        }
+      }
+      continue;
+    }
+
+    // ---- phase 3d: group the candidates by bottom, curvature order inside --
+    // a candidate from the scans is only real when its top is inside the window
+    for (uint32_t e = tid; e < poolCount; e += blockDim.x) {
+      const uint32_t to = L.u.b.pool[e].tOwner;
+      const uint32_t j = to >> 16, t = to & 0xFFFFu;
+      if (t >= L.u.b.hval[j]) atomicAdd(&L.u.b.cnt[j], 1u);
+    }
+    __syncthreads();
+    block_scan_array(L.u.b.cnt, nB, sh.scratch, &sh.runCarry);
+    const uint32_t nValid = sh.runCarry;
+    for (uint32_t e = tid; e < poolCount; e += blockDim.x) {
+      const Cand c = L.u.b.pool[e];
+      const uint32_t j = c.tOwner >> 16, t = c.tOwner & 0xFFFFu;
+      if (t >= L.u.b.hval[j]) L.u.b.pool2[atomicAdd(&L.u.b.cnt[j], 1u)] = c;
+    }
+    __syncthreads();  // cnt[j] is now the END of bottom j's group
+    for (uint32_t j = tid; j < nB; j += blockDim.x) {
+      const uint32_t s = j == 0 ? 0u : L.u.b.cnt[j - 1], e = L.u.b.cnt[j];
+      if (e - s < 2) continue;
+      Cand* grp = L.u.b.pool2 + s;
+      const int n = (int)(e - s);
+      // the reference's input order is ascending top rank (emission order) ...
+      for (int i = 1; i < n; ++i) {
+        const Cand v = grp[i];
+        int q = i;
+        while (q > 0 && (grp[q - 1].tOwner & 0xFFFFu) > (v.tOwner & 0xFFFFu)) { grp[q] = grp[q - 1]; --q; }
+        grp[q] = v;
+      }
+      // ... sorted by curvature with std::ranges::sort (BroadTripletSeedFilter.cpp:143-148)
+      std_sort(grp, n, cand_less);
+    }
+    __syncthreads();
+
+    // ---- phase 3e: one thread per candidate: weight -----------------------
+    for (uint32_t i = tid; i < nValid; i += blockDim.x) {
+      const Cand c = L.u.b.pool2[i];
+      const uint32_t j = c.tOwner >> 16;
+      const uint32_t s = j == 0 ? 0u : L.u.b.cnt[j - 1], e = L.u.b.cnt[j];
+      const Cand* grp = L.u.b.pool2 + s;
+      const float wgt = filter_weight(
+          cfg, (int)(e - s), (int)(i - s), c.impactOrWeight, [&](int q) { return grp[q].curv; },
+          [&](int q) { return grp[q].topR; });
+      L.u.b.pool2[i].impactOrWeight = wgt;  // nobody reads another candidate's impact
+    }
+    __syncthreads();
+
+    // ---- phase 3f: bounded heap replay (bottom-major, curvature order) ----
+    if (tid < 32) {
+      const int nLow = (int)cfg.maxSeedsPerSpMConf;
+      for (uint32_t c0 = 0; c0 < nValid && nLow > 0; c0 += 32) {
+        const uint32_t i = c0 + tid;
+        const int hs = sh.heapSize;
+        const float hmin = sh.heapMin;
+        bool want = false;
+        if (i < nValid) want = (hs < nLow) || (L.u.b.pool2[i].impactOrWeight > hmin);
+        uint32_t mask = __ballot_sync(0xffffffffu, want);
+        if (tid == 0) {
+          while (mask != 0u) {
+            const uint32_t q = c0 + (uint32_t)(__ffs(mask) - 1);
+            mask &= mask - 1u;
+            const Cand c = L.u.b.pool2[q];
+            const float wq = c.impactOrWeight;
+            StoredSeed sd;
+            sd.tOwner = c.tOwner;
+            sd.weight = wq;
+            if (sh.heapSize < nLow) {
+              const int slotI = sh.heapSize;
+              sh.storage[slotI] = sd;
+              sh.heap[slotI].weight = wq;
+              sh.heap[slotI].index = (uint32_t)slotI;
+              sh.heapSize = slotI + 1;
+              std_push_heap(sh.heap, sh.heapSize, heap_comp);
+            } else {
+              const WeightIndex smallest = sh.heap[0];
+              if (wq <= smallest.weight) continue;
+              sh.storage[smallest.index] = sd;
+              std_pop_heap(sh.heap, sh.heapSize, heap_comp);
+              sh.heap[sh.heapSize - 1].weight = wq;
+              sh.heap[sh.heapSize - 1].index = smallest.index;
+              std_push_heap(sh.heap, sh.heapSize, heap_comp);
+            }
+            sh.heapMin = sh.heap[0].weight;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    {
+      unsigned long long t = myTests;
+      for (int d = 16; d > 0; d >>= 1) t += __shfl_down_sync(0xffffffffu, t, d);
+      if (lane == 0) atomicAdd(&sh.cnt[kCntTripletTests], t);
     }
     __syncthreads();
 
     // ---- phase 4: per-middle selection (BroadTripletSeedFilter.cpp:324-393)
     if (tid == 0) {
       uint32_t nOut = 0;
-      if (!sh.bad) {
-        std_sort_heap(sh.heap, sh.heapSize, heap_comp);
-        uint32_t maxSeeds = (uint32_t)sh.heapSize;
-        if (maxSeeds > cfg.maxSeedsPerSpM) maxSeeds = cfg.maxSeedsPerSpM + 1;
-        for (uint32_t i = 0; i < (uint32_t)sh.heapSize && i < maxSeeds; ++i) {
-          const StoredSeed sd = sh.storage[sh.heap[i].index];
-          const size_t o = (size_t)w * p.seedsPerMiddle + i;
-          p.slotB[o] = sd.bottomPos;
-          p.slotM[o] = m;
-          p.slotT[o] = sd.topPos;
-          p.slotQ[o] = sd.weight;
-          p.slotZ[o] = sd.zOrigin;
-          ++nOut;
-        }
+      std_sort_heap(sh.heap, sh.heapSize, heap_comp);
+      uint32_t maxSeeds = (uint32_t)sh.heapSize;
+      if (maxSeeds > cfg.maxSeedsPerSpM) maxSeeds = cfg.maxSeedsPerSpM + 1;
+      for (uint32_t i = 0; i < (uint32_t)sh.heapSize && i < maxSeeds; ++i) {
+        const StoredSeed sd = sh.storage[sh.heap[i].index];
+        const uint32_t j = sd.tOwner >> 16, tRank = sd.tOwner & 0xFFFFu;
+        const size_t o = (size_t)w * p.seedsPerMiddle + i;
+        p.slotB[o] = seq_to_pos(L.bSeq[j], sh.winBp, sh.winBs, nBot);
+        p.slotM[o] = m;
+        p.slotT[o] = L.sPos[tRank];
+        p.slotQ[o] = sd.weight;
+        p.slotZ[o] = fsub(mid.z, fmul(mid.r, L.bCot[j]));  // zOrigin, BroadTripletSeedFilter.cpp:119
+        ++nOut;
       }
       p.slotCount[w] = nOut;
-      if (!sh.bad) {
-        sh.cnt[kCntBottomDoublets] += nB;
-        sh.cnt[kCntTopDoublets] += nT;
-        sh.cnt[kCntSeeds] += nOut;
-        sh.cnt[kCntTieMiddles] += sh.tie;
-      }
+      sh.cnt[kCntBottomDoublets] += nB;
+      sh.cnt[kCntTopDoublets] += nT;
+      sh.cnt[kCntCandidates] += nValid;
+      sh.cnt[kCntSeeds] += nOut;
+      sh.cnt[kCntTieMiddles] += sh.tie;
     }
   }
   __syncthreads();
@@ -1039,6 +1148,12 @@ __global__ void __launch_bounds__(kSeedThreads, 2) k_seed_middles(const __grid_c
     atomicAdd(p.counters + tid, sh.cnt[tid]);
   }
 }
+
+// the two capacity tiers (see seeding_plugin.cu)
+constexpr int kCapB0 = 2304, kCapT0 = 1664, kCapPool0 = 864, kBuckets = 2048;
+constexpr int kCapB1 = 3584, kCapT1 = 2816, kCapPool1 = 2048;
+using SeedLayout0 = SeedLayout<kCapB0, kCapT0, kCapPool0, kBuckets>;
+using SeedLayout1 = SeedLayout<kCapB1, kCapT1, kCapPool1, kBuckets>;
 
 // ---------------------------------------------------------------------------
 // Seed compaction (ordered): tiled exclusive scan of the per-middle counts

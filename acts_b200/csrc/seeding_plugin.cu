@@ -72,10 +72,9 @@ struct b200seed_handle {
   cudaStream_t stream = nullptr;
   int smCount = 0, ccMajor = 0, ccMinor = 0;
   // engine tunables
-  // per-middle shared-memory capacities: tier 0 takes every middle at 2 blocks
-  // per SM, middles that do not fit are re-queued to tier 1 (1 block per SM)
-  uint32_t capB[2] = {2304, 4608}, capT[2] = {1792, 3584}, capPool[2] = {896, 1792};
-  uint32_t nBuckets = 2048;
+  // per-middle shared-memory capacities are compile-time (seeding_kernels.cuh):
+  // tier 0 takes every middle at 2 blocks per SM, middles that do not fit are
+  // re-queued to tier 1 (1 block per SM)
   uint32_t sortSmemCap = 4096;
   int exactTies = 1;
   int seedBlocksPerSM[2] = {1, 1};
@@ -244,7 +243,6 @@ int enqueue(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal, const uint32_
   sp.slotQ = h->slotQ.as<float>(); sp.slotZ = h->slotZ.as<float>();
   sp.slotCount = h->slotCount.as<uint32_t>();
   sp.seedsPerMiddle = std::max<uint32_t>(plan.seedsPerMiddle, 1);
-  sp.nBuckets = h->nBuckets;
   sp.exactTies = h->exactTies;
   sp.counters = gp.counters;
   sp.status = gp.status;
@@ -255,16 +253,14 @@ int enqueue(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal, const uint32_
   sp.workList = nullptr;
   sp.overflowList = h->overflowList.as<uint32_t>();
   sp.overflowCount = wc + 1;
-  sp.capB = h->capB[0]; sp.capT = h->capT[0]; sp.capPool = h->capPool[0];
-  k_seed_middles<<<h->smCount * h->seedBlocksPerSM[0], kSeedThreads, h->seedSmemBytes[0], s>>>(sp);
+  k_seed_middles<kCapB0, kCapT0, kCapPool0, kBuckets><<<h->smCount * h->seedBlocksPerSM[0], kSeedThreads, h->seedSmemBytes[0], s>>>(sp);
   // tier 1: the middles that did not fit, with the large scratch
   sp.workCounter = wc + 2;
   sp.workList = h->overflowList.as<uint32_t>();
   sp.nWorkPtr = wc + 1;
   sp.overflowList = nullptr;
   sp.overflowCount = nullptr;
-  sp.capB = h->capB[1]; sp.capT = h->capT[1]; sp.capPool = h->capPool[1];
-  k_seed_middles<<<h->smCount * h->seedBlocksPerSM[1], kSeedThreads, h->seedSmemBytes[1], s>>>(sp);
+  k_seed_middles<kCapB1, kCapT1, kCapPool1, kBuckets><<<h->smCount * h->seedBlocksPerSM[1], kSeedThreads, h->seedSmemBytes[1], s>>>(sp);
   sp.nWorkPtr = wp.workStart + nNavAll;
   launches += 2;
 
@@ -328,9 +324,8 @@ int finish(b200seed_handle* h, cudaStream_t s, b200seed_seeds* out) {
   const int st = *h->hStatus;
   if (st & (kStatusOverflowDoublets | kStatusOverflowPool)) {
     return fail(B200SEED_ERR_OVERFLOW,
-                "per-middle scratch exhausted even in the large tier (doublets > " + std::to_string(h->capB[1]) +
-                    "/" + std::to_string(h->capT[1]) + " or candidates per round > " +
-                    std::to_string(h->capPool[1]) + "); raise B200SEED_CAP{B,T,POOL}_LARGE");
+                "per-middle scratch exhausted even in the large tier (doublets > " + std::to_string(kCapB1) + "/" +
+                    std::to_string(kCapT1) + " or candidates per middle > " + std::to_string(kCapPool1) + ")");
   }
   if (*h->hSeedTotal > h->lastCapacity) {
     return fail(B200SEED_ERR_CAPACITY, "seed buffers too small: need " + std::to_string(*h->hSeedTotal));
@@ -441,32 +436,25 @@ int b200seed_create(const b200seed_config* cfg, int device, b200seed_handle** ou
   CREATE_TRY(cudaMallocHost(&h->hStatus, 16));
   CREATE_TRY(cudaMallocHost(&h->hSeedTotal, 16));
 
-  h->capB[0] = env_u32("B200SEED_CAPB", h->capB[0]);
-  h->capT[0] = env_u32("B200SEED_CAPT", h->capT[0]);
-  h->capPool[0] = env_u32("B200SEED_CAPPOOL", h->capPool[0]);
-  h->capB[1] = env_u32("B200SEED_CAPB_LARGE", h->capB[1]);
-  h->capT[1] = env_u32("B200SEED_CAPT_LARGE", h->capT[1]);
-  h->capPool[1] = env_u32("B200SEED_CAPPOOL_LARGE", h->capPool[1]);
-  h->nBuckets = env_u32("B200SEED_BUCKETS", h->nBuckets);
   h->exactTies = (int)env_u32("B200SEED_EXACT_TIES", 1);
-  size_t maxSmem = 0;
-  for (int t = 0; t < 2; ++t) {
-    if (h->capB[t] > 65534 || h->capT[t] > 65534 || h->capPool[t] > 65534 || h->capB[t] < 32 || h->capT[t] < 32 ||
-        h->capPool[t] < 32) {
-      return cleanup(fail(B200SEED_ERR_INVALID_ARGUMENT, "B200SEED_CAP* must lie in [32, 65534]"));
-    }
-    h->seedSmemBytes[t] = seed_smem_bytes(h->capB[t], h->capT[t], h->capPool[t], h->nBuckets);
-    if (h->seedSmemBytes[t] > (size_t)prop.sharedMemPerBlockOptin) {
-      return cleanup(fail(B200SEED_ERR_INVALID_ARGUMENT, "per-middle scratch does not fit shared memory"));
-    }
-    maxSmem = std::max(maxSmem, h->seedSmemBytes[t]);
+  h->seedSmemBytes[0] = sizeof(SeedLayout0);
+  h->seedSmemBytes[1] = sizeof(SeedLayout1);
+  if (h->seedSmemBytes[1] > (size_t)prop.sharedMemPerBlockOptin) {
+    return cleanup(fail(B200SEED_ERR_CUDA, "device offers less shared memory per block than the seeding kernel needs"));
   }
-  CREATE_TRY(cudaFuncSetAttribute(k_seed_middles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem));
+  CREATE_TRY(cudaFuncSetAttribute(k_seed_middles<kCapB0, kCapT0, kCapPool0, kBuckets>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seedSmemBytes[0]));
+  CREATE_TRY(cudaFuncSetAttribute(k_seed_middles<kCapB1, kCapT1, kCapPool1, kBuckets>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seedSmemBytes[1]));
   CREATE_TRY(cudaFuncSetAttribute(k_sort_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->sortSmemCap * 8)));
-  for (int t = 0; t < 2; ++t) {
-    int blocksPerSM = 0;
-    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_seed_middles, kSeedThreads, h->seedSmemBytes[t]));
-    h->seedBlocksPerSM[t] = std::max(1, blocksPerSM);
+  {
+    int b0 = 0, b1 = 0;
+    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_seed_middles<kCapB0, kCapT0, kCapPool0, kBuckets>,
+                                                             kSeedThreads, h->seedSmemBytes[0]));
+    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_seed_middles<kCapB1, kCapT1, kCapPool1, kBuckets>,
+                                                             kSeedThreads, h->seedSmemBytes[1]));
+    h->seedBlocksPerSM[0] = std::max(1, b0);
+    h->seedBlocksPerSM[1] = std::max(1, b1);
   }
 
   int rc = upload(h->navBins, h->plan.navBins, h->stream);
