@@ -62,6 +62,25 @@ def build_model(force: bool = False) -> str:
     return MODEL_SO
 
 
+HOST_TEST_BIN = os.path.join(ROOT, "tests", "cpp", "host_mirror_main")
+
+
+def build_host_mirror_test(force: bool = False) -> str:
+    """C++20 driver of the host mirror class, linked against the plugin."""
+    src = os.path.join(ROOT, "tests", "cpp", "host_mirror_main.cpp")
+    hdr = os.path.join(ROOT, "acts_b200", "host", "GridTripletSeedingAlgorithm.hpp")
+    build_plugin()
+    if force or _stale(HOST_TEST_BIN, [src, hdr, PLUGIN_SO]):
+        cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=gnu++20", "-Wall", "-o", HOST_TEST_BIN, src,
+               "-L" + os.path.dirname(PLUGIN_SO), "-lacts_b200_seeding", "-Wl,-rpath," + os.path.dirname(PLUGIN_SO)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("g++ failed building the host mirror test")
+    return HOST_TEST_BIN
+
+
 if __name__ == "__main__":
     print(build_plugin(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_model(force="--force" in sys.argv))
+    print(build_host_mirror_test(force="--force" in sys.argv))

@@ -1,0 +1,218 @@
+// GridTripletSeedingAlgorithm.hpp -- C++20 host-side mirror of the reference
+// interface over the C ABI of the B200 plugin.
+//
+// Mirrors ActsExamples::GridTripletSeedingAlgorithm
+// (Examples/Algorithms/TrackFinding/include/ActsExamples/TrackFinding/
+// GridTripletSeedingAlgorithm.hpp:32-288): the nested Config has the same field
+// names, types, defaults and units; the constructor validates like the reference
+// constructor chain and throws the same exception classes
+// (std::invalid_argument / std::runtime_error / std::domain_error); execute()
+// takes the six float columns of the input SpacePointContainer and returns the
+// columns of the output SeedContainer (Core/include/Acts/EventData/
+// SeedContainer.hpp:208-213) in the reference's order.  Inside ACTS this class
+// body is what a Plugins/B200Seeding algorithm would contain, with the column
+// spans taken from SpacePointContainer::xColumn() etc..
+//
+// Header only; link against libacts_b200_seeding.so.  No CPU fallback.
+#pragma once
+
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <limits>
+#include <numbers>
+#include <span>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/acts_b200_seeding.h"
+
+namespace ActsB200 {
+
+/// Acts::SeedConfirmationRangeConfig
+struct SeedConfirmationRangeConfig {
+  float zMinSeedConf = std::numeric_limits<float>::lowest();
+  float zMaxSeedConf = std::numeric_limits<float>::max();
+  float rMaxSeedConf = std::numeric_limits<float>::max();
+  std::size_t nTopForLargeR = 0;
+  std::size_t nTopForSmallR = 0;
+  float seedConfMinBottomRadius = 60.f;
+  float seedConfMaxZOrigin = 150.f;
+  float minImpactSeedConf = 1.f;
+};
+
+/// Output seed columns (Acts::SeedContainer): indices refer to the caller's
+/// space point columns.
+struct SeedColumns {
+  std::vector<std::uint32_t> bottom, middle, top;
+  std::vector<float> quality, vertexZ;
+  std::size_t size() const { return quality.size(); }
+};
+
+/// Input space point columns (Acts::SpacePointContainer X, Y, Z, R, VarianceZ, VarianceR).
+struct SpacePointColumns {
+  std::span<const float> x, y, z, r, varianceZ, varianceR;
+};
+
+class GridTripletSeedingAlgorithm final {
+ public:
+  struct Config {
+    // identical to the reference Config, GridTripletSeedingAlgorithm.hpp:34-244
+    float bFieldInZ = static_cast<float>(2 * 0.000299792458);
+    float minPt = 0.4f;
+    float cotThetaMax = 10.01788f;
+    float impactMax = 20.f;
+    float deltaRMin = 5.f;
+    float deltaRMax = 270.f;
+    float deltaRMinTop = std::numeric_limits<float>::quiet_NaN();
+    float deltaRMaxTop = std::numeric_limits<float>::quiet_NaN();
+    float deltaRMinBottom = std::numeric_limits<float>::quiet_NaN();
+    float deltaRMaxBottom = std::numeric_limits<float>::quiet_NaN();
+    float rMin = 0.f;
+    float rMax = 600.f;
+    float zMin = -2800.f;
+    float zMax = 2800.f;
+    float phiMin = -std::numbers::pi_v<float>;
+    float phiMax = std::numbers::pi_v<float>;
+    int phiBinDeflectionCoverage = 1;
+    int maxPhiBins = 10000;
+    std::vector<std::pair<int, int>> zBinNeighborsTop;
+    std::vector<std::pair<int, int>> zBinNeighborsBottom;
+    int numPhiNeighbors = 1;
+    std::vector<float> zBinEdges;
+    std::vector<std::size_t> zBinsCustomLooping;
+    float rMinMiddle = 60.f;
+    float rMaxMiddle = 120.f;
+    bool useVariableMiddleSPRange = false;
+    std::vector<std::vector<float>> rRangeMiddleSP;
+    float deltaRMiddleMinSPRange = 10.f;
+    float deltaRMiddleMaxSPRange = 10.f;
+    float deltaZMin = -std::numeric_limits<float>::infinity();
+    float deltaZMax = std::numeric_limits<float>::infinity();
+    bool interactionPointCut = false;
+    float collisionRegionMin = -150.f;
+    float collisionRegionMax = +150.f;
+    float helixCutTolerance = 1.f;
+    float sigmaScattering = 5.f;
+    float radLengthPerSeed = 0.05f;
+    float toleranceParam = 1.1f;
+    float deltaInvHelixDiameter = 0.00003f;
+    float compatSeedWeight = 200.f;
+    float impactWeightFactor = 1.f;
+    float zOriginWeightFactor = 1.f;
+    unsigned int maxSeedsPerSpM = 5;
+    std::size_t compatSeedLimit = 2;
+    float seedWeightIncrement = 0.f;
+    float numSeedIncrement = std::numeric_limits<float>::infinity();
+    bool seedConfirmation = false;
+    SeedConfirmationRangeConfig centralSeedConfirmationRange;
+    SeedConfirmationRangeConfig forwardSeedConfirmationRange;
+    std::uint32_t maxSeedsPerSpMConf = 5;
+    std::uint32_t maxQualitySeedsPerSpMConf = 5;
+    bool useDeltaRinsteadOfTopRadius = false;
+    bool useExtraCuts = false;
+    /// engine option: CUDA device ordinal
+    int device = 0;
+  };
+
+  explicit GridTripletSeedingAlgorithm(const Config& cfg) : m_cfg(cfg) {
+    b200seed_config c{};
+    b200seed_config_init(&c);
+    c.bFieldInZ = cfg.bFieldInZ; c.minPt = cfg.minPt; c.cotThetaMax = cfg.cotThetaMax; c.impactMax = cfg.impactMax;
+    c.deltaRMin = cfg.deltaRMin; c.deltaRMax = cfg.deltaRMax;
+    c.deltaRMinTop = cfg.deltaRMinTop; c.deltaRMaxTop = cfg.deltaRMaxTop;
+    c.deltaRMinBottom = cfg.deltaRMinBottom; c.deltaRMaxBottom = cfg.deltaRMaxBottom;
+    c.rMin = cfg.rMin; c.rMax = cfg.rMax; c.zMin = cfg.zMin; c.zMax = cfg.zMax;
+    c.phiMin = cfg.phiMin; c.phiMax = cfg.phiMax;
+    c.phiBinDeflectionCoverage = cfg.phiBinDeflectionCoverage; c.maxPhiBins = cfg.maxPhiBins;
+    for (const auto& [a, b] : cfg.zBinNeighborsTop) { m_zTop.push_back(a); m_zTop.push_back(b); }
+    for (const auto& [a, b] : cfg.zBinNeighborsBottom) { m_zBottom.push_back(a); m_zBottom.push_back(b); }
+    c.zBinNeighborsTop = m_zTop.data(); c.nZBinNeighborsTop = static_cast<std::uint32_t>(cfg.zBinNeighborsTop.size());
+    c.zBinNeighborsBottom = m_zBottom.data(); c.nZBinNeighborsBottom = static_cast<std::uint32_t>(cfg.zBinNeighborsBottom.size());
+    c.numPhiNeighbors = cfg.numPhiNeighbors;
+    c.zBinEdges = cfg.zBinEdges.data(); c.nZBinEdges = static_cast<std::uint32_t>(cfg.zBinEdges.size());
+    for (std::size_t v : cfg.zBinsCustomLooping) m_looping.push_back(v);
+    c.zBinsCustomLooping = m_looping.data(); c.nZBinsCustomLooping = static_cast<std::uint32_t>(m_looping.size());
+    c.rMinMiddle = cfg.rMinMiddle; c.rMaxMiddle = cfg.rMaxMiddle;
+    c.useVariableMiddleSPRange = cfg.useVariableMiddleSPRange;
+    for (const auto& v : cfg.rRangeMiddleSP) {
+      if (v.size() < 2) throw std::invalid_argument("rRangeMiddleSP entries need {rMin, rMax}");
+      m_rRange.push_back(v[0]); m_rRange.push_back(v[1]);
+    }
+    c.rRangeMiddleSP = m_rRange.data(); c.nRRangeMiddleSP = static_cast<std::uint32_t>(cfg.rRangeMiddleSP.size());
+    c.deltaRMiddleMinSPRange = cfg.deltaRMiddleMinSPRange; c.deltaRMiddleMaxSPRange = cfg.deltaRMiddleMaxSPRange;
+    c.deltaZMin = cfg.deltaZMin; c.deltaZMax = cfg.deltaZMax; c.interactionPointCut = cfg.interactionPointCut;
+    c.collisionRegionMin = cfg.collisionRegionMin; c.collisionRegionMax = cfg.collisionRegionMax;
+    c.helixCutTolerance = cfg.helixCutTolerance; c.sigmaScattering = cfg.sigmaScattering;
+    c.radLengthPerSeed = cfg.radLengthPerSeed; c.toleranceParam = cfg.toleranceParam;
+    c.deltaInvHelixDiameter = cfg.deltaInvHelixDiameter; c.compatSeedWeight = cfg.compatSeedWeight;
+    c.impactWeightFactor = cfg.impactWeightFactor; c.zOriginWeightFactor = cfg.zOriginWeightFactor;
+    c.maxSeedsPerSpM = cfg.maxSeedsPerSpM; c.compatSeedLimit = cfg.compatSeedLimit;
+    c.seedWeightIncrement = cfg.seedWeightIncrement; c.numSeedIncrement = cfg.numSeedIncrement;
+    c.seedConfirmation = cfg.seedConfirmation;
+    copyRange(cfg.centralSeedConfirmationRange, c.centralSeedConfirmationRange);
+    copyRange(cfg.forwardSeedConfirmationRange, c.forwardSeedConfirmationRange);
+    c.maxSeedsPerSpMConf = cfg.maxSeedsPerSpMConf; c.maxQualitySeedsPerSpMConf = cfg.maxQualitySeedsPerSpMConf;
+    c.useDeltaRinsteadOfTopRadius = cfg.useDeltaRinsteadOfTopRadius; c.useExtraCuts = cfg.useExtraCuts;
+    check(b200seed_create(&c, cfg.device, &m_handle));
+  }
+  ~GridTripletSeedingAlgorithm() { b200seed_destroy(m_handle); }
+  GridTripletSeedingAlgorithm(const GridTripletSeedingAlgorithm&) = delete;
+  GridTripletSeedingAlgorithm& operator=(const GridTripletSeedingAlgorithm&) = delete;
+
+  /// Run the seeding algorithm on one event (reference: execute(ctx), .cpp:180-402).
+  /// `zWindows` are the optional per-event vertex z-windows (VertexZCuts, .cpp:69-97).
+  SeedColumns execute(const SpacePointColumns& sp,
+                      std::span<const std::pair<float, float>> zWindows = {}) const {
+    const std::size_t n = sp.x.size();
+    if (sp.y.size() != n || sp.z.size() != n || sp.r.size() != n || sp.varianceZ.size() != n || sp.varianceR.size() != n) {
+      throw std::invalid_argument("space point columns differ in length");
+    }
+    std::vector<float> lo, hi;
+    for (const auto& [a, b] : zWindows) { lo.push_back(a); hi.push_back(b); }
+    SeedColumns out;
+    std::size_t cap = std::max<std::size_t>(16, 2 * n);
+    for (;;) {
+      out.bottom.resize(cap); out.middle.resize(cap); out.top.resize(cap); out.quality.resize(cap); out.vertexZ.resize(cap);
+      b200seed_seeds s{out.bottom.data(), out.middle.data(), out.top.data(), out.quality.data(), out.vertexZ.data(), cap, 0};
+      const int rc = b200seed_run(m_handle, static_cast<std::uint32_t>(n), sp.x.data(), sp.y.data(), sp.z.data(), sp.r.data(),
+                                  sp.varianceZ.data(), sp.varianceR.data(), static_cast<std::uint32_t>(lo.size()), lo.data(),
+                                  hi.data(), &s);
+      if (rc == B200SEED_ERR_CAPACITY) { cap = s.size; continue; }
+      check(rc);
+      out.bottom.resize(s.size); out.middle.resize(s.size); out.top.resize(s.size); out.quality.resize(s.size); out.vertexZ.resize(s.size);
+      return out;
+    }
+  }
+
+  const Config& config() const { return m_cfg; }
+  b200seed_counters counters() const { b200seed_counters c{}; b200seed_get_counters(m_handle, &c); return c; }
+
+ private:
+  static void copyRange(const SeedConfirmationRangeConfig& a, b200seed_seed_confirmation_range& b) {
+    b.zMinSeedConf = a.zMinSeedConf; b.zMaxSeedConf = a.zMaxSeedConf; b.rMaxSeedConf = a.rMaxSeedConf;
+    b.nTopForLargeR = a.nTopForLargeR; b.nTopForSmallR = a.nTopForSmallR;
+    b.seedConfMinBottomRadius = a.seedConfMinBottomRadius; b.seedConfMaxZOrigin = a.seedConfMaxZOrigin;
+    b.minImpactSeedConf = a.minImpactSeedConf;
+  }
+  /// status code -> the exception class the reference throws
+  static void check(int rc) {
+    if (rc == B200SEED_OK) return;
+    const std::string msg = b200seed_last_error();
+    switch (rc) {
+      case B200SEED_ERR_INVALID_ARGUMENT: throw std::invalid_argument(msg);
+      case B200SEED_ERR_DOMAIN: throw std::domain_error(msg);
+      default: throw std::runtime_error(msg);
+    }
+  }
+
+  Config m_cfg;
+  std::vector<std::int32_t> m_zTop, m_zBottom;
+  std::vector<std::uint64_t> m_looping;
+  std::vector<float> m_rRange;
+  b200seed_handle* m_handle = nullptr;
+};
+
+}  // namespace ActsB200

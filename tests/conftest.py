@@ -18,6 +18,7 @@ def built():
 
     build.build_plugin()
     build.build_model()
+    build.build_host_mirror_test()
     from oracle import oracle as O
 
     O.build()
