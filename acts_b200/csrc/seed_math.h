@@ -385,9 +385,10 @@ enum PairClass : int {
   kPairEmit = 3    // candidate {top, curvature, impact}         (:155)
 };
 
-B2S_HD int eval_pair(const DeviceConfig& c, float rM, float varZM, float varRM,
-                     const BottomCtx& b, float cotThetaT, float erT, float iDeltaRT,
-                     float uT, float vT, float& curvature, float& impact) {
+template <bool kWithCurvature>
+B2S_HD int eval_pair_t(const DeviceConfig& c, float rM, float varZM, float varRM,
+                       const BottomCtx& b, float cotThetaT, float erT, float iDeltaRT,
+                       float uT, float vT, float& curvature, float& impact) {
   const float cotThetaAvg2 = fmul(b.cotThetaB, cotThetaT);
   // erT + erB + ((2 * (cotAvg2*varRM + varZM)) * iDeltaRB) * iDeltaRT, left to right
   const float corr = fmul(fmul(fmul(2.0f, fadd(fmul(cotThetaAvg2, varRM), varZM)), b.iDeltaRB), iDeltaRT);
@@ -407,9 +408,23 @@ B2S_HD int eval_pair(const DeviceConfig& c, float rM, float varZM, float varRM,
   if (deltaCotTheta2 > fadd(error2, p2scatterSigma)) return kPairFailB;
   const float im = fabs_(fmul(fsub(A, fmul(B, rM)), rM));
   if (im > c.impactMax) return kPairSkip;
-  curvature = fdiv(B, fsqrt(S2));
-  impact = im;
+  if (kWithCurvature) {
+    curvature = fdiv(B, fsqrt(S2));
+    impact = im;
+  }
   return kPairEmit;
+}
+B2S_HD int eval_pair(const DeviceConfig& c, float rM, float varZM, float varRM,
+                     const BottomCtx& b, float cotThetaT, float erT, float iDeltaRT,
+                     float uT, float vT, float& curvature, float& impact) {
+  return eval_pair_t<true>(c, rM, varZM, varRM, b, cotThetaT, erT, iDeltaRT, uT, vT, curvature, impact);
+}
+// classification only (the scans): no curvature division / square root
+B2S_HD int classify_pair(const DeviceConfig& c, float rM, float varZM, float varRM,
+                         const BottomCtx& b, float cotThetaT, float erT, float iDeltaRT,
+                         float uT, float vT) {
+  float cu, im;
+  return eval_pair_t<false>(c, rM, varZM, varRM, b, cotThetaT, erT, iDeltaRT, uT, vT, cu, im);
 }
 
 // ---------------------------------------------------------------------------
@@ -642,6 +657,34 @@ template <typename T, typename Less, typename Flagged>
 B2S_HD void std_sort_replay_ties(T* a, int n, Less less, Flagged flagged) {
   if (n <= 16) return;  // plain insertion sort: stable, input order decides
   constexpr int kThreshold = 16;
+  constexpr int kMaxTracked = 24;
+  // positions of the flagged elements, kept up to date across swaps so that
+  // "does this range still hold two tied elements" costs O(#tied) instead of a scan
+  int fpos[kMaxTracked];
+  int nf = 0;
+  bool tracked = true;
+  for (int i = 0; i < n; ++i) {
+    if (flagged(a[i])) {
+      if (nf < kMaxTracked) fpos[nf++] = i; else { tracked = false; }
+    }
+  }
+  auto countIn = [&](int first, int last) {
+    int c = 0;
+    if (tracked) {
+      for (int k = 0; k < nf; ++k) c += (fpos[k] >= first && fpos[k] < last) ? 1 : 0;
+    } else {
+      for (int i = first; i < last && c < 2; ++i) c += flagged(a[i]) ? 1 : 0;
+    }
+    return c;
+  };
+  auto swapAt = [&](int i, int j) {
+    const T t = a[i]; a[i] = a[j]; a[j] = t;
+    if (tracked && (flagged(t) || flagged(a[i]))) {
+      for (int k = 0; k < nf; ++k) {
+        if (fpos[k] == i) fpos[k] = j; else if (fpos[k] == j) fpos[k] = i;
+      }
+    }
+  };
   int lg = 0;
   for (unsigned v = (unsigned)n; v > 1; v >>= 1) ++lg;
   int stackFirst[64], stackLast[64], stackDepth[64];
@@ -651,13 +694,11 @@ B2S_HD void std_sort_replay_ties(T* a, int n, Less less, Flagged flagged) {
     --sp;
     int first = stackFirst[sp], last = stackLast[sp], depth = stackDepth[sp];
     while (last - first > kThreshold) {
-      int nFlagged = 0;
-      for (int i = first; i < last && nFlagged < 2; ++i) nFlagged += flagged(a[i]) ? 1 : 0;
-      if (nFlagged < 2) break;  // nothing left to decide in this range
+      if (countIn(first, last) < 2) break;  // nothing left to decide in this range
       if (depth == 0) {
         std_make_heap(a + first, last - first, less);
         std_sort_heap(a + first, last - first, less);
-        break;
+        break;  // (positions inside a heap-sorted range no longer matter: it is final)
       }
       --depth;
       const int mid = first + (last - first) / 2;
@@ -671,15 +712,16 @@ B2S_HD void std_sort_replay_ties(T* a, int n, Less less, Flagged flagged) {
         } else if (less(a[ia], a[ic])) pick = ia;
         else if (less(a[ib], a[ic])) pick = ic;
         else pick = ib;
-        const T t = a[first]; a[first] = a[pick]; a[pick] = t;
+        swapAt(first, pick);
       }
+      const T pivot = a[first];
       int lo = first + 1, hi = last;
       while (true) {
-        while (less(a[lo], a[first])) ++lo;
+        while (less(a[lo], pivot)) ++lo;
         --hi;
-        while (less(a[first], a[hi])) --hi;
+        while (less(pivot, a[hi])) --hi;
         if (!(lo < hi)) break;
-        const T t = a[lo]; a[lo] = a[hi]; a[hi] = t;
+        swapAt(lo, hi);
         ++lo;
       }
       const int cut = lo;

@@ -461,6 +461,7 @@ struct SeedShared {
   WeightIndex heap[kMaxHeap];
   StoredSeed storage[kMaxHeap];
   int heapSize;
+  int heapSorted;
   float heapMin;
   unsigned long long cnt[kCntSlots];
 };
@@ -494,8 +495,8 @@ struct SeedLayout {
       uint16_t rankT[CAPT];
     } a;
     struct {
-      Cand pool[CAPPOOL];
-      Cand pool2[CAPPOOL];
+      uint32_t pool[CAPPOOL];  // emission order: sorted top rank | sorted bottom rank << 16
+      Cand pool2[CAPPOOL];     // grouped by bottom, curvature order
       uint32_t cnt[CAPB + 1];
       uint16_t hval[CAPB];   // F value of the last failing top, later the window start
       uint16_t tstar[CAPB];  // rank of the last failing top of the prefix
@@ -773,13 +774,13 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
   constexpr uint32_t kSurvCap = 6u * CAPT;
 
   if (tid < (uint32_t)kCntSlots) sh.cnt[tid] = 0ull;
+  auto fetchWork = [&]() {  // thread 0 only
+    const uint32_t item = atomicAdd(p.workCounter, 1u);
+    sh.w = item < nWork ? (p.workList != nullptr ? p.workList[item] : item) : 0xFFFFFFFFu;
+  };
+  if (tid == 0) fetchWork();
 
   for (;;) {
-    __syncthreads();
-    if (tid == 0) {
-      const uint32_t item = atomicAdd(p.workCounter, 1u);
-      sh.w = item < nWork ? (p.workList != nullptr ? p.workList[item] : item) : 0xFFFFFFFFu;
-    }
     __syncthreads();
     const uint32_t w = sh.w;
     if (w == 0xFFFFFFFFu) break;
@@ -801,7 +802,7 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
       sh.mid = mid;
       sh.m = m;
       sh.nB = 0; sh.nT = 0; sh.tie = 0; sh.bad = 0; sh.heapSize = 0; sh.poolCount = 0;
-      sh.nextChunkA = 0; sh.nextChunkC = 0;
+      sh.nextChunkA = 0; sh.nextChunkC = 0; sh.heapSorted = 0;
       sh.nBotWin = nBot; sh.nTopWin = nTop;
     }
     {
@@ -841,6 +842,7 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
       sh.cnt[kCntMiddles] += 1;
     }
     __syncthreads();
+    if (tid == 0) fetchWork();  // next item: the global atomic's latency hides behind phase 1
 
     // ---- phase 1: doublets (tops first, TripletSeeder.cpp:52-82) ---------
     find_doublets<false>(p, sh, nTop, sh.winTs, sh.winTe, sh.winTp, surv, kSurvCap, L.u.a.uCotT, L.u.a.uSeqT, &sh.nT, CAPT);
@@ -914,7 +916,7 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
 
     // ---- phase 3a: H_j / brk_j scans, candidates emitted on the spot ------
     const MiddleSp mid = sh.mid;
-    unsigned long long myTests = 0;
+    uint32_t myTests = 0;
     auto bottomCtx = [&](uint32_t j, BottomCtx& bc) {
       const uint32_t pos = seq_to_pos(L.bSeq[j], sh.winBp, sh.winBs, nBot);
       const float2 zr = ldg2(p.pZR + pos), xy = ldg2(p.pXY + pos), var = ldg2(p.pVar + pos);
@@ -925,19 +927,9 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
       bc.cotThetaB = rec.cotTheta; bc.erB = rec.er; bc.iDeltaRB = rec.iDeltaR; bc.Ub = rec.u; bc.Vb = rec.v;
       bottom_ctx(cfg, bc);
     };
-    auto emit = [&](uint32_t j, uint32_t t, float cu, float im) {
+    auto emit = [&](uint32_t j, uint32_t t) {
       const uint32_t slot = atomicAdd(&sh.poolCount, 1u);
-      if (slot < (uint32_t)CAPPOOL) {
-        const float2 tzr = ldg2(p.pZR + L.sPos[t]);
-        float topR = tzr.y;
-        if (cfg.useDeltaRinsteadOfTopRadius) {
-          const float dr = fsub(tzr.y, mid.r), dz = fsub(tzr.x, mid.z);
-          topR = fsqrt(fadd(fmul(dr, dr), fmul(dz, dz)));
-        }
-        Cand c;
-        c.curv = cu; c.impactOrWeight = im; c.topR = topR; c.tOwner = t | (j << 16);
-        L.u.b.pool[slot] = c;
-      }
+      if (slot < (uint32_t)CAPPOOL) L.u.b.pool[slot] = t | (j << 16);
     };
     for (;;) {  // warps pull chunks of 32 consecutive bottoms: balances uneven windows
       uint32_t chunk = 0;
@@ -954,19 +946,18 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
         if (bc.cotThetaB < L.sCot[md]) hi = md; else lo = md + 1;
       }
       uint32_t H = 0, ts = 0;
-      float cu, im;
       for (int t = (int)lo - 1; t >= 0; --t) {  // down to the last failing top of the prefix
         ++myTests;
-        const int cls = eval_pair(cfg, mid.r, mid.varZ, mid.varR, bc, L.sCot[t], L.sEr[t], L.sIDR[t], L.sU[t], L.sV[t], cu, im);
+        const int cls = classify_pair(cfg, mid.r, mid.varZ, mid.varR, bc, L.sCot[t], L.sEr[t], L.sIDR[t], L.sU[t], L.sV[t]);
         if (cls == kPairFailA) { H = (uint32_t)t + 1; ts = (uint32_t)t; break; }
         if (cls == kPairFailB) { H = (uint32_t)t; ts = (uint32_t)t; break; }
-        if (cls == kPairEmit) emit(j, (uint32_t)t, cu, im);
+        if (cls == kPairEmit) emit(j, (uint32_t)t);
       }
       for (uint32_t k = lo; k < nT; ++k) {  // up to the first failing top beyond the prefix
         ++myTests;
-        const int cls = eval_pair(cfg, mid.r, mid.varZ, mid.varR, bc, L.sCot[k], L.sEr[k], L.sIDR[k], L.sU[k], L.sV[k], cu, im);
+        const int cls = classify_pair(cfg, mid.r, mid.varZ, mid.varR, bc, L.sCot[k], L.sEr[k], L.sIDR[k], L.sU[k], L.sV[k]);
         if (cls == kPairFailA || cls == kPairFailB) break;
-        if (cls == kPairEmit) emit(j, k, cu, im);
+        if (cls == kPairEmit) emit(j, k);
       }
       L.u.b.hval[j] = (uint16_t)H;
       L.u.b.tstar[j] = (uint16_t)ts;
@@ -1001,11 +992,10 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
       if (s >= te) continue;
       BottomCtx bc;
       bottomCtx(j, bc);
-      float cu, im;
       for (uint32_t t = s; t < te; ++t) {
         ++myTests;
-        const int cls = eval_pair(cfg, mid.r, mid.varZ, mid.varR, bc, L.sCot[t], L.sEr[t], L.sIDR[t], L.sU[t], L.sV[t], cu, im);
-        if (cls == kPairEmit) emit(j, t, cu, im);
+        const int cls = classify_pair(cfg, mid.r, mid.varZ, mid.varR, bc, L.sCot[t], L.sEr[t], L.sIDR[t], L.sU[t], L.sV[t]);
+        if (cls == kPairEmit) emit(j, t);
       }
     }
     for (uint32_t j = tid; j <= nB; j += blockDim.x) L.u.b.cnt[j] = 0;
@@ -1027,7 +1017,7 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
     // ---- phase 3d: group the candidates by bottom, curvature order inside --
     // a candidate from the scans is only real when its top is inside the window
     for (uint32_t e = tid; e < poolCount; e += blockDim.x) {
-      const uint32_t to = L.u.b.pool[e].tOwner;
+      const uint32_t to = L.u.b.pool[e];
       const uint32_t j = to >> 16, t = to & 0xFFFFu;
       if (t >= L.u.b.hval[j]) atomicAdd(&L.u.b.cnt[j], 1u);
     }
@@ -1035,9 +1025,22 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
     block_scan_array(L.u.b.cnt, nB, sh.scratch, &sh.runCarry);
     const uint32_t nValid = sh.runCarry;
     for (uint32_t e = tid; e < poolCount; e += blockDim.x) {
-      const Cand c = L.u.b.pool[e];
-      const uint32_t j = c.tOwner >> 16, t = c.tOwner & 0xFFFFu;
-      if (t >= L.u.b.hval[j]) L.u.b.pool2[atomicAdd(&L.u.b.cnt[j], 1u)] = c;
+      const uint32_t to = L.u.b.pool[e];
+      const uint32_t j = to >> 16, t = to & 0xFFFFu;
+      if (t < L.u.b.hval[j]) continue;
+      // the candidate's curvature and impact (TripletSeedFinder.cpp:148-155), one thread per candidate
+      BottomCtx bc;
+      bottomCtx(j, bc);
+      Cand c;
+      eval_pair(cfg, mid.r, mid.varZ, mid.varR, bc, L.sCot[t], L.sEr[t], L.sIDR[t], L.sU[t], L.sV[t], c.curv, c.impactOrWeight);
+      const float2 tzr = ldg2(p.pZR + L.sPos[t]);
+      c.topR = tzr.y;
+      if (cfg.useDeltaRinsteadOfTopRadius) {
+        const float dr = fsub(tzr.y, mid.r), dz = fsub(tzr.x, mid.z);
+        c.topR = fsqrt(fadd(fmul(dr, dr), fmul(dz, dz)));
+      }
+      c.tOwner = to;
+      L.u.b.pool2[atomicAdd(&L.u.b.cnt[j], 1u)] = c;
     }
     __syncthreads();  // cnt[j] is now the END of bottom j's group
     for (uint32_t j = tid; j < nB; j += blockDim.x) {
@@ -1070,58 +1073,107 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
     }
     __syncthreads();
 
-    // ---- phase 3f: bounded heap replay (bottom-major, curvature order) ----
+    // ---- phase 3f: bounded heap (CandidatesForMiddleSp.cpp:44-93) ----------
+    // The heap keeps the nLow largest weights; its final sort_heap order is
+    // unique unless weights tie.  Warp 0 therefore selects the nLow + 1 largest
+    // weights in registers (lane r holds the r-th largest, stable in arrival
+    // order).  Only if two of them are equal -- the cases where the reference's
+    // result depends on the heap's history -- the literal heap replay runs.
     if (tid < 32) {
       const int nLow = (int)cfg.maxSeedsPerSpMConf;
+      const int keep = nLow + 1;  // <= kMaxHeap + 1 <= 32 lanes
+      float myW = -3.402823466e+38f;
+      uint32_t myId = 0xFFFFFFFFu;
+      int filled = 0;
       for (uint32_t c0 = 0; c0 < nValid && nLow > 0; c0 += 32) {
-        const uint32_t i = c0 + tid;
-        const int hs = sh.heapSize;
-        const float hmin = sh.heapMin;
-        bool want = false;
-        if (i < nValid) want = (hs < nLow) || (L.u.b.pool2[i].impactOrWeight > hmin);
-        uint32_t mask = __ballot_sync(0xffffffffu, want);
-        if (tid == 0) {
-          while (mask != 0u) {
-            const uint32_t q = c0 + (uint32_t)(__ffs(mask) - 1);
-            mask &= mask - 1u;
-            const Cand c = L.u.b.pool2[q];
-            const float wq = c.impactOrWeight;
-            StoredSeed sd;
-            sd.tOwner = c.tOwner;
-            sd.weight = wq;
-            if (sh.heapSize < nLow) {
-              const int slotI = sh.heapSize;
-              sh.storage[slotI] = sd;
-              sh.heap[slotI].weight = wq;
-              sh.heap[slotI].index = (uint32_t)slotI;
-              sh.heapSize = slotI + 1;
-              std_push_heap(sh.heap, sh.heapSize, heap_comp);
-            } else {
-              const WeightIndex smallest = sh.heap[0];
-              if (wq <= smallest.weight) continue;
-              sh.storage[smallest.index] = sd;
-              std_pop_heap(sh.heap, sh.heapSize, heap_comp);
-              sh.heap[sh.heapSize - 1].weight = wq;
-              sh.heap[sh.heapSize - 1].index = smallest.index;
-              std_push_heap(sh.heap, sh.heapSize, heap_comp);
-            }
-            sh.heapMin = sh.heap[0].weight;
-          }
+        const uint32_t i = c0 + lane;
+        float wgt = 0.f;
+        uint32_t id = 0;
+        if (i < nValid) { wgt = L.u.b.pool2[i].impactOrWeight; id = L.u.b.pool2[i].tOwner; }
+        const float kth = __shfl_sync(0xffffffffu, myW, keep - 1);
+        uint32_t mask = __ballot_sync(0xffffffffu, i < nValid && (filled < keep || wgt > kth));
+        while (mask != 0u) {
+          const int src = __ffs(mask) - 1;
+          mask &= mask - 1u;
+          const float v = __shfl_sync(0xffffffffu, wgt, src);
+          const uint32_t vid = __shfl_sync(0xffffffffu, id, src);
+          // stable insertion: after every entry with weight >= v
+          const uint32_t ge = __ballot_sync(0xffffffffu, (int)lane < filled && myW >= v);
+          const int pos = __popc(ge);
+          if (pos >= keep) continue;
+          const float upW = __shfl_up_sync(0xffffffffu, myW, 1);
+          const uint32_t upId = __shfl_up_sync(0xffffffffu, myId, 1);
+          if ((int)lane > pos && (int)lane < keep) { myW = upW; myId = upId; }
+          if ((int)lane == pos) { myW = v; myId = vid; }
+          if (filled < keep) ++filled;
         }
-        __syncwarp();
+      }
+      // ties among the nLow + 1 largest -> the order / membership depends on the heap history
+      const float nextW = __shfl_down_sync(0xffffffffu, myW, 1);
+      const bool tieHere = (int)lane + 1 < filled && myW == nextW;
+      const bool anyTie = __any_sync(0xffffffffu, tieHere);
+      if (!anyTie) {
+        const int inHeap = filled < nLow ? filled : nLow;
+        if ((int)lane < inHeap) {
+          sh.heap[lane].weight = myW;
+          sh.heap[lane].index = lane;
+          sh.storage[lane].weight = myW;
+          sh.storage[lane].tOwner = myId;
+        }
+        if (lane == 0) { sh.heapSize = inHeap; sh.heapSorted = 1; }
+      } else {
+        // literal replay in the reference's push order (bottom-major, curvature order)
+        if (lane == 0) sh.heapSorted = 0;
+        for (uint32_t c0 = 0; c0 < nValid && nLow > 0; c0 += 32) {
+          const uint32_t i = c0 + tid;
+          const int hs = sh.heapSize;
+          const float hmin = sh.heapMin;
+          bool want = false;
+          if (i < nValid) want = (hs < nLow) || (L.u.b.pool2[i].impactOrWeight > hmin);
+          uint32_t mask = __ballot_sync(0xffffffffu, want);
+          if (tid == 0) {
+            while (mask != 0u) {
+              const uint32_t q = c0 + (uint32_t)(__ffs(mask) - 1);
+              mask &= mask - 1u;
+              const Cand c = L.u.b.pool2[q];
+              const float wq = c.impactOrWeight;
+              StoredSeed sd;
+              sd.tOwner = c.tOwner;
+              sd.weight = wq;
+              if (sh.heapSize < nLow) {
+                const int slotI = sh.heapSize;
+                sh.storage[slotI] = sd;
+                sh.heap[slotI].weight = wq;
+                sh.heap[slotI].index = (uint32_t)slotI;
+                sh.heapSize = slotI + 1;
+                std_push_heap(sh.heap, sh.heapSize, heap_comp);
+              } else {
+                const WeightIndex smallest = sh.heap[0];
+                if (wq <= smallest.weight) continue;
+                sh.storage[smallest.index] = sd;
+                std_pop_heap(sh.heap, sh.heapSize, heap_comp);
+                sh.heap[sh.heapSize - 1].weight = wq;
+                sh.heap[sh.heapSize - 1].index = smallest.index;
+                std_push_heap(sh.heap, sh.heapSize, heap_comp);
+              }
+              sh.heapMin = sh.heap[0].weight;
+            }
+          }
+          __syncwarp();
+        }
       }
     }
     {
-      unsigned long long t = myTests;
+      uint32_t t = myTests;
       for (int d = 16; d > 0; d >>= 1) t += __shfl_down_sync(0xffffffffu, t, d);
-      if (lane == 0) atomicAdd(&sh.cnt[kCntTripletTests], t);
+      if (lane == 0) atomicAdd(&sh.cnt[kCntTripletTests], (unsigned long long)t);
     }
     __syncthreads();
 
     // ---- phase 4: per-middle selection (BroadTripletSeedFilter.cpp:324-393)
     if (tid == 0) {
       uint32_t nOut = 0;
-      std_sort_heap(sh.heap, sh.heapSize, heap_comp);
+      if (!sh.heapSorted) std_sort_heap(sh.heap, sh.heapSize, heap_comp);
       uint32_t maxSeeds = (uint32_t)sh.heapSize;
       if (maxSeeds > cfg.maxSeedsPerSpM) maxSeeds = cfg.maxSeedsPerSpM + 1;
       for (uint32_t i = 0; i < (uint32_t)sh.heapSize && i < maxSeeds; ++i) {
@@ -1150,8 +1202,8 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
 }
 
 // the two capacity tiers (see seeding_plugin.cu)
-constexpr int kCapB0 = 2304, kCapT0 = 1664, kCapPool0 = 864, kBuckets = 2048;
-constexpr int kCapB1 = 3584, kCapT1 = 2816, kCapPool1 = 2048;
+constexpr int kCapB0 = 2304, kCapT0 = 1664, kCapPool0 = 1216, kBuckets = 2048;
+constexpr int kCapB1 = 3584, kCapT1 = 2816, kCapPool1 = 4096;
 using SeedLayout0 = SeedLayout<kCapB0, kCapT0, kCapPool0, kBuckets>;
 using SeedLayout1 = SeedLayout<kCapB1, kCapT1, kCapPool1, kBuckets>;
 
