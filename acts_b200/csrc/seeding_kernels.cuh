@@ -65,7 +65,7 @@ struct GridParams {
   // packed copy (reference coreSpacePoints)
   uint32_t* pIdx;
   float2 *pXY, *pZR, *pVar;
-  unsigned long long* sortScratch;  // [2 * nTotal] for bins larger than smem
+  unsigned long long* sortScratch;  // [4 * nTotal] for bins larger than smem
   uint32_t sortSmemCap;             // elements that fit the sort kernel's smem
   int exactTies;                    // replay libstdc++ std::sort tie order
   int* status;
@@ -195,6 +195,114 @@ __device__ __forceinline__ uint32_t first_true(uint32_t lo, uint32_t hi, Pred pr
 
 __device__ __forceinline__ float2 ldg2(const float2* p) { return __ldg(p); }
 
+// Item of the tie replays: sort key + payload (top bit of val may carry a flag).
+struct TieItem {
+  float key;
+  uint32_t val;
+};
+__device__ __forceinline__ bool tie_less(const TieItem& a, const TieItem& b) { return a.key < b.key; }
+
+// Pruned replay of libstdc++'s introsort (see std_sort_replay_ties in
+// seed_math.h) executed by ONE WARP: all 32 lanes call it with the same
+// arguments on an array in shared or global memory.  The Hoare partition of
+// libstdc++ pairs the k-th misplaced element from the left with the k-th
+// misplaced element from the right; here 32 + 32 elements are classified per
+// step with ballots and swapped by rank, the last < 64 elements of a partition
+// run through the literal sequential loop (tests/model: model_check_warp_replay
+// checks this formulation against std::sort).
+template <typename Flagged>
+__device__ __forceinline__ void warp_sort_replay_ties(TieItem* a, int n, Flagged flagged) {
+  if (n <= 16) return;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t ltMask = (1u << lane) - 1u;
+  int lg = 0;
+  for (unsigned v = (unsigned)n; v > 1; v >>= 1) ++lg;
+  int sf[64], sl[64], sd[64];
+  int sp = 0;
+  sf[0] = 0; sl[0] = n; sd[0] = 2 * lg; sp = 1;
+  while (sp > 0) {
+    --sp;
+    int first = sf[sp], last = sl[sp], depth = sd[sp];
+    while (last - first > 16) {
+      int c = 0;
+      for (int base = first; base < last && c < 2; base += 32) {
+        const int i = base + (int)lane;
+        const bool f = i < last && flagged(a[i]);
+        c += __popc(__ballot_sync(0xffffffffu, f));
+      }
+      if (c < 2) break;  // nothing left to decide in this range
+      if (depth == 0) {
+        if (lane == 0) {
+          std_make_heap(a + first, last - first, tie_less);
+          std_sort_heap(a + first, last - first, tie_less);
+        }
+        __syncwarp();
+        break;
+      }
+      --depth;
+      const int mid = first + (last - first) / 2;
+      {
+        const int ia = first + 1, ib = mid, ic = last - 1;
+        const TieItem va = a[ia], vb = a[ib], vc = a[ic];
+        int pick;
+        if (tie_less(va, vb)) {
+          if (tie_less(vb, vc)) pick = ib;
+          else if (tie_less(va, vc)) pick = ic;
+          else pick = ia;
+        } else if (tie_less(va, vc)) pick = ia;
+        else if (tie_less(vb, vc)) pick = ic;
+        else pick = ib;
+        __syncwarp();
+        if (lane == 0) {
+          const TieItem t = a[first]; a[first] = a[pick]; a[pick] = t;
+        }
+        __syncwarp();
+      }
+      const TieItem pivot = a[first];
+      int lo = first + 1, hi = last;
+      while (hi - lo >= 64) {
+        const TieItem el = a[lo + (int)lane], er = a[hi - 1 - (int)lane];
+        const bool ml = !tie_less(el, pivot), mr = !tie_less(pivot, er);
+        const uint32_t mL = __ballot_sync(0xffffffffu, ml), mR = __ballot_sync(0xffffffffu, mr);
+        const int nL = __popc(mL), nR = __popc(mR), s = nL < nR ? nL : nR;
+        const int rkL = __popc(mL & ltMask), rkR = __popc(mR & ltMask);
+        const bool swapL = ml && rkL < s, swapR = mr && rkR < s;
+        const int srcR = swapL ? (int)__fns(mR, 0, rkL + 1) : (int)lane;
+        const int srcL = swapR ? (int)__fns(mL, 0, rkR + 1) : (int)lane;
+        TieItem fromRight, fromLeft;
+        fromRight.key = __shfl_sync(0xffffffffu, er.key, srcR);
+        fromRight.val = __shfl_sync(0xffffffffu, er.val, srcR);
+        fromLeft.key = __shfl_sync(0xffffffffu, el.key, srcL);
+        fromLeft.val = __shfl_sync(0xffffffffu, el.val, srcL);
+        if (swapL) a[lo + (int)lane] = fromRight;
+        if (swapR) a[hi - 1 - (int)lane] = fromLeft;
+        const int newLo = nL == s ? lo + 32 : lo + (int)__fns(mL, 0, s + 1);
+        const int newHi = nR == s ? hi - 32 : hi - (int)__fns(mR, 0, s + 1);
+        lo = newLo;
+        hi = newHi;
+        __syncwarp();
+      }
+      int cut = 0;
+      if (lane == 0) {  // libstdc++ __unguarded_partition resumed from the same (lo, hi) state
+        while (true) {
+          while (tie_less(a[lo], pivot)) ++lo;
+          --hi;
+          while (tie_less(pivot, a[hi])) --hi;
+          if (!(lo < hi)) break;
+          const TieItem t = a[lo]; a[lo] = a[hi]; a[hi] = t;
+          ++lo;
+        }
+        cut = lo;
+      }
+      cut = __shfl_sync(0xffffffffu, cut, 0);
+      __syncwarp();
+      sf[sp] = cut; sl[sp] = last; sd[sp] = depth; ++sp;
+      last = cut;
+    }
+  }
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------------------
 // Grid stage
 // ---------------------------------------------------------------------------
@@ -274,20 +382,23 @@ __device__ __forceinline__ void block_bitonic_sort(unsigned long long* keys, uin
   }
 }
 
-struct RItem {
-  float key;
-  uint32_t val;
-};
-__device__ __forceinline__ bool ritem_less(const RItem& a, const RItem& b) { return a.key < b.key; }
+__device__ __forceinline__ bool bin_flagged(const TieItem& a) { return (a.val >> 31) != 0u; }
 
 // One block per (event, bin): order the bin by r and write the packed copy.
-//   exactTies = 1: entries are first put in insertion order (ascending original
-//     index, the order grid.insert produced, .cpp:211-221) and then sorted with
-//     the replayed libstdc++ std::sort (.cpp:223-228) so that equal radii end up
-//     in the reference's order.
-//   exactTies = 0: canonical (r, original index) order.
+// The reference sorts the bin's indices (inserted in ascending original index,
+// .cpp:211-221) with the unstable std::ranges::sort (.cpp:223-228).  Here:
+//   1. bitonic sort by (r, original index)              -> canonical order
+//   2. exactTies only, bins with equal radii only: the elements are put in
+//      insertion order (second bitonic sort, by original index) and one warp
+//      replays libstdc++'s introsort on them (pruned to the ranges that still
+//      hold tied elements); tied elements take the slots of their group in the
+//      order the replay leaves them in
+//   3. gather the six columns into the packed copy
+// `keys` and `work` hold `padded` (power of two >= n) 8-byte entries each, in
+// shared memory when they fit, else in the global scratch.
 __global__ void __launch_bounds__(kSortThreads) k_sort_bins(const __grid_constant__ GridParams p) {
   extern __shared__ unsigned long long smemKeys[];
+  __shared__ uint32_t sFlag;
   const uint32_t gb = blockIdx.x;
   const uint32_t b0 = p.binStart[gb], b1 = p.binStart[gb + 1];
   const uint32_t n = b1 - b0;
@@ -296,48 +407,91 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_bins(const __grid_constan
   const uint32_t evBase = __ldg(p.spOffsets + e);
   uint32_t padded = 1;
   while (padded < n) padded <<= 1;
-  unsigned long long* keys = padded <= p.sortSmemCap ? smemKeys : p.sortScratch + 2ull * b0;
+  const bool inSmem = padded <= p.sortSmemCap;
+  unsigned long long* keys = inSmem ? smemKeys : p.sortScratch + 4ull * b0;
+  unsigned long long* work = inSmem ? smemKeys + p.sortSmemCap : p.sortScratch + 4ull * b0 + 2ull * n;
   for (uint32_t i = threadIdx.x; i < padded; i += blockDim.x) {
     unsigned long long k = ~0ull;
     if (i < n) {
       const uint32_t idx = p.tmpIdx[b0 + i];
       const float r = __ldg(p.r + evBase + idx);
       const uint32_t rb = (r == 0.0f) ? 0u : __float_as_uint(r);  // r >= 0 inside the grid
-      k = p.exactTies ? (((unsigned long long)idx << 32) | rb) : (((unsigned long long)rb << 32) | idx);
+      k = ((unsigned long long)rb << 32) | idx;
     }
     keys[i] = k;
   }
+  if (threadIdx.x == 0) sFlag = 0;
   __syncthreads();
   block_bitonic_sort(keys, padded);
-  if (p.exactTies) {
-    RItem* items = reinterpret_cast<RItem*>(keys);
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-      const unsigned long long k = keys[i];
-      RItem it;
-      it.key = __uint_as_float((uint32_t)(k & 0xffffffffu));
-      it.val = (uint32_t)(k >> 32);
-      items[i] = it;  // same 8 bytes the key came from
-    }
+  if (p.exactTies && n > 16) {
+    bool t = false;
+    for (uint32_t i = threadIdx.x + 1; i < n; i += blockDim.x) t |= (keys[i] >> 32) == (keys[i - 1] >> 32);
+    if (t) sFlag = 1;
     __syncthreads();
-    if (threadIdx.x == 0) std_sort(items, (int)n, ritem_less);
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-      const uint32_t idx = items[i].val;
-      const uint32_t src = evBase + idx;
-      p.pIdx[b0 + i] = idx;
-      p.pXY[b0 + i] = make_float2(__ldg(p.x + src), __ldg(p.y + src));
-      p.pZR[b0 + i] = make_float2(__ldg(p.z + src), __ldg(p.r + src));
-      p.pVar[b0 + i] = make_float2(__ldg(p.varZ + src), __ldg(p.varR + src));
+    if (sFlag != 0) {  // block-uniform
+      // insertion order: sort (original index, canonical rank) by index
+      for (uint32_t i = threadIdx.x; i < padded; i += blockDim.x) {
+        work[i] = i < n ? (((keys[i] & 0xffffffffull) << 32) | i) : ~0ull;
+      }
+      __syncthreads();
+      block_bitonic_sort(work, padded);
+      TieItem* W = reinterpret_cast<TieItem*>(work);
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t rank = (uint32_t)(work[i] & 0xffffffffull);
+        const uint32_t rb = (uint32_t)(keys[rank] >> 32);
+        const bool tied = (rank > 0 && (uint32_t)(keys[rank - 1] >> 32) == rb) ||
+                          (rank + 1 < n && (uint32_t)(keys[rank + 1] >> 32) == rb);
+        TieItem it;
+        it.key = __uint_as_float(rb);
+        it.val = rank | (tied ? 0x80000000u : 0u);
+        W[i] = it;  // the same 8 bytes work[i] came from
+      }
+      __syncthreads();
+      if (threadIdx.x < 32) warp_sort_replay_ties(W, (int)n, bin_flagged);
+      __syncthreads();
+      // tied element k (in replay order) of a group takes the group's k-th canonical slot
+      uint32_t myDest = 0xFFFFFFFFu, myIdx = 0;
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {  // few tied elements: at most one per thread in practice
+        const TieItem it = W[i];
+        if (!bin_flagged(it)) continue;
+        const uint32_t rank = it.val & 0x7fffffffu;
+        const uint32_t rb = __float_as_uint(it.key);
+        uint32_t g = rank;
+        while (g > 0 && (uint32_t)(keys[g - 1] >> 32) == rb) --g;
+        uint32_t before = 0;
+        for (uint32_t q = 0; q < i; ++q) before += (bin_flagged(W[q]) && __float_as_uint(W[q].key) == rb) ? 1u : 0u;
+        if (myDest != 0xFFFFFFFFu) {  // a thread owning several tied elements writes the earlier one now (distinct slots)
+          p.tmpIdx[b0 + myDest] = myIdx;
+        }
+        myDest = g + before;
+        myIdx = (uint32_t)(keys[rank] & 0xffffffffull);
+      }
+      // stage the reassignments in tmpIdx (free from here on), then patch keys
+      if (myDest != 0xFFFFFFFFu) p.tmpIdx[b0 + myDest] = myIdx;
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t rb = (uint32_t)(keys[i] >> 32);
+        const bool tied = (i > 0 && (uint32_t)(keys[i - 1] >> 32) == rb) || (i + 1 < n && (uint32_t)(keys[i + 1] >> 32) == rb);
+        if (tied) {
+          const uint32_t idx = p.tmpIdx[b0 + i];
+          // all members of a group share rb, so only the index half changes
+          work[i] = ((unsigned long long)rb << 32) | idx;
+        } else {
+          work[i] = keys[i];
+        }
+      }
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) keys[i] = work[i];
+      __syncthreads();
     }
-  } else {
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-      const uint32_t idx = (uint32_t)(keys[i] & 0xffffffffu);
-      const uint32_t src = evBase + idx;
-      p.pIdx[b0 + i] = idx;
-      p.pXY[b0 + i] = make_float2(__ldg(p.x + src), __ldg(p.y + src));
-      p.pZR[b0 + i] = make_float2(__ldg(p.z + src), __ldg(p.r + src));
-      p.pVar[b0 + i] = make_float2(__ldg(p.varZ + src), __ldg(p.varR + src));
-    }
+  }
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t idx = (uint32_t)(keys[i] & 0xffffffffull);
+    const uint32_t src = evBase + idx;
+    p.pIdx[b0 + i] = idx;
+    p.pXY[b0 + i] = make_float2(__ldg(p.x + src), __ldg(p.y + src));
+    p.pZR[b0 + i] = make_float2(__ldg(p.z + src), __ldg(p.r + src));
+    p.pVar[b0 + i] = make_float2(__ldg(p.varZ + src), __ldg(p.varR + src));
   }
 }
 
@@ -704,17 +858,13 @@ __device__ __forceinline__ bool block_has_ties(uint32_t n, const float* cot, con
   return r;
 }
 
-struct TieItem {
-  float key;
-  uint32_t val;  // element index | tie group (first canonical rank) << 16; group 0xFFFF = unique key
-};
-__device__ __forceinline__ bool tie_less(const TieItem& a, const TieItem& b) { return a.key < b.key; }
+// cotTheta tie items: val = element index | tie group (first canonical rank) << 16; group 0xFFFF = unique key
 __device__ __forceinline__ bool tie_flagged(const TieItem& a) { return (a.val >> 16) != 0xFFFFu; }
 
 // Exact order inside groups of equal cotTheta: the reference sorts the doublets
 // with the unstable std::ranges::sort (DoubletSeedFinder.hpp:94-104) starting
 // from the emission order.  `sorted` holds the canonical (cot, seq) order; the
-// pruned replay of libstdc++'s introsort (seed_math.h) run by one thread on the
+// pruned replay of libstdc++'s introsort (warp_sort_replay_ties) run by one warp on the
 // emission-ordered copy W decides which member of a tie group takes which of the
 // group's slots.  seqSorted / grpOf are n-entry u16 scratch arrays.
 __device__ __forceinline__ void block_fix_ties(uint32_t n, const float* cot, const uint32_t* seq, uint32_t totalCand,
@@ -744,7 +894,7 @@ __device__ __forceinline__ void block_fix_ties(uint32_t n, const float* cot, con
     W[r] = it;
   }
   __syncthreads();
-  if (threadIdx.x == 0) std_sort_replay_ties(W, (int)n, tie_less, tie_flagged);
+  if (threadIdx.x < 32) warp_sort_replay_ties(W, (int)n, tie_flagged);
   __syncthreads();
   // member k (in W order) of group q goes to canonical slot q + k
   for (uint32_t r = threadIdx.x; r < n; r += blockDim.x) {

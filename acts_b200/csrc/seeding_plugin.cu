@@ -126,7 +126,7 @@ int ensure_workspace(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal) {
   CUDA_TRY(h->pXY.reserve(nT * 8));
   CUDA_TRY(h->pZR.reserve(nT * 8));
   CUDA_TRY(h->pVar.reserve(nT * 8));
-  CUDA_TRY(h->sortScratch.reserve(nT * 16));
+  CUDA_TRY(h->sortScratch.reserve(nT * 32));
   CUDA_TRY(h->midLo.reserve((nNavAll + 1) * 4));
   CUDA_TRY(h->midCount.reserve((nNavAll + 1) * 4));
   CUDA_TRY(h->workStart.reserve((nNavAll + 1) * 4));
@@ -201,7 +201,7 @@ int enqueue(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal, const uint32_
   ++launches;
   if (nTotal > 0) {
     k_scatter<<<elemBlocks, 256, 0, s>>>(gp);
-    k_sort_bins<<<nBinsAll, kSortThreads, (size_t)h->sortSmemCap * 8, s>>>(gp);
+    k_sort_bins<<<nBinsAll, kSortThreads, (size_t)h->sortSmemCap * 16, s>>>(gp);
     launches += 2;
   }
 
@@ -446,7 +446,7 @@ int b200seed_create(const b200seed_config* cfg, int device, b200seed_handle** ou
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seedSmemBytes[0]));
   CREATE_TRY(cudaFuncSetAttribute(k_seed_middles<kCapB1, kCapT1, kCapPool1, kBuckets>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seedSmemBytes[1]));
-  CREATE_TRY(cudaFuncSetAttribute(k_sort_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->sortSmemCap * 8)));
+  CREATE_TRY(cudaFuncSetAttribute(k_sort_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->sortSmemCap * 16)));
   {
     int b0 = 0, b1 = 0;
     CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_seed_middles<kCapB0, kCapT0, kCapPool0, kBuckets>,
@@ -570,8 +570,8 @@ static int run_host_batch(b200seed_handle* h, uint32_t nEvents, const uint32_t* 
     CUDA_TRY(h->binOf.reserve(colBytes));  // make sure workspaces exist before aliasing
     CUDA_TRY(h->tmpIdx.reserve(colBytes));
     // phi staging shares no workspace with the pipeline: use sortScratch's tail
-    CUDA_TRY(h->sortScratch.reserve((size_t)nTotal * 16 + colBytes));
-    dPhi = reinterpret_cast<float*>(h->sortScratch.as<unsigned char>() + (size_t)nTotal * 16);
+    CUDA_TRY(h->sortScratch.reserve((size_t)nTotal * 32 + colBytes));
+    dPhi = reinterpret_cast<float*>(h->sortScratch.as<unsigned char>() + (size_t)nTotal * 32);
     CUDA_TRY(cudaMemcpyAsync(dPhi, phi, (size_t)nTotal * 4, cudaMemcpyHostToDevice, s));
   }
   int rc = ensure_workspace(h, nEvents, nTotal);

@@ -406,6 +406,140 @@ int64_t model_check_tie_replay(uint64_t seed, int maxN, int trials, int nTieGrou
   return bad;
 }
 
+
+}  // extern "C" (templates below need C++ linkage)
+
+// ---------------------------------------------------------------------------
+// Scalar emulation of the WARP-parallel pruned replay used on the device
+// (seeding_kernels.cuh: warp_sort_replay_ties).  Lanes are emulated by loops;
+// the batch partition step must be equivalent to libstdc++'s sequential
+// __unguarded_partition.
+// ---------------------------------------------------------------------------
+namespace {
+inline int fnsEmu(uint32_t mask, int k) {  // lane of the k-th (1-based) set bit, -1 if none
+  for (int l = 0; l < 32; ++l) {
+    if (mask & (1u << l)) { if (--k == 0) return l; }
+  }
+  return -1;
+}
+template <typename T, typename Less, typename Flagged>
+void warpReplayEmu(T* a, int n, Less less, Flagged flagged) {
+  if (n <= 16) return;
+  int lg = 0;
+  for (unsigned v = (unsigned)n; v > 1; v >>= 1) ++lg;
+  int sf[64], sl[64], sd[64], sp = 0;
+  sf[0] = 0; sl[0] = n; sd[0] = 2 * lg; sp = 1;
+  while (sp > 0) {
+    --sp;
+    int first = sf[sp], last = sl[sp], depth = sd[sp];
+    while (last - first > 16) {
+      int c = 0;
+      for (int base = first; base < last && c < 2; base += 32) {
+        uint32_t m = 0;
+        for (int l = 0; l < 32; ++l) { const int i = base + l; if (i < last && flagged(a[i])) m |= 1u << l; }
+        c += __builtin_popcount(m);
+      }
+      if (c < 2) break;
+      if (depth == 0) { std_make_heap(a + first, last - first, less); std_sort_heap(a + first, last - first, less); break; }
+      --depth;
+      const int mid = first + (last - first) / 2;
+      {
+        const int ia = first + 1, ib = mid, ic = last - 1;
+        int pick;
+        if (less(a[ia], a[ib])) { if (less(a[ib], a[ic])) pick = ib; else if (less(a[ia], a[ic])) pick = ic; else pick = ia; }
+        else if (less(a[ia], a[ic])) pick = ia; else if (less(a[ib], a[ic])) pick = ic; else pick = ib;
+        std::swap(a[first], a[pick]);
+      }
+      const T pivot = a[first];
+      int lo = first + 1, hi = last;
+      while (hi - lo >= 64) {  // batch step: 32 from the left, 32 from the right
+        T el[32], er[32];
+        uint32_t mL = 0, mR = 0;
+        for (int l = 0; l < 32; ++l) {
+          el[l] = a[lo + l]; er[l] = a[hi - 1 - l];
+          if (!less(el[l], pivot)) mL |= 1u << l;
+          if (!less(pivot, er[l])) mR |= 1u << l;
+        }
+        const int nL = __builtin_popcount(mL), nR = __builtin_popcount(mR), s2 = std::min(nL, nR);
+        for (int l = 0; l < 32; ++l) {
+          if (mL & (1u << l)) { const int rk = __builtin_popcount(mL & ((1u << l) - 1u)); if (rk < s2) a[lo + l] = er[fnsEmu(mR, rk + 1)]; }
+          if (mR & (1u << l)) { const int rk = __builtin_popcount(mR & ((1u << l) - 1u)); if (rk < s2) a[hi - 1 - l] = el[fnsEmu(mL, rk + 1)]; }
+        }
+        const int newLo = (nL == s2) ? lo + 32 : lo + fnsEmu(mL, s2 + 1);
+        const int newHi = (nR == s2) ? hi - 32 : hi - fnsEmu(mR, s2 + 1);
+        lo = newLo; hi = newHi;
+      }
+      while (true) {  // serial remainder, libstdc++ __unguarded_partition from the same state
+        while (less(a[lo], pivot)) ++lo;
+        --hi;
+        while (less(pivot, a[hi])) --hi;
+        if (!(lo < hi)) break;
+        std::swap(a[lo], a[hi]);
+        ++lo;
+      }
+      const int cut = lo;
+      sf[sp] = cut; sl[sp] = last; sd[sp] = depth; ++sp;
+      last = cut;
+    }
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int64_t model_check_warp_replay(uint64_t seed, int maxN, int trials, int nTieGroups, int fullSort) {
+  std::mt19937_64 rng(seed);
+  int64_t bad = 0;
+  for (int t = 0; t < trials; ++t) {
+    const int n = 2 + (int)(rng() % (uint64_t)(maxN - 1));
+    std::vector<SortItem> in(n);
+    const int mode = (int)(rng() % 4);
+    for (int i = 0; i < n; ++i) {
+      float key = (float)(rng() % 100000007ull);
+      if (mode == 1) key = (float)i; else if (mode == 2) key = (float)(n - i);
+      in[i] = {key, (uint32_t)i};
+    }
+    const int groups = (int)(rng() % (uint64_t)(nTieGroups + 1));
+    for (int gI = 0; gI < groups; ++gI) {
+      const int k = 2 + (int)(rng() % 3);
+      const float key = in[rng() % n].key;
+      for (int j = 0; j < k; ++j) in[rng() % n].key = key;
+    }
+    std::vector<SortItem> ref = in;
+    std::sort(ref.begin(), ref.end(), sortItemLess);
+    std::vector<uint32_t> canon(n);
+    for (int i = 0; i < n; ++i) canon[i] = i;
+    std::sort(canon.begin(), canon.end(), [&](uint32_t x, uint32_t y) { if (in[x].key != in[y].key) return in[x].key < in[y].key; return x < y; });
+    std::vector<uint32_t> group(n, 0xFFFFFFFFu);
+    for (int i = 0; i < n; ++i) {
+      const bool tp = i > 0 && in[canon[i]].key == in[canon[i - 1]].key;
+      const bool tn = i + 1 < n && in[canon[i]].key == in[canon[i + 1]].key;
+      if (tp || tn || fullSort) {
+        int q = i;
+        while (q > 0 && in[canon[q - 1]].key == in[canon[i]].key) --q;
+        group[canon[i]] = (uint32_t)q;
+      }
+    }
+    if (n > 16) {
+      struct W { float key; uint32_t val; uint32_t grp; };
+      std::vector<W> w(n);
+      for (int i = 0; i < n; ++i) w[i] = {in[i].key, (uint32_t)i, group[i]};
+      warpReplayEmu(w.data(), n, [](const W& x, const W& y) { return x.key < y.key; }, [](const W& e) { return e.grp != 0xFFFFFFFFu; });
+      for (int i = 0; i < n; ++i) if (group[canon[i]] != 0xFFFFFFFFu) canon[i] = 0xFFFFFFFFu;
+      for (int i = 0; i < n; ++i) {
+        if (w[i].grp == 0xFFFFFFFFu) continue;
+        uint32_t s2 = w[i].grp;
+        while (canon[s2] != 0xFFFFFFFFu) ++s2;
+        canon[s2] = w[i].val;
+      }
+    }
+    for (int i = 0; i < n; ++i) {
+      if (canon[i] != ref[i].val) { ++bad; break; }
+    }
+  }
+  return bad;
+}
+
 // adversarial input for median-of-3 quicksort (forces the heap-sort fallback)
 int64_t model_check_std_sort_killer(int n) {
   // Musser's median-of-3 killer sequence

@@ -28,6 +28,8 @@ def lib():
         L.model_check_std_sort_killer.restype = C.c_int64
         L.model_check_tie_replay.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int]
         L.model_check_tie_replay.restype = C.c_int64
+        L.model_check_warp_replay.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.model_check_warp_replay.restype = C.c_int64
         L.model_check_heap.argtypes = [C.c_uint64, C.c_int]
         L.model_check_heap.restype = C.c_int64
         L.model_check_atan2f.argtypes = [C.c_uint64, C.c_int64]
