@@ -1095,19 +1095,38 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
         const uint32_t md = (lo + hi) >> 1;
         if (bc.cotThetaB < L.sCot[md]) hi = md; else lo = md + 1;
       }
+      // One merged loop: every lane first walks down from |P_j| - 1 to the last
+      // failing top of the prefix, then up from |P_j| to the first failing top
+      // beyond it.  Lanes switch direction individually, so a warp runs for
+      // max_j(a_j + f_j) steps instead of max_j a_j + max_j f_j.
       uint32_t H = 0, ts = 0;
-      for (int t = (int)lo - 1; t >= 0; --t) {  // down to the last failing top of the prefix
+      int tb = (int)lo - 1;
+      uint32_t tf = lo;
+      bool backDone = tb < 0, fwdDone = tf >= nT;
+      while (!(backDone && fwdDone)) {
+        const bool doBack = !backDone;
+        const uint32_t t = doBack ? (uint32_t)tb : tf;
         ++myTests;
         const int cls = classify_pair(cfg, mid.r, mid.varZ, mid.varR, bc, L.sCot[t], L.sEr[t], L.sIDR[t], L.sU[t], L.sV[t]);
-        if (cls == kPairFailA) { H = (uint32_t)t + 1; ts = (uint32_t)t; break; }
-        if (cls == kPairFailB) { H = (uint32_t)t; ts = (uint32_t)t; break; }
-        if (cls == kPairEmit) emit(j, (uint32_t)t);
-      }
-      for (uint32_t k = lo; k < nT; ++k) {  // up to the first failing top beyond the prefix
-        ++myTests;
-        const int cls = classify_pair(cfg, mid.r, mid.varZ, mid.varR, bc, L.sCot[k], L.sEr[k], L.sIDR[k], L.sU[k], L.sV[k]);
-        if (cls == kPairFailA || cls == kPairFailB) break;
-        if (cls == kPairEmit) emit(j, k);
+        const bool fail = cls == kPairFailA || cls == kPairFailB;
+        if (cls == kPairEmit) emit(j, t);
+        if (doBack) {
+          if (fail) {
+            H = cls == kPairFailA ? t + 1 : t;
+            ts = t;
+            backDone = true;
+          } else {
+            --tb;
+            backDone = tb < 0;
+          }
+        } else {
+          if (fail) {
+            fwdDone = true;
+          } else {
+            ++tf;
+            fwdDone = tf >= nT;
+          }
+        }
       }
       L.u.b.hval[j] = (uint16_t)H;
       L.u.b.tstar[j] = (uint16_t)ts;
@@ -1131,21 +1150,29 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
     __syncthreads();
 
     // ---- phase 3c: pairs in [start_j, t*_j) that the scans did not touch --
-    for (;;) {
-      uint32_t chunk = 0;
-      if (lane == 0) chunk = atomicAdd(&sh.nextChunkC, 32u);
-      chunk = __shfl_sync(0xffffffffu, chunk, 0);
-      if (chunk >= nB) break;
-      const uint32_t j = chunk + lane;
-      if (j >= nB) continue;
-      const uint32_t s = L.u.b.hval[j], te = L.u.b.tstar[j];
-      if (s >= te) continue;
-      BottomCtx bc;
-      bottomCtx(j, bc);
-      for (uint32_t t = s; t < te; ++t) {
-        ++myTests;
-        const int cls = classify_pair(cfg, mid.r, mid.varZ, mid.varR, bc, L.sCot[t], L.sEr[t], L.sIDR[t], L.sU[t], L.sV[t]);
-        if (cls == kPairEmit) emit(j, t);
+    // few bottoms have such a gap: list them first, then one thread per listed bottom
+    {
+      uint16_t* gapList = reinterpret_cast<uint16_t*>(L.u.b.pool2);  // pool2 is free until phase 3d
+      if (tid == 0) sh.nSurv = 0;
+      __syncthreads();
+      for (uint32_t base = 0; base < nB; base += blockDim.x) {
+        const uint32_t j = base + tid;
+        const bool has = j < nB && L.u.b.hval[j] < L.u.b.tstar[j];
+        const uint32_t slot = warp_append(&sh.nSurv, has);
+        if (has) gapList[slot] = (uint16_t)j;
+      }
+      __syncthreads();
+      const uint32_t nGap = sh.nSurv;
+      for (uint32_t q = tid; q < nGap; q += blockDim.x) {
+        const uint32_t j = gapList[q];
+        const uint32_t s = L.u.b.hval[j], te = L.u.b.tstar[j];
+        BottomCtx bc;
+        bottomCtx(j, bc);
+        for (uint32_t t = s; t < te; ++t) {
+          ++myTests;
+          const int cls = classify_pair(cfg, mid.r, mid.varZ, mid.varR, bc, L.sCot[t], L.sEr[t], L.sIDR[t], L.sU[t], L.sV[t]);
+          if (cls == kPairEmit) emit(j, t);
+        }
       }
     }
     for (uint32_t j = tid; j <= nB; j += blockDim.x) L.u.b.cnt[j] = 0;
