@@ -908,8 +908,13 @@ __device__ __forceinline__ void block_fix_ties(uint32_t n, const float* cot, con
   __syncthreads();
 }
 
-template <int CAPB, int CAPT, int CAPPOOL, int NBK>
-__global__ void __launch_bounds__(kSeedThreads, (sizeof(SeedLayout<CAPB, CAPT, CAPPOOL, NBK>) <= 115712) ? 2 : 1)
+// blocks per SM that fit the 227 KB of shared memory (1 KB per block is reserved)
+constexpr int seed_blocks_per_sm(size_t layoutBytes) {
+  return layoutBytes + 1024 <= 232448 / 3 ? 3 : (layoutBytes + 1024 <= 232448 / 2 ? 2 : 1);
+}
+
+template <int CAPB, int CAPT, int CAPPOOL, int NBK, int THREADS>
+__global__ void __launch_bounds__(THREADS, seed_blocks_per_sm(sizeof(SeedLayout<CAPB, CAPT, CAPPOOL, NBK>)))
 k_seed_middles(const __grid_constant__ SeedParams p) {
   using Layout = SeedLayout<CAPB, CAPT, CAPPOOL, NBK>;
   extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -1378,11 +1383,12 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
   }
 }
 
-// the two capacity tiers (see seeding_plugin.cu)
-constexpr int kCapB0 = 2304, kCapT0 = 1664, kCapPool0 = 1216, kBuckets = 2048;
-constexpr int kCapB1 = 3584, kCapT1 = 2816, kCapPool1 = 4096;
-using SeedLayout0 = SeedLayout<kCapB0, kCapT0, kCapPool0, kBuckets>;
-using SeedLayout1 = SeedLayout<kCapB1, kCapT1, kCapPool1, kBuckets>;
+// the capacity tiers (see seeding_plugin.cu): {bottoms, tops, candidates, buckets, threads}
+struct Tier0 { static constexpr int B = 1536, T = 1152, P = 768, K = 1024, N = 384; };
+struct Tier1 { static constexpr int B = 2304, T = 1664, P = 1216, K = 2048, N = 512; };
+struct Tier2 { static constexpr int B = 3584, T = 2816, P = 4096, K = 2048, N = 512; };
+template <typename TR> using TierLayout = SeedLayout<TR::B, TR::T, TR::P, TR::K>;
+constexpr int kNumTiers = 3;
 
 // ---------------------------------------------------------------------------
 // Seed compaction (ordered): tiled exclusive scan of the per-middle counts

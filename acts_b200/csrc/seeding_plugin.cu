@@ -77,8 +77,8 @@ struct b200seed_handle {
   // re-queued to tier 1 (1 block per SM)
   uint32_t sortSmemCap = 4096;
   int exactTies = 1;
-  int seedBlocksPerSM[2] = {1, 1};
-  size_t seedSmemBytes[2] = {0, 0};
+  int seedBlocksPerSM[kNumTiers] = {1, 1, 1};
+  size_t seedSmemBytes[kNumTiers] = {0, 0, 0};
   // constant tables
   DevBuf navBins, botOffsets, botBins, topOffsets, topBins;
   // per-batch workspaces
@@ -133,7 +133,7 @@ int ensure_workspace(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal) {
   CUDA_TRY(h->workPos.reserve(nT * 4));
   CUDA_TRY(h->workEG.reserve(nT * 4));
   CUDA_TRY(h->workCounter.reserve(32));
-  CUDA_TRY(h->overflowList.reserve(nT * 4));
+  CUDA_TRY(h->overflowList.reserve(nT * 8));
   CUDA_TRY(h->slotB.reserve(nT * K * 4));
   CUDA_TRY(h->slotM.reserve(nT * K * 4));
   CUDA_TRY(h->slotT.reserve(nT * K * 4));
@@ -246,23 +246,33 @@ int enqueue(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal, const uint32_
   sp.exactTies = h->exactTies;
   sp.counters = gp.counters;
   sp.status = gp.status;
-  // workCounter words: [0] tier-0 ticket, [1] overflow count, [2] tier-1 ticket
+  // workCounter words: [0] tier-0 ticket, [1] overflow count 0->1, [2] tier-1 ticket,
+  // [3] overflow count 1->2, [4] tier-2 ticket
   uint32_t* wc = h->workCounter.as<uint32_t>();
-  // tier 0: every middle
+  uint32_t* ov0 = h->overflowList.as<uint32_t>();
+  uint32_t* ov1 = ov0 + std::max<uint32_t>(nTotal, 1);
+  // tier 0: every middle, small scratch, 3 blocks per SM
   sp.workCounter = wc + 0;
   sp.workList = nullptr;
-  sp.overflowList = h->overflowList.as<uint32_t>();
+  sp.overflowList = ov0;
   sp.overflowCount = wc + 1;
-  k_seed_middles<kCapB0, kCapT0, kCapPool0, kBuckets><<<h->smCount * h->seedBlocksPerSM[0], kSeedThreads, h->seedSmemBytes[0], s>>>(sp);
-  // tier 1: the middles that did not fit, with the large scratch
+  k_seed_middles<Tier0::B, Tier0::T, Tier0::P, Tier0::K, Tier0::N><<<h->smCount * h->seedBlocksPerSM[0], Tier0::N, h->seedSmemBytes[0], s>>>(sp);
+  // tier 1: the middles that did not fit tier 0
   sp.workCounter = wc + 2;
-  sp.workList = h->overflowList.as<uint32_t>();
+  sp.workList = ov0;
   sp.nWorkPtr = wc + 1;
+  sp.overflowList = ov1;
+  sp.overflowCount = wc + 3;
+  k_seed_middles<Tier1::B, Tier1::T, Tier1::P, Tier1::K, Tier1::N><<<h->smCount * h->seedBlocksPerSM[1], Tier1::N, h->seedSmemBytes[1], s>>>(sp);
+  // tier 2: the rest, largest scratch, 1 block per SM
+  sp.workCounter = wc + 4;
+  sp.workList = ov1;
+  sp.nWorkPtr = wc + 3;
   sp.overflowList = nullptr;
   sp.overflowCount = nullptr;
-  k_seed_middles<kCapB1, kCapT1, kCapPool1, kBuckets><<<h->smCount * h->seedBlocksPerSM[1], kSeedThreads, h->seedSmemBytes[1], s>>>(sp);
+  k_seed_middles<Tier2::B, Tier2::T, Tier2::P, Tier2::K, Tier2::N><<<h->smCount * h->seedBlocksPerSM[2], Tier2::N, h->seedSmemBytes[2], s>>>(sp);
   sp.nWorkPtr = wp.workStart + nNavAll;
-  launches += 2;
+  launches += 3;
 
   CUDA_TRY(cudaEventRecord(h->ev[3], s));
   CompactParams cp{};
@@ -324,8 +334,8 @@ int finish(b200seed_handle* h, cudaStream_t s, b200seed_seeds* out) {
   const int st = *h->hStatus;
   if (st & (kStatusOverflowDoublets | kStatusOverflowPool)) {
     return fail(B200SEED_ERR_OVERFLOW,
-                "per-middle scratch exhausted even in the large tier (doublets > " + std::to_string(kCapB1) + "/" +
-                    std::to_string(kCapT1) + " or candidates per middle > " + std::to_string(kCapPool1) + ")");
+                "per-middle scratch exhausted even in the largest tier (doublets > " + std::to_string(Tier2::B) + "/" +
+                    std::to_string(Tier2::T) + " or candidates per middle > " + std::to_string(Tier2::P) + ")");
   }
   if (*h->hSeedTotal > h->lastCapacity) {
     return fail(B200SEED_ERR_CAPACITY, "seed buffers too small: need " + std::to_string(*h->hSeedTotal));
@@ -437,24 +447,31 @@ int b200seed_create(const b200seed_config* cfg, int device, b200seed_handle** ou
   CREATE_TRY(cudaMallocHost(&h->hSeedTotal, 16));
 
   h->exactTies = (int)env_u32("B200SEED_EXACT_TIES", 1);
-  h->seedSmemBytes[0] = sizeof(SeedLayout0);
-  h->seedSmemBytes[1] = sizeof(SeedLayout1);
-  if (h->seedSmemBytes[1] > (size_t)prop.sharedMemPerBlockOptin) {
+  h->seedSmemBytes[0] = sizeof(TierLayout<Tier0>);
+  h->seedSmemBytes[1] = sizeof(TierLayout<Tier1>);
+  h->seedSmemBytes[2] = sizeof(TierLayout<Tier2>);
+  if (h->seedSmemBytes[2] > (size_t)prop.sharedMemPerBlockOptin) {
     return cleanup(fail(B200SEED_ERR_CUDA, "device offers less shared memory per block than the seeding kernel needs"));
   }
-  CREATE_TRY(cudaFuncSetAttribute(k_seed_middles<kCapB0, kCapT0, kCapPool0, kBuckets>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seedSmemBytes[0]));
-  CREATE_TRY(cudaFuncSetAttribute(k_seed_middles<kCapB1, kCapT1, kCapPool1, kBuckets>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seedSmemBytes[1]));
+  auto k0 = k_seed_middles<Tier0::B, Tier0::T, Tier0::P, Tier0::K, Tier0::N>;
+  auto k1 = k_seed_middles<Tier1::B, Tier1::T, Tier1::P, Tier1::K, Tier1::N>;
+  auto k2 = k_seed_middles<Tier2::B, Tier2::T, Tier2::P, Tier2::K, Tier2::N>;
+  CREATE_TRY(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seedSmemBytes[0]));
+  CREATE_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seedSmemBytes[1]));
+  CREATE_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seedSmemBytes[2]));
   CREATE_TRY(cudaFuncSetAttribute(k_sort_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->sortSmemCap * 16)));
   {
-    int b0 = 0, b1 = 0;
-    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_seed_middles<kCapB0, kCapT0, kCapPool0, kBuckets>,
-                                                             kSeedThreads, h->seedSmemBytes[0]));
-    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_seed_middles<kCapB1, kCapT1, kCapPool1, kBuckets>,
-                                                             kSeedThreads, h->seedSmemBytes[1]));
-    h->seedBlocksPerSM[0] = std::max(1, b0);
-    h->seedBlocksPerSM[1] = std::max(1, b1);
+    int b = 0;
+    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k0, Tier0::N, h->seedSmemBytes[0]));
+    h->seedBlocksPerSM[0] = std::max(1, b);
+    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k1, Tier1::N, h->seedSmemBytes[1]));
+    h->seedBlocksPerSM[1] = std::max(1, b);
+    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k2, Tier2::N, h->seedSmemBytes[2]));
+    h->seedBlocksPerSM[2] = std::max(1, b);
+  }
+  if (std::getenv("B200SEED_VERBOSE") != nullptr) {
+    std::fprintf(stderr, "b200seed: tiers smem %zu/%zu/%zu bytes, blocks per SM %d/%d/%d\n", h->seedSmemBytes[0],
+                 h->seedSmemBytes[1], h->seedSmemBytes[2], h->seedBlocksPerSM[0], h->seedBlocksPerSM[1], h->seedBlocksPerSM[2]);
   }
 
   int rc = upload(h->navBins, h->plan.navBins, h->stream);
