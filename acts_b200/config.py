@@ -207,6 +207,7 @@ class Doublets(C.Structure):
         ("yNew", C.c_void_p),
         ("middleCapacity", C.c_uint64),
         ("doubletCapacity", C.c_uint64),
+        ("gpuMilliseconds", C.c_float),
     ]
 
 

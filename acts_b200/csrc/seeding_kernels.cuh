@@ -1452,6 +1452,112 @@ __global__ void k_event_offsets(const __grid_constant__ CompactParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// Materialised doublet search (two-pass count / scan / fill), one warp per
+// middle space point.  This is the north star's "allocation-free two-pass"
+// variant: every compatible doublet is written to HBM as a 32-byte record in the
+// reference's emission order (neighbour bins in order, ascending position).
+// The production path keeps the doublets in shared memory instead (DESIGN.md
+// section 6); this path backs b200seed_debug_doublets (stage-level parity) and the
+// measurement of the HBM-bound variant.
+// ---------------------------------------------------------------------------
+struct DoubletDumpParams {
+  DeviceConfig cfg;
+  const float2 *pXY, *pZR, *pVar;
+  const uint32_t* binStart;
+  const uint32_t *navBins, *botOffsets, *botBins, *topOffsets, *topBins;
+  const uint32_t *workPos, *workEG;
+  uint32_t nWork, nNav, nBins;
+  const float *zWinLo, *zWinHi;
+  int nZWin;
+  uint32_t* count;       // [nWork]  bottoms + tops
+  uint32_t* nBottom;     // [nWork]
+  const uint32_t* first; // [nWork + 1] exclusive scan of count (fill pass)
+  uint32_t* otherPos;
+  float *cotTheta, *iDeltaR, *er, *u, *v, *xNew, *yNew;
+};
+
+template <bool kFill>
+__global__ void __launch_bounds__(256) k_doublets_materialised(const __grid_constant__ DoubletDumpParams p) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t ltMask = (1u << lane) - 1u;
+  const uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
+  const DeviceConfig& cfg = p.cfg;
+  for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < p.nWork; w += warpsPerGrid) {
+    const uint32_t m = __ldg(p.workPos + w);
+    const uint32_t eg = __ldg(p.workEG + w);
+    const uint32_t ev = eg / p.nNav, g = eg - ev * p.nNav;
+    const uint32_t* bs = p.binStart + (size_t)ev * p.nBins;
+    const uint32_t botBeg = __ldg(p.botOffsets + g), nBot = __ldg(p.botOffsets + g + 1) - botBeg;
+    const uint32_t topBeg = __ldg(p.topOffsets + g), nTop = __ldg(p.topOffsets + g + 1) - topBeg;
+    MiddleSp mid;
+    {
+      const float2 mxy = ldg2(p.pXY + m), mzr = ldg2(p.pZR + m), mvar = ldg2(p.pVar + m);
+      mid.x = mxy.x; mid.y = mxy.y; mid.z = mzr.x; mid.r = mzr.y; mid.varZ = mvar.x; mid.varR = mvar.y;
+      middle_info(mid);
+    }
+    const float rM = mid.r;
+    const float firstMiddleR = ldg2(p.pZR + bs[__ldg(p.navBins + g)]).y;
+    uint32_t out = kFill ? p.first[w] : 0u;
+    uint32_t nB = 0, nAll = 0;
+    for (uint32_t side = 0; side < 2; ++side) {  // bottoms first, then tops
+      const uint32_t nWin = side == 0 ? nBot : nTop;
+      for (uint32_t k = 0; k < nWin; ++k) {
+        const uint32_t bin = __ldg((side == 0 ? p.botBins + botBeg : p.topBins + topBeg) + k);
+        const uint32_t b0 = bs[bin], b1 = bs[bin + 1];
+        uint32_t s, e;
+        if (side == 0) {
+          const float trimValue = fsub(firstMiddleR, cfg.dRMaxB);
+          const uint32_t trim = warp_first_true(b0, b1, [&](uint32_t i) { return !(ldg2(p.pZR + i).y < trimValue); });
+          s = warp_first_true(trim, b1, [&](uint32_t i) { return fsub(rM, ldg2(p.pZR + i).y) <= cfg.dRMaxB; });
+          e = warp_first_true(s, b1, [&](uint32_t i) { return fsub(rM, ldg2(p.pZR + i).y) < cfg.dRMinB; });
+        } else {
+          const float trimValue = fadd(firstMiddleR, cfg.dRMinT);
+          const uint32_t trim = warp_first_true(b0, b1, [&](uint32_t i) { return !(ldg2(p.pZR + i).y < trimValue); });
+          s = warp_first_true(trim, b1, [&](uint32_t i) { return fsub(ldg2(p.pZR + i).y, rM) >= cfg.dRMinT; });
+          e = warp_first_true(s, b1, [&](uint32_t i) { return fsub(ldg2(p.pZR + i).y, rM) > cfg.dRMaxT; });
+        }
+        for (uint32_t base = s; base < e; base += 32) {
+          const uint32_t o = base + lane;
+          bool pass = false;
+          DoubletRec rec;
+          if (o < e) {
+            const float2 zr = ldg2(p.pZR + o);
+            float dR, dZ;
+            const bool ok = side == 0 ? doublet_zr_cuts<true>(cfg, mid, zr.x, zr.y, dR, dZ)
+                                      : doublet_zr_cuts<false>(cfg, mid, zr.x, zr.y, dR, dZ);
+            if (ok) {
+              const float2 xy = ldg2(p.pXY + o), var = ldg2(p.pVar + o);
+              pass = side == 0 ? doublet_finish<true>(cfg, mid, dR, dZ, xy.x, xy.y, zr.y, var.x, var.y, p.zWinLo, p.zWinHi, p.nZWin, rec)
+                               : doublet_finish<false>(cfg, mid, dR, dZ, xy.x, xy.y, zr.y, var.x, var.y, p.zWinLo, p.zWinHi, p.nZWin, rec);
+            }
+          }
+          const uint32_t mask = __ballot_sync(0xffffffffu, pass);
+          if (kFill && pass) {
+            const uint32_t d = out + (uint32_t)__popc(mask & ltMask);
+            p.otherPos[d] = o;
+            p.cotTheta[d] = rec.cotTheta;
+            p.iDeltaR[d] = rec.iDeltaR;
+            p.er[d] = rec.er;
+            p.u[d] = rec.u;
+            p.v[d] = rec.v;
+            p.xNew[d] = rec.xNew;
+            p.yNew[d] = rec.yNew;
+          }
+          const uint32_t c = (uint32_t)__popc(mask);
+          out += c;
+          nAll += c;
+        }
+      }
+      if (side == 0) nB = nAll;
+    }
+    if (!kFill && lane == 0) {
+      p.count[w] = nAll;
+      p.nBottom[w] = nB;
+    }
+  }
+}
+
 // phi = atan2f(y, x) replay, for validation against the host libm
 __global__ void k_atan2f(const float* __restrict__ y, const float* __restrict__ x, float* __restrict__ out, unsigned long long n) {
   for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {

@@ -94,6 +94,7 @@ struct b200seed_handle {
   unsigned long long* hSeedTotal = nullptr;
   // state of the last call
   uint32_t lastEvents = 0, lastTotal = 0;
+  int lastZWin = 0;
   unsigned long long lastCapacity = 0;
   const unsigned long long* lastSeedOffsets = nullptr;
   b200seed_counters lastCounters{};
@@ -306,6 +307,7 @@ int enqueue(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal, const uint32_
   CUDA_TRY(cudaMemcpyAsync(h->hCounters + kCntSlots, h->binStart.as<uint32_t>() + nBinsAll, 4, cudaMemcpyDeviceToHost, s));
   h->lastEvents = nEvents;
   h->lastTotal = nTotal;
+  h->lastZWin = nZWin;
   h->lastCapacity = outCapacity;
   h->launches = launches;
   h->pending = true;
@@ -683,9 +685,82 @@ int b200seed_debug_grid(b200seed_handle* h, uint64_t capacity, uint32_t* copiedF
 }
 
 int b200seed_debug_doublets(b200seed_handle* h, b200seed_doublets* out) {
-  (void)h;
-  (void)out;
-  return fail(B200SEED_ERR_UNSUPPORTED, "materialised doublet dump is not built yet");
+  if (h == nullptr || out == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (h->lastEvents == 0) return fail(B200SEED_ERR_INVALID_ARGUMENT, "no previous run on this handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  cudaStream_t s = h->stream;
+  const uint32_t nWork = (uint32_t)h->lastCounters.nMiddles;
+  const HostPlan& plan = h->plan;
+  DevBuf count, nBottom, first;
+  struct Guard {
+    std::vector<DevBuf*> bufs;
+    ~Guard() { for (DevBuf* b : bufs) b->release(); }
+  } guard;
+  guard.bufs = {&count, &nBottom, &first};
+  CUDA_TRY(count.reserve(((size_t)nWork + 1) * 4));
+  CUDA_TRY(nBottom.reserve(((size_t)nWork + 1) * 4));
+  CUDA_TRY(first.reserve(((size_t)nWork + 2) * 4));
+  DoubletDumpParams dp{};
+  dp.cfg = plan.dev;
+  if (h->lastZWin > 0) dp.cfg.doubletCuts = kCutsVertexZ;
+  dp.pXY = h->pXY.as<float2>(); dp.pZR = h->pZR.as<float2>(); dp.pVar = h->pVar.as<float2>();
+  dp.binStart = h->binStart.as<uint32_t>();
+  dp.navBins = h->navBins.as<uint32_t>();
+  dp.botOffsets = h->botOffsets.as<uint32_t>(); dp.botBins = h->botBins.as<uint32_t>();
+  dp.topOffsets = h->topOffsets.as<uint32_t>(); dp.topBins = h->topBins.as<uint32_t>();
+  dp.workPos = h->workPos.as<uint32_t>(); dp.workEG = h->workEG.as<uint32_t>();
+  dp.nWork = nWork; dp.nNav = (uint32_t)plan.navBins.size(); dp.nBins = (uint32_t)plan.dev.nGlobalBins;
+  dp.zWinLo = h->zWin.as<float>(); dp.zWinHi = h->zWin.as<float>() + kMaxZWindows; dp.nZWin = h->lastZWin;
+  dp.count = count.as<uint32_t>(); dp.nBottom = nBottom.as<uint32_t>(); dp.first = first.as<uint32_t>();
+  const int blocks = h->smCount * 8;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  CUDA_TRY(cudaEventRecord(e0, s));
+  if (nWork > 0) k_doublets_materialised<false><<<blocks, 256, 0, s>>>(dp);
+  k_scan<<<1, kScanThreads, 0, s>>>(dp.count, first.as<uint32_t>(), nWork);
+  uint32_t total = 0;
+  CUDA_TRY(cudaMemcpyAsync(&total, first.as<uint32_t>() + nWork, 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  out->nMiddles = nWork;
+  out->nDoublets = total;
+  if (out->middlePos == nullptr) {  // size query
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    out->gpuMilliseconds = 0.f;
+    return B200SEED_OK;
+  }
+  if (out->middleCapacity < nWork || out->doubletCapacity < total) {
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return fail(B200SEED_ERR_CAPACITY, "debug_doublets buffers too small");
+  }
+  DevBuf cols[8];
+  for (DevBuf& b : cols) guard.bufs.push_back(&b);
+  for (DevBuf& b : cols) CUDA_TRY(b.reserve(std::max<size_t>(4, (size_t)total * 4)));
+  dp.otherPos = cols[0].as<uint32_t>();
+  dp.cotTheta = cols[1].as<float>(); dp.iDeltaR = cols[2].as<float>(); dp.er = cols[3].as<float>();
+  dp.u = cols[4].as<float>(); dp.v = cols[5].as<float>(); dp.xNew = cols[6].as<float>(); dp.yNew = cols[7].as<float>();
+  if (nWork > 0) k_doublets_materialised<true><<<blocks, 256, 0, s>>>(dp);
+  CUDA_TRY(cudaEventRecord(e1, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  cudaEventElapsedTime(&out->gpuMilliseconds, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  std::vector<uint32_t> first32((size_t)nWork + 1);
+  CUDA_TRY(cudaMemcpy(first32.data(), first.ptr, ((size_t)nWork + 1) * 4, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i <= nWork; ++i) out->firstDoublet[i] = first32[i];
+  if (nWork > 0) {
+    CUDA_TRY(cudaMemcpy(out->middlePos, h->workPos.ptr, (size_t)nWork * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out->nBottom, nBottom.ptr, (size_t)nWork * 4, cudaMemcpyDeviceToHost));
+  }
+  if (total > 0) {
+    void* dst[8] = {out->otherPos, out->cotTheta, out->iDeltaR, out->er, out->u, out->v, out->xNew, out->yNew};
+    for (int i = 0; i < 8; ++i) CUDA_TRY(cudaMemcpy(dst[i], cols[i].ptr, (size_t)total * 4, cudaMemcpyDeviceToHost));
+  }
+  return B200SEED_OK;
 }
 
 int b200seed_debug_atan2f(b200seed_handle* h, uint64_t n, const float* y, const float* x, float* phi) {

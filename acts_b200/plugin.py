@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 from . import config as cfgmod
-from .config import Config, Counters, Info, Seeds
+from .config import Config, Counters, Doublets, Info, Seeds
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libacts_b200_seeding.so")
@@ -62,7 +62,7 @@ def lib():
         L.b200seed_run_batch_device.argtypes = [vp, u32, u32, vp] + [f32p] * 6 + [vp, C.POINTER(Seeds), vp]
         L.b200seed_sync.argtypes = [vp, C.POINTER(Seeds)]
         L.b200seed_debug_grid.argtypes = [vp, u64] + [vp] * 7 + [u64, vp, vp]
-        L.b200seed_debug_doublets.argtypes = [vp, vp]
+        L.b200seed_debug_doublets.argtypes = [vp, C.POINTER(Doublets)]
         L.b200seed_debug_atan2f.argtypes = [vp, u64, vp, vp, vp]
         _lib = L
     return _lib
@@ -209,6 +209,26 @@ class SeedingEngine:
         _check(lib().b200seed_debug_grid(self._h, n, *[_p(g[k]) for k in ("copiedFromIndex", "x", "y", "z", "r", "varZ", "varR")],
                                          nb, _p(g["binBegin"]), _p(g["binEnd"])))
         return g
+
+    def debug_doublets(self, fetch: bool = True) -> dict:
+        """Materialised two-pass doublet search of the last batch (``b200seed_debug_doublets``)."""
+        d = Doublets()
+        _check(lib().b200seed_debug_doublets(self._h, C.byref(d)))
+        nm, nd = int(d.nMiddles), int(d.nDoublets)
+        out = {"nMiddles": nm, "nDoublets": nd}
+        if not fetch:
+            return out
+        arr = {"middlePos": np.zeros(nm, np.uint32), "firstDoublet": np.zeros(nm + 1, np.uint64),
+               "nBottom": np.zeros(nm, np.uint32), "otherPos": np.zeros(nd, np.uint32)}
+        for k in ("cotTheta", "iDeltaR", "er", "u", "v", "xNew", "yNew"):
+            arr[k] = np.zeros(nd, np.float32)
+        for k, a in arr.items():
+            setattr(d, k, _p(a))
+        d.middleCapacity, d.doubletCapacity = nm, nd
+        _check(lib().b200seed_debug_doublets(self._h, C.byref(d)))
+        out.update(arr)
+        out["gpuMilliseconds"] = float(d.gpuMilliseconds)
+        return out
 
     def device_atan2f(self, y: np.ndarray, x: np.ndarray) -> np.ndarray:
         y = np.ascontiguousarray(y, dtype=np.float32)

@@ -316,6 +316,7 @@ typedef struct b200seed_doublets {
   float* yNew;
   uint64_t middleCapacity;
   uint64_t doubletCapacity;
+  float gpuMilliseconds;  /* out: GPU time of count + scan + fill (CUDA events) */
 } b200seed_doublets;
 int b200seed_debug_doublets(b200seed_handle* h, b200seed_doublets* out);
 

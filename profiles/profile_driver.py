@@ -13,6 +13,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--events", type=int, default=1)
 ap.add_argument("--mu", type=float, default=200.0)
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--doublets", action="store_true")
 a = ap.parse_args()
 cfg = config.pu200_config(plugin.config_init)
 eng = plugin.SeedingEngine(cfg)
@@ -21,3 +22,8 @@ cols, off = events.concat_events(evs)
 for _ in range(a.reps):
     res = eng.run_batch(cols, off)
 print("seeds", sum(r["quality"].size for r in res), eng.counters(), eng.stage_times_ms())
+if "--doublets" in sys.argv:
+    d = eng.debug_doublets()
+    gb = d["nDoublets"] * 32 / 1e9
+    print("materialised doublets: %d middles, %d doublets, %.2f GB written, count+scan+fill %.3f ms -> %.0f GB/s of doublet writes"
+          % (d["nMiddles"], d["nDoublets"], gb, d["gpuMilliseconds"], gb / (d["gpuMilliseconds"] * 1e-3)))

@@ -279,3 +279,27 @@ def test_property_checks_at_full_size(plugin):
     diff = set(orig.items()) ^ set(ref.items())
     assert len(diff) <= 8, len(diff)
     eng.close()
+
+
+def test_materialised_doublets_match_oracle(plugin, O):
+    """Stage-level parity of the doublet search (DoubletSeedFinder.cpp:41-273): per middle the same
+    bottoms and tops in the reference's emission order with bit-identical
+    {cotTheta, iDeltaR, er, u, v, x', y'} (two-pass count / scan / fill path)."""
+    from acts_b200 import events
+
+    for name, mu in (("pu200", 20), ("itk_like", 20), ("pu200", 40)):
+        override = dict(interactionPointCut=1) if mu == 40 else {}
+        eng = plugin.SeedingEngine(make_config(name, plugin.config_init).update(**override))
+        orc = O.Oracle(make_config(name, O.config_init).update(**override))
+        ev = events.pileup_event(2, mu=mu)
+        eng.run(ev)
+        got = eng.debug_doublets()
+        ref = orc.run(ev, dump_doublets=True)["doublets"]
+        assert got["nMiddles"] == ref["middlePos"].size
+        assert np.array_equal(got["middlePos"], ref["middlePos"])
+        assert np.array_equal(got["firstDoublet"], ref["firstDoublet"])
+        assert np.array_equal(got["nBottom"], ref["nBottom"])
+        assert np.array_equal(got["otherPos"], ref["otherPos"])
+        for k in ("cotTheta", "iDeltaR", "er", "u", "v", "xNew", "yNew"):
+            assert np.array_equal(got[k].view(np.uint32), ref[k].view(np.uint32)), (name, k)
+        eng.close()
