@@ -910,7 +910,8 @@ __device__ __forceinline__ void block_fix_ties(uint32_t n, const float* cot, con
 
 // blocks per SM that fit the 227 KB of shared memory (1 KB per block is reserved)
 constexpr int seed_blocks_per_sm(size_t layoutBytes) {
-  return layoutBytes + 1024 <= 232448 / 3 ? 3 : (layoutBytes + 1024 <= 232448 / 2 ? 2 : 1);
+  return layoutBytes + 1024 <= 232448 / 4 ? 4
+         : (layoutBytes + 1024 <= 232448 / 3 ? 3 : (layoutBytes + 1024 <= 232448 / 2 ? 2 : 1));
 }
 
 template <int CAPB, int CAPT, int CAPPOOL, int NBK, int THREADS>
@@ -1384,6 +1385,8 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
 }
 
 // the capacity tiers (see seeding_plugin.cu): {bottoms, tops, candidates, buckets, threads}
+// Measured on B200 at <mu>=200 (profiles/README.md): 3 tiers (3/2/1 blocks per SM) 8.4 ms/event,
+// 2 tiers (2/1) 10.0 ms, 4 tiers with a 256-thread 4-blocks-per-SM first tier 9.0 ms.
 struct Tier0 { static constexpr int B = 1536, T = 1152, P = 768, K = 1024, N = 384; };
 struct Tier1 { static constexpr int B = 2304, T = 1664, P = 1216, K = 2048, N = 512; };
 struct Tier2 { static constexpr int B = 3584, T = 2816, P = 4096, K = 2048, N = 512; };

@@ -133,8 +133,8 @@ int ensure_workspace(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal) {
   CUDA_TRY(h->workStart.reserve((nNavAll + 1) * 4));
   CUDA_TRY(h->workPos.reserve(nT * 4));
   CUDA_TRY(h->workEG.reserve(nT * 4));
-  CUDA_TRY(h->workCounter.reserve(32));
-  CUDA_TRY(h->overflowList.reserve(nT * 8));
+  CUDA_TRY(h->workCounter.reserve(64));
+  CUDA_TRY(h->overflowList.reserve(nT * 4 * (kNumTiers - 1)));
   CUDA_TRY(h->slotB.reserve(nT * K * 4));
   CUDA_TRY(h->slotM.reserve(nT * K * 4));
   CUDA_TRY(h->slotT.reserve(nT * K * 4));
@@ -167,7 +167,7 @@ int enqueue(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal, const uint32_
 
   CUDA_TRY(cudaMemsetAsync(h->binCount.ptr, 0, ((size_t)nBinsAll + 1) * 4, s));
   CUDA_TRY(cudaMemsetAsync(h->binCursor.ptr, 0, ((size_t)nBinsAll + 1) * 4, s));
-  CUDA_TRY(cudaMemsetAsync(h->workCounter.ptr, 0, 32, s));
+  CUDA_TRY(cudaMemsetAsync(h->workCounter.ptr, 0, 64, s));
   CUDA_TRY(cudaMemsetAsync(h->counters.ptr, 0, kCntSlots * 8, s));
   CUDA_TRY(cudaMemsetAsync(h->status.ptr, 0, 16, s));
 
@@ -247,33 +247,28 @@ int enqueue(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal, const uint32_
   sp.exactTies = h->exactTies;
   sp.counters = gp.counters;
   sp.status = gp.status;
-  // workCounter words: [0] tier-0 ticket, [1] overflow count 0->1, [2] tier-1 ticket,
-  // [3] overflow count 1->2, [4] tier-2 ticket
-  uint32_t* wc = h->workCounter.as<uint32_t>();
-  uint32_t* ov0 = h->overflowList.as<uint32_t>();
-  uint32_t* ov1 = ov0 + std::max<uint32_t>(nTotal, 1);
-  // tier 0: every middle, small scratch, 3 blocks per SM
-  sp.workCounter = wc + 0;
-  sp.workList = nullptr;
-  sp.overflowList = ov0;
-  sp.overflowCount = wc + 1;
-  k_seed_middles<Tier0::B, Tier0::T, Tier0::P, Tier0::K, Tier0::N><<<h->smCount * h->seedBlocksPerSM[0], Tier0::N, h->seedSmemBytes[0], s>>>(sp);
-  // tier 1: the middles that did not fit tier 0
-  sp.workCounter = wc + 2;
-  sp.workList = ov0;
-  sp.nWorkPtr = wc + 1;
-  sp.overflowList = ov1;
-  sp.overflowCount = wc + 3;
-  k_seed_middles<Tier1::B, Tier1::T, Tier1::P, Tier1::K, Tier1::N><<<h->smCount * h->seedBlocksPerSM[1], Tier1::N, h->seedSmemBytes[1], s>>>(sp);
-  // tier 2: the rest, largest scratch, 1 block per SM
-  sp.workCounter = wc + 4;
-  sp.workList = ov1;
-  sp.nWorkPtr = wc + 3;
-  sp.overflowList = nullptr;
-  sp.overflowCount = nullptr;
-  k_seed_middles<Tier2::B, Tier2::T, Tier2::P, Tier2::K, Tier2::N><<<h->smCount * h->seedBlocksPerSM[2], Tier2::N, h->seedSmemBytes[2], s>>>(sp);
+  // Capacity tiers: tier 0 takes every middle with the smallest scratch (most
+  // blocks per SM); a middle whose lists do not fit is re-queued to the next
+  // tier.  workCounter words: [2k] ticket of tier k, [2k+1] overflow count k -> k+1.
+  {
+    uint32_t* wc = h->workCounter.as<uint32_t>();
+    uint32_t* ovBase = h->overflowList.as<uint32_t>();
+    const size_t ovStride = std::max<uint32_t>(nTotal, 1);
+    auto launchTier = [&](int t, auto kernel, int threads) {
+      sp.workCounter = wc + 2 * t;
+      sp.workList = t == 0 ? nullptr : ovBase + (size_t)(t - 1) * ovStride;
+      sp.nWorkPtr = t == 0 ? wp.workStart + nNavAll : wc + 2 * (t - 1) + 1;
+      const bool last = t == kNumTiers - 1;
+      sp.overflowList = last ? nullptr : ovBase + (size_t)t * ovStride;
+      sp.overflowCount = last ? nullptr : wc + 2 * t + 1;
+      kernel<<<h->smCount * h->seedBlocksPerSM[t], threads, h->seedSmemBytes[t], s>>>(sp);
+    };
+    launchTier(0, k_seed_middles<Tier0::B, Tier0::T, Tier0::P, Tier0::K, Tier0::N>, Tier0::N);
+    launchTier(1, k_seed_middles<Tier1::B, Tier1::T, Tier1::P, Tier1::K, Tier1::N>, Tier1::N);
+    launchTier(2, k_seed_middles<Tier2::B, Tier2::T, Tier2::P, Tier2::K, Tier2::N>, Tier2::N);
+  }
   sp.nWorkPtr = wp.workStart + nNavAll;
-  launches += 3;
+  launches += kNumTiers;
 
   CUDA_TRY(cudaEventRecord(h->ev[3], s));
   CompactParams cp{};
@@ -449,31 +444,29 @@ int b200seed_create(const b200seed_config* cfg, int device, b200seed_handle** ou
   CREATE_TRY(cudaMallocHost(&h->hSeedTotal, 16));
 
   h->exactTies = (int)env_u32("B200SEED_EXACT_TIES", 1);
-  h->seedSmemBytes[0] = sizeof(TierLayout<Tier0>);
-  h->seedSmemBytes[1] = sizeof(TierLayout<Tier1>);
-  h->seedSmemBytes[2] = sizeof(TierLayout<Tier2>);
-  if (h->seedSmemBytes[2] > (size_t)prop.sharedMemPerBlockOptin) {
-    return cleanup(fail(B200SEED_ERR_CUDA, "device offers less shared memory per block than the seeding kernel needs"));
-  }
-  auto k0 = k_seed_middles<Tier0::B, Tier0::T, Tier0::P, Tier0::K, Tier0::N>;
-  auto k1 = k_seed_middles<Tier1::B, Tier1::T, Tier1::P, Tier1::K, Tier1::N>;
-  auto k2 = k_seed_middles<Tier2::B, Tier2::T, Tier2::P, Tier2::K, Tier2::N>;
-  CREATE_TRY(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seedSmemBytes[0]));
-  CREATE_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seedSmemBytes[1]));
-  CREATE_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seedSmemBytes[2]));
-  CREATE_TRY(cudaFuncSetAttribute(k_sort_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->sortSmemCap * 16)));
   {
-    int b = 0;
-    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k0, Tier0::N, h->seedSmemBytes[0]));
-    h->seedBlocksPerSM[0] = std::max(1, b);
-    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k1, Tier1::N, h->seedSmemBytes[1]));
-    h->seedBlocksPerSM[1] = std::max(1, b);
-    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k2, Tier2::N, h->seedSmemBytes[2]));
-    h->seedBlocksPerSM[2] = std::max(1, b);
+    auto setupTier = [&](int t, auto kernel, int threads, size_t bytes) -> cudaError_t {
+      h->seedSmemBytes[t] = bytes;
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      if (e != cudaSuccess) return e;
+      int b = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, threads, bytes);
+      h->seedBlocksPerSM[t] = std::max(1, b);
+      return e;
+    };
+    if (sizeof(TierLayout<Tier2>) > (size_t)prop.sharedMemPerBlockOptin) {
+      return cleanup(fail(B200SEED_ERR_CUDA, "device offers less shared memory per block than the seeding kernel needs"));
+    }
+    CREATE_TRY(setupTier(0, k_seed_middles<Tier0::B, Tier0::T, Tier0::P, Tier0::K, Tier0::N>, Tier0::N, sizeof(TierLayout<Tier0>)));
+    CREATE_TRY(setupTier(1, k_seed_middles<Tier1::B, Tier1::T, Tier1::P, Tier1::K, Tier1::N>, Tier1::N, sizeof(TierLayout<Tier1>)));
+    CREATE_TRY(setupTier(2, k_seed_middles<Tier2::B, Tier2::T, Tier2::P, Tier2::K, Tier2::N>, Tier2::N, sizeof(TierLayout<Tier2>)));
   }
+  CREATE_TRY(cudaFuncSetAttribute(k_sort_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->sortSmemCap * 16)));
   if (std::getenv("B200SEED_VERBOSE") != nullptr) {
-    std::fprintf(stderr, "b200seed: tiers smem %zu/%zu/%zu bytes, blocks per SM %d/%d/%d\n", h->seedSmemBytes[0],
-                 h->seedSmemBytes[1], h->seedSmemBytes[2], h->seedBlocksPerSM[0], h->seedBlocksPerSM[1], h->seedBlocksPerSM[2]);
+    for (int t = 0; t < kNumTiers; ++t) {
+      std::fprintf(stderr, "b200seed: tier %d: %zu bytes of shared memory, %d blocks per SM\n", t, h->seedSmemBytes[t],
+                   h->seedBlocksPerSM[t]);
+    }
   }
 
   int rc = upload(h->navBins, h->plan.navBins, h->stream);
