@@ -83,6 +83,9 @@ struct WorkParams {
   uint32_t* workStart;  // [nEvents * nNav + 1]
   uint32_t* workPos;    // [nTotal]
   uint32_t* workEG;     // [nTotal]
+  // phi-sector split of a single event over several GPUs: only middle bins
+  // whose phi bin lies in [phiFirst, phiFirst + phiCount) are seeded
+  uint32_t phiFirst, phiCount;
 };
 
 struct SeedParams {
@@ -544,7 +547,10 @@ __global__ void __launch_bounds__(256) k_middle_ranges(const __grid_constant__ W
     const uint32_t bin = p.navBins[g];
     const uint32_t b0 = bs[bin], b1 = bs[bin + 1];
     uint32_t lo = b0, hi = b0;
-    if (b0 != b1) {
+    // local phi bin (1-based) of this middle bin: global = (phi * (nZ + 2) + z) * (nR + 2) + r
+    const uint32_t phiBin = bin / (uint32_t)((p.cfg.nZ + 2) * (p.cfg.nR + 2));
+    const bool inSector = phiBin >= p.phiFirst && phiBin - p.phiFirst < p.phiCount;
+    if (b0 != b1 && inSector) {
       const float2 range = radius_range_for_middle(p.cfg, p.pZR[b0].x, variable);
       // TripletSeeder.cpp:183-195: skip r < min, stop at r > max (bin is r-sorted)
       lo = first_true(b0, b1, [&](uint32_t i) { return !(p.pZR[i].y < range.x); });

@@ -77,6 +77,7 @@ struct b200seed_handle {
   // re-queued to tier 1 (1 block per SM)
   uint32_t sortSmemCap = 4096;
   int exactTies = 1;
+  uint32_t phiFirst = 1, phiCount = 0xFFFFFFFFu;  // middle phi-bin sector (default: all)
   int seedBlocksPerSM[kNumTiers] = {1, 1, 1};
   size_t seedSmemBytes[kNumTiers] = {0, 0, 0};
   // constant tables
@@ -218,6 +219,8 @@ int enqueue(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal, const uint32_
   wp.workStart = h->workStart.as<uint32_t>();
   wp.workPos = h->workPos.as<uint32_t>();
   wp.workEG = h->workEG.as<uint32_t>();
+  wp.phiFirst = h->phiFirst;
+  wp.phiCount = h->phiCount;
   k_middle_ranges<<<nEvents, 256, 0, s>>>(wp);
   k_scan<<<1, kScanThreads, 0, s>>>(wp.midCount, wp.workStart, nNavAll);
   k_fill_work<<<(nNavAll * 32 + 255) / 256, 256, 0, s>>>(wp);
@@ -515,6 +518,28 @@ int b200seed_get_info(const b200seed_handle* h, b200seed_info* info) {
 int b200seed_get_counters(const b200seed_handle* h, b200seed_counters* c) {
   if (h == nullptr || c == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL argument");
   *c = h->lastCounters;
+  return B200SEED_OK;
+}
+
+// Restrict the following calls on this handle to the middle space points whose
+// phi bin lies in [firstPhiBin, firstPhiBin + nPhiBins) (1-based local bins;
+// nPhiBins = 0 restores "all").  Used to split ONE event over several GPUs:
+// every GPU builds the full grid, seeds its own sector (neighbour bins are read
+// across the sector border like everywhere else) and the per-sector seed lists,
+// concatenated in sector order, are the reference's output (phi is the
+// outermost navigation axis, GridIterator.ipp:228-242).
+int b200seed_set_phi_sector(b200seed_handle* h, uint32_t firstPhiBin, uint32_t nPhiBins) {
+  if (h == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL handle");
+  if (nPhiBins == 0) {
+    h->phiFirst = 1;
+    h->phiCount = 0xFFFFFFFFu;
+    return B200SEED_OK;
+  }
+  if (firstPhiBin < 1 || firstPhiBin > (uint32_t)h->plan.dev.phiBins) {
+    return fail(B200SEED_ERR_INVALID_ARGUMENT, "phi sector outside [1, phiBins]");
+  }
+  h->phiFirst = firstPhiBin;
+  h->phiCount = nPhiBins;
   return B200SEED_OK;
 }
 

@@ -23,7 +23,7 @@ LIB_PATH = os.path.join(_HERE, "libacts_b200_seeding.so")
 EXPORTED_SYMBOLS = [
     "b200seed_config_init", "b200seed_plan_info", "b200seed_plan_tables", "b200seed_create",
     "b200seed_destroy", "b200seed_last_error", "b200seed_get_info", "b200seed_get_counters",
-    "b200seed_get_stage_times",
+    "b200seed_get_stage_times", "b200seed_set_phi_sector",
     "b200seed_run", "b200seed_run_with_phi", "b200seed_run_batch", "b200seed_run_batch_device",
     "b200seed_sync", "b200seed_debug_grid", "b200seed_debug_doublets", "b200seed_debug_atan2f",
 ]
@@ -56,6 +56,7 @@ def lib():
         L.b200seed_get_info.argtypes = [vp, C.POINTER(Info)]
         L.b200seed_get_counters.argtypes = [vp, C.POINTER(Counters)]
         L.b200seed_get_stage_times.argtypes = [vp, vp]
+        L.b200seed_set_phi_sector.argtypes = [vp, u32, u32]
         L.b200seed_run.argtypes = [vp, u32] + [f32p] * 6 + [u32, f32p, f32p, C.POINTER(Seeds)]
         L.b200seed_run_with_phi.argtypes = [vp, u32] + [f32p] * 7 + [C.POINTER(Seeds)]
         L.b200seed_run_batch.argtypes = [vp, u32, vp] + [f32p] * 6 + [vp, C.POINTER(Seeds)]
@@ -139,6 +140,10 @@ class SeedingEngine:
         c = Counters()
         _check(lib().b200seed_get_counters(self._h, C.byref(c)))
         return c.as_dict()
+
+    def set_phi_sector(self, first_phi_bin: int = 1, n_phi_bins: int = 0):
+        """Seed only middles in phi bins [first, first + n) (1-based); n = 0 -> all."""
+        _check(lib().b200seed_set_phi_sector(self._h, first_phi_bin, n_phi_bins))
 
     def stage_times_ms(self) -> dict:
         ms = np.zeros(4, dtype=np.float32)

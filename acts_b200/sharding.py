@@ -30,3 +30,12 @@ def gather_seed_counts(local_counts: dict[int, int], n_events: int, group=None) 
     if missing:
         raise RuntimeError(f"events without a result: {missing[:8]}")
     return [merged[e] for e in range(n_events)]
+
+
+def phi_sector_of_rank(n_phi_bins: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous block of middle phi bins (1-based first bin, count) of one rank when a
+    single event is split over `world` GPUs (latency mode, BASELINE.json configs[4])."""
+    base, extra = divmod(n_phi_bins, world)
+    first = 1 + rank * base + min(rank, extra)
+    count = base + (1 if rank < extra else 0)
+    return first, count

@@ -279,6 +279,13 @@ int b200seed_run_batch_device(b200seed_handle* h, uint32_t nEvents,
 /* Wait for the last *_device call; fills out->size, returns deferred errors. */
 int b200seed_sync(b200seed_handle* h, b200seed_seeds* out);
 
+/* Single-event split over several GPUs: restrict
+ * the following calls on this handle to the middle space points whose phi bin
+ * (1-based) lies in [firstPhiBin, firstPhiBin + nPhiBins); nPhiBins = 0 restores
+ * "all".  Sector results concatenated in sector order equal the unsplit result.
+ * Valid because seedConfirmation = false has no cross-middle state. */
+int b200seed_set_phi_sector(b200seed_handle* h, uint32_t firstPhiBin, uint32_t nPhiBins);
+
 /* GPU time of the stages of the last completed call, milliseconds (CUDA events
  * on the launching stream): ms[0] grid build, ms[1] middle work list,
  * ms[2] seeding kernel, ms[3] ordered seed compaction. */

@@ -50,3 +50,14 @@ def test_gather_detects_missing_events():
 
     with pytest.raises(RuntimeError):
         sharding.gather_seed_counts({0: 1, 2: 3}, 3)
+
+
+def test_phi_sectors_partition_the_bins():
+    from acts_b200 import sharding
+
+    for n_phi, world in ((53, 8), (53, 2), (26, 4), (5, 8), (138, 3)):
+        seen = []
+        for rank in range(world):
+            first, count = sharding.phi_sector_of_rank(n_phi, rank, world)
+            seen.extend(range(first, first + count))
+        assert seen == list(range(1, n_phi + 1))
