@@ -611,7 +611,8 @@ struct SeedShared {
   MiddleSp mid;
   uint32_t w, m, eg;
   uint32_t nB, nT, nSurv, poolCount, nValid;
-  uint32_t tie, tieTmp, bad;
+  uint32_t tie, tieB, tieT, bad;
+  int cotMinB, cotMaxB, cotMinT, cotMaxT;  // ordered-int images of the cotTheta ranges
   uint32_t runCarry;
   uint32_t nextChunkA, nextChunkC;
   uint32_t nBotWin, nTopWin;
@@ -651,8 +652,7 @@ struct SeedLayout {
       uint32_t uSeqB[CAPB];
       float uCotT[CAPT];
       uint32_t uSeqT[CAPT];
-      uint16_t rankB[CAPB];
-      uint16_t rankT[CAPT];
+      uint16_t rankAll[CAPB + CAPT];  // sorted order: [0, nB) bottoms, [nB, nB + nT) tops (indices into u*B / u*T)
     } a;
     struct {
       uint32_t pool[CAPPOOL];  // emission order: sorted top rank | sorted bottom rank << 16
@@ -719,52 +719,97 @@ __device__ __forceinline__ uint32_t warp_first_true(uint32_t lo, uint32_t hi, Pr
   return mask != 0u ? lo + (uint32_t)(__ffs(mask) - 1) : hi;
 }
 
-// Doublet search for one side (DoubletSeedFinder.cpp:41-273), two passes so that
-// the expensive transform runs on dense warps:
-//   pass 1: (z, r) cuts over the r windows, survivors appended as seq -> surv[]
+// float <-> int image that preserves the order (for shared-memory atomicMin/Max)
+__device__ __forceinline__ int float_to_ordered(float f) {
+  const int k = __float_as_int(f);
+  return k >= 0 ? k : k ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+// Doublet search for BOTH sides of one middle (DoubletSeedFinder.cpp:41-273), two
+// passes so that the expensive transform runs on dense warps:
+//   pass 1: (z, r) cuts over all r windows (tops, then bottoms); survivors are
+//           appended as seq | side << 31 -> surv[]
 //   pass 2: coordinate transform / remaining cuts on the survivors -> (cot, seq)
-template <bool kBottom>
-__device__ __forceinline__ void find_doublets(const SeedParams& p, SeedShared& sh, uint32_t nWin, const uint32_t* winS,
-                                              const uint32_t* winE, const uint32_t* winP, uint32_t* surv, uint32_t survCap,
-                                              float* cotOut, uint32_t* seqOut, uint32_t* counter, uint32_t cap) {
+//           lists of the two sides + the cotTheta range of each list
+// (the reference skips the bottoms of a middle without tops, TripletSeeder.cpp:62;
+// here both sides are searched together, a middle without tops is dropped after)
+__device__ __forceinline__ void find_doublets_both(const SeedParams& p, SeedShared& sh, uint32_t nBot, uint32_t nTop,
+                                                   uint32_t* surv, uint32_t survCap, float* cotB, uint32_t* seqB,
+                                                   uint32_t capB, float* cotT, uint32_t* seqT, uint32_t capT) {
   const MiddleSp mid = sh.mid;
-  if (threadIdx.x == 0) sh.nSurv = 0;
-  __syncthreads();
-  for (uint32_t k = 0; k < nWin; ++k) {
-    const uint32_t s = winS[k], e = winE[k], pre = winP[k];
+  for (uint32_t k = 0; k < nTop; ++k) {
+    const uint32_t s = sh.winTs[k], e = sh.winTe[k], pre = sh.winTp[k];
     for (uint32_t base = s; base < e; base += blockDim.x) {
       const uint32_t o = base + threadIdx.x;
       bool pass = false;
       if (o < e) {
         const float2 zr = ldg2(p.pZR + o);
         float dR, dZ;
-        pass = doublet_zr_cuts<kBottom>(p.cfg, mid, zr.x, zr.y, dR, dZ);
+        pass = doublet_zr_cuts<false>(p.cfg, mid, zr.x, zr.y, dR, dZ);
       }
       const uint32_t slot = warp_append(&sh.nSurv, pass);
       if (pass && slot < survCap) surv[slot] = pre + (o - s);
     }
   }
+  for (uint32_t k = 0; k < nBot; ++k) {
+    const uint32_t s = sh.winBs[k], e = sh.winBe[k], pre = sh.winBp[k];
+    for (uint32_t base = s; base < e; base += blockDim.x) {
+      const uint32_t o = base + threadIdx.x;
+      bool pass = false;
+      if (o < e) {
+        const float2 zr = ldg2(p.pZR + o);
+        float dR, dZ;
+        pass = doublet_zr_cuts<true>(p.cfg, mid, zr.x, zr.y, dR, dZ);
+      }
+      const uint32_t slot = warp_append(&sh.nSurv, pass);
+      if (pass && slot < survCap) surv[slot] = (pre + (o - s)) | 0x80000000u;
+    }
+  }
   __syncthreads();
   const uint32_t nS = sh.nSurv < survCap ? sh.nSurv : survCap;
-  if (sh.nSurv > survCap && threadIdx.x == 0) *counter = cap + 1;  // forces the overflow path
+  if (sh.nSurv > survCap && threadIdx.x == 0) sh.nB = capB + 1;  // forces the overflow path
+  float mnB = 3.0e38f, mxB = -3.0e38f, mnT = 3.0e38f, mxT = -3.0e38f;
   for (uint32_t base = 0; base < nS; base += blockDim.x) {
     const uint32_t i = base + threadIdx.x;
-    bool pass = false;
+    bool passB = false, passT = false;
     DoubletRec rec;
     uint32_t seq = 0;
     if (i < nS) {
-      seq = surv[i];
-      const uint32_t o = seq_to_pos(seq, winP, winS, nWin);
-      const float2 zr = ldg2(p.pZR + o), xy = ldg2(p.pXY + o), var = ldg2(p.pVar + o);
-      float dR, dZ;
-      doublet_zr_cuts<kBottom>(p.cfg, mid, zr.x, zr.y, dR, dZ);
-      pass = doublet_finish<kBottom>(p.cfg, mid, dR, dZ, xy.x, xy.y, zr.y, var.x, var.y, p.zWinLo, p.zWinHi, p.nZWin, rec);
+      const uint32_t sv = surv[i];
+      seq = sv & 0x7fffffffu;
+      if (sv >> 31) {
+        const uint32_t o = seq_to_pos(seq, sh.winBp, sh.winBs, nBot);
+        const float2 zr = ldg2(p.pZR + o), xy = ldg2(p.pXY + o), var = ldg2(p.pVar + o);
+        float dR, dZ;
+        doublet_zr_cuts<true>(p.cfg, mid, zr.x, zr.y, dR, dZ);
+        passB = doublet_finish<true>(p.cfg, mid, dR, dZ, xy.x, xy.y, zr.y, var.x, var.y, p.zWinLo, p.zWinHi, p.nZWin, rec);
+      } else {
+        const uint32_t o = seq_to_pos(seq, sh.winTp, sh.winTs, nTop);
+        const float2 zr = ldg2(p.pZR + o), xy = ldg2(p.pXY + o), var = ldg2(p.pVar + o);
+        float dR, dZ;
+        doublet_zr_cuts<false>(p.cfg, mid, zr.x, zr.y, dR, dZ);
+        passT = doublet_finish<false>(p.cfg, mid, dR, dZ, xy.x, xy.y, zr.y, var.x, var.y, p.zWinLo, p.zWinHi, p.nZWin, rec);
+      }
     }
-    const uint32_t slot = warp_append(counter, pass);
-    if (pass && slot < cap) {
-      cotOut[slot] = rec.cotTheta;
-      seqOut[slot] = seq;
+    const uint32_t slotB = warp_append(&sh.nB, passB);
+    const uint32_t slotT = warp_append(&sh.nT, passT);
+    if (passB) {
+      mnB = fminf(mnB, rec.cotTheta); mxB = fmaxf(mxB, rec.cotTheta);
+      if (slotB < capB) { cotB[slotB] = rec.cotTheta; seqB[slotB] = seq; }
     }
+    if (passT) {
+      mnT = fminf(mnT, rec.cotTheta); mxT = fmaxf(mxT, rec.cotTheta);
+      if (slotT < capT) { cotT[slotT] = rec.cotTheta; seqT[slotT] = seq; }
+    }
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    mnB = fminf(mnB, __shfl_xor_sync(0xffffffffu, mnB, d)); mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, d));
+    mnT = fminf(mnT, __shfl_xor_sync(0xffffffffu, mnT, d)); mxT = fmaxf(mxT, __shfl_xor_sync(0xffffffffu, mxT, d));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&sh.cotMinB, float_to_ordered(mnB)); atomicMax(&sh.cotMaxB, float_to_ordered(mxB));
+    atomicMin(&sh.cotMinT, float_to_ordered(mnT)); atomicMax(&sh.cotMaxT, float_to_ordered(mxT));
   }
   __syncthreads();
 }
@@ -792,13 +837,12 @@ struct SeqKey {  // order by emission index (unique)
   __device__ __forceinline__ bool after(uint32_t u, uint32_t v) const { return seq[u] > seq[v]; }
 };
 
-// Exclusive scan (sum) of a shared array of n words in place; *carry gets the
-// total.  Every thread scans kItems consecutive words serially, one block scan
-// combines the per-thread sums.
-__device__ __forceinline__ void block_scan_array(uint32_t* a, uint32_t n, uint32_t* scratch, uint32_t* carry) {
-  constexpr uint32_t kItems = 4;
-  if (threadIdx.x == 0) *carry = 0;
-  __syncthreads();
+// Exclusive scan (sum) of a shared array of n words in place; returns the total
+// (to every thread).  Every thread scans kItems consecutive words serially, one
+// block scan combines the per-thread sums: a single pass for n <= 8 * blockDim.x.
+__device__ __forceinline__ uint32_t block_scan_array(uint32_t* a, uint32_t n, uint32_t* scratch) {
+  constexpr uint32_t kItems = 8;
+  uint32_t carry = 0;
   for (uint32_t base = 0; base < n; base += blockDim.x * kItems) {
     const uint32_t i0 = base + threadIdx.x * kItems;
     uint32_t v[kItems];
@@ -809,27 +853,27 @@ __device__ __forceinline__ void block_scan_array(uint32_t* a, uint32_t n, uint32
       sum += v[k];
     }
     uint32_t total;
-    uint32_t run = block_scan_exclusive(sum, scratch, total, OpSum()) + *carry;
+    uint32_t run = block_scan_exclusive(sum, scratch, total, OpSum()) + carry;
 #pragma unroll
     for (uint32_t k = 0; k < kItems; ++k) {
       if ((i0 + k) < n) a[i0 + k] = run;
       run += v[k];
     }
-    __syncthreads();
-    if (threadIdx.x == 0) *carry += total;
-    __syncthreads();
+    carry += total;
   }
+  __syncthreads();
+  return carry;
 }
 
 // Bucket sort of n elements: sorted[rank] = element index.
 template <typename Key>
 __device__ __forceinline__ void block_bucket_sort(uint32_t n, const Key key, uint16_t* sorted, uint32_t* buckets,
-                                                  uint32_t nBk, uint32_t* scratch, uint32_t* carry) {
+                                                  uint32_t nBk, uint32_t* scratch) {
   for (uint32_t i = threadIdx.x; i <= nBk; i += blockDim.x) buckets[i] = 0;
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(buckets + key.bucket(i), 1u);
   __syncthreads();
-  block_scan_array(buckets, nBk, scratch, carry);
+  block_scan_array(buckets, nBk, scratch);
   // scatter: after this loop buckets[b] is the END of bucket b
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
     sorted[atomicAdd(buckets + key.bucket(i), 1u)] = (uint16_t)i;
@@ -847,6 +891,68 @@ __device__ __forceinline__ void block_bucket_sort(uint32_t n, const Key key, uin
       }
       sorted[j] = v;
     }
+  }
+  __syncthreads();
+}
+
+// Combined bucket sort of the bottom and top doublet lists of one middle by
+// (cotTheta, seq): the bottoms use buckets [0, nBk / 2), the tops [nBk / 2, nBk),
+// each list spread over its own cotTheta range.  rankAll[0, nB) are the bottoms
+// in sorted order, rankAll[nB, nB + nT) the tops (values index the per-side
+// arrays).  *tieB / *tieT are set when a list holds equal neighbours (equal keys
+// always share a bucket).
+__device__ __forceinline__ void block_sort_both(uint32_t nB, const float* cotB, const uint32_t* seqB, float minB, float maxB,
+                                                uint32_t nT, const float* cotT, const uint32_t* seqT, float minT, float maxT,
+                                                uint16_t* rankAll, uint32_t* buckets, uint32_t nBk, uint32_t* scratch,
+                                                uint32_t* tieB, uint32_t* tieT) {
+  const uint32_t half = nBk >> 1;
+  const float scaleB = maxB > minB ? (float)half / (maxB - minB) : 0.0f;
+  const float scaleT = maxT > minT ? (float)half / (maxT - minT) : 0.0f;
+  auto bucketOf = [&](uint32_t e) {
+    const bool bottom = e < nB;
+    const float c = bottom ? cotB[e] : cotT[e - nB];
+    float t = bottom ? fmul(fsub(c, minB), scaleB) : fmul(fsub(c, minT), scaleT);  // monotone in c
+    if (!(t > 0.0f)) t = 0.0f;
+    uint32_t b = (uint32_t)t;
+    if (b >= half) b = half - 1;
+    return bottom ? b : half + b;
+  };
+  const uint32_t n = nB + nT;
+  for (uint32_t i = threadIdx.x; i <= nBk; i += blockDim.x) buckets[i] = 0;
+  __syncthreads();
+  for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) atomicAdd(buckets + bucketOf(e), 1u);
+  __syncthreads();
+  block_scan_array(buckets, nBk, scratch);
+  for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
+    rankAll[atomicAdd(buckets + bucketOf(e), 1u)] = (uint16_t)(e < nB ? e : e - nB);
+  }
+  __syncthreads();  // buckets[b] is now the END of bucket b
+  for (uint32_t b = threadIdx.x; b < nBk; b += blockDim.x) {
+    const uint32_t s = b == 0 ? 0u : buckets[b - 1], e = buckets[b];
+    if (e - s < 2) continue;
+    const bool bottom = b < half;
+    const float* cot = bottom ? cotB : cotT;
+    const uint32_t* seq = bottom ? seqB : seqT;
+    bool tie = false;
+    for (uint32_t i = s + 1; i < e; ++i) {
+      const uint16_t v = rankAll[i];
+      const float cv = cot[v];
+      const uint32_t sv = seq[v];
+      uint32_t j = i;
+      while (j > s) {
+        const uint16_t u = rankAll[j - 1];
+        const float cu = cot[u];
+        tie |= cu == cv;
+        if (cu > cv || (cu == cv && seq[u] > sv)) {
+          rankAll[j] = u;
+          --j;
+        } else {
+          break;
+        }
+      }
+      rankAll[j] = v;
+    }
+    if (tie) *(bottom ? tieB : tieT) = 1u;
   }
   __syncthreads();
 }
@@ -875,9 +981,9 @@ __device__ __forceinline__ bool tie_flagged(const TieItem& a) { return (a.val >>
 // group's slots.  seqSorted / grpOf are n-entry u16 scratch arrays.
 __device__ __forceinline__ void block_fix_ties(uint32_t n, const float* cot, const uint32_t* seq, uint32_t totalCand,
                                                uint16_t* sorted, TieItem* W, uint16_t* seqSorted, uint16_t* grpOf,
-                                               uint32_t* buckets, uint32_t nBk, uint32_t* scratch, uint32_t* carry) {
+                                               uint32_t* buckets, uint32_t nBk, uint32_t* scratch) {
   SeqKey sk{seq, totalCand > 0 ? totalCand : 1u, (int)nBk};
-  block_bucket_sort(n, sk, seqSorted, buckets, nBk, scratch, carry);
+  block_bucket_sort(n, sk, seqSorted, buckets, nBk, scratch);
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
     const uint16_t e = sorted[i];
     const float c = cot[e];
@@ -963,7 +1069,8 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
       middle_info(mid);
       sh.mid = mid;
       sh.m = m;
-      sh.nB = 0; sh.nT = 0; sh.tie = 0; sh.bad = 0; sh.heapSize = 0; sh.poolCount = 0;
+      sh.nB = 0; sh.nT = 0; sh.nSurv = 0; sh.tie = 0; sh.tieB = 0; sh.tieT = 0; sh.bad = 0; sh.heapSize = 0; sh.poolCount = 0;
+      sh.cotMinB = 0x7fffffff; sh.cotMaxB = (int)0x80000000; sh.cotMinT = 0x7fffffff; sh.cotMaxT = (int)0x80000000;
       sh.nextChunkA = 0; sh.nextChunkC = 0; sh.heapSorted = 0;
       sh.nBotWin = nBot; sh.nTopWin = nTop;
     }
@@ -1006,19 +1113,13 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
     __syncthreads();
     if (tid == 0) fetchWork();  // next item: the global atomic's latency hides behind phase 1
 
-    // ---- phase 1: doublets (tops first, TripletSeeder.cpp:52-82) ---------
-    find_doublets<false>(p, sh, nTop, sh.winTs, sh.winTe, sh.winTp, surv, kSurvCap, L.u.a.uCotT, L.u.a.uSeqT, &sh.nT, CAPT);
-    const uint32_t nT = sh.nT;
-    if (nT == 0) {
-      if (tid == 0) p.slotCount[w] = 0;
-      continue;
-    }
-    find_doublets<true>(p, sh, nBot, sh.winBs, sh.winBe, sh.winBp, surv, kSurvCap, L.u.a.uCotB, L.u.a.uSeqB, &sh.nB, CAPB);
-    const uint32_t nB = sh.nB;
-    if (nB == 0 || nT > (uint32_t)CAPT || nB > (uint32_t)CAPB) {
+    // ---- phase 1: doublets of both sides (TripletSeeder.cpp:52-82) -------
+    find_doublets_both(p, sh, nBot, nTop, surv, kSurvCap, L.u.a.uCotB, L.u.a.uSeqB, CAPB, L.u.a.uCotT, L.u.a.uSeqT, CAPT);
+    const uint32_t nT = sh.nT, nB = sh.nB;
+    if (nT == 0 || nB == 0 || nT > (uint32_t)CAPT || nB > (uint32_t)CAPB) {
       if (tid == 0) {
         p.slotCount[w] = 0;
-        if (nB != 0) {  // does not fit this launch's scratch: hand over to the large-capacity launch
+        if (nT != 0 && nB != 0) {  // does not fit this launch's scratch: hand over to the next tier
           if (p.overflowList != nullptr) {
             p.overflowList[atomicAdd(p.overflowCount, 1u)] = w;
             sh.cnt[kCntMiddles] -= 1;  // counted again by the launch that completes it
@@ -1031,39 +1132,35 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
     }
 
     // ---- phase 2: order both lists like DoubletSeedFinder.hpp:94-104 -------
-    const float bkScale = (float)NBK / (2.0f * cfg.cotThetaMax);
     TieItem* tieW = reinterpret_cast<TieItem*>(L.sCot);
     uint16_t* tieSeqSorted = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(L.sCot) + 8u * CAPB);
     uint16_t* tieGrpOf = tieSeqSorted + CAPB;
+    uint16_t* rankB = L.u.a.rankAll;
+    uint16_t* rankT = L.u.a.rankAll + nB;
+    block_sort_both(nB, L.u.a.uCotB, L.u.a.uSeqB, ordered_to_float(sh.cotMinB), ordered_to_float(sh.cotMaxB), nT,
+                    L.u.a.uCotT, L.u.a.uSeqT, ordered_to_float(sh.cotMinT), ordered_to_float(sh.cotMaxT), L.u.a.rankAll,
+                    L.buckets, NBK, sh.scratch, &sh.tieB, &sh.tieT);
     {
-      CotKey bk{L.u.a.uCotB, L.u.a.uSeqB, cfg.cotThetaMax, bkScale, NBK};
-      block_bucket_sort(nB, bk, L.u.a.rankB, L.buckets, NBK, sh.scratch, &sh.runCarry);
-      const bool tieB = block_has_ties(nB, L.u.a.uCotB, L.u.a.rankB, &sh.tieTmp);
-      if (tieB && tid == 0) sh.tie = 1;
+      const bool tieB = sh.tieB != 0, tieT = sh.tieT != 0;  // block-uniform (read after the sort's last barrier)
+      if ((tieB || tieT) && tid == 0) sh.tie = 1;
       if (tieB && p.exactTies && nB > 16) {
-        block_fix_ties(nB, L.u.a.uCotB, L.u.a.uSeqB, sh.winBp[nBot], L.u.a.rankB, tieW, tieSeqSorted, tieGrpOf, L.buckets,
-                       NBK, sh.scratch, &sh.runCarry);
+        block_fix_ties(nB, L.u.a.uCotB, L.u.a.uSeqB, sh.winBp[nBot], rankB, tieW, tieSeqSorted, tieGrpOf, L.buckets, NBK,
+                       sh.scratch);
+      }
+      if (tieT && p.exactTies && nT > 16) {
+        block_fix_ties(nT, L.u.a.uCotT, L.u.a.uSeqT, sh.winTp[nTop], rankT, tieW, tieSeqSorted, tieGrpOf, L.buckets, NBK,
+                       sh.scratch);
       }
       for (uint32_t j = tid; j < nB; j += blockDim.x) {
-        const uint32_t idx = L.u.a.rankB[j];
+        const uint32_t idx = rankB[j];
         L.bCot[j] = L.u.a.uCotB[idx];
         L.bSeq[j] = L.u.a.uSeqB[idx];
-      }
-    }
-    {
-      CotKey tk{L.u.a.uCotT, L.u.a.uSeqT, cfg.cotThetaMax, bkScale, NBK};
-      block_bucket_sort(nT, tk, L.u.a.rankT, L.buckets, NBK, sh.scratch, &sh.runCarry);
-      const bool tieT = block_has_ties(nT, L.u.a.uCotT, L.u.a.rankT, &sh.tieTmp);
-      if (tieT && tid == 0) sh.tie = 1;
-      if (tieT && p.exactTies && nT > 16) {
-        block_fix_ties(nT, L.u.a.uCotT, L.u.a.uSeqT, sh.winTp[nTop], L.u.a.rankT, tieW, tieSeqSorted, tieGrpOf, L.buckets,
-                       NBK, sh.scratch, &sh.runCarry);
       }
     }
     // tops: full records in sorted order (recomputed from the space points);
     // from here on the sorted-top arrays hold what their names say
     for (uint32_t t = tid; t < nT; t += blockDim.x) {
-      const uint32_t idx = L.u.a.rankT[t];
+      const uint32_t idx = rankT[t];
       const uint32_t pos = seq_to_pos(L.u.a.uSeqT[idx], sh.winTp, sh.winTs, nTop);
       const float2 zr = ldg2(p.pZR + pos), xy = ldg2(p.pXY + pos), var = ldg2(p.pVar + pos);
       float dR, dZ;
@@ -1211,8 +1308,7 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
       if (t >= L.u.b.hval[j]) atomicAdd(&L.u.b.cnt[j], 1u);
     }
     __syncthreads();
-    block_scan_array(L.u.b.cnt, nB, sh.scratch, &sh.runCarry);
-    const uint32_t nValid = sh.runCarry;
+    const uint32_t nValid = block_scan_array(L.u.b.cnt, nB, sh.scratch);
     for (uint32_t e = tid; e < poolCount; e += blockDim.x) {
       const uint32_t to = L.u.b.pool[e];
       const uint32_t j = to >> 16, t = to & 0xFFFFu;
