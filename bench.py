@@ -295,6 +295,14 @@ def run_gpu(args):
     # neighbouring phi bins, plus 8 B per work item and 20 B per seed slot written
     alg_bytes = (2 * cfg.numPhiNeighbors + 1) * 24 * n_in + 8 * cnt["nMiddles"] + 20 * cnt["nSeeds"]
     achieved = alg_bytes / (seed_ms_avg * 1e-3) / 1e9
+    # DRAM traffic of the dominant kernel from the committed ncu capture (same batch shape)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get("events_per_launch") == E:
+            traffic = int(tj["dram_bytes_read"] + tj["dram_bytes_write"])
     # FP32 view: operations the reference algorithm itself needs (oracle counts)
     alg_flop = None
     fp32 = None
@@ -338,12 +346,14 @@ def run_gpu(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches_per_step * args.steps),
         "roofline": {"bound": "hbm", "kernel": "k_seed_middles", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": seed_ms_avg,
                      "grid_stage_ms": float(np.mean(grid_ms)),
                      "grid_stage_gbs": 52.0 * n_in / (float(np.mean(grid_ms)) * 1e-3) / 1e9,
-                     "note": "fused per-middle kernel: doublets never leave shared memory, so the HBM fraction is "
-                             "small by design; the binding limit is FP32 instruction issue (see `compute`)"},
+                     "note": "fused per-middle kernel (all capacity tiers): doublets never leave shared memory, so the "
+                             "HBM fraction is small by design and the DRAM traffic (ncu, profiles/r1_traffic.json) is "
+                             "below the algorithmic bytes because the packed space points stay in L2; the binding "
+                             "limit is FP32 instruction issue and block-barrier latency (see `compute`, DESIGN.md)"},
         "compute": fp32,
         "cpu_baseline": cpu,
         "counters_last_step": cnt,
