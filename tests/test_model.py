@@ -38,6 +38,17 @@ def test_pruned_tie_replay_matches_std_sort(env):
     assert L.model_check_tie_replay(4, 2000, 2000, 40) == 0
 
 
+def test_warp_parallel_replay_formulation_matches_std_sort(env):
+    """Scalar emulation of the device's warp-parallel partition (32 + 32 elements per step, k-th
+    misplaced left swapped with k-th misplaced right) against std::sort."""
+    L = env[3].lib()
+    assert L.model_check_warp_replay(1, 3000, 2000, 3, 0) == 0
+    assert L.model_check_warp_replay(2, 60000, 60, 6, 0) == 0
+    assert L.model_check_warp_replay(3, 200, 20000, 2, 0) == 0
+    assert L.model_check_warp_replay(4, 2500, 2000, 40, 0) == 0
+    assert L.model_check_warp_replay(5, 1000, 2000, 500, 0) == 0
+
+
 def test_heap_replay_matches_libstdcxx(env):
     assert env[3].lib().model_check_heap(5, 200000) == 0
 
