@@ -731,6 +731,60 @@ B2S_HD void std_sort_replay_ties(T* a, int n, Less less, Flagged flagged) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// Acts::estimateTrackParamsFromSeed (free parameters, FP64):
+// Core/src/Seeding/EstimateTrackParamsFromSeed.cpp:20-160.  out = {pos0 (3),
+// time, direction (3), q/p}.  Not bit-exact by contract: the reference goes
+// through Eigen (general affine inverse, expression templates) and the host
+// libm; the north star's tolerance for estimated parameters is 1e-9 relative.
+// ---------------------------------------------------------------------------
+B2S_HD void estimate_free_params(const double sp0[3], double t0, const double sp1[3], const double sp2[3],
+                                 const double bField[3], double out[8]) {
+  // estimationFrameLocalToGlobal, :20-41
+  const double rel[3] = {sp1[0] - sp0[0], sp1[1] - sp0[1], sp1[2] - sp0[2]};
+  const double bNorm = sqrt(bField[0] * bField[0] + bField[1] * bField[1] + bField[2] * bField[2]);
+  const double zA[3] = {bField[0] / bNorm, bField[1] / bNorm, bField[2] / bNorm};
+  double yA[3] = {zA[1] * rel[2] - zA[2] * rel[1], zA[2] * rel[0] - zA[0] * rel[2], zA[0] * rel[1] - zA[1] * rel[0]};
+  const double yN = sqrt(yA[0] * yA[0] + yA[1] * yA[1] + yA[2] * yA[2]);
+  yA[0] /= yN; yA[1] /= yN; yA[2] /= yN;
+  const double xA[3] = {yA[1] * zA[2] - yA[2] * zA[1], yA[2] * zA[0] - yA[0] * zA[2], yA[0] * zA[1] - yA[1] * zA[0]};
+  // local = R^-1 (p - sp0); R = [xA yA zA] is a rotation, its inverse is the transpose
+  const double d2[3] = {sp2[0] - sp0[0], sp2[1] - sp0[1], sp2[2] - sp0[2]};
+  const double l1[3] = {xA[0] * rel[0] + xA[1] * rel[1] + xA[2] * rel[2], yA[0] * rel[0] + yA[1] * rel[1] + yA[2] * rel[2],
+                        zA[0] * rel[0] + zA[1] * rel[1] + zA[2] * rel[2]};
+  const double l2[3] = {xA[0] * d2[0] + xA[1] * d2[1] + xA[2] * d2[2], yA[0] * d2[0] + yA[1] * d2[1] + yA[2] * d2[2],
+                        zA[0] * d2[0] + zA[1] * d2[1] + zA[2] * d2[2]};
+  // performConformalMapping, :75-86
+  const double n1 = l1[0] * l1[0] + l1[1] * l1[1], n2 = l2[0] * l2[0] + l2[1] * l2[1];
+  const double u1 = l1[0] / n1, v1 = l1[1] / n1, u2 = l2[0] / n2, v2 = l2[1] / n2;
+  const double du = u2 - u1, dv = v2 - v1;
+  const double A = dv / du;
+  const double B = v1 - A * u1;
+  const double bOverS = (v1 * u2 - v2 * u1) / sqrt(du * du + dv * dv);
+  // computeDzDs, :43-65
+  const double r1x = 2 * B * l1[0] + A, r1y = 2 * B * l1[1] - 1;
+  const double r2x = 2 * B * l2[0] + A, r2y = 2 * B * l2[1] - 1;
+  const double dPhi = atan2(r2y, r2x) - atan2(r1y, r1x);
+  const double dZ = l2[2] - l1[2];
+  const double hx = dPhi / 2;
+  // Acts::sinc, MathHelpers.hpp:256-266
+  const double eps = 1.4901161193847656e-08 * 6;  // sqrt(DBL_EPSILON) * 6
+  const double sincC = fabs(hx) < eps ? 1.0 : sin(hx) / hx;
+  const double ddx = l2[0] - l1[0], ddy = l2[1] - l1[1];
+  const double dzds = sincC * dZ / sqrt(ddx * ddx + ddy * ddy);
+  // computeLocalTangent at local0 = (0, 0): r = (A, -1), t = (-r.y, r.x, |r| dzds), :88-97
+  double t[3] = {1.0, A, sqrt(A * A + 1.0) * dzds};
+  const double tn = sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+  t[0] /= tn; t[1] /= tn; t[2] /= tn;
+  out[0] = sp0[0]; out[1] = sp0[1]; out[2] = sp0[2];
+  out[3] = t0;
+  out[4] = xA[0] * t[0] + yA[0] * t[1] + zA[0] * t[2];
+  out[5] = xA[1] * t[0] + yA[1] * t[1] + zA[1] * t[2];
+  out[6] = xA[2] * t[0] + yA[2] * t[1] + zA[2] * t[2];
+  const double qOverPt = 2 * bOverS / bNorm;  // :138-141
+  out[7] = qOverPt / sqrt(1.0 + dzds * dzds);
+}
+
 // Monotone (non-decreasing in the key) bucket of a cot(theta) key for the
 // in-block bucket sort.  Keys are expected inside [-cotThetaMax, cotThetaMax]
 // but any value is clamped.

@@ -1663,6 +1663,27 @@ __global__ void __launch_bounds__(256) k_doublets_materialised(const __grid_cons
   }
 }
 
+// Free track parameters of every seed (Acts::estimateTrackParamsFromSeed,
+// Core/src/Seeding/EstimateTrackParamsFromSeed.cpp:114-160), FP64, one thread per seed.
+__global__ void __launch_bounds__(256) k_estimate_params(const uint32_t* __restrict__ b, const uint32_t* __restrict__ m,
+                                                         const uint32_t* __restrict__ t, const float* __restrict__ x,
+                                                         const float* __restrict__ y, const float* __restrict__ z,
+                                                         double bx, double by, double bz, double* __restrict__ out,
+                                                         unsigned long long n) {
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t ib = b[i], im = m[i], it = t[i];
+    const double s0[3] = {(double)x[ib], (double)y[ib], (double)z[ib]};
+    const double s1[3] = {(double)x[im], (double)y[im], (double)z[im]};
+    const double s2[3] = {(double)x[it], (double)y[it], (double)z[it]};
+    const double bf[3] = {bx, by, bz};
+    double o[8];
+    estimate_free_params(s0, 0.0, s1, s2, bf, o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[i * 8 + k] = o[k];
+  }
+}
+
 // phi = atan2f(y, x) replay, for validation against the host libm
 __global__ void k_atan2f(const float* __restrict__ y, const float* __restrict__ x, float* __restrict__ out, unsigned long long n) {
   for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {

@@ -781,6 +781,42 @@ int b200seed_debug_doublets(b200seed_handle* h, b200seed_doublets* out) {
   return B200SEED_OK;
 }
 
+int b200seed_estimate_params(b200seed_handle* h, uint64_t nSeeds, const uint32_t* bottom, const uint32_t* middle,
+                             const uint32_t* top, uint32_t nSpacePoints, const float* x, const float* y, const float* z,
+                             const double* bField, double* freeParams) {
+  if (h == nullptr || bField == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (nSeeds == 0) return B200SEED_OK;
+  if (bottom == nullptr || middle == nullptr || top == nullptr || x == nullptr || y == nullptr || z == nullptr ||
+      freeParams == nullptr) {
+    return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL argument");
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  DevBuf idx[3], col[3], out;
+  struct Guard {
+    std::vector<DevBuf*> bufs;
+    ~Guard() { for (DevBuf* b : bufs) b->release(); }
+  } guard;
+  guard.bufs = {&idx[0], &idx[1], &idx[2], &col[0], &col[1], &col[2], &out};
+  const uint32_t* hi[3] = {bottom, middle, top};
+  const float* hc[3] = {x, y, z};
+  for (int k = 0; k < 3; ++k) {
+    CUDA_TRY(idx[k].reserve(nSeeds * 4));
+    CUDA_TRY(col[k].reserve(std::max<size_t>(4, (size_t)nSpacePoints * 4)));
+    CUDA_TRY(cudaMemcpyAsync(idx[k].ptr, hi[k], nSeeds * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(col[k].ptr, hc[k], (size_t)nSpacePoints * 4, cudaMemcpyHostToDevice, s));
+  }
+  CUDA_TRY(out.reserve(nSeeds * 64));
+  const int blocks = (int)std::min<uint64_t>((nSeeds + 255) / 256, (uint64_t)h->smCount * 8);
+  k_estimate_params<<<blocks, 256, 0, s>>>(idx[0].as<uint32_t>(), idx[1].as<uint32_t>(), idx[2].as<uint32_t>(),
+                                           col[0].as<float>(), col[1].as<float>(), col[2].as<float>(), bField[0], bField[1],
+                                           bField[2], out.as<double>(), nSeeds);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(freeParams, out.ptr, nSeeds * 64, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return B200SEED_OK;
+}
+
 int b200seed_debug_atan2f(b200seed_handle* h, uint64_t n, const float* y, const float* x, float* phi) {
   if (h == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL handle");
   if (n == 0) return B200SEED_OK;

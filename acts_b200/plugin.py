@@ -23,7 +23,7 @@ LIB_PATH = os.path.join(_HERE, "libacts_b200_seeding.so")
 EXPORTED_SYMBOLS = [
     "b200seed_config_init", "b200seed_plan_info", "b200seed_plan_tables", "b200seed_create",
     "b200seed_destroy", "b200seed_last_error", "b200seed_get_info", "b200seed_get_counters",
-    "b200seed_get_stage_times", "b200seed_set_phi_sector",
+    "b200seed_get_stage_times", "b200seed_set_phi_sector", "b200seed_estimate_params",
     "b200seed_run", "b200seed_run_with_phi", "b200seed_run_batch", "b200seed_run_batch_device",
     "b200seed_sync", "b200seed_debug_grid", "b200seed_debug_doublets", "b200seed_debug_atan2f",
 ]
@@ -57,6 +57,7 @@ def lib():
         L.b200seed_get_counters.argtypes = [vp, C.POINTER(Counters)]
         L.b200seed_get_stage_times.argtypes = [vp, vp]
         L.b200seed_set_phi_sector.argtypes = [vp, u32, u32]
+        L.b200seed_estimate_params.argtypes = [vp, u64, vp, vp, vp, u32, vp, vp, vp, vp, vp]
         L.b200seed_run.argtypes = [vp, u32] + [f32p] * 6 + [u32, f32p, f32p, C.POINTER(Seeds)]
         L.b200seed_run_with_phi.argtypes = [vp, u32] + [f32p] * 7 + [C.POINTER(Seeds)]
         L.b200seed_run_batch.argtypes = [vp, u32, vp] + [f32p] * 6 + [vp, C.POINTER(Seeds)]
@@ -144,6 +145,16 @@ class SeedingEngine:
     def set_phi_sector(self, first_phi_bin: int = 1, n_phi_bins: int = 0):
         """Seed only middles in phi bins [first, first + n) (1-based); n = 0 -> all."""
         _check(lib().b200seed_set_phi_sector(self._h, first_phi_bin, n_phi_bins))
+
+    def estimate_params(self, seeds: dict, ev: dict, b_field=(0.0, 0.0, 2 * 0.000299792458)) -> np.ndarray:
+        """Free parameters (n, 8) of the seeds: ``b200seed_estimate_params``."""
+        n = int(seeds["bottom"].size)
+        idx = [np.ascontiguousarray(seeds[k], dtype=np.uint32) for k in ("bottom", "middle", "top")]
+        cols = [np.ascontiguousarray(ev[k], dtype=np.float32) for k in ("x", "y", "z")]
+        bf = np.ascontiguousarray(b_field, dtype=np.float64)
+        out = np.zeros((n, 8), dtype=np.float64)
+        _check(lib().b200seed_estimate_params(self._h, n, *[_p(a) for a in idx], cols[0].size, *[_p(c) for c in cols], _p(bf), _p(out)))
+        return out
 
     def stage_times_ms(self) -> dict:
         ms = np.zeros(4, dtype=np.float32)

@@ -291,6 +291,18 @@ int b200seed_set_phi_sector(b200seed_handle* h, uint32_t firstPhiBin, uint32_t n
  * ms[2] seeding kernel, ms[3] ordered seed compaction. */
 int b200seed_get_stage_times(const b200seed_handle* h, float* ms);
 
+/* "Next" row f1: free track parameters of every seed, FP64 on the
+ * device.  Replaces Acts::estimateTrackParamsFromSeed(sp0, sp1, sp2, bField)
+ * (Core/src/Seeding/EstimateTrackParamsFromSeed.cpp:106-160): freeParams holds 8 doubles
+ * per seed {x, y, z of the bottom space point, time = 0, direction (3), q/p}.  bottom /
+ * middle / top index the float columns x, y, z (host memory); bField is {Bx, By, Bz} in
+ * the reference's native units (1 T = 0.000299792458).  Agreement with the reference
+ * arithmetic: 1e-9 relative (not bit-exact: the reference goes through Eigen). */
+int b200seed_estimate_params(b200seed_handle* h, uint64_t nSeeds, const uint32_t* bottom,
+                             const uint32_t* middle, const uint32_t* top, uint32_t nSpacePoints,
+                             const float* x, const float* y, const float* z, const double* bField,
+                             double* freeParams);
+
 /* ---- stage-level introspection (parity tests of the grid / doublet stages) */
 
 /* After a run: the packed, bin-ordered, r-sorted space point copy of the LAST

@@ -76,6 +76,7 @@ def lib():
         L.oracle_result_dump_doublets.argtypes = [C.c_void_p]
         L.oracle_result_dump_doublets.restype = C.c_uint64
         L.oracle_result_dump.argtypes = [C.c_void_p] * 12
+        L.oracle_estimate_params.argtypes = [C.c_uint64] + [C.c_void_p] * 8
         L.oracle_run_many.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 7 + [C.c_int, C.c_uint32, C.c_void_p]
         L.oracle_run_many.restype = C.c_int64
         _lib = L
@@ -200,6 +201,17 @@ class Oracle:
         if tot < 0:
             raise OracleError(-1, "oracle_run_many failed")
         return counts
+
+
+def estimate_params(seeds: dict, ev: dict, b_field=(0.0, 0.0, 2 * 0.000299792458)) -> np.ndarray:
+    """Reference arithmetic of Acts::estimateTrackParamsFromSeed for every seed -> (n, 8) float64."""
+    n = int(seeds["bottom"].size)
+    idx = [np.ascontiguousarray(seeds[k], dtype=np.uint32) for k in ("bottom", "middle", "top")]
+    cols = [np.ascontiguousarray(ev[k], dtype=np.float32) for k in ("x", "y", "z")]
+    bf = np.ascontiguousarray(b_field, dtype=np.float64)
+    out = np.zeros((n, 8), dtype=np.float64)
+    lib().oracle_estimate_params(n, *[_p(a) for a in idx], *[_p(c) for c in cols], _p(bf), _p(out))
+    return out
 
 
 def seed_set(res: dict) -> dict:

@@ -24,6 +24,7 @@
 #include "../include/acts_b200_seeding.h"
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cmath>
 #include <cstdint>
@@ -1485,6 +1486,86 @@ void oracle_result_dump(const oracle_event_result* r, std::uint32_t* middlePos,
   std::memcpy(v, d.v.data(), n * 4);
   std::memcpy(xNew, d.x.data(), n * 4);
   std::memcpy(yNew, d.y.data(), n * 4);
+}
+
+// ---------------------------------------------------------------------------
+// estimateTrackParamsFromSeed, Core/src/Seeding/EstimateTrackParamsFromSeed.cpp:20-160,
+// restated with explicit 3-vectors.  Like Eigen's Transform<double,3,Affine>::inverse()
+// the inverse of the frame is computed as a general 3x3 inverse (cofactors /
+// determinant), not as a transpose.
+// ---------------------------------------------------------------------------
+void oracle_estimate_params(std::uint64_t nSeeds, const std::uint32_t* bottom, const std::uint32_t* middle,
+                            const std::uint32_t* top, const float* x, const float* y, const float* z,
+                            const double* bField, double* out) {
+  using V3 = std::array<double, 3>;
+  auto sub = [](const V3& a, const V3& b) { return V3{a[0] - b[0], a[1] - b[1], a[2] - b[2]}; };
+  auto cross = [](const V3& a, const V3& b) {
+    return V3{a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+  };
+  auto norm = [](const V3& a) { return std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); };
+  auto normalized = [&](const V3& a) { const double n = norm(a); return V3{a[0] / n, a[1] / n, a[2] / n}; };
+  for (std::uint64_t i = 0; i < nSeeds; ++i) {
+    const V3 sp0{x[bottom[i]], y[bottom[i]], z[bottom[i]]};
+    const V3 sp1{x[middle[i]], y[middle[i]], z[middle[i]]};
+    const V3 sp2{x[top[i]], y[top[i]], z[top[i]]};
+    const V3 b{bField[0], bField[1], bField[2]};
+    // estimationFrameLocalToGlobal :20-41
+    const V3 relVec = sub(sp1, sp0);
+    const V3 newZ = normalized(b);
+    const V3 newY = normalized(cross(newZ, relVec));
+    const V3 newX = cross(newY, newZ);
+    // rotation with columns newX, newY, newZ: R[r][c]
+    const double R[3][3] = {{newX[0], newY[0], newZ[0]}, {newX[1], newY[1], newZ[1]}, {newX[2], newY[2], newZ[2]}};
+    // general inverse
+    const double det = R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1]) - R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0]) +
+                       R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
+    double I[3][3];
+    I[0][0] = (R[1][1] * R[2][2] - R[1][2] * R[2][1]) / det;
+    I[0][1] = (R[0][2] * R[2][1] - R[0][1] * R[2][2]) / det;
+    I[0][2] = (R[0][1] * R[1][2] - R[0][2] * R[1][1]) / det;
+    I[1][0] = (R[1][2] * R[2][0] - R[1][0] * R[2][2]) / det;
+    I[1][1] = (R[0][0] * R[2][2] - R[0][2] * R[2][0]) / det;
+    I[1][2] = (R[0][2] * R[1][0] - R[0][0] * R[1][2]) / det;
+    I[2][0] = (R[1][0] * R[2][1] - R[1][1] * R[2][0]) / det;
+    I[2][1] = (R[0][1] * R[2][0] - R[0][0] * R[2][1]) / det;
+    I[2][2] = (R[0][0] * R[1][1] - R[0][1] * R[1][0]) / det;
+    auto toLocal = [&](const V3& p) {
+      const V3 d = sub(p, sp0);
+      return V3{I[0][0] * d[0] + I[0][1] * d[1] + I[0][2] * d[2], I[1][0] * d[0] + I[1][1] * d[1] + I[1][2] * d[2],
+                I[2][0] * d[0] + I[2][1] * d[1] + I[2][2] * d[2]};
+    };
+    const V3 local1 = toLocal(sp1), local2 = toLocal(sp2);
+    // performConformalMapping :75-86
+    const double n1 = local1[0] * local1[0] + local1[1] * local1[1];
+    const double n2 = local2[0] * local2[0] + local2[1] * local2[1];
+    const double uv1[2] = {local1[0] / n1, local1[1] / n1}, uv2[2] = {local2[0] / n2, local2[1] / n2};
+    const double duv[2] = {uv2[0] - uv1[0], uv2[1] - uv1[1]};
+    const double A = duv[1] / duv[0];
+    const double B = uv1[1] - A * uv1[0];
+    const double bOverS = (uv1[1] * uv2[0] - uv2[1] * uv1[0]) / std::sqrt(duv[0] * duv[0] + duv[1] * duv[1]);
+    // computeDzDs :43-65
+    auto localPhi = [&](const V3& l) {
+      const double rx = 2 * B * l[0] - (-A), ry = 2 * B * l[1] - 1;
+      return std::atan2(ry, rx);
+    };
+    const double dPhi = localPhi(local2) - localPhi(local1);
+    const double dZ = local2[2] - local1[2];
+    static const double eps = std::sqrt(std::numeric_limits<double>::epsilon()) * 6;  // MathHelpers.hpp:256-266
+    const double hx = dPhi / 2;
+    const double sincCorrection = std::abs(hx) < eps ? 1.0 : std::sin(hx) / hx;
+    const double dd[2] = {local2[0] - local1[0], local2[1] - local1[1]};
+    const double dzds = sincCorrection * dZ / std::sqrt(dd[0] * dd[0] + dd[1] * dd[1]);
+    // computeLocalTangent at local0 = 0 :88-97
+    const double r[2] = {2 * B * 0.0 - (-A), 2 * B * 0.0 - 1};
+    const V3 tl = normalized(V3{-r[1], r[0], std::sqrt(r[0] * r[0] + r[1] * r[1]) * dzds});
+    const V3 direction{R[0][0] * tl[0] + R[0][1] * tl[1] + R[0][2] * tl[2], R[1][0] * tl[0] + R[1][1] * tl[1] + R[1][2] * tl[2],
+                       R[2][0] * tl[0] + R[2][1] * tl[1] + R[2][2] * tl[2]};
+    const double qOverPt = 2 * bOverS / norm(b);
+    double* o = out + 8 * i;
+    o[0] = sp0[0]; o[1] = sp0[1]; o[2] = sp0[2]; o[3] = 0.0;
+    o[4] = direction[0]; o[5] = direction[1]; o[6] = direction[2];
+    o[7] = qOverPt / std::sqrt(1 * 1 + dzds * dzds);  // fastHypot(1, dzds)
+  }
 }
 
 // Timed multi-event run for the CPU baseline: events are handed out

@@ -330,3 +330,23 @@ def test_phi_sector_split_concatenates_to_the_full_result(plugin, O):
     eng.set_phi_sector(1, 0)
     assert _same_bits(eng.run(ev), ref)
     eng.close()
+
+
+def test_estimated_track_parameters_match_reference_arithmetic(plugin, O):
+    """'Next' row f1: FP64 free parameters of every seed on the device vs the oracle's restatement of
+    Acts::estimateTrackParamsFromSeed.  Tolerance 1e-9 relative (north star), written here."""
+    from acts_b200 import events
+
+    eng = plugin.SeedingEngine(make_config("pu200", plugin.config_init))
+    ev = events.pileup_event(4, mu=60)
+    seeds = eng.run(ev)
+    assert seeds["quality"].size > 10000
+    got = eng.estimate_params(seeds, ev)
+    ref = O.estimate_params(seeds, ev)
+    assert got.shape == ref.shape == (seeds["quality"].size, 8)
+    scale = np.maximum(np.abs(ref), 1e-300)
+    rel = np.abs(got - ref) / scale
+    # direction components close to zero are compared on the unit-vector scale
+    rel[:, 4:7] = np.abs(got[:, 4:7] - ref[:, 4:7])
+    assert np.nanmax(rel) < 1e-9, np.nanmax(rel)
+    eng.close()

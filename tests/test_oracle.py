@@ -187,3 +187,23 @@ def test_empty_and_out_of_grid_inputs(O):
     ev = _helix_points([32.0, 72.0, 116.0], pt=2.0, phi0=0.3, z0=12.0, cot=0.5)
     ev["r"][2] = 250.0  # outside rMax = 200: dropped, no seed possible
     assert orc.run(ev)["quality"].size == 0
+
+
+def test_estimated_parameters_recover_the_generated_helix(O):
+    """f1 oracle (Acts::estimateTrackParamsFromSeed): a seed on an ideal helix gives back its
+    direction and charge-signed curvature."""
+    pt, phi0, z0, cot = 2.0, 0.3, 12.0, 0.5
+    for q in (1.0, -1.0):
+        ev = _helix_points([32.0, 72.0, 116.0], pt=pt, phi0=phi0, z0=z0, cot=cot, q=q)
+        seeds = {"bottom": np.array([0], np.uint32), "middle": np.array([1], np.uint32), "top": np.array([2], np.uint32)}
+        par = O.estimate_params(seeds, ev)[0]
+        assert np.allclose(par[:3], [ev["x"][0], ev["y"][0], ev["z"][0]])
+        assert abs(np.linalg.norm(par[4:7]) - 1.0) < 1e-12
+        p = pt * math.sqrt(1 + cot * cot)
+        assert abs(abs(par[7]) - 1.0 / p) < 2e-3 / p           # |q/p|
+        assert abs(par[6] / math.hypot(par[4], par[5]) - cot) < 2e-3   # dz/ds = cot(theta)
+        # the two charges bend in opposite directions
+        if q > 0:
+            qp_plus = par[7]
+        else:
+            assert qp_plus * par[7] < 0
