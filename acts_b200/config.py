@@ -184,6 +184,7 @@ class Counters(C.Structure):
         ("nSeeds", C.c_uint64),
         ("nTieMiddles", C.c_uint64),
         ("nKernelLaunches", C.c_uint64),
+        ("nConfirmationRounds", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -277,6 +278,32 @@ def itk_like_config(init) -> Config:
         deltaRMaxBottom=150.0,
     )
     return cfg
+
+
+def confirmation_overrides() -> dict:
+    """The seed-confirmation block of the ITk pixel configuration
+    (Python/Examples/python/itk.py:354-376,442-447)."""
+    rng = dict(rMaxSeedConf=140.0, nTopForLargeR=1, nTopForSmallR=2, seedConfMinBottomRadius=60.0,
+               seedConfMaxZOrigin=150.0, minImpactSeedConf=1.0)
+    return dict(
+        seedConfirmation=1,
+        centralSeedConfirmationRange=dict(zMinSeedConf=-500.0, zMaxSeedConf=500.0, **rng),
+        forwardSeedConfirmationRange=dict(zMinSeedConf=-3000.0, zMaxSeedConf=3000.0, **rng),
+        zOriginWeightFactor=1.0,
+        compatSeedWeight=100.0,
+        impactWeightFactor=100.0,
+        compatSeedLimit=3,
+        numSeedIncrement=100.0,
+        seedWeightIncrement=0.0,
+        maxSeedsPerSpMConf=5,
+        maxQualitySeedsPerSpMConf=5,
+    )
+
+
+def itk_conf_config(init) -> Config:
+    """itk_like_config with seedConfirmation = true (the second published
+    configuration's filter, itk.py:300-560, on the generic-detector geometry)."""
+    return itk_like_config(init).update(**confirmation_overrides())
 
 
 NAN = math.nan

@@ -313,10 +313,29 @@ void build(const b200seed_config& c, HostPlan& plan) {
   }
   d.maxSeedsPerSpMConf = c.maxSeedsPerSpMConf;
   d.useDeltaRinsteadOfTopRadius = c.useDeltaRinsteadOfTopRadius ? 1 : 0;
-  if (c.seedConfirmation) {
-    throw Fail{B200SEED_ERR_UNSUPPORTED,
-               "seedConfirmation = true couples all middle space points through "
-               "bestSeedQualityMap (BroadTripletSeedFilter.cpp:278-285); not on the device yet"};
+  // seed confirmation, GridTripletSeedingAlgorithm.cpp:163-171
+  d.seedConfirmation = c.seedConfirmation ? 1 : 0;
+  d.zOriginWeightFactor = c.zOriginWeightFactor;
+  if (c.seedConfirmation && c.maxQualitySeedsPerSpMConf > static_cast<uint32_t>(kMaxHeap)) {
+    throw Fail{B200SEED_ERR_UNSUPPORTED, "maxQualitySeedsPerSpMConf > " + std::to_string(kMaxHeap)};
+  }
+  d.maxQualitySeedsPerSpMConf = c.maxQualitySeedsPerSpMConf;
+  {
+    const b200seed_seed_confirmation_range* src[2] = {&c.centralSeedConfirmationRange, &c.forwardSeedConfirmationRange};
+    ConfRange* dst[2] = {&d.confCentral, &d.confForward};
+    for (int i = 0; i < 2; ++i) {
+      if (c.seedConfirmation && (src[i]->nTopForLargeR > 0x7fffffffull || src[i]->nTopForSmallR > 0x7fffffffull)) {
+        throw Fail{B200SEED_ERR_UNSUPPORTED, "nTopForLargeR / nTopForSmallR beyond 2^31 - 1"};
+      }
+      dst[i]->zMinSeedConf = src[i]->zMinSeedConf;
+      dst[i]->zMaxSeedConf = src[i]->zMaxSeedConf;
+      dst[i]->rMaxSeedConf = src[i]->rMaxSeedConf;
+      dst[i]->nTopForLargeR = static_cast<uint32_t>(std::min<uint64_t>(src[i]->nTopForLargeR, 0x7fffffffull));
+      dst[i]->nTopForSmallR = static_cast<uint32_t>(std::min<uint64_t>(src[i]->nTopForSmallR, 0x7fffffffull));
+      dst[i]->seedConfMinBottomRadius = src[i]->seedConfMinBottomRadius;
+      dst[i]->seedConfMaxZOrigin = src[i]->seedConfMaxZOrigin;
+      dst[i]->minImpactSeedConf = src[i]->minImpactSeedConf;
+    }
   }
 
   // middle r range, GridTripletSeedingAlgorithm.cpp:404-421
@@ -341,9 +360,10 @@ void build(const b200seed_config& c, HostPlan& plan) {
     }
   }
 
+  // BroadTripletSeedFilter.cpp:336-348: at most maxSeedsPerSpM + 1 of the collector's candidates
+  const uint32_t collectorMax = c.maxSeedsPerSpMConf + (c.seedConfirmation ? c.maxQualitySeedsPerSpMConf : 0u);
   plan.seedsPerMiddle = std::min<uint32_t>(
-      c.maxSeedsPerSpMConf,
-      c.maxSeedsPerSpM == std::numeric_limits<uint32_t>::max() ? c.maxSeedsPerSpMConf : c.maxSeedsPerSpM + 1);
+      collectorMax, c.maxSeedsPerSpM == std::numeric_limits<uint32_t>::max() ? collectorMax : c.maxSeedsPerSpM + 1);
   plan.relaxedFloat = c.relaxedFloat != 0;
 
   b200seed_info& info = plan.info;

@@ -197,6 +197,13 @@ constexpr int kMaxHeap = 16;          // maxSeedsPerSpMConf supported
 
 enum DoubletCutKind : int { kCutsNone = 0, kCutsItk = 1, kCutsVertexZ = 2 };
 
+// SeedConfirmationRangeConfig (SeedConfirmationRangeConfig.hpp) with the counts narrowed to 32 bits
+struct ConfRange {
+  float zMinSeedConf, zMaxSeedConf, rMaxSeedConf;
+  uint32_t nTopForLargeR, nTopForSmallR;
+  float seedConfMinBottomRadius, seedConfMaxZOrigin, minImpactSeedConf;
+};
+
 struct DeviceConfig {
   // grid axes (Axis.hpp, doubles like the reference)
   double phiMin, phiMax, phiWidth;
@@ -222,6 +229,11 @@ struct DeviceConfig {
   uint32_t maxSeedsPerSpM;
   uint32_t maxSeedsPerSpMConf;  // heap capacity nLow
   int32_t useDeltaRinsteadOfTopRadius;
+  // seed confirmation (BroadTripletSeedFilter.cpp:63-94,107-136,253-301)
+  int32_t seedConfirmation;
+  uint32_t maxQualitySeedsPerSpMConf;  // heap capacity nHigh
+  float zOriginWeightFactor;
+  ConfRange confCentral, confForward;
   // middle r range
   int32_t useVariableMiddleSPRange;
   float rMinMiddle, rMaxMiddle;
@@ -437,7 +449,7 @@ B2S_HD int classify_pair(const DeviceConfig& c, float rM, float varZM, float var
 // ---------------------------------------------------------------------------
 template <typename CurvAt, typename TopRAt>
 B2S_HD float filter_weight(const DeviceConfig& c, int n, int k, float impact, CurvAt curvAt,
-                           TopRAt topRAt) {
+                           TopRAt topRAt, uint32_t& nCompatOut) {
   const float invHelixDiameter = curvAt(k);
   const float lowerLimitCurv = fsub(invHelixDiameter, c.deltaInvHelixDiameter);
   const float upperLimitCurv = fadd(invHelixDiameter, c.deltaInvHelixDiameter);
@@ -470,7 +482,37 @@ B2S_HD float filter_weight(const DeviceConfig& c, int n, int k, float impact, Cu
   if ((float)nCompat > c.numSeedIncrement) {
     weight = fadd(weight, c.seedWeightIncrement);
   }
+  nCompatOut = nCompat;
   return weight;
+}
+template <typename CurvAt, typename TopRAt>
+B2S_HD float filter_weight(const DeviceConfig& c, int n, int k, float impact, CurvAt curvAt,
+                           TopRAt topRAt) {
+  uint32_t nCompat;
+  return filter_weight(c, n, k, impact, curvAt, topRAt, nCompat);
+}
+
+// Seed confirmation: the region of a space point and its minimum number of tops
+// (BroadTripletSeedFilter.cpp:72-82 for the middle, :120-134 for the bottom)
+B2S_HD const ConfRange& conf_range(const DeviceConfig& c, float z) {
+  const bool isForwardRegion = z > c.confCentral.zMaxSeedConf || z < c.confCentral.zMinSeedConf;
+  return isForwardRegion ? c.confForward : c.confCentral;
+}
+B2S_HD uint32_t conf_n_top(const ConfRange& range, float r) {
+  return r > range.rMaxSeedConf ? range.nTopForLargeR : range.nTopForSmallR;
+}
+// The confirmation part of the per-candidate filter (:253-276) that does not
+// depend on the collector or on bestSeedQualityMap.  Returns false when the
+// candidate is dropped; otherwise `weight` gets its z-origin term and
+// `deltaSeedConf` (>= 0) is set.
+B2S_HD bool conf_candidate(const DeviceConfig& c, const ConfRange& rangeB, float rB, float zOrigin,
+                           float impact, uint32_t nCompat, float& weight, int& deltaSeedConf) {
+  deltaSeedConf = (int)(nCompat + 1u - conf_n_top(rangeB, rB));
+  if (deltaSeedConf < 0) return false;
+  const bool seedRangeCuts = rB < rangeB.seedConfMinBottomRadius || fabs_(zOrigin) > rangeB.seedConfMaxZOrigin;
+  if (seedRangeCuts && deltaSeedConf == 0 && impact > rangeB.minImpactSeedConf) return false;
+  weight = fadd(weight, fadd(-fmul(fabs_(zOrigin), c.zOriginWeightFactor), c.compatSeedWeight));
+  return true;
 }
 
 // ---------------------------------------------------------------------------

@@ -28,7 +28,6 @@
 namespace b200seed {
 
 constexpr uint32_t kInvalidBin = 0xFFFFFFFFu;
-constexpr int kSeedThreads = 512;
 constexpr int kSortThreads = 256;
 constexpr int kScanThreads = 1024;
 constexpr int kTile = 2048;  // elements per block in the tiled scan
@@ -48,7 +47,8 @@ enum CounterSlot : int {
 enum StatusBits : int {
   kStatusOverflowDoublets = 1,
   kStatusOverflowPool = 2,
-  kStatusBinTooLarge = 4
+  kStatusBinTooLarge = 4,
+  kStatusOverflowRecords = 8
 };
 
 struct GridParams {
@@ -109,7 +109,20 @@ struct SeedParams {
   int exactTies;  // replay libstdc++ std::sort inside groups of equal cotTheta
   unsigned long long* counters;
   int* status;
+  // seedConfirmation only: the weighted candidates of every middle, in the reference's push order
+  uint4* rec;            // {bottom pos, top pos, weight bits, meta}
+  float* recZ;           // zOrigin
+  uint32_t *recBegin, *recCount;  // per work item
+  uint32_t* recCounter;  // bump allocator (keeps counting past the capacity: tells the host what to reserve)
+  uint32_t recCapacity;
 };
+
+// meta word of a candidate record
+constexpr uint32_t kRecGroupMask = 0xFFFFu;      // sorted rank of the bottom = group id
+constexpr int kRecGroupSizeShift = 16;           // min(#candidates of the group, 3)
+constexpr uint32_t kRecNeedsTwoTops = 1u << 18;  // bottom radius <= rMaxSeedConf of the middle's region
+constexpr uint32_t kRecQuality = 1u << 19;       // deltaSeedConf > 0
+constexpr uint32_t kRecKeep = 1u << 31;          // in-kernel only
 
 struct CompactParams {
   const uint32_t* nWorkPtr;
@@ -1026,7 +1039,7 @@ constexpr int seed_blocks_per_sm(size_t layoutBytes) {
          : (layoutBytes + 1024 <= 232448 / 3 ? 3 : (layoutBytes + 1024 <= 232448 / 2 ? 2 : 1));
 }
 
-template <int CAPB, int CAPT, int CAPPOOL, int NBK, int THREADS>
+template <int CAPB, int CAPT, int CAPPOOL, int NBK, int THREADS, bool kConf>
 __global__ void __launch_bounds__(THREADS, seed_blocks_per_sm(sizeof(SeedLayout<CAPB, CAPT, CAPPOOL, NBK>)))
 k_seed_middles(const __grid_constant__ SeedParams p) {
   using Layout = SeedLayout<CAPB, CAPT, CAPPOOL, NBK>;
@@ -1116,10 +1129,12 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
     // ---- phase 1: doublets of both sides (TripletSeeder.cpp:52-82) -------
     find_doublets_both(p, sh, nBot, nTop, surv, kSurvCap, L.u.a.uCotB, L.u.a.uSeqB, CAPB, L.u.a.uCotT, L.u.a.uSeqT, CAPT);
     const uint32_t nT = sh.nT, nB = sh.nB;
-    if (nT == 0 || nB == 0 || nT > (uint32_t)CAPT || nB > (uint32_t)CAPB) {
+    bool insufficient = false;  // BroadTripletSeedFilter::sufficientTopDoublets (.cpp:63-94, TripletSeeder.cpp:67-69)
+    if constexpr (kConf) insufficient = nT < conf_n_top(conf_range(cfg, sh.mid.z), sh.mid.r);
+    if (insufficient || nT == 0 || nB == 0 || nT > (uint32_t)CAPT || nB > (uint32_t)CAPB) {
       if (tid == 0) {
         p.slotCount[w] = 0;
-        if (nT != 0 && nB != 0) {  // does not fit this launch's scratch: hand over to the next tier
+        if (!insufficient && nT != 0 && nB != 0) {  // does not fit this launch's scratch: hand over to the next tier
           if (p.overflowList != nullptr) {
             p.overflowList[atomicAdd(p.overflowCount, 1u)] = w;
             sh.cnt[kCntMiddles] -= 1;  // counted again by the launch that completes it
@@ -1345,6 +1360,73 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
     }
     __syncthreads();
 
+    if constexpr (kConf) {
+      // ---- seedConfirmation: weights and the map-independent cuts of every candidate
+      // (BroadTripletSeedFilter.cpp:253-276), then the survivors go to global memory in
+      // the reference's push order; k_conf_replay applies the collector and
+      // bestSeedQualityMap logic on them.
+      const float rMaxSeedConfMid = conf_range(cfg, mid.z).rMaxSeedConf;  // state().rMaxSeedConf, :84
+      uint32_t myKept = 0;
+      for (uint32_t i = tid; i < nValid; i += blockDim.x) {
+        const Cand c = L.u.b.pool2[i];
+        const uint32_t j = c.tOwner >> 16;
+        const uint32_t s = j == 0 ? 0u : L.u.b.cnt[j - 1], e = L.u.b.cnt[j];
+        const Cand* grp = L.u.b.pool2 + s;
+        uint32_t nCompat;
+        float wgt = filter_weight(
+            cfg, (int)(e - s), (int)(i - s), c.impactOrWeight, [&](int q) { return grp[q].curv; },
+            [&](int q) { return grp[q].topR; }, nCompat);
+        const float2 bzr = ldg2(p.pZR + seq_to_pos(L.bSeq[j], sh.winBp, sh.winBs, nBot));
+        const float zOrigin = fsub(mid.z, fmul(mid.r, L.bCot[j]));  // :119
+        int deltaSeedConf;
+        const bool keepIt = conf_candidate(cfg, conf_range(cfg, bzr.x), bzr.y, zOrigin, c.impactOrWeight, nCompat, wgt, deltaSeedConf);
+        uint32_t meta = j | ((e - s < 3u ? e - s : 3u) << kRecGroupSizeShift);
+        if (!(bzr.y > rMaxSeedConfMid)) meta |= kRecNeedsTwoTops;  // :107-110
+        if (deltaSeedConf > 0) meta |= kRecQuality;
+        if (keepIt) { meta |= kRecKeep; ++myKept; }
+        L.u.b.pool2[i].impactOrWeight = wgt;  // nobody reads another candidate's impact
+        L.u.b.pool[i] = meta;                 // the emission records are dead after phase 3d
+      }
+      uint32_t nKept;
+      block_scan_exclusive(myKept, sh.scratch, nKept, OpSum());
+      if (tid == 0) {
+        const uint32_t base = nKept != 0 ? atomicAdd(p.recCounter, nKept) : 0u;
+        sh.runCarry = base;
+        const bool fits = (unsigned long long)base + nKept <= (unsigned long long)p.recCapacity;
+        if (!fits) atomicOr(p.status, kStatusOverflowRecords);
+        p.recBegin[w] = base;
+        p.recCount[w] = fits ? nKept : 0u;
+        p.slotCount[w] = 0;
+        sh.cnt[kCntBottomDoublets] += nB;
+        sh.cnt[kCntTopDoublets] += nT;
+        sh.cnt[kCntCandidates] += nValid;
+        sh.cnt[kCntTieMiddles] += sh.tie;
+      }
+      __syncthreads();
+      const uint32_t recBase = sh.runCarry;
+      if ((unsigned long long)recBase + nKept <= (unsigned long long)p.recCapacity) {
+        uint32_t carry = 0;
+        for (uint32_t base = 0; base < nValid; base += blockDim.x) {
+          const uint32_t i = base + tid;
+          const uint32_t meta = i < nValid ? L.u.b.pool[i] : 0u;
+          const bool keepIt = (meta & kRecKeep) != 0u;
+          uint32_t total;
+          const uint32_t rank = carry + block_scan_exclusive(keepIt ? 1u : 0u, sh.scratch, total, OpSum());
+          carry += total;
+          if (keepIt) {
+            const Cand c = L.u.b.pool2[i];
+            const uint32_t j = meta & kRecGroupMask;
+            const size_t o = (size_t)recBase + rank;
+            p.rec[o] = make_uint4(seq_to_pos(L.bSeq[j], sh.winBp, sh.winBs, nBot), L.sPos[c.tOwner & 0xFFFFu],
+                                  __float_as_uint(c.impactOrWeight), meta & ~kRecKeep);
+            p.recZ[o] = fsub(mid.z, fmul(mid.r, L.bCot[j]));
+          }
+        }
+      }
+      uint32_t t = myTests;
+      for (int d = 16; d > 0; d >>= 1) t += __shfl_down_sync(0xffffffffu, t, d);
+      if (lane == 0) atomicAdd(&sh.cnt[kCntTripletTests], (unsigned long long)t);
+    } else {
     // ---- phase 3e: one thread per candidate: weight -----------------------
     for (uint32_t i = tid; i < nValid; i += blockDim.x) {
       const Cand c = L.u.b.pool2[i];
@@ -1479,6 +1561,7 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
       sh.cnt[kCntSeeds] += nOut;
       sh.cnt[kCntTieMiddles] += sh.tie;
     }
+    }  // !kConf
   }
   __syncthreads();
   if (tid < (uint32_t)kCntSlots && tid != (uint32_t)kCntInGrid && sh.cnt[tid] != 0ull) {
@@ -1555,6 +1638,247 @@ __global__ void k_event_offsets(const __grid_constant__ CompactParams p) {
     // seedStart[nWork] is only written when nWork > 0
     p.seedOffsets[e] = nWork == 0 ? 0ull : (unsigned long long)p.seedStart[w];
   }
+}
+
+// ---------------------------------------------------------------------------
+// seedConfirmation = true.  The reference threads one mutable map through the
+// whole event: bestSeedQualityMap[sp] = best quality of the seeds emitted so far
+// that contain sp (BroadTripletSeedFilter.cpp:33-50,278-285,364-376), read by
+// every later middle.  The device resolves that order dependence by fixed-point
+// iteration over rounds: round r replays the collector logic of every middle
+// (one warp each) against Q_r(sp, w) = max quality over the seeds that round
+// r - 1 emitted for middles BEFORE w (round 0: empty map).  The seeds of the
+// first middle in order are final after round 0, and by induction everything is
+// final once a round reproduces its predecessor; the fixed point is exactly the
+// sequential result.  Seeds live in two slot sets (previous / current); the
+// per-space-point lists of the previous round's seeds are linked lists built by
+// k_conf_link (node = 3 * slot + role).
+// ---------------------------------------------------------------------------
+struct ConfParams {
+  DeviceConfig cfg;
+  const uint32_t* nWorkPtr;
+  const uint32_t* workPos;
+  const uint4* rec;
+  const float* recZ;
+  const uint32_t *recBegin, *recCount;
+  const uint32_t *prevB, *prevT;  // the previous round's seeds
+  const float* prevQ;
+  const uint32_t* prevCount;
+  uint32_t *curB, *curM, *curT;   // this round's seeds
+  float *curQ, *curZ;
+  uint32_t* curCount;
+  int* head;        // [nTotal] first node of a space point, -1: none
+  int* next;        // [3 * nWork * seedsPerMiddle]
+  uint32_t seedsPerMiddle;
+  int round;
+  uint32_t* changed;  // [rounds] number of middles whose seeds differ from the previous round
+};
+
+__device__ __forceinline__ bool conf_converged(const ConfParams& p) {
+  return p.round >= 2 && p.changed[p.round - 1] == 0u;
+}
+
+__global__ void __launch_bounds__(256) k_conf_link(const __grid_constant__ ConfParams p) {
+  if (conf_converged(p)) return;
+  const uint32_t nSlots = *p.nWorkPtr * p.seedsPerMiddle;
+  for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < nSlots; slot += gridDim.x * blockDim.x) {
+    const uint32_t w = slot / p.seedsPerMiddle, i = slot - w * p.seedsPerMiddle;
+    if (i >= p.prevCount[w]) continue;
+    const uint32_t sp[3] = {p.prevB[slot], p.workPos[w], p.prevT[slot]};
+#pragma unroll
+    for (int role = 0; role < 3; ++role) {
+      const int node = (int)(slot * 3u + (uint32_t)role);
+      p.next[node] = atomicExch(p.head + sp[role], node);
+    }
+  }
+}
+
+// getBestSeedQuality (.cpp:24-31) as of just before work item w
+__device__ __forceinline__ float conf_best(const ConfParams& p, uint32_t sp, uint32_t w) {
+  float best = -3.402823466e+38f;  // numeric_limits<float>::lowest()
+  for (int node = p.head[sp]; node >= 0; node = p.next[node]) {
+    const uint32_t slot = (uint32_t)node / 3u;
+    if (slot / p.seedsPerMiddle < w) {
+      const float q = p.prevQ[slot];
+      best = q > best ? q : best;  // std::max(quality, it->second), .cpp:41
+    }
+  }
+  return best;
+}
+
+struct ConfSeed {
+  uint32_t b, t;
+  float weight, zOrigin;
+  uint32_t isQuality;
+};
+
+// CandidatesForMiddleSp::push (detail/CandidatesForMiddleSp.cpp:44-78), one of the two heaps
+__device__ __forceinline__ void conf_push(WeightIndex* heap, int& size, int nMax, ConfSeed* storage, int& nStored,
+                                          const ConfSeed& sd) {
+  if (nMax == 0) return;
+  if (size < nMax) {
+    storage[nStored] = sd;
+    heap[size].weight = sd.weight;
+    heap[size].index = (uint32_t)nStored;
+    ++nStored;
+    ++size;
+    std_push_heap(heap, size, heap_comp);
+    return;
+  }
+  const WeightIndex smallest = heap[0];
+  if (sd.weight <= smallest.weight) return;
+  storage[smallest.index] = sd;
+  std_pop_heap(heap, size, heap_comp);
+  heap[size - 1].weight = sd.weight;
+  heap[size - 1].index = smallest.index;
+  std_push_heap(heap, size, heap_comp);
+}
+
+constexpr int kConfWarps = 4;
+
+__global__ void __launch_bounds__(kConfWarps * 32) k_conf_replay(const __grid_constant__ ConfParams p) {
+  if (conf_converged(p)) return;
+  __shared__ WeightIndex heapHigh[kConfWarps][kMaxHeap], heapLow[kConfWarps][kMaxHeap];
+  __shared__ ConfSeed storageAll[kConfWarps][2 * kMaxHeap];
+  const DeviceConfig& cfg = p.cfg;
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  WeightIndex* hHigh = heapHigh[wib];
+  WeightIndex* hLow = heapLow[wib];
+  ConfSeed* storage = storageAll[wib];
+  const int maxHigh = (int)cfg.maxQualitySeedsPerSpMConf, maxLow = (int)cfg.maxSeedsPerSpMConf;
+  const uint32_t nWork = *p.nWorkPtr;
+  const uint32_t warpsPerGrid = gridDim.x * kConfWarps;
+  const float kLowest = -3.402823466e+38f;
+  uint32_t myChanged = 0;
+  for (uint32_t w = blockIdx.x * kConfWarps + wib; w < nWork; w += warpsPerGrid) {
+    const uint32_t n = p.recCount[w];
+    const uint32_t K = p.seedsPerMiddle;
+    const size_t slot0 = (size_t)w * K;
+    uint32_t nOut = 0;
+    if (n != 0) {
+      const uint32_t recBase = p.recBegin[w];
+      const uint32_t m = p.workPos[w];
+      const float bestM = conf_best(p, m, w);
+      int nHigh = 0, nLow = 0, nStored = 0;  // maintained by lane 0, broadcast where the warp needs them
+      // state of the (middle, bottom) group being processed
+      uint32_t curGroup = 0xFFFFFFFFu;
+      bool groupSkip = false;
+      float bestB = kLowest;
+      bool lowHas = false;  // maxWeightSeed / weightMax / maxWeightTopSp, .cpp:138-140
+      float lowW = kLowest, lowZ = 0.f;
+      uint32_t lowT = 0, lowB = 0;
+      auto closeGroup = [&]() {  // .cpp:305-321: the best lower-quality seed, only without quality seeds
+        if (lane == 0 && lowHas && nHigh == 0) {
+          ConfSeed sd{lowB, lowT, lowW, lowZ, 0u};
+          conf_push(hLow, nLow, maxLow, storage, nStored, sd);
+        }
+        lowHas = false;
+        lowW = kLowest;
+      };
+      for (uint32_t c0 = 0; c0 < n; c0 += 32) {
+        const uint32_t i = c0 + lane;
+        const bool valid = i < n;
+        uint4 r = make_uint4(0, 0, 0, 0);
+        float z = 0.f;
+        if (valid) { r = p.rec[recBase + i]; z = p.recZ[recBase + i]; }
+        const uint32_t grp = valid ? (r.w & kRecGroupMask) : 0xFFFFFFFFu;
+        const float wgt = __uint_as_float(r.z);
+        const float bestT = valid ? conf_best(p, r.y, w) : kLowest;
+        uint32_t todo = __ballot_sync(0xffffffffu, valid);
+        while (todo != 0u) {
+          const int first = __ffs(todo) - 1;
+          const uint32_t g = __shfl_sync(0xffffffffu, grp, first);
+          const uint32_t piece = __ballot_sync(0xffffffffu, valid && grp == g) & todo;  // groups are contiguous
+          todo &= ~piece;
+          if (g != curGroup) {
+            closeGroup();
+            curGroup = g;
+            const uint32_t meta = __shfl_sync(0xffffffffu, r.w, first);
+            const uint32_t bPos = __shfl_sync(0xffffffffu, r.x, first);
+            const int nHighNow = __shfl_sync(0xffffffffu, nHigh, 0);
+            // minCompatibleTopSPs, .cpp:106-118
+            const uint32_t minTops = ((meta & kRecNeedsTwoTops) ? 2u : 1u) + (nHighNow > 0 ? 1u : 0u);
+            groupSkip = ((meta >> kRecGroupSizeShift) & 3u) < minTops;
+            bestB = groupSkip ? kLowest : conf_best(p, bPos, w);
+          }
+          if (groupSkip) continue;
+          const bool mine = ((piece >> lane) & 1u) != 0u;
+          // .cpp:278-285
+          const bool pass = mine && !(wgt < bestB && wgt < bestM && wgt < bestT);
+          const bool quality = (r.w & kRecQuality) != 0u;
+          uint32_t hi = __ballot_sync(0xffffffffu, pass && quality);
+          const uint32_t lo = __ballot_sync(0xffffffffu, pass && !quality);
+          if (lo != 0u) {
+            // first maximum of the piece; an earlier piece of the group wins ties (weight > weightMax, .cpp:296)
+            float best = (pass && !quality) ? wgt : kLowest;
+            uint32_t bestLane = (pass && !quality) ? lane : 32u;
+            for (int d = 16; d > 0; d >>= 1) {
+              const float ow = __shfl_xor_sync(0xffffffffu, best, d);
+              const uint32_t ol = __shfl_xor_sync(0xffffffffu, bestLane, d);
+              if (ol != 32u && (bestLane == 32u || ow > best || (ow == best && ol < bestLane))) { best = ow; bestLane = ol; }
+            }
+            const uint32_t bt = __shfl_sync(0xffffffffu, r.y, bestLane & 31u);
+            const uint32_t bb = __shfl_sync(0xffffffffu, r.x, bestLane & 31u);
+            const float bz = __shfl_sync(0xffffffffu, z, bestLane & 31u);
+            if (!lowHas || best > lowW) {
+              if (best > lowW) { lowHas = true; lowW = best; lowT = bt; lowB = bb; lowZ = bz; }
+            }
+          }
+          while (hi != 0u) {  // quality seeds go to the collector in order, .cpp:287-295
+            const int src = __ffs(hi) - 1;
+            hi &= hi - 1u;
+            ConfSeed sd;
+            sd.b = __shfl_sync(0xffffffffu, r.x, src);
+            sd.t = __shfl_sync(0xffffffffu, r.y, src);
+            sd.weight = __shfl_sync(0xffffffffu, wgt, src);
+            sd.zOrigin = __shfl_sync(0xffffffffu, z, src);
+            sd.isQuality = 1u;
+            if (lane == 0) conf_push(hHigh, nHigh, maxHigh, storage, nStored, sd);
+          }
+        }
+      }
+      closeGroup();
+      __syncwarp();
+      // ---- filterTripletsMiddleFixed, .cpp:324-393 (lane 0)
+      if (lane == 0) {
+        std_sort_heap(hHigh, nHigh, heap_comp);
+        std_sort_heap(hLow, nLow, heap_comp);
+        const uint32_t total = (uint32_t)(nHigh + nLow);
+        uint32_t maxSeeds = total;
+        if (maxSeeds > cfg.maxSeedsPerSpM) maxSeeds = cfg.maxSeedsPerSpM + 1;
+        for (uint32_t k = 0; k < total && nOut < maxSeeds; ++k) {
+          const ConfSeed sd = storage[k < (uint32_t)nHigh ? hHigh[k].index : hLow[k - (uint32_t)nHigh].index];
+          if (nHigh > 0 && sd.isQuality == 0u) continue;
+          // the map as of now: the previous middles' seeds plus this middle's own earlier ones (.cpp:375)
+          float qB = conf_best(p, sd.b, w), qM = bestM, qT = conf_best(p, sd.t, w);
+          for (uint32_t e = 0; e < nOut; ++e) {
+            const float qe = p.curQ[slot0 + e];
+            const uint32_t eb = p.curB[slot0 + e], et = p.curT[slot0 + e];
+            qM = qe > qM ? qe : qM;
+            if (eb == sd.b || et == sd.b) qB = qe > qB ? qe : qB;
+            if (eb == sd.t || et == sd.t) qT = qe > qT ? qe : qT;
+          }
+          if (sd.weight < qB && sd.weight < qM && sd.weight < qT) continue;
+          p.curB[slot0 + nOut] = sd.b;
+          p.curM[slot0 + nOut] = m;
+          p.curT[slot0 + nOut] = sd.t;
+          p.curQ[slot0 + nOut] = sd.weight;
+          p.curZ[slot0 + nOut] = sd.zOrigin;
+          ++nOut;
+        }
+      }
+    }
+    if (lane == 0) {
+      p.curCount[w] = nOut;
+      bool same = p.round > 0 && p.prevCount[w] == nOut;
+      for (uint32_t e = 0; same && e < nOut; ++e) {
+        same = p.prevB[slot0 + e] == p.curB[slot0 + e] && p.prevT[slot0 + e] == p.curT[slot0 + e] &&
+               __float_as_uint(p.prevQ[slot0 + e]) == __float_as_uint(p.curQ[slot0 + e]);
+      }
+      if (!same) ++myChanged;
+    }
+  }
+  if (lane == 0 && myChanged != 0u) atomicAdd(p.changed + p.round, myChanged);
 }
 
 // ---------------------------------------------------------------------------

@@ -58,6 +58,12 @@ struct DevBuf {
   T* as() const { return static_cast<T*>(ptr); }
 };
 
+// confState words: [0] record counter, [kConfChangedBase + r] middles changed in round r
+constexpr int kConfChangedBase = 8;
+constexpr int kConfMaxRounds = 1016;
+constexpr int kConfStateWords = kConfChangedBase + kConfMaxRounds;
+constexpr int kConfRoundsPerBatch = 12;  // rounds enqueued before the host looks at the convergence flags
+
 uint32_t env_u32(const char* name, uint32_t def) {
   const char* v = std::getenv(name);
   if (v == nullptr || *v == 0) return def;
@@ -89,6 +95,24 @@ struct b200seed_handle {
   DevBuf slotB, slotM, slotT, slotQ, slotZ, slotCount, seedStart, tileSums, tilePrefix;
   DevBuf outB, outM, outT, outQ, outZ, seedOffsets;  // device outputs of the host API
   DevBuf counters, status, zWin;
+  // seedConfirmation: candidate records, second slot set, per-space-point seed lists, {record counter, changed[round]}
+  DevBuf rec, recZ, recBegin, recCount, slot2B, slot2M, slot2T, slot2Q, slot2Z, slot2Count, confHead, confNext, confState;
+  uint32_t* hConfState = nullptr;  // pinned mirror of confState
+  size_t recCapacity = 0;
+  int confRoundsLaunched = 0;
+  ConfParams confParams{};
+  CompactParams compactParams{};
+  struct EnqueueArgs {
+    uint32_t nEvents = 0, nTotal = 0;
+    const uint32_t* dOffsets = nullptr;
+    const float *x = nullptr, *y = nullptr, *z = nullptr, *r = nullptr, *varZ = nullptr, *varR = nullptr, *dPhi = nullptr;
+    int nZWin = 0;
+    uint32_t *outB = nullptr, *outM = nullptr, *outT = nullptr;
+    float *outQ = nullptr, *outZ = nullptr;
+    unsigned long long outCapacity = 0;
+    unsigned long long* dSeedOffsets = nullptr;
+    cudaStream_t stream = nullptr;
+  } last;
   // pinned host mirrors
   unsigned long long* hCounters = nullptr;  // [kCntSlots]
   int* hStatus = nullptr;
@@ -99,6 +123,7 @@ struct b200seed_handle {
   unsigned long long lastCapacity = 0;
   const unsigned long long* lastSeedOffsets = nullptr;
   b200seed_counters lastCounters{};
+  uint32_t lastConfRounds = 0;
   bool pending = false;
   uint64_t launches = 0;
   // stage boundaries of the last call: start | grid | work list | seeding | compaction
@@ -149,15 +174,94 @@ int ensure_workspace(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal) {
   CUDA_TRY(h->counters.reserve(kCntSlots * 8));
   CUDA_TRY(h->status.reserve(16));
   CUDA_TRY(h->zWin.reserve(2 * kMaxZWindows * 4));
+  if (h->plan.dev.seedConfirmation) {
+    if (h->recCapacity < 32 * nT) h->recCapacity = 32 * nT;  // grown on demand by finish()
+    h->recCapacity = std::min<size_t>(h->recCapacity, 0xFFFFFFF0u);
+    CUDA_TRY(h->rec.reserve(h->recCapacity * 16));
+    CUDA_TRY(h->recZ.reserve(h->recCapacity * 4));
+    CUDA_TRY(h->recBegin.reserve(nT * 4));
+    CUDA_TRY(h->recCount.reserve(nT * 4));
+    CUDA_TRY(h->slot2B.reserve(nT * K * 4));
+    CUDA_TRY(h->slot2M.reserve(nT * K * 4));
+    CUDA_TRY(h->slot2T.reserve(nT * K * 4));
+    CUDA_TRY(h->slot2Q.reserve(nT * K * 4));
+    CUDA_TRY(h->slot2Z.reserve(nT * K * 4));
+    CUDA_TRY(h->slot2Count.reserve(nT * 4));
+    CUDA_TRY(h->confHead.reserve(nT * 4));
+    CUDA_TRY(h->confNext.reserve(nT * K * 3 * 4));
+    CUDA_TRY(h->confState.reserve(kConfStateWords * 4));
+  }
   return B200SEED_OK;
 }
 
-// Enqueue the whole pipeline for a batch whose inputs already live on the device.
-int enqueue(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal, const uint32_t* dOffsets,
-            const float* x, const float* y, const float* z, const float* r, const float* varZ,
-            const float* varR, const float* dPhi, int nZWin, uint32_t* outB, uint32_t* outM,
-            uint32_t* outT, float* outQ, float* outZ, unsigned long long outCapacity,
-            unsigned long long* dSeedOffsets, cudaStream_t s) {
+template <typename TR, bool kConf>
+constexpr auto seed_kernel() {
+  return k_seed_middles<TR::B, TR::T, TR::P, TR::K, TR::N, kConf>;
+}
+
+// Rounds [first, first + count) of the seedConfirmation fixed point (seeding_kernels.cuh, k_conf_replay).
+// Round r reads the seeds of slot set (r + 1) & 1 and writes set r & 1.
+int enqueue_conf_rounds(b200seed_handle* h, int first, int count, cudaStream_t s) {
+  const uint32_t nTotal = std::max<uint32_t>(h->last.nTotal, 1);
+  const uint32_t K = std::max<uint32_t>(h->plan.seedsPerMiddle, 1);
+  uint32_t* setB[2] = {h->slotB.as<uint32_t>(), h->slot2B.as<uint32_t>()};
+  uint32_t* setM[2] = {h->slotM.as<uint32_t>(), h->slot2M.as<uint32_t>()};
+  uint32_t* setT[2] = {h->slotT.as<uint32_t>(), h->slot2T.as<uint32_t>()};
+  float* setQ[2] = {h->slotQ.as<float>(), h->slot2Q.as<float>()};
+  float* setZ[2] = {h->slotZ.as<float>(), h->slot2Z.as<float>()};
+  uint32_t* setCount[2] = {h->slotCount.as<uint32_t>(), h->slot2Count.as<uint32_t>()};
+  ConfParams cp = h->confParams;
+  const int linkBlocks = std::max(1, std::min<int>((int)(((size_t)nTotal * K + 255) / 256), h->smCount * 8));
+  const int replayBlocks = h->smCount * 16;
+  for (int r = first; r < first + count; ++r) {
+    const int cur = r & 1, prev = cur ^ 1;
+    cp.round = r;
+    cp.prevB = setB[prev]; cp.prevT = setT[prev]; cp.prevQ = setQ[prev]; cp.prevCount = setCount[prev];
+    cp.curB = setB[cur]; cp.curM = setM[cur]; cp.curT = setT[cur]; cp.curQ = setQ[cur]; cp.curZ = setZ[cur];
+    cp.curCount = setCount[cur];
+    CUDA_TRY(cudaMemsetAsync(h->confHead.ptr, 0xFF, (size_t)nTotal * 4, s));
+    if (r > 0) {
+      k_conf_link<<<linkBlocks, 256, 0, s>>>(cp);
+      ++h->launches;
+    }
+    k_conf_replay<<<replayBlocks, kConfWarps * 32, 0, s>>>(cp);
+    ++h->launches;
+  }
+  h->confRoundsLaunched = first + count;
+  return B200SEED_OK;
+}
+
+// Ordered seed compaction + the copies of everything the host reads after the sync.
+int enqueue_tail(b200seed_handle* h, cudaStream_t s) {
+  const CompactParams& cp = h->compactParams;
+  const uint32_t nEvents = h->last.nEvents;
+  const uint32_t nBinsAll = nEvents * (uint32_t)h->plan.dev.nGlobalBins;
+  const uint32_t nTiles = std::max<uint32_t>(1, (h->last.nTotal + kTile - 1) / kTile);
+  k_tile_sums<<<nTiles, 256, 0, s>>>(cp);
+  k_scan<<<1, kScanThreads, 0, s>>>(cp.tileSums, cp.tilePrefix, nTiles);
+  k_compact_seeds<<<nTiles, 256, 0, s>>>(cp);
+  k_event_offsets<<<1, 256, 0, s>>>(cp);
+  h->launches += 4;
+  CUDA_TRY(cudaEventRecord(h->ev[4], s));
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(h->hCounters, h->counters.ptr, kCntSlots * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h->hStatus, h->status.ptr, 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h->hSeedTotal, h->last.dSeedOffsets + nEvents, 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h->hCounters + kCntSlots, h->binStart.as<uint32_t>() + nBinsAll, 4, cudaMemcpyDeviceToHost, s));
+  if (h->plan.dev.seedConfirmation) {
+    CUDA_TRY(cudaMemcpyAsync(h->hConfState, h->confState.ptr, kConfStateWords * 4, cudaMemcpyDeviceToHost, s));
+  }
+  return B200SEED_OK;
+}
+
+// Enqueue the whole pipeline for a batch whose inputs already live on the device (h->last holds the arguments).
+int enqueue(b200seed_handle* h) {
+  const b200seed_handle::EnqueueArgs& a = h->last;
+  const uint32_t nEvents = a.nEvents, nTotal = a.nTotal;
+  const uint32_t* dOffsets = a.dOffsets;
+  const float *x = a.x, *y = a.y, *z = a.z, *r = a.r, *varZ = a.varZ, *varR = a.varR, *dPhi = a.dPhi;
+  const int nZWin = a.nZWin;
+  cudaStream_t s = a.stream;
   int rc = ensure_workspace(h, nEvents, nTotal);
   if (rc != B200SEED_OK) return rc;
   const HostPlan& plan = h->plan;
@@ -250,6 +354,17 @@ int enqueue(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal, const uint32_
   sp.exactTies = h->exactTies;
   sp.counters = gp.counters;
   sp.status = gp.status;
+  const bool conf = plan.dev.seedConfirmation != 0;
+  if (conf) {
+    sp.rec = h->rec.as<uint4>();
+    sp.recZ = h->recZ.as<float>();
+    sp.recBegin = h->recBegin.as<uint32_t>();
+    sp.recCount = h->recCount.as<uint32_t>();
+    sp.recCounter = h->confState.as<uint32_t>();
+    sp.recCapacity = (uint32_t)h->recCapacity;
+    CUDA_TRY(cudaMemsetAsync(h->recCount.ptr, 0, (size_t)std::max<uint32_t>(nTotal, 1) * 4, s));
+    CUDA_TRY(cudaMemsetAsync(h->confState.ptr, 0, kConfStateWords * 4, s));
+  }
   // Capacity tiers: tier 0 takes every middle with the smallest scratch (most
   // blocks per SM); a middle whose lists do not fit is re-queued to the next
   // tier.  workCounter words: [2k] ticket of tier k, [2k+1] overflow count k -> k+1.
@@ -266,15 +381,37 @@ int enqueue(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal, const uint32_
       sp.overflowCount = last ? nullptr : wc + 2 * t + 1;
       kernel<<<h->smCount * h->seedBlocksPerSM[t], threads, h->seedSmemBytes[t], s>>>(sp);
     };
-    launchTier(0, k_seed_middles<Tier0::B, Tier0::T, Tier0::P, Tier0::K, Tier0::N>, Tier0::N);
-    launchTier(1, k_seed_middles<Tier1::B, Tier1::T, Tier1::P, Tier1::K, Tier1::N>, Tier1::N);
-    launchTier(2, k_seed_middles<Tier2::B, Tier2::T, Tier2::P, Tier2::K, Tier2::N>, Tier2::N);
+    if (conf) {
+      launchTier(0, seed_kernel<Tier0, true>(), Tier0::N);
+      launchTier(1, seed_kernel<Tier1, true>(), Tier1::N);
+      launchTier(2, seed_kernel<Tier2, true>(), Tier2::N);
+    } else {
+      launchTier(0, seed_kernel<Tier0, false>(), Tier0::N);
+      launchTier(1, seed_kernel<Tier1, false>(), Tier1::N);
+      launchTier(2, seed_kernel<Tier2, false>(), Tier2::N);
+    }
   }
   sp.nWorkPtr = wp.workStart + nNavAll;
   launches += kNumTiers;
+  h->launches = launches;
+  if (conf) {
+    ConfParams& cf = h->confParams;
+    cf = ConfParams{};
+    cf.cfg = plan.dev;
+    cf.nWorkPtr = sp.nWorkPtr;
+    cf.workPos = sp.workPos;
+    cf.rec = sp.rec; cf.recZ = sp.recZ; cf.recBegin = sp.recBegin; cf.recCount = sp.recCount;
+    cf.head = h->confHead.as<int>();
+    cf.next = h->confNext.as<int>();
+    cf.seedsPerMiddle = sp.seedsPerMiddle;
+    cf.changed = h->confState.as<uint32_t>() + kConfChangedBase;
+    rc = enqueue_conf_rounds(h, 0, kConfRoundsPerBatch, s);
+    if (rc != B200SEED_OK) return rc;
+  }
 
   CUDA_TRY(cudaEventRecord(h->ev[3], s));
-  CompactParams cp{};
+  CompactParams& cp = h->compactParams;
+  cp = CompactParams{};
   cp.nWorkPtr = sp.nWorkPtr;
   cp.slotCount = sp.slotCount;
   cp.tileSums = h->tileSums.as<uint32_t>();
@@ -282,38 +419,53 @@ int enqueue(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal, const uint32_
   cp.slotB = sp.slotB; cp.slotM = sp.slotM; cp.slotT = sp.slotT; cp.slotQ = sp.slotQ; cp.slotZ = sp.slotZ;
   cp.seedsPerMiddle = sp.seedsPerMiddle;
   cp.pIdx = gp.pIdx;
-  cp.outB = outB; cp.outM = outM; cp.outT = outT; cp.outQ = outQ; cp.outZ = outZ;
-  cp.outCapacity = outCapacity;
-  cp.seedOffsets = dSeedOffsets;
+  cp.outB = a.outB; cp.outM = a.outM; cp.outT = a.outT; cp.outQ = a.outQ; cp.outZ = a.outZ;
+  cp.outCapacity = a.outCapacity;
+  cp.seedOffsets = a.dSeedOffsets;
   cp.workStart = wp.workStart;
   cp.seedStart = h->seedStart.as<uint32_t>();
   cp.nEvents = nEvents; cp.nNav = nNav;
   cp.counters = gp.counters;
-  const uint32_t nTiles = std::max<uint32_t>(1, (nTotal + kTile - 1) / kTile);
-  k_tile_sums<<<nTiles, 256, 0, s>>>(cp);
-  k_scan<<<1, kScanThreads, 0, s>>>(cp.tileSums, cp.tilePrefix, nTiles);
-  k_compact_seeds<<<nTiles, 256, 0, s>>>(cp);
-  k_event_offsets<<<1, 256, 0, s>>>(cp);
-  launches += 4;
-  CUDA_TRY(cudaEventRecord(h->ev[4], s));
-  CUDA_TRY(cudaGetLastError());
-
-  // results the host needs after the sync
-  CUDA_TRY(cudaMemcpyAsync(h->hCounters, h->counters.ptr, kCntSlots * 8, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(h->hStatus, h->status.ptr, 4, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(h->hSeedTotal, dSeedOffsets + nEvents, 8, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(h->hCounters + kCntSlots, h->binStart.as<uint32_t>() + nBinsAll, 4, cudaMemcpyDeviceToHost, s));
+  rc = enqueue_tail(h, s);
+  if (rc != B200SEED_OK) return rc;
   h->lastEvents = nEvents;
   h->lastTotal = nTotal;
   h->lastZWin = nZWin;
-  h->lastCapacity = outCapacity;
-  h->launches = launches;
+  h->lastCapacity = a.outCapacity;
   h->pending = true;
   return B200SEED_OK;
 }
 
 int finish(b200seed_handle* h, cudaStream_t s, b200seed_seeds* out) {
   CUDA_TRY(cudaStreamSynchronize(s));
+  if (h->plan.dev.seedConfirmation) {
+    // the two host decisions of the seedConfirmation path: grow the record pool, run more rounds
+    for (;;) {
+      if (*h->hStatus & kStatusOverflowRecords) {
+        const size_t need = h->hConfState[0];
+        if (need > 0xFFFFFFF0u) return fail(B200SEED_ERR_OVERFLOW, "more than 2^32 candidate records in one batch: split it");
+        h->recCapacity = need + need / 8 + 1024;
+        int rc = enqueue(h);
+        if (rc != B200SEED_OK) return rc;
+        CUDA_TRY(cudaStreamSynchronize(s));
+        continue;
+      }
+      const int rounds = h->confRoundsLaunched;
+      int used = rounds;
+      for (int r = 1; r < rounds; ++r) {
+        if (h->hConfState[kConfChangedBase + r] == 0u) { used = r + 1; break; }
+      }
+      h->lastConfRounds = (uint32_t)used;
+      if (h->hConfState[kConfChangedBase + rounds - 1] == 0u) break;  // a round reproduced its predecessor
+      if (rounds + kConfRoundsPerBatch > kConfMaxRounds) {
+        return fail(B200SEED_ERR_RUNTIME, "seedConfirmation fixed point not reached after " + std::to_string(rounds) + " rounds");
+      }
+      int rc = enqueue_conf_rounds(h, rounds, kConfRoundsPerBatch, s);
+      if (rc == B200SEED_OK) rc = enqueue_tail(h, s);
+      if (rc != B200SEED_OK) return rc;
+      CUDA_TRY(cudaStreamSynchronize(s));
+    }
+  }
   h->pending = false;
   for (int i = 0; i < 4; ++i) {
     if (cudaEventElapsedTime(&h->stageMs[i], h->ev[i], h->ev[i + 1]) != cudaSuccess) h->stageMs[i] = 0.f;
@@ -330,6 +482,7 @@ int finish(b200seed_handle* h, cudaStream_t s, b200seed_seeds* out) {
   c.nSeeds = *h->hSeedTotal;
   c.nTieMiddles = h->hCounters[kCntTieMiddles];
   c.nKernelLaunches = h->launches;
+  c.nConfirmationRounds = h->plan.dev.seedConfirmation ? h->lastConfRounds : 0;
   if (out != nullptr) out->size = *h->hSeedTotal;
   const int st = *h->hStatus;
   if (st & (kStatusOverflowDoublets | kStatusOverflowPool)) {
@@ -460,9 +613,16 @@ int b200seed_create(const b200seed_config* cfg, int device, b200seed_handle** ou
     if (sizeof(TierLayout<Tier2>) > (size_t)prop.sharedMemPerBlockOptin) {
       return cleanup(fail(B200SEED_ERR_CUDA, "device offers less shared memory per block than the seeding kernel needs"));
     }
-    CREATE_TRY(setupTier(0, k_seed_middles<Tier0::B, Tier0::T, Tier0::P, Tier0::K, Tier0::N>, Tier0::N, sizeof(TierLayout<Tier0>)));
-    CREATE_TRY(setupTier(1, k_seed_middles<Tier1::B, Tier1::T, Tier1::P, Tier1::K, Tier1::N>, Tier1::N, sizeof(TierLayout<Tier1>)));
-    CREATE_TRY(setupTier(2, k_seed_middles<Tier2::B, Tier2::T, Tier2::P, Tier2::K, Tier2::N>, Tier2::N, sizeof(TierLayout<Tier2>)));
+    if (h->plan.dev.seedConfirmation) {
+      CREATE_TRY(setupTier(0, seed_kernel<Tier0, true>(), Tier0::N, sizeof(TierLayout<Tier0>)));
+      CREATE_TRY(setupTier(1, seed_kernel<Tier1, true>(), Tier1::N, sizeof(TierLayout<Tier1>)));
+      CREATE_TRY(setupTier(2, seed_kernel<Tier2, true>(), Tier2::N, sizeof(TierLayout<Tier2>)));
+      CREATE_TRY(cudaMallocHost(&h->hConfState, kConfStateWords * 4));
+    } else {
+      CREATE_TRY(setupTier(0, seed_kernel<Tier0, false>(), Tier0::N, sizeof(TierLayout<Tier0>)));
+      CREATE_TRY(setupTier(1, seed_kernel<Tier1, false>(), Tier1::N, sizeof(TierLayout<Tier1>)));
+      CREATE_TRY(setupTier(2, seed_kernel<Tier2, false>(), Tier2::N, sizeof(TierLayout<Tier2>)));
+    }
   }
   CREATE_TRY(cudaFuncSetAttribute(k_sort_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->sortSmemCap * 16)));
   if (std::getenv("B200SEED_VERBOSE") != nullptr) {
@@ -497,9 +657,12 @@ void b200seed_destroy(b200seed_handle* h) {
                     &h->sortScratch, &h->midLo, &h->midCount, &h->workStart, &h->workPos, &h->workEG,
                     &h->workCounter, &h->overflowList, &h->slotB, &h->slotM, &h->slotT, &h->slotQ, &h->slotZ, &h->slotCount,
                     &h->seedStart, &h->tileSums, &h->tilePrefix, &h->outB, &h->outM, &h->outT, &h->outQ,
-                    &h->outZ, &h->seedOffsets, &h->counters, &h->status, &h->zWin}) {
+                    &h->outZ, &h->seedOffsets, &h->counters, &h->status, &h->zWin, &h->rec, &h->recZ, &h->recBegin,
+                    &h->recCount, &h->slot2B, &h->slot2M, &h->slot2T, &h->slot2Q, &h->slot2Z, &h->slot2Count,
+                    &h->confHead, &h->confNext, &h->confState}) {
     b->release();
   }
+  if (h->hConfState != nullptr) cudaFreeHost(h->hConfState);
   for (int i = 0; i < 5; ++i) {
     if (h->ev[i] != nullptr) cudaEventDestroy(h->ev[i]);
   }
@@ -562,9 +725,17 @@ int b200seed_run_batch_device(b200seed_handle* h, uint32_t nEvents, uint32_t nSp
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = cudaStream != nullptr ? static_cast<cudaStream_t>(cudaStream) : h->stream;
   h->lastSeedOffsets = reinterpret_cast<const unsigned long long*>(seedOffsets);
-  return enqueue(h, nEvents, nSpacePointsTotal, spOffsets, x, y, z, r, varZ, varR, nullptr, 0,
-                 out->bottom, out->middle, out->top, out->quality, out->vertexZ, out->capacity,
-                 reinterpret_cast<unsigned long long*>(seedOffsets), s);
+  b200seed_handle::EnqueueArgs& a = h->last;
+  a = b200seed_handle::EnqueueArgs{};
+  a.nEvents = nEvents; a.nTotal = nSpacePointsTotal; a.dOffsets = spOffsets;
+  a.x = x; a.y = y; a.z = z; a.r = r; a.varZ = varZ; a.varR = varR;
+  a.outB = static_cast<uint32_t*>(out->bottom); a.outM = static_cast<uint32_t*>(out->middle);
+  a.outT = static_cast<uint32_t*>(out->top);
+  a.outQ = static_cast<float*>(out->quality); a.outZ = static_cast<float*>(out->vertexZ);
+  a.outCapacity = out->capacity;
+  a.dSeedOffsets = reinterpret_cast<unsigned long long*>(seedOffsets);
+  a.stream = s;
+  return enqueue(h);
 }
 
 int b200seed_sync(b200seed_handle* h, b200seed_seeds* out) {
@@ -573,7 +744,7 @@ int b200seed_sync(b200seed_handle* h, b200seed_seeds* out) {
   // the stream of the last call is ordered with the handle's stream through
   // the device-wide synchronisation below (the caller may have used its own)
   CUDA_TRY(cudaDeviceSynchronize());
-  return finish(h, h->stream, out);
+  return finish(h, h->last.stream != nullptr ? h->last.stream : h->stream, out);
 }
 
 static int run_host_batch(b200seed_handle* h, uint32_t nEvents, const uint32_t* spOffsets, const float* x,
@@ -625,10 +796,20 @@ static int run_host_batch(b200seed_handle* h, uint32_t nEvents, const uint32_t* 
   CUDA_TRY(h->outQ.reserve(maxSeeds * 4));
   CUDA_TRY(h->outZ.reserve(maxSeeds * 4));
   CUDA_TRY(h->seedOffsets.reserve(((size_t)nEvents + 1) * 8));
-  rc = enqueue(h, nEvents, nTotal, h->inOffsets.as<uint32_t>(), h->inX.as<float>(), h->inY.as<float>(),
-               h->inZ.as<float>(), h->inR.as<float>(), h->inVarZ.as<float>(), h->inVarR.as<float>(), dPhi,
-               (int)nZWin, h->outB.as<uint32_t>(), h->outM.as<uint32_t>(), h->outT.as<uint32_t>(),
-               h->outQ.as<float>(), h->outZ.as<float>(), maxSeeds, h->seedOffsets.as<unsigned long long>(), s);
+  {
+    b200seed_handle::EnqueueArgs& a = h->last;
+    a = b200seed_handle::EnqueueArgs{};
+    a.nEvents = nEvents; a.nTotal = nTotal; a.dOffsets = h->inOffsets.as<uint32_t>();
+    a.x = h->inX.as<float>(); a.y = h->inY.as<float>(); a.z = h->inZ.as<float>(); a.r = h->inR.as<float>();
+    a.varZ = h->inVarZ.as<float>(); a.varR = h->inVarR.as<float>(); a.dPhi = dPhi;
+    a.nZWin = (int)nZWin;
+    a.outB = h->outB.as<uint32_t>(); a.outM = h->outM.as<uint32_t>(); a.outT = h->outT.as<uint32_t>();
+    a.outQ = h->outQ.as<float>(); a.outZ = h->outZ.as<float>();
+    a.outCapacity = maxSeeds;
+    a.dSeedOffsets = h->seedOffsets.as<unsigned long long>();
+    a.stream = s;
+  }
+  rc = enqueue(h);
   if (rc != B200SEED_OK) return rc;
   b200seed_seeds tmp{};
   rc = finish(h, s, &tmp);

@@ -17,7 +17,7 @@ from . import config as cfgmod
 from .config import Config, Counters, Doublets, Info, Seeds
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libacts_b200_seeding.so")
+LIB_PATH = os.environ.get("B200SEED_LIB", os.path.join(_HERE, "libacts_b200_seeding.so"))  # override: kernel experiments
 
 # every symbol include/acts_b200_seeding.h declares
 EXPORTED_SYMBOLS = [

@@ -202,6 +202,7 @@ typedef struct b200seed_counters {
   uint64_t nSeeds;         /* S                                             */
   uint64_t nTieMiddles;    /* middles that needed the exact-tie slow path   */
   uint64_t nKernelLaunches;/* kernels launched by the call                  */
+  uint64_t nConfirmationRounds; /* seedConfirmation: rounds until the bestSeedQualityMap fixed point (0 otherwise) */
 } b200seed_counters;
 
 typedef struct b200seed_handle b200seed_handle;

@@ -14,8 +14,11 @@ ap.add_argument("--events", type=int, default=1)
 ap.add_argument("--mu", type=float, default=200.0)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--doublets", action="store_true")
+ap.add_argument("--conf", action="store_true", help="seedConfirmation = true (ITk pixel filter block)")
 a = ap.parse_args()
 cfg = config.pu200_config(plugin.config_init)
+if a.conf:
+    cfg.update(**config.confirmation_overrides())
 eng = plugin.SeedingEngine(cfg)
 evs = [events.pileup_event(i, mu=a.mu) for i in range(a.events)]
 cols, off = events.concat_events(evs)

@@ -25,11 +25,11 @@ def built():
     return True
 
 
-CONFIGS = ("seeding_py", "pu200", "itk_like")
+CONFIGS = ("seeding_py", "pu200", "itk_like", "itk_conf")
 
 
 def make_config(name, init):
     from acts_b200 import config
 
     return {"seeding_py": config.seeding_py_config, "pu200": config.pu200_config,
-            "itk_like": config.itk_like_config}[name](init)
+            "itk_like": config.itk_like_config, "itk_conf": config.itk_conf_config}[name](init)

@@ -129,6 +129,21 @@ def test_full_size_event_mu200(plugin, O):
     eng.close()
 
 
+def test_full_size_event_mu200_seed_confirmation(plugin, O):
+    """<mu>=200 with seedConfirmation = true: ~4.8e4 middles coupled through bestSeedQualityMap."""
+    from acts_b200 import config as cm
+    from acts_b200 import events
+
+    ev = events.pileup_event(1, mu=200)
+    eng = plugin.SeedingEngine(make_config("pu200", plugin.config_init).update(**cm.confirmation_overrides()))
+    got = eng.run(ev)
+    ref = O.Oracle(make_config("pu200", O.config_init).update(**cm.confirmation_overrides())).run(ev)
+    assert ref["quality"].size > 10_000
+    assert _same_bits(got, ref)
+    assert eng.counters()["nConfirmationRounds"] >= 2
+    eng.close()
+
+
 @pytest.mark.parametrize("override", [
     dict(interactionPointCut=1),
     dict(useExtraCuts=1),
@@ -159,6 +174,48 @@ def test_config_variants(plugin, O, override):
         got = eng.run(ev)
         ref = orc.run(ev)
         assert _same_bits(got, ref), f"{override} event {i}"
+    eng.close()
+
+
+@pytest.mark.parametrize("base,extra,cases", [
+    ("itk_conf", {}, ((0, 5), (1, 20), (2, 60))),
+    ("pu200", "conf", ((0, 20), (3, 60))),
+    ("pu200", dict(maxQualitySeedsPerSpMConf=0), ((0, 20),)),
+    ("pu200", dict(maxQualitySeedsPerSpMConf=1, maxSeedsPerSpMConf=2, maxSeedsPerSpM=0), ((1, 40),)),
+    ("pu200", dict(maxSeedsPerSpM=3, zOriginWeightFactor=0.0, impactWeightFactor=1.0, compatSeedWeight=200.0), ((2, 40),)),
+    ("itk_conf", dict(useDeltaRinsteadOfTopRadius=1, seedWeightIncrement=7.0, numSeedIncrement=0.0), ((4, 40),)),
+])
+def test_seed_confirmation_matches_oracle(plugin, O, base, extra, cases):
+    """seedConfirmation = true: the event-wide bestSeedQualityMap order dependence
+    (BroadTripletSeedFilter.cpp:278-285,364-376) resolved on the device, bit for bit."""
+    from acts_b200 import config as cm
+    from acts_b200 import events
+
+    def mk(init):
+        cfg = make_config(base, init)
+        if base == "pu200":
+            cfg.update(**cm.confirmation_overrides())
+        if isinstance(extra, dict):
+            cfg.update(**extra)
+        return cfg
+
+    eng = plugin.SeedingEngine(mk(plugin.config_init))
+    orc = O.Oracle(mk(O.config_init))
+    for i, mu in cases:
+        ev = events.pileup_event(i, mu=mu)
+        got = eng.run(ev)
+        ref = orc.run(ev)
+        assert ref["quality"].size > 0
+        assert O.seed_set(got) == O.seed_set(ref), f"{base} {extra} event {i}: seed set differs"
+        assert _same_bits(got, ref), f"{base} {extra} event {i}: order differs"
+        cnt = eng.counters()
+        assert cnt["nCandidates"] == ref["counters"]["nCandidates"]
+        assert 2 <= cnt["nConfirmationRounds"] <= 64
+    # a batch shares the launches; the fixed point is per event all the same
+    evs = [events.pileup_event(10 + k, mu=m) for k, m in enumerate((20, 5, 40))]
+    cols, offsets = events.concat_events(evs)
+    for ev, got in zip(evs, eng.run_batch(cols, offsets)):
+        assert _same_bits(got, orc.run(ev))
     eng.close()
 
 

@@ -100,7 +100,7 @@ def test_config_errors_map_to_reference_exceptions(plugin, O):
 def test_unsupported_configs_are_rejected_loudly(plugin):
     from acts_b200 import config as cm
 
-    for override in (dict(seedConfirmation=1), dict(compatSeedLimit=9), dict(maxSeedsPerSpMConf=17)):
+    for override in (dict(seedConfirmation=1, maxQualitySeedsPerSpMConf=17), dict(compatSeedLimit=9), dict(maxSeedsPerSpMConf=17)):
         with pytest.raises(plugin.SeedingError) as ei:
             plugin.plan_info(make_config("pu200", plugin.config_init).update(**override))
         assert ei.value.code == cm.ERR_UNSUPPORTED
