@@ -693,6 +693,10 @@ int b200seed_get_counters(const b200seed_handle* h, b200seed_counters* c) {
 // outermost navigation axis, GridIterator.ipp:228-242).
 int b200seed_set_phi_sector(b200seed_handle* h, uint32_t firstPhiBin, uint32_t nPhiBins) {
   if (h == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL handle");
+  if (nPhiBins != 0 && h->plan.dev.seedConfirmation) {
+    return fail(B200SEED_ERR_UNSUPPORTED,
+                "seedConfirmation couples the middles of an event through bestSeedQualityMap: no phi-sector split");
+  }
   if (nPhiBins == 0) {
     h->phiFirst = 1;
     h->phiCount = 0xFFFFFFFFu;

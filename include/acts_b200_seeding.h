@@ -284,7 +284,8 @@ int b200seed_sync(b200seed_handle* h, b200seed_seeds* out);
  * the following calls on this handle to the middle space points whose phi bin
  * (1-based) lies in [firstPhiBin, firstPhiBin + nPhiBins); nPhiBins = 0 restores
  * "all".  Sector results concatenated in sector order equal the unsplit result.
- * Valid because seedConfirmation = false has no cross-middle state. */
+ * Valid because seedConfirmation = false has no cross-middle state; refused
+ * with B200SEED_ERR_UNSUPPORTED on a seedConfirmation handle. */
 int b200seed_set_phi_sector(b200seed_handle* h, uint32_t firstPhiBin, uint32_t nPhiBins);
 
 /* GPU time of the stages of the last completed call, milliseconds (CUDA events

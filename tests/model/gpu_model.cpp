@@ -14,6 +14,8 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
+#include <limits>
 #include <random>
 #include <utility>
 #include <vector>
@@ -58,12 +60,25 @@ struct Doublet {
   uint32_t seq;  // emission index in the reference's order
 };
 
+// seedConfirmation: what k_seed_middles<kConf> leaves in HBM for one middle
+struct ConfRecord {
+  uint32_t b, t;  // packed positions
+  float weight, zOrigin;
+  uint32_t group;      // sorted rank of the bottom
+  uint32_t groupSize;  // min(#candidates of the group, 3)
+  bool needsTwoTops, quality;
+};
+struct ConfMiddle {
+  uint32_t m;
+  std::vector<ConfRecord> rec;
+};
+
 // One middle space point, restructured algorithm.  tieMode: 0 canonical
 // (key, seq) order, 1 replay libstdc++ std::sort from the emission order.
 void processMiddle(const DeviceConfig& c, const Packed& p, uint32_t m, uint32_t firstMiddleInBin,
                    const std::vector<Window>& bottomBins, const std::vector<Window>& topBins,
                    const float* zLo, const float* zHi, int nZWin, int tieMode,
-                   std::vector<SeedOut>& out, uint64_t* stats) {
+                   std::vector<SeedOut>& out, uint64_t* stats, std::vector<ConfMiddle>* conf = nullptr) {
   MiddleSp mid{p.x[m], p.y[m], p.z[m], p.r[m], p.varZ[m], p.varR[m], 0, 0, 0, 0};
   middle_info(mid);
   const float firstMiddleR = p.r[firstMiddleInBin];
@@ -103,6 +118,7 @@ void processMiddle(const DeviceConfig& c, const Packed& p, uint32_t m, uint32_t 
   std::vector<Doublet> tops, bottoms;
   collect(false, topBins, tops);
   if (tops.empty()) return;
+  if (c.seedConfirmation && tops.size() < conf_n_top(conf_range(c, mid.z), mid.r)) return;  // sufficientTopDoublets
   collect(true, bottomBins, bottoms);
   if (bottoms.empty()) return;
   stats[0] += bottoms.size();
@@ -214,6 +230,7 @@ void processMiddle(const DeviceConfig& c, const Packed& p, uint32_t m, uint32_t 
   }
 
   // --- candidates, filter, bounded heap -------------------------------------
+  if (c.seedConfirmation) conf->push_back({m, {}});
   struct Cand { float curv, impact, topR; uint32_t topPos; };
   const int nLow = (int)c.maxSeedsPerSpMConf;
   std::vector<WeightIndex> heap;  // size <= nLow
@@ -245,6 +262,23 @@ void processMiddle(const DeviceConfig& c, const Packed& p, uint32_t m, uint32_t 
     order.resize(n);
     for (int i = 0; i < n; ++i) order[i] = {cands[i].curv, (uint32_t)i};
     std_sort(order.data(), n, sortItemLess);  // BroadTripletSeedFilter.cpp:143-148
+    if (c.seedConfirmation) {
+      // map- and collector-independent part of the filter; the rest is confReplay()
+      const uint32_t bp = bottoms[j].pos;
+      const float rMaxSeedConfMid = conf_range(c, mid.z).rMaxSeedConf;
+      for (int k = 0; k < n; ++k) {
+        const Cand& cd = cands[order[k].val];
+        uint32_t nCompat;
+        float w = filter_weight(
+            c, n, k, cd.impact, [&](int i) { return cands[order[i].val].curv; },
+            [&](int i) { return cands[order[i].val].topR; }, nCompat);
+        int dsc;
+        if (!conf_candidate(c, conf_range(c, p.z[bp]), p.r[bp], zOrigin, cd.impact, nCompat, w, dsc)) continue;
+        conf->back().rec.push_back({bp, cd.topPos, w, zOrigin, (uint32_t)j, (uint32_t)std::min(n, 3),
+                                    !(p.r[bp] > rMaxSeedConfMid), dsc > 0});
+      }
+      continue;
+    }
     for (int k = 0; k < n; ++k) {
       const Cand& cd = cands[order[k].val];
       const float w = filter_weight(
@@ -266,6 +300,7 @@ void processMiddle(const DeviceConfig& c, const Packed& p, uint32_t m, uint32_t 
       std_push_heap(heap.data(), (int)heap.size(), heap_comp);
     }
   }
+  if (c.seedConfirmation) return;
   // toSortedCandidates + filterTripletsMiddleFixed (BroadTripletSeedFilter.cpp:324-393)
   std_sort_heap(heap.data(), (int)heap.size(), heap_comp);
   size_t maxSeeds = heap.size();
@@ -274,6 +309,132 @@ void processMiddle(const DeviceConfig& c, const Packed& p, uint32_t m, uint32_t 
     const Stored& s = storage[heap[i].index];
     out.push_back({p.copiedFrom[s.b], p.copiedFrom[m], p.copiedFrom[s.t], s.w, s.z});
   }
+}
+
+// ---------------------------------------------------------------------------
+// seedConfirmation: scalar twin of k_conf_link / k_conf_replay and of the round
+// loop in seeding_plugin.cu.  Seeds of a round: per middle (in processing
+// order) a short list; Q(sp, w) = best quality over the previous round's seeds
+// of middles before w that contain sp.
+// ---------------------------------------------------------------------------
+struct ConfSeedM {
+  uint32_t b, t;
+  float weight, zOrigin;
+  bool quality;
+  bool operator==(const ConfSeedM& o) const {
+    return b == o.b && t == o.t && std::memcmp(&weight, &o.weight, 4) == 0;
+  }
+};
+using ConfRound = std::vector<std::vector<ConfSeedM>>;  // [middle in order] -> seeds
+
+struct ConfLists {  // per space point: (middle order, quality)
+  std::vector<std::vector<std::pair<uint32_t, float>>> of;
+  float best(uint32_t sp, uint32_t w) const {
+    float q = std::numeric_limits<float>::lowest();
+    for (const auto& e : of[sp]) if (e.first < w && e.second > q) q = e.second;
+    return q;
+  }
+};
+
+void confPush(std::vector<WeightIndex>& heap, size_t nMax, std::vector<ConfSeedM>& storage, const ConfSeedM& sd) {
+  if (nMax == 0) return;
+  if (heap.size() < nMax) {
+    storage.push_back(sd);
+    heap.push_back({sd.weight, (uint32_t)storage.size() - 1});
+    std_push_heap(heap.data(), (int)heap.size(), heap_comp);
+    return;
+  }
+  const WeightIndex smallest = heap[0];
+  if (sd.weight <= smallest.weight) return;
+  storage[smallest.index] = sd;
+  std_pop_heap(heap.data(), (int)heap.size(), heap_comp);
+  heap.back() = {sd.weight, smallest.index};
+  std_push_heap(heap.data(), (int)heap.size(), heap_comp);
+}
+
+std::vector<ConfSeedM> confReplay(const DeviceConfig& c, const ConfMiddle& cm, uint32_t w, const ConfLists& q) {
+  std::vector<WeightIndex> high, low;
+  std::vector<ConfSeedM> storage;
+  const float bestM = q.best(cm.m, w);
+  size_t i = 0;
+  const size_t n = cm.rec.size();
+  while (i < n) {
+    size_t e = i;
+    while (e < n && cm.rec[e].group == cm.rec[i].group) ++e;
+    const ConfRecord& g = cm.rec[i];
+    const uint32_t minTops = (g.needsTwoTops ? 2u : 1u) + (high.empty() ? 0u : 1u);
+    if (g.groupSize >= minTops) {
+      const float bestB = q.best(g.b, w);
+      bool lowHas = false;
+      ConfSeedM lowBest{};
+      float lowW = std::numeric_limits<float>::lowest();
+      for (size_t k = i; k < e; ++k) {
+        const ConfRecord& r = cm.rec[k];
+        if (r.weight < bestB && r.weight < bestM && r.weight < q.best(r.t, w)) continue;
+        if (r.quality) {
+          confPush(high, c.maxQualitySeedsPerSpMConf, storage, {r.b, r.t, r.weight, r.zOrigin, true});
+        } else if (r.weight > lowW) {  // evaluated for every group; only used while no quality seed exists
+          lowW = r.weight;
+          lowBest = {r.b, r.t, r.weight, r.zOrigin, false};
+          lowHas = true;
+        }
+      }
+      if (lowHas && high.empty()) confPush(low, c.maxSeedsPerSpMConf, storage, lowBest);
+    }
+    i = e;
+  }
+  std_sort_heap(high.data(), (int)high.size(), heap_comp);
+  std_sort_heap(low.data(), (int)low.size(), heap_comp);
+  std::vector<ConfSeedM> sorted, out;
+  for (const WeightIndex& h : high) sorted.push_back(storage[h.index]);
+  for (const WeightIndex& l : low) sorted.push_back(storage[l.index]);
+  size_t maxSeeds = sorted.size();
+  if (maxSeeds > c.maxSeedsPerSpM) maxSeeds = c.maxSeedsPerSpM + 1;
+  for (const ConfSeedM& sd : sorted) {
+    if (out.size() >= maxSeeds) break;
+    if (!high.empty() && !sd.quality) continue;
+    float qB = q.best(sd.b, w), qM = bestM, qT = q.best(sd.t, w);
+    for (const ConfSeedM& e : out) {  // the middle's own earlier seeds are already in the map
+      qM = std::max(qM, e.weight);
+      if (e.b == sd.b || e.t == sd.b) qB = std::max(qB, e.weight);
+      if (e.b == sd.t || e.t == sd.t) qT = std::max(qT, e.weight);
+    }
+    if (sd.weight < qB && sd.weight < qM && sd.weight < qT) continue;
+    out.push_back(sd);
+  }
+  return out;
+}
+
+// returns the number of rounds (>= 2), seeds appended to `out`
+int confFixedPoint(const DeviceConfig& c, const Packed& p, size_t nSp, const std::vector<ConfMiddle>& middles,
+                   std::vector<SeedOut>& out) {
+  ConfRound prev(middles.size()), cur(middles.size());
+  int rounds = 0;
+  for (;;) {
+    ConfLists lists;
+    lists.of.resize(nSp);
+    if (rounds > 0) {
+      for (uint32_t w = 0; w < middles.size(); ++w) {
+        for (const ConfSeedM& sd : prev[w]) {
+          for (uint32_t sp : {sd.b, middles[w].m, sd.t}) lists.of[sp].push_back({w, sd.weight});
+        }
+      }
+    }
+    bool changed = rounds == 0;
+    for (uint32_t w = 0; w < middles.size(); ++w) {
+      cur[w] = confReplay(c, middles[w], w, lists);
+      if (rounds > 0 && !(cur[w] == prev[w])) changed = true;
+    }
+    ++rounds;
+    prev.swap(cur);
+    if (!changed) break;
+  }
+  for (uint32_t w = 0; w < middles.size(); ++w) {
+    for (const ConfSeedM& sd : prev[w]) {
+      out.push_back({p.copiedFrom[sd.b], p.copiedFrom[middles[w].m], p.copiedFrom[sd.t], sd.weight, sd.zOrigin});
+    }
+  }
+  return rounds;
 }
 
 }  // namespace
@@ -295,6 +456,7 @@ int64_t model_run(const DeviceConfig* cfg, const uint32_t* copiedFrom, const flo
                   uint64_t* stats) {
   Packed p{copiedFrom, x, y, z, r, varZ, varR};
   std::vector<SeedOut> out;
+  std::vector<ConfMiddle> confMiddles;
   for (int i = 0; i < 8; ++i) stats[i] = 0;
   for (uint32_t g = 0; g < nMiddleBins; ++g) {
     const uint32_t mb = middleBins[g];
@@ -306,8 +468,16 @@ int64_t model_run(const DeviceConfig* cfg, const uint32_t* copiedFrom, const flo
     const uint32_t mlo = firstTrue(binBegin[mb], binEnd[mb], [&](uint32_t i) { return !(r[i] < rangeMin[g]); });
     const uint32_t mhi = firstTrue(mlo, binEnd[mb], [&](uint32_t i) { return r[i] > rangeMax[g]; });
     for (uint32_t m = mlo; m < mhi; ++m) {
-      processMiddle(*cfg, p, m, binBegin[mb], bot, top, zLo, zHi, (int)nZWin, tieMode, out, stats);
+      processMiddle(*cfg, p, m, binBegin[mb], bot, top, zLo, zHi, (int)nZWin, tieMode, out, stats, &confMiddles);
     }
+  }
+  if (cfg->seedConfirmation) {
+    size_t nSp = 0;
+    for (const ConfMiddle& cm : confMiddles) {
+      nSp = std::max<size_t>(nSp, cm.m + 1);
+      for (const ConfRecord& rc : cm.rec) nSp = std::max<size_t>(nSp, std::max(rc.b, rc.t) + 1);
+    }
+    stats[4] = (uint64_t)confFixedPoint(*cfg, p, nSp, confMiddles, out);
   }
   if (out.size() <= capacity) {
     for (size_t i = 0; i < out.size(); ++i) {

@@ -95,7 +95,8 @@ def run(cfg, grid: dict, tie_mode: int = 0, z_windows=None) -> dict:
     assert 0 <= n <= cap
     return {"bottom": ob[:n], "middle": om[:n], "top": ot[:n], "quality": oq[:n], "vertexZ": oz[:n],
             "stats": {"nBottomDoublets": int(stats[0]), "nTopDoublets": int(stats[1]),
-                      "nTripletTests": int(stats[2]), "nCandidates": int(stats[3])}}
+                      "nTripletTests": int(stats[2]), "nCandidates": int(stats[3]),
+                      "nConfirmationRounds": int(stats[4])}}
 
 
 def bin_index(cfg, x, y, z, r):

@@ -58,7 +58,7 @@ def test_atan2f_replay_matches_host_libm(env):
     assert env[3].lib().model_check_atan2f(99, 30_000_000) == 0
 
 
-@pytest.mark.parametrize("name", [c for c in CONFIGS if c != "itk_conf"])  # the model has no seed-confirmation replay
+@pytest.mark.parametrize("name", CONFIGS)
 def test_model_equals_oracle(env, name):
     events, plugin, O, M = env
     cfg = make_config(name, plugin.config_init)
@@ -75,6 +75,29 @@ def test_model_equals_oracle(env, name):
         got0 = M.run(cfg, stable["grid"], tie_mode=0)
         for k in KEYS:
             assert np.array_equal(got0[k].view(np.uint32), stable[k].view(np.uint32))
+
+
+def test_seed_confirmation_fixed_point_equals_sequential_map(env):
+    """seedConfirmation: records + collector replay + fixed-point rounds (what k_conf_replay and the round loop do)
+    reproduce the reference's sequential bestSeedQualityMap pass; the rounds really iterate (> 2)."""
+    events, plugin, O, M = env
+    from acts_b200 import config as cm
+
+    deepest = 0
+    for base, extra in (("itk_conf", {}), ("pu200", cm.confirmation_overrides()),
+                        ("pu200", dict(cm.confirmation_overrides(), maxQualitySeedsPerSpMConf=0)),
+                        ("pu200", dict(cm.confirmation_overrides(), maxSeedsPerSpM=0, maxSeedsPerSpMConf=1))):
+        cfg = make_config(base, plugin.config_init).update(**extra)
+        orc = O.Oracle(make_config(base, O.config_init).update(**extra))
+        for i, mu in ((1, 30), (4, 60)):
+            ev = events.pileup_event(i, mu=mu)
+            ref = orc.run(ev, want_grid=True)
+            got = M.run(cfg, ref["grid"], tie_mode=2)
+            assert ref["quality"].size > 100
+            for k in KEYS:
+                assert np.array_equal(got[k].view(np.uint32), ref[k].view(np.uint32)), (base, extra, i, k)
+            deepest = max(deepest, got["stats"]["nConfirmationRounds"])
+    assert deepest > 2
 
 
 def test_model_bin_index_equals_oracle(env):
