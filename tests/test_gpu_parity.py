@@ -4,6 +4,8 @@ Bit-exact bar: identical (bottom, middle, top) triplets, bit-identical quality
 and vertexZ, and -- with the exact tie replay of the bin sort -- the same seed
 ORDER as the reference.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -407,3 +409,36 @@ def test_estimated_track_parameters_match_reference_arithmetic(plugin, O):
     rel[:, 4:7] = np.abs(got[:, 4:7] - ref[:, 4:7])
     assert np.nanmax(rel) < 1e-9, np.nanmax(rel)
     eng.close()
+
+
+def test_csv_replay_round_trip(plugin, O, tmp_path):
+    """ACTS CSV dumps -> engine -> CsvSeedWriter layout, and back; equals the oracle on the same file."""
+    import subprocess
+    import sys
+
+    from acts_b200 import csvio, events
+
+    src, dst = tmp_path / "in", tmp_path / "out"
+    src.mkdir()
+    orc = O.Oracle(make_config("pu200", O.config_init))
+    refs = {}
+    for e, mu in ((0, 5), (7, 20)):
+        ev = events.pileup_event(e, mu=mu)
+        ids = (np.arange(ev["x"].size, dtype=np.uint64) * 3 + 11)  # measurement ids are not positions
+        csvio.write_spacepoints(csvio.per_event_filepath(str(src), "spacepoint.csv", e), ev, measurement_id=ids)
+        sp = csvio.read_spacepoints(csvio.per_event_filepath(str(src), "spacepoint.csv", e))
+        for k in ("x", "y", "z", "varZ", "varR"):
+            assert np.array_equal(sp[k].view(np.uint32), ev[k].view(np.uint32)), k  # 9 digits: exact round trip
+        refs[e] = (sp, orc.run(sp))
+        # the "reference run" seed file next to the space points, for --compare
+        csvio.write_seeds(csvio.per_event_filepath(str(src), "seed.csv", e), refs[e][1], sp, measurement_id=ids)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "replay_csv.py"), "--input-dir", str(src),
+                          "--output-dir", str(dst), "--compare"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "only here 0, only there 0, value mismatches 0" in res.stdout
+    for e, (sp, ref) in refs.items():
+        got = csvio.read_seeds(csvio.per_event_filepath(str(dst), "seed.csv", e), measurement_id=sp["measurement_id"])
+        assert np.array_equal(got["bottom"], ref["bottom"]) and np.array_equal(got["top"], ref["top"])
+        assert np.array_equal(got["quality"].view(np.uint32), ref["quality"].view(np.uint32))
+        assert np.all(got["pT"] > 0)
