@@ -14,14 +14,24 @@ CSRC = os.path.join(ROOT, "acts_b200", "csrc")
 PLUGIN_SO = os.path.join(ROOT, "acts_b200", "libacts_b200_seeding.so")
 MODEL_SO = os.path.join(ROOT, "tests", "model", "libgpu_model.so")
 
-NVCC_FLAGS = [
+COMMON_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++20",
-    # exact binary32 replay of the reference: no FMA contraction, IEEE div/sqrt
-    "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-    "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall",
-    "-shared",
 ]
+# exact binary32 replay of the reference: no FMA contraction, IEEE div/sqrt
+EXACT_FLAGS = ["-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+               "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall"]
+# relaxedFloat fast path: contraction and approximate reciprocals allowed on the device
+RELAXED_FLAGS = ["-fmad=true", "-prec-div=false", "-prec-sqrt=false", "-ftz=true",
+                 "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall"]
+# The library holds two engines compiled from the same sources under private symbol
+# prefixes / namespaces (csrc/engine_symbols.h) plus the exported ABI (csrc/seeding_abi.cpp).
+ENGINES = {
+    "exact": ["-DB200SEED_ENGINE_PREFIX=b200ex_", "-DB200SEED_NS=b200seed", *EXACT_FLAGS],
+    "relaxed": ["-DB200SEED_ENGINE_PREFIX=b200rx_", "-DB200SEED_NS=b200seed_rx", "-DB200SEED_RELAXED=1", *RELAXED_FLAGS],
+}
+NVCC_FLAGS = [*COMMON_FLAGS, *EXACT_FLAGS, "-shared"]  # single-engine builds (tools/build_variant.py)
+OBJ_DIR = os.path.join(ROOT, "build", "obj")
 
 
 def _stale(target, sources):
@@ -32,20 +42,44 @@ def _stale(target, sources):
 
 
 def plugin_sources():
-    names = ["seeding_plugin.cu", "host_plan.cpp", "seeding_kernels.cuh", "seed_math.h", "host_plan.hpp"]
+    names = ["seeding_plugin.cu", "host_plan.cpp", "seeding_abi.cpp", "engine_symbols.h", "seeding_kernels.cuh",
+             "seed_math.h", "host_plan.hpp"]
     return [os.path.join(CSRC, n) for n in names] + [os.path.join(ROOT, "include", "acts_b200_seeding.h")]
+
+
+def engine_compile_commands(verbose: bool = False, extra=()):
+    """nvcc -c command lines of the engine objects + the ABI object: [(object, argv)]."""
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    pre = ["-include", os.path.join(CSRC, "engine_symbols.h")]
+    cmds = []
+    for name, flags in ENGINES.items():
+        for src in ("seeding_plugin.cu", "host_plan.cpp"):
+            obj = os.path.join(OBJ_DIR, "%s_%s.o" % (name, src.split(".")[0]))
+            ptxas = ["-Xptxas", "-v" if verbose else "-warn-spills"] if src.endswith(".cu") else []
+            cmds.append((obj, ["nvcc", *COMMON_FLAGS, *flags, *extra, *pre, *ptxas, "-c", "-o", obj, os.path.join(CSRC, src)]))
+    obj = os.path.join(OBJ_DIR, "seeding_abi.o")
+    cmds.append((obj, ["nvcc", *COMMON_FLAGS, *EXACT_FLAGS, "-c", "-o", obj, os.path.join(CSRC, "seeding_abi.cpp")]))
+    return cmds
 
 
 def build_plugin(force: bool = False, verbose: bool = False) -> str:
     srcs = plugin_sources()
     if force or _stale(PLUGIN_SO, srcs):
-        cmd = ["nvcc", *NVCC_FLAGS, "-Xptxas", "-v" if verbose else "-warn-spills", "-o", PLUGIN_SO,
-               os.path.join(CSRC, "seeding_plugin.cu"), os.path.join(CSRC, "host_plan.cpp")]
-        res = subprocess.run(cmd, capture_output=True, text=True)
-        if verbose or res.returncode != 0:
-            sys.stderr.write(res.stdout + res.stderr)
-        if res.returncode != 0:
+        cmds = engine_compile_commands(verbose)
+        procs = [(obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)) for obj, cmd in cmds]
+        failed = False
+        for obj, proc in procs:
+            out, _ = proc.communicate()
+            if verbose or proc.returncode != 0:
+                sys.stderr.write(out)
+            failed |= proc.returncode != 0
+        if failed:
             raise RuntimeError("nvcc failed building the seeding plugin")
+        link = ["nvcc", *COMMON_FLAGS, "-shared", "-o", PLUGIN_SO, *[obj for obj, _ in cmds]]
+        res = subprocess.run(link, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("linking the seeding plugin failed")
     return PLUGIN_SO
 
 

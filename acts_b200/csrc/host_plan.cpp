@@ -9,7 +9,7 @@
 #include <limits>
 #include <numbers>
 
-namespace b200seed {
+namespace B200SEED_NS {
 
 namespace {
 
@@ -460,4 +460,4 @@ void config_defaults(b200seed_config& c) {
   c.relaxedFloat = 0;
 }
 
-}  // namespace b200seed
+}  // namespace B200SEED_NS

@@ -18,7 +18,7 @@
 #include "../../include/acts_b200_seeding.h"
 #include "seed_math.h"
 
-namespace b200seed {
+namespace B200SEED_NS {
 
 struct PlanError {
   int code = B200SEED_OK;
@@ -47,4 +47,4 @@ bool make_host_plan(const b200seed_config& cfg, HostPlan& plan, PlanError& err);
 // Reference defaults (GridTripletSeedingAlgorithm.hpp:34-244).
 void config_defaults(b200seed_config& cfg);
 
-}  // namespace b200seed
+}  // namespace B200SEED_NS

@@ -16,6 +16,14 @@
 
 #include <stdint.h>
 
+// Two engines are compiled from the same sources into one library (build.py):
+// the exact one (namespace b200seed) and the relaxedFloat fast path
+// (-DB200SEED_RELAXED -DB200SEED_NS=b200seed_rx, FMA contraction and
+// approximate division / square root allowed).
+#ifndef B200SEED_NS
+#define B200SEED_NS b200seed
+#endif
+
 #if defined(__CUDACC__)
 #define B2S_HD __host__ __device__ __forceinline__
 #else
@@ -27,12 +35,28 @@
 #include <cstring>
 #endif
 
-namespace b200seed {
+namespace B200SEED_NS {
 
 // ---------------------------------------------------------------------------
 // IEEE binary32 primitives
 // ---------------------------------------------------------------------------
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(B200SEED_RELAXED)
+// relaxedFloat: plain operators, the compiler may contract them into FMAs and
+// use approximate reciprocals (-fmad=true -prec-div=false -prec-sqrt=false -ftz=true)
+B2S_HD float fmul(float a, float b) { return a * b; }
+B2S_HD float fadd(float a, float b) { return a + b; }
+B2S_HD float fsub(float a, float b) { return a - b; }
+B2S_HD float fdiv(float a, float b) { return a / b; }
+B2S_HD float fsqrt(float a) { return sqrtf(a); }
+B2S_HD double dadd(double a, double b) { return a + b; }
+B2S_HD double dsub(double a, double b) { return a - b; }
+B2S_HD double dmul(double a, double b) { return a * b; }
+B2S_HD double ddiv(double a, double b) { return a / b; }
+B2S_HD uint32_t f2u(float f) { return __float_as_uint(f); }
+B2S_HD float u2f(uint32_t u) { return __uint_as_float(u); }
+B2S_HD float fabs_(float a) { return fabsf(a); }
+B2S_HD double dfloor(double a) { return floor(a); }
+#elif defined(__CUDA_ARCH__)
 B2S_HD float fmul(float a, float b) { return __fmul_rn(a, b); }
 B2S_HD float fadd(float a, float b) { return __fadd_rn(a, b); }
 B2S_HD float fsub(float a, float b) { return __fsub_rn(a, b); }
@@ -838,4 +862,4 @@ B2S_HD int cot_bucket(float cot, float cotMax, float scale, int nBuckets) {
   return b;
 }
 
-}  // namespace b200seed
+}  // namespace B200SEED_NS

@@ -1,0 +1,209 @@
+// seeding_abi.cpp -- the exported C ABI (include/acts_b200_seeding.h).
+//
+// The library contains two engines built from the same sources (engine_symbols.h):
+//   b200ex_*  exact binary32 replay of the reference cuts (bit-identical seeds)
+//   b200rx_*  relaxedFloat fast path (FMA contraction, approximate division / sqrt,
+//             CUDA atan2f, no tie-order replay) -- results NOT guaranteed identical
+// b200seed_create routes a handle to one of them by cfg->relaxedFloat; every other
+// call is forwarded to the engine the handle belongs to.  Host-only planning
+// (validation, derived constants, tables) is the same code in both; the exact one serves it.
+#include <new>
+
+#include "../../include/acts_b200_seeding.h"
+
+extern "C" {
+
+#define B200SEED_DECLARE_ENGINE(P)                                                                          \
+  struct P##handle;                                                                                         \
+  int P##config_init(b200seed_config*);                                                                     \
+  int P##plan_info(const b200seed_config*, b200seed_info*);                                                 \
+  int P##plan_tables(const b200seed_config*, void*, uint64_t, uint32_t*, uint32_t*, uint32_t*, uint32_t*,   \
+                     uint32_t*, uint64_t*);                                                                 \
+  int P##create(const b200seed_config*, int, P##handle**);                                                  \
+  void P##destroy(P##handle*);                                                                              \
+  const char* P##last_error(void);                                                                          \
+  int P##get_info(const P##handle*, b200seed_info*);                                                        \
+  int P##get_counters(const P##handle*, b200seed_counters*);                                                \
+  int P##run(P##handle*, uint32_t, const float*, const float*, const float*, const float*, const float*,    \
+             const float*, uint32_t, const float*, const float*, b200seed_seeds*);                          \
+  int P##run_with_phi(P##handle*, uint32_t, const float*, const float*, const float*, const float*,         \
+                      const float*, const float*, const float*, b200seed_seeds*);                           \
+  int P##run_batch(P##handle*, uint32_t, const uint32_t*, const float*, const float*, const float*,         \
+                   const float*, const float*, const float*, uint64_t*, b200seed_seeds*);                   \
+  int P##run_batch_device(P##handle*, uint32_t, uint32_t, const uint32_t*, const float*, const float*,      \
+                          const float*, const float*, const float*, const float*, uint64_t*,                \
+                          b200seed_seeds*, void*);                                                          \
+  int P##sync(P##handle*, b200seed_seeds*);                                                                 \
+  int P##set_phi_sector(P##handle*, uint32_t, uint32_t);                                                    \
+  int P##get_stage_times(const P##handle*, float*);                                                         \
+  int P##estimate_params(P##handle*, uint64_t, const uint32_t*, const uint32_t*, const uint32_t*, uint32_t, \
+                         const float*, const float*, const float*, const double*, double*);                 \
+  int P##debug_grid(P##handle*, uint64_t, uint32_t*, float*, float*, float*, float*, float*, float*,        \
+                    uint64_t, uint32_t*, uint32_t*);                                                        \
+  int P##debug_doublets(P##handle*, b200seed_doublets*);                                                    \
+  int P##debug_atan2f(P##handle*, uint64_t, const float*, const float*, float*);
+
+B200SEED_DECLARE_ENGINE(b200ex_)
+B200SEED_DECLARE_ENGINE(b200rx_)
+
+}  // extern "C"
+
+struct b200seed_handle {
+  b200ex_handle* exact = nullptr;
+  b200rx_handle* relaxed = nullptr;
+};
+
+namespace {
+
+thread_local int g_lastEngine = 0;  // whose last_error() the caller should see: 0 exact, 1 relaxed, 2 this file
+thread_local const char* g_ownError = "";
+
+int own_error(const char* msg) {
+  g_lastEngine = 2;
+  g_ownError = msg;
+  return B200SEED_ERR_INVALID_ARGUMENT;
+}
+
+}  // namespace
+
+// forward a call to the engine of the handle
+#define B200SEED_FORWARD(h, call_exact, call_relaxed)                \
+  do {                                                               \
+    if ((h) == nullptr) return own_error("NULL handle");             \
+    if ((h)->relaxed != nullptr) {                                   \
+      g_lastEngine = 1;                                              \
+      return call_relaxed;                                           \
+    }                                                                \
+    g_lastEngine = 0;                                                \
+    return call_exact;                                               \
+  } while (0)
+
+extern "C" {
+
+const char* b200seed_last_error(void) {
+  if (g_lastEngine == 2) return g_ownError;
+  return g_lastEngine == 1 ? b200rx_last_error() : b200ex_last_error();
+}
+
+int b200seed_config_init(b200seed_config* cfg) {
+  g_lastEngine = 0;
+  return b200ex_config_init(cfg);
+}
+
+int b200seed_plan_info(const b200seed_config* cfg, b200seed_info* info) {
+  g_lastEngine = 0;
+  return b200ex_plan_info(cfg, info);
+}
+
+int b200seed_plan_tables(const b200seed_config* cfg, void* deviceConfig, uint64_t deviceConfigBytes,
+                         uint32_t* navBins, uint32_t* botOffsets, uint32_t* botBins, uint32_t* topOffsets,
+                         uint32_t* topBins, uint64_t* sizes) {
+  g_lastEngine = 0;
+  return b200ex_plan_tables(cfg, deviceConfig, deviceConfigBytes, navBins, botOffsets, botBins, topOffsets, topBins, sizes);
+}
+
+int b200seed_create(const b200seed_config* cfg, int device, b200seed_handle** out) {
+  if (cfg == nullptr || out == nullptr) return own_error("NULL argument");
+  *out = nullptr;
+  b200seed_handle* h = new (std::nothrow) b200seed_handle;
+  if (h == nullptr) return own_error("out of memory");
+  int rc;
+  // struct_size / abi_version are validated by the engine; relaxedFloat is the last member of the struct
+  const bool relaxed = cfg->struct_size == sizeof(b200seed_config) && cfg->relaxedFloat != 0;
+  if (relaxed) {
+    g_lastEngine = 1;
+    rc = b200rx_create(cfg, device, &h->relaxed);
+  } else {
+    g_lastEngine = 0;
+    rc = b200ex_create(cfg, device, &h->exact);
+  }
+  if (rc != B200SEED_OK) {
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return B200SEED_OK;
+}
+
+void b200seed_destroy(b200seed_handle* h) {
+  if (h == nullptr) return;
+  if (h->exact != nullptr) b200ex_destroy(h->exact);
+  if (h->relaxed != nullptr) b200rx_destroy(h->relaxed);
+  delete h;
+}
+
+int b200seed_get_info(const b200seed_handle* h, b200seed_info* info) {
+  B200SEED_FORWARD(h, b200ex_get_info(h->exact, info), b200rx_get_info(h->relaxed, info));
+}
+
+int b200seed_get_counters(const b200seed_handle* h, b200seed_counters* c) {
+  B200SEED_FORWARD(h, b200ex_get_counters(h->exact, c), b200rx_get_counters(h->relaxed, c));
+}
+
+int b200seed_run(b200seed_handle* h, uint32_t n, const float* x, const float* y, const float* z, const float* r,
+                 const float* varZ, const float* varR, uint32_t nZWindows, const float* zWindowLo,
+                 const float* zWindowHi, b200seed_seeds* out) {
+  B200SEED_FORWARD(h, b200ex_run(h->exact, n, x, y, z, r, varZ, varR, nZWindows, zWindowLo, zWindowHi, out),
+                   b200rx_run(h->relaxed, n, x, y, z, r, varZ, varR, nZWindows, zWindowLo, zWindowHi, out));
+}
+
+int b200seed_run_with_phi(b200seed_handle* h, uint32_t n, const float* x, const float* y, const float* z,
+                          const float* r, const float* varZ, const float* varR, const float* phi,
+                          b200seed_seeds* out) {
+  B200SEED_FORWARD(h, b200ex_run_with_phi(h->exact, n, x, y, z, r, varZ, varR, phi, out),
+                   b200rx_run_with_phi(h->relaxed, n, x, y, z, r, varZ, varR, phi, out));
+}
+
+int b200seed_run_batch(b200seed_handle* h, uint32_t nEvents, const uint32_t* spOffsets, const float* x,
+                       const float* y, const float* z, const float* r, const float* varZ, const float* varR,
+                       uint64_t* seedOffsets, b200seed_seeds* out) {
+  B200SEED_FORWARD(h, b200ex_run_batch(h->exact, nEvents, spOffsets, x, y, z, r, varZ, varR, seedOffsets, out),
+                   b200rx_run_batch(h->relaxed, nEvents, spOffsets, x, y, z, r, varZ, varR, seedOffsets, out));
+}
+
+int b200seed_run_batch_device(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal, const uint32_t* spOffsets,
+                              const float* x, const float* y, const float* z, const float* r, const float* varZ,
+                              const float* varR, uint64_t* seedOffsets, b200seed_seeds* out, void* cudaStream) {
+  B200SEED_FORWARD(
+      h, b200ex_run_batch_device(h->exact, nEvents, nTotal, spOffsets, x, y, z, r, varZ, varR, seedOffsets, out, cudaStream),
+      b200rx_run_batch_device(h->relaxed, nEvents, nTotal, spOffsets, x, y, z, r, varZ, varR, seedOffsets, out, cudaStream));
+}
+
+int b200seed_sync(b200seed_handle* h, b200seed_seeds* out) {
+  B200SEED_FORWARD(h, b200ex_sync(h->exact, out), b200rx_sync(h->relaxed, out));
+}
+
+int b200seed_set_phi_sector(b200seed_handle* h, uint32_t firstPhiBin, uint32_t nPhiBins) {
+  B200SEED_FORWARD(h, b200ex_set_phi_sector(h->exact, firstPhiBin, nPhiBins),
+                   b200rx_set_phi_sector(h->relaxed, firstPhiBin, nPhiBins));
+}
+
+int b200seed_get_stage_times(const b200seed_handle* h, float* ms) {
+  B200SEED_FORWARD(h, b200ex_get_stage_times(h->exact, ms), b200rx_get_stage_times(h->relaxed, ms));
+}
+
+int b200seed_estimate_params(b200seed_handle* h, uint64_t nSeeds, const uint32_t* bottom, const uint32_t* middle,
+                             const uint32_t* top, uint32_t nSpacePoints, const float* x, const float* y,
+                             const float* z, const double* bField, double* freeParams) {
+  B200SEED_FORWARD(
+      h, b200ex_estimate_params(h->exact, nSeeds, bottom, middle, top, nSpacePoints, x, y, z, bField, freeParams),
+      b200rx_estimate_params(h->relaxed, nSeeds, bottom, middle, top, nSpacePoints, x, y, z, bField, freeParams));
+}
+
+int b200seed_debug_grid(b200seed_handle* h, uint64_t capacity, uint32_t* copiedFromIndex, float* x, float* y,
+                        float* z, float* r, float* varZ, float* varR, uint64_t binCapacity, uint32_t* binBegin,
+                        uint32_t* binEnd) {
+  B200SEED_FORWARD(
+      h, b200ex_debug_grid(h->exact, capacity, copiedFromIndex, x, y, z, r, varZ, varR, binCapacity, binBegin, binEnd),
+      b200rx_debug_grid(h->relaxed, capacity, copiedFromIndex, x, y, z, r, varZ, varR, binCapacity, binBegin, binEnd));
+}
+
+int b200seed_debug_doublets(b200seed_handle* h, b200seed_doublets* out) {
+  B200SEED_FORWARD(h, b200ex_debug_doublets(h->exact, out), b200rx_debug_doublets(h->relaxed, out));
+}
+
+int b200seed_debug_atan2f(b200seed_handle* h, uint64_t n, const float* y, const float* x, float* phi) {
+  B200SEED_FORWARD(h, b200ex_debug_atan2f(h->exact, n, y, x, phi), b200rx_debug_atan2f(h->relaxed, n, y, x, phi));
+}
+
+}  // extern "C"

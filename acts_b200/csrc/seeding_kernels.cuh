@@ -25,7 +25,7 @@
 
 #include "seed_math.h"
 
-namespace b200seed {
+namespace B200SEED_NS {
 
 constexpr uint32_t kInvalidBin = 0xFFFFFFFFu;
 constexpr int kSortThreads = 256;
@@ -334,7 +334,11 @@ __global__ void __launch_bounds__(256) k_bin_count(const __grid_constant__ GridP
     const float x = __ldg(p.x + i), y = __ldg(p.y + i), z = __ldg(p.z + i), r = __ldg(p.r + i);
     int32_t bin = -1;
     if (!(p.cfg.useExtraCuts && !itk_sp_select(r, z))) {
+#ifdef B200SEED_RELAXED
+      const float phi = p.phi != nullptr ? __ldg(p.phi + i) : atan2f(y, x);  // CUDA libm, not glibc's rounding
+#else
       const float phi = p.phi != nullptr ? __ldg(p.phi + i) : glibc_atan2f(y, x);
+#endif
       bin = grid_bin_index(p.cfg, phi, z, r);
     }
     uint32_t gb = kInvalidBin;
@@ -2015,4 +2019,4 @@ __global__ void k_atan2f(const float* __restrict__ y, const float* __restrict__ 
   }
 }
 
-}  // namespace b200seed
+}  // namespace B200SEED_NS

@@ -17,7 +17,7 @@
 #include "host_plan.hpp"
 #include "seeding_kernels.cuh"
 
-using namespace b200seed;
+using namespace B200SEED_NS;
 
 namespace {
 
@@ -558,9 +558,14 @@ int b200seed_create(const b200seed_config* cfg, int device, b200seed_handle** ou
     delete h;
     return fail(err.code, err.message);
   }
-  if (h->plan.relaxedFloat) {
+#ifdef B200SEED_RELAXED
+  const bool engineRelaxed = true;
+#else
+  const bool engineRelaxed = false;
+#endif
+  if (h->plan.relaxedFloat != engineRelaxed) {  // seeding_abi.cpp picks the engine by cfg->relaxedFloat
     delete h;
-    return fail(B200SEED_ERR_UNSUPPORTED, "relaxedFloat fast path is not built yet; only the exact binary32 path exists");
+    return fail(B200SEED_ERR_INVALID_ARGUMENT, "relaxedFloat does not match the engine this handle was routed to");
   }
   int nDev = 0;
   cudaError_t ce = cudaGetDeviceCount(&nDev);
@@ -599,7 +604,8 @@ int b200seed_create(const b200seed_config* cfg, int device, b200seed_handle** ou
   CREATE_TRY(cudaMallocHost(&h->hStatus, 16));
   CREATE_TRY(cudaMallocHost(&h->hSeedTotal, 16));
 
-  h->exactTies = (int)env_u32("B200SEED_EXACT_TIES", 1);
+  // the tie-order replay of the unstable sorts only makes sense when the keys are the reference's bit for bit
+  h->exactTies = engineRelaxed ? 0 : (int)env_u32("B200SEED_EXACT_TIES", 1);
   {
     auto setupTier = [&](int t, auto kernel, int threads, size_t bytes) -> cudaError_t {
       h->seedSmemBytes[t] = bytes;

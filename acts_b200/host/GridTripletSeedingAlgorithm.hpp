@@ -115,6 +115,8 @@ class GridTripletSeedingAlgorithm final {
     bool useExtraCuts = false;
     /// engine option: CUDA device ordinal
     int device = 0;
+    /// engine option: float fast path (FMA contraction, approximate division); seeds not guaranteed identical
+    bool relaxedFloat = false;
   };
 
   explicit GridTripletSeedingAlgorithm(const Config& cfg) : m_cfg(cfg) {
@@ -156,6 +158,7 @@ class GridTripletSeedingAlgorithm final {
     copyRange(cfg.forwardSeedConfirmationRange, c.forwardSeedConfirmationRange);
     c.maxSeedsPerSpMConf = cfg.maxSeedsPerSpMConf; c.maxQualitySeedsPerSpMConf = cfg.maxQualitySeedsPerSpMConf;
     c.useDeltaRinsteadOfTopRadius = cfg.useDeltaRinsteadOfTopRadius; c.useExtraCuts = cfg.useExtraCuts;
+    c.relaxedFloat = cfg.relaxedFloat;
     check(b200seed_create(&c, cfg.device, &m_handle));
   }
   ~GridTripletSeedingAlgorithm() { b200seed_destroy(m_handle); }

@@ -442,3 +442,27 @@ def test_csv_replay_round_trip(plugin, O, tmp_path):
         assert np.array_equal(got["bottom"], ref["bottom"]) and np.array_equal(got["top"], ref["top"])
         assert np.array_equal(got["quality"].view(np.uint32), ref["quality"].view(np.uint32))
         assert np.all(got["pT"] > 0)
+
+
+def test_relaxed_float_fast_path_is_close_but_separate(plugin, O):
+    """relaxedFloat = 1 routes to the second engine of the library: almost the same seeds (reported as a
+    seed-efficiency delta by bench.py), never claimed exact; the exact engine is untouched by it."""
+    from acts_b200 import events
+
+    cfg = make_config("pu200", plugin.config_init)
+    cfg.relaxedFloat = 1
+    fast = plugin.SeedingEngine(cfg)
+    exact = plugin.SeedingEngine(make_config("pu200", plugin.config_init))
+    orc = O.Oracle(make_config("pu200", O.config_init))
+    for i, mu in ((0, 20), (1, 60)):
+        ev = events.pileup_event(i, mu=mu)
+        ref = orc.run(ev)
+        got = fast.run(ev)
+        ka, kb = set(O.seed_set(ref)), set(O.seed_set(got))
+        eff = len(ka & kb) / len(ka)
+        fake = len(kb - ka) / len(kb)
+        assert eff > 0.995 and fake < 0.005, (eff, fake)
+        assert _same_bits(exact.run(ev), ref)
+    assert fast.counters()["nKernelLaunches"] > 0
+    fast.close()
+    exact.close()

@@ -8,12 +8,15 @@ import subprocess
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from acts_b200.build import CSRC, NVCC_FLAGS, ROOT  # noqa: E402
+from acts_b200 import build  # noqa: E402
 
 name, flags = sys.argv[1], sys.argv[2:]
-out = os.path.join(ROOT, "acts_b200", "variants", name + ".so")
+out = os.path.join(build.ROOT, "acts_b200", "variants", name + ".so")
 os.makedirs(os.path.dirname(out), exist_ok=True)
-cmd = ["nvcc", *NVCC_FLAGS, *flags, "-Xptxas", "-warn-spills", "-o", out,
-       os.path.join(CSRC, "seeding_plugin.cu"), os.path.join(CSRC, "host_plan.cpp")]
-subprocess.run(cmd, check=True)
+build.OBJ_DIR = os.path.join(build.ROOT, "build", "obj_" + name)
+cmds = build.engine_compile_commands(extra=flags)
+procs = [subprocess.Popen(cmd) for _, cmd in cmds]
+if any(p.wait() != 0 for p in procs):
+    sys.exit("compile failed")
+subprocess.run(["nvcc", *build.COMMON_FLAGS, "-shared", "-o", out, *[obj for obj, _ in cmds]], check=True)
 print(out)
