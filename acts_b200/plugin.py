@@ -199,13 +199,23 @@ class SeedingEngine:
         k = int(s.size)
         return {name: arr[:k] for name, arr in out.items()}
 
-    def run_batch(self, cols: dict, offsets: np.ndarray, capacity=None) -> list[dict]:
-        """A batch of events through ``b200seed_run_batch``; returns one dict per event."""
+    def run_batch(self, cols: dict, offsets: np.ndarray, capacity=None, out=None) -> list[dict]:
+        """A batch of events through ``b200seed_run_batch``; returns one dict per event.
+
+        ``out`` may hold caller-owned (e.g. pinned) seed columns ``bottom/middle/top`` (uint32) and
+        ``quality/vertexZ`` (float32) that are reused from call to call."""
         arrs = self._cols(cols)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
         n_events = offsets.size - 1
         cap = capacity if capacity is not None else max(16, int(offsets[-1]) * 6)
-        out, s = self._alloc(cap)
+        if out is not None:
+            cap = min(int(a.size) for a in out.values())
+            s = Seeds()
+            s.bottom, s.middle, s.top = _p(out["bottom"]), _p(out["middle"]), _p(out["top"])
+            s.quality, s.vertexZ = _p(out["quality"]), _p(out["vertexZ"])
+            s.capacity = cap
+        else:
+            out, s = self._alloc(cap)
         seed_offsets = np.zeros(n_events + 1, dtype=np.uint64)
         _check(lib().b200seed_run_batch(self._h, n_events, _p(offsets), *[_p(a) for a in arrs], _p(seed_offsets), C.byref(s)))
         res = []
