@@ -851,6 +851,34 @@ B2S_HD void estimate_free_params(const double sp0[3], double t0, const double sp
   out[7] = qOverPt / sqrt(1.0 + dzds * dzds);
 }
 
+// ---------------------------------------------------------------------------
+// Pixel space point from one measurement on a planar surface ("next" row f4):
+// createPixelSpacePoint (Examples/Algorithms/TrackFinding/src/SpacePointMaker.cpp:44-76),
+// PlaneSurface::localToGlobal (Core/src/Surfaces/PlaneSurface.cpp:72-75),
+// Surface::referenceFrame (Core/src/Surfaces/Surface.cpp:243-247) and
+// PixelSpacePointBuilder::computeCovarianceZR (Core/src/SpacePointFormation/PixelSpacePointBuilder.cpp:17-42).
+// T is the row-major 3x4 affine local->global transform of the surface; the six outputs are the
+// float columns of the SpacePointContainer.  FP64 like the reference (Eigen), rounded to float at the end.
+// ---------------------------------------------------------------------------
+B2S_HD void pixel_space_point(const double T[12], double loc0, double loc1, double c00, double c01, double c11,
+                              float out[6]) {
+  // global = linear * (loc0, loc1, 0) + translation
+  const double gx = T[0] * loc0 + T[1] * loc1 + T[3];
+  const double gy = T[4] * loc0 + T[5] * loc1 + T[7];
+  const double gz = T[8] * loc0 + T[9] * loc1 + T[11];
+  const double rr = sqrt(gx * gx + gy * gy);  // fastHypot, MathHelpers.hpp:93-96
+  const double scale = 1 / rr;
+  // jacXyzToZr = [[0, 0, 1], [scale x, scale y, 0]];  jac = jacXyzToZr * rot.topLeftCorner<3, 2>()
+  const double jx = scale * gx, jy = scale * gy;
+  const double j00 = T[8], j01 = T[9];
+  const double j10 = jx * T[0] + jy * T[4], j11 = jx * T[1] + jy * T[5];
+  // diag(jac * cov * jac^T)
+  const double varZ = j00 * (c00 * j00 + c01 * j01) + j01 * (c01 * j00 + c11 * j01);
+  const double varR = j10 * (c00 * j10 + c01 * j11) + j11 * (c01 * j10 + c11 * j11);
+  out[0] = (float)gx; out[1] = (float)gy; out[2] = (float)gz; out[3] = (float)rr;
+  out[4] = (float)varZ; out[5] = (float)varR;
+}
+
 // Monotone (non-decreasing in the key) bucket of a cot(theta) key for the
 // in-block bucket sort.  Keys are expected inside [-cotThetaMax, cotThetaMax]
 // but any value is clamped.

@@ -38,6 +38,9 @@ extern "C" {
   int P##get_stage_times(const P##handle*, float*);                                                         \
   int P##estimate_params(P##handle*, uint64_t, const uint32_t*, const uint32_t*, const uint32_t*, uint32_t, \
                          const float*, const float*, const float*, const double*, double*);                 \
+  int P##make_pixel_spacepoints(P##handle*, uint32_t, const uint32_t*, const double*, const double*,        \
+                                const double*, const double*, const double*, uint32_t, const double*,       \
+                                float*, float*, float*, float*, float*, float*);                            \
   int P##debug_grid(P##handle*, uint64_t, uint32_t*, float*, float*, float*, float*, float*, float*,        \
                     uint64_t, uint32_t*, uint32_t*);                                                        \
   int P##debug_doublets(P##handle*, b200seed_doublets*);                                                    \
@@ -188,6 +191,17 @@ int b200seed_estimate_params(b200seed_handle* h, uint64_t nSeeds, const uint32_t
   B200SEED_FORWARD(
       h, b200ex_estimate_params(h->exact, nSeeds, bottom, middle, top, nSpacePoints, x, y, z, bField, freeParams),
       b200rx_estimate_params(h->relaxed, nSeeds, bottom, middle, top, nSpacePoints, x, y, z, bField, freeParams));
+}
+
+int b200seed_make_pixel_spacepoints(b200seed_handle* h, uint32_t n, const uint32_t* surface, const double* loc0,
+                                    const double* loc1, const double* cov00, const double* cov01, const double* cov11,
+                                    uint32_t nSurfaces, const double* transforms, float* x, float* y, float* z,
+                                    float* r, float* varZ, float* varR) {
+  B200SEED_FORWARD(h,
+                   b200ex_make_pixel_spacepoints(h->exact, n, surface, loc0, loc1, cov00, cov01, cov11, nSurfaces,
+                                                 transforms, x, y, z, r, varZ, varR),
+                   b200rx_make_pixel_spacepoints(h->relaxed, n, surface, loc0, loc1, cov00, cov01, cov11, nSurfaces,
+                                                 transforms, x, y, z, r, varZ, varR));
 }
 
 int b200seed_debug_grid(b200seed_handle* h, uint64_t capacity, uint32_t* copiedFromIndex, float* x, float* y,

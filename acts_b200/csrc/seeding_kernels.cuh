@@ -2012,6 +2012,31 @@ __global__ void __launch_bounds__(256) k_estimate_params(const uint32_t* __restr
   }
 }
 
+// Pixel space points from measurements (SpacePointMaker.cpp:44-76), FP64, one thread per measurement
+struct SpacePointMakerParams {
+  const uint32_t* surface;  // [n] index into transforms
+  const double *loc0, *loc1, *cov00, *cov01, *cov11;
+  const double* transforms;  // [nSurfaces][12] row-major 3x4
+  float *x, *y, *z, *r, *varZ, *varR;
+  uint32_t n, nSurfaces;
+  int* status;
+};
+__global__ void __launch_bounds__(256) k_pixel_spacepoints(const __grid_constant__ SpacePointMakerParams p) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += gridDim.x * blockDim.x) {
+    const uint32_t sf = p.surface[i];
+    if (sf >= p.nSurfaces) {
+      atomicOr(p.status, 1);
+      continue;
+    }
+    double T[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) T[k] = __ldg(p.transforms + (size_t)sf * 12 + k);
+    float o[6];
+    pixel_space_point(T, p.loc0[i], p.loc1[i], p.cov00[i], p.cov01[i], p.cov11[i], o);
+    p.x[i] = o[0]; p.y[i] = o[1]; p.z[i] = o[2]; p.r[i] = o[3]; p.varZ[i] = o[4]; p.varR[i] = o[5];
+  }
+}
+
 // phi = atan2f(y, x) replay, for validation against the host libm
 __global__ void k_atan2f(const float* __restrict__ y, const float* __restrict__ x, float* __restrict__ out, unsigned long long n) {
   for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {

@@ -1008,6 +1008,58 @@ int b200seed_estimate_params(b200seed_handle* h, uint64_t nSeeds, const uint32_t
   return B200SEED_OK;
 }
 
+int b200seed_make_pixel_spacepoints(b200seed_handle* h, uint32_t n, const uint32_t* surface, const double* loc0,
+                                    const double* loc1, const double* cov00, const double* cov01, const double* cov11,
+                                    uint32_t nSurfaces, const double* transforms, float* x, float* y, float* z,
+                                    float* r, float* varZ, float* varR) {
+  if (h == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL handle");
+  if (n == 0) return B200SEED_OK;
+  const double* dcol[5] = {loc0, loc1, cov00, cov01, cov11};
+  float* ocol[6] = {x, y, z, r, varZ, varR};
+  for (const double* c : dcol) if (c == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL measurement column");
+  for (float* c : ocol) if (c == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL space point column");
+  if (surface == nullptr || transforms == nullptr || nSurfaces == 0) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL / empty surface table");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  DevBuf dsurf, din[5], dtr, dout[6], dstat;
+  struct Guard {
+    std::vector<DevBuf*> bufs;
+    ~Guard() { for (DevBuf* b : bufs) b->release(); }
+  } guard;
+  guard.bufs = {&dsurf, &dtr, &dstat};
+  for (DevBuf& b : din) guard.bufs.push_back(&b);
+  for (DevBuf& b : dout) guard.bufs.push_back(&b);
+  CUDA_TRY(dsurf.reserve((size_t)n * 4));
+  CUDA_TRY(cudaMemcpyAsync(dsurf.ptr, surface, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  for (int k = 0; k < 5; ++k) {
+    CUDA_TRY(din[k].reserve((size_t)n * 8));
+    CUDA_TRY(cudaMemcpyAsync(din[k].ptr, dcol[k], (size_t)n * 8, cudaMemcpyHostToDevice, s));
+  }
+  CUDA_TRY(dtr.reserve((size_t)nSurfaces * 96));
+  CUDA_TRY(cudaMemcpyAsync(dtr.ptr, transforms, (size_t)nSurfaces * 96, cudaMemcpyHostToDevice, s));
+  for (DevBuf& b : dout) CUDA_TRY(b.reserve((size_t)n * 4));
+  CUDA_TRY(dstat.reserve(16));
+  CUDA_TRY(cudaMemsetAsync(dstat.ptr, 0, 16, s));
+  SpacePointMakerParams mp{};
+  mp.surface = dsurf.as<uint32_t>();
+  mp.loc0 = din[0].as<double>(); mp.loc1 = din[1].as<double>();
+  mp.cov00 = din[2].as<double>(); mp.cov01 = din[3].as<double>(); mp.cov11 = din[4].as<double>();
+  mp.transforms = dtr.as<double>();
+  mp.x = dout[0].as<float>(); mp.y = dout[1].as<float>(); mp.z = dout[2].as<float>(); mp.r = dout[3].as<float>();
+  mp.varZ = dout[4].as<float>(); mp.varR = dout[5].as<float>();
+  mp.n = n; mp.nSurfaces = nSurfaces;
+  mp.status = dstat.as<int>();
+  const int blocks = (int)std::min<uint64_t>(((uint64_t)n + 255) / 256, (uint64_t)h->smCount * 8);
+  k_pixel_spacepoints<<<blocks, 256, 0, s>>>(mp);
+  CUDA_TRY(cudaGetLastError());
+  for (int k = 0; k < 6; ++k) CUDA_TRY(cudaMemcpyAsync(ocol[k], dout[k].ptr, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  int st = 0;
+  CUDA_TRY(cudaMemcpyAsync(&st, dstat.ptr, 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (st != 0) return fail(B200SEED_ERR_INVALID_ARGUMENT, "surface index out of range");
+  return B200SEED_OK;
+}
+
 int b200seed_debug_atan2f(b200seed_handle* h, uint64_t n, const float* y, const float* x, float* phi) {
   if (h == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL handle");
   if (n == 0) return B200SEED_OK;

@@ -140,3 +140,48 @@ def concat_events(events: list[dict]) -> tuple[dict, np.ndarray]:
         offsets[i + 1] = offsets[i] + e["x"].size
     cols = {k: np.ascontiguousarray(np.concatenate([e[k] for e in events])) for k in ("x", "y", "z", "r", "varZ", "varR")}
     return cols, offsets
+
+
+def pixel_measurements(event: int, n: int = 20000, seed: int = 42) -> tuple[dict, np.ndarray]:
+    """Synthetic pixel measurements on generic-detector-like planar modules (input of the f4 space point maker).
+
+    Barrel modules are planes tangent to the cylinders r = {32, 72, 116, 172} mm, tilted by 0.14 rad around the
+    z axis (GenericDetectorBuilder.cpp:328-335); endcap modules are planes perpendicular to z at
+    |z| = {600, 700, 820, 960} mm.  Local frame: x along the measurement (r-phi) direction, y along z (barrel) or r
+    (endcap).  Returns (measurements, transforms): surface index, local position (float64), local covariance
+    (pitch^2/12 on the diagonal, a small correlation so that every covariance term is exercised), and the
+    (nSurfaces, 3, 4) local->global affine matrices.
+    """
+    rng = np.random.default_rng(seed + 7919 * event + 13)
+    transforms = []
+    for rl in (32.0, 72.0, 116.0, 172.0):
+        n_phi = int(2 * np.pi * rl / 14.0)
+        for k in range(n_phi):
+            phi = 2 * np.pi * k / n_phi
+            for zc in np.arange(-468.0, 469.0, 72.0):
+                normal_phi = phi + 0.14
+                ux = np.array([-np.sin(normal_phi), np.cos(normal_phi), 0.0])  # local x
+                uy = np.array([0.0, 0.0, 1.0])                                  # local y
+                uz = np.cross(ux, uy)
+                centre = np.array([rl * np.cos(phi), rl * np.sin(phi), zc])
+                transforms.append(np.column_stack([ux, uy, uz, centre]))
+    for zd in (600.0, 700.0, 820.0, 960.0):
+        for sign in (-1.0, 1.0):
+            for k in range(40):
+                phi = 2 * np.pi * k / 40
+                for rc in (60.0, 130.0):
+                    ux = np.array([-np.sin(phi), np.cos(phi), 0.0])
+                    uy = np.array([np.cos(phi), np.sin(phi), 0.0])
+                    uz = np.cross(ux, uy) * sign
+                    centre = np.array([rc * np.cos(phi), rc * np.sin(phi), sign * zd])
+                    transforms.append(np.column_stack([ux, sign * uy, uz, centre]))
+    transforms = np.ascontiguousarray(np.stack(transforms), dtype=np.float64)
+    ns = transforms.shape[0]
+    surface = rng.integers(0, ns, n).astype(np.uint32)
+    loc0 = rng.uniform(-8.4, 8.4, n)
+    loc1 = rng.uniform(-36.0, 36.0, n)
+    var = 0.0144338 ** 2 * rng.uniform(0.5, 4.0, (n, 2))
+    rho = rng.uniform(-0.3, 0.3, n)
+    meas = {"surface": surface, "loc0": loc0, "loc1": loc1, "cov00": var[:, 0], "cov11": var[:, 1],
+            "cov01": rho * np.sqrt(var[:, 0] * var[:, 1])}
+    return meas, transforms

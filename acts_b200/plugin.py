@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = [
     "b200seed_config_init", "b200seed_plan_info", "b200seed_plan_tables", "b200seed_create",
     "b200seed_destroy", "b200seed_last_error", "b200seed_get_info", "b200seed_get_counters",
     "b200seed_get_stage_times", "b200seed_set_phi_sector", "b200seed_estimate_params",
+    "b200seed_make_pixel_spacepoints",
     "b200seed_run", "b200seed_run_with_phi", "b200seed_run_batch", "b200seed_run_batch_device",
     "b200seed_sync", "b200seed_debug_grid", "b200seed_debug_doublets", "b200seed_debug_atan2f",
 ]
@@ -58,6 +59,7 @@ def lib():
         L.b200seed_get_stage_times.argtypes = [vp, vp]
         L.b200seed_set_phi_sector.argtypes = [vp, u32, u32]
         L.b200seed_estimate_params.argtypes = [vp, u64, vp, vp, vp, u32, vp, vp, vp, vp, vp]
+        L.b200seed_make_pixel_spacepoints.argtypes = [vp, u32] + [vp] * 6 + [u32] + [vp] * 7
         L.b200seed_run.argtypes = [vp, u32] + [f32p] * 6 + [u32, f32p, f32p, C.POINTER(Seeds)]
         L.b200seed_run_with_phi.argtypes = [vp, u32] + [f32p] * 7 + [C.POINTER(Seeds)]
         L.b200seed_run_batch.argtypes = [vp, u32, vp] + [f32p] * 6 + [vp, C.POINTER(Seeds)]
@@ -154,6 +156,19 @@ class SeedingEngine:
         bf = np.ascontiguousarray(b_field, dtype=np.float64)
         out = np.zeros((n, 8), dtype=np.float64)
         _check(lib().b200seed_estimate_params(self._h, n, *[_p(a) for a in idx], cols[0].size, *[_p(c) for c in cols], _p(bf), _p(out)))
+        return out
+
+    def make_pixel_spacepoints(self, meas: dict, transforms: np.ndarray) -> dict:
+        """Measurements on planar surfaces -> the six space-point columns: ``b200seed_make_pixel_spacepoints``.
+
+        ``meas``: surface (uint32), loc0, loc1, cov00, cov01, cov11 (float64); ``transforms``: (nSurfaces, 3, 4)."""
+        n = int(meas["surface"].size)
+        sf = np.ascontiguousarray(meas["surface"], dtype=np.uint32)
+        cols = [np.ascontiguousarray(meas[k], dtype=np.float64) for k in ("loc0", "loc1", "cov00", "cov01", "cov11")]
+        tr = np.ascontiguousarray(transforms, dtype=np.float64).reshape(-1, 12)
+        out = {k: np.zeros(n, np.float32) for k in ("x", "y", "z", "r", "varZ", "varR")}
+        _check(lib().b200seed_make_pixel_spacepoints(self._h, n, _p(sf), *[_p(c) for c in cols], tr.shape[0], _p(tr),
+                                                     *[_p(out[k]) for k in ("x", "y", "z", "r", "varZ", "varR")]))
         return out
 
     def stage_times_ms(self) -> dict:

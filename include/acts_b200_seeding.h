@@ -305,6 +305,22 @@ int b200seed_estimate_params(b200seed_handle* h, uint64_t nSeeds, const uint32_t
                              const float* x, const float* y, const float* z, const double* bField,
                              double* freeParams);
 
+/* "Next" row f4: pixel space points from measurements, FP64 on the
+ * device.  Replaces createPixelSpacePoint of the upstream SpacePointMaker
+ * (Examples/Algorithms/TrackFinding/src/SpacePointMaker.cpp:44-76): global position
+ * PlaneSurface::localToGlobal (Core/src/Surfaces/PlaneSurface.cpp:72-75), r = fastHypot(x, y),
+ * (varZ, varR) = diag of PixelSpacePointBuilder::computeCovarianceZR
+ * (Core/src/SpacePointFormation/PixelSpacePointBuilder.cpp:17-42).  Measurement i lies on
+ * surface[i]; transforms holds nSurfaces row-major 3x4 affine local->global matrices
+ * (rotation | translation) of planar surfaces; (loc0, loc1) and (cov00, cov01, cov11) are the
+ * local position and covariance of the measurement.  The six outputs are the float columns
+ * b200seed_run takes.  All pointers are host memory. */
+int b200seed_make_pixel_spacepoints(b200seed_handle* h, uint32_t n, const uint32_t* surface,
+                                    const double* loc0, const double* loc1, const double* cov00,
+                                    const double* cov01, const double* cov11, uint32_t nSurfaces,
+                                    const double* transforms, float* x, float* y, float* z,
+                                    float* r, float* varZ, float* varR);
+
 /* ---- stage-level introspection (parity tests of the grid / doublet stages) */
 
 /* After a run: the packed, bin-ordered, r-sorted space point copy of the LAST

@@ -77,6 +77,8 @@ def lib():
         L.oracle_result_dump_doublets.restype = C.c_uint64
         L.oracle_result_dump.argtypes = [C.c_void_p] * 12
         L.oracle_estimate_params.argtypes = [C.c_uint64] + [C.c_void_p] * 8
+        L.oracle_make_pixel_spacepoints.argtypes = [C.c_uint32] + [C.c_void_p] * 6 + [C.c_uint32] + [C.c_void_p] * 7
+        L.oracle_make_pixel_spacepoints.restype = C.c_int
         L.oracle_run_many.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 7 + [C.c_int, C.c_uint32, C.c_void_p]
         L.oracle_run_many.restype = C.c_int64
         _lib = L
@@ -211,6 +213,22 @@ def estimate_params(seeds: dict, ev: dict, b_field=(0.0, 0.0, 2 * 0.000299792458
     bf = np.ascontiguousarray(b_field, dtype=np.float64)
     out = np.zeros((n, 8), dtype=np.float64)
     lib().oracle_estimate_params(n, *[_p(a) for a in idx], *[_p(c) for c in cols], _p(bf), _p(out))
+    return out
+
+
+def make_pixel_spacepoints(meas: dict, transforms: np.ndarray) -> dict:
+    """Reference arithmetic of SpacePointMaker's createPixelSpacePoint for every measurement.
+
+    ``meas``: surface (uint32), loc0, loc1, cov00, cov01, cov11 (float64); ``transforms``: (nSurfaces, 3, 4)."""
+    n = int(meas["surface"].size)
+    sf = np.ascontiguousarray(meas["surface"], dtype=np.uint32)
+    cols = [np.ascontiguousarray(meas[k], dtype=np.float64) for k in ("loc0", "loc1", "cov00", "cov01", "cov11")]
+    tr = np.ascontiguousarray(transforms, dtype=np.float64).reshape(-1, 12)
+    out = {k: np.zeros(n, np.float32) for k in ("x", "y", "z", "r", "varZ", "varR")}
+    rc = lib().oracle_make_pixel_spacepoints(n, _p(sf), *[_p(c) for c in cols], tr.shape[0], _p(tr),
+                                             *[_p(out[k]) for k in ("x", "y", "z", "r", "varZ", "varR")])
+    if rc != 0:
+        raise ValueError("surface index out of range")
     return out
 
 

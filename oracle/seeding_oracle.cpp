@@ -1614,4 +1614,58 @@ std::int64_t oracle_run_many(const oracle_handle* h, std::uint32_t nEvents,
   return failed ? -1 : total.load();
 }
 
+// ---------------------------------------------------------------------------
+// Pixel space points from measurements ("next" row f4), restating
+// createPixelSpacePoint (Examples/Algorithms/TrackFinding/src/SpacePointMaker.cpp:44-76)
+// with the matrices written out the way the reference forms them:
+//   global   = transform * Vector3(loc0, loc1, 0)            PlaneSurface.cpp:72-75
+//   rot      = transform.matrix().block<3,3>(0,0)            Surface.cpp:243-247
+//   jacXyzToZr (2x3), jac = jacXyzToZr * rot.topLeftCorner<3,2>(), jac * localCov * jac^T
+//                                                            PixelSpacePointBuilder.cpp:17-42
+// transforms: row-major 3x4 per surface.  Returns -1 on a bad surface index.
+// ---------------------------------------------------------------------------
+int oracle_make_pixel_spacepoints(std::uint32_t n, const std::uint32_t* surface, const double* loc0,
+                                  const double* loc1, const double* cov00, const double* cov01,
+                                  const double* cov11, std::uint32_t nSurfaces, const double* transforms,
+                                  float* x, float* y, float* z, float* r, float* varZ, float* varR) {
+  for (std::uint32_t i = 0; i < n; ++i) {
+    if (surface[i] >= nSurfaces) return -1;
+    const double* T = transforms + static_cast<std::size_t>(surface[i]) * 12;
+    const double local3[3] = {loc0[i], loc1[i], 0.};
+    double global[3];
+    for (int a = 0; a < 3; ++a) {
+      double acc = 0;
+      for (int c = 0; c < 3; ++c) acc += T[a * 4 + c] * local3[c];
+      global[a] = acc + T[a * 4 + 3];
+    }
+    const double scale = 1 / std::sqrt(global[0] * global[0] + global[1] * global[1]);
+    double jacXyzToZr[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    jacXyzToZr[0][2] = 1;
+    jacXyzToZr[1][0] = scale * global[0];
+    jacXyzToZr[1][1] = scale * global[1];
+    double jac[2][2];
+    for (int a = 0; a < 2; ++a) {
+      for (int b = 0; b < 2; ++b) {
+        double acc = 0;
+        for (int k = 0; k < 3; ++k) acc += jacXyzToZr[a][k] * T[k * 4 + b];
+        jac[a][b] = acc;
+      }
+    }
+    const double C2[2][2] = {{cov00[i], cov01[i]}, {cov01[i], cov11[i]}};
+    double jc[2][2];
+    for (int a = 0; a < 2; ++a) {
+      for (int b = 0; b < 2; ++b) jc[a][b] = jac[a][0] * C2[0][b] + jac[a][1] * C2[1][b];
+    }
+    const double vz = jc[0][0] * jac[0][0] + jc[0][1] * jac[0][1];
+    const double vr = jc[1][0] * jac[1][0] + jc[1][1] * jac[1][1];
+    x[i] = static_cast<float>(global[0]);
+    y[i] = static_cast<float>(global[1]);
+    z[i] = static_cast<float>(global[2]);
+    r[i] = static_cast<float>(std::sqrt(global[0] * global[0] + global[1] * global[1]));
+    varZ[i] = static_cast<float>(vz);
+    varR[i] = static_cast<float>(vr);
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -466,3 +466,25 @@ def test_relaxed_float_fast_path_is_close_but_separate(plugin, O):
     assert fast.counters()["nKernelLaunches"] > 0
     fast.close()
     exact.close()
+
+
+def test_pixel_space_points_from_measurements(plugin, O):
+    """f4: SpacePointMaker's pixel path on the device (FP64) against the oracle's restatement; the float32 columns
+    are what the seeding consumes, so they are compared bit for bit (at most one float ulp where the two double
+    evaluation orders round differently) and then seeded."""
+    from acts_b200 import events
+
+    eng = plugin.SeedingEngine(make_config("pu200", plugin.config_init))
+    meas, tr = events.pixel_measurements(1, n=60000)
+    got = eng.make_pixel_spacepoints(meas, tr)
+    ref = O.make_pixel_spacepoints(meas, tr)
+    for k in ("x", "y", "z", "r", "varZ", "varR"):
+        assert np.all(np.abs(got[k] - ref[k]) <= np.spacing(np.abs(ref[k]))), k
+        assert np.mean(got[k].view(np.uint32) == ref[k].view(np.uint32)) > 0.999, k
+    bad = dict(meas, surface=np.full_like(meas["surface"], tr.shape[0]))
+    with pytest.raises(plugin.SeedingError):
+        eng.make_pixel_spacepoints(bad, tr)
+    # the columns feed the seeding call directly
+    orc = O.Oracle(make_config("pu200", O.config_init))
+    assert _same_bits(eng.run(got), orc.run(got))
+    eng.close()

@@ -207,3 +207,33 @@ def test_estimated_parameters_recover_the_generated_helix(O):
             qp_plus = par[7]
         else:
             assert qp_plus * par[7] < 0
+
+
+def test_pixel_space_point_maker_against_independent_float64(O):
+    """f4: createPixelSpacePoint (SpacePointMaker.cpp:44-76) restated in the oracle vs a numpy float64 evaluation
+    of the same formulas (global = T (l0, l1, 0, 1); J = d(z, r)/d(x, y, z) R[:, :2]; diag(J C J^T))."""
+    from acts_b200 import events
+
+    meas, tr = events.pixel_measurements(3, n=5000)
+    got = O.make_pixel_spacepoints(meas, tr)
+    T = tr[meas["surface"]]
+    loc = np.stack([meas["loc0"], meas["loc1"], np.zeros_like(meas["loc0"]), np.ones_like(meas["loc0"])], axis=1)
+    g = np.einsum("nij,nj->ni", T, loc)
+    rr = np.hypot(g[:, 0], g[:, 1])
+    J = np.zeros((g.shape[0], 2, 3))
+    J[:, 0, 2] = 1
+    J[:, 1, 0] = g[:, 0] / rr
+    J[:, 1, 1] = g[:, 1] / rr
+    jac = np.einsum("nak,nkb->nab", J, T[:, :, :2])
+    Cm = np.stack([np.stack([meas["cov00"], meas["cov01"]], 1), np.stack([meas["cov01"], meas["cov11"]], 1)], 1)
+    cov = np.einsum("nab,nbc,ndc->nad", jac, Cm, jac)
+    for k, ref in (("x", g[:, 0]), ("y", g[:, 1]), ("z", g[:, 2]), ("r", rr), ("varZ", cov[:, 0, 0]), ("varR", cov[:, 1, 1])):
+        r32 = ref.astype(np.float32)
+        assert np.all(np.abs(got[k] - r32) <= np.spacing(np.abs(r32))), k   # float32 columns: at most one ulp apart
+        assert np.mean(got[k] == r32) > 0.999, k
+    # barrel modules: varZ is the local-y variance, varR tiny (tilt only); a hand-checkable case
+    one = {"surface": np.array([0], np.uint32), "loc0": np.array([0.0]), "loc1": np.array([0.0]),
+           "cov00": np.array([4.0]), "cov01": np.array([0.0]), "cov11": np.array([9.0])}
+    sp = O.make_pixel_spacepoints(one, tr)
+    assert sp["varZ"][0] == 9.0 and abs(sp["varR"][0] - 4.0 * np.sin(0.14) ** 2) < 1e-6
+    assert abs(sp["r"][0] - 32.0) < 1e-5 and sp["z"][0] == -468.0
