@@ -185,6 +185,11 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device; the seeding path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # The contract is ONE JSON line on stdout, but NCCL writes its "NCCL version ..." banner to fd 1 when the first
+    # communicator is created: everything between here and the final print goes to stderr instead.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -441,7 +446,10 @@ def run_gpu(args):
         "counters_last_step": cnt,
         "seeds_last_step": int(n_seeds_last),
     }
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0
