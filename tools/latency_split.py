@@ -27,6 +27,7 @@ from acts_b200 import config, events, plugin, sharding  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--mu", type=float, default=300.0)
 ap.add_argument("--reps", type=int, default=10)
+ap.add_argument("--relaxed", action="store_true", help="the relaxedFloat engine (reported separately)")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1"))
 rank = int(os.environ.get("RANK", "0"))
@@ -35,6 +36,7 @@ torch.cuda.set_device(local)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 cfg = config.pu200_config(plugin.config_init)
+cfg.relaxedFloat = 1 if a.relaxed else 0
 eng = plugin.SeedingEngine(cfg, device=local)
 ev = events.pileup_event(0, mu=a.mu)
 
@@ -68,7 +70,7 @@ if world > 1:
 if rank == 0:
     cat = {k: np.concatenate([p[k] for p in parts]) for k in ("bottom", "middle", "top", "quality", "vertexZ")}
     same = all(np.array_equal(cat[k].view(np.uint32), full[k].view(np.uint32)) for k in cat)
-    print(json.dumps({"mode": "single-event phi-sector split", "mu": a.mu, "space_points": int(ev["x"].size),
+    print(json.dumps({"mode": "single-event phi-sector split", "engine": "relaxedFloat" if a.relaxed else "exact", "mu": a.mu, "space_points": int(ev["x"].size),
                       "n_gpus": world, "seeds": int(full["quality"].size), "split_equals_unsplit": bool(same),
                       "latency_ms_split": float(t[0]) * 1e3, "latency_ms_one_gpu": float(t[1]) * 1e3}))
 if world > 1:
