@@ -62,7 +62,7 @@ struct DevBuf {
 constexpr int kConfChangedBase = 8;
 constexpr int kConfMaxRounds = 1016;
 constexpr int kConfStateWords = kConfChangedBase + kConfMaxRounds;
-constexpr int kConfRoundsPerBatch = 12;  // rounds enqueued before the host looks at the convergence flags
+constexpr int kConfRoundsPerBatch = 12;  // default number of rounds enqueued before the host looks at the convergence flags
 
 uint32_t env_u32(const char* name, uint32_t def) {
   const char* v = std::getenv(name);
@@ -98,6 +98,8 @@ struct b200seed_handle {
   // seedConfirmation: candidate records, second slot set, per-space-point seed lists, {record counter, changed[round]}
   DevBuf rec, recZ, recBegin, recCount, slot2B, slot2M, slot2T, slot2Q, slot2Z, slot2Count, confHead, confNext, confState;
   uint32_t* hConfState = nullptr;  // pinned mirror of confState
+  int confRoundsPerBatch = kConfRoundsPerBatch;  // B200SEED_CONF_ROUNDS (tests exercise the continuation path with 2)
+  uint32_t recPerSpacePoint = 32;                // B200SEED_REC_PER_SP: first guess of the record pool
   size_t recCapacity = 0;
   int confRoundsLaunched = 0;
   ConfParams confParams{};
@@ -175,7 +177,7 @@ int ensure_workspace(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal) {
   CUDA_TRY(h->status.reserve(16));
   CUDA_TRY(h->zWin.reserve(2 * kMaxZWindows * 4));
   if (h->plan.dev.seedConfirmation) {
-    if (h->recCapacity < 32 * nT) h->recCapacity = 32 * nT;  // grown on demand by finish()
+    if (h->recCapacity < (size_t)h->recPerSpacePoint * nT) h->recCapacity = (size_t)h->recPerSpacePoint * nT;  // grown on demand by finish()
     h->recCapacity = std::min<size_t>(h->recCapacity, 0xFFFFFFF0u);
     CUDA_TRY(h->rec.reserve(h->recCapacity * 16));
     CUDA_TRY(h->recZ.reserve(h->recCapacity * 4));
@@ -405,7 +407,7 @@ int enqueue(b200seed_handle* h) {
     cf.next = h->confNext.as<int>();
     cf.seedsPerMiddle = sp.seedsPerMiddle;
     cf.changed = h->confState.as<uint32_t>() + kConfChangedBase;
-    rc = enqueue_conf_rounds(h, 0, kConfRoundsPerBatch, s);
+    rc = enqueue_conf_rounds(h, 0, h->confRoundsPerBatch, s);
     if (rc != B200SEED_OK) return rc;
   }
 
@@ -457,10 +459,10 @@ int finish(b200seed_handle* h, cudaStream_t s, b200seed_seeds* out) {
       }
       h->lastConfRounds = (uint32_t)used;
       if (h->hConfState[kConfChangedBase + rounds - 1] == 0u) break;  // a round reproduced its predecessor
-      if (rounds + kConfRoundsPerBatch > kConfMaxRounds) {
+      if (rounds + h->confRoundsPerBatch > kConfMaxRounds) {
         return fail(B200SEED_ERR_RUNTIME, "seedConfirmation fixed point not reached after " + std::to_string(rounds) + " rounds");
       }
-      int rc = enqueue_conf_rounds(h, rounds, kConfRoundsPerBatch, s);
+      int rc = enqueue_conf_rounds(h, rounds, h->confRoundsPerBatch, s);
       if (rc == B200SEED_OK) rc = enqueue_tail(h, s);
       if (rc != B200SEED_OK) return rc;
       CUDA_TRY(cudaStreamSynchronize(s));
@@ -604,6 +606,8 @@ int b200seed_create(const b200seed_config* cfg, int device, b200seed_handle** ou
   CREATE_TRY(cudaMallocHost(&h->hStatus, 16));
   CREATE_TRY(cudaMallocHost(&h->hSeedTotal, 16));
 
+  h->confRoundsPerBatch = (int)std::min<uint32_t>(std::max<uint32_t>(env_u32("B200SEED_CONF_ROUNDS", kConfRoundsPerBatch), 2u), 64u);
+  h->recPerSpacePoint = std::max<uint32_t>(env_u32("B200SEED_REC_PER_SP", 32), 1u);
   // the tie-order replay of the unstable sorts only makes sense when the keys are the reference's bit for bit
   h->exactTies = engineRelaxed ? 0 : (int)env_u32("B200SEED_EXACT_TIES", 1);
   {

@@ -34,11 +34,15 @@ for r in rows:
 sass = list(csv.reader(open(sass_csv)))
 hdr = sass[1]
 idx = {h: i for i, h in enumerate(hdr)}
+STALLS = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
 ins = []
+stall_of = {}
 for r in sass[2:]:
     try:
-        ins.append((int(r[0], 16), int(r[idx['Instructions Executed']]), int(r[idx['Thread Instructions Executed']]),
+        a = int(r[0], 16)
+        ins.append((a, int(r[idx['Instructions Executed']]), int(r[idx['Thread Instructions Executed']]),
                     int(r[idx['# Samples']]), int(r[idx['stall_barrier']])))
+        stall_of[a] = [int(r[idx[h]]) for h in STALLS]
     except Exception:
         pass
 ins.sort()
@@ -131,6 +135,7 @@ def helper_phase(lines):
 
 phase = collections.defaultdict(lambda: [0, 0, 0, 0])
 func = collections.defaultdict(lambda: [0, 0, 0, 0])
+phase_stalls = collections.defaultdict(lambda: [0] * len(STALLS))
 curp = "?"
 for a, i, t, s, b in ins:
     lines = addr2lines.get(a, [])
@@ -141,6 +146,8 @@ for a, i, t, s, b in ins:
         curp = p
     elif helper_phase(lines):
         curp = helper_phase(lines)
+    for q, v in enumerate(stall_of[a]):
+        phase_stalls[curp][q] += v
     for agg, key in ((phase, curp), (func, innermost(lines) if lines else "no line info")):
         agg[key][0] += i
         agg[key][1] += t
@@ -156,3 +163,11 @@ for title, agg in (("kernel phase (outermost line in the kernel body)", phase), 
         if v[0] == 0 and v[2] == 0:
             continue
         print("%-48s %6.1f%% %6.1f%% %6.1f %15.1f%%" % (k[:48], 100 * v[0] / ti, 100 * v[2] / ts, v[1] / max(v[0], 1), 100 * v[3] / max(v[2], 1)))
+
+print()
+print("stall reasons per phase (share of the phase's samples; 'selected' = issuing)")
+for k, v in sorted(phase.items(), key=lambda x: -x[1][2]):
+    st = phase_stalls[k]
+    tot = max(sum(st), 1)
+    top = sorted(zip(st, STALLS), reverse=True)[:5]
+    print("%-28s %s" % (k[:28], ", ".join("%s %.0f%%" % (n.replace('stall_', ''), 100 * c / tot) for c, n in top)))

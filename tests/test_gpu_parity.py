@@ -131,6 +131,26 @@ def test_full_size_event_mu200(plugin, O):
     eng.close()
 
 
+def test_seed_confirmation_host_decisions(plugin, O, monkeypatch):
+    """The two host-side decisions of the seedConfirmation path: the record pool is grown and the batch re-run when
+    the first guess was short, and more rounds are enqueued when the first batch of rounds did not converge."""
+    from acts_b200 import config as cm
+    from acts_b200 import events
+
+    monkeypatch.setenv("B200SEED_REC_PER_SP", "1")
+    monkeypatch.setenv("B200SEED_CONF_ROUNDS", "2")
+    eng = plugin.SeedingEngine(make_config("pu200", plugin.config_init).update(**cm.confirmation_overrides()))
+    orc = O.Oracle(make_config("pu200", O.config_init).update(**cm.confirmation_overrides()))
+    for i, mu in ((2, 60), (5, 30)):
+        ev = events.pileup_event(i, mu=mu)
+        got = eng.run(ev)
+        ref = orc.run(ev)
+        assert ref["counters"]["nCandidates"] > ev["x"].size  # more records than the pool's first guess
+        assert _same_bits(got, ref)
+        assert eng.counters()["nConfirmationRounds"] > 2      # needed a second batch of rounds
+    eng.close()
+
+
 def test_full_size_event_mu200_seed_confirmation(plugin, O):
     """<mu>=200 with seedConfirmation = true: ~4.8e4 middles coupled through bestSeedQualityMap."""
     from acts_b200 import config as cm
