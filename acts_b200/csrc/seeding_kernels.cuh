@@ -27,6 +27,9 @@
 
 namespace B200SEED_NS {
 
+#ifndef B200SEED_WORK_CHUNK
+#define B200SEED_WORK_CHUNK 8  // consecutive work items a block takes at a time (1 = none)
+#endif
 constexpr uint32_t kInvalidBin = 0xFFFFFFFFu;
 constexpr int kSortThreads = 256;
 constexpr int kScanThreads = 1024;
@@ -636,6 +639,8 @@ struct SeedShared {
   uint32_t winBs[kMaxNeighborBins], winBe[kMaxNeighborBins], winBp[kMaxNeighborBins + 1];
   uint32_t winTs[kMaxNeighborBins], winTe[kMaxNeighborBins], winTp[kMaxNeighborBins + 1];
   uint32_t scratch[34];
+  uint32_t itemNext, itemEnd;  // consecutive work items still owned by this block
+  uint32_t winBhi[kMaxNeighborBins], winThi[kMaxNeighborBins];  // end of every neighbour bin (window search bound)
   WeightIndex heap[kMaxHeap];
   StoredSeed storage[kMaxHeap];
   int heapSize;
@@ -742,6 +747,17 @@ __device__ __forceinline__ int float_to_ordered(float f) {
   return k >= 0 ? k : k ^ 0x7fffffff;
 }
 __device__ __forceinline__ float ordered_to_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+// first_true with a hint: the answer is expected within 32 elements of `lo` (windows of consecutive middles of a bin)
+template <typename Pred>
+__device__ __forceinline__ uint32_t warp_first_true_near(uint32_t lo, uint32_t hi, Pred pred) {
+  if (lo >= hi) return hi;
+  const uint32_t q = lo + (threadIdx.x & 31);
+  const uint32_t mask = __ballot_sync(0xffffffffu, q < hi && pred(q));
+  if (mask != 0u) return lo + (uint32_t)(__ffs(mask) - 1);
+  if (hi - lo <= 32u) return hi;
+  return warp_first_true(lo + 32u, hi, pred);
+}
 
 // Doublet search for BOTH sides of one middle (DoubletSeedFinder.cpp:41-273), two
 // passes so that the expensive transform runs on dense warps:
@@ -1059,11 +1075,24 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
   constexpr uint32_t kSurvCap = 6u * CAPT;
 
   if (tid < (uint32_t)kCntSlots) sh.cnt[tid] = 0ull;
-  auto fetchWork = [&]() {  // thread 0 only
-    const uint32_t item = atomicAdd(p.workCounter, 1u);
-    sh.w = item < nWork ? (p.workList != nullptr ? p.workList[item] : item) : 0xFFFFFFFFu;
+  // thread 0 only.  A block takes B200SEED_WORK_CHUNK consecutive work items at a time: consecutive items are
+  // middles of the same bin in ascending r, whose neighbour windows differ by a few elements (phase 0).
+  auto fetchWork = [&]() {
+    if (sh.itemNext >= sh.itemEnd) {
+      // single items near the end of the list keep the tail balanced (the racy peek only picks the chunk size)
+      const uint32_t seen = *reinterpret_cast<volatile uint32_t*>(p.workCounter);
+      const uint32_t chunk = (seen < nWork && nWork - seen > gridDim.x * (uint32_t)(4 * B200SEED_WORK_CHUNK))
+                                 ? (uint32_t)B200SEED_WORK_CHUNK : 1u;
+      const uint32_t base = atomicAdd(p.workCounter, chunk);
+      sh.itemNext = base;
+      sh.itemEnd = base + chunk < nWork ? base + chunk : nWork;
+      if (base >= nWork) { sh.itemEnd = base; sh.w = 0xFFFFFFFFu; return; }
+    }
+    const uint32_t item = sh.itemNext++;
+    sh.w = p.workList != nullptr ? p.workList[item] : item;
   };
-  if (tid == 0) fetchWork();
+  if (tid == 0) { sh.itemNext = 0; sh.itemEnd = 0; fetchWork(); }
+  uint32_t prevEG = 0xFFFFFFFFu, prevW = 0xFFFFFFF0u;
 
   for (;;) {
     __syncthreads();
@@ -1096,6 +1125,31 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
       // one warp per neighbour bin, 32-ary searches
       const uint32_t mb0 = bs[__ldg(p.navBins + g)];
       const float firstMiddleR = ldg2(p.pZR + mb0).y;
+      // block-uniform: the previous middle of this block was the preceding one of the same bin (ascending r), so its
+      // windows, still in sh.win*, are lower bounds of the new ones (overflow lists of later tiers are unordered)
+      const bool sameBin = eg == prevEG && w == prevW + 1u;
+      prevEG = eg;
+      prevW = w;
+      if (sameBin) {
+        for (uint32_t k = warp; k < nBot + nTop; k += nWarps) {
+          if (k < nBot) {
+            const uint32_t b1 = sh.winBhi[k];
+            const uint32_t s = warp_first_true_near(sh.winBs[k], b1, [&](uint32_t i) { return fsub(rM, ldg2(p.pZR + i).y) <= cfg.dRMaxB; });
+            const uint32_t e0 = sh.winBe[k] > s ? sh.winBe[k] : s;
+            const uint32_t e = warp_first_true_near(e0, b1, [&](uint32_t i) { return fsub(rM, ldg2(p.pZR + i).y) < cfg.dRMinB; });
+            __syncwarp();
+            if (lane == 0) { sh.winBs[k] = s; sh.winBe[k] = e; }
+          } else {
+            const uint32_t kt = k - nBot;
+            const uint32_t b1 = sh.winThi[kt];
+            const uint32_t s = warp_first_true_near(sh.winTs[kt], b1, [&](uint32_t i) { return fsub(ldg2(p.pZR + i).y, rM) >= cfg.dRMinT; });
+            const uint32_t e0 = sh.winTe[kt] > s ? sh.winTe[kt] : s;
+            const uint32_t e = warp_first_true_near(e0, b1, [&](uint32_t i) { return fsub(ldg2(p.pZR + i).y, rM) > cfg.dRMaxT; });
+            __syncwarp();
+            if (lane == 0) { sh.winTs[kt] = s; sh.winTe[kt] = e; }
+          }
+        }
+      } else
       for (uint32_t k = warp; k < nBot + nTop; k += nWarps) {
         if (k < nBot) {
           const uint32_t bin = __ldg(p.botBins + botBeg + k);
@@ -1104,7 +1158,10 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
           const uint32_t trim = warp_first_true(b0, b1, [&](uint32_t i) { return !(ldg2(p.pZR + i).y < trimValue); });
           const uint32_t s = warp_first_true(trim, b1, [&](uint32_t i) { return fsub(rM, ldg2(p.pZR + i).y) <= cfg.dRMaxB; });
           const uint32_t e = warp_first_true(s, b1, [&](uint32_t i) { return fsub(rM, ldg2(p.pZR + i).y) < cfg.dRMinB; });
-          if (lane == 0) { sh.winBs[k] = s; sh.winBe[k] = e; }
+          if (lane == 0) {
+            sh.winBs[k] = s; sh.winBe[k] = e;
+            sh.winBhi[k] = b1;
+          }
         } else {
           const uint32_t kt = k - nBot;
           const uint32_t bin = __ldg(p.topBins + topBeg + kt);
@@ -1113,7 +1170,10 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
           const uint32_t trim = warp_first_true(b0, b1, [&](uint32_t i) { return !(ldg2(p.pZR + i).y < trimValue); });
           const uint32_t s = warp_first_true(trim, b1, [&](uint32_t i) { return fsub(ldg2(p.pZR + i).y, rM) >= cfg.dRMinT; });
           const uint32_t e = warp_first_true(s, b1, [&](uint32_t i) { return fsub(ldg2(p.pZR + i).y, rM) > cfg.dRMaxT; });
-          if (lane == 0) { sh.winTs[kt] = s; sh.winTe[kt] = e; }
+          if (lane == 0) {
+            sh.winTs[kt] = s; sh.winTe[kt] = e;
+            sh.winThi[kt] = b1;
+          }
         }
       }
     }
