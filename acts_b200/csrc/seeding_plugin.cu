@@ -738,6 +738,12 @@ int b200seed_run_batch_device(b200seed_handle* h, uint32_t nEvents, uint32_t nSp
   }
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = cudaStream != nullptr ? static_cast<cudaStream_t>(cudaStream) : h->stream;
+  if (h->pending && h->plan.dev.seedConfirmation) {
+    // the convergence of the seedConfirmation rounds (and the size of the record pool) is a host decision taken at
+    // the sync: a previous asynchronous call is completed first, so that it can never pass unchecked
+    int rc = finish(h, h->last.stream != nullptr ? h->last.stream : h->stream, nullptr);
+    if (rc != B200SEED_OK) return rc;
+  }
   h->lastSeedOffsets = reinterpret_cast<const unsigned long long*>(seedOffsets);
   b200seed_handle::EnqueueArgs& a = h->last;
   a = b200seed_handle::EnqueueArgs{};

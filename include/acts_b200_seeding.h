@@ -269,7 +269,10 @@ int b200seed_run_batch(b200seed_handle* h, uint32_t nEvents,
  * seedOffsets, out->columns) is DEVICE memory on the handle's device and the
  * work is enqueued on `cudaStream` (a cudaStream_t passed as void*; NULL = the
  * handle's own stream).  Asynchronous: out->size is only valid after
- * b200seed_sync.  Used to time the path with inputs resident in HBM. */
+ * b200seed_sync.  Used to time the path with inputs resident in HBM.  Several
+ * calls may be enqueued before one b200seed_sync (counters / errors then refer
+ * to the last one); with seedConfirmation = true a call first completes the
+ * previous one, because the fixed-point rounds are checked on the host. */
 int b200seed_run_batch_device(b200seed_handle* h, uint32_t nEvents,
                               uint32_t nSpacePointsTotal,
                               const uint32_t* spOffsets, const float* x,
