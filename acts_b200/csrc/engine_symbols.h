@@ -30,6 +30,7 @@
 #define b200seed_get_stage_times B200SEED_E(get_stage_times)
 #define b200seed_estimate_params B200SEED_E(estimate_params)
 #define b200seed_make_pixel_spacepoints B200SEED_E(make_pixel_spacepoints)
+#define b200seed_run_measurements B200SEED_E(run_measurements)
 #define b200seed_debug_grid B200SEED_E(debug_grid)
 #define b200seed_debug_doublets B200SEED_E(debug_doublets)
 #define b200seed_debug_atan2f B200SEED_E(debug_atan2f)

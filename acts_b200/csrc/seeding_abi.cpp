@@ -41,6 +41,9 @@ extern "C" {
   int P##make_pixel_spacepoints(P##handle*, uint32_t, const uint32_t*, const double*, const double*,        \
                                 const double*, const double*, const double*, uint32_t, const double*,       \
                                 float*, float*, float*, float*, float*, float*);                            \
+  int P##run_measurements(P##handle*, uint32_t, const uint32_t*, const double*, const double*, const double*, \
+                          const double*, const double*, uint32_t, const double*, uint32_t, const float*,     \
+                          const float*, float*, float*, float*, float*, float*, float*, b200seed_seeds*);    \
   int P##debug_grid(P##handle*, uint64_t, uint32_t*, float*, float*, float*, float*, float*, float*,        \
                     uint64_t, uint32_t*, uint32_t*);                                                        \
   int P##debug_doublets(P##handle*, b200seed_doublets*);                                                    \
@@ -202,6 +205,18 @@ int b200seed_make_pixel_spacepoints(b200seed_handle* h, uint32_t n, const uint32
                                                  transforms, x, y, z, r, varZ, varR),
                    b200rx_make_pixel_spacepoints(h->relaxed, n, surface, loc0, loc1, cov00, cov01, cov11, nSurfaces,
                                                  transforms, x, y, z, r, varZ, varR));
+}
+
+int b200seed_run_measurements(b200seed_handle* h, uint32_t n, const uint32_t* surface, const double* loc0,
+                              const double* loc1, const double* cov00, const double* cov01, const double* cov11,
+                              uint32_t nSurfaces, const double* transforms, uint32_t nZWindows, const float* zWindowLo,
+                              const float* zWindowHi, float* x, float* y, float* z, float* r, float* varZ, float* varR,
+                              b200seed_seeds* out) {
+  B200SEED_FORWARD(h,
+                   b200ex_run_measurements(h->exact, n, surface, loc0, loc1, cov00, cov01, cov11, nSurfaces, transforms,
+                                           nZWindows, zWindowLo, zWindowHi, x, y, z, r, varZ, varR, out),
+                   b200rx_run_measurements(h->relaxed, n, surface, loc0, loc1, cov00, cov01, cov11, nSurfaces, transforms,
+                                           nZWindows, zWindowLo, zWindowHi, x, y, z, r, varZ, varR, out));
 }
 
 int b200seed_debug_grid(b200seed_handle* h, uint64_t capacity, uint32_t* copiedFromIndex, float* x, float* y,

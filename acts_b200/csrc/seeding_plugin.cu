@@ -767,10 +767,20 @@ int b200seed_sync(b200seed_handle* h, b200seed_seeds* out) {
   return finish(h, h->last.stream != nullptr ? h->last.stream : h->stream, out);
 }
 
+// measurements of one event as the source of the space points (b200seed_run_measurements)
+struct MeasurementSource {
+  const uint32_t* surface;
+  const double* col[5];  // loc0, loc1, cov00, cov01, cov11
+  uint32_t nSurfaces;
+  const double* transforms;
+  float* spOut[6];  // optional host copies of the space point columns
+};
+
 static int run_host_batch(b200seed_handle* h, uint32_t nEvents, const uint32_t* spOffsets, const float* x,
                           const float* y, const float* z, const float* r, const float* varZ,
                           const float* varR, const float* phi, uint32_t nZWin, const float* zLo,
-                          const float* zHi, uint64_t* seedOffsets, b200seed_seeds* out) {
+                          const float* zHi, uint64_t* seedOffsets, b200seed_seeds* out,
+                          const MeasurementSource* meas = nullptr) {
   if (h == nullptr || out == nullptr || spOffsets == nullptr || nEvents == 0) {
     return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL argument or empty batch");
   }
@@ -785,12 +795,53 @@ static int run_host_batch(b200seed_handle* h, uint32_t nEvents, const uint32_t* 
   CUDA_TRY(h->inOffsets.reserve(((size_t)nEvents + 1) * 4));
   DevBuf* cols[6] = {&h->inX, &h->inY, &h->inZ, &h->inR, &h->inVarZ, &h->inVarR};
   const float* src[6] = {x, y, z, r, varZ, varR};
+  DevBuf measBuf[7], measStatus;
+  struct Guard {
+    std::vector<DevBuf*> bufs;
+    ~Guard() { for (DevBuf* b : bufs) b->release(); }
+  } measGuard;
   for (int i = 0; i < 6; ++i) {
     CUDA_TRY(cols[i]->reserve(colBytes));
-    if (nTotal > 0) {
+    if (nTotal > 0 && meas == nullptr) {
       if (src[i] == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL space point column");
       CUDA_TRY(cudaMemcpyAsync(cols[i]->ptr, src[i], (size_t)nTotal * 4, cudaMemcpyHostToDevice, s));
     }
+  }
+  if (meas != nullptr && nTotal > 0) {
+    // the space points are made on the device, straight into the input columns of the pipeline
+    for (DevBuf& b : measBuf) measGuard.bufs.push_back(&b);
+    measGuard.bufs.push_back(&measStatus);
+    CUDA_TRY(measBuf[5].reserve((size_t)nTotal * 4));
+    CUDA_TRY(cudaMemcpyAsync(measBuf[5].ptr, meas->surface, (size_t)nTotal * 4, cudaMemcpyHostToDevice, s));
+    for (int k = 0; k < 5; ++k) {
+      CUDA_TRY(measBuf[k].reserve((size_t)nTotal * 8));
+      CUDA_TRY(cudaMemcpyAsync(measBuf[k].ptr, meas->col[k], (size_t)nTotal * 8, cudaMemcpyHostToDevice, s));
+    }
+    CUDA_TRY(measBuf[6].reserve((size_t)meas->nSurfaces * 96));
+    CUDA_TRY(cudaMemcpyAsync(measBuf[6].ptr, meas->transforms, (size_t)meas->nSurfaces * 96, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(measStatus.reserve(16));
+    CUDA_TRY(cudaMemsetAsync(measStatus.ptr, 0, 16, s));
+    SpacePointMakerParams mp{};
+    mp.surface = measBuf[5].as<uint32_t>();
+    mp.loc0 = measBuf[0].as<double>(); mp.loc1 = measBuf[1].as<double>();
+    mp.cov00 = measBuf[2].as<double>(); mp.cov01 = measBuf[3].as<double>(); mp.cov11 = measBuf[4].as<double>();
+    mp.transforms = measBuf[6].as<double>();
+    mp.x = h->inX.as<float>(); mp.y = h->inY.as<float>(); mp.z = h->inZ.as<float>(); mp.r = h->inR.as<float>();
+    mp.varZ = h->inVarZ.as<float>(); mp.varR = h->inVarR.as<float>();
+    mp.n = nTotal; mp.nSurfaces = meas->nSurfaces;
+    mp.status = measStatus.as<int>();
+    const int blocks = (int)std::min<uint64_t>(((uint64_t)nTotal + 255) / 256, (uint64_t)h->smCount * 8);
+    k_pixel_spacepoints<<<blocks, 256, 0, s>>>(mp);
+    CUDA_TRY(cudaGetLastError());
+    int st = 0;
+    CUDA_TRY(cudaMemcpyAsync(&st, measStatus.ptr, 4, cudaMemcpyDeviceToHost, s));
+    for (int i = 0; i < 6; ++i) {
+      if (meas->spOut[i] != nullptr) {
+        CUDA_TRY(cudaMemcpyAsync(meas->spOut[i], cols[i]->ptr, (size_t)nTotal * 4, cudaMemcpyDeviceToHost, s));
+      }
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (st != 0) return fail(B200SEED_ERR_INVALID_ARGUMENT, "surface index out of range");
   }
   CUDA_TRY(cudaMemcpyAsync(h->inOffsets.ptr, spOffsets, ((size_t)nEvents + 1) * 4, cudaMemcpyHostToDevice, s));
   float* dPhi = nullptr;
@@ -850,6 +901,21 @@ static int run_host_batch(b200seed_handle* h, uint32_t nEvents, const uint32_t* 
   }
   CUDA_TRY(cudaStreamSynchronize(s));
   return B200SEED_OK;
+}
+
+int b200seed_run_measurements(b200seed_handle* h, uint32_t n, const uint32_t* surface, const double* loc0,
+                              const double* loc1, const double* cov00, const double* cov01, const double* cov11,
+                              uint32_t nSurfaces, const double* transforms, uint32_t nZWindows, const float* zWindowLo,
+                              const float* zWindowHi, float* x, float* y, float* z, float* r, float* varZ, float* varR,
+                              b200seed_seeds* out) {
+  if (n > 0 && (surface == nullptr || loc0 == nullptr || loc1 == nullptr || cov00 == nullptr || cov01 == nullptr ||
+                cov11 == nullptr || transforms == nullptr || nSurfaces == 0)) {
+    return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL measurement column or empty surface table");
+  }
+  MeasurementSource ms{surface, {loc0, loc1, cov00, cov01, cov11}, nSurfaces, transforms, {x, y, z, r, varZ, varR}};
+  const uint32_t offsets[2] = {0, n};
+  return run_host_batch(h, 1, offsets, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nZWindows,
+                        zWindowLo, zWindowHi, nullptr, out, &ms);
 }
 
 int b200seed_run(b200seed_handle* h, uint32_t nSpacePoints, const float* x, const float* y, const float* z,

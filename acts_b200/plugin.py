@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "b200seed_config_init", "b200seed_plan_info", "b200seed_plan_tables", "b200seed_create",
     "b200seed_destroy", "b200seed_last_error", "b200seed_get_info", "b200seed_get_counters",
     "b200seed_get_stage_times", "b200seed_set_phi_sector", "b200seed_estimate_params",
-    "b200seed_make_pixel_spacepoints",
+    "b200seed_make_pixel_spacepoints", "b200seed_run_measurements",
     "b200seed_run", "b200seed_run_with_phi", "b200seed_run_batch", "b200seed_run_batch_device",
     "b200seed_sync", "b200seed_debug_grid", "b200seed_debug_doublets", "b200seed_debug_atan2f",
 ]
@@ -60,6 +60,7 @@ def lib():
         L.b200seed_set_phi_sector.argtypes = [vp, u32, u32]
         L.b200seed_estimate_params.argtypes = [vp, u64, vp, vp, vp, u32, vp, vp, vp, vp, vp]
         L.b200seed_make_pixel_spacepoints.argtypes = [vp, u32] + [vp] * 6 + [u32] + [vp] * 7
+        L.b200seed_run_measurements.argtypes = [vp, u32] + [vp] * 6 + [u32, vp, u32, vp, vp] + [vp] * 6 + [C.POINTER(Seeds)]
         L.b200seed_run.argtypes = [vp, u32] + [f32p] * 6 + [u32, f32p, f32p, C.POINTER(Seeds)]
         L.b200seed_run_with_phi.argtypes = [vp, u32] + [f32p] * 7 + [C.POINTER(Seeds)]
         L.b200seed_run_batch.argtypes = [vp, u32, vp] + [f32p] * 6 + [vp, C.POINTER(Seeds)]
@@ -170,6 +171,20 @@ class SeedingEngine:
         _check(lib().b200seed_make_pixel_spacepoints(self._h, n, _p(sf), *[_p(c) for c in cols], tr.shape[0], _p(tr),
                                                      *[_p(out[k]) for k in ("x", "y", "z", "r", "varZ", "varR")]))
         return out
+
+    def run_measurements(self, meas: dict, transforms: np.ndarray, want_spacepoints: bool = False):
+        """Measurements -> space points -> seeds in one call (``b200seed_run_measurements``)."""
+        n = int(meas["surface"].size)
+        sf = np.ascontiguousarray(meas["surface"], dtype=np.uint32)
+        cols = [np.ascontiguousarray(meas[k], dtype=np.float64) for k in ("loc0", "loc1", "cov00", "cov01", "cov11")]
+        tr = np.ascontiguousarray(transforms, dtype=np.float64).reshape(-1, 12)
+        sp = {k: np.zeros(n, np.float32) for k in ("x", "y", "z", "r", "varZ", "varR")} if want_spacepoints else None
+        out, s = self._alloc(max(16, n * 6))
+        sp_ptrs = [_p(sp[k]) for k in ("x", "y", "z", "r", "varZ", "varR")] if sp is not None else [None] * 6
+        _check(lib().b200seed_run_measurements(self._h, n, _p(sf), *[_p(c) for c in cols], tr.shape[0], _p(tr), 0, None, None,
+                                               *sp_ptrs, C.byref(s)))
+        seeds = {name: arr[:int(s.size)] for name, arr in out.items()}
+        return (seeds, sp) if want_spacepoints else seeds
 
     def stage_times_ms(self) -> dict:
         ms = np.zeros(4, dtype=np.float32)

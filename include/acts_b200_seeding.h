@@ -324,6 +324,18 @@ int b200seed_make_pixel_spacepoints(b200seed_handle* h, uint32_t n, const uint32
                                     const double* transforms, float* x, float* y, float* z,
                                     float* r, float* varZ, float* varR);
 
+/* b200seed_make_pixel_spacepoints + b200seed_run without the host round trip: the space
+ * points of ONE event are made on the device straight into the input columns of the
+ * seeding pipeline (SpacePointMaker -> GridTripletSeedingAlgorithm of the reference
+ * chain, reconstruction.py:1001-1077).  x .. varR are optional (NULL) host outputs of the
+ * space point columns; seed indices refer to the measurement order. */
+int b200seed_run_measurements(b200seed_handle* h, uint32_t n, const uint32_t* surface,
+                              const double* loc0, const double* loc1, const double* cov00,
+                              const double* cov01, const double* cov11, uint32_t nSurfaces,
+                              const double* transforms, uint32_t nZWindows,
+                              const float* zWindowLo, const float* zWindowHi, float* x, float* y,
+                              float* z, float* r, float* varZ, float* varR, b200seed_seeds* out);
+
 /* ---- stage-level introspection (parity tests of the grid / doublet stages) */
 
 /* After a run: the packed, bin-ordered, r-sorted space point copy of the LAST

@@ -507,6 +507,12 @@ def test_pixel_space_points_from_measurements(plugin, O):
     # the columns feed the seeding call directly
     orc = O.Oracle(make_config("pu200", O.config_init))
     assert _same_bits(eng.run(got), orc.run(got))
+    # ... and the fused entry (no host round trip of the space points) gives the same columns and seeds
+    seeds, sp = eng.run_measurements(meas, tr, want_spacepoints=True)
+    for k in ("x", "y", "z", "r", "varZ", "varR"):
+        assert np.array_equal(sp[k].view(np.uint32), got[k].view(np.uint32)), k
+    assert _same_bits(seeds, orc.run(got))
+    assert _same_bits(eng.run_measurements(meas, tr), seeds)
     eng.close()
 
 
