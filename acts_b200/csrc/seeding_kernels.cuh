@@ -1736,6 +1736,11 @@ struct ConfParams {
   uint32_t seedsPerMiddle;
   int round;
   uint32_t* changed;  // [rounds] number of middles whose seeds differ from the previous round
+  // Space points contained in a seed (old or new) of a middle whose output changed in the previous round: a middle
+  // that reads none of them sees the same map as one round ago and keeps its seeds without a replay.
+  const uint8_t* dirty;  // [nTotal] written by the previous round
+  uint8_t* dirtyNext;    // [nTotal] for the next round (cleared before this round)
+  const float* prevZ;
 };
 
 __device__ __forceinline__ bool conf_converged(const ConfParams& p) {
@@ -1819,6 +1824,26 @@ __global__ void __launch_bounds__(kConfWarps * 32) k_conf_replay(const __grid_co
     const uint32_t K = p.seedsPerMiddle;
     const size_t slot0 = (size_t)w * K;
     uint32_t nOut = 0;
+    if (n != 0 && p.round >= 2) {
+      const uint32_t recBase = p.recBegin[w];
+      bool touched = p.dirty[p.workPos[w]] != 0;
+      for (uint32_t i = lane; i < n; i += 32) {
+        const uint4 r = p.rec[recBase + i];
+        touched |= (p.dirty[r.x] | p.dirty[r.y]) != 0;
+      }
+      if (!__any_sync(0xffffffffu, touched)) {  // same inputs as in the previous round: same seeds
+        const uint32_t c = p.prevCount[w];
+        if (lane < c) {
+          p.curB[slot0 + lane] = p.prevB[slot0 + lane];
+          p.curM[slot0 + lane] = p.workPos[w];
+          p.curT[slot0 + lane] = p.prevT[slot0 + lane];
+          p.curQ[slot0 + lane] = p.prevQ[slot0 + lane];
+          p.curZ[slot0 + lane] = p.prevZ[slot0 + lane];
+        }
+        if (lane == 0) p.curCount[w] = c;
+        continue;
+      }
+    }
     if (n != 0) {
       const uint32_t recBase = p.recBegin[w];
       const uint32_t m = p.workPos[w];
@@ -1939,7 +1964,14 @@ __global__ void __launch_bounds__(kConfWarps * 32) k_conf_replay(const __grid_co
         same = p.prevB[slot0 + e] == p.curB[slot0 + e] && p.prevT[slot0 + e] == p.curT[slot0 + e] &&
                __float_as_uint(p.prevQ[slot0 + e]) == __float_as_uint(p.curQ[slot0 + e]);
       }
-      if (!same) ++myChanged;
+      if (!same) {
+        ++myChanged;
+        p.dirtyNext[p.workPos[w]] = 1;
+        if (p.round > 0) {
+          for (uint32_t e = 0; e < p.prevCount[w]; ++e) { p.dirtyNext[p.prevB[slot0 + e]] = 1; p.dirtyNext[p.prevT[slot0 + e]] = 1; }
+        }
+        for (uint32_t e = 0; e < nOut; ++e) { p.dirtyNext[p.curB[slot0 + e]] = 1; p.dirtyNext[p.curT[slot0 + e]] = 1; }
+      }
     }
   }
   if (lane == 0 && myChanged != 0u) atomicAdd(p.changed + p.round, myChanged);

@@ -96,7 +96,7 @@ struct b200seed_handle {
   DevBuf outB, outM, outT, outQ, outZ, seedOffsets;  // device outputs of the host API
   DevBuf counters, status, zWin;
   // seedConfirmation: candidate records, second slot set, per-space-point seed lists, {record counter, changed[round]}
-  DevBuf rec, recZ, recBegin, recCount, slot2B, slot2M, slot2T, slot2Q, slot2Z, slot2Count, confHead, confNext, confState;
+  DevBuf rec, recZ, recBegin, recCount, slot2B, slot2M, slot2T, slot2Q, slot2Z, slot2Count, confHead, confNext, confState, confDirty;
   uint32_t* hConfState = nullptr;  // pinned mirror of confState
   int confRoundsPerBatch = kConfRoundsPerBatch;  // B200SEED_CONF_ROUNDS (tests exercise the continuation path with 2)
   uint32_t recPerSpacePoint = 32;                // B200SEED_REC_PER_SP: first guess of the record pool
@@ -192,6 +192,7 @@ int ensure_workspace(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal) {
     CUDA_TRY(h->confHead.reserve(nT * 4));
     CUDA_TRY(h->confNext.reserve(nT * K * 3 * 4));
     CUDA_TRY(h->confState.reserve(kConfStateWords * 4));
+    CUDA_TRY(h->confDirty.reserve(2 * nT));
   }
   return B200SEED_OK;
 }
@@ -221,6 +222,10 @@ int enqueue_conf_rounds(b200seed_handle* h, int first, int count, cudaStream_t s
     cp.prevB = setB[prev]; cp.prevT = setT[prev]; cp.prevQ = setQ[prev]; cp.prevCount = setCount[prev];
     cp.curB = setB[cur]; cp.curM = setM[cur]; cp.curT = setT[cur]; cp.curQ = setQ[cur]; cp.curZ = setZ[cur];
     cp.curCount = setCount[cur];
+    cp.prevZ = setZ[prev];
+    cp.dirty = h->confDirty.as<uint8_t>() + (size_t)(r & 1) * nTotal;
+    cp.dirtyNext = h->confDirty.as<uint8_t>() + (size_t)((r + 1) & 1) * nTotal;
+    CUDA_TRY(cudaMemsetAsync(cp.dirtyNext, 0, nTotal, s));
     CUDA_TRY(cudaMemsetAsync(h->confHead.ptr, 0xFF, (size_t)nTotal * 4, s));
     if (r > 0) {
       k_conf_link<<<linkBlocks, 256, 0, s>>>(cp);
@@ -669,7 +674,7 @@ void b200seed_destroy(b200seed_handle* h) {
                     &h->seedStart, &h->tileSums, &h->tilePrefix, &h->outB, &h->outM, &h->outT, &h->outQ,
                     &h->outZ, &h->seedOffsets, &h->counters, &h->status, &h->zWin, &h->rec, &h->recZ, &h->recBegin,
                     &h->recCount, &h->slot2B, &h->slot2M, &h->slot2T, &h->slot2Q, &h->slot2Z, &h->slot2Count,
-                    &h->confHead, &h->confNext, &h->confState}) {
+                    &h->confHead, &h->confNext, &h->confState, &h->confDirty}) {
     b->release();
   }
   if (h->hConfState != nullptr) cudaFreeHost(h->hConfState);
