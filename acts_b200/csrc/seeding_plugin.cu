@@ -1145,19 +1145,22 @@ int b200seed_debug_atan2f(b200seed_handle* h, uint64_t n, const float* y, const 
   if (h == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL handle");
   if (n == 0) return B200SEED_OK;
   CUDA_TRY(cudaSetDevice(h->device));
-  float *dy = nullptr, *dx = nullptr, *dp = nullptr;
-  CUDA_TRY(cudaMalloc(&dy, n * 4));
-  CUDA_TRY(cudaMalloc(&dx, n * 4));
-  CUDA_TRY(cudaMalloc(&dp, n * 4));
-  cudaMemcpy(dy, y, n * 4, cudaMemcpyHostToDevice);
-  cudaMemcpy(dx, x, n * 4, cudaMemcpyHostToDevice);
-  k_atan2f<<<h->smCount * 8, 256, 0, h->stream>>>(dy, dx, dp, n);
-  cudaStreamSynchronize(h->stream);
-  cudaError_t e = cudaMemcpy(phi, dp, n * 4, cudaMemcpyDeviceToHost);
-  cudaFree(dy);
-  cudaFree(dx);
-  cudaFree(dp);
-  if (e != cudaSuccess) return fail(B200SEED_ERR_CUDA, cudaGetErrorString(e));
+  if (y == nullptr || x == nullptr || phi == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL argument");
+  DevBuf dy, dx, dp;
+  struct Guard {
+    std::vector<DevBuf*> bufs;
+    ~Guard() { for (DevBuf* b : bufs) b->release(); }
+  } guard;
+  guard.bufs = {&dy, &dx, &dp};
+  CUDA_TRY(dy.reserve(n * 4));
+  CUDA_TRY(dx.reserve(n * 4));
+  CUDA_TRY(dp.reserve(n * 4));
+  CUDA_TRY(cudaMemcpyAsync(dy.ptr, y, n * 4, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(dx.ptr, x, n * 4, cudaMemcpyHostToDevice, h->stream));
+  k_atan2f<<<h->smCount * 8, 256, 0, h->stream>>>(dy.as<float>(), dx.as<float>(), dp.as<float>(), n);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(phi, dp.ptr, n * 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
   return B200SEED_OK;
 }
 
