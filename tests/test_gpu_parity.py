@@ -297,6 +297,32 @@ def test_edge_cases(plugin, O):
     eng.close()
 
 
+@pytest.mark.parametrize("conf", [False, True])
+def test_quantised_coordinates_tie_storm(plugin, O, conf):
+    """Coordinates snapped to a coarse lattice: equal radii inside bins, equal cotTheta in the doublet lists, equal
+    curvatures in candidate groups and equal weights in the collector heaps -- every order-dependent step of the
+    reference (three unstable sorts, the bounded heaps, the strict-greater selections) has to be replayed."""
+    from acts_b200 import config as cm
+    from acts_b200 import events
+
+    extra = cm.confirmation_overrides() if conf else {}
+    eng = plugin.SeedingEngine(make_config("pu200", plugin.config_init).update(**extra))
+    orc = O.Oracle(make_config("pu200", O.config_init).update(**extra))
+    for i, mu, step in ((0, 30, 0.5), (1, 60, 2.0)):
+        ev = events.pileup_event(i, mu=mu)
+        q = {k: v.copy() for k, v in ev.items()}
+        for k in ("x", "y", "z"):
+            q[k] = (np.round(q[k] / np.float32(step)) * np.float32(step)).astype(np.float32)
+        q["r"] = np.sqrt(q["x"].astype(np.float64) ** 2 + q["y"].astype(np.float64) ** 2).astype(np.float32)
+        q["varZ"][:] = np.float32(0.01)
+        q["varR"][:] = np.float32(0.01)
+        got, ref = eng.run(q), orc.run(q)
+        assert ref["quality"].size > 100
+        assert ref["counters"]["nCotTieMiddles"] > 10 and ref["counters"]["nWeightTieMiddles"] > 0
+        assert _same_bits(got, ref), (conf, i)
+    eng.close()
+
+
 def test_canonical_tie_mode_gives_same_seed_set(plugin, O, monkeypatch):
     """B200SEED_EXACT_TIES=0 (canonical (key, index) order): same seed SET on these events."""
     from acts_b200 import events
