@@ -208,12 +208,20 @@ class SeedingEngine:
         s.capacity = capacity
         return out, s
 
-    def run(self, ev: dict, z_windows=None, phi=None, capacity=None) -> dict:
-        """One event through ``b200seed_run`` (host buffers in, host seeds out)."""
+    def run(self, ev: dict, z_windows=None, phi=None, capacity=None, out=None) -> dict:
+        """One event through ``b200seed_run`` (host buffers in, host seeds out).
+
+        ``out`` may hold caller-owned (e.g. pinned) seed columns that are reused from call to call."""
         cols = self._cols(ev)
         n = cols[0].size
         cap = capacity if capacity is not None else max(16, n * 6)
-        out, s = self._alloc(cap)
+        if out is not None:
+            s = Seeds()
+            s.bottom, s.middle, s.top = _p(out["bottom"]), _p(out["middle"]), _p(out["top"])
+            s.quality, s.vertexZ = _p(out["quality"]), _p(out["vertexZ"])
+            s.capacity = min(int(a.size) for a in out.values())
+        else:
+            out, s = self._alloc(cap)
         if phi is not None:
             phi = np.ascontiguousarray(phi, dtype=np.float32)
             rc = lib().b200seed_run_with_phi(self._h, n, *[_p(c) for c in cols], _p(phi), C.byref(s))

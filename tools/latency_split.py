@@ -39,6 +39,11 @@ cfg = config.pu200_config(plugin.config_init)
 cfg.relaxedFloat = 1 if a.relaxed else 0
 eng = plugin.SeedingEngine(cfg, device=local)
 ev = events.pileup_event(0, mu=a.mu)
+# pinned host buffers on both sides, like a production caller (pageable memory costs a staging copy each way)
+ev = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() for k, v in ev.items()}
+cap = ev["x"].size * 6
+pinned_out = {k: torch.empty(cap, dtype=torch.int32).pin_memory().numpy().view(np.uint32) for k in ("bottom", "middle", "top")}
+pinned_out.update({k: torch.empty(cap, dtype=torch.float32).pin_memory().numpy() for k in ("quality", "vertexZ")})
 
 
 def timed(fn):
@@ -57,9 +62,10 @@ def timed(fn):
 
 first, count = sharding.phi_sector_of_rank(eng.info().phiBins, rank, world)
 eng.set_phi_sector(first, count)
-mine, t_split = timed(lambda: eng.run(ev))
+mine, t_split = timed(lambda: eng.run(ev, out=pinned_out))
+mine = {k: v.copy() for k, v in mine.items()}
 eng.set_phi_sector(1, 0)
-full, t_full = timed(lambda: eng.run(ev))
+full, t_full = timed(lambda: eng.run(ev, out=pinned_out))
 t = torch.tensor([t_split, t_full], dtype=torch.float64, device="cuda")
 parts = [mine]
 if world > 1:
