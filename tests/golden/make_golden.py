@@ -27,9 +27,11 @@ CASES = [
     ("pu200_mu10_ev0", "pu200", "pileup", 0, 10.0),
     ("pu200_mu20_ev3", "pu200", "pileup", 3, 20.0),
     ("itk_like_mu10_ev1", "itk_like", "pileup", 1, 10.0),
+    ("itk_conf_mu20_ev2", "itk_conf", "pileup", 2, 20.0),  # seedConfirmation = true
 ]
 
-MAKE = {"seeding_py": config.seeding_py_config, "pu200": config.pu200_config, "itk_like": config.itk_like_config}
+MAKE = {"seeding_py": config.seeding_py_config, "pu200": config.pu200_config, "itk_like": config.itk_like_config,
+        "itk_conf": config.itk_conf_config}
 
 
 def main():
