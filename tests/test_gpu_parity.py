@@ -512,6 +512,18 @@ def test_relaxed_float_fast_path_is_close_but_separate(plugin, O):
     assert fast.counters()["nKernelLaunches"] > 0
     fast.close()
     exact.close()
+    # the fast path also runs the seedConfirmation rounds; a flipped cut can move a few seeds through the shared map
+    from acts_b200 import config as cm
+
+    cfgc = make_config("pu200", plugin.config_init).update(**cm.confirmation_overrides())
+    cfgc.relaxedFloat = 1
+    fastc = plugin.SeedingEngine(cfgc)
+    orcc = O.Oracle(make_config("pu200", O.config_init).update(**cm.confirmation_overrides()))
+    ev = events.pileup_event(2, mu=60)
+    ka, kb = set(O.seed_set(orcc.run(ev))), set(O.seed_set(fastc.run(ev)))
+    assert len(ka & kb) / len(ka) > 0.99 and len(kb - ka) / len(kb) < 0.01
+    assert fastc.counters()["nConfirmationRounds"] >= 2
+    fastc.close()
 
 
 def test_pixel_space_points_from_measurements(plugin, O):
