@@ -10,7 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # status codes (acts_b200_seeding.h)
 OK, ERR_INVALID_ARGUMENT, ERR_RUNTIME, ERR_DOMAIN, ERR_UNSUPPORTED, ERR_CUDA, ERR_CAPACITY, ERR_OVERFLOW = range(8)
@@ -97,6 +97,9 @@ class Config(C.Structure):
         ("maxQualitySeedsPerSpMConf", C.c_uint32),
         ("useDeltaRinsteadOfTopRadius", C.c_uint8),
         ("useExtraCuts", C.c_uint8),
+        ("useVertexZCuts", C.c_uint8),
+        ("vertexZNSigma", C.c_double),
+        ("vertexZMargin", C.c_double),
         ("relaxedFloat", C.c_uint8),
     ]
 

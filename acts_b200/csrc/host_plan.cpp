@@ -457,6 +457,9 @@ void config_defaults(b200seed_config& c) {
   c.maxQualitySeedsPerSpMConf = 5;
   c.useDeltaRinsteadOfTopRadius = 0;
   c.useExtraCuts = 0;
+  c.useVertexZCuts = 0;
+  c.vertexZNSigma = 3.0;
+  c.vertexZMargin = 0.0;
   c.relaxedFloat = 0;
 }
 

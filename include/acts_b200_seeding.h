@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define B200SEED_ABI_VERSION 1
+#define B200SEED_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------- */
 enum {
@@ -150,6 +150,16 @@ typedef struct b200seed_config {
 
   /* other */
   uint8_t useExtraCuts; /* ITk fast-tracking SP selector + doublet cut (.cpp:33-62) */
+  /* Vertex-z constraint (Config::inputVertices / vertexZNSigma / vertexZMargin,
+   * GridTripletSeedingAlgorithm.hpp:239-243).  useVertexZCuts = 1 stands for a
+   * non-empty `inputVertices` key: the VertexZCuts functor then takes the doublet
+   * experiment-cut slot for EVERY event (.cpp:292-297) -- the ITk doublet cut of
+   * useExtraCuts is not applied, and an event without vertices accepts every
+   * doublet (.cpp:77-79).  b200seed_run_vertices builds the windows from
+   * (z, var z) like .cpp:187-206 with the two parameters below. */
+  uint8_t useVertexZCuts;
+  double vertexZNSigma;
+  double vertexZMargin;
 
   /* Engine options (no reference counterpart).
    * relaxedFloat = 0: bit-exact binary32 replay of the reference cuts (default).

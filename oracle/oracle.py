@@ -79,6 +79,7 @@ def lib():
         L.oracle_estimate_params.argtypes = [C.c_uint64] + [C.c_void_p] * 8
         L.oracle_make_pixel_spacepoints.argtypes = [C.c_uint32] + [C.c_void_p] * 6 + [C.c_uint32] + [C.c_void_p] * 7
         L.oracle_make_pixel_spacepoints.restype = C.c_int
+        L.oracle_vertex_windows.argtypes = [C.POINTER(Config), C.c_uint32] + [C.c_void_p] * 4
         L.oracle_run_many.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 7 + [C.c_int, C.c_uint32, C.c_void_p]
         L.oracle_run_many.restype = C.c_int64
         _lib = L
@@ -140,10 +141,21 @@ class Oracle:
     def bin_index(self, phi, z, r):
         return int(lib().oracle_bin_index(self._h, phi, z, r))
 
+    def vertex_windows(self, vertex_z, vertex_var_z):
+        """The reference's z windows of a vertex list (GridTripletSeedingAlgorithm.cpp:187-206)."""
+        vz = np.ascontiguousarray(vertex_z, dtype=np.float64)
+        vv = np.ascontiguousarray(vertex_var_z, dtype=np.float64)
+        lo = np.zeros(vz.size, np.float32)
+        hi = np.zeros(vz.size, np.float32)
+        lib().oracle_vertex_windows(C.byref(self._cfg), vz.size, _p(vz), _p(vv), _p(lo), _p(hi))
+        return list(zip(lo.tolist(), hi.tolist()))
+
     def run(self, ev: dict, sort_mode: int = 0, dump_doublets: bool = False,
-            z_windows=None, phi_override=None, want_grid: bool = False) -> dict:
+            z_windows=None, phi_override=None, want_grid: bool = False, vertices=None) -> dict:
         cols = [np.ascontiguousarray(ev[k], dtype=np.float32) for k in ("x", "y", "z", "r", "varZ", "varR")]
         n = cols[0].size
+        if vertices is not None:
+            z_windows = self.vertex_windows(*vertices)
         lo = hi = None
         nzw = 0
         if z_windows is not None and len(z_windows) > 0:

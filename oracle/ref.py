@@ -43,7 +43,7 @@ def lib():
             build()
         L = C.CDLL(_LIB_PATH)
         L.ref_last_error.restype = C.c_char_p
-        L.ref_create.argtypes = [C.POINTER(Config), C.c_int, C.c_double, C.c_double, C.POINTER(C.c_void_p)]
+        L.ref_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
         L.ref_destroy.argtypes = [C.c_void_p]
         L.ref_run.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 6 + [C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
         L.ref_result_num_seeds.argtypes = [C.c_void_p]
@@ -67,14 +67,13 @@ def _p(a):
 
 
 class Reference:
-    """The reference algorithm object.  ``vertices`` = (nSigma, margin) configures ``inputVertices``."""
+    """The reference algorithm object.  ``cfg.useVertexZCuts`` configures ``inputVertices``."""
 
-    def __init__(self, cfg: Config, vertices: tuple[float, float] | None = None):
+    def __init__(self, cfg: Config):
         self._h = C.c_void_p()
         self._cfg = cfg  # keeps the arrays the struct points to alive
-        self._with_vertices = vertices is not None
-        ns, mg = vertices if vertices is not None else (3.0, 0.0)
-        rc = lib().ref_create(C.byref(cfg), int(self._with_vertices), float(ns), float(mg), C.byref(self._h))
+        self._with_vertices = bool(cfg.useVertexZCuts)
+        rc = lib().ref_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
             raise ReferenceError_(rc, lib().ref_last_error().decode())
 
@@ -89,7 +88,8 @@ class Reference:
         except Exception:
             pass
 
-    def run(self, ev: dict, vertex_z=None, vertex_var_z=None) -> dict:
+    def run(self, ev: dict, vertices=None) -> dict:
+        vertex_z, vertex_var_z = vertices if vertices is not None else (None, None)
         cols = [np.ascontiguousarray(ev[k], dtype=np.float32) for k in ("x", "y", "z", "r", "varZ", "varR")]
         n = cols[0].size
         vz = vv = None

@@ -86,7 +86,7 @@ Acts::SeedConfirmationRangeConfig toRange(const b200seed_seed_confirmation_range
   return o;
 }
 
-Algorithm::Config toConfig(const b200seed_config& c, bool withVertices, double nSigma, double margin) {
+Algorithm::Config toConfig(const b200seed_config& c) {
   Algorithm::Config o;
   o.inputSpacePoints = "spacepoints";
   o.outputSeeds = "seeds";
@@ -143,11 +143,9 @@ Algorithm::Config toConfig(const b200seed_config& c, bool withVertices, double n
   o.maxQualitySeedsPerSpMConf = c.maxQualitySeedsPerSpMConf;
   o.useDeltaRinsteadOfTopRadius = c.useDeltaRinsteadOfTopRadius != 0;
   o.useExtraCuts = c.useExtraCuts != 0;
-  if (withVertices) {
-    o.inputVertices = "vertices";
-    o.vertexZNSigma = nSigma;
-    o.vertexZMargin = margin;
-  }
+  if (c.useVertexZCuts != 0) o.inputVertices = "vertices";
+  o.vertexZNSigma = c.vertexZNSigma;
+  o.vertexZMargin = c.vertexZMargin;
   return o;
 }
 
@@ -185,15 +183,15 @@ extern "C" {
 
 const char* ref_last_error() { return g_error.c_str(); }
 
-// Constructs the reference algorithm.  withVertices != 0 configures `inputVertices`
+// Constructs the reference algorithm.  cfg->useVertexZCuts != 0 configures `inputVertices`
 // (GridTripletSeedingAlgorithm.hpp:239-243): every ref_run then passes (z, sigma_z^2)
 // per vertex and the reference builds the windows itself (.cpp:187-206).
-int ref_create(const b200seed_config* cfg, int withVertices, double vertexZNSigma, double vertexZMargin, void** out) {
+int ref_create(const b200seed_config* cfg, void** out) {
   *out = nullptr;
   auto h = std::make_unique<RefHandle>();
   const int rc = guarded([&] {
-    h->withVertices = withVertices != 0;
-    h->algorithm = std::make_unique<Algorithm>(toConfig(*cfg, h->withVertices, vertexZNSigma, vertexZMargin),
+    h->withVertices = cfg->useVertexZCuts != 0;
+    h->algorithm = std::make_unique<Algorithm>(toConfig(*cfg),
                                                Acts::getDefaultLogger("GridTripletSeeding", Acts::Logging::WARNING));
     h->harness = std::make_unique<Harness>("spacepoints", h->withVertices ? "vertices" : "", "seeds");
   });

@@ -1165,7 +1165,9 @@ void runEvent(Event& ev) {
       std::floor(maxRange / 2) * 2 - s.cfg.deltaRMiddleMaxSPRange};
 
   DoubletCuts cuts = DoubletCuts::None;
-  if (ev.zw.n > 0) {
+  // .cpp:292-297: a configured `inputVertices` key connects VertexZCuts for every event
+  // (an empty window list then accepts every doublet, .cpp:77-79)
+  if (s.cfg.useVertexZCuts || ev.zw.n > 0) {
     cuts = DoubletCuts::VertexZ;
   } else if (s.cfg.useExtraCuts) {
     cuts = DoubletCuts::Itk;
@@ -1321,6 +1323,9 @@ void oracle_config_init(b200seed_config* c) {
   c->maxQualitySeedsPerSpMConf = 5;
   c->useDeltaRinsteadOfTopRadius = 0;
   c->useExtraCuts = 0;
+  c->useVertexZCuts = 0;
+  c->vertexZNSigma = 3.0;
+  c->vertexZMargin = 0.0;
   c->relaxedFloat = 0;
 }
 
@@ -1394,6 +1399,20 @@ struct oracle_event_result {
   Event ev;
   DoubletDump dump;
 };
+
+// GridTripletSeedingAlgorithm.cpp:187-206: one z window per vertex,
+// [z - half, z + half] with half = vertexZNSigma * sqrt(cov(2, 2)) + vertexZMargin in double,
+// narrowed to float at the end.
+void oracle_vertex_windows(const b200seed_config* cfg, std::uint32_t nVertices, const double* vertexZ,
+                           const double* vertexVarZ, float* lo, float* hi) {
+  for (std::uint32_t i = 0; i < nVertices; ++i) {
+    const double z = vertexZ[i];
+    const double sigmaZ = std::sqrt(vertexVarZ[i]);
+    const double half = cfg->vertexZNSigma * sigmaZ + cfg->vertexZMargin;
+    lo[i] = static_cast<float>(z - half);
+    hi[i] = static_cast<float>(z + half);
+  }
+}
 
 // Run one event.  Returns an opaque result the caller reads with the
 // accessors below and frees with oracle_result_free.

@@ -1,0 +1,183 @@
+"""Pins the oracle (the restatement the GPU path is compared with) to the REFERENCE ITSELF.
+
+``oracle/_ref/libseeding_ref.so`` is the unmodified ``GridTripletSeedingAlgorithm`` + ``Core/src/Seeding``
+sources of acts-project/acts, compiled where they lie under ``/root/reference`` by ``oracle/Makefile``
+(``make ref``) against stand-in headers for the absent third-party pieces (``oracle/ref_shim``).
+Every test here runs the same inputs through the reference's own ``execute()`` and through the oracle and
+demands bit-identical seeds IN THE SAME ORDER (bottom, middle, top, quality bits, vertexZ bits).
+CPU only; skipped when neither the reference tree nor a prebuilt library is present.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from tests.conftest import make_config
+
+KEYS = ("bottom", "middle", "top", "quality", "vertexZ")
+
+
+def _same_bits(a, b):
+    return all(np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)) for k in KEYS)
+
+
+@pytest.fixture(scope="module")
+def O(built):
+    from oracle import oracle
+
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def R(built):
+    from oracle import ref
+
+    ref.build()
+    if not ref.available():
+        pytest.skip("oracle/_ref not built and /root/reference not present")
+    return ref
+
+
+def test_recipe_compiles_only_sources_under_the_reference_tree():
+    """The committed recipe names reference translation units by path; nothing of them is in the repo."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mk = open(os.path.join(here, "oracle", "Makefile")).read()
+    block = mk[mk.index("REF_SRCS ="):mk.index("REF_INC")]
+    srcs = [ln.strip().rstrip("\\").strip() for ln in block.splitlines()[1:] if ln.strip()]
+    assert len(srcs) >= 12 and all(s.startswith("$(REF)/") for s in srcs)
+    assert any(s.endswith("GridTripletSeedingAlgorithm.cpp") for s in srcs)
+    for name in ("DoubletSeedFinder.cpp", "TripletSeedFinder.cpp", "BroadTripletSeedFilter.cpp", "TripletSeeder.cpp",
+                 "CandidatesForMiddleSp.cpp", "CylindricalSpacePointGrid.cpp", "SpacePointGridPhiBinning.cpp"):
+        assert any(s.endswith("/" + name) for s in srcs), name
+        assert not glob.glob(os.path.join(here, "**", name), recursive=True), f"{name} must not be copied into the repo"
+
+
+@pytest.mark.parametrize("name,kind,mu,ids", [
+    ("seeding_py", "muon", 0, (0, 1, 2, 3)),
+    ("pu200", "pileup", 5, (0, 1)),
+    ("pu200", "pileup", 20, (0, 1, 2)),
+    ("pu200", "pileup", 60, (0, 1)),
+    ("itk_like", "pileup", 20, (0, 1)),
+    ("itk_like", "pileup", 60, (0,)),
+    ("itk_conf", "pileup", 20, (0, 2)),
+    ("itk_conf", "pileup", 60, (1,)),
+])
+def test_oracle_matches_reference(O, R, name, kind, mu, ids):
+    from acts_b200 import events
+
+    orc = O.Oracle(make_config(name, O.config_init))
+    ref = R.Reference(make_config(name, O.config_init))
+    for i in ids:
+        ev = events.muon_gun_event(i) if kind == "muon" else events.pileup_event(i, mu=mu)
+        a, b = orc.run(ev), ref.run(ev)
+        assert b["bottom"].size > 0
+        assert _same_bits(a, b), f"{name} event {i}"
+
+
+def test_oracle_matches_reference_on_random_configurations(O, R):
+    """Differential fuzzing of the restatement against the reference: cuts, z binning, custom navigation,
+    per-bin middle ranges, variable middle range, ITk cuts, filter knobs, seed confirmation."""
+    from acts_b200 import events
+    from tests.fuzz import random_config
+
+    rng = np.random.default_rng(20261017)
+    done = 0
+    for trial in range(120):
+        cfg, o = random_config(rng, O.config_init)
+        try:
+            orc = O.Oracle(cfg)
+        except O.OracleError as e:
+            with pytest.raises(R.ReferenceError_) as ei:  # the reference constructor refuses it too, same class
+                R.Reference(cfg)
+            assert ei.value.code == e.code, (o, str(e), str(ei.value))
+            continue
+        ref = R.Reference(cfg)
+        ev = events.pileup_event(300 + trial, mu=float(rng.choice([3, 10, 25, 45])))
+        assert _same_bits(orc.run(ev), ref.run(ev)), (trial, o)
+        done += 1
+    assert done >= 90
+
+
+def test_vertex_z_windows_match_reference(O, R):
+    """Config::inputVertices / vertexZNSigma / vertexZMargin (GridTripletSeedingAlgorithm.hpp:239-243, .cpp:187-206,
+    292-297): the reference builds the windows from the vertices; the oracle from the same (z, var z)."""
+    from acts_b200 import events
+
+    rng = np.random.default_rng(5)
+    for extra, ns, mg in ((0, 3.0, 0.0), (1, 2.0, 1.5), (0, 0.5, 0.25), (1, 5.0, 0.0)):
+        cfg = make_config("pu200", O.config_init).update(useVertexZCuts=1, vertexZNSigma=ns, vertexZMargin=mg, useExtraCuts=extra)
+        orc, ref = O.Oracle(cfg), R.Reference(cfg)
+        for i, nv in ((0, 1), (1, 7), (2, 60), (3, 0)):
+            ev = events.pileup_event(40 + i, mu=30)
+            vz = rng.normal(0.0, 55.5, nv)
+            vv = rng.uniform(0.05, 4.0, nv) ** 2
+            a = orc.run(ev, vertices=(vz, vv))
+            b = ref.run(ev, vertices=(vz, vv))
+            assert _same_bits(a, b), (extra, ns, mg, nv)
+            if nv == 0:  # no vertex: every doublet accepted, and the ITk doublet cut is NOT applied (.cpp:292-297)
+                plain = O.Oracle(make_config("pu200", O.config_init).update(useExtraCuts=0)).run(ev)
+                if not extra:
+                    assert _same_bits(a, plain)
+            elif nv == 1:  # one narrow window removes most seeds
+                assert a["bottom"].size < 0.5 * O.Oracle(make_config("pu200", O.config_init)).run(ev)["bottom"].size
+
+
+def test_quantised_coordinates_tie_storm_matches_reference(O, R):
+    """Pixel-pitch quantised coordinates: radius, cotTheta, curvature and weight ties everywhere, so the
+    three unstable std::ranges::sort calls and the heap order decide the result -- the restated libstdc++
+    algorithms must agree with the real ones inside the reference build."""
+    from acts_b200 import events
+
+    for name in ("pu200", "itk_conf"):
+        orc = O.Oracle(make_config(name, O.config_init))
+        ref = R.Reference(make_config(name, O.config_init))
+        for i, q in ((0, 0.5), (1, 2.0), (2, 8.0)):
+            ev = events.pileup_event(60 + i, mu=25)
+            x = np.round(ev["x"] / q) * q
+            y = np.round(ev["y"] / q) * q
+            z = np.round(ev["z"] / (4 * q)) * (4 * q)
+            ev = dict(ev, x=x.astype(np.float32), y=y.astype(np.float32), z=z.astype(np.float32),
+                      r=np.hypot(x.astype(np.float64), y.astype(np.float64)).astype(np.float32))
+            a, b = orc.run(ev), ref.run(ev)
+            assert a["counters"]["nCotTieMiddles"] > 0 and a["counters"]["nRTieBins"] > 0
+            assert _same_bits(a, b), (name, q)
+
+
+def test_full_size_event_matches_reference(O, R):
+    """BASELINE.json configs[2] size: one <mu>=200 event (~1e5 space points) through the reference's execute()."""
+    from acts_b200 import events
+
+    ev = events.pileup_event(0, mu=200)
+    a = O.Oracle(make_config("pu200", O.config_init)).run(ev)
+    b = R.Reference(make_config("pu200", O.config_init)).run(ev)
+    assert b["bottom"].size > 50_000
+    assert _same_bits(a, b)
+
+
+def test_golden_fixtures_match_reference(R, O):
+    """tests/golden/*.npz were written by the oracle (tests/golden/make_golden.py); the reference
+    reproduces every one of them, so the fixtures are reference outputs."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    files = sorted(glob.glob(os.path.join(here, "golden", "*.npz")))
+    assert len(files) >= 6
+    for f in files:
+        g = np.load(f, allow_pickle=False)
+        name = str(g["config"])
+        ev = {k: g[k] for k in ("x", "y", "z", "r", "varZ", "varR")}
+        b = R.Reference(make_config(name, O.config_init)).run(ev)
+        want = {k: g[k] for k in KEYS}
+        assert _same_bits(want, b), os.path.basename(f)
+
+
+def test_reference_entered_from_many_threads(R, O):
+    """execute() is const and entered concurrently by the Sequencer's workers (Sequencer.cpp:472-525):
+    eight threads through ONE reference algorithm object give the single-threaded seed counts."""
+    from acts_b200 import events
+
+    evs = [events.pileup_event(i, mu=20) for i in range(12)]
+    cols, offsets = events.concat_events(evs)
+    ref = R.Reference(make_config("pu200", O.config_init))
+    counts = ref.run_many(cols, offsets, n_threads=8)
+    single = [ref.run(ev)["bottom"].size for ev in evs]
+    assert counts.tolist() == single
