@@ -28,6 +28,10 @@
 #define b200seed_sync B200SEED_E(sync)
 #define b200seed_set_phi_sector B200SEED_E(set_phi_sector)
 #define b200seed_get_stage_times B200SEED_E(get_stage_times)
+#define b200seed_get_stage_times_ex B200SEED_E(get_stage_times_ex)
+#define b200seed_run_vertices B200SEED_E(run_vertices)
+#define b200seed_vertex_windows B200SEED_E(vertex_windows)
+#define b200seed_run_batch_windows B200SEED_E(run_batch_windows)
 #define b200seed_estimate_params B200SEED_E(estimate_params)
 #define b200seed_make_pixel_spacepoints B200SEED_E(make_pixel_spacepoints)
 #define b200seed_run_measurements B200SEED_E(run_measurements)

@@ -365,6 +365,9 @@ void build(const b200seed_config& c, HostPlan& plan) {
   plan.seedsPerMiddle = std::min<uint32_t>(
       collectorMax, c.maxSeedsPerSpM == std::numeric_limits<uint32_t>::max() ? collectorMax : c.maxSeedsPerSpM + 1);
   plan.relaxedFloat = c.relaxedFloat != 0;
+  plan.useVertexZCuts = c.useVertexZCuts != 0;
+  plan.vertexZNSigma = c.vertexZNSigma;
+  plan.vertexZMargin = c.vertexZMargin;
 
   b200seed_info& info = plan.info;
   std::memset(&info, 0, sizeof(info));

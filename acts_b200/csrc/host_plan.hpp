@@ -38,6 +38,9 @@ struct HostPlan {
   // per-middle output slots: min(maxSeedsPerSpM + 1, maxSeedsPerSpMConf)
   uint32_t seedsPerMiddle = 0;
   bool relaxedFloat = false;
+  // Config::inputVertices / vertexZNSigma / vertexZMargin (GridTripletSeedingAlgorithm.hpp:239-243)
+  bool useVertexZCuts = false;
+  double vertexZNSigma = 3.0, vertexZMargin = 0.0;
 };
 
 // Validates like the reference (same exception classes mapped to status codes)

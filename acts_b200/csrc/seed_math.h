@@ -215,7 +215,6 @@ B2S_HD float glibc_atan2f(float y, float x) {
 // ---------------------------------------------------------------------------
 constexpr int kMaxZEdges = 64;        // z bins + 1 supported on the device
 constexpr int kMaxNeighborBins = 64;  // non-empty-able neighbour bins per side per middle bin
-constexpr int kMaxZWindows = 32;      // VertexZCuts windows per event
 constexpr int kMaxCompatSeedLimit = 8;
 constexpr int kMaxHeap = 16;          // maxSeedsPerSpMConf supported
 
@@ -352,7 +351,7 @@ template <bool kBottom>
 B2S_HD bool doublet_finish(const DeviceConfig& c, const MiddleSp& m, float deltaR, float deltaZ,
                            float xO, float yO, float rO, float varZO, float varRO,
                            const float* zWinLo, const float* zWinHi, int nZWin,
-                           DoubletRec& out) {
+                           DoubletRec& out, bool sortedWindows = false) {
   const float deltaX = fsub(xO, m.x);
   const float deltaY = fsub(yO, m.y);
   const float xNewFrame = fadd(fmul(deltaX, m.cosPhiM), fmul(deltaY, m.sinPhiM));
@@ -384,8 +383,19 @@ B2S_HD bool doublet_finish(const DeviceConfig& c, const MiddleSp& m, float delta
   } else if (c.doubletCuts == kCutsVertexZ && nZWin > 0) {  // VertexZCuts, .cpp:78-96
     const float zOrigin = fsub(m.z, fmul(m.r, cotTheta));
     bool inside = false;
-    for (int k = 0; k < nZWin; ++k) {
-      if (zOrigin >= zWinLo[k] && zOrigin <= zWinHi[k]) { inside = true; break; }
+    if (sortedWindows) {
+      // the device gets the windows merged into disjoint intervals in ascending order (same union, so the same
+      // "inside any window" answer): the first interval that ends at or after zOrigin decides
+      int lo = 0, hi = nZWin;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (zWinHi[mid] < zOrigin) lo = mid + 1; else hi = mid;
+      }
+      inside = lo < nZWin && zOrigin >= zWinLo[lo];
+    } else {
+      for (int k = 0; k < nZWin; ++k) {
+        if (zOrigin >= zWinLo[k] && zOrigin <= zWinHi[k]) { inside = true; break; }
+      }
     }
     if (!inside) return false;
   }

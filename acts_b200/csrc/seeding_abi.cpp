@@ -36,6 +36,13 @@ extern "C" {
   int P##sync(P##handle*, b200seed_seeds*);                                                                 \
   int P##set_phi_sector(P##handle*, uint32_t, uint32_t);                                                    \
   int P##get_stage_times(const P##handle*, float*);                                                         \
+  int P##get_stage_times_ex(const P##handle*, float*, uint32_t);                                            \
+  int P##run_vertices(P##handle*, uint32_t, const float*, const float*, const float*, const float*,         \
+                      const float*, const float*, uint32_t, const double*, const double*, b200seed_seeds*); \
+  int P##vertex_windows(const P##handle*, uint32_t, const double*, const double*, float*, float*);          \
+  int P##run_batch_windows(P##handle*, uint32_t, const uint32_t*, const float*, const float*, const float*, \
+                           const float*, const float*, const float*, const uint32_t*, const float*,         \
+                           const float*, uint64_t*, b200seed_seeds*);                                       \
   int P##estimate_params(P##handle*, uint64_t, const uint32_t*, const uint32_t*, const uint32_t*, uint32_t, \
                          const float*, const float*, const float*, const double*, double*);                 \
   int P##make_pixel_spacepoints(P##handle*, uint32_t, const uint32_t*, const double*, const double*,        \
@@ -186,6 +193,34 @@ int b200seed_set_phi_sector(b200seed_handle* h, uint32_t firstPhiBin, uint32_t n
 
 int b200seed_get_stage_times(const b200seed_handle* h, float* ms) {
   B200SEED_FORWARD(h, b200ex_get_stage_times(h->exact, ms), b200rx_get_stage_times(h->relaxed, ms));
+}
+
+int b200seed_get_stage_times_ex(const b200seed_handle* h, float* ms, uint32_t n) {
+  B200SEED_FORWARD(h, b200ex_get_stage_times_ex(h->exact, ms, n), b200rx_get_stage_times_ex(h->relaxed, ms, n));
+}
+
+int b200seed_run_vertices(b200seed_handle* h, uint32_t nSpacePoints, const float* x, const float* y, const float* z,
+                          const float* r, const float* varZ, const float* varR, uint32_t nVertices,
+                          const double* vertexZ, const double* vertexVarZ, b200seed_seeds* out) {
+  B200SEED_FORWARD(h, b200ex_run_vertices(h->exact, nSpacePoints, x, y, z, r, varZ, varR, nVertices, vertexZ, vertexVarZ, out),
+                   b200rx_run_vertices(h->relaxed, nSpacePoints, x, y, z, r, varZ, varR, nVertices, vertexZ, vertexVarZ, out));
+}
+
+int b200seed_vertex_windows(const b200seed_handle* h, uint32_t nVertices, const double* vertexZ, const double* vertexVarZ,
+                            float* windowLo, float* windowHi) {
+  B200SEED_FORWARD(h, b200ex_vertex_windows(h->exact, nVertices, vertexZ, vertexVarZ, windowLo, windowHi),
+                   b200rx_vertex_windows(h->relaxed, nVertices, vertexZ, vertexVarZ, windowLo, windowHi));
+}
+
+int b200seed_run_batch_windows(b200seed_handle* h, uint32_t nEvents, const uint32_t* spOffsets, const float* x,
+                               const float* y, const float* z, const float* r, const float* varZ, const float* varR,
+                               const uint32_t* windowOffsets, const float* zWindowLo, const float* zWindowHi,
+                               uint64_t* seedOffsets, b200seed_seeds* out) {
+  B200SEED_FORWARD(h,
+                   b200ex_run_batch_windows(h->exact, nEvents, spOffsets, x, y, z, r, varZ, varR, windowOffsets, zWindowLo,
+                                            zWindowHi, seedOffsets, out),
+                   b200rx_run_batch_windows(h->relaxed, nEvents, spOffsets, x, y, z, r, varZ, varR, windowOffsets,
+                                            zWindowLo, zWindowHi, seedOffsets, out));
 }
 
 int b200seed_estimate_params(b200seed_handle* h, uint64_t nSeeds, const uint32_t* bottom, const uint32_t* middle,

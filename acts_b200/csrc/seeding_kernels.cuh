@@ -7,9 +7,12 @@
 //   k_middle_ranges / k_fill_work
 //        BinnedGroup iteration + middle r range, TripletSeeder.cpp:183-195,
 //        GridTripletSeedingAlgorithm.cpp:346-371,404-421
+//   k_doublets<count> / k_cap_* / k_plan_chunks / k_doublets<fill>
+//        doublet search, two passes (count, then fill into an HBM arena)
+//        TripletSeeder.cpp:52-82,138-181, DoubletSeedFinder.cpp:41-273
 //   k_seed_middles
-//        doublets, cotTheta sort, triplets, filter, per-middle selection
-//        TripletSeeder.cpp:21-107,138-181, DoubletSeedFinder.cpp:41-273,
+//        cotTheta sort, triplets, filter, per-middle selection
+//        TripletSeeder.cpp:21-42,89-107, DoubletSeedFinder.hpp:94-104,
 //        TripletSeedFinder.cpp:34-162, BroadTripletSeedFilter.cpp:96-393,
 //        CandidatesForMiddleSp.cpp:44-93
 //   k_tile_sums / k_compact_seeds / k_event_offsets
@@ -51,7 +54,8 @@ enum StatusBits : int {
   kStatusOverflowDoublets = 1,
   kStatusOverflowPool = 2,
   kStatusBinTooLarge = 4,
-  kStatusOverflowRecords = 8
+  kStatusOverflowRecords = 8,
+  kStatusArenaTooSmall = 16
 };
 
 struct GridParams {
@@ -90,42 +94,6 @@ struct WorkParams {
   // whose phi bin lies in [phiFirst, phiFirst + phiCount) are seeded
   uint32_t phiFirst, phiCount;
 };
-
-struct SeedParams {
-  DeviceConfig cfg;
-  const float2 *pXY, *pZR, *pVar;
-  const uint32_t* binStart;
-  const uint32_t *navBins, *botOffsets, *botBins, *topOffsets, *topBins;
-  const uint32_t *workPos, *workEG;
-  const uint32_t* nWorkPtr;   // number of items of THIS launch
-  const uint32_t* workList;   // NULL: items are 0..n-1; else indices into workPos/workEG
-  uint32_t* overflowList;     // middles that did not fit this launch's scratch (NULL: error)
-  uint32_t* overflowCount;
-  uint32_t nNav, nBins;
-  const float *zWinLo, *zWinHi;
-  int nZWin;
-  uint32_t* workCounter;
-  uint32_t *slotB, *slotM, *slotT;
-  float *slotQ, *slotZ;
-  uint32_t* slotCount;
-  uint32_t seedsPerMiddle;
-  int exactTies;  // replay libstdc++ std::sort inside groups of equal cotTheta
-  unsigned long long* counters;
-  int* status;
-  // seedConfirmation only: the weighted candidates of every middle, in the reference's push order
-  uint4* rec;            // {bottom pos, top pos, weight bits, meta}
-  float* recZ;           // zOrigin
-  uint32_t *recBegin, *recCount;  // per work item
-  uint32_t* recCounter;  // bump allocator (keeps counting past the capacity: tells the host what to reserve)
-  uint32_t recCapacity;
-};
-
-// meta word of a candidate record
-constexpr uint32_t kRecGroupMask = 0xFFFFu;      // sorted rank of the bottom = group id
-constexpr int kRecGroupSizeShift = 16;           // min(#candidates of the group, 3)
-constexpr uint32_t kRecNeedsTwoTops = 1u << 18;  // bottom radius <= rMaxSeedConf of the middle's region
-constexpr uint32_t kRecQuality = 1u << 19;       // deltaSeedConf > 0
-constexpr uint32_t kRecKeep = 1u << 31;          // in-kernel only
 
 struct CompactParams {
   const uint32_t* nWorkPtr;
@@ -593,105 +561,6 @@ __global__ void __launch_bounds__(256) k_fill_work(const __grid_constant__ WorkP
   }
 }
 
-// ---------------------------------------------------------------------------
-// Seeding kernel: one block per middle space point (persistent blocks pulling
-// work items from an atomic counter).  Per middle:
-//   phase 0  r windows of every neighbour bin (warp-parallel 32-ary searches)
-//   phase 1  doublet search, two passes per side: (z, r) cuts + compaction of the
-//            survivors, then the dense coordinate transform -> (cotTheta, seq)
-//   phase 2  order both lists like the reference's sortByCotTheta (bucket sort
-//            by (cotTheta, seq) + pruned libstdc++ introsort replay for ties);
-//            tops get their full records in sorted order
-//   phase 3  one thread per bottom doublet, no barrier inside the loops:
-//            a) H_j / brk_j scans; every pair is evaluated once and candidates
-//               are emitted on the spot          (TripletSeedFinder.cpp:34-162)
-//            b) window starts = exclusive prefix max of H
-//            c) the few pairs in [start_j, t*_j) the scans did not touch
-//            d) candidates grouped by bottom (counting sort), each group in
-//               curvature order                  (BroadTripletSeedFilter.cpp:143-148)
-//            e) one thread per candidate: weight  (BroadTripletSeedFilter.cpp:162-251)
-//            f) bounded heap replay in the reference's push order
-//               (CandidatesForMiddleSp.cpp:44-75)
-//   phase 4  sort_heap, keep min(n, maxSeedsPerSpM + 1), write the seed slots
-// ---------------------------------------------------------------------------
-struct Cand {
-  float curv;
-  float impactOrWeight;
-  float topR;
-  uint32_t tOwner;  // sorted top rank | sorted bottom rank << 16
-};
-__device__ __forceinline__ bool cand_less(const Cand& a, const Cand& b) { return a.curv < b.curv; }
-
-struct StoredSeed {
-  uint32_t tOwner;  // candidate identity (sorted top rank | sorted bottom rank << 16)
-  float weight;
-};
-
-struct SeedShared {
-  MiddleSp mid;
-  uint32_t w, m, eg;
-  uint32_t nB, nT, nSurv, poolCount, nValid;
-  uint32_t tie, tieB, tieT, bad;
-  int cotMinB, cotMaxB, cotMinT, cotMaxT;  // ordered-int images of the cotTheta ranges
-  uint32_t runCarry;
-  uint32_t nextChunkA, nextChunkC;
-  uint32_t nBotWin, nTopWin;
-  uint32_t winBs[kMaxNeighborBins], winBe[kMaxNeighborBins], winBp[kMaxNeighborBins + 1];
-  uint32_t winTs[kMaxNeighborBins], winTe[kMaxNeighborBins], winTp[kMaxNeighborBins + 1];
-  uint32_t scratch[34];
-  uint32_t itemNext, itemEnd;  // consecutive work items still owned by this block
-  uint32_t winBhi[kMaxNeighborBins], winThi[kMaxNeighborBins];  // end of every neighbour bin (window search bound)
-  WeightIndex heap[kMaxHeap];
-  StoredSeed storage[kMaxHeap];
-  int heapSize;
-  int heapSorted;
-  float heapMin;
-  unsigned long long cnt[kCntSlots];
-};
-
-// Static shared-memory layout of one block.  The sorted-top arrays double as
-// scratch (survivor list of phase 1, tie-replay work arrays of phase 2) until
-// they are written at the end of phase 2; the arena switches from the unsorted
-// doublet lists (phases 1-2) to the candidate pools (phase 3).
-template <int CAPB, int CAPT, int CAPPOOL, int NBK>
-struct SeedLayout {
-  static_assert(CAPB <= 2 * CAPT, "tie-replay scratch of the bottoms lives in the sorted-top arrays");
-  static_assert(CAPB + CAPT <= 6 * CAPT, "survivor list lives in the sorted-top arrays");
-  static_assert(CAPB < 65535 && CAPT < 65535 && CAPPOOL < 65535, "16-bit ranks");
-  SeedShared sh;
-  float bCot[CAPB];      // bottoms in sorted order (from phase 2 on)
-  uint32_t bSeq[CAPB];
-  float sCot[CAPT];      // tops in sorted order; contiguous block of 24 * CAPT bytes
-  float sIDR[CAPT];
-  float sEr[CAPT];
-  float sU[CAPT];
-  float sV[CAPT];
-  uint32_t sPos[CAPT];
-  uint32_t buckets[NBK + 1];
-  union Arena {
-    struct {
-      float uCotB[CAPB];
-      uint32_t uSeqB[CAPB];
-      float uCotT[CAPT];
-      uint32_t uSeqT[CAPT];
-      uint16_t rankAll[CAPB + CAPT];  // sorted order: [0, nB) bottoms, [nB, nB + nT) tops (indices into u*B / u*T)
-    } a;
-    struct {
-      uint32_t pool[CAPPOOL];  // emission order: sorted top rank | sorted bottom rank << 16
-      Cand pool2[CAPPOOL];     // grouped by bottom, curvature order
-      uint32_t cnt[CAPB + 1];
-      uint16_t hval[CAPB];   // F value of the last failing top, later the window start
-      uint16_t tstar[CAPB];  // rank of the last failing top of the prefix
-    } b;
-  } u;
-};
-
-__device__ __forceinline__ uint32_t seq_to_pos(uint32_t seq, const uint32_t* prefix, const uint32_t* start, uint32_t nWin) {
-  uint32_t k = 0;
-  while (k + 1 < nWin && prefix[k + 1] <= seq) ++k;
-  return start[k] + (seq - prefix[k]);
-}
-
 // First index in [lo, hi) where the monotone predicate holds (hi if none),
 // searched by a whole warp: 32 probes per step instead of one.
 template <typename Pred>
@@ -759,118 +628,593 @@ __device__ __forceinline__ uint32_t warp_first_true_near(uint32_t lo, uint32_t h
   return warp_first_true(lo + 32u, hi, pred);
 }
 
-// Doublet search for BOTH sides of one middle (DoubletSeedFinder.cpp:41-273), two
-// passes so that the expensive transform runs on dense warps:
-//   pass 1: (z, r) cuts over all r windows (tops, then bottoms); survivors are
-//           appended as seq | side << 31 -> surv[]
-//   pass 2: coordinate transform / remaining cuts on the survivors -> (cot, seq)
-//           lists of the two sides + the cotTheta range of each list
-// (the reference skips the bottoms of a middle without tops, TripletSeeder.cpp:62;
-// here both sides are searched together, a middle without tops is dropped after)
-__device__ __forceinline__ void find_doublets_both(const SeedParams& p, SeedShared& sh, uint32_t nBot, uint32_t nTop,
-                                                   uint32_t* surv, uint32_t survCap, float* cotB, uint32_t* seqB,
-                                                   uint32_t capB, float* cotT, uint32_t* seqT, uint32_t capT) {
-  const MiddleSp mid = sh.mid;
-  for (uint32_t k = 0; k < nTop; ++k) {
-    const uint32_t s = sh.winTs[k], e = sh.winTe[k], pre = sh.winTp[k];
-    for (uint32_t base = s; base < e; base += blockDim.x) {
-      const uint32_t o = base + threadIdx.x;
-      bool pass = false;
-      if (o < e) {
-        const float2 zr = ldg2(p.pZR + o);
-        float dR, dZ;
-        pass = doublet_zr_cuts<false>(p.cfg, mid, zr.x, zr.y, dR, dZ);
-      }
-      const uint32_t slot = warp_append(&sh.nSurv, pass);
-      if (pass && slot < survCap) surv[slot] = pre + (o - s);
-    }
-  }
-  for (uint32_t k = 0; k < nBot; ++k) {
-    const uint32_t s = sh.winBs[k], e = sh.winBe[k], pre = sh.winBp[k];
-    for (uint32_t base = s; base < e; base += blockDim.x) {
-      const uint32_t o = base + threadIdx.x;
-      bool pass = false;
-      if (o < e) {
-        const float2 zr = ldg2(p.pZR + o);
-        float dR, dZ;
-        pass = doublet_zr_cuts<true>(p.cfg, mid, zr.x, zr.y, dR, dZ);
-      }
-      const uint32_t slot = warp_append(&sh.nSurv, pass);
-      if (pass && slot < survCap) surv[slot] = (pre + (o - s)) | 0x80000000u;
-    }
-  }
-  __syncthreads();
-  const uint32_t nS = sh.nSurv < survCap ? sh.nSurv : survCap;
-  if (sh.nSurv > survCap && threadIdx.x == 0) sh.nB = capB + 1;  // forces the overflow path
-  float mnB = 3.0e38f, mxB = -3.0e38f, mnT = 3.0e38f, mxT = -3.0e38f;
-  for (uint32_t base = 0; base < nS; base += blockDim.x) {
-    const uint32_t i = base + threadIdx.x;
-    bool passB = false, passT = false;
-    DoubletRec rec;
-    uint32_t seq = 0;
-    if (i < nS) {
-      const uint32_t sv = surv[i];
-      seq = sv & 0x7fffffffu;
-      if (sv >> 31) {
-        const uint32_t o = seq_to_pos(seq, sh.winBp, sh.winBs, nBot);
-        const float2 zr = ldg2(p.pZR + o), xy = ldg2(p.pXY + o), var = ldg2(p.pVar + o);
-        float dR, dZ;
-        doublet_zr_cuts<true>(p.cfg, mid, zr.x, zr.y, dR, dZ);
-        passB = doublet_finish<true>(p.cfg, mid, dR, dZ, xy.x, xy.y, zr.y, var.x, var.y, p.zWinLo, p.zWinHi, p.nZWin, rec);
-      } else {
-        const uint32_t o = seq_to_pos(seq, sh.winTp, sh.winTs, nTop);
-        const float2 zr = ldg2(p.pZR + o), xy = ldg2(p.pXY + o), var = ldg2(p.pVar + o);
-        float dR, dZ;
-        doublet_zr_cuts<false>(p.cfg, mid, zr.x, zr.y, dR, dZ);
-        passT = doublet_finish<false>(p.cfg, mid, dR, dZ, xy.x, xy.y, zr.y, var.x, var.y, p.zWinLo, p.zWinHi, p.nZWin, rec);
-      }
-    }
-    const uint32_t slotB = warp_append(&sh.nB, passB);
-    const uint32_t slotT = warp_append(&sh.nT, passT);
-    if (passB) {
-      mnB = fminf(mnB, rec.cotTheta); mxB = fmaxf(mxB, rec.cotTheta);
-      if (slotB < capB) { cotB[slotB] = rec.cotTheta; seqB[slotB] = seq; }
-    }
-    if (passT) {
-      mnT = fminf(mnT, rec.cotTheta); mxT = fmaxf(mxT, rec.cotTheta);
-      if (slotT < capT) { cotT[slotT] = rec.cotTheta; seqT[slotT] = seq; }
-    }
-  }
-  for (int d = 16; d > 0; d >>= 1) {
-    mnB = fminf(mnB, __shfl_xor_sync(0xffffffffu, mnB, d)); mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, d));
-    mnT = fminf(mnT, __shfl_xor_sync(0xffffffffu, mnT, d)); mxT = fmaxf(mxT, __shfl_xor_sync(0xffffffffu, mxT, d));
-  }
-  if ((threadIdx.x & 31) == 0) {
-    atomicMin(&sh.cotMinB, float_to_ordered(mnB)); atomicMax(&sh.cotMaxB, float_to_ordered(mxB));
-    atomicMin(&sh.cotMinT, float_to_ordered(mnT)); atomicMax(&sh.cotMaxT, float_to_ordered(mxT));
-  }
-  __syncthreads();
+
+// ---------------------------------------------------------------------------
+// Doublet stage (DoubletSeedFinder.cpp:41-273, TripletSeeder.cpp:52-82,138-181):
+// two passes, count then fill, so that the output is allocation-free.
+//   k_doublets<false>  one warp per middle: r windows of every neighbour bin, the
+//                      (z, r) cuts of every candidate -> capT / capB = survivors
+//                      per side (= the doublet counts unless a cut of the second
+//                      half -- interaction-point cut, experiment cuts -- rejects
+//                      more: an upper bound that sizes the middle's arena slot)
+//   k_cap_*            tiled exclusive scan of the slot sizes (64-bit prefix)
+//   k_plan_chunks      chunks of consecutive work items that fit the arena
+//   k_doublets<true>   the same sweep again; survivors are queued per warp so that
+//                      the coordinate transform runs on dense warps; every doublet
+//                      is written as one 32-byte record {sp, cotTheta, iDeltaR, er,
+//                      u, v, x', y'} (the reference's DoubletsForMiddleSp columns,
+//                      DoubletSeedFinder.hpp:26-262) + its cotTheta key, in the
+//                      reference's emission order (neighbour bins in order, ascending
+//                      position inside a bin); the middle gets a header and is
+//                      appended to the work list of the shared-memory class its
+//                      exact list sizes fit (k_seed_middles)
+// ---------------------------------------------------------------------------
+struct __align__(16) DoubletRecord {
+  uint32_t pos;  // packed position of the other space point
+  float cotTheta, iDeltaR, er, u, v, xNew, yNew;
+};
+static_assert(sizeof(DoubletRecord) == 32, "one 32-byte sector per doublet");
+
+struct __align__(16) MiddleHeader {
+  uint32_t nB, nT;     // doublets of the two sides (0 / 0: the middle does not reach the triplet stage)
+  uint32_t capB;       // slot layout: bottoms at [offset, offset + nB), tops at [offset + capB, offset + capB + nT)
+  uint32_t offset;     // first record of the middle's slot, relative to the chunk's arena
+  int cotMinB, cotMaxB, cotMinT, cotMaxT;  // ordered-int images of the cotTheta ranges (bucket sort scaling)
+};
+static_assert(sizeof(MiddleHeader) == 32, "header is loaded as two 16-byte words");
+
+// Shared-memory classes of k_seed_middles: a middle goes to the smallest class its lists fit.
+constexpr int kNumSeedClasses = 6;  // 5 shared-memory classes + the spill class (lists in global memory)
+constexpr int kSpillClass = kNumSeedClasses - 1;
+constexpr uint32_t kMaxListLength = 65534;  // 16-bit ranks
+constexpr uint32_t kMaxChunks = 4096;
+
+// Byte offsets of the per-middle arrays of k_seed_middles inside the block's dynamic shared memory (or, for
+// the spill class, the block's global scratch).  Everything is sized by the EXACT list lengths of the middle.
+struct SeedCarve {
+  uint32_t oRankB;    // u16[nB]   sorted rank -> index of the bottom in the arena slot
+  uint32_t oTstar;    // u16[nB]   |P_j|, later the last failing top of the prefix
+  uint32_t oTops;     // 6 x u32[nT] sorted tops: cotTheta, iDeltaR, er, u, v, pos
+  uint32_t oBuckets;  // u32[nBk + 1]
+  uint32_t nBk;
+  // region a (until the tops are gathered)
+  uint32_t oKeyB, oKeyT;  // float[nB], float[nT]
+  uint32_t oRankT;        // u16[nT]
+  uint32_t oTie, oTieGrp; // TieItem[max(nB, nT)], u16[max(nB, nT)]
+  // region b (after the tops are gathered), overlays region a
+  uint32_t oHval;     // u16[nB]
+  uint32_t oCnt;      // u32[nB + 1]
+  uint32_t oPool;     // u32[P] emission records, then Cand[P]
+  uint32_t endA;
+  uint32_t minBytes;  // with the smallest pool the class assignment guarantees
+};
+
+B2S_HD uint32_t carve_align(uint32_t v) { return (v + 15u) & ~15u; }
+B2S_HD uint32_t seed_pool_min(uint32_t nB) { return nB / 2u + 32u; }  // candidates per middle: 0.29 nB on average at <mu>=200 (a middle whose pool overflows moves up one class)
+constexpr uint32_t kPoolEntryBytes = 20;  // u32 emission record + 16-byte Cand
+
+B2S_HD SeedCarve seed_carve(uint32_t nB, uint32_t nT) {
+  SeedCarve c;
+  uint32_t o = 0;
+  c.oRankB = o; o = carve_align(o + 2u * nB);
+  c.oTstar = o; o = carve_align(o + 2u * nB);
+  c.oTops = o; o = carve_align(o + 24u * nT);
+  uint32_t nBk = 64;
+  while (nBk < 4096u && nBk * 2u < nB + nT) nBk <<= 1;
+  c.nBk = nBk;
+  c.oBuckets = o; o = carve_align(o + 4u * (nBk + 1u));
+  uint32_t a = o;
+  c.oKeyB = a; a = carve_align(a + 4u * nB);
+  c.oKeyT = a; a = carve_align(a + 4u * nT);
+  c.oRankT = a; a = carve_align(a + 2u * nT);
+  const uint32_t n = nB > nT ? nB : nT;
+  c.oTie = a; a = carve_align(a + 8u * n);
+  c.oTieGrp = a; a = carve_align(a + 2u * n);
+  c.endA = a;
+  uint32_t b = o;
+  c.oHval = b; b = carve_align(b + 2u * nB);
+  c.oCnt = b; b = carve_align(b + 4u * (nB + 1u));
+  c.oPool = b;
+  const uint32_t withPool = b + kPoolEntryBytes * seed_pool_min(nB);
+  c.minBytes = a > withPool ? a : withPool;
+  return c;
 }
 
-// Keys of the in-block bucket sort.  bucket() must be monotone in the order
-// and after(u, v) tells whether element u sorts strictly after element v.
-struct CotKey {  // order by (cotTheta, emission index)
-  const float* cot;
-  const uint32_t* seq;
-  float cotMax, scale;
-  int nBk;
-  __device__ __forceinline__ int bucket(uint32_t i) const { return cot_bucket(cot[i], cotMax, scale, nBk); }
-  __device__ __forceinline__ bool after(uint32_t u, uint32_t v) const {
-    const float cu = cot[u], cv = cot[v];
-    return cu > cv || (cu == cv && seq[u] > seq[v]);
-  }
-};
-struct SeqKey {  // order by emission index (unique)
-  const uint32_t* seq;
-  uint32_t total;
-  int nBk;
-  __device__ __forceinline__ int bucket(uint32_t i) const {
-    return (int)(((unsigned long long)seq[i] * (unsigned long long)nBk) / (unsigned long long)total);
-  }
-  __device__ __forceinline__ bool after(uint32_t u, uint32_t v) const { return seq[u] > seq[v]; }
+struct DoubletParams {
+  DeviceConfig cfg;
+  const float2 *pXY, *pZR, *pVar;
+  const uint32_t* binStart;
+  const uint32_t *navBins, *botOffsets, *botBins, *topOffsets, *topBins;
+  const uint32_t *workPos, *workEG;
+  const uint32_t* nWorkPtr;
+  uint32_t nNav, nBins;
+  // VertexZCuts: per event disjoint windows in ascending order; event e owns [zWinOffsets[e], zWinOffsets[e + 1])
+  // (zWinOffsets == NULL: the nZWin windows apply to every event)
+  const float *zWinLo, *zWinHi;
+  const uint32_t* zWinOffsets;
+  int nZWin;
+  uint32_t* workCounter;  // ticket counter of this launch
+  uint32_t *capB, *capT;  // [nWork] (z, r) survivors per side
+  uint32_t* planWords;    // [0] largest footprint, [1] largest capB, [2] largest capT (atomicMax)
+  // fill pass
+  uint32_t itemFirst, itemEnd;           // the chunk: work items [itemFirst, itemEnd)
+  const unsigned long long* slotPrefix;  // [nWork + 1] exclusive prefix of capB + capT
+  DoubletRecord* rec;                    // arena of the chunk
+  float* key;
+  MiddleHeader* hdr;                     // [nWork]
+  uint32_t* slotCount;                   // [nWork] seeds per middle (zeroed here for middles without triplet stage)
+  uint32_t* classList;                   // [kNumSeedClasses][classStride]
+  uint32_t* classCount;                  // [kNumSeedClasses]
+  uint32_t classStride;
+  uint32_t classBytes[kNumSeedClasses];  // capacity of every shared-memory class (spill: unused)
+  int conf;                              // seedConfirmation: sufficientTopDoublets after the top search
+  unsigned long long* counters;
+  int* status;
 };
 
-// Exclusive scan (sum) of a shared array of n words in place; returns the total
+// r windows of the neighbour bins of one middle, searched by one warp (TripletSeeder.cpp:157-195,
+// DoubletSeedFinder.cpp:73-93,105-122: monotone predicates over an r-sorted bin, evaluated with the
+// reference's float expressions).  `near` = the arrays hold the windows of the preceding middle of the
+// same bin (ascending r): they are lower bounds of the new ones.
+struct WarpWindows {
+  uint32_t s[2 * kMaxNeighborBins], e[2 * kMaxNeighborBins], hi[2 * kMaxNeighborBins];  // bottoms first, then tops
+};
+
+__device__ __forceinline__ void warp_windows(const DoubletParams& p, const uint32_t* bs, uint32_t botBeg, uint32_t nBot,
+                                             uint32_t topBeg, uint32_t nTop, float rM, float firstMiddleR, bool near,
+                                             WarpWindows& W) {
+  const DeviceConfig& cfg = p.cfg;
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint32_t k = 0; k < nBot + nTop; ++k) {
+    uint32_t s, e, b1;
+    if (k < nBot) {
+      auto inMax = [&](uint32_t i) { return fsub(rM, ldg2(p.pZR + i).y) <= cfg.dRMaxB; };
+      auto belowMin = [&](uint32_t i) { return fsub(rM, ldg2(p.pZR + i).y) < cfg.dRMinB; };
+      if (near) {
+        b1 = W.hi[k];
+        s = warp_first_true_near(W.s[k], b1, inMax);
+        const uint32_t e0 = W.e[k] > s ? W.e[k] : s;
+        e = warp_first_true_near(e0, b1, belowMin);
+      } else {
+        const uint32_t bin = __ldg(p.botBins + botBeg + k);
+        const uint32_t b0 = bs[bin];
+        b1 = bs[bin + 1];
+        const float trimValue = fsub(firstMiddleR, cfg.dRMaxB);
+        const uint32_t trim = warp_first_true(b0, b1, [&](uint32_t i) { return !(ldg2(p.pZR + i).y < trimValue); });
+        s = warp_first_true(trim, b1, inMax);
+        e = warp_first_true(s, b1, belowMin);
+      }
+    } else {
+      auto inMin = [&](uint32_t i) { return fsub(ldg2(p.pZR + i).y, rM) >= cfg.dRMinT; };
+      auto aboveMax = [&](uint32_t i) { return fsub(ldg2(p.pZR + i).y, rM) > cfg.dRMaxT; };
+      if (near) {
+        b1 = W.hi[k];
+        s = warp_first_true_near(W.s[k], b1, inMin);
+        const uint32_t e0 = W.e[k] > s ? W.e[k] : s;
+        e = warp_first_true_near(e0, b1, aboveMax);
+      } else {
+        const uint32_t bin = __ldg(p.topBins + topBeg + (k - nBot));
+        const uint32_t b0 = bs[bin];
+        b1 = bs[bin + 1];
+        const float trimValue = fadd(firstMiddleR, cfg.dRMinT);
+        const uint32_t trim = warp_first_true(b0, b1, [&](uint32_t i) { return !(ldg2(p.pZR + i).y < trimValue); });
+        s = warp_first_true(trim, b1, inMin);
+        e = warp_first_true(s, b1, aboveMax);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) { W.s[k] = s; W.e[k] = e; W.hi[k] = b1; }
+  }
+  __syncwarp();
+}
+
+constexpr int kDoubletWarps = 8;
+constexpr int kDoubletQueue = 160;  // < 32 left over + up to 128 new survivors per step
+
+// One side of one middle.  Count pass: returns the number of (z, r) survivors.  Fill pass: survivors are
+// queued (warp-private queue of kDoubletQueue positions) and finished 32 at a time; returns the number of doublets written.
+template <bool kBottom, bool kFill>
+__device__ __forceinline__ uint32_t doublet_side(const DoubletParams& p, const MiddleSp& mid, const uint32_t* winS,
+                                                 const uint32_t* winE, uint32_t nWin, uint32_t* queue,
+                                                 DoubletRecord* recOut, float* keyOut, float& cotMin, float& cotMax,
+                                                 const float* zLo, const float* zHi, int nZ) {
+  const DeviceConfig& cfg = p.cfg;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t ltMask = (1u << lane) - 1u;
+  uint32_t myCount = 0;  // count pass: per lane
+  uint32_t qn = 0, nOut = 0;
+  float mn = 3.0e38f, mx = -3.0e38f;
+  auto drain = [&](uint32_t n) {  // finish the first n (<= 32) queued candidates
+    bool ok = false;
+    DoubletRecord out;
+    if (lane < n) {
+      const uint32_t o = queue[lane];
+      const float2 zr = ldg2(p.pZR + o), xy = ldg2(p.pXY + o), var = ldg2(p.pVar + o);
+      float dR, dZ;
+      doublet_zr_cuts<kBottom>(cfg, mid, zr.x, zr.y, dR, dZ);
+      DoubletRec rec;
+      ok = doublet_finish<kBottom>(cfg, mid, dR, dZ, xy.x, xy.y, zr.y, var.x, var.y, zLo, zHi, nZ, rec, true);
+      out.pos = o; out.cotTheta = rec.cotTheta; out.iDeltaR = rec.iDeltaR; out.er = rec.er;
+      out.u = rec.u; out.v = rec.v; out.xNew = rec.xNew; out.yNew = rec.yNew;
+    }
+    const uint32_t mask = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+      const uint32_t d = nOut + (uint32_t)__popc(mask & ltMask);
+      float4* dst = reinterpret_cast<float4*>(recOut + d);
+      dst[0] = make_float4(__uint_as_float(out.pos), out.cotTheta, out.iDeltaR, out.er);
+      dst[1] = make_float4(out.u, out.v, out.xNew, out.yNew);
+      keyOut[d] = out.cotTheta;
+      mn = fminf(mn, out.cotTheta);
+      mx = fmaxf(mx, out.cotTheta);
+    }
+    nOut += (uint32_t)__popc(mask);
+    const uint32_t rest = qn - n;
+    for (uint32_t base = 0; base < rest; base += 32u) {  // move the rest to the front (reads of a step precede its writes)
+      const uint32_t i = base + lane;
+      const uint32_t carry = i < rest ? queue[i + n] : 0u;
+      __syncwarp();
+      if (i < rest) queue[i] = carry;
+      __syncwarp();
+    }
+    qn = rest;
+  };
+  for (uint32_t k = 0; k < nWin; ++k) {
+    const uint32_t s = winS[k], e = winE[k];
+    for (uint32_t base = s; base < e; base += 128u) {
+      float2 zr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t o = base + 32u * (uint32_t)u + lane;
+        zr[u] = o < e ? ldg2(p.pZR + o) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t o = base + 32u * (uint32_t)u + lane;
+        float dR, dZ;
+        const bool pass = o < e && doublet_zr_cuts<kBottom>(cfg, mid, zr[u].x, zr[u].y, dR, dZ);
+        if (!kFill) {
+          myCount += pass ? 1u : 0u;
+        } else {
+          const uint32_t mask = __ballot_sync(0xffffffffu, pass);
+          if (pass) queue[qn + (uint32_t)__popc(mask & ltMask)] = o;
+          qn += (uint32_t)__popc(mask);
+        }
+      }
+      if (kFill) {
+        __syncwarp();
+        while (qn >= 32u) drain(32u);  // qn < 32 + 128 before: kDoubletQueue entries suffice
+      }
+    }
+  }
+  if (!kFill) {
+    for (int d = 16; d > 0; d >>= 1) myCount += __shfl_xor_sync(0xffffffffu, myCount, d);
+    return myCount;
+  }
+  if (qn > 0u) drain(qn);
+  for (int d = 16; d > 0; d >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  }
+  cotMin = mn;
+  cotMax = mx;
+  return nOut;
+}
+
+template <bool kFill>
+__global__ void __launch_bounds__(kDoubletWarps * 32) k_doublets(const __grid_constant__ DoubletParams p) {
+  __shared__ WarpWindows sWin[kDoubletWarps];
+  __shared__ uint32_t sQueue[kDoubletWarps][kDoubletQueue];
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const DeviceConfig& cfg = p.cfg;
+  WarpWindows& W = sWin[wib];
+  uint32_t* queue = sQueue[wib];
+  const uint32_t itemFirst = kFill ? p.itemFirst : 0u;
+  const uint32_t itemEnd = kFill ? p.itemEnd : *p.nWorkPtr;
+  const uint32_t nItems = itemEnd - itemFirst;
+  const uint32_t nWarpsGrid = gridDim.x * (uint32_t)kDoubletWarps;
+  unsigned long long cntMiddles = 0, cntB = 0, cntT = 0;
+  uint32_t maxFoot = 0, maxB = 0, maxT = 0;
+  uint32_t prevEG = 0xFFFFFFFFu, prevW = 0xFFFFFFF0u;
+  for (;;) {
+    // a warp takes B200SEED_WORK_CHUNK consecutive items (middles of one bin in ascending r: window hints), single
+    // items near the end of the list keep the tail balanced
+    uint32_t it0 = 0, it1 = 0;
+    if (lane == 0) {
+      const uint32_t seen = *reinterpret_cast<volatile uint32_t*>(p.workCounter);
+      const uint32_t chunk = (seen < nItems && nItems - seen > nWarpsGrid * (uint32_t)(2 * B200SEED_WORK_CHUNK))
+                                 ? (uint32_t)B200SEED_WORK_CHUNK : 1u;
+      it0 = atomicAdd(p.workCounter, chunk);
+      it1 = it0 + chunk < nItems ? it0 + chunk : nItems;
+    }
+    it0 = __shfl_sync(0xffffffffu, it0, 0);
+    it1 = __shfl_sync(0xffffffffu, it1, 0);
+    if (it0 >= nItems) break;
+    for (uint32_t it = it0; it < it1; ++it) {
+      const uint32_t w = itemFirst + it;
+      uint32_t capT = 0, capB = 0;
+      if (kFill) {
+        capT = __ldg(p.capT + w);
+        capB = __ldg(p.capB + w);
+        if (capT == 0u || capB == 0u) {  // no triplet stage (TripletSeeder.cpp:62,79)
+          if (lane == 0) {
+            MiddleHeader h{};
+            h.capB = capB;
+            p.hdr[w] = h;
+            p.slotCount[w] = 0;
+          }
+          continue;
+        }
+      }
+      const uint32_t m = __ldg(p.workPos + w);
+      const uint32_t eg = __ldg(p.workEG + w);
+      const uint32_t ev = eg / p.nNav, g = eg - ev * p.nNav;
+      const uint32_t* bs = p.binStart + (size_t)ev * p.nBins;
+      const uint32_t botBeg = __ldg(p.botOffsets + g), nBot = __ldg(p.botOffsets + g + 1) - botBeg;
+      const uint32_t topBeg = __ldg(p.topOffsets + g), nTop = __ldg(p.topOffsets + g + 1) - topBeg;
+      MiddleSp mid;
+      {
+        const float2 mxy = ldg2(p.pXY + m), mzr = ldg2(p.pZR + m), mvar = ldg2(p.pVar + m);
+        mid.x = mxy.x; mid.y = mxy.y; mid.z = mzr.x; mid.r = mzr.y; mid.varZ = mvar.x; mid.varR = mvar.y;
+        middle_info(mid);
+      }
+      const float firstMiddleR = ldg2(p.pZR + bs[__ldg(p.navBins + g)]).y;
+      const bool near = eg == prevEG && w == prevW + 1u;
+      prevEG = eg;
+      prevW = w;
+      warp_windows(p, bs, botBeg, nBot, topBeg, nTop, mid.r, firstMiddleR, near, W);
+      if (!kFill) {
+        ++cntMiddles;
+        float a, b;
+        capT = doublet_side<false, false>(p, mid, W.s + nBot, W.e + nBot, nTop, queue, nullptr, nullptr, a, b, nullptr, nullptr, 0);
+        if (capT != 0u) capB = doublet_side<true, false>(p, mid, W.s, W.e, nBot, queue, nullptr, nullptr, a, b, nullptr, nullptr, 0);
+        if (capB == 0u) capT = 0u;  // a middle without bottoms or without tops costs nothing later
+        if (capB > kMaxListLength || capT > kMaxListLength) {
+          if (lane == 0) atomicOr(p.status, kStatusOverflowDoublets);
+          capB = 0; capT = 0;
+        }
+        if (lane == 0) { p.capB[w] = capB; p.capT[w] = capT; }
+        if (capB != 0u) {
+          const uint32_t foot = seed_carve(capB, capT).minBytes;
+          maxFoot = foot > maxFoot ? foot : maxFoot;
+          maxB = capB > maxB ? capB : maxB;
+          maxT = capT > maxT ? capT : maxT;
+        }
+      } else {
+        const unsigned long long slot = p.slotPrefix[w] - p.slotPrefix[p.itemFirst];
+        DoubletRecord* recSlot = p.rec + slot;
+        float* keySlot = p.key + slot;
+        float mnT = 0.f, mxT = 0.f, mnB = 0.f, mxB = 0.f;
+        const uint32_t zw0 = p.zWinOffsets != nullptr ? __ldg(p.zWinOffsets + ev) : 0u;
+        const int nZ = p.zWinOffsets != nullptr ? (int)(__ldg(p.zWinOffsets + ev + 1) - zw0) : p.nZWin;
+        const float *zLo = p.zWinLo + zw0, *zHi = p.zWinHi + zw0;
+        const uint32_t nT = doublet_side<false, true>(p, mid, W.s + nBot, W.e + nBot, nTop, queue, recSlot + capB, keySlot + capB, mnT, mxT, zLo, zHi, nZ);
+        bool go = nT != 0u;
+        if (go && p.conf) go = !(nT < conf_n_top(conf_range(cfg, mid.z), mid.r));  // BroadTripletSeedFilter.cpp:63-94
+        uint32_t nB = 0;
+        if (go) nB = doublet_side<true, true>(p, mid, W.s, W.e, nBot, queue, recSlot, keySlot, mnB, mxB, zLo, zHi, nZ);
+        go = go && nB != 0u;
+        if (lane == 0) {
+          MiddleHeader h{};
+          h.capB = capB;
+          h.offset = (uint32_t)slot;
+          if (go) {
+            h.nB = nB; h.nT = nT;
+            h.cotMinB = float_to_ordered(mnB); h.cotMaxB = float_to_ordered(mxB);
+            h.cotMinT = float_to_ordered(mnT); h.cotMaxT = float_to_ordered(mxT);
+            const uint32_t foot = seed_carve(nB, nT).minBytes;
+            int c = 0;
+            while (c < kSpillClass && foot > p.classBytes[c]) ++c;
+            p.classList[(size_t)c * p.classStride + atomicAdd(p.classCount + c, 1u)] = w;
+          } else {
+            p.slotCount[w] = 0;
+          }
+          p.hdr[w] = h;
+        }
+        if (go) { cntB += nB; cntT += nT; }
+      }
+    }
+  }
+  if (lane == 0) {
+    if (!kFill) {
+      if (cntMiddles != 0ull) atomicAdd(p.counters + kCntMiddles, cntMiddles);
+      if (maxFoot != 0u) {
+        atomicMax(p.planWords + 0, maxFoot);
+        atomicMax(p.planWords + 1, maxB);
+        atomicMax(p.planWords + 2, maxT);
+      }
+    } else {
+      if (cntB != 0ull) atomicAdd(p.counters + kCntBottomDoublets, cntB);
+      if (cntT != 0ull) atomicAdd(p.counters + kCntTopDoublets, cntT);
+    }
+  }
+}
+
+// slot sizes -> 64-bit exclusive prefix (tiled: per-tile sums, scan of the tile sums, per-tile scan)
+struct SlotScanParams {
+  const uint32_t* nWorkPtr;
+  const uint32_t *capB, *capT;
+  unsigned long long* tileSums;    // [nTiles + 1]
+  unsigned long long* tilePrefix;  // [nTiles + 1]
+  unsigned long long* slotPrefix;  // [nWork + 1]
+  // chunk plan
+  unsigned long long arenaRecords;  // capacity of the arena in records
+  uint32_t* chunkBounds;            // [kMaxChunks + 1]
+  uint32_t* planWords;              // [3] number of chunks, [4] nWork
+  int* status;
+};
+
+__global__ void __launch_bounds__(256) k_cap_tile_sums(const __grid_constant__ SlotScanParams p) {
+  __shared__ uint32_t scratch[34];
+  const uint32_t nWork = *p.nWorkPtr;
+  uint32_t s = 0;
+  for (uint32_t i = threadIdx.x; i < (uint32_t)kTile; i += blockDim.x) {
+    const uint32_t w = blockIdx.x * kTile + i;
+    if (w < nWork) s += p.capB[w] + p.capT[w];  // <= 2048 * 2 * 65534: fits 32 bits
+  }
+  uint32_t total;
+  block_scan_exclusive(s, scratch, total, OpSum());
+  if (threadIdx.x == 0) p.tileSums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_u64(const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out, uint32_t n) {
+  // n tile sums (a few hundred): one warp, serial over chunks of 32
+  if (threadIdx.x >= 32) return;
+  const uint32_t lane = threadIdx.x;
+  unsigned long long carry = 0;
+  for (uint32_t base = 0; base < n; base += 32) {
+    const uint32_t i = base + lane;
+    unsigned long long v = i < n ? in[i] : 0ull, incl = v;
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= (uint32_t)d) incl += o;
+    }
+    if (i < n) out[i] = carry + incl - v;
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) out[n] = carry;
+}
+
+__global__ void __launch_bounds__(256) k_cap_prefix(const __grid_constant__ SlotScanParams p) {
+  __shared__ uint32_t scratch[34];
+  __shared__ uint32_t carry;
+  const uint32_t nWork = *p.nWorkPtr;
+  const uint32_t tile = blockIdx.x;
+  if (tile * (uint32_t)kTile >= nWork && !(tile == 0 && nWork == 0)) return;
+  const unsigned long long tileBase = p.tilePrefix[tile];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < (uint32_t)kTile; base += blockDim.x) {
+    const uint32_t w = tile * kTile + base + threadIdx.x;
+    const uint32_t n = w < nWork ? p.capB[w] + p.capT[w] : 0u;
+    uint32_t total;
+    const uint32_t excl = block_scan_exclusive(n, scratch, total, OpSum());
+    const uint32_t c = carry;
+    if (w < nWork) p.slotPrefix[w] = tileBase + c + excl;
+    __syncthreads();
+    if (threadIdx.x == 0) carry = c + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && (tile + 1) * (uint32_t)kTile >= nWork) p.slotPrefix[nWork] = tileBase + carry;
+}
+
+// Greedy chunks of consecutive work items whose slots fit the arena (one thread: a binary search per chunk).
+__global__ void k_plan_chunks(const __grid_constant__ SlotScanParams p) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const uint32_t nWork = *p.nWorkPtr;
+  uint32_t first = 0, n = 0;
+  p.chunkBounds[0] = 0;
+  while (first < nWork) {
+    const unsigned long long limit = p.slotPrefix[first] + p.arenaRecords;
+    uint32_t lo = first + 1, hi = nWork;  // the last end in [first + 1, nWork] with slotPrefix[end] <= limit
+    if (p.slotPrefix[lo] > limit) {
+      atomicOr(p.status, kStatusArenaTooSmall);  // a single middle larger than the arena (host sizes it for 2 * kMaxListLength)
+    } else {
+      while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo + 1) >> 1);
+        if (p.slotPrefix[mid] <= limit) lo = mid; else hi = mid - 1;
+      }
+    }
+    if (n == kMaxChunks) {
+      atomicOr(p.status, kStatusArenaTooSmall);
+      break;
+    }
+    p.chunkBounds[++n] = lo;
+    first = lo;
+  }
+  p.planWords[3] = n;
+  p.planWords[4] = nWork;
+}
+
+// ---------------------------------------------------------------------------
+// Seeding kernel: one block per middle space point (persistent blocks pulling
+// the work list of one shared-memory class).  The doublets of the middle come
+// from the arena written by k_doublets<true>; every array below is sized by the
+// middle's exact list lengths (SeedCarve).  Per middle:
+//   phase 1  cotTheta keys of both lists -> shared memory
+//   phase 2  order both lists like the reference's sortByCotTheta (bucket sort
+//            by (cotTheta, emission index) + pruned libstdc++ introsort replay for
+//            ties); sorted tops are gathered into shared memory, |P_j| (tops with
+//            cotT <= cotB_j) is found for every bottom
+//   phase 3  a) H_j / brk_j scans, one lane per bottom with lane refill: a lane
+//               that finishes its bottom takes the next one, every pair is
+//               evaluated once and candidates are emitted on the spot
+//                                                  (TripletSeedFinder.cpp:34-162)
+//            b) window starts = exclusive prefix max of H
+//            c) the few pairs in [start_j, t*_j) the scans did not touch
+//            d) candidates grouped by bottom (counting sort), each group in
+//               curvature order                  (BroadTripletSeedFilter.cpp:143-148)
+//            e) one thread per candidate: weight  (BroadTripletSeedFilter.cpp:162-251)
+//            f) bounded heap replay in the reference's push order
+//               (CandidatesForMiddleSp.cpp:44-75)
+//   phase 4  sort_heap, keep min(n, maxSeedsPerSpM + 1), write the seed slots
+// ---------------------------------------------------------------------------
+struct SeedParams {
+  DeviceConfig cfg;
+  const float2 *pXY, *pZR, *pVar;
+  const uint32_t* workPos;
+  // the chunk's doublets
+  const MiddleHeader* hdr;
+  const DoubletRecord* rec;
+  const float* key;
+  // work list of this launch (one shared-memory class of one chunk)
+  const uint32_t* workList;
+  const uint32_t* nWorkPtr;
+  uint32_t* workCounter;
+  uint32_t* overflowList;   // middles whose candidate pool did not fit: next class (NULL: error)
+  uint32_t* overflowCount;
+  uint32_t arrayBytes;      // bytes of dynamic shared memory (spill class: of global scratch) per block
+  unsigned char* spillScratch;
+  uint32_t *slotB, *slotM, *slotT;
+  float *slotQ, *slotZ;
+  uint32_t* slotCount;
+  uint32_t seedsPerMiddle;
+  int exactTies;  // replay libstdc++ std::sort inside groups of equal cotTheta
+  unsigned long long* counters;
+  int* status;
+  // seedConfirmation only: the weighted candidates of every middle, in the reference's push order
+  uint4* rec4;           // {bottom pos, top pos, weight bits, meta}
+  float* recZ;           // zOrigin
+  uint32_t *recBegin, *recCount;  // per work item
+  uint32_t* recCounter;  // bump allocator (keeps counting past the capacity: tells the host what to reserve)
+  uint32_t recCapacity;
+};
+
+// meta word of a candidate record
+constexpr uint32_t kRecGroupMask = 0xFFFFu;      // sorted rank of the bottom = group id
+constexpr int kRecGroupSizeShift = 16;           // min(#candidates of the group, 3)
+constexpr uint32_t kRecNeedsTwoTops = 1u << 18;  // bottom radius <= rMaxSeedConf of the middle's region
+constexpr uint32_t kRecQuality = 1u << 19;       // deltaSeedConf > 0
+constexpr uint32_t kRecKeep = 1u << 31;          // in-kernel only
+
+struct Cand {
+  float curv;
+  float impactOrWeight;
+  float topR;
+  uint32_t tOwner;  // sorted top rank | sorted bottom rank << 16
+};
+__device__ __forceinline__ bool cand_less(const Cand& a, const Cand& b) { return a.curv < b.curv; }
+
+struct StoredSeed {
+  uint32_t tOwner;  // candidate identity (sorted top rank | sorted bottom rank << 16)
+  float weight;
+};
+
+struct SeedShared {
+  uint32_t w;
+  uint32_t poolCount, nSurv;
+  uint32_t tie, tieB, tieT;
+  uint32_t nextBottom;
+  uint32_t runCarry;
+  uint32_t scratch[34];
+  WeightIndex heap[kMaxHeap];
+  StoredSeed storage[kMaxHeap];
+  int heapSize;
+  int heapSorted;
+  float heapMin;
+  unsigned long long cnt[kCntSlots];
+};
+
+// Exclusive scan (sum) of an array of n words in place; returns the total
 // (to every thread).  Every thread scans kItems consecutive words serially, one
 // block scan combines the per-thread sums: a single pass for n <= 8 * blockDim.x.
 __device__ __forceinline__ uint32_t block_scan_array(uint32_t* a, uint32_t n, uint32_t* scratch) {
@@ -898,45 +1242,15 @@ __device__ __forceinline__ uint32_t block_scan_array(uint32_t* a, uint32_t n, ui
   return carry;
 }
 
-// Bucket sort of n elements: sorted[rank] = element index.
-template <typename Key>
-__device__ __forceinline__ void block_bucket_sort(uint32_t n, const Key key, uint16_t* sorted, uint32_t* buckets,
-                                                  uint32_t nBk, uint32_t* scratch) {
-  for (uint32_t i = threadIdx.x; i <= nBk; i += blockDim.x) buckets[i] = 0;
-  __syncthreads();
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(buckets + key.bucket(i), 1u);
-  __syncthreads();
-  block_scan_array(buckets, nBk, scratch);
-  // scatter: after this loop buckets[b] is the END of bucket b
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-    sorted[atomicAdd(buckets + key.bucket(i), 1u)] = (uint16_t)i;
-  }
-  __syncthreads();
-  // order every bucket; buckets hold O(1) entries
-  for (uint32_t b = threadIdx.x; b < nBk; b += blockDim.x) {
-    const uint32_t s = b == 0 ? 0u : buckets[b - 1], e = buckets[b];
-    for (uint32_t i = s + 1; i < e; ++i) {
-      const uint16_t v = sorted[i];
-      uint32_t j = i;
-      while (j > s && key.after(sorted[j - 1], v)) {
-        sorted[j] = sorted[j - 1];
-        --j;
-      }
-      sorted[j] = v;
-    }
-  }
-  __syncthreads();
-}
-
 // Combined bucket sort of the bottom and top doublet lists of one middle by
-// (cotTheta, seq): the bottoms use buckets [0, nBk / 2), the tops [nBk / 2, nBk),
-// each list spread over its own cotTheta range.  rankAll[0, nB) are the bottoms
-// in sorted order, rankAll[nB, nB + nT) the tops (values index the per-side
-// arrays).  *tieB / *tieT are set when a list holds equal neighbours (equal keys
-// always share a bucket).
-__device__ __forceinline__ void block_sort_both(uint32_t nB, const float* cotB, const uint32_t* seqB, float minB, float maxB,
-                                                uint32_t nT, const float* cotT, const uint32_t* seqT, float minT, float maxT,
-                                                uint16_t* rankAll, uint32_t* buckets, uint32_t nBk, uint32_t* scratch,
+// (cotTheta, emission index): the bottoms use buckets [0, nBk / 2), the tops
+// [nBk / 2, nBk), each list spread over its own cotTheta range.  rankB[0, nB) /
+// rankT[0, nT) are the lists in sorted order (values index the per-side key
+// arrays = the arena slot).  *tieB / *tieT are set when a list holds equal
+// neighbours (equal keys always share a bucket).
+__device__ __forceinline__ void block_sort_both(uint32_t nB, const float* cotB, float minB, float maxB, uint32_t nT,
+                                                const float* cotT, float minT, float maxT, uint16_t* rankB,
+                                                uint16_t* rankT, uint32_t* buckets, uint32_t nBk, uint32_t* scratch,
                                                 uint32_t* tieB, uint32_t* tieT) {
   const uint32_t half = nBk >> 1;
   const float scaleB = maxB > minB ? (float)half / (maxB - minB) : 0.0f;
@@ -957,7 +1271,8 @@ __device__ __forceinline__ void block_sort_both(uint32_t nB, const float* cotB, 
   __syncthreads();
   block_scan_array(buckets, nBk, scratch);
   for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
-    rankAll[atomicAdd(buckets + bucketOf(e), 1u)] = (uint16_t)(e < nB ? e : e - nB);
+    const uint32_t q = atomicAdd(buckets + bucketOf(e), 1u);  // bottoms fill [0, nB), tops [nB, n)
+    if (e < nB) rankB[q] = (uint16_t)e; else rankT[q - nB] = (uint16_t)(e - nB);
   }
   __syncthreads();  // buckets[b] is now the END of bucket b
   for (uint32_t b = threadIdx.x; b < nBk; b += blockDim.x) {
@@ -965,42 +1280,28 @@ __device__ __forceinline__ void block_sort_both(uint32_t nB, const float* cotB, 
     if (e - s < 2) continue;
     const bool bottom = b < half;
     const float* cot = bottom ? cotB : cotT;
-    const uint32_t* seq = bottom ? seqB : seqT;
+    uint16_t* rank = bottom ? rankB : rankT - nB;
     bool tie = false;
     for (uint32_t i = s + 1; i < e; ++i) {
-      const uint16_t v = rankAll[i];
+      const uint16_t v = rank[i];
       const float cv = cot[v];
-      const uint32_t sv = seq[v];
       uint32_t j = i;
       while (j > s) {
-        const uint16_t u = rankAll[j - 1];
+        const uint16_t u = rank[j - 1];
         const float cu = cot[u];
         tie |= cu == cv;
-        if (cu > cv || (cu == cv && seq[u] > sv)) {
-          rankAll[j] = u;
+        if (cu > cv || (cu == cv && u > v)) {
+          rank[j] = u;
           --j;
         } else {
           break;
         }
       }
-      rankAll[j] = v;
+      rank[j] = v;
     }
     if (tie) *(bottom ? tieB : tieT) = 1u;
   }
   __syncthreads();
-}
-
-// true (block-uniform) when two neighbours of the sorted list have equal keys
-__device__ __forceinline__ bool block_has_ties(uint32_t n, const float* cot, const uint16_t* sorted, uint32_t* flag) {
-  if (threadIdx.x == 0) *flag = 0;
-  __syncthreads();
-  bool t = false;
-  for (uint32_t i = threadIdx.x + 1; i < n; i += blockDim.x) t |= cot[sorted[i]] == cot[sorted[i - 1]];
-  if (t) *flag = 1;
-  __syncthreads();
-  const bool r = *flag != 0;
-  __syncthreads();
-  return r;
 }
 
 // cotTheta tie items: val = element index | tie group (first canonical rank) << 16; group 0xFFFF = unique key
@@ -1008,15 +1309,11 @@ __device__ __forceinline__ bool tie_flagged(const TieItem& a) { return (a.val >>
 
 // Exact order inside groups of equal cotTheta: the reference sorts the doublets
 // with the unstable std::ranges::sort (DoubletSeedFinder.hpp:94-104) starting
-// from the emission order.  `sorted` holds the canonical (cot, seq) order; the
-// pruned replay of libstdc++'s introsort (warp_sort_replay_ties) run by one warp on the
-// emission-ordered copy W decides which member of a tie group takes which of the
-// group's slots.  seqSorted / grpOf are n-entry u16 scratch arrays.
-__device__ __forceinline__ void block_fix_ties(uint32_t n, const float* cot, const uint32_t* seq, uint32_t totalCand,
-                                               uint16_t* sorted, TieItem* W, uint16_t* seqSorted, uint16_t* grpOf,
-                                               uint32_t* buckets, uint32_t nBk, uint32_t* scratch) {
-  SeqKey sk{seq, totalCand > 0 ? totalCand : 1u, (int)nBk};
-  block_bucket_sort(n, sk, seqSorted, buckets, nBk, scratch);
+// from the emission order = the order of the arena slot.  `sorted` holds the
+// canonical (cot, index) order; the pruned replay of libstdc++'s introsort
+// (warp_sort_replay_ties) run by one warp on the emission-ordered copy W decides
+// which member of a tie group takes which of the group's slots.
+__device__ __forceinline__ void block_fix_ties(uint32_t n, const float* cot, uint16_t* sorted, TieItem* W, uint16_t* grpOf) {
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
     const uint16_t e = sorted[i];
     const float c = cot[e];
@@ -1032,306 +1329,240 @@ __device__ __forceinline__ void block_fix_ties(uint32_t n, const float* cot, con
   }
   __syncthreads();
   for (uint32_t r = threadIdx.x; r < n; r += blockDim.x) {
-    const uint16_t e = seqSorted[r];
     TieItem it;
-    it.key = cot[e];
-    it.val = (uint32_t)e | ((uint32_t)grpOf[e] << 16);
+    it.key = cot[r];
+    it.val = r | ((uint32_t)grpOf[r] << 16);
     W[r] = it;
   }
   __syncthreads();
-  if (threadIdx.x < 32) warp_sort_replay_ties(W, (int)n, tie_flagged);
-  __syncthreads();
-  // member k (in W order) of group q goes to canonical slot q + k
-  for (uint32_t r = threadIdx.x; r < n; r += blockDim.x) {
-    const TieItem it = W[r];
-    const uint32_t g = it.val >> 16;
-    if (g == 0xFFFFu) continue;
-    uint32_t before = 0;
-    for (uint32_t q = 0; q < r; ++q) before += (W[q].val >> 16) == g ? 1u : 0u;
-    sorted[g + before] = (uint16_t)(it.val & 0xFFFFu);
+  if (threadIdx.x < 32) {
+    warp_sort_replay_ties(W, (int)n, tie_flagged);
+    // member k (in W order) of group g goes to canonical slot g + k.  The ranks come from a ballot scan over
+    // W; grpOf (dead once W is built) is reused as the running member count of every group, indexed by g.
+    const uint32_t lane = threadIdx.x;
+    for (uint32_t i = lane; i < n; i += 32) grpOf[i] = 0;
+    __syncwarp();
+    for (uint32_t base = 0; base < n; base += 32) {
+      const uint32_t r = base + lane;
+      TieItem it;
+      it.key = 0.f;
+      it.val = 0xFFFF0000u;
+      if (r < n) it = W[r];
+      const uint32_t g = it.val >> 16;
+      const bool flagged = g != 0xFFFFu;
+      const uint32_t same = __match_any_sync(0xffffffffu, flagged ? g : 0x80000000u + lane);  // unflagged lanes match themselves only
+      const uint32_t before = (uint32_t)__popc(same & ((1u << lane) - 1u));
+      uint32_t carried = 0;
+      if (flagged && before == 0u) {  // first member of its group in this step: one lane per group, no race
+        carried = grpOf[g];
+        grpOf[g] = (uint16_t)(carried + (uint32_t)__popc(same));
+      }
+      carried = __shfl_sync(0xffffffffu, carried, __ffs(same) - 1);
+      if (flagged) sorted[g + carried + before] = (uint16_t)(it.val & 0xFFFFu);
+      __syncwarp();
+    }
   }
   __syncthreads();
 }
 
-// blocks per SM that fit the 227 KB of shared memory (1 KB per block is reserved)
-constexpr int seed_blocks_per_sm(size_t layoutBytes) {
-  return layoutBytes + 1024 <= 232448 / 4 ? 4
-         : (layoutBytes + 1024 <= 232448 / 3 ? 3 : (layoutBytes + 1024 <= 232448 / 2 ? 2 : 1));
-}
-
-template <int CAPB, int CAPT, int CAPPOOL, int NBK, int THREADS, bool kConf>
-__global__ void __launch_bounds__(THREADS, seed_blocks_per_sm(sizeof(SeedLayout<CAPB, CAPT, CAPPOOL, NBK>)))
-k_seed_middles(const __grid_constant__ SeedParams p) {
-  using Layout = SeedLayout<CAPB, CAPT, CAPPOOL, NBK>;
+// The block size is a launch parameter (any multiple of 32 up to 1024): every class runs the same code with the
+// thread count that fills the SM next to its shared-memory footprint (seeding_plugin.cu: kSeedClassShape).
+template <bool kConf, bool kSpill>
+__global__ void __launch_bounds__(1024, 1) k_seed_middles(const __grid_constant__ SeedParams p) {
+  const uint32_t THREADS = blockDim.x;
   extern __shared__ __align__(16) unsigned char smemRaw[];
-  Layout& L = *reinterpret_cast<Layout*>(smemRaw);
-  SeedShared& sh = L.sh;
+  __shared__ SeedShared sh;
   const uint32_t tid = threadIdx.x;
-  const uint32_t lane = tid & 31, warp = tid >> 5, nWarps = blockDim.x >> 5;
+  const uint32_t lane = tid & 31;
+  const uint32_t ltMask = (1u << lane) - 1u;
   const DeviceConfig& cfg = p.cfg;
   const uint32_t nWork = *p.nWorkPtr;
-  // scratch overlays on the (not yet written) sorted-top arrays
-  uint32_t* surv = reinterpret_cast<uint32_t*>(L.sCot);
-  constexpr uint32_t kSurvCap = 6u * CAPT;
+  unsigned char* const base = kSpill ? p.spillScratch + (size_t)blockIdx.x * p.arrayBytes : smemRaw;
 
   if (tid < (uint32_t)kCntSlots) sh.cnt[tid] = 0ull;
-  // thread 0 only.  A block takes B200SEED_WORK_CHUNK consecutive work items at a time: consecutive items are
-  // middles of the same bin in ascending r, whose neighbour windows differ by a few elements (phase 0).
-  auto fetchWork = [&]() {
-    if (sh.itemNext >= sh.itemEnd) {
-      // single items near the end of the list keep the tail balanced (the racy peek only picks the chunk size)
-      const uint32_t seen = *reinterpret_cast<volatile uint32_t*>(p.workCounter);
-      const uint32_t chunk = (seen < nWork && nWork - seen > gridDim.x * (uint32_t)(4 * B200SEED_WORK_CHUNK))
-                                 ? (uint32_t)B200SEED_WORK_CHUNK : 1u;
-      const uint32_t base = atomicAdd(p.workCounter, chunk);
-      sh.itemNext = base;
-      sh.itemEnd = base + chunk < nWork ? base + chunk : nWork;
-      if (base >= nWork) { sh.itemEnd = base; sh.w = 0xFFFFFFFFu; return; }
-    }
-    const uint32_t item = sh.itemNext++;
-    sh.w = p.workList != nullptr ? p.workList[item] : item;
-  };
-  if (tid == 0) { sh.itemNext = 0; sh.itemEnd = 0; fetchWork(); }
-  uint32_t prevEG = 0xFFFFFFFFu, prevW = 0xFFFFFFF0u;
+  if (tid == 0) {
+    const uint32_t item = atomicAdd(p.workCounter, 1u);
+    sh.w = item < nWork ? p.workList[item] : 0xFFFFFFFFu;
+  }
 
   for (;;) {
     __syncthreads();
     const uint32_t w = sh.w;
     if (w == 0xFFFFFFFFu) break;
+    __syncthreads();  // everybody has read sh.w before thread 0 fetches the next item
 
-    // ---- phase 0: middle, r windows ------------------------------------
+    // ---- phase 0: header, middle, carve-up ---------------------------------
+    const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(p.hdr + w));
+    const int4 h1 = __ldg(reinterpret_cast<const int4*>(p.hdr + w) + 1);
+    const uint32_t nB = h0.x, nT = h0.y;
+    const DoubletRecord* recB = p.rec + h0.w;
+    const DoubletRecord* recT = recB + h0.z;
+    const float* gKeyB = p.key + h0.w;
+    const float* gKeyT = gKeyB + h0.z;
     const uint32_t m = __ldg(p.workPos + w);
-    const uint32_t eg = __ldg(p.workEG + w);
-    const uint32_t ev = eg / p.nNav, g = eg - ev * p.nNav;
-    const uint32_t* bs = p.binStart + (size_t)ev * p.nBins;
-    const uint32_t botBeg = __ldg(p.botOffsets + g), nBot = __ldg(p.botOffsets + g + 1) - botBeg;
-    const uint32_t topBeg = __ldg(p.topOffsets + g), nTop = __ldg(p.topOffsets + g + 1) - topBeg;
-    const float2 mzr = ldg2(p.pZR + m);
-    const float rM = mzr.y;
-    if (tid == 0) {
-      const float2 mxy = ldg2(p.pXY + m), mvar = ldg2(p.pVar + m);
-      MiddleSp mid;
+    MiddleSp mid;
+    {
+      const float2 mxy = ldg2(p.pXY + m), mzr = ldg2(p.pZR + m), mvar = ldg2(p.pVar + m);
       mid.x = mxy.x; mid.y = mxy.y; mid.z = mzr.x; mid.r = mzr.y; mid.varZ = mvar.x; mid.varR = mvar.y;
       middle_info(mid);
-      sh.mid = mid;
-      sh.m = m;
-      sh.nB = 0; sh.nT = 0; sh.nSurv = 0; sh.tie = 0; sh.tieB = 0; sh.tieT = 0; sh.bad = 0; sh.heapSize = 0; sh.poolCount = 0;
-      sh.cotMinB = 0x7fffffff; sh.cotMaxB = (int)0x80000000; sh.cotMinT = 0x7fffffff; sh.cotMaxT = (int)0x80000000;
-      sh.nextChunkA = 0; sh.nextChunkC = 0; sh.heapSorted = 0;
-      sh.nBotWin = nBot; sh.nTopWin = nTop;
     }
-    {
-      // first middle space point of the bin (TripletSeeder.cpp:157-181 pre-trim);
-      // one warp per neighbour bin, 32-ary searches
-      const uint32_t mb0 = bs[__ldg(p.navBins + g)];
-      const float firstMiddleR = ldg2(p.pZR + mb0).y;
-      // block-uniform: the previous middle of this block was the preceding one of the same bin (ascending r), so its
-      // windows, still in sh.win*, are lower bounds of the new ones (overflow lists of later tiers are unordered)
-      const bool sameBin = eg == prevEG && w == prevW + 1u;
-      prevEG = eg;
-      prevW = w;
-      if (sameBin) {
-        for (uint32_t k = warp; k < nBot + nTop; k += nWarps) {
-          if (k < nBot) {
-            const uint32_t b1 = sh.winBhi[k];
-            const uint32_t s = warp_first_true_near(sh.winBs[k], b1, [&](uint32_t i) { return fsub(rM, ldg2(p.pZR + i).y) <= cfg.dRMaxB; });
-            const uint32_t e0 = sh.winBe[k] > s ? sh.winBe[k] : s;
-            const uint32_t e = warp_first_true_near(e0, b1, [&](uint32_t i) { return fsub(rM, ldg2(p.pZR + i).y) < cfg.dRMinB; });
-            __syncwarp();
-            if (lane == 0) { sh.winBs[k] = s; sh.winBe[k] = e; }
-          } else {
-            const uint32_t kt = k - nBot;
-            const uint32_t b1 = sh.winThi[kt];
-            const uint32_t s = warp_first_true_near(sh.winTs[kt], b1, [&](uint32_t i) { return fsub(ldg2(p.pZR + i).y, rM) >= cfg.dRMinT; });
-            const uint32_t e0 = sh.winTe[kt] > s ? sh.winTe[kt] : s;
-            const uint32_t e = warp_first_true_near(e0, b1, [&](uint32_t i) { return fsub(ldg2(p.pZR + i).y, rM) > cfg.dRMaxT; });
-            __syncwarp();
-            if (lane == 0) { sh.winTs[kt] = s; sh.winTe[kt] = e; }
-          }
-        }
-      } else
-      for (uint32_t k = warp; k < nBot + nTop; k += nWarps) {
-        if (k < nBot) {
-          const uint32_t bin = __ldg(p.botBins + botBeg + k);
-          const uint32_t b0 = bs[bin], b1 = bs[bin + 1];
-          const float trimValue = fsub(firstMiddleR, cfg.dRMaxB);
-          const uint32_t trim = warp_first_true(b0, b1, [&](uint32_t i) { return !(ldg2(p.pZR + i).y < trimValue); });
-          const uint32_t s = warp_first_true(trim, b1, [&](uint32_t i) { return fsub(rM, ldg2(p.pZR + i).y) <= cfg.dRMaxB; });
-          const uint32_t e = warp_first_true(s, b1, [&](uint32_t i) { return fsub(rM, ldg2(p.pZR + i).y) < cfg.dRMinB; });
-          if (lane == 0) {
-            sh.winBs[k] = s; sh.winBe[k] = e;
-            sh.winBhi[k] = b1;
-          }
-        } else {
-          const uint32_t kt = k - nBot;
-          const uint32_t bin = __ldg(p.topBins + topBeg + kt);
-          const uint32_t b0 = bs[bin], b1 = bs[bin + 1];
-          const float trimValue = fadd(firstMiddleR, cfg.dRMinT);
-          const uint32_t trim = warp_first_true(b0, b1, [&](uint32_t i) { return !(ldg2(p.pZR + i).y < trimValue); });
-          const uint32_t s = warp_first_true(trim, b1, [&](uint32_t i) { return fsub(ldg2(p.pZR + i).y, rM) >= cfg.dRMinT; });
-          const uint32_t e = warp_first_true(s, b1, [&](uint32_t i) { return fsub(ldg2(p.pZR + i).y, rM) > cfg.dRMaxT; });
-          if (lane == 0) {
-            sh.winTs[kt] = s; sh.winTe[kt] = e;
-            sh.winThi[kt] = b1;
-          }
-        }
-      }
-    }
-    __syncthreads();
-    if (tid == 0) {
-      uint32_t acc = 0;
-      for (uint32_t k = 0; k < nBot; ++k) { sh.winBp[k] = acc; acc += sh.winBe[k] - sh.winBs[k]; }
-      sh.winBp[nBot] = acc;
-      acc = 0;
-      for (uint32_t k = 0; k < nTop; ++k) { sh.winTp[k] = acc; acc += sh.winTe[k] - sh.winTs[k]; }
-      sh.winTp[nTop] = acc;
-      sh.cnt[kCntMiddles] += 1;
-    }
-    __syncthreads();
-    if (tid == 0) fetchWork();  // next item: the global atomic's latency hides behind phase 1
+    const SeedCarve cv = seed_carve(nB, nT);
+    uint16_t* rankB = reinterpret_cast<uint16_t*>(base + cv.oRankB);
+    uint16_t* tstar = reinterpret_cast<uint16_t*>(base + cv.oTstar);
+    float* sCot = reinterpret_cast<float*>(base + cv.oTops);
+    float* sIDR = sCot + nT;
+    float* sEr = sIDR + nT;
+    float* sU = sEr + nT;
+    float* sV = sU + nT;
+    uint32_t* sPos = reinterpret_cast<uint32_t*>(sV + nT);
+    uint32_t* buckets = reinterpret_cast<uint32_t*>(base + cv.oBuckets);
+    float* keyB = reinterpret_cast<float*>(base + cv.oKeyB);
+    float* keyT = reinterpret_cast<float*>(base + cv.oKeyT);
+    uint16_t* rankT = reinterpret_cast<uint16_t*>(base + cv.oRankT);
+    TieItem* tieW = reinterpret_cast<TieItem*>(base + cv.oTie);
+    uint16_t* tieGrp = reinterpret_cast<uint16_t*>(base + cv.oTieGrp);
+    uint16_t* hval = reinterpret_cast<uint16_t*>(base + cv.oHval);
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(base + cv.oCnt);
+    const uint32_t poolCap = (p.arrayBytes - cv.oPool) / kPoolEntryBytes;
+    uint32_t* pool = reinterpret_cast<uint32_t*>(base + cv.oPool);
+    Cand* pool2 = reinterpret_cast<Cand*>(base + carve_align(cv.oPool + 4u * poolCap));
 
-    // ---- phase 1: doublets of both sides (TripletSeeder.cpp:52-82) -------
-    find_doublets_both(p, sh, nBot, nTop, surv, kSurvCap, L.u.a.uCotB, L.u.a.uSeqB, CAPB, L.u.a.uCotT, L.u.a.uSeqT, CAPT);
-    const uint32_t nT = sh.nT, nB = sh.nB;
-    bool insufficient = false;  // BroadTripletSeedFilter::sufficientTopDoublets (.cpp:63-94, TripletSeeder.cpp:67-69)
-    if constexpr (kConf) insufficient = nT < conf_n_top(conf_range(cfg, sh.mid.z), sh.mid.r);
-    if (insufficient || nT == 0 || nB == 0 || nT > (uint32_t)CAPT || nB > (uint32_t)CAPB) {
-      if (tid == 0) {
-        p.slotCount[w] = 0;
-        if (!insufficient && nT != 0 && nB != 0) {  // does not fit this launch's scratch: hand over to the next tier
-          if (p.overflowList != nullptr) {
-            p.overflowList[atomicAdd(p.overflowCount, 1u)] = w;
-            sh.cnt[kCntMiddles] -= 1;  // counted again by the launch that completes it
-          } else {
-            atomicOr(p.status, kStatusOverflowDoublets);
-          }
-        }
-      }
-      continue;
+    if (tid == 0) {
+      sh.tie = 0; sh.tieB = 0; sh.tieT = 0; sh.heapSize = 0; sh.poolCount = 0; sh.nextBottom = 0; sh.heapSorted = 0;
+      const uint32_t item = atomicAdd(p.workCounter, 1u);  // next item: the latency hides behind this middle
+      sh.w = item < nWork ? p.workList[item] : 0xFFFFFFFFu;
     }
+
+    // ---- phase 1: keys ---------------------------------------------------------
+    for (uint32_t i = tid; i < nB; i += THREADS) keyB[i] = __ldg(gKeyB + i);
+    for (uint32_t i = tid; i < nT; i += THREADS) keyT[i] = __ldg(gKeyT + i);
+    __syncthreads();
 
     // ---- phase 2: order both lists like DoubletSeedFinder.hpp:94-104 -------
-    TieItem* tieW = reinterpret_cast<TieItem*>(L.sCot);
-    uint16_t* tieSeqSorted = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(L.sCot) + 8u * CAPB);
-    uint16_t* tieGrpOf = tieSeqSorted + CAPB;
-    uint16_t* rankB = L.u.a.rankAll;
-    uint16_t* rankT = L.u.a.rankAll + nB;
-    block_sort_both(nB, L.u.a.uCotB, L.u.a.uSeqB, ordered_to_float(sh.cotMinB), ordered_to_float(sh.cotMaxB), nT,
-                    L.u.a.uCotT, L.u.a.uSeqT, ordered_to_float(sh.cotMinT), ordered_to_float(sh.cotMaxT), L.u.a.rankAll,
-                    L.buckets, NBK, sh.scratch, &sh.tieB, &sh.tieT);
+    block_sort_both(nB, keyB, ordered_to_float(h1.x), ordered_to_float(h1.y), nT, keyT, ordered_to_float(h1.z),
+                    ordered_to_float(h1.w), rankB, rankT, buckets, cv.nBk, sh.scratch, &sh.tieB, &sh.tieT);
     {
       const bool tieB = sh.tieB != 0, tieT = sh.tieT != 0;  // block-uniform (read after the sort's last barrier)
       if ((tieB || tieT) && tid == 0) sh.tie = 1;
-      if (tieB && p.exactTies && nB > 16) {
-        block_fix_ties(nB, L.u.a.uCotB, L.u.a.uSeqB, sh.winBp[nBot], rankB, tieW, tieSeqSorted, tieGrpOf, L.buckets, NBK,
-                       sh.scratch);
-      }
-      if (tieT && p.exactTies && nT > 16) {
-        block_fix_ties(nT, L.u.a.uCotT, L.u.a.uSeqT, sh.winTp[nTop], rankT, tieW, tieSeqSorted, tieGrpOf, L.buckets, NBK,
-                       sh.scratch);
-      }
-      for (uint32_t j = tid; j < nB; j += blockDim.x) {
-        const uint32_t idx = rankB[j];
-        L.bCot[j] = L.u.a.uCotB[idx];
-        L.bSeq[j] = L.u.a.uSeqB[idx];
-      }
+      if (tieB && p.exactTies && nB > 16) block_fix_ties(nB, keyB, rankB, tieW, tieGrp);
+      if (tieT && p.exactTies && nT > 16) block_fix_ties(nT, keyT, rankT, tieW, tieGrp);
     }
-    // tops: full records in sorted order (recomputed from the space points);
-    // from here on the sorted-top arrays hold what their names say
-    for (uint32_t t = tid; t < nT; t += blockDim.x) {
-      const uint32_t idx = rankT[t];
-      const uint32_t pos = seq_to_pos(L.u.a.uSeqT[idx], sh.winTp, sh.winTs, nTop);
-      const float2 zr = ldg2(p.pZR + pos), xy = ldg2(p.pXY + pos), var = ldg2(p.pVar + pos);
-      float dR, dZ;
-      DoubletRec rec;
-      doublet_zr_cuts<false>(cfg, sh.mid, zr.x, zr.y, dR, dZ);
-      doublet_finish<false>(cfg, sh.mid, dR, dZ, xy.x, xy.y, zr.y, var.x, var.y, p.zWinLo, p.zWinHi, p.nZWin, rec);
-      // all reads of the arena / scratch for this t are done before the writes below
-      L.sCot[t] = rec.cotTheta; L.sIDR[t] = rec.iDeltaR; L.sEr[t] = rec.er; L.sU[t] = rec.u; L.sV[t] = rec.v;
-      L.sPos[t] = pos;
+    // tops: full records in sorted order
+    for (uint32_t t = tid; t < nT; t += THREADS) {
+      const float4* src = reinterpret_cast<const float4*>(recT + rankT[t]);
+      const float4 a = __ldg(src), b = __ldg(src + 1);
+      sPos[t] = __float_as_uint(a.x); sCot[t] = a.y; sIDR[t] = a.z; sEr[t] = a.w; sU[t] = b.x; sV[t] = b.y;
     }
-    __syncthreads();  // the arena now belongs to phase 3
+    __syncthreads();
+    // |P_j|: tops with cotT <= cotB_j
+    for (uint32_t j = tid; j < nB; j += THREADS) {
+      const float c = keyB[rankB[j]];
+      uint32_t lo = 0, hi = nT;
+      while (lo < hi) {
+        const uint32_t md = (lo + hi) >> 1;
+        if (c < sCot[md]) hi = md; else lo = md + 1;
+      }
+      tstar[j] = (uint16_t)lo;
+    }
+    __syncthreads();  // region a (keys, rankT, tie scratch) is dead, region b starts
 
     // ---- phase 3a: H_j / brk_j scans, candidates emitted on the spot ------
-    const MiddleSp mid = sh.mid;
     uint32_t myTests = 0;
     auto bottomCtx = [&](uint32_t j, BottomCtx& bc) {
-      const uint32_t pos = seq_to_pos(L.bSeq[j], sh.winBp, sh.winBs, nBot);
-      const float2 zr = ldg2(p.pZR + pos), xy = ldg2(p.pXY + pos), var = ldg2(p.pVar + pos);
-      float dR, dZ;
-      DoubletRec rec;
-      doublet_zr_cuts<true>(cfg, mid, zr.x, zr.y, dR, dZ);
-      doublet_finish<true>(cfg, mid, dR, dZ, xy.x, xy.y, zr.y, var.x, var.y, p.zWinLo, p.zWinHi, p.nZWin, rec);
-      bc.cotThetaB = rec.cotTheta; bc.erB = rec.er; bc.iDeltaRB = rec.iDeltaR; bc.Ub = rec.u; bc.Vb = rec.v;
+      const float4* src = reinterpret_cast<const float4*>(recB + rankB[j]);
+      const float4 a = __ldg(src), b = __ldg(src + 1);
+      bc.cotThetaB = a.y; bc.iDeltaRB = a.z; bc.erB = a.w; bc.Ub = b.x; bc.Vb = b.y;
       bottom_ctx(cfg, bc);
     };
     auto emit = [&](uint32_t j, uint32_t t) {
       const uint32_t slot = atomicAdd(&sh.poolCount, 1u);
-      if (slot < (uint32_t)CAPPOOL) L.u.b.pool[slot] = t | (j << 16);
+      if (slot < poolCap) pool[slot] = t | (j << 16);
     };
-    for (;;) {  // warps pull chunks of 32 consecutive bottoms: balances uneven windows
-      uint32_t chunk = 0;
-      if (lane == 0) chunk = atomicAdd(&sh.nextChunkA, 32u);
-      chunk = __shfl_sync(0xffffffffu, chunk, 0);
-      if (chunk >= nB) break;
-      const uint32_t j = chunk + lane;
-      if (j >= nB) continue;
-      BottomCtx bc;
-      bottomCtx(j, bc);
-      uint32_t lo = 0, hi = nT;  // |P_j|: tops with cotT <= cotB
-      while (lo < hi) {
-        const uint32_t md = (lo + hi) >> 1;
-        if (bc.cotThetaB < L.sCot[md]) hi = md; else lo = md + 1;
-      }
-      // One merged loop: every lane first walks down from |P_j| - 1 to the last
-      // failing top of the prefix, then up from |P_j| to the first failing top
-      // beyond it.  Lanes switch direction individually, so a warp runs for
-      // max_j(a_j + f_j) steps instead of max_j a_j + max_j f_j.
-      uint32_t H = 0, ts = 0;
-      int tb = (int)lo - 1;
-      uint32_t tf = lo;
-      bool backDone = tb < 0, fwdDone = tf >= nT;
-      while (!(backDone && fwdDone)) {
-        const bool doBack = !backDone;
-        const uint32_t t = doBack ? (uint32_t)tb : tf;
-        ++myTests;
-        const int cls = classify_pair(cfg, mid.r, mid.varZ, mid.varR, bc, L.sCot[t], L.sEr[t], L.sIDR[t], L.sU[t], L.sV[t]);
-        const bool fail = cls == kPairFailA || cls == kPairFailB;
-        if (cls == kPairEmit) emit(j, t);
-        if (doBack) {
-          if (fail) {
-            H = cls == kPairFailA ? t + 1 : t;
-            ts = t;
-            backDone = true;
-          } else {
-            --tb;
-            backDone = tb < 0;
+    {
+      // One lane per bottom; a lane that finishes takes the next unassigned bottom as soon as kRefill lanes
+      // of its warp are idle, so the warp stays full although the windows differ in length.  Per bottom one
+      // merged loop: down from |P_j| - 1 to the last failing top of the prefix, then up from |P_j| to the
+      // first failing top beyond it.
+      constexpr uint32_t kRefill = 12;
+      bool active = false, exhausted = false;
+      uint32_t j = 0, H = 0, ts = 0, tf = 0;
+      int tb = -1;
+      bool backDone = true, fwdDone = true;
+      BottomCtx bc{};
+      for (;;) {
+        const uint32_t idleMask = __ballot_sync(0xffffffffu, !active);
+        if (!exhausted && (idleMask == 0xffffffffu || (uint32_t)__popc(idleMask) >= kRefill)) {
+          const uint32_t nIdle = (uint32_t)__popc(idleMask);
+          uint32_t first = 0;
+          if (lane == 0) first = atomicAdd(&sh.nextBottom, nIdle);
+          first = __shfl_sync(0xffffffffu, first, 0);
+          if (first + nIdle >= nB) exhausted = true;
+          if (!active) {
+            const uint32_t jn = first + (uint32_t)__popc(idleMask & ltMask);
+            if (jn < nB) {
+              j = jn;
+              bottomCtx(j, bc);
+              const uint32_t lo = tstar[j];
+              H = 0; ts = 0;
+              tb = (int)lo - 1;
+              tf = lo;
+              backDone = tb < 0;
+              fwdDone = tf >= nT;
+              active = true;
+            }
           }
-        } else {
-          if (fail) {
-            fwdDone = true;
-          } else {
-            ++tf;
-            fwdDone = tf >= nT;
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0u) {
+          if (exhausted) break;
+          continue;
+        }
+        if (active) {
+          if (!(backDone && fwdDone)) {
+            const bool doBack = !backDone;
+            const uint32_t t = doBack ? (uint32_t)tb : tf;
+            ++myTests;
+            const int cls = classify_pair(cfg, mid.r, mid.varZ, mid.varR, bc, sCot[t], sEr[t], sIDR[t], sU[t], sV[t]);
+            const bool fail = cls == kPairFailA || cls == kPairFailB;
+            if (cls == kPairEmit) emit(j, t);
+            if (doBack) {
+              if (fail) {
+                H = cls == kPairFailA ? t + 1 : t;
+                ts = t;
+                backDone = true;
+              } else {
+                --tb;
+                backDone = tb < 0;
+              }
+            } else {
+              if (fail) {
+                fwdDone = true;
+              } else {
+                ++tf;
+                fwdDone = tf >= nT;
+              }
+            }
+          }
+          if (backDone && fwdDone) {
+            hval[j] = (uint16_t)H;
+            tstar[j] = (uint16_t)ts;
+            active = false;
           }
         }
       }
-      L.u.b.hval[j] = (uint16_t)H;
-      L.u.b.tstar[j] = (uint16_t)ts;
     }
     __syncthreads();
 
     // ---- phase 3b: window start = exclusive running max of H --------------
     {
-      const uint32_t chunk = (nB + blockDim.x - 1) / blockDim.x;
+      const uint32_t chunk = (nB + THREADS - 1) / THREADS;
       const uint32_t c0 = tid * chunk, c1 = (c0 + chunk < nB) ? c0 + chunk : nB;
       uint32_t localMax = 0;
-      for (uint32_t j = c0; j < c1; ++j) localMax = localMax > L.u.b.hval[j] ? localMax : (uint32_t)L.u.b.hval[j];
+      for (uint32_t j = c0; j < c1; ++j) localMax = localMax > hval[j] ? localMax : (uint32_t)hval[j];
       uint32_t blockMax;
       uint32_t run = block_scan_exclusive(localMax, sh.scratch, blockMax, OpMax());
       for (uint32_t j = c0; j < c1; ++j) {
-        const uint32_t h = L.u.b.hval[j];
-        L.u.b.hval[j] = (uint16_t)run;
+        const uint32_t h = hval[j];
+        hval[j] = (uint16_t)run;
         run = run > h ? run : h;
       }
     }
@@ -1340,38 +1571,37 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
     // ---- phase 3c: pairs in [start_j, t*_j) that the scans did not touch --
     // few bottoms have such a gap: list them first, then one thread per listed bottom
     {
-      uint16_t* gapList = reinterpret_cast<uint16_t*>(L.u.b.pool2);  // pool2 is free until phase 3d
+      uint16_t* gapList = reinterpret_cast<uint16_t*>(pool2);  // pool2 is free until phase 3d
       if (tid == 0) sh.nSurv = 0;
       __syncthreads();
-      for (uint32_t base = 0; base < nB; base += blockDim.x) {
-        const uint32_t j = base + tid;
-        const bool has = j < nB && L.u.b.hval[j] < L.u.b.tstar[j];
+      for (uint32_t b0 = 0; b0 < nB; b0 += THREADS) {
+        const uint32_t j = b0 + tid;
+        const bool has = j < nB && hval[j] < tstar[j];
         const uint32_t slot = warp_append(&sh.nSurv, has);
         if (has) gapList[slot] = (uint16_t)j;
       }
       __syncthreads();
       const uint32_t nGap = sh.nSurv;
-      for (uint32_t q = tid; q < nGap; q += blockDim.x) {
+      for (uint32_t q = tid; q < nGap; q += THREADS) {
         const uint32_t j = gapList[q];
-        const uint32_t s = L.u.b.hval[j], te = L.u.b.tstar[j];
+        const uint32_t s = hval[j], te = tstar[j];
         BottomCtx bc;
         bottomCtx(j, bc);
         for (uint32_t t = s; t < te; ++t) {
           ++myTests;
-          const int cls = classify_pair(cfg, mid.r, mid.varZ, mid.varR, bc, L.sCot[t], L.sEr[t], L.sIDR[t], L.sU[t], L.sV[t]);
+          const int cls = classify_pair(cfg, mid.r, mid.varZ, mid.varR, bc, sCot[t], sEr[t], sIDR[t], sU[t], sV[t]);
           if (cls == kPairEmit) emit(j, t);
         }
       }
     }
-    for (uint32_t j = tid; j <= nB; j += blockDim.x) L.u.b.cnt[j] = 0;
+    for (uint32_t j = tid; j <= nB; j += THREADS) cnt[j] = 0;
     __syncthreads();
     const uint32_t poolCount = sh.poolCount;
-    if (poolCount > (uint32_t)CAPPOOL) {
+    if (poolCount > poolCap) {
       if (tid == 0) {
         p.slotCount[w] = 0;
         if (p.overflowList != nullptr) {
           p.overflowList[atomicAdd(p.overflowCount, 1u)] = w;
-          sh.cnt[kCntMiddles] -= 1;
         } else {
           atomicOr(p.status, kStatusOverflowPool);
         }
@@ -1381,36 +1611,36 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
 
     // ---- phase 3d: group the candidates by bottom, curvature order inside --
     // a candidate from the scans is only real when its top is inside the window
-    for (uint32_t e = tid; e < poolCount; e += blockDim.x) {
-      const uint32_t to = L.u.b.pool[e];
+    for (uint32_t e = tid; e < poolCount; e += THREADS) {
+      const uint32_t to = pool[e];
       const uint32_t j = to >> 16, t = to & 0xFFFFu;
-      if (t >= L.u.b.hval[j]) atomicAdd(&L.u.b.cnt[j], 1u);
+      if (t >= hval[j]) atomicAdd(&cnt[j], 1u);
     }
     __syncthreads();
-    const uint32_t nValid = block_scan_array(L.u.b.cnt, nB, sh.scratch);
-    for (uint32_t e = tid; e < poolCount; e += blockDim.x) {
-      const uint32_t to = L.u.b.pool[e];
+    const uint32_t nValid = block_scan_array(cnt, nB, sh.scratch);
+    for (uint32_t e = tid; e < poolCount; e += THREADS) {
+      const uint32_t to = pool[e];
       const uint32_t j = to >> 16, t = to & 0xFFFFu;
-      if (t < L.u.b.hval[j]) continue;
+      if (t < hval[j]) continue;
       // the candidate's curvature and impact (TripletSeedFinder.cpp:148-155), one thread per candidate
       BottomCtx bc;
       bottomCtx(j, bc);
       Cand c;
-      eval_pair(cfg, mid.r, mid.varZ, mid.varR, bc, L.sCot[t], L.sEr[t], L.sIDR[t], L.sU[t], L.sV[t], c.curv, c.impactOrWeight);
-      const float2 tzr = ldg2(p.pZR + L.sPos[t]);
+      eval_pair(cfg, mid.r, mid.varZ, mid.varR, bc, sCot[t], sEr[t], sIDR[t], sU[t], sV[t], c.curv, c.impactOrWeight);
+      const float2 tzr = ldg2(p.pZR + sPos[t]);
       c.topR = tzr.y;
       if (cfg.useDeltaRinsteadOfTopRadius) {
         const float dr = fsub(tzr.y, mid.r), dz = fsub(tzr.x, mid.z);
         c.topR = fsqrt(fadd(fmul(dr, dr), fmul(dz, dz)));
       }
       c.tOwner = to;
-      L.u.b.pool2[atomicAdd(&L.u.b.cnt[j], 1u)] = c;
+      pool2[atomicAdd(&cnt[j], 1u)] = c;
     }
     __syncthreads();  // cnt[j] is now the END of bottom j's group
-    for (uint32_t j = tid; j < nB; j += blockDim.x) {
-      const uint32_t s = j == 0 ? 0u : L.u.b.cnt[j - 1], e = L.u.b.cnt[j];
+    for (uint32_t j = tid; j < nB; j += THREADS) {
+      const uint32_t s = j == 0 ? 0u : cnt[j - 1], e = cnt[j];
       if (e - s < 2) continue;
-      Cand* grp = L.u.b.pool2 + s;
+      Cand* grp = pool2 + s;
       const int n = (int)(e - s);
       // the reference's input order is ascending top rank (emission order) ...
       for (int i = 1; i < n; ++i) {
@@ -1431,38 +1661,37 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
       // bestSeedQualityMap logic on them.
       const float rMaxSeedConfMid = conf_range(cfg, mid.z).rMaxSeedConf;  // state().rMaxSeedConf, :84
       uint32_t myKept = 0;
-      for (uint32_t i = tid; i < nValid; i += blockDim.x) {
-        const Cand c = L.u.b.pool2[i];
+      for (uint32_t i = tid; i < nValid; i += THREADS) {
+        const Cand c = pool2[i];
         const uint32_t j = c.tOwner >> 16;
-        const uint32_t s = j == 0 ? 0u : L.u.b.cnt[j - 1], e = L.u.b.cnt[j];
-        const Cand* grp = L.u.b.pool2 + s;
+        const uint32_t s = j == 0 ? 0u : cnt[j - 1], e = cnt[j];
+        const Cand* grp = pool2 + s;
         uint32_t nCompat;
         float wgt = filter_weight(
             cfg, (int)(e - s), (int)(i - s), c.impactOrWeight, [&](int q) { return grp[q].curv; },
             [&](int q) { return grp[q].topR; }, nCompat);
-        const float2 bzr = ldg2(p.pZR + seq_to_pos(L.bSeq[j], sh.winBp, sh.winBs, nBot));
-        const float zOrigin = fsub(mid.z, fmul(mid.r, L.bCot[j]));  // :119
+        const float4 br = __ldg(reinterpret_cast<const float4*>(recB + rankB[j]));  // {pos, cotTheta, ...}
+        const float2 bzr = ldg2(p.pZR + __float_as_uint(br.x));
+        const float zOrigin = fsub(mid.z, fmul(mid.r, br.y));  // :119
         int deltaSeedConf;
         const bool keepIt = conf_candidate(cfg, conf_range(cfg, bzr.x), bzr.y, zOrigin, c.impactOrWeight, nCompat, wgt, deltaSeedConf);
         uint32_t meta = j | ((e - s < 3u ? e - s : 3u) << kRecGroupSizeShift);
         if (!(bzr.y > rMaxSeedConfMid)) meta |= kRecNeedsTwoTops;  // :107-110
         if (deltaSeedConf > 0) meta |= kRecQuality;
         if (keepIt) { meta |= kRecKeep; ++myKept; }
-        L.u.b.pool2[i].impactOrWeight = wgt;  // nobody reads another candidate's impact
-        L.u.b.pool[i] = meta;                 // the emission records are dead after phase 3d
+        pool2[i].impactOrWeight = wgt;  // nobody reads another candidate's impact
+        pool[i] = meta;                 // the emission records are dead after phase 3d
       }
       uint32_t nKept;
       block_scan_exclusive(myKept, sh.scratch, nKept, OpSum());
       if (tid == 0) {
-        const uint32_t base = nKept != 0 ? atomicAdd(p.recCounter, nKept) : 0u;
-        sh.runCarry = base;
-        const bool fits = (unsigned long long)base + nKept <= (unsigned long long)p.recCapacity;
+        const uint32_t first = nKept != 0 ? atomicAdd(p.recCounter, nKept) : 0u;
+        sh.runCarry = first;
+        const bool fits = (unsigned long long)first + nKept <= (unsigned long long)p.recCapacity;
         if (!fits) atomicOr(p.status, kStatusOverflowRecords);
-        p.recBegin[w] = base;
+        p.recBegin[w] = first;
         p.recCount[w] = fits ? nKept : 0u;
         p.slotCount[w] = 0;
-        sh.cnt[kCntBottomDoublets] += nB;
-        sh.cnt[kCntTopDoublets] += nT;
         sh.cnt[kCntCandidates] += nValid;
         sh.cnt[kCntTieMiddles] += sh.tie;
       }
@@ -1470,20 +1699,20 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
       const uint32_t recBase = sh.runCarry;
       if ((unsigned long long)recBase + nKept <= (unsigned long long)p.recCapacity) {
         uint32_t carry = 0;
-        for (uint32_t base = 0; base < nValid; base += blockDim.x) {
-          const uint32_t i = base + tid;
-          const uint32_t meta = i < nValid ? L.u.b.pool[i] : 0u;
+        for (uint32_t b0 = 0; b0 < nValid; b0 += THREADS) {
+          const uint32_t i = b0 + tid;
+          const uint32_t meta = i < nValid ? pool[i] : 0u;
           const bool keepIt = (meta & kRecKeep) != 0u;
           uint32_t total;
           const uint32_t rank = carry + block_scan_exclusive(keepIt ? 1u : 0u, sh.scratch, total, OpSum());
           carry += total;
           if (keepIt) {
-            const Cand c = L.u.b.pool2[i];
+            const Cand c = pool2[i];
             const uint32_t j = meta & kRecGroupMask;
             const size_t o = (size_t)recBase + rank;
-            p.rec[o] = make_uint4(seq_to_pos(L.bSeq[j], sh.winBp, sh.winBs, nBot), L.sPos[c.tOwner & 0xFFFFu],
-                                  __float_as_uint(c.impactOrWeight), meta & ~kRecKeep);
-            p.recZ[o] = fsub(mid.z, fmul(mid.r, L.bCot[j]));
+            const float4 br = __ldg(reinterpret_cast<const float4*>(recB + rankB[j]));
+            p.rec4[o] = make_uint4(__float_as_uint(br.x), sPos[c.tOwner & 0xFFFFu], __float_as_uint(c.impactOrWeight), meta & ~kRecKeep);
+            p.recZ[o] = fsub(mid.z, fmul(mid.r, br.y));
           }
         }
       }
@@ -1492,19 +1721,20 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
       if (lane == 0) atomicAdd(&sh.cnt[kCntTripletTests], (unsigned long long)t);
     } else {
     // ---- phase 3e: one thread per candidate: weight -----------------------
-    for (uint32_t i = tid; i < nValid; i += blockDim.x) {
-      const Cand c = L.u.b.pool2[i];
+    for (uint32_t i = tid; i < nValid; i += THREADS) {
+      const Cand c = pool2[i];
       const uint32_t j = c.tOwner >> 16;
-      const uint32_t s = j == 0 ? 0u : L.u.b.cnt[j - 1], e = L.u.b.cnt[j];
-      const Cand* grp = L.u.b.pool2 + s;
+      const uint32_t s = j == 0 ? 0u : cnt[j - 1], e = cnt[j];
+      const Cand* grp = pool2 + s;
       const float wgt = filter_weight(
           cfg, (int)(e - s), (int)(i - s), c.impactOrWeight, [&](int q) { return grp[q].curv; },
           [&](int q) { return grp[q].topR; });
-      L.u.b.pool2[i].impactOrWeight = wgt;  // nobody reads another candidate's impact
+      pool2[i].impactOrWeight = wgt;  // nobody reads another candidate's impact
     }
     __syncthreads();
 
-    // ---- phase 3f: bounded heap (CandidatesForMiddleSp.cpp:44-93) ----------
+    // ---- phase 3f + 4: bounded heap (CandidatesForMiddleSp.cpp:44-93) and the per-middle
+    // selection (BroadTripletSeedFilter.cpp:324-393), all by warp 0 -----------------------
     // The heap keeps the nLow largest weights; its final sort_heap order is
     // unique unless weights tie.  Warp 0 therefore selects the nLow + 1 largest
     // weights in registers (lane r holds the r-th largest, stable in arrival
@@ -1520,7 +1750,7 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
         const uint32_t i = c0 + lane;
         float wgt = 0.f;
         uint32_t id = 0;
-        if (i < nValid) { wgt = L.u.b.pool2[i].impactOrWeight; id = L.u.b.pool2[i].tOwner; }
+        if (i < nValid) { wgt = pool2[i].impactOrWeight; id = pool2[i].tOwner; }
         const float kth = __shfl_sync(0xffffffffu, myW, keep - 1);
         uint32_t mask = __ballot_sync(0xffffffffu, i < nValid && (filled < keep || wgt > kth));
         while (mask != 0u) {
@@ -1543,30 +1773,23 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
       const float nextW = __shfl_down_sync(0xffffffffu, myW, 1);
       const bool tieHere = (int)lane + 1 < filled && myW == nextW;
       const bool anyTie = __any_sync(0xffffffffu, tieHere);
-      if (!anyTie) {
-        const int inHeap = filled < nLow ? filled : nLow;
-        if ((int)lane < inHeap) {
-          sh.heap[lane].weight = myW;
-          sh.heap[lane].index = lane;
-          sh.storage[lane].weight = myW;
-          sh.storage[lane].tOwner = myId;
-        }
-        if (lane == 0) { sh.heapSize = inHeap; sh.heapSorted = 1; }
-      } else {
+      int inHeap = filled < nLow ? filled : nLow;
+      if (anyTie) {
         // literal replay in the reference's push order (bottom-major, curvature order)
-        if (lane == 0) sh.heapSorted = 0;
+        if (lane == 0) { sh.heapSize = 0; }
+        __syncwarp();
         for (uint32_t c0 = 0; c0 < nValid && nLow > 0; c0 += 32) {
-          const uint32_t i = c0 + tid;
+          const uint32_t i = c0 + lane;
           const int hs = sh.heapSize;
           const float hmin = sh.heapMin;
           bool want = false;
-          if (i < nValid) want = (hs < nLow) || (L.u.b.pool2[i].impactOrWeight > hmin);
+          if (i < nValid) want = (hs < nLow) || (pool2[i].impactOrWeight > hmin);
           uint32_t mask = __ballot_sync(0xffffffffu, want);
-          if (tid == 0) {
+          if (lane == 0) {
             while (mask != 0u) {
               const uint32_t q = c0 + (uint32_t)(__ffs(mask) - 1);
               mask &= mask - 1u;
-              const Cand c = L.u.b.pool2[q];
+              const Cand c = pool2[q];
               const float wq = c.impactOrWeight;
               StoredSeed sd;
               sd.tOwner = c.tOwner;
@@ -1592,55 +1815,47 @@ k_seed_middles(const __grid_constant__ SeedParams p) {
           }
           __syncwarp();
         }
+        if (lane == 0) std_sort_heap(sh.heap, sh.heapSize, heap_comp);
+        __syncwarp();
+        inHeap = sh.heapSize;
+        if ((int)lane < inHeap) {
+          const StoredSeed sd = sh.storage[sh.heap[lane].index];
+          myW = sd.weight;
+          myId = sd.tOwner;
+        }
       }
-    }
-    {
+      // phase 4: lane i writes seed i
+      uint32_t maxSeeds = (uint32_t)inHeap;
+      if (maxSeeds > cfg.maxSeedsPerSpM) maxSeeds = cfg.maxSeedsPerSpM + 1;
+      if (lane < maxSeeds) {
+        const uint32_t j = myId >> 16, tRank = myId & 0xFFFFu;
+        const float4 br = __ldg(reinterpret_cast<const float4*>(recB + rankB[j]));
+        const size_t o = (size_t)w * p.seedsPerMiddle + lane;
+        p.slotB[o] = __float_as_uint(br.x);
+        p.slotM[o] = m;
+        p.slotT[o] = sPos[tRank];
+        p.slotQ[o] = myW;
+        p.slotZ[o] = fsub(mid.z, fmul(mid.r, br.y));  // zOrigin, BroadTripletSeedFilter.cpp:119
+      }
+      uint32_t t = myTests;
+      for (int d = 16; d > 0; d >>= 1) t += __shfl_down_sync(0xffffffffu, t, d);
+      if (lane == 0) {
+        p.slotCount[w] = maxSeeds;
+        atomicAdd(&sh.cnt[kCntTripletTests], (unsigned long long)t);
+        sh.cnt[kCntCandidates] += nValid;
+        sh.cnt[kCntSeeds] += maxSeeds;
+        sh.cnt[kCntTieMiddles] += sh.tie;
+      }
+    } else {
       uint32_t t = myTests;
       for (int d = 16; d > 0; d >>= 1) t += __shfl_down_sync(0xffffffffu, t, d);
       if (lane == 0) atomicAdd(&sh.cnt[kCntTripletTests], (unsigned long long)t);
     }
-    __syncthreads();
-
-    // ---- phase 4: per-middle selection (BroadTripletSeedFilter.cpp:324-393)
-    if (tid == 0) {
-      uint32_t nOut = 0;
-      if (!sh.heapSorted) std_sort_heap(sh.heap, sh.heapSize, heap_comp);
-      uint32_t maxSeeds = (uint32_t)sh.heapSize;
-      if (maxSeeds > cfg.maxSeedsPerSpM) maxSeeds = cfg.maxSeedsPerSpM + 1;
-      for (uint32_t i = 0; i < (uint32_t)sh.heapSize && i < maxSeeds; ++i) {
-        const StoredSeed sd = sh.storage[sh.heap[i].index];
-        const uint32_t j = sd.tOwner >> 16, tRank = sd.tOwner & 0xFFFFu;
-        const size_t o = (size_t)w * p.seedsPerMiddle + i;
-        p.slotB[o] = seq_to_pos(L.bSeq[j], sh.winBp, sh.winBs, nBot);
-        p.slotM[o] = m;
-        p.slotT[o] = L.sPos[tRank];
-        p.slotQ[o] = sd.weight;
-        p.slotZ[o] = fsub(mid.z, fmul(mid.r, L.bCot[j]));  // zOrigin, BroadTripletSeedFilter.cpp:119
-        ++nOut;
-      }
-      p.slotCount[w] = nOut;
-      sh.cnt[kCntBottomDoublets] += nB;
-      sh.cnt[kCntTopDoublets] += nT;
-      sh.cnt[kCntCandidates] += nValid;
-      sh.cnt[kCntSeeds] += nOut;
-      sh.cnt[kCntTieMiddles] += sh.tie;
-    }
     }  // !kConf
   }
   __syncthreads();
-  if (tid < (uint32_t)kCntSlots && tid != (uint32_t)kCntInGrid && sh.cnt[tid] != 0ull) {
-    atomicAdd(p.counters + tid, sh.cnt[tid]);
-  }
+  if (tid < (uint32_t)kCntSlots && sh.cnt[tid] != 0ull) atomicAdd(p.counters + tid, sh.cnt[tid]);
 }
-
-// the capacity tiers (see seeding_plugin.cu): {bottoms, tops, candidates, buckets, threads}
-// Measured on B200 at <mu>=200 (profiles/README.md): 3 tiers (3/2/1 blocks per SM) 8.4 ms/event,
-// 2 tiers (2/1) 10.0 ms, 4 tiers with a 256-thread 4-blocks-per-SM first tier 9.0 ms.
-struct Tier0 { static constexpr int B = 1536, T = 1152, P = 768, K = 1024, N = 384; };
-struct Tier1 { static constexpr int B = 2304, T = 1664, P = 1216, K = 2048, N = 512; };
-struct Tier2 { static constexpr int B = 3584, T = 2816, P = 4096, K = 2048, N = 512; };
-template <typename TR> using TierLayout = SeedLayout<TR::B, TR::T, TR::P, TR::K>;
-constexpr int kNumTiers = 3;
 
 // ---------------------------------------------------------------------------
 // Seed compaction (ordered): tiled exclusive scan of the per-middle counts
@@ -1975,112 +2190,6 @@ __global__ void __launch_bounds__(kConfWarps * 32) k_conf_replay(const __grid_co
     }
   }
   if (lane == 0 && myChanged != 0u) atomicAdd(p.changed + p.round, myChanged);
-}
-
-// ---------------------------------------------------------------------------
-// Materialised doublet search (two-pass count / scan / fill), one warp per
-// middle space point.  This is the north star's "allocation-free two-pass"
-// variant: every compatible doublet is written to HBM as a 32-byte record in the
-// reference's emission order (neighbour bins in order, ascending position).
-// The production path keeps the doublets in shared memory instead (DESIGN.md
-// section 6); this path backs b200seed_debug_doublets (stage-level parity) and the
-// measurement of the HBM-bound variant.
-// ---------------------------------------------------------------------------
-struct DoubletDumpParams {
-  DeviceConfig cfg;
-  const float2 *pXY, *pZR, *pVar;
-  const uint32_t* binStart;
-  const uint32_t *navBins, *botOffsets, *botBins, *topOffsets, *topBins;
-  const uint32_t *workPos, *workEG;
-  uint32_t nWork, nNav, nBins;
-  const float *zWinLo, *zWinHi;
-  int nZWin;
-  uint32_t* count;       // [nWork]  bottoms + tops
-  uint32_t* nBottom;     // [nWork]
-  const uint32_t* first; // [nWork + 1] exclusive scan of count (fill pass)
-  uint32_t* otherPos;
-  float *cotTheta, *iDeltaR, *er, *u, *v, *xNew, *yNew;
-};
-
-template <bool kFill>
-__global__ void __launch_bounds__(256) k_doublets_materialised(const __grid_constant__ DoubletDumpParams p) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t ltMask = (1u << lane) - 1u;
-  const uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
-  const DeviceConfig& cfg = p.cfg;
-  for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < p.nWork; w += warpsPerGrid) {
-    const uint32_t m = __ldg(p.workPos + w);
-    const uint32_t eg = __ldg(p.workEG + w);
-    const uint32_t ev = eg / p.nNav, g = eg - ev * p.nNav;
-    const uint32_t* bs = p.binStart + (size_t)ev * p.nBins;
-    const uint32_t botBeg = __ldg(p.botOffsets + g), nBot = __ldg(p.botOffsets + g + 1) - botBeg;
-    const uint32_t topBeg = __ldg(p.topOffsets + g), nTop = __ldg(p.topOffsets + g + 1) - topBeg;
-    MiddleSp mid;
-    {
-      const float2 mxy = ldg2(p.pXY + m), mzr = ldg2(p.pZR + m), mvar = ldg2(p.pVar + m);
-      mid.x = mxy.x; mid.y = mxy.y; mid.z = mzr.x; mid.r = mzr.y; mid.varZ = mvar.x; mid.varR = mvar.y;
-      middle_info(mid);
-    }
-    const float rM = mid.r;
-    const float firstMiddleR = ldg2(p.pZR + bs[__ldg(p.navBins + g)]).y;
-    uint32_t out = kFill ? p.first[w] : 0u;
-    uint32_t nB = 0, nAll = 0;
-    for (uint32_t side = 0; side < 2; ++side) {  // bottoms first, then tops
-      const uint32_t nWin = side == 0 ? nBot : nTop;
-      for (uint32_t k = 0; k < nWin; ++k) {
-        const uint32_t bin = __ldg((side == 0 ? p.botBins + botBeg : p.topBins + topBeg) + k);
-        const uint32_t b0 = bs[bin], b1 = bs[bin + 1];
-        uint32_t s, e;
-        if (side == 0) {
-          const float trimValue = fsub(firstMiddleR, cfg.dRMaxB);
-          const uint32_t trim = warp_first_true(b0, b1, [&](uint32_t i) { return !(ldg2(p.pZR + i).y < trimValue); });
-          s = warp_first_true(trim, b1, [&](uint32_t i) { return fsub(rM, ldg2(p.pZR + i).y) <= cfg.dRMaxB; });
-          e = warp_first_true(s, b1, [&](uint32_t i) { return fsub(rM, ldg2(p.pZR + i).y) < cfg.dRMinB; });
-        } else {
-          const float trimValue = fadd(firstMiddleR, cfg.dRMinT);
-          const uint32_t trim = warp_first_true(b0, b1, [&](uint32_t i) { return !(ldg2(p.pZR + i).y < trimValue); });
-          s = warp_first_true(trim, b1, [&](uint32_t i) { return fsub(ldg2(p.pZR + i).y, rM) >= cfg.dRMinT; });
-          e = warp_first_true(s, b1, [&](uint32_t i) { return fsub(ldg2(p.pZR + i).y, rM) > cfg.dRMaxT; });
-        }
-        for (uint32_t base = s; base < e; base += 32) {
-          const uint32_t o = base + lane;
-          bool pass = false;
-          DoubletRec rec;
-          if (o < e) {
-            const float2 zr = ldg2(p.pZR + o);
-            float dR, dZ;
-            const bool ok = side == 0 ? doublet_zr_cuts<true>(cfg, mid, zr.x, zr.y, dR, dZ)
-                                      : doublet_zr_cuts<false>(cfg, mid, zr.x, zr.y, dR, dZ);
-            if (ok) {
-              const float2 xy = ldg2(p.pXY + o), var = ldg2(p.pVar + o);
-              pass = side == 0 ? doublet_finish<true>(cfg, mid, dR, dZ, xy.x, xy.y, zr.y, var.x, var.y, p.zWinLo, p.zWinHi, p.nZWin, rec)
-                               : doublet_finish<false>(cfg, mid, dR, dZ, xy.x, xy.y, zr.y, var.x, var.y, p.zWinLo, p.zWinHi, p.nZWin, rec);
-            }
-          }
-          const uint32_t mask = __ballot_sync(0xffffffffu, pass);
-          if (kFill && pass) {
-            const uint32_t d = out + (uint32_t)__popc(mask & ltMask);
-            p.otherPos[d] = o;
-            p.cotTheta[d] = rec.cotTheta;
-            p.iDeltaR[d] = rec.iDeltaR;
-            p.er[d] = rec.er;
-            p.u[d] = rec.u;
-            p.v[d] = rec.v;
-            p.xNew[d] = rec.xNew;
-            p.yNew[d] = rec.yNew;
-          }
-          const uint32_t c = (uint32_t)__popc(mask);
-          out += c;
-          nAll += c;
-        }
-      }
-      if (side == 0) nB = nAll;
-    }
-    if (!kFill && lane == 0) {
-      p.count[w] = nAll;
-      p.nBottom[w] = nB;
-    }
-  }
 }
 
 // Free track parameters of every seed (Acts::estimateTrackParamsFromSeed,

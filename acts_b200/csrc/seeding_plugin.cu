@@ -84,17 +84,26 @@ struct b200seed_handle {
   uint32_t sortSmemCap = 4096;
   int exactTies = 1;
   uint32_t phiFirst = 1, phiCount = 0xFFFFFFFFu;  // middle phi-bin sector (default: all)
-  int seedBlocksPerSM[kNumTiers] = {1, 1, 1};
-  size_t seedSmemBytes[kNumTiers] = {0, 0, 0};
+  // shared-memory classes of the seeding kernel (seeding_kernels.cuh): blocks per SM, dynamic bytes per block
+  int classBlocksPerSM[kNumSeedClasses] = {1, 1, 1, 1, 1, 1};
+  uint32_t classBytes[kNumSeedClasses] = {0, 0, 0, 0, 0, 0};
+  int doubletBlocksPerSM[2] = {1, 1};  // count / fill
+  size_t arenaMaxBytes = (size_t)2048 << 20;  // B200SEED_ARENA_MB: doublet arena per chunk of middles
   // constant tables
   DevBuf navBins, botOffsets, botBins, topOffsets, topBins;
   // per-batch workspaces
   DevBuf inOffsets, inX, inY, inZ, inR, inVarZ, inVarR;  // staging of host inputs
   DevBuf binOf, binCount, binStart, binCursor, tmpIdx, pIdx, pXY, pZR, pVar, sortScratch;
-  DevBuf midLo, midCount, workStart, workPos, workEG, workCounter, overflowList;
+  DevBuf midLo, midCount, workStart, workPos, workEG, workCounter;
+  // doublet stage: slot sizes and prefix, chunk plan, arena, per-middle headers, per-class work lists
+  DevBuf capB, capT, slotPrefix, capTileSums, capTilePrefix, planDev, hdr, classList, arenaRec, arenaKey, spillScratch;
+  uint32_t* hPlan = nullptr;  // pinned: planWords[8] + chunkBounds[kMaxChunks + 1]
+  std::vector<uint32_t> lastChunkBounds;  // of the last call (debug_doublets)
   DevBuf slotB, slotM, slotT, slotQ, slotZ, slotCount, seedStart, tileSums, tilePrefix;
   DevBuf outB, outM, outT, outQ, outZ, seedOffsets;  // device outputs of the host API
-  DevBuf counters, status, zWin;
+  DevBuf counters, status, zWin, zWinOffsets;
+  uint32_t zWinCapacity = 1;  // windows per column of zWin (lo column, then hi column)
+  DoubletParams lastDoublets{};  // of the last call (debug_doublets re-runs the fill pass chunk by chunk)
   // seedConfirmation: candidate records, second slot set, per-space-point seed lists, {record counter, changed[round]}
   DevBuf rec, recZ, recBegin, recCount, slot2B, slot2M, slot2T, slot2Q, slot2Z, slot2Count, confHead, confNext, confState, confDirty;
   uint32_t* hConfState = nullptr;  // pinned mirror of confState
@@ -109,6 +118,8 @@ struct b200seed_handle {
     const uint32_t* dOffsets = nullptr;
     const float *x = nullptr, *y = nullptr, *z = nullptr, *r = nullptr, *varZ = nullptr, *varR = nullptr, *dPhi = nullptr;
     int nZWin = 0;
+    bool vertexCuts = false;            // VertexZCuts connected (cfg.useVertexZCuts, or windows given)
+    const uint32_t* dZWinOffsets = nullptr;  // per-event window ranges (NULL: all events share [0, nZWin))
     uint32_t *outB = nullptr, *outM = nullptr, *outT = nullptr;
     float *outQ = nullptr, *outZ = nullptr;
     unsigned long long outCapacity = 0;
@@ -130,7 +141,11 @@ struct b200seed_handle {
   uint64_t launches = 0;
   // stage boundaries of the last call: start | grid | work list | seeding | compaction
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  float stageMs[4] = {0, 0, 0, 0};
+  // inside the seeding stage: after the count pass + chunk plan, then (after fill, after seeding) per chunk
+  cudaEvent_t evCount = nullptr;
+  std::vector<cudaEvent_t> evChunk;
+  uint32_t chunksTimed = 0;
+  float stageMs[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // grid, work list, seeding, compaction, doublet count, doublet fill, seed middles
 };
 
 namespace {
@@ -161,8 +176,13 @@ int ensure_workspace(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal) {
   CUDA_TRY(h->workStart.reserve((nNavAll + 1) * 4));
   CUDA_TRY(h->workPos.reserve(nT * 4));
   CUDA_TRY(h->workEG.reserve(nT * 4));
-  CUDA_TRY(h->workCounter.reserve(64));
-  CUDA_TRY(h->overflowList.reserve(nT * 4 * (kNumTiers - 1)));
+  CUDA_TRY(h->workCounter.reserve(16 * 4 * ((size_t)kMaxChunks + 2)));
+  CUDA_TRY(h->capB.reserve(nT * 4));
+  CUDA_TRY(h->capT.reserve(nT * 4));
+  CUDA_TRY(h->slotPrefix.reserve((nT + 1) * 8));
+  CUDA_TRY(h->hdr.reserve(nT * sizeof(MiddleHeader)));
+  CUDA_TRY(h->classList.reserve(nT * 4 * kNumSeedClasses));
+  CUDA_TRY(h->planDev.reserve(((size_t)kMaxChunks + 1 + 8) * 4));
   CUDA_TRY(h->slotB.reserve(nT * K * 4));
   CUDA_TRY(h->slotM.reserve(nT * K * 4));
   CUDA_TRY(h->slotT.reserve(nT * K * 4));
@@ -173,9 +193,10 @@ int ensure_workspace(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal) {
   const size_t nTiles = (nT + kTile - 1) / kTile;
   CUDA_TRY(h->tileSums.reserve((nTiles + 1) * 4));
   CUDA_TRY(h->tilePrefix.reserve((nTiles + 1) * 4));
+  CUDA_TRY(h->capTileSums.reserve((nTiles + 1) * 8));
+  CUDA_TRY(h->capTilePrefix.reserve((nTiles + 1) * 8));
   CUDA_TRY(h->counters.reserve(kCntSlots * 8));
   CUDA_TRY(h->status.reserve(16));
-  CUDA_TRY(h->zWin.reserve(2 * kMaxZWindows * 4));
   if (h->plan.dev.seedConfirmation) {
     if (h->recCapacity < (size_t)h->recPerSpacePoint * nT) h->recCapacity = (size_t)h->recPerSpacePoint * nT;  // grown on demand by finish()
     h->recCapacity = std::min<size_t>(h->recCapacity, 0xFFFFFFF0u);
@@ -197,10 +218,18 @@ int ensure_workspace(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal) {
   return B200SEED_OK;
 }
 
-template <typename TR, bool kConf>
-constexpr auto seed_kernel() {
-  return k_seed_middles<TR::B, TR::T, TR::P, TR::K, TR::N, kConf>;
+// Shared-memory classes of k_seed_middles: {threads, blocks per SM aimed at}.  A middle goes to the smallest class
+// whose dynamic shared memory holds its lists (exact sizes, SeedCarve); the last class keeps them in global memory.
+struct SeedClassShape { int threads, blocksPerSM; };
+// (64 registers per thread: 32 warps fit an SM)
+constexpr SeedClassShape kSeedClassShape[kNumSeedClasses] = {{160, 6}, {256, 4}, {320, 3}, {512, 2}, {1024, 1}, {1024, 1}};
+
+using SeedKernel = void (*)(const SeedParams);
+template <bool kConf>
+SeedKernel seed_kernel(int c) {
+  return c == kSpillClass ? k_seed_middles<kConf, true> : k_seed_middles<kConf, false>;
 }
+SeedKernel seed_kernel(bool conf, int c) { return conf ? seed_kernel<true>(c) : seed_kernel<false>(c); }
 
 // Rounds [first, first + count) of the seedConfirmation fixed point (seeding_kernels.cuh, k_conf_replay).
 // Round r reads the seeds of slot set (r + 1) & 1 and writes set r & 1.
@@ -279,7 +308,7 @@ int enqueue(b200seed_handle* h) {
 
   CUDA_TRY(cudaMemsetAsync(h->binCount.ptr, 0, ((size_t)nBinsAll + 1) * 4, s));
   CUDA_TRY(cudaMemsetAsync(h->binCursor.ptr, 0, ((size_t)nBinsAll + 1) * 4, s));
-  CUDA_TRY(cudaMemsetAsync(h->workCounter.ptr, 0, 64, s));
+  CUDA_TRY(cudaMemsetAsync(h->workCounter.ptr, 0, 16 * 4 * ((size_t)kMaxChunks + 2), s));
   CUDA_TRY(cudaMemsetAsync(h->counters.ptr, 0, kCntSlots * 8, s));
   CUDA_TRY(cudaMemsetAsync(h->status.ptr, 0, 16, s));
 
@@ -338,22 +367,107 @@ int enqueue(b200seed_handle* h) {
   launches += 3;
 
   CUDA_TRY(cudaEventRecord(h->ev[2], s));
+  const bool conf = plan.dev.seedConfirmation != 0;
+  const uint32_t nWorkMax = std::max<uint32_t>(nTotal, 1);
+  uint32_t* wc = h->workCounter.as<uint32_t>();  // 16 words per launch group: [0] count pass, [1 + c] chunk c
+  uint32_t* planWords = h->planDev.as<uint32_t>();
+  CUDA_TRY(cudaMemsetAsync(planWords, 0, 8 * 4, s));
+
+  // ---- doublet stage, pass 1: slot sizes ------------------------------------
+  DoubletParams dp{};
+  dp.cfg = plan.dev;
+  if (h->last.vertexCuts) dp.cfg.doubletCuts = kCutsVertexZ;  // takes the experimentCuts slot, .cpp:291-296
+  dp.pXY = gp.pXY; dp.pZR = gp.pZR; dp.pVar = gp.pVar;
+  dp.binStart = gp.binStart;
+  dp.navBins = h->navBins.as<uint32_t>();
+  dp.botOffsets = h->botOffsets.as<uint32_t>();
+  dp.botBins = h->botBins.as<uint32_t>();
+  dp.topOffsets = h->topOffsets.as<uint32_t>();
+  dp.topBins = h->topBins.as<uint32_t>();
+  dp.workPos = wp.workPos; dp.workEG = wp.workEG;
+  dp.nWorkPtr = wp.workStart + nNavAll;
+  dp.nNav = nNav; dp.nBins = nBins;
+  dp.zWinLo = h->zWin.as<float>();
+  dp.zWinHi = h->zWin.as<float>() + h->zWinCapacity;
+  dp.zWinOffsets = a.dZWinOffsets;
+  dp.nZWin = nZWin;
+  dp.workCounter = wc;
+  dp.capB = h->capB.as<uint32_t>(); dp.capT = h->capT.as<uint32_t>();
+  dp.planWords = planWords;
+  dp.slotPrefix = h->slotPrefix.as<unsigned long long>();
+  dp.hdr = h->hdr.as<MiddleHeader>();
+  dp.slotCount = h->slotCount.as<uint32_t>();
+  dp.classList = h->classList.as<uint32_t>();
+  dp.classStride = nWorkMax;
+  for (int c = 0; c < kNumSeedClasses; ++c) dp.classBytes[c] = h->classBytes[c];
+  dp.conf = conf ? 1 : 0;
+  dp.counters = gp.counters;
+  dp.status = gp.status;
+  k_doublets<false><<<h->smCount * h->doubletBlocksPerSM[0], kDoubletWarps * 32, 0, s>>>(dp);
+  ++launches;
+
+  // ---- slot prefix, chunk plan; the host reads the plan (the one synchronisation inside a call) ---
+  const uint32_t nTiles = std::max<uint32_t>(1, (nTotal + kTile - 1) / kTile);
+  const unsigned long long arenaRecordsMax = std::max<unsigned long long>(h->arenaMaxBytes / 36ull, 4ull * kMaxListLength);
+  SlotScanParams ssp{};
+  ssp.nWorkPtr = dp.nWorkPtr;
+  ssp.capB = dp.capB; ssp.capT = dp.capT;
+  ssp.tileSums = h->capTileSums.as<unsigned long long>();
+  ssp.tilePrefix = h->capTilePrefix.as<unsigned long long>();
+  ssp.slotPrefix = h->slotPrefix.as<unsigned long long>();
+  ssp.arenaRecords = arenaRecordsMax;
+  ssp.chunkBounds = planWords + 8;
+  ssp.planWords = planWords;
+  ssp.status = gp.status;
+  k_cap_tile_sums<<<nTiles, 256, 0, s>>>(ssp);
+  k_scan_u64<<<1, 32, 0, s>>>(ssp.tileSums, ssp.tilePrefix, nTiles);
+  k_cap_prefix<<<nTiles, 256, 0, s>>>(ssp);
+  k_plan_chunks<<<1, 1, 0, s>>>(ssp);
+  launches += 4;
+  CUDA_TRY(cudaEventRecord(h->evCount, s));
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(h->hPlan, planWords, (8 + (size_t)kMaxChunks + 1) * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h->hStatus, h->status.ptr, 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (*h->hStatus & kStatusOverflowDoublets) {
+    return fail(B200SEED_ERR_OVERFLOW, "a middle space point with more than " + std::to_string(kMaxListLength) +
+                                           " doublet candidates on one side (16-bit ranks)");
+  }
+  if (*h->hStatus & kStatusArenaTooSmall) {
+    return fail(B200SEED_ERR_OVERFLOW, "doublet arena too small for this batch: raise B200SEED_ARENA_MB");
+  }
+  const uint32_t nChunks = h->hPlan[3];
+  const uint32_t* bounds = h->hPlan + 8;
+  h->lastChunkBounds.assign(bounds, bounds + nChunks + 1);
+  // arena: the largest chunk (its slots are the prefix difference, read back below with the plan)
+  unsigned long long chunkRecordsMax = 0;
+  {
+    std::vector<unsigned long long> edge(nChunks + 1, 0ull);
+    for (uint32_t c = 0; c <= nChunks; ++c) {
+      CUDA_TRY(cudaMemcpyAsync(&edge[c], h->slotPrefix.as<unsigned long long>() + bounds[c], 8, cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (uint32_t c = 0; c < nChunks; ++c) chunkRecordsMax = std::max(chunkRecordsMax, edge[c + 1] - edge[c]);
+  }
+  CUDA_TRY(h->arenaRec.reserve(std::max<size_t>(64, (size_t)chunkRecordsMax * sizeof(DoubletRecord))));
+  CUDA_TRY(h->arenaKey.reserve(std::max<size_t>(64, (size_t)chunkRecordsMax * 4)));
+  // spill class: per-block scratch for the largest lists of the batch + a candidate pool
+  const uint32_t maxCapB = h->hPlan[1], maxCapT = h->hPlan[2];
+  const SeedCarve spillCarve = seed_carve(std::max<uint32_t>(maxCapB, 1), std::max<uint32_t>(maxCapT, 1));
+  const uint32_t spillPool = std::max<uint32_t>(4u * seed_pool_min(maxCapB), 1u << 18);
+  const uint32_t spillBytes = carve_align(spillCarve.oPool + kPoolEntryBytes * spillPool + 64);
+  const bool spillLikely = h->hPlan[0] > h->classBytes[kSpillClass - 1];
+  const int spillBlocks = spillLikely ? h->smCount * 2 : 16;
+  CUDA_TRY(h->spillScratch.reserve((size_t)spillBytes * (size_t)spillBlocks));
+
   SeedParams sp{};
-  sp.cfg = plan.dev;
-  if (nZWin > 0) sp.cfg.doubletCuts = kCutsVertexZ;  // takes the experimentCuts slot, .cpp:291-296
+  sp.cfg = dp.cfg;
   sp.pXY = gp.pXY; sp.pZR = gp.pZR; sp.pVar = gp.pVar;
-  sp.binStart = gp.binStart;
-  sp.navBins = h->navBins.as<uint32_t>();
-  sp.botOffsets = h->botOffsets.as<uint32_t>();
-  sp.botBins = h->botBins.as<uint32_t>();
-  sp.topOffsets = h->topOffsets.as<uint32_t>();
-  sp.topBins = h->topBins.as<uint32_t>();
-  sp.workPos = wp.workPos; sp.workEG = wp.workEG;
-  sp.nWorkPtr = wp.workStart + nNavAll;
-  sp.nNav = nNav; sp.nBins = nBins;
-  sp.zWinLo = h->zWin.as<float>();
-  sp.zWinHi = h->zWin.as<float>() + kMaxZWindows;
-  sp.nZWin = nZWin;
+  sp.workPos = wp.workPos;
+  sp.hdr = dp.hdr;
+  sp.rec = h->arenaRec.as<DoubletRecord>();
+  sp.key = h->arenaKey.as<float>();
+  sp.spillScratch = h->spillScratch.as<unsigned char>();
   sp.slotB = h->slotB.as<uint32_t>(); sp.slotM = h->slotM.as<uint32_t>(); sp.slotT = h->slotT.as<uint32_t>();
   sp.slotQ = h->slotQ.as<float>(); sp.slotZ = h->slotZ.as<float>();
   sp.slotCount = h->slotCount.as<uint32_t>();
@@ -361,53 +475,58 @@ int enqueue(b200seed_handle* h) {
   sp.exactTies = h->exactTies;
   sp.counters = gp.counters;
   sp.status = gp.status;
-  const bool conf = plan.dev.seedConfirmation != 0;
   if (conf) {
-    sp.rec = h->rec.as<uint4>();
+    sp.rec4 = h->rec.as<uint4>();
     sp.recZ = h->recZ.as<float>();
     sp.recBegin = h->recBegin.as<uint32_t>();
     sp.recCount = h->recCount.as<uint32_t>();
     sp.recCounter = h->confState.as<uint32_t>();
     sp.recCapacity = (uint32_t)h->recCapacity;
-    CUDA_TRY(cudaMemsetAsync(h->recCount.ptr, 0, (size_t)std::max<uint32_t>(nTotal, 1) * 4, s));
+    CUDA_TRY(cudaMemsetAsync(h->recCount.ptr, 0, (size_t)nWorkMax * 4, s));
     CUDA_TRY(cudaMemsetAsync(h->confState.ptr, 0, kConfStateWords * 4, s));
   }
-  // Capacity tiers: tier 0 takes every middle with the smallest scratch (most
-  // blocks per SM); a middle whose lists do not fit is re-queued to the next
-  // tier.  workCounter words: [2k] ticket of tier k, [2k+1] overflow count k -> k+1.
-  {
-    uint32_t* wc = h->workCounter.as<uint32_t>();
-    uint32_t* ovBase = h->overflowList.as<uint32_t>();
-    const size_t ovStride = std::max<uint32_t>(nTotal, 1);
-    auto launchTier = [&](int t, auto kernel, int threads) {
-      sp.workCounter = wc + 2 * t;
-      sp.workList = t == 0 ? nullptr : ovBase + (size_t)(t - 1) * ovStride;
-      sp.nWorkPtr = t == 0 ? wp.workStart + nNavAll : wc + 2 * (t - 1) + 1;
-      const bool last = t == kNumTiers - 1;
-      sp.overflowList = last ? nullptr : ovBase + (size_t)t * ovStride;
-      sp.overflowCount = last ? nullptr : wc + 2 * t + 1;
-      kernel<<<h->smCount * h->seedBlocksPerSM[t], threads, h->seedSmemBytes[t], s>>>(sp);
-    };
-    if (conf) {
-      launchTier(0, seed_kernel<Tier0, true>(), Tier0::N);
-      launchTier(1, seed_kernel<Tier1, true>(), Tier1::N);
-      launchTier(2, seed_kernel<Tier2, true>(), Tier2::N);
-    } else {
-      launchTier(0, seed_kernel<Tier0, false>(), Tier0::N);
-      launchTier(1, seed_kernel<Tier1, false>(), Tier1::N);
-      launchTier(2, seed_kernel<Tier2, false>(), Tier2::N);
-    }
+  dp.rec = h->arenaRec.as<DoubletRecord>();
+  dp.key = h->arenaKey.as<float>();
+  // ---- per chunk: doublet fill, then the seeding kernel of every shared-memory class --------
+  while (h->evChunk.size() < 2 * (size_t)nChunks) {
+    cudaEvent_t e = nullptr;
+    CUDA_TRY(cudaEventCreate(&e));
+    h->evChunk.push_back(e);
   }
+  h->chunksTimed = nChunks;
+  for (uint32_t c = 0; c < nChunks; ++c) {
+    uint32_t* cw = wc + 16 * (c + 1);  // [0] fill ticket, [1 + k] ticket of class k, [8 + k] list length of class k
+    dp.itemFirst = bounds[c];
+    dp.itemEnd = bounds[c + 1];
+    dp.workCounter = cw;
+    dp.classCount = cw + 8;
+    k_doublets<true><<<h->smCount * h->doubletBlocksPerSM[1], kDoubletWarps * 32, 0, s>>>(dp);
+    CUDA_TRY(cudaEventRecord(h->evChunk[2 * c], s));
+    for (int k = 0; k < kNumSeedClasses; ++k) {
+      const bool last = k == kSpillClass;
+      sp.workList = dp.classList + (size_t)k * dp.classStride;
+      sp.nWorkPtr = cw + 8 + k;
+      sp.workCounter = cw + 1 + k;
+      sp.overflowList = last ? nullptr : dp.classList + (size_t)(k + 1) * dp.classStride;
+      sp.overflowCount = last ? nullptr : cw + 8 + k + 1;
+      sp.arrayBytes = last ? spillBytes : h->classBytes[k];
+      const int blocks = last ? spillBlocks : h->smCount * h->classBlocksPerSM[k];
+      seed_kernel(conf, k)<<<blocks, kSeedClassShape[k].threads, last ? 0 : h->classBytes[k], s>>>(sp);
+    }
+    CUDA_TRY(cudaEventRecord(h->evChunk[2 * c + 1], s));
+    launches += 1 + kNumSeedClasses;
+  }
+  CUDA_TRY(cudaGetLastError());
   sp.nWorkPtr = wp.workStart + nNavAll;
-  launches += kNumTiers;
   h->launches = launches;
+  h->lastDoublets = dp;
   if (conf) {
     ConfParams& cf = h->confParams;
     cf = ConfParams{};
     cf.cfg = plan.dev;
     cf.nWorkPtr = sp.nWorkPtr;
     cf.workPos = sp.workPos;
-    cf.rec = sp.rec; cf.recZ = sp.recZ; cf.recBegin = sp.recBegin; cf.recCount = sp.recCount;
+    cf.rec = sp.rec4; cf.recZ = sp.recZ; cf.recBegin = sp.recBegin; cf.recCount = sp.recCount;
     cf.head = h->confHead.as<int>();
     cf.next = h->confNext.as<int>();
     cf.seedsPerMiddle = sp.seedsPerMiddle;
@@ -477,6 +596,17 @@ int finish(b200seed_handle* h, cudaStream_t s, b200seed_seeds* out) {
   for (int i = 0; i < 4; ++i) {
     if (cudaEventElapsedTime(&h->stageMs[i], h->ev[i], h->ev[i + 1]) != cudaSuccess) h->stageMs[i] = 0.f;
   }
+  {
+    float t = 0.f;
+    h->stageMs[4] = cudaEventElapsedTime(&t, h->ev[2], h->evCount) == cudaSuccess ? t : 0.f;
+    h->stageMs[5] = 0.f;
+    h->stageMs[6] = 0.f;
+    for (uint32_t c = 0; c < h->chunksTimed; ++c) {
+      cudaEvent_t before = c == 0 ? h->evCount : h->evChunk[2 * c - 1];
+      if (cudaEventElapsedTime(&t, before, h->evChunk[2 * c]) == cudaSuccess) h->stageMs[5] += t;
+      if (cudaEventElapsedTime(&t, h->evChunk[2 * c], h->evChunk[2 * c + 1]) == cudaSuccess) h->stageMs[6] += t;
+    }
+  }
   (void)cudaGetLastError();
   b200seed_counters& c = h->lastCounters;
   c.nSpacePoints = h->lastTotal;
@@ -494,8 +624,8 @@ int finish(b200seed_handle* h, cudaStream_t s, b200seed_seeds* out) {
   const int st = *h->hStatus;
   if (st & (kStatusOverflowDoublets | kStatusOverflowPool)) {
     return fail(B200SEED_ERR_OVERFLOW,
-                "per-middle scratch exhausted even in the largest tier (doublets > " + std::to_string(Tier2::B) + "/" +
-                    std::to_string(Tier2::T) + " or candidates per middle > " + std::to_string(Tier2::P) + ")");
+                "a middle space point exceeds the engine's limits (more than " + std::to_string(kMaxListLength) +
+                    " doublets on one side, or more triplet candidates than the spill class's pool holds)");
   }
   if (*h->hSeedTotal > h->lastCapacity) {
     return fail(B200SEED_ERR_CAPACITY, "seed buffers too small: need " + std::to_string(*h->hSeedTotal));
@@ -615,36 +745,45 @@ int b200seed_create(const b200seed_config* cfg, int device, b200seed_handle** ou
   h->recPerSpacePoint = std::max<uint32_t>(env_u32("B200SEED_REC_PER_SP", 32), 1u);
   // the tie-order replay of the unstable sorts only makes sense when the keys are the reference's bit for bit
   h->exactTies = engineRelaxed ? 0 : (int)env_u32("B200SEED_EXACT_TIES", 1);
+  h->arenaMaxBytes = (size_t)std::max<uint32_t>(env_u32("B200SEED_ARENA_MB", 2048), 64u) << 20;
+  CREATE_TRY(cudaEventCreate(&h->evCount));
+  CREATE_TRY(cudaMallocHost(&h->hPlan, (8 + (size_t)kMaxChunks + 1 + 8) * 4));
   {
-    auto setupTier = [&](int t, auto kernel, int threads, size_t bytes) -> cudaError_t {
-      h->seedSmemBytes[t] = bytes;
-      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-      if (e != cudaSuccess) return e;
+    // dynamic shared memory of every class: what is left of the SM for N resident blocks (1 KB per block is
+    // reserved by the system, the kernel's static shared memory comes on top)
+    const bool conf = h->plan.dev.seedConfirmation != 0;
+    if (conf) CREATE_TRY(cudaMallocHost(&h->hConfState, kConfStateWords * 4));
+    for (int c = 0; c < kNumSeedClasses; ++c) {
+      SeedKernel k = seed_kernel(conf, c);
+      cudaFuncAttributes fa{};
+      CREATE_TRY(cudaFuncGetAttributes(&fa, k));
+      uint32_t bytes = 0;
+      if (c != kSpillClass) {
+        const size_t perBlock = (size_t)prop.sharedMemPerMultiprocessor / (size_t)kSeedClassShape[c].blocksPerSM;
+        size_t dyn = perBlock - 1024 - fa.sharedSizeBytes;
+        dyn = std::min<size_t>(dyn, (size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes);
+        bytes = (uint32_t)(dyn & ~(size_t)127);
+        CREATE_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      }
+      h->classBytes[c] = bytes;
       int b = 0;
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, threads, bytes);
-      h->seedBlocksPerSM[t] = std::max(1, b);
-      return e;
-    };
-    if (sizeof(TierLayout<Tier2>) > (size_t)prop.sharedMemPerBlockOptin) {
-      return cleanup(fail(B200SEED_ERR_CUDA, "device offers less shared memory per block than the seeding kernel needs"));
+      CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k, kSeedClassShape[c].threads, bytes));
+      h->classBlocksPerSM[c] = std::max(1, b);
     }
-    if (h->plan.dev.seedConfirmation) {
-      CREATE_TRY(setupTier(0, seed_kernel<Tier0, true>(), Tier0::N, sizeof(TierLayout<Tier0>)));
-      CREATE_TRY(setupTier(1, seed_kernel<Tier1, true>(), Tier1::N, sizeof(TierLayout<Tier1>)));
-      CREATE_TRY(setupTier(2, seed_kernel<Tier2, true>(), Tier2::N, sizeof(TierLayout<Tier2>)));
-      CREATE_TRY(cudaMallocHost(&h->hConfState, kConfStateWords * 4));
-    } else {
-      CREATE_TRY(setupTier(0, seed_kernel<Tier0, false>(), Tier0::N, sizeof(TierLayout<Tier0>)));
-      CREATE_TRY(setupTier(1, seed_kernel<Tier1, false>(), Tier1::N, sizeof(TierLayout<Tier1>)));
-      CREATE_TRY(setupTier(2, seed_kernel<Tier2, false>(), Tier2::N, sizeof(TierLayout<Tier2>)));
-    }
+    int b = 0;
+    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_doublets<false>, kDoubletWarps * 32, 0));
+    h->doubletBlocksPerSM[0] = std::max(1, b);
+    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_doublets<true>, kDoubletWarps * 32, 0));
+    h->doubletBlocksPerSM[1] = std::max(1, b);
   }
   CREATE_TRY(cudaFuncSetAttribute(k_sort_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->sortSmemCap * 16)));
   if (std::getenv("B200SEED_VERBOSE") != nullptr) {
-    for (int t = 0; t < kNumTiers; ++t) {
-      std::fprintf(stderr, "b200seed: tier %d: %zu bytes of shared memory, %d blocks per SM\n", t, h->seedSmemBytes[t],
-                   h->seedBlocksPerSM[t]);
+    for (int c = 0; c < kNumSeedClasses; ++c) {
+      std::fprintf(stderr, "b200seed: seed class %d: %d threads, %u bytes of shared memory, %d blocks per SM\n", c,
+                   kSeedClassShape[c].threads, h->classBytes[c], h->classBlocksPerSM[c]);
     }
+    std::fprintf(stderr, "b200seed: doublet kernels: %d / %d blocks per SM (count / fill)\n", h->doubletBlocksPerSM[0],
+                 h->doubletBlocksPerSM[1]);
   }
 
   int rc = upload(h->navBins, h->plan.navBins, h->stream);
@@ -670,7 +809,8 @@ void b200seed_destroy(b200seed_handle* h) {
                     &h->inX, &h->inY, &h->inZ, &h->inR, &h->inVarZ, &h->inVarR, &h->binOf, &h->binCount,
                     &h->binStart, &h->binCursor, &h->tmpIdx, &h->pIdx, &h->pXY, &h->pZR, &h->pVar,
                     &h->sortScratch, &h->midLo, &h->midCount, &h->workStart, &h->workPos, &h->workEG,
-                    &h->workCounter, &h->overflowList, &h->slotB, &h->slotM, &h->slotT, &h->slotQ, &h->slotZ, &h->slotCount,
+                    &h->workCounter, &h->capB, &h->capT, &h->slotPrefix, &h->capTileSums, &h->capTilePrefix, &h->planDev,
+                    &h->hdr, &h->classList, &h->arenaRec, &h->arenaKey, &h->spillScratch, &h->zWinOffsets, &h->slotB, &h->slotM, &h->slotT, &h->slotQ, &h->slotZ, &h->slotCount,
                     &h->seedStart, &h->tileSums, &h->tilePrefix, &h->outB, &h->outM, &h->outT, &h->outQ,
                     &h->outZ, &h->seedOffsets, &h->counters, &h->status, &h->zWin, &h->rec, &h->recZ, &h->recBegin,
                     &h->recCount, &h->slot2B, &h->slot2M, &h->slot2T, &h->slot2Q, &h->slot2Z, &h->slot2Count,
@@ -678,6 +818,9 @@ void b200seed_destroy(b200seed_handle* h) {
     b->release();
   }
   if (h->hConfState != nullptr) cudaFreeHost(h->hConfState);
+  if (h->hPlan != nullptr) cudaFreeHost(h->hPlan);
+  if (h->evCount != nullptr) cudaEventDestroy(h->evCount);
+  for (cudaEvent_t e : h->evChunk) cudaEventDestroy(e);
   for (int i = 0; i < 5; ++i) {
     if (h->ev[i] != nullptr) cudaEventDestroy(h->ev[i]);
   }
@@ -734,6 +877,12 @@ int b200seed_get_stage_times(const b200seed_handle* h, float* ms) {
   return B200SEED_OK;
 }
 
+int b200seed_get_stage_times_ex(const b200seed_handle* h, float* ms, uint32_t n) {
+  if (h == nullptr || ms == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL argument");
+  for (uint32_t i = 0; i < n && i < 7; ++i) ms[i] = h->stageMs[i];
+  return B200SEED_OK;
+}
+
 int b200seed_run_batch_device(b200seed_handle* h, uint32_t nEvents, uint32_t nSpacePointsTotal,
                               const uint32_t* spOffsets, const float* x, const float* y, const float* z,
                               const float* r, const float* varZ, const float* varR, uint64_t* seedOffsets,
@@ -760,6 +909,7 @@ int b200seed_run_batch_device(b200seed_handle* h, uint32_t nEvents, uint32_t nSp
   a.outCapacity = out->capacity;
   a.dSeedOffsets = reinterpret_cast<unsigned long long*>(seedOffsets);
   a.stream = s;
+  a.vertexCuts = h->plan.useVertexZCuts;  // no windows on this entry: every doublet passes the vertex cut
   return enqueue(h);
 }
 
@@ -781,17 +931,45 @@ struct MeasurementSource {
   float* spOut[6];  // optional host copies of the space point columns
 };
 
+// VertexZCuts windows of a call: `offsets` == NULL: the nZWin windows apply to every event of the batch,
+// else event e owns windows [offsets[e], offsets[e + 1]).
+struct WindowSource {
+  uint32_t nZWin = 0;
+  const float* lo = nullptr;
+  const float* hi = nullptr;
+  const uint32_t* offsets = nullptr;
+};
+
+// The windows of one event merged into disjoint intervals in ascending order: the union -- and with it the
+// answer of VertexZCuts::operator() (.cpp:78-96), "inside any window" -- is unchanged, and the device can
+// find the deciding interval by binary search however many vertices there are.
+static void merge_windows(const float* lo, const float* hi, uint32_t n, std::vector<float>& outLo, std::vector<float>& outHi,
+                          size_t first) {
+  std::vector<std::pair<float, float>> w;
+  w.reserve(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    if (lo[i] <= hi[i]) w.emplace_back(lo[i], hi[i]);  // an empty (or NaN) window contains nothing
+  }
+  std::sort(w.begin(), w.end());
+  for (const auto& [a, b] : w) {
+    if (outLo.size() > first && a <= outHi.back()) {  // overlaps (or touches) the current interval
+      if (b > outHi.back()) outHi.back() = b;
+    } else {
+      outLo.push_back(a);
+      outHi.push_back(b);
+    }
+  }
+}
+
 static int run_host_batch(b200seed_handle* h, uint32_t nEvents, const uint32_t* spOffsets, const float* x,
                           const float* y, const float* z, const float* r, const float* varZ,
-                          const float* varR, const float* phi, uint32_t nZWin, const float* zLo,
-                          const float* zHi, uint64_t* seedOffsets, b200seed_seeds* out,
-                          const MeasurementSource* meas = nullptr) {
+                          const float* varR, const float* phi, const WindowSource& win, uint64_t* seedOffsets,
+                          b200seed_seeds* out, const MeasurementSource* meas = nullptr) {
   if (h == nullptr || out == nullptr || spOffsets == nullptr || nEvents == 0) {
     return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL argument or empty batch");
   }
-  if (nZWin > (uint32_t)kMaxZWindows) {
-    return fail(B200SEED_ERR_UNSUPPORTED, "more than " + std::to_string(kMaxZWindows) + " vertex z windows");
-  }
+  const uint32_t nZWin = win.nZWin;
+  if (nZWin > 0 && (win.lo == nullptr || win.hi == nullptr)) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL z window column");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
   const uint32_t nTotal = spOffsets[nEvents] - spOffsets[0];
@@ -860,9 +1038,36 @@ static int run_host_batch(b200seed_handle* h, uint32_t nEvents, const uint32_t* 
   }
   int rc = ensure_workspace(h, nEvents, nTotal);
   if (rc != B200SEED_OK) return rc;
-  if (nZWin > 0) {
-    CUDA_TRY(cudaMemcpyAsync(h->zWin.ptr, zLo, nZWin * 4, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(h->zWin.as<float>() + kMaxZWindows, zHi, nZWin * 4, cudaMemcpyHostToDevice, s));
+  // vertex z windows: merged per event, uploaded as {lo column, hi column} (+ per-event offsets)
+  uint32_t nMerged = 0;
+  const uint32_t* dWinOffsets = nullptr;
+  {
+    std::vector<float> mLo, mHi;
+    std::vector<uint32_t> mOff;
+    if (win.offsets != nullptr) {
+      mOff.push_back(0);
+      for (uint32_t e = 0; e < nEvents; ++e) {
+        const uint32_t a = win.offsets[e], b = win.offsets[e + 1];
+        if (b < a || b > nZWin) return fail(B200SEED_ERR_INVALID_ARGUMENT, "z window offsets are not ascending / exceed the window count");
+        merge_windows(win.lo + a, win.hi + a, b - a, mLo, mHi, mLo.size());
+        mOff.push_back((uint32_t)mLo.size());
+      }
+    } else {
+      merge_windows(win.lo, win.hi, nZWin, mLo, mHi, 0);
+    }
+    nMerged = (uint32_t)mLo.size();
+    h->zWinCapacity = std::max<uint32_t>(nMerged, 1);
+    CUDA_TRY(h->zWin.reserve((size_t)h->zWinCapacity * 8));
+    if (nMerged > 0) {
+      CUDA_TRY(cudaMemcpyAsync(h->zWin.ptr, mLo.data(), (size_t)nMerged * 4, cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaMemcpyAsync(h->zWin.as<float>() + h->zWinCapacity, mHi.data(), (size_t)nMerged * 4, cudaMemcpyHostToDevice, s));
+    }
+    if (!mOff.empty()) {
+      CUDA_TRY(h->zWinOffsets.reserve(mOff.size() * 4));
+      CUDA_TRY(cudaMemcpyAsync(h->zWinOffsets.ptr, mOff.data(), mOff.size() * 4, cudaMemcpyHostToDevice, s));
+      dWinOffsets = h->zWinOffsets.as<uint32_t>();
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));  // the staging vectors go out of scope
   }
   const size_t K = std::max<uint32_t>(h->plan.seedsPerMiddle, 1);
   const size_t maxSeeds = std::max<size_t>(1, (size_t)nTotal * K);
@@ -878,7 +1083,9 @@ static int run_host_batch(b200seed_handle* h, uint32_t nEvents, const uint32_t* 
     a.nEvents = nEvents; a.nTotal = nTotal; a.dOffsets = h->inOffsets.as<uint32_t>();
     a.x = h->inX.as<float>(); a.y = h->inY.as<float>(); a.z = h->inZ.as<float>(); a.r = h->inR.as<float>();
     a.varZ = h->inVarZ.as<float>(); a.varR = h->inVarR.as<float>(); a.dPhi = dPhi;
-    a.nZWin = (int)nZWin;
+    a.nZWin = (int)nMerged;
+    a.dZWinOffsets = dWinOffsets;
+    a.vertexCuts = h->plan.useVertexZCuts || nZWin > 0 || win.offsets != nullptr;
     a.outB = h->outB.as<uint32_t>(); a.outM = h->outM.as<uint32_t>(); a.outT = h->outT.as<uint32_t>();
     a.outQ = h->outQ.as<float>(); a.outZ = h->outZ.as<float>();
     a.outCapacity = maxSeeds;
@@ -919,15 +1126,65 @@ int b200seed_run_measurements(b200seed_handle* h, uint32_t n, const uint32_t* su
   }
   MeasurementSource ms{surface, {loc0, loc1, cov00, cov01, cov11}, nSurfaces, transforms, {x, y, z, r, varZ, varR}};
   const uint32_t offsets[2] = {0, n};
-  return run_host_batch(h, 1, offsets, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nZWindows,
-                        zWindowLo, zWindowHi, nullptr, out, &ms);
+  WindowSource win;
+  win.nZWin = nZWindows; win.lo = zWindowLo; win.hi = zWindowHi;
+  return run_host_batch(h, 1, offsets, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, win, nullptr, out, &ms);
 }
 
 int b200seed_run(b200seed_handle* h, uint32_t nSpacePoints, const float* x, const float* y, const float* z,
                  const float* r, const float* varZ, const float* varR, uint32_t nZWindows,
                  const float* zWindowLo, const float* zWindowHi, b200seed_seeds* out) {
   const uint32_t offsets[2] = {0, nSpacePoints};
-  return run_host_batch(h, 1, offsets, x, y, z, r, varZ, varR, nullptr, nZWindows, zWindowLo, zWindowHi, nullptr, out);
+  WindowSource win;
+  win.nZWin = nZWindows; win.lo = zWindowLo; win.hi = zWindowHi;
+  return run_host_batch(h, 1, offsets, x, y, z, r, varZ, varR, nullptr, win, nullptr, out);
+}
+
+// GridTripletSeedingAlgorithm.cpp:187-206: one z window per vertex, [z - half, z + half] with
+// half = vertexZNSigma * sqrt(cov(2, 2)) + vertexZMargin, evaluated in double and narrowed to float.
+int b200seed_vertex_windows(const b200seed_handle* h, uint32_t nVertices, const double* vertexZ, const double* vertexVarZ,
+                            float* windowLo, float* windowHi) {
+  if (h == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL handle");
+  if (nVertices > 0 && (vertexZ == nullptr || vertexVarZ == nullptr || windowLo == nullptr || windowHi == nullptr)) {
+    return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL vertex column");
+  }
+  for (uint32_t i = 0; i < nVertices; ++i) {
+    const double zv = vertexZ[i];
+    const double sigmaZ = std::sqrt(vertexVarZ[i]);
+    const double half = h->plan.vertexZNSigma * sigmaZ + h->plan.vertexZMargin;
+    windowLo[i] = static_cast<float>(zv - half);
+    windowHi[i] = static_cast<float>(zv + half);
+  }
+  return B200SEED_OK;
+}
+
+// One event with its reconstructed vertices (Config::inputVertices): the windows are built like the reference does.
+int b200seed_run_vertices(b200seed_handle* h, uint32_t nSpacePoints, const float* x, const float* y, const float* z,
+                          const float* r, const float* varZ, const float* varR, uint32_t nVertices,
+                          const double* vertexZ, const double* vertexVarZ, b200seed_seeds* out) {
+  if (h == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL handle");
+  if (!h->plan.useVertexZCuts) {
+    return fail(B200SEED_ERR_INVALID_ARGUMENT, "b200seed_run_vertices needs a handle created with useVertexZCuts = 1 (inputVertices configured)");
+  }
+  std::vector<float> lo(nVertices), hi(nVertices);
+  int rc = b200seed_vertex_windows(h, nVertices, vertexZ, vertexVarZ, lo.data(), hi.data());
+  if (rc != B200SEED_OK) return rc;
+  const uint32_t offsets[2] = {0, nSpacePoints};
+  const uint32_t winOffsets[2] = {0, nVertices};
+  WindowSource win;
+  win.nZWin = nVertices; win.lo = lo.data(); win.hi = hi.data(); win.offsets = winOffsets;
+  return run_host_batch(h, 1, offsets, x, y, z, r, varZ, varR, nullptr, win, nullptr, out);
+}
+
+// A batch of events, each with its own z windows: event e owns windows [windowOffsets[e], windowOffsets[e + 1]).
+int b200seed_run_batch_windows(b200seed_handle* h, uint32_t nEvents, const uint32_t* spOffsets, const float* x,
+                               const float* y, const float* z, const float* r, const float* varZ, const float* varR,
+                               const uint32_t* windowOffsets, const float* zWindowLo, const float* zWindowHi,
+                               uint64_t* seedOffsets, b200seed_seeds* out) {
+  if (windowOffsets == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL window offsets");
+  WindowSource win;
+  win.nZWin = windowOffsets[nEvents]; win.lo = zWindowLo; win.hi = zWindowHi; win.offsets = windowOffsets;
+  return run_host_batch(h, nEvents, spOffsets, x, y, z, r, varZ, varR, nullptr, win, seedOffsets, out);
 }
 
 // b200seed_run with a caller-provided phi column (optional precomputed
@@ -937,13 +1194,13 @@ int b200seed_run_with_phi(b200seed_handle* h, uint32_t nSpacePoints, const float
                           const float* z, const float* r, const float* varZ, const float* varR,
                           const float* phi, b200seed_seeds* out) {
   const uint32_t offsets[2] = {0, nSpacePoints};
-  return run_host_batch(h, 1, offsets, x, y, z, r, varZ, varR, phi, 0, nullptr, nullptr, nullptr, out);
+  return run_host_batch(h, 1, offsets, x, y, z, r, varZ, varR, phi, WindowSource{}, nullptr, out);
 }
 
 int b200seed_run_batch(b200seed_handle* h, uint32_t nEvents, const uint32_t* spOffsets, const float* x,
                        const float* y, const float* z, const float* r, const float* varZ, const float* varR,
                        uint64_t* seedOffsets, b200seed_seeds* out) {
-  return run_host_batch(h, nEvents, spOffsets, x, y, z, r, varZ, varR, nullptr, 0, nullptr, nullptr, seedOffsets, out);
+  return run_host_batch(h, nEvents, spOffsets, x, y, z, r, varZ, varR, nullptr, WindowSource{}, seedOffsets, out);
 }
 
 int b200seed_debug_grid(b200seed_handle* h, uint64_t capacity, uint32_t* copiedFromIndex, float* x, float* y,
@@ -974,6 +1231,10 @@ int b200seed_debug_grid(b200seed_handle* h, uint64_t capacity, uint32_t* copiedF
   return B200SEED_OK;
 }
 
+// Stage-level view of the PRODUCTION doublet stage: the fill pass of the last call is run again chunk by chunk and
+// the arena is copied out (bottoms first, then tops, per middle, in the reference's emission order).  Middles that
+// do not reach the triplet stage (no tops, no bottoms, or -- seedConfirmation -- too few tops) have no bottoms here:
+// like the reference, the engine does not search them (TripletSeeder.cpp:62-69).
 int b200seed_debug_doublets(b200seed_handle* h, b200seed_doublets* out) {
   if (h == nullptr || out == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL argument");
   if (h->lastEvents == 0) return fail(B200SEED_ERR_INVALID_ARGUMENT, "no previous run on this handle");
@@ -981,75 +1242,56 @@ int b200seed_debug_doublets(b200seed_handle* h, b200seed_doublets* out) {
   CUDA_TRY(cudaDeviceSynchronize());
   cudaStream_t s = h->stream;
   const uint32_t nWork = (uint32_t)h->lastCounters.nMiddles;
-  const HostPlan& plan = h->plan;
-  DevBuf count, nBottom, first;
-  struct Guard {
-    std::vector<DevBuf*> bufs;
-    ~Guard() { for (DevBuf* b : bufs) b->release(); }
-  } guard;
-  guard.bufs = {&count, &nBottom, &first};
-  CUDA_TRY(count.reserve(((size_t)nWork + 1) * 4));
-  CUDA_TRY(nBottom.reserve(((size_t)nWork + 1) * 4));
-  CUDA_TRY(first.reserve(((size_t)nWork + 2) * 4));
-  DoubletDumpParams dp{};
-  dp.cfg = plan.dev;
-  if (h->lastZWin > 0) dp.cfg.doubletCuts = kCutsVertexZ;
-  dp.pXY = h->pXY.as<float2>(); dp.pZR = h->pZR.as<float2>(); dp.pVar = h->pVar.as<float2>();
-  dp.binStart = h->binStart.as<uint32_t>();
-  dp.navBins = h->navBins.as<uint32_t>();
-  dp.botOffsets = h->botOffsets.as<uint32_t>(); dp.botBins = h->botBins.as<uint32_t>();
-  dp.topOffsets = h->topOffsets.as<uint32_t>(); dp.topBins = h->topBins.as<uint32_t>();
-  dp.workPos = h->workPos.as<uint32_t>(); dp.workEG = h->workEG.as<uint32_t>();
-  dp.nWork = nWork; dp.nNav = (uint32_t)plan.navBins.size(); dp.nBins = (uint32_t)plan.dev.nGlobalBins;
-  dp.zWinLo = h->zWin.as<float>(); dp.zWinHi = h->zWin.as<float>() + kMaxZWindows; dp.nZWin = h->lastZWin;
-  dp.count = count.as<uint32_t>(); dp.nBottom = nBottom.as<uint32_t>(); dp.first = first.as<uint32_t>();
-  const int blocks = h->smCount * 8;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  CUDA_TRY(cudaEventCreate(&e0));
-  CUDA_TRY(cudaEventCreate(&e1));
-  CUDA_TRY(cudaEventRecord(e0, s));
-  if (nWork > 0) k_doublets_materialised<false><<<blocks, 256, 0, s>>>(dp);
-  k_scan<<<1, kScanThreads, 0, s>>>(dp.count, first.as<uint32_t>(), nWork);
-  uint32_t total = 0;
-  CUDA_TRY(cudaMemcpyAsync(&total, first.as<uint32_t>() + nWork, 4, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
+  const uint32_t nChunks = h->lastChunkBounds.empty() ? 0u : (uint32_t)h->lastChunkBounds.size() - 1;
+  DoubletParams dp = h->lastDoublets;
+  std::vector<MiddleHeader> hdr(nWork);
+  std::vector<uint32_t> capT(nWork);
+  uint64_t total = 0;
   out->nMiddles = nWork;
-  out->nDoublets = total;
-  if (out->middlePos == nullptr) {  // size query
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    out->gpuMilliseconds = 0.f;
-    return B200SEED_OK;
-  }
-  if (out->middleCapacity < nWork || out->doubletCapacity < total) {
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    return fail(B200SEED_ERR_CAPACITY, "debug_doublets buffers too small");
-  }
-  DevBuf cols[8];
-  for (DevBuf& b : cols) guard.bufs.push_back(&b);
-  for (DevBuf& b : cols) CUDA_TRY(b.reserve(std::max<size_t>(4, (size_t)total * 4)));
-  dp.otherPos = cols[0].as<uint32_t>();
-  dp.cotTheta = cols[1].as<float>(); dp.iDeltaR = cols[2].as<float>(); dp.er = cols[3].as<float>();
-  dp.u = cols[4].as<float>(); dp.v = cols[5].as<float>(); dp.xNew = cols[6].as<float>(); dp.yNew = cols[7].as<float>();
-  if (nWork > 0) k_doublets_materialised<true><<<blocks, 256, 0, s>>>(dp);
-  CUDA_TRY(cudaEventRecord(e1, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
-  CUDA_TRY(cudaGetLastError());
-  cudaEventElapsedTime(&out->gpuMilliseconds, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  std::vector<uint32_t> first32((size_t)nWork + 1);
-  CUDA_TRY(cudaMemcpy(first32.data(), first.ptr, ((size_t)nWork + 1) * 4, cudaMemcpyDeviceToHost));
-  for (size_t i = 0; i <= nWork; ++i) out->firstDoublet[i] = first32[i];
+  // the headers of every chunk are still in place after the run
   if (nWork > 0) {
-    CUDA_TRY(cudaMemcpy(out->middlePos, h->workPos.ptr, (size_t)nWork * 4, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(out->nBottom, nBottom.ptr, (size_t)nWork * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(hdr.data(), h->hdr.ptr, (size_t)nWork * sizeof(MiddleHeader), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(capT.data(), h->capT.ptr, (size_t)nWork * 4, cudaMemcpyDeviceToHost));
   }
-  if (total > 0) {
-    void* dst[8] = {out->otherPos, out->cotTheta, out->iDeltaR, out->er, out->u, out->v, out->xNew, out->yNew};
-    for (int i = 0; i < 8; ++i) CUDA_TRY(cudaMemcpy(dst[i], cols[i].ptr, (size_t)total * 4, cudaMemcpyDeviceToHost));
+  for (uint32_t w = 0; w < nWork; ++w) total += (uint64_t)hdr[w].nB + hdr[w].nT;
+  out->nDoublets = total;
+  out->gpuMilliseconds = h->stageMs[4] + h->stageMs[5];
+  if (out->middlePos == nullptr) return B200SEED_OK;  // size query
+  if (out->middleCapacity < nWork || out->doubletCapacity < total) return fail(B200SEED_ERR_CAPACITY, "debug_doublets buffers too small");
+  if (nWork > 0) CUDA_TRY(cudaMemcpy(out->middlePos, h->workPos.ptr, (size_t)nWork * 4, cudaMemcpyDeviceToHost));
+  uint64_t o = 0;
+  uint32_t* scratchCounters = h->workCounter.as<uint32_t>() + 16 * ((size_t)kMaxChunks + 1);
+  std::vector<DoubletRecord> rec;
+  for (uint32_t c = 0; c < nChunks; ++c) {
+    const uint32_t w0 = h->lastChunkBounds[c], w1 = h->lastChunkBounds[c + 1];
+    CUDA_TRY(cudaMemsetAsync(scratchCounters, 0, 16 * 4, s));
+    dp.itemFirst = w0;
+    dp.itemEnd = w1;
+    dp.workCounter = scratchCounters;
+    dp.classCount = scratchCounters + 8;
+    dp.counters = h->counters.as<unsigned long long>();  // scribbled on: the host copy of the last run is what counts
+    k_doublets<true><<<h->smCount * h->doubletBlocksPerSM[1], kDoubletWarps * 32, 0, s>>>(dp);
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaGetLastError());
+    uint64_t slots = 0;
+    for (uint32_t w = w0; w < w1; ++w) slots = std::max<uint64_t>(slots, (uint64_t)hdr[w].offset + hdr[w].capB + capT[w]);
+    rec.resize(std::max<uint64_t>(slots, 1));
+    if (slots > 0) CUDA_TRY(cudaMemcpy(rec.data(), h->arenaRec.ptr, slots * sizeof(DoubletRecord), cudaMemcpyDeviceToHost));
+    for (uint32_t w = w0; w < w1; ++w) {
+      out->firstDoublet[w] = o;
+      out->nBottom[w] = hdr[w].nB;
+      for (int side = 0; side < 2; ++side) {
+        const DoubletRecord* src = rec.data() + hdr[w].offset + (side == 0 ? 0u : hdr[w].capB);
+        const uint32_t n = side == 0 ? hdr[w].nB : hdr[w].nT;
+        for (uint32_t i = 0; i < n; ++i, ++o) {
+          out->otherPos[o] = src[i].pos;
+          out->cotTheta[o] = src[i].cotTheta; out->iDeltaR[o] = src[i].iDeltaR; out->er[o] = src[i].er;
+          out->u[o] = src[i].u; out->v[o] = src[i].v; out->xNew[o] = src[i].xNew; out->yNew[o] = src[i].yNew;
+        }
+      }
+    }
   }
+  out->firstDoublet[nWork] = o;
   return B200SEED_OK;
 }
 

@@ -23,7 +23,8 @@ LIB_PATH = os.environ.get("B200SEED_LIB", os.path.join(_HERE, "libacts_b200_seed
 EXPORTED_SYMBOLS = [
     "b200seed_config_init", "b200seed_plan_info", "b200seed_plan_tables", "b200seed_create",
     "b200seed_destroy", "b200seed_last_error", "b200seed_get_info", "b200seed_get_counters",
-    "b200seed_get_stage_times", "b200seed_set_phi_sector", "b200seed_estimate_params",
+    "b200seed_get_stage_times", "b200seed_get_stage_times_ex", "b200seed_set_phi_sector", "b200seed_estimate_params",
+    "b200seed_run_vertices", "b200seed_vertex_windows", "b200seed_run_batch_windows",
     "b200seed_make_pixel_spacepoints", "b200seed_run_measurements",
     "b200seed_run", "b200seed_run_with_phi", "b200seed_run_batch", "b200seed_run_batch_device",
     "b200seed_sync", "b200seed_debug_grid", "b200seed_debug_doublets", "b200seed_debug_atan2f",
@@ -57,6 +58,10 @@ def lib():
         L.b200seed_get_info.argtypes = [vp, C.POINTER(Info)]
         L.b200seed_get_counters.argtypes = [vp, C.POINTER(Counters)]
         L.b200seed_get_stage_times.argtypes = [vp, vp]
+        L.b200seed_get_stage_times_ex.argtypes = [vp, vp, u32]
+        L.b200seed_run_vertices.argtypes = [vp, u32] + [f32p] * 6 + [u32, vp, vp, C.POINTER(Seeds)]
+        L.b200seed_vertex_windows.argtypes = [vp, u32, vp, vp, vp, vp]
+        L.b200seed_run_batch_windows.argtypes = [vp, u32, vp] + [f32p] * 6 + [vp, f32p, f32p, vp, C.POINTER(Seeds)]
         L.b200seed_set_phi_sector.argtypes = [vp, u32, u32]
         L.b200seed_estimate_params.argtypes = [vp, u64, vp, vp, vp, u32, vp, vp, vp, vp, vp]
         L.b200seed_make_pixel_spacepoints.argtypes = [vp, u32] + [vp] * 6 + [u32] + [vp] * 7
@@ -187,9 +192,18 @@ class SeedingEngine:
         return (seeds, sp) if want_spacepoints else seeds
 
     def stage_times_ms(self) -> dict:
-        ms = np.zeros(4, dtype=np.float32)
-        _check(lib().b200seed_get_stage_times(self._h, _p(ms)))
-        return {"grid": float(ms[0]), "work": float(ms[1]), "seed": float(ms[2]), "compact": float(ms[3])}
+        ms = np.zeros(7, dtype=np.float32)
+        _check(lib().b200seed_get_stage_times_ex(self._h, _p(ms), 7))
+        return {"grid": float(ms[0]), "work": float(ms[1]), "seed": float(ms[2]), "compact": float(ms[3]),
+                "doublet_count": float(ms[4]), "doublet_fill": float(ms[5]), "seed_middles": float(ms[6])}
+
+    def vertex_windows(self, vertex_z, vertex_var_z):
+        """The reference's z windows of a vertex list (``b200seed_vertex_windows``)."""
+        vz = np.ascontiguousarray(vertex_z, dtype=np.float64)
+        vv = np.ascontiguousarray(vertex_var_z, dtype=np.float64)
+        lo, hi = np.zeros(vz.size, np.float32), np.zeros(vz.size, np.float32)
+        _check(lib().b200seed_vertex_windows(self._h, vz.size, _p(vz), _p(vv), _p(lo), _p(hi)))
+        return lo, hi
 
     @staticmethod
     def _cols(ev):
@@ -208,9 +222,10 @@ class SeedingEngine:
         s.capacity = capacity
         return out, s
 
-    def run(self, ev: dict, z_windows=None, phi=None, capacity=None, out=None) -> dict:
+    def run(self, ev: dict, z_windows=None, phi=None, capacity=None, out=None, vertices=None) -> dict:
         """One event through ``b200seed_run`` (host buffers in, host seeds out).
 
+        ``vertices`` = (z, var z) goes through ``b200seed_run_vertices`` (Config::inputVertices).
         ``out`` may hold caller-owned (e.g. pinned) seed columns that are reused from call to call."""
         cols = self._cols(ev)
         n = cols[0].size
@@ -222,7 +237,11 @@ class SeedingEngine:
             s.capacity = min(int(a.size) for a in out.values())
         else:
             out, s = self._alloc(cap)
-        if phi is not None:
+        if vertices is not None:
+            vz = np.ascontiguousarray(vertices[0], dtype=np.float64)
+            vv = np.ascontiguousarray(vertices[1], dtype=np.float64)
+            rc = lib().b200seed_run_vertices(self._h, n, *[_p(c) for c in cols], vz.size, _p(vz), _p(vv), C.byref(s))
+        elif phi is not None:
             phi = np.ascontiguousarray(phi, dtype=np.float32)
             rc = lib().b200seed_run_with_phi(self._h, n, *[_p(c) for c in cols], _p(phi), C.byref(s))
         else:
@@ -237,8 +256,10 @@ class SeedingEngine:
         k = int(s.size)
         return {name: arr[:k] for name, arr in out.items()}
 
-    def run_batch(self, cols: dict, offsets: np.ndarray, capacity=None, out=None) -> list[dict]:
+    def run_batch(self, cols: dict, offsets: np.ndarray, capacity=None, out=None, z_windows=None) -> list[dict]:
         """A batch of events through ``b200seed_run_batch``; returns one dict per event.
+
+        ``z_windows``: one list of (lo, hi) per event -> ``b200seed_run_batch_windows``.
 
         ``out`` may hold caller-owned (e.g. pinned) seed columns ``bottom/middle/top`` (uint32) and
         ``quality/vertexZ`` (float32) that are reused from call to call."""
@@ -255,7 +276,15 @@ class SeedingEngine:
         else:
             out, s = self._alloc(cap)
         seed_offsets = np.zeros(n_events + 1, dtype=np.uint64)
-        _check(lib().b200seed_run_batch(self._h, n_events, _p(offsets), *[_p(a) for a in arrs], _p(seed_offsets), C.byref(s)))
+        if z_windows is not None:
+            w_off = np.zeros(n_events + 1, dtype=np.uint32)
+            w_off[1:] = np.cumsum([len(w) for w in z_windows])
+            lo = np.ascontiguousarray([w[0] for ws in z_windows for w in ws], dtype=np.float32)
+            hi = np.ascontiguousarray([w[1] for ws in z_windows for w in ws], dtype=np.float32)
+            _check(lib().b200seed_run_batch_windows(self._h, n_events, _p(offsets), *[_p(a) for a in arrs], _p(w_off), _p(lo), _p(hi),
+                                                    _p(seed_offsets), C.byref(s)))
+        else:
+            _check(lib().b200seed_run_batch(self._h, n_events, _p(offsets), *[_p(a) for a in arrs], _p(seed_offsets), C.byref(s)))
         res = []
         for e in range(n_events):
             a, b = int(seed_offsets[e]), int(seed_offsets[e + 1])

@@ -257,6 +257,31 @@ int b200seed_run(b200seed_handle* h, uint32_t nSpacePoints, const float* x,
                  const float* zWindowLo, const float* zWindowHi,
                  b200seed_seeds* out);
 
+/* Config::inputVertices (GridTripletSeedingAlgorithm.hpp:239-243, .cpp:187-206): one event together with its
+ * reconstructed vertices (z position and its variance, the (2, 2) element of the vertex covariance).  The z
+ * windows are built exactly like the reference does (double arithmetic, narrowed to float); any number of
+ * vertices, including none (every doublet then passes).  The handle must have useVertexZCuts = 1. */
+int b200seed_run_vertices(b200seed_handle* h, uint32_t nSpacePoints, const float* x,
+                          const float* y, const float* z, const float* r,
+                          const float* varZ, const float* varR, uint32_t nVertices,
+                          const double* vertexZ, const double* vertexVarZ,
+                          b200seed_seeds* out);
+
+/* The window construction of b200seed_run_vertices on its own (for the batch entry below). */
+int b200seed_vertex_windows(const b200seed_handle* h, uint32_t nVertices,
+                            const double* vertexZ, const double* vertexVarZ,
+                            float* windowLo, float* windowHi);
+
+/* b200seed_run_batch with per-event z windows: event e owns windows
+ * [windowOffsets[e], windowOffsets[e + 1]) of (zWindowLo, zWindowHi). */
+int b200seed_run_batch_windows(b200seed_handle* h, uint32_t nEvents,
+                               const uint32_t* spOffsets, const float* x,
+                               const float* y, const float* z, const float* r,
+                               const float* varZ, const float* varR,
+                               const uint32_t* windowOffsets, const float* zWindowLo,
+                               const float* zWindowHi, uint64_t* seedOffsets,
+                               b200seed_seeds* out);
+
 /* b200seed_run with a caller-provided azimuth column (phi[i] replaces the
  * on-device atan2f(y, x) replay; everything else is identical). */
 int b200seed_run_with_phi(b200seed_handle* h, uint32_t nSpacePoints, const float* x,
@@ -305,6 +330,10 @@ int b200seed_set_phi_sector(b200seed_handle* h, uint32_t firstPhiBin, uint32_t n
  * on the launching stream): ms[0] grid build, ms[1] middle work list,
  * ms[2] seeding kernel, ms[3] ordered seed compaction. */
 int b200seed_get_stage_times(const b200seed_handle* h, float* ms);
+/* The first n (<= 7) of: ms[0..3] as above, ms[4] doublet count pass + slot scan + chunk plan,
+ * ms[5] doublet fill pass (all chunks), ms[6] per-middle seeding kernels (all chunks);
+ * ms[2] = ms[4] + ms[5] + ms[6]. */
+int b200seed_get_stage_times_ex(const b200seed_handle* h, float* ms, uint32_t n);
 
 /* "Next" row f1: free track parameters of every seed, FP64 on the
  * device.  Replaces Acts::estimateTrackParamsFromSeed(sp0, sp1, sp2, bField)

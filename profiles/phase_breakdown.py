@@ -58,13 +58,13 @@ def find(s):
 
 
 marks = [(n, find(t)) for n, t in [
-    ("phase 0 windows", "---- phase 0: middle"), ("phase 1 doublets", "---- phase 1: doublets"),
+    ("phase 0 header / carve-up", "---- phase 0: header"), ("phase 1 keys", "---- phase 1: keys"),
     ("phase 2 sort both lists", "---- phase 2: order both"), ("phase 2 top records", "// tops: full records in sorted order"),
     ("phase 3a scans", "---- phase 3a"), ("phase 3b prefix max", "---- phase 3b"), ("phase 3c gap", "---- phase 3c"),
     ("phase 3d group candidates", "---- phase 3d"), ("seedConfirmation records", "---- seedConfirmation: weights"),
-    ("phase 3e weights", "---- phase 3e"), ("phase 3f selection", "---- phase 3f"), ("phase 4 seeds", "---- phase 4")]]
+    ("phase 3e weights", "---- phase 3e"), ("phase 3f selection + phase 4 seeds", "---- phase 3f")]]
 kstart = find("k_seed_middles(const __grid_constant__ SeedParams p)")
-kend = find("// the capacity tiers (see seeding_plugin.cu)")
+kend = find("// Seed compaction (ordered): tiled exclusive scan of the per-middle counts")
 
 
 def functions(src, pattern):
@@ -115,7 +115,7 @@ def innermost(lines):
 
 # helpers that are called from exactly one phase: used when an instruction has no call-site frame
 HELPER_PHASE = {
-    "find_doublets_both": "phase 1 doublets", "warp_append": "phase 1 doublets",
+    "warp_append": "phase 3c gap",
     "block_sort_both": "phase 2 sort both lists", "block_bucket_sort": "phase 2 sort both lists",
     "block_fix_ties": "phase 2 sort both lists", "block_has_ties": "phase 2 sort both lists",
     "warp_sort_replay_ties": "phase 2 sort both lists", "tie_flagged": "phase 2 sort both lists",

@@ -387,26 +387,44 @@ def test_property_checks_at_full_size(plugin):
 
 
 def test_materialised_doublets_match_oracle(plugin, O):
-    """Stage-level parity of the doublet search (DoubletSeedFinder.cpp:41-273): per middle the same
-    bottoms and tops in the reference's emission order with bit-identical
-    {cotTheta, iDeltaR, er, u, v, x', y'} (two-pass count / scan / fill path)."""
+    """Stage-level parity of the PRODUCTION doublet stage (k_doublets, DoubletSeedFinder.cpp:41-273): per middle
+    the same bottoms and tops in the reference's emission order with bit-identical
+    {cotTheta, iDeltaR, er, u, v, x', y'} -- the 32-byte records the seeding kernel reads from the arena.
+    Like the reference (TripletSeeder.cpp:62-69,79) the engine does not search the bottoms of a middle that has
+    no tops (or, with seedConfirmation, too few), and drops the tops of a middle without bottoms."""
     from acts_b200 import events
 
-    for name, mu in (("pu200", 20), ("itk_like", 20), ("pu200", 40)):
-        override = dict(interactionPointCut=1) if mu == 40 else {}
+    for name, mu, override in (("pu200", 20, {}), ("itk_like", 20, {}), ("pu200", 40, dict(interactionPointCut=1)),
+                               ("itk_conf", 20, {})):
         eng = plugin.SeedingEngine(make_config(name, plugin.config_init).update(**override))
         orc = O.Oracle(make_config(name, O.config_init).update(**override))
         ev = events.pileup_event(2, mu=mu)
-        eng.run(ev)
+        seeds = eng.run(ev)
         got = eng.debug_doublets()
-        ref = orc.run(ev, dump_doublets=True)["doublets"]
+        full = orc.run(ev, dump_doublets=True)
+        ref = full["doublets"]
+        assert _same_bits(seeds, full)
         assert got["nMiddles"] == ref["middlePos"].size
         assert np.array_equal(got["middlePos"], ref["middlePos"])
-        assert np.array_equal(got["firstDoublet"], ref["firstDoublet"])
-        assert np.array_equal(got["nBottom"], ref["nBottom"])
-        assert np.array_equal(got["otherPos"], ref["otherPos"])
-        for k in ("cotTheta", "iDeltaR", "er", "u", "v", "xNew", "yNew"):
-            assert np.array_equal(got[k].view(np.uint32), ref[k].view(np.uint32)), (name, k)
+        n_checked = 0
+        for w in range(got["nMiddles"]):
+            g0, g1 = int(got["firstDoublet"][w]), int(got["firstDoublet"][w + 1])
+            r0, r1 = int(ref["firstDoublet"][w]), int(ref["firstDoublet"][w + 1])
+            if g1 == g0:
+                # not searched: the reference's own lists say why (one side empty, or too few tops)
+                r_nb = int(ref["nBottom"][w])
+                r_nt = (r1 - r0) - r_nb
+                assert r_nb == 0 or r_nt == 0 or name == "itk_conf", (name, w, r_nb, r_nt)
+                continue
+            assert (g1 - g0, int(got["nBottom"][w])) == (r1 - r0, int(ref["nBottom"][w])), (name, w)
+            assert np.array_equal(got["otherPos"][g0:g1], ref["otherPos"][r0:r1]), (name, w)
+            for k in ("cotTheta", "iDeltaR", "er", "u", "v", "xNew", "yNew"):
+                assert np.array_equal(got[k][g0:g1].view(np.uint32), ref[k][r0:r1].view(np.uint32)), (name, w, k)
+            n_checked += 1
+        assert n_checked > 0.5 * got["nMiddles"]
+        cnt = eng.counters()
+        assert cnt["nBottomDoublets"] == full["counters"]["nBottomDoublets"]
+        assert cnt["nTopDoublets"] == full["counters"]["nTopDoublets"]
         eng.close()
 
 
@@ -579,16 +597,11 @@ def test_random_configurations_match_oracle(plugin, O):
             zw = [(-60.0, -20.0), (5.0, 45.0)]
         eng = plugin.SeedingEngine(cfg)
         orc = O.Oracle(cfgo)
-        try:
-            got = eng.run(ev, z_windows=zw)
-        except plugin.SeedingError as e:  # capacity tiers exhausted is loud, never wrong
-            assert e.code == 7, (trial, o, str(e))
-            eng.close()
-            continue
+        got = eng.run(ev, z_windows=zw)  # no configuration is refused for its size: the spill class takes what shared memory cannot
         ref = orc.run(ev, z_windows=zw)
         assert _same_bits(got, ref), (trial, o)
         eng.close()
         done += 1
         if done == 48:
             break
-    assert done >= 40
+    assert done == 48
