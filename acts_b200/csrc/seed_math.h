@@ -434,7 +434,7 @@ enum PairClass : int {
 template <bool kWithCurvature>
 B2S_HD int eval_pair_t(const DeviceConfig& c, float rM, float varZM, float varRM,
                        const BottomCtx& b, float cotThetaT, float erT, float iDeltaRT,
-                       float uT, float vT, float& curvature, float& impact) {
+                       float uT, const float* vTPtr, float& curvature, float& impact) {
   const float cotThetaAvg2 = fmul(b.cotThetaB, cotThetaT);
   // erT + erB + ((2 * (cotAvg2*varRM + varZM)) * iDeltaRB) * iDeltaRT, left to right
   const float corr = fmul(fmul(fmul(2.0f, fadd(fmul(cotThetaAvg2, varRM), varZM)), b.iDeltaRB), iDeltaRT);
@@ -444,6 +444,7 @@ B2S_HD int eval_pair_t(const DeviceConfig& c, float rM, float varZM, float varRM
   if (deltaCotTheta2 > fadd(error2, b.scatteringInRegion2)) return kPairFailA;
   const float dU = fsub(uT, b.Ub);
   if (dU == 0) return kPairSkip;
+  const float vT = *vTPtr;  // only pairs that pass the first slope cut read it
   const float A = fdiv(fsub(vT, b.Vb), dU);
   const float S2 = fadd(1.0f, fmul(A, A));
   const float B = fsub(b.Vb, fmul(A, b.Ub));
@@ -463,14 +464,21 @@ B2S_HD int eval_pair_t(const DeviceConfig& c, float rM, float varZM, float varRM
 B2S_HD int eval_pair(const DeviceConfig& c, float rM, float varZM, float varRM,
                      const BottomCtx& b, float cotThetaT, float erT, float iDeltaRT,
                      float uT, float vT, float& curvature, float& impact) {
-  return eval_pair_t<true>(c, rM, varZM, varRM, b, cotThetaT, erT, iDeltaRT, uT, vT, curvature, impact);
+  return eval_pair_t<true>(c, rM, varZM, varRM, b, cotThetaT, erT, iDeltaRT, uT, &vT, curvature, impact);
 }
 // classification only (the scans): no curvature division / square root
 B2S_HD int classify_pair(const DeviceConfig& c, float rM, float varZM, float varRM,
                          const BottomCtx& b, float cotThetaT, float erT, float iDeltaRT,
                          float uT, float vT) {
   float cu, im;
-  return eval_pair_t<false>(c, rM, varZM, varRM, b, cotThetaT, erT, iDeltaRT, uT, vT, cu, im);
+  return eval_pair_t<false>(c, rM, varZM, varRM, b, cotThetaT, erT, iDeltaRT, uT, &vT, cu, im);
+}
+// the scans: v of the top is read only when the pair gets past the first slope cut
+B2S_HD int classify_pair_lazy(const DeviceConfig& c, float rM, float varZM, float varRM,
+                              const BottomCtx& b, float cotThetaT, float erT, float iDeltaRT,
+                              float uT, const float* vTPtr) {
+  float cu, im;
+  return eval_pair_t<false>(c, rM, varZM, varRM, b, cotThetaT, erT, iDeltaRT, uT, vTPtr, cu, im);
 }
 
 // ---------------------------------------------------------------------------

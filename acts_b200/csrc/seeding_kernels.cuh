@@ -30,6 +30,12 @@
 
 namespace B200SEED_NS {
 
+#ifndef B200SEED_SPLIT_WALKERS
+#define B200SEED_SPLIT_WALKERS 0  // scans: 1 = separate backward / forward walkers per bottom, 0 = one merged walk
+#endif
+#ifndef B200SEED_REFILL
+#define B200SEED_REFILL 12  // idle lanes of a warp that trigger a refill of the scan walkers
+#endif
 #ifndef B200SEED_WORK_CHUNK
 #define B200SEED_WORK_CHUNK 8  // consecutive work items a block takes at a time (1 = none)
 #endif
@@ -674,7 +680,7 @@ constexpr uint32_t kMaxChunks = 4096;
 struct SeedCarve {
   uint32_t oRankB;    // u16[nB]   sorted rank -> index of the bottom in the arena slot
   uint32_t oTstar;    // u16[nB]   |P_j|, later the last failing top of the prefix
-  uint32_t oTops;     // 6 x u32[nT] sorted tops: cotTheta, iDeltaR, er, u, v, pos
+  uint32_t oTops;     // sorted tops: float4[nT] {cotTheta, er, iDeltaR, u}, float[nT] v, u32[nT] pos
   uint32_t oBuckets;  // u32[nBk + 1]
   uint32_t nBk;
   // region a (until the tops are gathered)
@@ -1409,11 +1415,8 @@ __global__ void __launch_bounds__(1024, 1) k_seed_middles(const __grid_constant_
     const SeedCarve cv = seed_carve(nB, nT);
     uint16_t* rankB = reinterpret_cast<uint16_t*>(base + cv.oRankB);
     uint16_t* tstar = reinterpret_cast<uint16_t*>(base + cv.oTstar);
-    float* sCot = reinterpret_cast<float*>(base + cv.oTops);
-    float* sIDR = sCot + nT;
-    float* sEr = sIDR + nT;
-    float* sU = sEr + nT;
-    float* sV = sU + nT;
+    float4* sA = reinterpret_cast<float4*>(base + cv.oTops);  // sorted tops: {cotTheta, er, iDeltaR, u}, then v, then pos
+    float* sV = reinterpret_cast<float*>(sA + nT);
     uint32_t* sPos = reinterpret_cast<uint32_t*>(sV + nT);
     uint32_t* buckets = reinterpret_cast<uint32_t*>(base + cv.oBuckets);
     float* keyB = reinterpret_cast<float*>(base + cv.oKeyB);
@@ -1451,7 +1454,9 @@ __global__ void __launch_bounds__(1024, 1) k_seed_middles(const __grid_constant_
     for (uint32_t t = tid; t < nT; t += THREADS) {
       const float4* src = reinterpret_cast<const float4*>(recT + rankT[t]);
       const float4 a = __ldg(src), b = __ldg(src + 1);
-      sPos[t] = __float_as_uint(a.x); sCot[t] = a.y; sIDR[t] = a.z; sEr[t] = a.w; sU[t] = b.x; sV[t] = b.y;
+      sPos[t] = __float_as_uint(a.x);
+      sA[t] = make_float4(a.y, a.w, a.z, b.x);
+      sV[t] = b.y;
     }
     __syncthreads();
     // |P_j|: tops with cotT <= cotB_j
@@ -1460,7 +1465,7 @@ __global__ void __launch_bounds__(1024, 1) k_seed_middles(const __grid_constant_
       uint32_t lo = 0, hi = nT;
       while (lo < hi) {
         const uint32_t md = (lo + hi) >> 1;
-        if (c < sCot[md]) hi = md; else lo = md + 1;
+        if (c < sA[md].x) hi = md; else lo = md + 1;
       }
       tstar[j] = (uint16_t)lo;
     }
@@ -1478,37 +1483,37 @@ __global__ void __launch_bounds__(1024, 1) k_seed_middles(const __grid_constant_
       const uint32_t slot = atomicAdd(&sh.poolCount, 1u);
       if (slot < poolCap) pool[slot] = t | (j << 16);
     };
+#if B200SEED_SPLIT_WALKERS
     {
-      // One lane per bottom; a lane that finishes takes the next unassigned bottom as soon as kRefill lanes
-      // of its warp are idle, so the warp stays full although the windows differ in length.  Per bottom one
-      // merged loop: down from |P_j| - 1 to the last failing top of the prefix, then up from |P_j| to the
-      // first failing top beyond it.
-      constexpr uint32_t kRefill = 12;
-      bool active = false, exhausted = false;
-      uint32_t j = 0, H = 0, ts = 0, tf = 0;
-      int tb = -1;
-      bool backDone = true, fwdDone = true;
+      // Two walkers per bottom, one lane each: the backward one goes down from |P_j| - 1 to the last failing top
+      // of the prefix (-> H_j, t*_j), the forward one up from |P_j| to the first failing top beyond it (brk_j).
+      // A lane that finishes takes the next unassigned walker as soon as kRefill lanes of its warp are idle, so the
+      // warp stays full although the walks differ in length.  Both walkers of a bottom start in the same step (they
+      // read |P_j| from tstar[j] before the backward one can overwrite it with t*_j).
+      constexpr uint32_t kRefill = B200SEED_REFILL;
+      bool active = false, exhausted = false;  // exhausted is warp-uniform
+      uint32_t j = 0;
+      int t = 0, tEnd = 0, step = 0;
       BottomCtx bc{};
       for (;;) {
         const uint32_t idleMask = __ballot_sync(0xffffffffu, !active);
-        if (!exhausted && (idleMask == 0xffffffffu || (uint32_t)__popc(idleMask) >= kRefill)) {
-          const uint32_t nIdle = (uint32_t)__popc(idleMask);
+        const uint32_t nIdle = (uint32_t)__popc(idleMask);
+        if (!exhausted && nIdle >= kRefill) {
+          const uint32_t nPairs = nIdle >> 1;
           uint32_t first = 0;
-          if (lane == 0) first = atomicAdd(&sh.nextBottom, nIdle);
+          if (lane == 0) first = atomicAdd(&sh.nextBottom, nPairs);
           first = __shfl_sync(0xffffffffu, first, 0);
-          if (first + nIdle >= nB) exhausted = true;
+          exhausted = first + nPairs >= nB;
           if (!active) {
-            const uint32_t jn = first + (uint32_t)__popc(idleMask & ltMask);
-            if (jn < nB) {
+            const uint32_t rank = (uint32_t)__popc(idleMask & ltMask);
+            const uint32_t jn = first + (rank >> 1);
+            if (rank < 2u * nPairs && jn < nB) {
               j = jn;
               bottomCtx(j, bc);
-              const uint32_t lo = tstar[j];
-              H = 0; ts = 0;
-              tb = (int)lo - 1;
-              tf = lo;
-              backDone = tb < 0;
-              fwdDone = tf >= nT;
-              active = true;
+              const int P = (int)tstar[j];
+              if (rank & 1u) { t = P; step = 1; tEnd = (int)nT; } else { t = P - 1; step = -1; tEnd = -1; }
+              active = t != tEnd;
+              if (!active && step < 0) { hval[j] = 0; tstar[j] = 0; }  // empty prefix
             }
           }
         }
@@ -1517,32 +1522,83 @@ __global__ void __launch_bounds__(1024, 1) k_seed_middles(const __grid_constant_
           continue;
         }
         if (active) {
-          if (!(backDone && fwdDone)) {
-            const bool doBack = !backDone;
-            const uint32_t t = doBack ? (uint32_t)tb : tf;
-            ++myTests;
-            const int cls = classify_pair(cfg, mid.r, mid.varZ, mid.varR, bc, sCot[t], sEr[t], sIDR[t], sU[t], sV[t]);
-            const bool fail = cls == kPairFailA || cls == kPairFailB;
-            if (cls == kPairEmit) emit(j, t);
-            if (doBack) {
-              if (fail) {
-                H = cls == kPairFailA ? t + 1 : t;
-                ts = t;
-                backDone = true;
-              } else {
-                --tb;
-                backDone = tb < 0;
-              }
-            } else {
-              if (fail) {
-                fwdDone = true;
-              } else {
-                ++tf;
-                fwdDone = tf >= nT;
-              }
+          ++myTests;
+          const float4 a = sA[t];
+          const int cls = classify_pair_lazy(cfg, mid.r, mid.varZ, mid.varR, bc, a.x, a.y, a.z, a.w, sV + t);
+          if (cls == kPairEmit) emit(j, (uint32_t)t);
+          if (cls <= kPairFailB) {  // the walk ends at the first failing top
+            if (step < 0) {
+              hval[j] = (uint16_t)(cls == kPairFailA ? t + 1 : t);
+              tstar[j] = (uint16_t)t;
+            }
+            active = false;
+          } else {
+            t += step;
+            if (t == tEnd) {
+              if (step < 0) { hval[j] = 0; tstar[j] = 0; }  // no failing top in the prefix
+              active = false;
             }
           }
-          if (backDone && fwdDone) {
+        }
+      }
+    }
+#else
+    {
+      // One lane per bottom; a lane that finishes takes the next unassigned bottom as soon as kRefill lanes
+      // of its warp are idle, so the warp stays full although the windows differ in length.  Per bottom one
+      // merged walk: down from |P_j| - 1 to the last failing top of the prefix (-> H_j, t*_j), then up from
+      // |P_j| to the first failing top beyond it (brk_j).
+      constexpr uint32_t kRefill = B200SEED_REFILL;
+      bool active = false, exhausted = false;  // exhausted is warp-uniform
+      uint32_t j = 0, H = 0, ts = 0;
+      int t = 0, tUp = 0, step = 0;
+      BottomCtx bc{};
+      for (;;) {
+        const uint32_t idleMask = __ballot_sync(0xffffffffu, !active);
+        const uint32_t nIdle = (uint32_t)__popc(idleMask);
+        if (!exhausted && nIdle >= kRefill) {
+          uint32_t first = 0;
+          if (lane == 0) first = atomicAdd(&sh.nextBottom, nIdle);
+          first = __shfl_sync(0xffffffffu, first, 0);
+          exhausted = first + nIdle >= nB;
+          if (!active) {
+            const uint32_t jn = first + (uint32_t)__popc(idleMask & ltMask);
+            if (jn < nB) {
+              j = jn;
+              bottomCtx(j, bc);
+              const int P = (int)tstar[j];
+              H = 0; ts = 0;
+              tUp = P;
+              if (P > 0) { t = P - 1; step = -1; } else { t = 0; step = 1; }
+              active = t < (int)nT;  // nT > 0: always
+            }
+          }
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0u) {
+          if (exhausted) break;
+          continue;
+        }
+        if (active) {
+          ++myTests;
+          const float4 a = sA[t];
+          const int cls = classify_pair_lazy(cfg, mid.r, mid.varZ, mid.varR, bc, a.x, a.y, a.z, a.w, sV + t);
+          if (cls == kPairEmit) emit(j, (uint32_t)t);
+          const bool fail = cls <= kPairFailB;
+          bool done = false;
+          if (step < 0) {
+            if (fail) { H = (uint32_t)(cls == kPairFailA ? t + 1 : t); ts = (uint32_t)t; }
+            if (fail || t == 0) {  // the prefix is done: turn around
+              t = tUp;
+              step = 1;
+              done = t >= (int)nT;
+            } else {
+              --t;
+            }
+          } else {
+            ++t;
+            done = fail || t >= (int)nT;
+          }
+          if (done) {
             hval[j] = (uint16_t)H;
             tstar[j] = (uint16_t)ts;
             active = false;
@@ -1550,6 +1606,7 @@ __global__ void __launch_bounds__(1024, 1) k_seed_middles(const __grid_constant_
         }
       }
     }
+#endif
     __syncthreads();
 
     // ---- phase 3b: window start = exclusive running max of H --------------
@@ -1589,7 +1646,8 @@ __global__ void __launch_bounds__(1024, 1) k_seed_middles(const __grid_constant_
         bottomCtx(j, bc);
         for (uint32_t t = s; t < te; ++t) {
           ++myTests;
-          const int cls = classify_pair(cfg, mid.r, mid.varZ, mid.varR, bc, sCot[t], sEr[t], sIDR[t], sU[t], sV[t]);
+          const float4 a = sA[t];
+          const int cls = classify_pair_lazy(cfg, mid.r, mid.varZ, mid.varR, bc, a.x, a.y, a.z, a.w, sV + t);
           if (cls == kPairEmit) emit(j, t);
         }
       }
@@ -1626,7 +1684,8 @@ __global__ void __launch_bounds__(1024, 1) k_seed_middles(const __grid_constant_
       BottomCtx bc;
       bottomCtx(j, bc);
       Cand c;
-      eval_pair(cfg, mid.r, mid.varZ, mid.varR, bc, sCot[t], sEr[t], sIDR[t], sU[t], sV[t], c.curv, c.impactOrWeight);
+      const float4 a = sA[t];
+      eval_pair(cfg, mid.r, mid.varZ, mid.varR, bc, a.x, a.y, a.z, a.w, sV[t], c.curv, c.impactOrWeight);
       const float2 tzr = ldg2(p.pZR + sPos[t]);
       c.topR = tzr.y;
       if (cfg.useDeltaRinsteadOfTopRadius) {
