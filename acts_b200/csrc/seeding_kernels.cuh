@@ -1373,8 +1373,11 @@ __device__ __forceinline__ void block_fix_ties(uint32_t n, const float* cot, uin
 
 // The block size is a launch parameter (any multiple of 32 up to 1024): every class runs the same code with the
 // thread count that fills the SM next to its shared-memory footprint (seeding_plugin.cu: kSeedClassShape).
+#ifndef B200SEED_SEED_REGS
+#define B200SEED_SEED_REGS 56  // 36 warps per SM; measured against 64 (32 warps) and 48 (42 warps, spills)
+#endif
 template <bool kConf, bool kSpill>
-__global__ void __launch_bounds__(1024, 1) k_seed_middles(const __grid_constant__ SeedParams p) {
+__global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_constant__ SeedParams p) {
   const uint32_t THREADS = blockDim.x;
   extern __shared__ __align__(16) unsigned char smemRaw[];
   __shared__ SeedShared sh;

@@ -86,6 +86,7 @@ struct b200seed_handle {
   uint32_t phiFirst = 1, phiCount = 0xFFFFFFFFu;  // middle phi-bin sector (default: all)
   // shared-memory classes of the seeding kernel (seeding_kernels.cuh): blocks per SM, dynamic bytes per block
   int classBlocksPerSM[kNumSeedClasses] = {1, 1, 1, 1, 1, 1};
+  int classThreads[kNumSeedClasses] = {32, 32, 32, 32, 32, 32};
   uint32_t classBytes[kNumSeedClasses] = {0, 0, 0, 0, 0, 0};
   int doubletBlocksPerSM[2] = {1, 1};  // count / fill
   size_t arenaMaxBytes = (size_t)2048 << 20;  // B200SEED_ARENA_MB: doublet arena per chunk of middles
@@ -221,8 +222,8 @@ int ensure_workspace(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal) {
 // Shared-memory classes of k_seed_middles: {threads, blocks per SM aimed at}.  A middle goes to the smallest class
 // whose dynamic shared memory holds its lists (exact sizes, SeedCarve); the last class keeps them in global memory.
 struct SeedClassShape { int threads, blocksPerSM; };
-// (64 registers per thread: 32 warps fit an SM)
-constexpr SeedClassShape kSeedClassShape[kNumSeedClasses] = {{160, 6}, {256, 4}, {320, 3}, {512, 2}, {1024, 1}, {1024, 1}};
+// (56 registers per thread: 36 warps fit an SM; thread counts measured, tools/sweep_regs.sh)
+constexpr SeedClassShape kSeedClassShape[kNumSeedClasses] = {{192, 6}, {288, 4}, {384, 3}, {576, 2}, {1024, 1}, {1024, 1}};
 
 using SeedKernel = void (*)(const SeedParams);
 template <bool kConf>
@@ -511,7 +512,7 @@ int enqueue(b200seed_handle* h) {
       sp.overflowCount = last ? nullptr : cw + 8 + k + 1;
       sp.arrayBytes = last ? spillBytes : h->classBytes[k];
       const int blocks = last ? spillBlocks : h->smCount * h->classBlocksPerSM[k];
-      seed_kernel(conf, k)<<<blocks, kSeedClassShape[k].threads, last ? 0 : h->classBytes[k], s>>>(sp);
+      seed_kernel(conf, k)<<<blocks, h->classThreads[k], last ? 0 : h->classBytes[k], s>>>(sp);
     }
     CUDA_TRY(cudaEventRecord(h->evChunk[2 * c + 1], s));
     launches += 1 + kNumSeedClasses;
@@ -766,8 +767,16 @@ int b200seed_create(const b200seed_config* cfg, int device, b200seed_handle** ou
         CREATE_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
       }
       h->classBytes[c] = bytes;
+      h->classThreads[c] = kSeedClassShape[c].threads;
+      if (const char* v = std::getenv("B200SEED_CLASS_THREADS")) {  // kernel experiments: "160,256,320,512,1024,1024"
+        int t[kNumSeedClasses] = {0};
+        if (std::sscanf(v, "%d,%d,%d,%d,%d,%d", &t[0], &t[1], &t[2], &t[3], &t[4], &t[5]) == kNumSeedClasses && t[c] >= 32 &&
+            t[c] <= 1024 && t[c] % 32 == 0) {
+          h->classThreads[c] = t[c];
+        }
+      }
       int b = 0;
-      CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k, kSeedClassShape[c].threads, bytes));
+      CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k, h->classThreads[c], bytes));
       h->classBlocksPerSM[c] = std::max(1, b);
     }
     int b = 0;
@@ -780,7 +789,7 @@ int b200seed_create(const b200seed_config* cfg, int device, b200seed_handle** ou
   if (std::getenv("B200SEED_VERBOSE") != nullptr) {
     for (int c = 0; c < kNumSeedClasses; ++c) {
       std::fprintf(stderr, "b200seed: seed class %d: %d threads, %u bytes of shared memory, %d blocks per SM\n", c,
-                   kSeedClassShape[c].threads, h->classBytes[c], h->classBlocksPerSM[c]);
+                   h->classThreads[c], h->classBytes[c], h->classBlocksPerSM[c]);
     }
     std::fprintf(stderr, "b200seed: doublet kernels: %d / %d blocks per SM (count / fill)\n", h->doubletBlocksPerSM[0],
                  h->doubletBlocksPerSM[1]);
