@@ -978,6 +978,8 @@ __global__ void __launch_bounds__(kDoubletWarps * 32) k_doublets(const __grid_co
           if (lane == 0) atomicOr(p.status, kStatusOverflowDoublets);
           capB = 0; capT = 0;
         }
+        capB = (capB + 3u) & ~3u;  // slots and their two halves start on 16-byte boundaries of the key array (TMA)
+        capT = (capT + 3u) & ~3u;
         if (lane == 0) { p.capB[w] = capB; p.capT[w] = capT; }
         if (capB != 0u) {
           const uint32_t foot = seed_carve(capB, capT).minBytes;
@@ -1376,6 +1378,35 @@ __device__ __forceinline__ void block_fix_ties(uint32_t n, const float* cot, uin
 #ifndef B200SEED_SEED_REGS
 #define B200SEED_SEED_REGS 56  // 36 warps per SM; measured against 64 (32 warps) and 48 (42 warps, spills)
 #endif
+// ---- TMA bulk copies (cp.async.bulk, 1-D, global -> shared) completing on an mbarrier ----------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bytes: multiple of 16; dst and src 16-byte aligned
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MBAR_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra MBAR_WAIT_%=;\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// generic-proxy accesses to shared memory before, async-proxy (TMA) writes to the same bytes after
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 template <bool kConf, bool kSpill>
 __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_constant__ SeedParams p) {
   const uint32_t THREADS = blockDim.x;
@@ -1388,16 +1419,20 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
   const uint32_t nWork = *p.nWorkPtr;
   unsigned char* const base = kSpill ? p.spillScratch + (size_t)blockIdx.x * p.arrayBytes : smemRaw;
 
+  __shared__ __align__(8) uint64_t keyBar;  // completion of the TMA copies of the cotTheta keys
+  uint32_t keyParity = 0;
   if (tid < (uint32_t)kCntSlots) sh.cnt[tid] = 0ull;
   if (tid == 0) {
     const uint32_t item = atomicAdd(p.workCounter, 1u);
     sh.w = item < nWork ? p.workList[item] : 0xFFFFFFFFu;
+    if (!kSpill) mbar_init(&keyBar, 1);
   }
 
   for (;;) {
     __syncthreads();
     const uint32_t w = sh.w;
     if (w == 0xFFFFFFFFu) break;
+    if (!kSpill) fence_proxy_async();  // this thread's accesses to the previous middle's arrays, before the TMA writes below
     __syncthreads();  // everybody has read sh.w before thread 0 fetches the next item
 
     // ---- phase 0: header, middle, carve-up ---------------------------------
@@ -1440,9 +1475,22 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
     }
 
     // ---- phase 1: keys ---------------------------------------------------------
-    for (uint32_t i = tid; i < nB; i += THREADS) keyB[i] = __ldg(gKeyB + i);
-    for (uint32_t i = tid; i < nT; i += THREADS) keyT[i] = __ldg(gKeyT + i);
-    __syncthreads();
+    // Two TMA bulk copies stage the contiguous cotTheta key spans of the middle's arena slot in shared memory
+    // (slots and list capacities are multiples of four records, so both spans are 16-byte aligned and padded).
+    if constexpr (!kSpill) {
+      if (tid == 0) {
+        const uint32_t bytesB = ((nB + 3u) & ~3u) * 4u, bytesT = ((nT + 3u) & ~3u) * 4u;
+        mbar_expect_tx(&keyBar, bytesB + bytesT);
+        tma_bulk_g2s(keyB, gKeyB, bytesB, &keyBar);
+        tma_bulk_g2s(keyT, gKeyT, bytesT, &keyBar);
+      }
+      mbar_wait(&keyBar, keyParity);
+      keyParity ^= 1u;
+    } else {
+      for (uint32_t i = tid; i < nB; i += THREADS) keyB[i] = __ldg(gKeyB + i);
+      for (uint32_t i = tid; i < nT; i += THREADS) keyT[i] = __ldg(gKeyT + i);
+      __syncthreads();
+    }
 
     // ---- phase 2: order both lists like DoubletSeedFinder.hpp:94-104 -------
     block_sort_both(nB, keyB, ordered_to_float(h1.x), ordered_to_float(h1.y), nT, keyT, ordered_to_float(h1.z),
