@@ -2308,10 +2308,16 @@ __global__ void __launch_bounds__(256) k_estimate_params(const uint32_t* __restr
                                                          const uint32_t* __restrict__ t, const float* __restrict__ x,
                                                          const float* __restrict__ y, const float* __restrict__ z,
                                                          double bx, double by, double bz, double* __restrict__ out,
-                                                         unsigned long long n) {
+                                                         unsigned long long n, uint32_t nSpacePoints, int* status) {
   for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * blockDim.x) {
     const uint32_t ib = b[i], im = m[i], it = t[i];
+    if (ib >= nSpacePoints || im >= nSpacePoints || it >= nSpacePoints) {  // caller-supplied indices: never read outside the columns
+      atomicOr(status, 1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) out[i * 8 + k] = 0.0;
+      continue;
+    }
     const double s0[3] = {(double)x[ib], (double)y[ib], (double)z[ib]};
     const double s1[3] = {(double)x[im], (double)y[im], (double)z[im]};
     const double s2[3] = {(double)x[it], (double)y[it], (double)z[it]};

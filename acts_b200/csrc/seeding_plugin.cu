@@ -864,6 +864,11 @@ int b200seed_set_phi_sector(b200seed_handle* h, uint32_t firstPhiBin, uint32_t n
     return fail(B200SEED_ERR_UNSUPPORTED,
                 "seedConfirmation couples the middles of an event through bestSeedQualityMap: no phi-sector split");
   }
+  if (nPhiBins == 0 && firstPhiBin == B200SEED_PHI_SECTOR_EMPTY) {  // a rank without bins (more ranks than phi bins): no middles at all
+    h->phiFirst = 0xFFFFFFFFu;
+    h->phiCount = 0;
+    return B200SEED_OK;
+  }
   if (nPhiBins == 0) {
     h->phiFirst = 1;
     h->phiCount = 0xFFFFFFFFu;
@@ -1315,12 +1320,16 @@ int b200seed_estimate_params(b200seed_handle* h, uint64_t nSeeds, const uint32_t
   }
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
-  DevBuf idx[3], col[3], out;
+  const double bNorm2 = bField[0] * bField[0] + bField[1] * bField[1] + bField[2] * bField[2];
+  if (!(bNorm2 > 0.0)) return fail(B200SEED_ERR_INVALID_ARGUMENT, "estimate_params: magnetic field of zero (or NaN) norm");
+  DevBuf idx[3], col[3], out, st;
   struct Guard {
     std::vector<DevBuf*> bufs;
     ~Guard() { for (DevBuf* b : bufs) b->release(); }
   } guard;
-  guard.bufs = {&idx[0], &idx[1], &idx[2], &col[0], &col[1], &col[2], &out};
+  guard.bufs = {&idx[0], &idx[1], &idx[2], &col[0], &col[1], &col[2], &out, &st};
+  CUDA_TRY(st.reserve(16));
+  CUDA_TRY(cudaMemsetAsync(st.ptr, 0, 16, s));
   const uint32_t* hi[3] = {bottom, middle, top};
   const float* hc[3] = {x, y, z};
   for (int k = 0; k < 3; ++k) {
@@ -1333,10 +1342,13 @@ int b200seed_estimate_params(b200seed_handle* h, uint64_t nSeeds, const uint32_t
   const int blocks = (int)std::min<uint64_t>((nSeeds + 255) / 256, (uint64_t)h->smCount * 8);
   k_estimate_params<<<blocks, 256, 0, s>>>(idx[0].as<uint32_t>(), idx[1].as<uint32_t>(), idx[2].as<uint32_t>(),
                                            col[0].as<float>(), col[1].as<float>(), col[2].as<float>(), bField[0], bField[1],
-                                           bField[2], out.as<double>(), nSeeds);
+                                           bField[2], out.as<double>(), nSeeds, nSpacePoints, st.as<int>());
   CUDA_TRY(cudaGetLastError());
+  int bad = 0;
+  CUDA_TRY(cudaMemcpyAsync(&bad, st.ptr, 4, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(freeParams, out.ptr, nSeeds * 64, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
+  if (bad != 0) return fail(B200SEED_ERR_INVALID_ARGUMENT, "estimate_params: a seed refers to a space point index >= nSpacePoints");
   return B200SEED_OK;
 }
 

@@ -150,8 +150,11 @@ class SeedingEngine:
         _check(lib().b200seed_get_counters(self._h, C.byref(c)))
         return c.as_dict()
 
-    def set_phi_sector(self, first_phi_bin: int = 1, n_phi_bins: int = 0):
-        """Seed only middles in phi bins [first, first + n) (1-based); n = 0 -> all."""
+    def set_phi_sector(self, first_phi_bin: int = 1, n_phi_bins: int = 0, empty: bool = False):
+        """Seed only middles in phi bins [first, first + n) (1-based); n = 0 -> all; ``empty``: no bin at all
+        (a rank of a split with more ranks than phi bins)."""
+        if empty:
+            first_phi_bin, n_phi_bins = 0xFFFFFFFF, 0
         _check(lib().b200seed_set_phi_sector(self._h, first_phi_bin, n_phi_bins))
 
     def estimate_params(self, seeds: dict, ev: dict, b_field=(0.0, 0.0, 2 * 0.000299792458)) -> np.ndarray:

@@ -34,8 +34,22 @@ def gather_seed_counts(local_counts: dict[int, int], n_events: int, group=None) 
 
 def phi_sector_of_rank(n_phi_bins: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous block of middle phi bins (1-based first bin, count) of one rank when a
-    single event is split over `world` GPUs (latency mode, BASELINE.json configs[4])."""
+    single event is split over `world` GPUs (latency mode, BASELINE.json configs[4]).
+
+    With more ranks than phi bins the surplus ranks get count 0: they must seed NOTHING
+    (``SeedingEngine.set_phi_sector(empty=True)`` / ``apply_phi_sector`` below) -- a plain
+    ``set_phi_sector(first, 0)`` means "all bins" and would duplicate every seed."""
     base, extra = divmod(n_phi_bins, world)
     first = 1 + rank * base + min(rank, extra)
     count = base + (1 if rank < extra else 0)
+    return first, count
+
+
+def apply_phi_sector(engine, n_phi_bins: int, rank: int, world: int) -> tuple[int, int]:
+    """Restrict ``engine`` to the sector of ``rank``; ranks without bins are set to the empty sector."""
+    first, count = phi_sector_of_rank(n_phi_bins, rank, world)
+    if count == 0:
+        engine.set_phi_sector(empty=True)
+    else:
+        engine.set_phi_sector(first, count)
     return first, count

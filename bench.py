@@ -14,14 +14,20 @@ elapsed time.
 
 Printed JSON (one line, rank 0):
   value      events/s, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e        events/s through the host C ABI (b200seed_run_batch) with pinned
-             host buffers: H2D of the six columns and D2H of the seeds inside
-             the timed region
-  roofline   dominant kernel (k_seed_middles): algorithmic HBM bytes / time vs
-             the measured HBM peak, plus the FP32 view in `compute` (the fused
-             kernel is instruction-issue bound)
-  cpu_baseline  the oracle (CPU port of the reference algorithm) timed on the
-             host cores on a bounded sample
+  e2e        events/s through the host C ABI the way the reference is called: one
+             event per b200seed_run call from Sequencer-like worker threads (one
+             handle each), pinned host buffers, H2D of the six columns and D2H of
+             the seeds inside the timed region (thread count swept to saturation)
+  parity     timed events re-seeded by the UNMODIFIED reference (oracle/_ref) on the
+             host cores and compared bit for bit, order included; a mismatch fails the run
+  roofline   dominant kernel (k_seed_middles, all launches of a step): algorithmic HBM
+             bytes / time vs the measured HBM peak; `doublet_stage` is the HBM-bound
+             fill pass; `compute` the FP32 view
+  cpu_baseline / --impl reference   the reference's own GridTripletSeedingAlgorithm
+             (oracle/_ref, built from the unmodified sources) on whole events, one
+             event per execute() call from all host threads, like the Sequencer
+  latency    config 5: one <mu>=300 event, unsplit on one GPU and split into phi
+             sectors over the N ranks of the run
 """
 from __future__ import annotations
 
@@ -123,29 +129,40 @@ def host_cores():
 
 
 # ---------------------------------------------------------------------------
-# reference arm: the CPU restatement of the reference algorithm on the host cores
+# reference arm: the reference's own implementation on the host cores
 # ---------------------------------------------------------------------------
-def cpu_reference_rate(n_threads, steps, warmup, nav_stride, evs=None):
-    """events/s of the oracle with n_threads workers.  One step = n_threads
-    events, each seeded on 1/nav_stride of its middle bins (bounded sample;
-    the grid is built in full), handed out dynamically like the Sequencer's
-    parallel_for over events."""
-    from acts_b200 import config, events
+def reference_engine():
+    """(object with run_many(cols, offsets, n_threads), kind): oracle/_ref = the unmodified reference sources
+    when the library is there (built where /root/reference is mounted, travels with the snapshot), else the
+    oracle port."""
+    from acts_b200 import config
     from oracle import oracle as O
 
-    orc = O.Oracle(config.pu200_config(O.config_init))
-    if evs is None:
-        evs = make_events(min(n_threads, 8))
+    try:
+        from oracle import ref as R
+
+        if R.available() or R.build():
+            return R.Reference(config.pu200_config(O.config_init)), "reference"
+    except Exception:
+        pass
+    return O.Oracle(config.pu200_config(O.config_init)), "port"
+
+
+def cpu_reference_rate(n_threads, steps, warmup, evs):
+    """events/s of the reference algorithm: one step = n_threads WHOLE events, one event per execute() call,
+    handed out to n_threads worker threads that share one algorithm object (Sequencer.cpp:472-525)."""
+    from acts_b200 import events
+
+    eng, kind = reference_engine()
     batch = [evs[i % len(evs)] for i in range(n_threads)]
     cols, off = events.concat_events(batch)
     for _ in range(warmup):
-        orc.run_many(cols, off, n_threads, nav_stride)
+        eng.run_many(cols, off, n_threads)
     t0 = time.perf_counter()
     for _ in range(steps):
-        orc.run_many(cols, off, n_threads, nav_stride)
+        eng.run_many(cols, off, n_threads)
     dt = time.perf_counter() - t0
-    events_equiv = steps * n_threads / float(nav_stride)
-    return events_equiv / dt, dt / steps
+    return steps * n_threads / dt, dt / steps, kind
 
 
 def run_reference(args):
@@ -153,16 +170,20 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = host_cores()
-    nav_stride = 8
-    rate, step_s = cpu_reference_rate(cores, args.steps, args.warmup, nav_stride)
-    sample = (f"{cores} events per step (one per thread), each seeded on every {nav_stride}th middle phi-bin "
-              f"(1/{nav_stride} of the event's seeding work, full grid build), oracle C++ -O2 no -march")
+    # a whole <mu>=200 event costs ~13 s of one core: one untimed step is warm-up enough for a CPU arm and keeps
+    # the run at (1 + K) x ~14 s
+    warm = min(args.warmup, 1)
+    rate, step_s, kind = cpu_reference_rate(cores, args.steps, warm, make_events(min(cores, 16)))
+    sample = (f"{cores} whole events per step, one event per execute() call from {cores} worker threads sharing one "
+              f"algorithm object (the Sequencer's pattern); "
+              + ("unmodified reference sources (oracle/_ref), default build flags -O2, no -march" if kind == "reference"
+                 else "oracle port, -O2, no -march") + f"; {warm} untimed warm-up step(s)")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": warm, "ms_per_step": step_s * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "events_per_step": cores / nav_stride},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "events_per_step": cores},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -172,11 +193,39 @@ def run_reference(args):
 # ---------------------------------------------------------------------------
 # this repo's arm
 # ---------------------------------------------------------------------------
+KEYS = ("bottom", "middle", "top", "quality", "vertexZ")
+
+
+def pinned(shape_or_array, dtype=None):
+    import torch
+
+    if isinstance(shape_or_array, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(shape_or_array)).pin_memory()
+        return t, t.numpy()
+    t = torch.empty(shape_or_array, dtype=dtype).pin_memory()
+    return t, t.numpy()
+
+
+def pinned_seed_columns(cap):
+    import torch
+
+    keep, out = [], {}
+    for k in KEYS:
+        t, a = pinned(cap, torch.float32 if k in ("quality", "vertexZ") else torch.int32)
+        keep.append(t)
+        out[k] = a.view(np.uint32) if k in ("bottom", "middle", "top") else a
+    return keep, out
+
+
+def same_bits(a, b):
+    return all(np.array_equal(np.asarray(a[k]).view(np.uint32), np.asarray(b[k]).view(np.uint32)) for k in KEYS)
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
 
-    from acts_b200 import config, events, plugin
+    from acts_b200 import config, events, plugin, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -194,9 +243,11 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
 
     E = args.events_per_step
-    # every rank seeds its own events (event sharding: event e -> rank e mod world)
+    # Weak scaling: every GPU gets the same amount of work per step.  All ranks seed the SAME pool of events (event
+    # e of the pool stands for events e, e + pool, ... of a long run): with different random events per rank the
+    # max-over-ranks time would measure the spread of the event sizes (4 % at N = 8 in round 1), not the engine.
     n_distinct = max(E, args.distinct_events)
-    evs = make_events(n_distinct, first=rank * n_distinct)
+    evs = make_events(n_distinct, first=0)
     cfg = config.pu200_config(plugin.config_init)
     eng = plugin.SeedingEngine(cfg, device=local)
     K = max(1, int(plugin.plan_tables(cfg)["seedsPerMiddle"]))
@@ -213,114 +264,202 @@ def run_gpu(args):
         d_out = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(3)] + \
                 [torch.empty(cap, dtype=torch.float32, device=dev) for _ in range(2)]
         d_soff = torch.zeros(E + 1, dtype=torch.int64, device=dev)
-        h_cols = {k: torch.from_numpy(cols[k]).pin_memory() for k in cols}
         batches.append(dict(cols=cols, off=off, n_total=n_total, d_cols=d_cols, d_off=d_off, cap=cap, d_out=d_out,
-                            d_soff=d_soff, h_cols=h_cols))
+                            d_soff=d_soff))
     # a real (non-NULL) stream: the plugin enqueues on it and the CUDA events below see the work
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
 
-    def step_device(i):
+    def step_device(engine, i):
         b = batches[i % n_batches]
-        eng.run_batch_device(E, b["n_total"], b["d_off"].data_ptr(), [t.data_ptr() for t in b["d_cols"]],
-                             b["d_soff"].data_ptr(), [t.data_ptr() for t in b["d_out"]], b["cap"],
-                             stream=C.c_void_p(stream.cuda_stream))
+        engine.run_batch_device(E, b["n_total"], b["d_off"].data_ptr(), [t.data_ptr() for t in b["d_cols"]],
+                                b["d_soff"].data_ptr(), [t.data_ptr() for t in b["d_out"]], b["cap"],
+                                stream=C.c_void_p(stream.cuda_stream))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for i in range(args.warmup):
-        step_device(i)
+        step_device(eng, i)
     eng.sync()
     launches_per_step = eng.counters()["nKernelLaunches"]
 
-    seed_ms, grid_ms = [], []
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         e0.record(stream)
         for i in range(args.steps):
-            step_device(args.warmup + i)
+            step_device(eng, args.warmup + i)
         e1.record(stream)
         barrier()
-    elapsed_ms = e0.elapsed_time(e1)
+    elapsed_ms = max_over_ranks(e0.elapsed_time(e1))
     n_seeds_last = eng.sync()
     cnt = eng.counters()
-    # per-kernel durations, measured live with the plugin's CUDA events (same
-    # stream) in a second, identically shaped pass so that reading the events
-    # back does not put host syncs into the timed region above
+    value = world * E * args.steps / (elapsed_ms * 1e-3)
+    # per-stage durations, measured live with the plugin's CUDA events (same stream) in a second, identically
+    # shaped pass so that reading the events back does not put host syncs into the timed region above
+    stage = {k: [] for k in ("grid", "seed", "doublet_count", "doublet_fill", "seed_middles")}
     for i in range(min(args.steps, 8)):
-        step_device(args.warmup + i)
+        step_device(eng, args.warmup + i)
         eng.sync()
         st = eng.stage_times_ms()
-        seed_ms.append(st["seed"])
-        grid_ms.append(st["grid"])
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    value = world * E * args.steps / (elapsed_ms * 1e-3)
+        for k in stage:
+            stage[k].append(st[k])
+    stage = {k: float(np.mean(v)) for k, v in stage.items()}
+    cnt_stage = eng.counters()  # counters of the last batch of the stage pass
 
-    # ---- end to end through the host C ABI ---------------------------------
-    # The reference runs this algorithm from several Sequencer worker threads, one event (here: batch) per call
-    # (Sequencer.cpp:472-525); the plugin's contract is one handle per worker thread.  `e2e_threads` workers, each
-    # with its own handle and pinned buffers, call the synchronous b200seed_run_batch: the copies of one call
-    # overlap the kernels of the other.
-    import threading
+    # ---- end to end through the host C ABI, the reference's call pattern -----------------------------
+    # The reference's execute() is entered by several Sequencer worker threads, ONE EVENT PER CALL
+    # (Sequencer.cpp:472-525).  T worker threads, each with its own handle and pinned buffers, call the
+    # synchronous b200seed_run: the copies of one call overlap the kernels of the others.  T is swept upwards
+    # until the rate stops growing.
+    ev_pinned = []
+    keep_alive = []
+    for ev in evs:
+        d = {}
+        for k in ("x", "y", "z", "r", "varZ", "varR"):
+            t, a = pinned(ev[k])
+            keep_alive.append(t)
+            d[k] = a
+        ev_pinned.append(d)
+    cap_ev = max(ev["x"].size for ev in evs) * K
+    h2d_ev = int(np.mean([ev["x"].size for ev in evs])) * 24
 
-    n_thr = max(1, args.e2e_threads)
-    engines = [eng] + [plugin.SeedingEngine(cfg, device=local) for _ in range(n_thr - 1)]
-    cap_max = max(b["cap"] for b in batches)
-    pinned_out = []
-    for _ in range(n_thr):
-        pinned_out.append({
-            "bottom": torch.empty(cap_max, dtype=torch.int32).pin_memory().numpy().view(np.uint32),
-            "middle": torch.empty(cap_max, dtype=torch.int32).pin_memory().numpy().view(np.uint32),
-            "top": torch.empty(cap_max, dtype=torch.int32).pin_memory().numpy().view(np.uint32),
-            "quality": torch.empty(cap_max, dtype=torch.float32).pin_memory().numpy(),
-            "vertexZ": torch.empty(cap_max, dtype=torch.float32).pin_memory().numpy()})
-    host_cols = [{k: v.numpy() for k, v in b["h_cols"].items()} for b in batches]
-    d2h_seen = [0] * n_thr
+    def e2e_per_event(n_thr, n_calls):
+        engines = [plugin.SeedingEngine(cfg, device=local) for _ in range(n_thr)]
+        outs = [pinned_seed_columns(cap_ev) for _ in range(n_thr)]
+        seeds_seen = [0] * n_thr
+        nxt = [0]
+        lock = threading.Lock()
 
-    def step_host(t, i):
-        b = batches[i % n_batches]
-        res = engines[t].run_batch(host_cols[i % n_batches], b["off"], out=pinned_out[t])
-        d2h_seen[t] = sum(r["quality"].size for r in res) * 20 + (E + 1) * 8
+        def worker(t, limit):
+            torch.cuda.set_device(local)
+            while True:
+                with lock:  # dynamic event queue, like tbb::parallel_for over the events
+                    i = nxt[0]
+                    nxt[0] += 1
+                if i >= limit:
+                    return
+                res = engines[t].run(ev_pinned[i % len(ev_pinned)], out=outs[t][1])
+                seeds_seen[t] += res["quality"].size
 
-    def worker(t, first, count):
-        torch.cuda.set_device(local)
-        for i in range(first + t, first + count, n_thr):
-            step_host(t, i)
+        def run(limit):
+            nxt[0] = 0
+            ths = [threading.Thread(target=worker, args=(t, limit)) for t in range(n_thr)]
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
 
-    def run_threads(first, count):
-        ths = [threading.Thread(target=worker, args=(t, first, count)) for t in range(n_thr)]
-        for th in ths:
+        run(2 * n_thr)  # warm-up: every handle allocates its workspaces
+        for k in range(n_thr):
+            seeds_seen[k] = 0
+        barrier()
+        t0 = time.perf_counter()
+        run(n_calls)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        d2h = 20.0 * sum(seeds_seen) / n_calls
+        for e in engines:
+            e.close()
+        return world * n_calls / dt, d2h
+
+    sweep = {}
+    best_t, best_rate, d2h_ev = 1, 0.0, 0.0
+    n_calls = max(16, min(64, 4 * args.steps))
+    for n_thr in [int(t) for t in args.e2e_threads.split(",")]:
+        rate, d2h = e2e_per_event(n_thr, n_calls)
+        sweep[str(n_thr)] = rate
+        if rate > best_rate:
+            best_t, best_rate, d2h_ev = n_thr, rate, d2h
+        elif rate < 1.02 * best_rate:
+            break  # saturated
+
+    # ---- parity of the timed events against the reference itself ------------------------------------------
+    parity = None
+    if args.parity_events > 0:
+        ref_eng, ref_kind = reference_engine()
+        n_check = args.parity_events if world == 1 else min(args.parity_events, 2)
+        picks = [(rank * 7 + 5 * j) % n_distinct for j in range(n_check)]  # events of the timed batches
+        got_all = {i: eng.run(evs[i]) for i in picks}
+        ths = []
+        wants = {}
+
+        def ref_worker(i):
+            wants[i] = ref_eng.run(evs[i])
+
+        for i in picks:
+            th = threading.Thread(target=ref_worker, args=(i,))
             th.start()
+            ths.append(th)
         for th in ths:
             th.join()
+        bad = sum(0 if same_bits(got_all[i], wants[i]) else 1 for i in picks)
+        t = torch.tensor([float(bad), float(len(picks))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        parity = {"events_checked": int(t[1].item()), "mismatches": int(t[0].item()),
+                  "against": "unmodified reference sources (oracle/_ref)" if ref_kind == "reference" else "oracle port",
+                  "compared": "seed triplets, order, quality bits, vertexZ bits"}
 
-    run_threads(0, 2 * n_thr)  # warm-up: every handle allocates its workspaces
-    e2e_steps = max(n_thr, min(args.steps, 10))
-    barrier()
-    t0 = time.perf_counter()
-    run_threads(2 * n_thr, e2e_steps)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    d2h = max(d2h_seen)
-    for extra in engines[1:]:
-        extra.close()
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * E * e2e_steps / float(t.item())
-    h2d = batches[0]["n_total"] * 24 + (E + 1) * 4
+    # ---- config 5: one <mu>=300 event, unsplit and split into phi sectors over the ranks of this run -------
+    latency = None
+    if args.latency:
+        ev300 = events.pileup_event(900, mu=300.0)
+        p300 = {}
+        for k in ("x", "y", "z", "r", "varZ", "varR"):
+            t, a = pinned(ev300[k])
+            keep_alive.append(t)
+            p300[k] = a
+        keep_o, out300 = pinned_seed_columns(ev300["x"].size * K)
+        n_phi = eng.info().phiBins
+
+        def timed_run(reps=5):
+            eng.run(p300, out=out300)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                res = eng.run(p300, out=out300)
+            dt = (time.perf_counter() - t0) / reps
+            return dt, res
+
+        unsplit_s, full = timed_run()
+        full = {k: full[k].copy() for k in KEYS}
+        latency = {"mu": 300, "space_points": int(ev300["x"].size), "seeds": int(full["quality"].size),
+                   "unsplit_ms_one_gpu": unsplit_s * 1e3}
+        if world > 1 and world <= n_phi:
+            first, count = sharding.phi_sector_of_rank(n_phi, rank, world)
+            eng.set_phi_sector(first, count)
+            split_s, part = timed_run()
+            eng.set_phi_sector(1, 0)
+            split_ms = max_over_ranks(split_s) * 1e3
+            # the one exchange step: gather the per-sector seed lists (padded) and concatenate in sector order
+            n_mine = part["quality"].size
+            counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+            dist.all_gather(counts, torch.tensor([n_mine], dtype=torch.int64, device=dev))
+            n_max = int(max(int(c.item()) for c in counts))
+            gathered = {}
+            for k in KEYS:
+                mine = torch.zeros(n_max, dtype=torch.int32, device=dev)
+                mine[:n_mine] = torch.from_numpy(part[k].view(np.int32).copy()).to(dev)
+                parts = [torch.zeros(n_max, dtype=torch.int32, device=dev) for _ in range(world)]
+                dist.all_gather(parts, mine)
+                gathered[k] = np.concatenate([p_[:int(c.item())].cpu().numpy().view(np.uint32) for p_, c in zip(parts, counts)])
+            identical = all(np.array_equal(gathered[k], full[k].view(np.uint32)) for k in KEYS)
+            latency.update({"split_ms": split_ms, "sectors": world, "split_equals_unsplit": bool(identical)})
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return 0
+        return 0 if (parity is None or parity["mismatches"] == 0) else 3
 
     # ---- optional float fast path (relaxedFloat), reported separately -------
     relaxed = None
@@ -328,30 +467,22 @@ def run_gpu(args):
         rcfg = config.pu200_config(plugin.config_init)
         rcfg.relaxedFloat = 1
         reng = plugin.SeedingEngine(rcfg, device=local)
-
-        def step_relaxed(i):
-            b = batches[i % n_batches]
-            reng.run_batch_device(E, b["n_total"], b["d_off"].data_ptr(), [t.data_ptr() for t in b["d_cols"]],
-                                  b["d_soff"].data_ptr(), [t.data_ptr() for t in b["d_out"]], b["cap"],
-                                  stream=C.c_void_p(stream.cuda_stream))
-
         for i in range(args.warmup):
-            step_relaxed(i)
+            step_device(reng, i)
         reng.sync()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         r0.record(stream)
         for i in range(args.steps):
-            step_relaxed(args.warmup + i)
+            step_device(reng, args.warmup + i)
         r1.record(stream)
         torch.cuda.synchronize()
         reng.sync()
         r_ms = r0.elapsed_time(r1)
         # seed-efficiency delta on one batch: exact engine = the reference's seeds, bit for bit
         b = batches[0]
-        host = {k: v.numpy() for k, v in b["h_cols"].items()}
-        ex = eng.run_batch(host, b["off"], capacity=b["cap"])
-        rx = reng.run_batch(host, b["off"], capacity=b["cap"])
+        ex = eng.run_batch(b["cols"], b["off"], capacity=b["cap"])
+        rx = reng.run_batch(b["cols"], b["off"], capacity=b["cap"])
         n_ref = n_rx = n_common = n_same_q = 0
         for a_, b_ in zip(ex, rx):
             sa = {(int(x), int(y), int(z)): float(q) for x, y, z, q in zip(a_["bottom"], a_["middle"], a_["top"], a_["quality"])}
@@ -368,54 +499,54 @@ def run_gpu(args):
                            "no tie replay); efficiency = exact seeds also found / exact seeds on one batch"}
         reng.close()
 
-    # ---- roofline of the dominant kernel ------------------------------------
+    # ---- roofline ------------------------------------------------------------------------------------------
     peak_gbs, peak_src, sm_max = load_peaks()
     b0 = batches[(args.warmup + min(args.steps, 8) - 1) % n_batches]
-    seed_ms_avg = float(np.mean(seed_ms))
-    n_in = cnt["nInGrid"]
-    # algorithmic HBM bytes of the FUSED seeding kernel: every
-    # packed space point (24 B) is needed by its own and the 2*numPhiNeighbors
-    # neighbouring phi bins, plus 8 B per work item and 20 B per seed slot written
-    alg_bytes = (2 * cfg.numPhiNeighbors + 1) * 24 * n_in + 8 * cnt["nMiddles"] + 20 * cnt["nSeeds"]
-    achieved = alg_bytes / (seed_ms_avg * 1e-3) / 1e9
-    # DRAM traffic of the dominant kernel from the committed ncu capture (same batch shape)
+    n_in = cnt_stage["nInGrid"]
+    n_dbl = cnt_stage["nBottomDoublets"] + cnt_stage["nTopDoublets"]
+    # k_seed_middles (dominant: all its launches of one step): every doublet of the arena is read once as a
+    # 32-byte record + a 4-byte key, every middle's 32-byte header, 20 bytes per seed slot written
+    alg_bytes = 36 * n_dbl + 32 * cnt_stage["nMiddles"] + 20 * cnt_stage["nSeeds"]
+    achieved = alg_bytes / (stage["seed_middles"] * 1e-3) / 1e9
+    # doublet fill pass (HBM-bound stage): 36 bytes written per doublet + 24 bytes of every packed space point read
+    # by its own and the 2 * numPhiNeighbors neighbouring phi bins + the header
+    fill_bytes = 36 * n_dbl + (2 * cfg.numPhiNeighbors + 1) * 24 * n_in + 32 * cnt_stage["nMiddles"]
+    fill_gbs = fill_bytes / (stage["doublet_fill"] * 1e-3) / 1e9
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
-        if tj.get("events_per_launch") == E:
-            traffic = int(tj["dram_bytes_read"] + tj["dram_bytes_write"])
+        if tj.get("events_per_step") == E:
+            traffic = int(tj["k_seed_middles"]["dram_bytes_read"] + tj["k_seed_middles"]["dram_bytes_write"])
     # FP32 view: operations the reference algorithm itself needs (oracle counts)
-    alg_flop = None
     fp32 = None
     if args.oracle_counters:
         from oracle import oracle as O
 
         orc = O.Oracle(config.pu200_config(O.config_init))
-        pair = dbl = trip = 0
         e_first = ((args.warmup + min(args.steps, 8) - 1) % n_batches) * E
-        for ev in evs[e_first:e_first + 1]:
-            c = orc.run(ev)["counters"]
-            pair, dbl, trip = c["nPairTests"], c["nBottomDoublets"] + c["nTopDoublets"], c["nTripletTests"]
-        alg_flop = E * (pair * FLOP_PAIR_TEST + dbl * FLOP_DOUBLET + trip * FLOP_TRIPLET_TEST)
-    clk = clocks.summary()
-    if alg_flop is not None:
-        sm_mhz = clk["sm_mhz"] or sm_max
+        c = orc.run(evs[e_first])["counters"]
+        alg_flop = E * (c["nPairTests"] * FLOP_PAIR_TEST + (c["nBottomDoublets"] + c["nTopDoublets"]) * FLOP_DOUBLET +
+                        c["nTripletTests"] * FLOP_TRIPLET_TEST)
+        clk0 = clocks.summary()
+        sm_mhz = clk0["sm_mhz"] or sm_max
         peak_fp32 = 148 * 128 * sm_mhz * 1e6 / 1e12  # FADD/FMUL per second without FMA, TFLOP/s
-        ach = alg_flop / (seed_ms_avg * 1e-3) / 1e12
+        ach = alg_flop / (stage["seed"] * 1e-3) / 1e12
         fp32 = {"bound": "fp32-issue (no FMA allowed on the exact path)", "achieved": ach, "peak": peak_fp32,
                 "unit": "TFLOP/s", "frac": ach / peak_fp32,
-                "note": "algorithmic flop = oracle pair tests x9 + doublets x24 + triplet tests x28, first event of the batch x16"}
+                "note": "algorithmic flop = oracle pair tests x9 + doublets x24 + triplet tests x28 of the first event of "
+                        "the batch x events per step, over the whole seeding stage (doublets + triplets)"}
+    clk = clocks.summary()
 
     cores = host_cores()
     cpu = None
     if not args.no_cpu_baseline:
-        nav_stride = 8
-        rate, step_s = cpu_reference_rate(cores, 1, 0, nav_stride, evs=evs[:min(cores, 8)])
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{cores} events in parallel (one per thread), each seeded on every {nav_stride}th middle "
-                         f"phi-bin (1/{nav_stride} of the seeding work, full grid build); {step_s:.1f} s of wall time"}
+        rate, step_s, kind = cpu_reference_rate(cores, 1, 0, evs[:min(cores, 16)])
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{cores} whole events, one per execute() call from {cores} worker threads sharing one algorithm "
+                         f"object (the Sequencer's pattern), " + ("unmodified reference sources (oracle/_ref)" if kind == "reference" else "oracle port") +
+                         f"; {step_s:.1f} s of wall time"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -423,25 +554,32 @@ def run_gpu(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "events_per_step_per_gpu": E, "space_points_per_step_per_gpu": b0["n_total"],
                    "l2_policy": f"inputs larger than L2: {n_batches} distinct resident batches "
-                                f"({n_batches * b0['n_total'] * 24 / 1e6:.0f} MB of columns) rotated",
-                   "parallelism": f"event sharding over {world} GPU(s), no data-path collective"},
+                                f"({n_batches * b0['n_total'] * 24 / 1e6:.0f} MB of columns) rotated; the doublet arena "
+                                f"(~{36 * n_dbl / 1e9:.0f} GB per step) streams through HBM",
+                   "parallelism": f"event sharding over {world} GPU(s), same event pool on every rank, no data-path collective"},
         "clocks": clk,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "host_threads_per_gpu": n_thr, "steps": e2e_steps,
-                "note": "synchronous b200seed_run_batch calls (pinned host buffers in, pinned seeds out) from "
-                        "host_threads_per_gpu worker threads, one handle each, like the Sequencer's workers"},
+        "e2e": {"value": best_rate, "unit": UNIT, "h2d_bytes_per_step": int(h2d_ev), "d2h_bytes_per_step": int(d2h_ev),
+                "host_threads_per_gpu": best_t, "calls": n_calls, "threads_sweep": sweep,
+                "note": "one event per synchronous b200seed_run call (pinned host buffers in, pinned seeds out) from "
+                        "host_threads_per_gpu Sequencer-like worker threads, one handle each, dynamic event queue; "
+                        "a step of this leg is one event"},
         "gpu_launches": int(launches_per_step * args.steps),
+        "parity": parity,
         "roofline": {"bound": "hbm", "kernel": "k_seed_middles", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": seed_ms_avg,
-                     "grid_stage_ms": float(np.mean(grid_ms)),
-                     "grid_stage_gbs": 52.0 * n_in / (float(np.mean(grid_ms)) * 1e-3) / 1e9,
-                     "note": "fused per-middle kernel (all capacity tiers): doublets never leave shared memory, so the "
-                             "HBM fraction is small by design and the DRAM traffic (ncu, profiles/r1_traffic.json) is "
-                             "below the algorithmic bytes because the packed space points stay in L2; the binding "
-                             "limit is FP32 instruction issue and block-barrier latency (see `compute`, DESIGN.md)"},
+                     "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": stage["seed_middles"],
+                     "launch": "all k_seed_middles launches of one step (one per shared-memory class and arena chunk)",
+                     "doublet_stage": {"kernel": "k_doublets<fill>", "ms": stage["doublet_fill"], "achieved": fill_gbs,
+                                       "frac": fill_gbs / peak_gbs, "algorithmic_bytes": int(fill_bytes),
+                                       "count_pass_ms": stage["doublet_count"]},
+                     "grid_stage_ms": stage["grid"],
+                     "grid_stage_gbs": 52.0 * n_in / (stage["grid"] * 1e-3) / 1e9,
+                     "note": "k_seed_middles reads every doublet of the HBM arena once, but it is bound by FP32 "
+                             "instruction issue / latency, not by HBM (see `compute`, DESIGN.md section 6); the "
+                             "HBM-bound stage is the doublet fill pass (`doublet_stage`)"},
         "compute": fp32,
         "relaxed_float": relaxed,
+        "latency": latency,
         "cpu_baseline": cpu,
         "counters_last_step": cnt,
         "seeds_last_step": int(n_seeds_last),
@@ -452,6 +590,9 @@ def run_gpu(args):
     sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and parity["mismatches"] != 0:
+        sys.stderr.write("bench.py: PARITY FAILURE against the reference on the timed events\n")
+        return 3
     return 0
 
 
@@ -464,7 +605,9 @@ def main():
     ap.add_argument("--events-per-step", type=int, default=EVENTS_PER_STEP)
     ap.add_argument("--distinct-events", type=int, default=N_DISTINCT_EVENTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-threads", type=int, default=2, help="host worker threads (handles) per GPU of the e2e leg")
+    ap.add_argument("--e2e-threads", default="1,2,3,4,6", help="host worker threads (handles) per GPU swept by the e2e leg")
+    ap.add_argument("--parity-events", type=int, default=4, help="timed events re-seeded by the reference and compared (0: skip)")
+    ap.add_argument("--no-latency", dest="latency", action="store_false", help="skip the <mu>=300 latency block")
     ap.add_argument("--no-relaxed", dest="relaxed", action="store_false", help="skip the relaxedFloat fast-path report")
     ap.add_argument("--no-oracle-counters", dest="oracle_counters", action="store_false")
     args = ap.parse_args()

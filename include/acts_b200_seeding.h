@@ -325,6 +325,9 @@ int b200seed_sync(b200seed_handle* h, b200seed_seeds* out);
  * Valid because seedConfirmation = false has no cross-middle state; refused
  * with B200SEED_ERR_UNSUPPORTED on a seedConfirmation handle. */
 int b200seed_set_phi_sector(b200seed_handle* h, uint32_t firstPhiBin, uint32_t nPhiBins);
+/* firstPhiBin = B200SEED_PHI_SECTOR_EMPTY with nPhiBins = 0: the EMPTY sector (a rank that got no bins because
+ * there are more ranks than phi bins seeds nothing, instead of falling back to "all"). */
+#define B200SEED_PHI_SECTOR_EMPTY 0xFFFFFFFFu
 
 /* GPU time of the stages of the last completed call, milliseconds (CUDA events
  * on the launching stream): ms[0] grid build, ms[1] middle work list,

@@ -114,6 +114,125 @@ def test_batch_equals_single_events(plugin, O):
     eng.close()
 
 
+def _oracle_many(O, cfg_name, evs, overrides=None, **kw):
+    """The oracle on several full-size events at once (one thread and one oracle object per event; the
+    ctypes call releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(ev):
+        cfg = make_config(cfg_name, O.config_init)
+        if overrides:
+            cfg.update(**overrides)
+        return O.Oracle(cfg).run(ev, **kw)
+
+    with ThreadPoolExecutor(max_workers=min(len(evs), os.cpu_count() or 1)) as pool:
+        return list(pool.map(one, evs))
+
+
+def test_eight_full_size_events_mu200(plugin, O):
+    """BASELINE.json configs[2] / [3]: eight <mu>=200 events (~1e5 space points each), one call per event and one
+    batch call, exact seed sets in the reference's order; the same events with seedConfirmation = true."""
+    from acts_b200 import config as cm
+    from acts_b200 import events
+
+    evs = [events.pileup_event(10 + i, mu=200) for i in range(8)]
+    refs = _oracle_many(O, "pu200", evs)
+    eng = plugin.SeedingEngine(make_config("pu200", plugin.config_init))
+    for ev, ref in zip(evs, refs):
+        got = eng.run(ev)
+        assert ref["quality"].size > 50_000
+        assert _same_bits(got, ref)
+        cnt = eng.counters()
+        for k in ("nMiddles", "nBottomDoublets", "nTopDoublets", "nCandidates"):
+            assert cnt[k] == ref["counters"][k], k
+    cols, offsets = events.concat_events(evs)
+    for got, ref in zip(eng.run_batch(cols, offsets), refs):
+        assert _same_bits(got, ref)
+    eng.close()
+    conf = cm.confirmation_overrides()
+    refs = _oracle_many(O, "pu200", evs, overrides=conf)
+    eng = plugin.SeedingEngine(make_config("pu200", plugin.config_init).update(**conf))
+    for got, ref in zip(eng.run_batch(cols, offsets), refs):
+        assert ref["quality"].size > 10_000
+        assert _same_bits(got, ref)
+    eng.close()
+
+
+def test_mu300_event_unsplit_and_eight_sector_split(plugin, O):
+    """BASELINE.json configs[4]: one <mu>=300 event (~1.5e5 space points) through the exact engine, unsplit and
+    split into 8 phi sectors (run one after the other, as 8 GPUs would in parallel): both bit-identical to the oracle."""
+    from acts_b200 import events, sharding
+
+    ev = events.pileup_event(900, mu=300)
+    assert ev["x"].size > 130_000
+    ref = _oracle_many(O, "pu200", [ev])[0]
+    eng = plugin.SeedingEngine(make_config("pu200", plugin.config_init))
+    assert _same_bits(eng.run(ev), ref)
+    n_phi = eng.info().phiBins
+    parts = []
+    for rank in range(8):
+        first, count = sharding.phi_sector_of_rank(n_phi, rank, 8)
+        eng.set_phi_sector(first, count)
+        parts.append(eng.run(ev))
+    eng.set_phi_sector(1, 0)
+    got = {k: np.concatenate([p[k] for p in parts]) for k in KEYS}
+    assert _same_bits(got, ref)
+    eng.close()
+
+
+def test_vertex_z_cuts_match_oracle(plugin, O):
+    """Config::inputVertices at the boundary: b200seed_run_vertices builds the windows like .cpp:187-206; the cut is
+    connected for every event of such a handle (no vertex: every doublet passes and the ITk doublet cut stays off,
+    .cpp:292-297); 200 vertices and per-event windows of a batch are fine (merged intervals, binary search)."""
+    from acts_b200 import events
+
+    rng = np.random.default_rng(11)
+    for extra, ns, mg in ((0, 3.0, 0.0), (1, 2.0, 1.5)):
+        over = dict(useVertexZCuts=1, vertexZNSigma=ns, vertexZMargin=mg, useExtraCuts=extra)
+        eng = plugin.SeedingEngine(make_config("pu200", plugin.config_init).update(**over))
+        orc = O.Oracle(make_config("pu200", O.config_init).update(**over))
+        evs, wins = [], []
+        for i, nv in ((0, 1), (1, 7), (2, 200), (3, 0)):
+            ev = events.pileup_event(40 + i, mu=30)
+            vz, vv = rng.normal(0.0, 55.5, nv), rng.uniform(0.05, 2.0, nv) ** 2
+            got = eng.run(ev, vertices=(vz, vv))
+            ref = orc.run(ev, vertices=(vz, vv))
+            assert _same_bits(got, ref), (extra, nv)
+            lo, hi = eng.vertex_windows(vz, vv)
+            assert [(float(a), float(b)) for a, b in zip(lo, hi)] == orc.vertex_windows(vz, vv)
+            evs.append(ev)
+            wins.append(list(zip(lo.tolist(), hi.tolist())))
+        cols, offsets = events.concat_events(evs)
+        for ev, w, got in zip(evs, wins, eng.run_batch(cols, offsets, z_windows=wins)):
+            assert _same_bits(got, orc.run(ev, z_windows=w) if w else orc.run(ev)), extra
+        eng.close()
+
+
+def test_nothing_is_refused_for_its_size(plugin, O):
+    """The reference's per-middle containers are unbounded (DoubletSeedFinder.hpp:26-262).  Every phi bin a
+    neighbour at <mu>=60 gives middles with ~1e4 doublets per side: far beyond shared memory, taken by the spill
+    class (lists in global memory); a tiny arena forces many chunks.  Same seeds, bit for bit."""
+    from acts_b200 import events
+
+    ev = events.pileup_event(3, mu=60)
+    over = dict(numPhiNeighbors=40)
+    ref = O.Oracle(make_config("pu200", O.config_init).update(**over)).run(ev)
+    assert ref["counters"]["maxBottoms"] > 5000
+    eng = plugin.SeedingEngine(make_config("pu200", plugin.config_init).update(**over))
+    assert _same_bits(eng.run(ev), ref)
+    eng.close()
+    os.environ["B200SEED_ARENA_MB"] = "64"
+    try:
+        eng = plugin.SeedingEngine(make_config("pu200", plugin.config_init))
+        ev2 = events.pileup_event(1, mu=200)
+        got = eng.run(ev2)
+        assert eng.counters()["nKernelLaunches"] > 100  # dozens of arena chunks
+        assert _same_bits(got, _oracle_many(O, "pu200", [ev2])[0])
+        eng.close()
+    finally:
+        del os.environ["B200SEED_ARENA_MB"]
+
+
 def test_full_size_event_mu200(plugin, O):
     """BASELINE.json configs[2]: <mu>=200, ~1e5 space points, exact seed set and order."""
     from acts_b200 import events
@@ -437,16 +556,14 @@ def test_phi_sector_split_concatenates_to_the_full_result(plugin, O):
     ev = events.pileup_event(3, mu=60)
     ref = O.Oracle(make_config("pu200", O.config_init)).run(ev)
     n_phi = eng.info().phiBins
-    for world in (2, 8, 53):
+    for world in (2, 8, 53, 64):  # 64 > 53 phi bins: the surplus ranks hold the empty sector and contribute nothing
         parts = []
         covered = 0
         for rank in range(world):
-            first, count = sharding.phi_sector_of_rank(n_phi, rank, world)
+            first, count = sharding.apply_phi_sector(eng, n_phi, rank, world)
             covered += count
-            if count == 0:
-                continue
-            eng.set_phi_sector(first, count)
             parts.append(eng.run(ev))
+            assert count > 0 or parts[-1]["quality"].size == 0
         assert covered == n_phi
         got = {k: np.concatenate([p[k] for p in parts]) for k in KEYS}
         assert _same_bits(got, ref), world
@@ -472,6 +589,25 @@ def test_estimated_track_parameters_match_reference_arithmetic(plugin, O):
     # direction components close to zero are compared on the unit-vector scale
     rel[:, 4:7] = np.abs(got[:, 4:7] - ref[:, 4:7])
     assert np.nanmax(rel) < 1e-9, np.nanmax(rel)
+    eng.close()
+
+
+def test_estimate_params_reference_known_answer(plugin, O):
+    """Tests/UnitTests/Core/Seeding/EstimateTrackParamsFromSeedTest.cpp:187-195 (trackparm_estimate_aligined):
+    three aligned space points give q/p == 0 exactly, on the device and in the oracle."""
+    ev = {"x": np.array([-72.775, -84.325, -98.175], np.float32), "y": np.array([-0.325, -0.325, -0.325], np.float32),
+          "z": np.array([-615.6, -715.6, -835.6], np.float32)}
+    seeds = {"bottom": np.array([0], np.uint32), "middle": np.array([1], np.uint32), "top": np.array([2], np.uint32)}
+    b = (0.0, 0.0, 0.000899377)
+    eng = plugin.SeedingEngine(make_config("pu200", plugin.config_init))
+    got = eng.estimate_params(seeds, ev, b_field=b)
+    ref = O.estimate_params(seeds, ev, b_field=b)
+    assert got[0, 7] == 0.0 and ref[0, 7] == 0.0
+    assert not np.isnan(got).any()
+    # an index outside the space point columns is refused, not read (ADVICE: unchecked device reads)
+    bad = dict(seeds, top=np.array([7], np.uint32))
+    with pytest.raises(plugin.SeedingError):
+        eng.estimate_params(bad, ev, b_field=b)
     eng.close()
 
 

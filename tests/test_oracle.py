@@ -237,3 +237,14 @@ def test_pixel_space_point_maker_against_independent_float64(O):
     sp = O.make_pixel_spacepoints(one, tr)
     assert sp["varZ"][0] == 9.0 and abs(sp["varR"][0] - 4.0 * np.sin(0.14) ** 2) < 1e-6
     assert abs(sp["r"][0] - 32.0) < 1e-5 and sp["z"][0] == -468.0
+
+
+def test_estimate_params_reference_known_answer(O):
+    """Tests/UnitTests/Core/Seeding/EstimateTrackParamsFromSeedTest.cpp:187-195 (trackparm_estimate_aligined):
+    three aligned space points give q/p == 0 exactly."""
+    ev = {"x": np.array([-72.775, -84.325, -98.175], np.float32), "y": np.array([-0.325, -0.325, -0.325], np.float32),
+          "z": np.array([-615.6, -715.6, -835.6], np.float32)}
+    seeds = {"bottom": np.array([0], np.uint32), "middle": np.array([1], np.uint32), "top": np.array([2], np.uint32)}
+    out = O.estimate_params(seeds, ev, b_field=(0.0, 0.0, 0.000899377))
+    assert out[0, 7] == 0.0
+    assert not np.isnan(out).any()
