@@ -97,7 +97,12 @@ struct b200seed_handle {
   DevBuf binOf, binCount, binStart, binCursor, tmpIdx, pIdx, pXY, pZR, pVar, sortScratch;
   DevBuf midLo, midCount, workStart, workPos, workEG, workCounter;
   // doublet stage: slot sizes and prefix, chunk plan, arena, per-middle headers, per-class work lists
-  DevBuf capB, capT, slotPrefix, capTileSums, capTilePrefix, planDev, hdr, classList, arenaRec, arenaKey, spillScratch;
+  DevBuf capB, capT, slotPrefix, capTileSums, capTilePrefix, planDev, hdr, classList, arenaRec[2], arenaKey[2], spillScratch;
+  // Consecutive chunks alternate between two internal streams (and two arena halves): the tail of one chunk's
+  // seeding kernels overlaps the fill pass of the next.  B200SEED_CHUNK_STREAMS=1 serialises them (stage timing).
+  int chunkStreams = 2;
+  cudaStream_t chunkStream[2] = {nullptr, nullptr};
+  cudaEvent_t evPlan = nullptr, evChunkEnd[2] = {nullptr, nullptr};
   uint32_t* hPlan = nullptr;  // pinned: planWords[8] + chunkBounds[kMaxChunks + 1]
   std::vector<uint32_t> lastChunkBounds;  // of the last call (debug_doublets)
   DevBuf slotB, slotM, slotT, slotQ, slotZ, slotCount, seedStart, tileSums, tilePrefix;
@@ -182,7 +187,7 @@ int ensure_workspace(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal) {
   CUDA_TRY(h->capT.reserve(nT * 4));
   CUDA_TRY(h->slotPrefix.reserve((nT + 1) * 8));
   CUDA_TRY(h->hdr.reserve(nT * sizeof(MiddleHeader)));
-  CUDA_TRY(h->classList.reserve(nT * 4 * kNumSeedClasses));
+  CUDA_TRY(h->classList.reserve(nT * 4 * kNumSeedClasses * 2));
   CUDA_TRY(h->planDev.reserve(((size_t)kMaxChunks + 1 + 8) * 4));
   CUDA_TRY(h->slotB.reserve(nT * K * 4));
   CUDA_TRY(h->slotM.reserve(nT * K * 4));
@@ -409,7 +414,9 @@ int enqueue(b200seed_handle* h) {
 
   // ---- slot prefix, chunk plan; the host reads the plan (the one synchronisation inside a call) ---
   const uint32_t nTiles = std::max<uint32_t>(1, (nTotal + kTile - 1) / kTile);
-  const unsigned long long arenaRecordsMax = std::max<unsigned long long>(h->arenaMaxBytes / 36ull, 4ull * kMaxListLength);
+  const int nStreams = h->chunkStreams;
+  const unsigned long long arenaRecordsMax =
+      std::max<unsigned long long>(h->arenaMaxBytes / 36ull / (unsigned long long)nStreams, 4ull * kMaxListLength);
   SlotScanParams ssp{};
   ssp.nWorkPtr = dp.nWorkPtr;
   ssp.capB = dp.capB; ssp.capT = dp.capT;
@@ -450,24 +457,24 @@ int enqueue(b200seed_handle* h) {
     CUDA_TRY(cudaStreamSynchronize(s));
     for (uint32_t c = 0; c < nChunks; ++c) chunkRecordsMax = std::max(chunkRecordsMax, edge[c + 1] - edge[c]);
   }
-  CUDA_TRY(h->arenaRec.reserve(std::max<size_t>(64, (size_t)chunkRecordsMax * sizeof(DoubletRecord))));
-  CUDA_TRY(h->arenaKey.reserve(std::max<size_t>(64, (size_t)chunkRecordsMax * 4)));
+  for (int a = 0; a < (nChunks > 1 ? nStreams : 1); ++a) {
+    CUDA_TRY(h->arenaRec[a].reserve(std::max<size_t>(64, (size_t)chunkRecordsMax * sizeof(DoubletRecord))));
+    CUDA_TRY(h->arenaKey[a].reserve(std::max<size_t>(64, (size_t)chunkRecordsMax * 4)));
+  }
   // spill class: per-block scratch for the largest lists of the batch + a candidate pool
   const uint32_t maxCapB = h->hPlan[1], maxCapT = h->hPlan[2];
   const SeedCarve spillCarve = seed_carve(std::max<uint32_t>(maxCapB, 1), std::max<uint32_t>(maxCapT, 1));
   const uint32_t spillPool = std::max<uint32_t>(4u * seed_pool_min(maxCapB), 1u << 18);
   const uint32_t spillBytes = carve_align(spillCarve.oPool + kPoolEntryBytes * spillPool + 64);
   const bool spillLikely = h->hPlan[0] > h->classBytes[kSpillClass - 1];
-  const int spillBlocks = spillLikely ? h->smCount * 2 : 16;
-  CUDA_TRY(h->spillScratch.reserve((size_t)spillBytes * (size_t)spillBlocks));
+  const int spillBlocks = spillLikely ? h->smCount : 16;
+  CUDA_TRY(h->spillScratch.reserve((size_t)spillBytes * (size_t)spillBlocks * (size_t)nStreams));
 
   SeedParams sp{};
   sp.cfg = dp.cfg;
   sp.pXY = gp.pXY; sp.pZR = gp.pZR; sp.pVar = gp.pVar;
   sp.workPos = wp.workPos;
   sp.hdr = dp.hdr;
-  sp.rec = h->arenaRec.as<DoubletRecord>();
-  sp.key = h->arenaKey.as<float>();
   sp.spillScratch = h->spillScratch.as<unsigned char>();
   sp.slotB = h->slotB.as<uint32_t>(); sp.slotM = h->slotM.as<uint32_t>(); sp.slotT = h->slotT.as<uint32_t>();
   sp.slotQ = h->slotQ.as<float>(); sp.slotZ = h->slotZ.as<float>();
@@ -486,8 +493,6 @@ int enqueue(b200seed_handle* h) {
     CUDA_TRY(cudaMemsetAsync(h->recCount.ptr, 0, (size_t)nWorkMax * 4, s));
     CUDA_TRY(cudaMemsetAsync(h->confState.ptr, 0, kConfStateWords * 4, s));
   }
-  dp.rec = h->arenaRec.as<DoubletRecord>();
-  dp.key = h->arenaKey.as<float>();
   // ---- per chunk: doublet fill, then the seeding kernel of every shared-memory class --------
   while (h->evChunk.size() < 2 * (size_t)nChunks) {
     cudaEvent_t e = nullptr;
@@ -495,32 +500,54 @@ int enqueue(b200seed_handle* h) {
     h->evChunk.push_back(e);
   }
   h->chunksTimed = nChunks;
+  const bool overlap = nStreams > 1 && nChunks > 1;
+  if (overlap) {
+    CUDA_TRY(cudaEventRecord(h->evPlan, s));
+    for (int a = 0; a < nStreams; ++a) CUDA_TRY(cudaStreamWaitEvent(h->chunkStream[a], h->evPlan, 0));
+  }
   for (uint32_t c = 0; c < nChunks; ++c) {
+    const int a = overlap ? (int)(c % (uint32_t)nStreams) : 0;
+    cudaStream_t cs = overlap ? h->chunkStream[a] : s;
     uint32_t* cw = wc + 16 * (c + 1);  // [0] fill ticket, [1 + k] ticket of class k, [8 + k] list length of class k
-    dp.itemFirst = bounds[c];
-    dp.itemEnd = bounds[c + 1];
-    dp.workCounter = cw;
-    dp.classCount = cw + 8;
-    k_doublets<true><<<h->smCount * h->doubletBlocksPerSM[1], kDoubletWarps * 32, 0, s>>>(dp);
-    CUDA_TRY(cudaEventRecord(h->evChunk[2 * c], s));
+    uint32_t* lists = dp.classList + (size_t)a * kNumSeedClasses * dp.classStride;
+    DoubletParams dpc = dp;
+    dpc.itemFirst = bounds[c];
+    dpc.itemEnd = bounds[c + 1];
+    dpc.workCounter = cw;
+    dpc.classCount = cw + 8;
+    dpc.classList = lists;
+    dpc.rec = h->arenaRec[a].as<DoubletRecord>();
+    dpc.key = h->arenaKey[a].as<float>();
+    k_doublets<true><<<h->smCount * h->doubletBlocksPerSM[1], kDoubletWarps * 32, 0, cs>>>(dpc);
+    CUDA_TRY(cudaEventRecord(h->evChunk[2 * c], cs));
+    sp.rec = dpc.rec;
+    sp.key = dpc.key;
+    sp.spillScratch = h->spillScratch.as<unsigned char>() + (size_t)a * spillBytes * (size_t)spillBlocks;
     for (int k = 0; k < kNumSeedClasses; ++k) {
       const bool last = k == kSpillClass;
-      sp.workList = dp.classList + (size_t)k * dp.classStride;
+      sp.workList = lists + (size_t)k * dp.classStride;
       sp.nWorkPtr = cw + 8 + k;
       sp.workCounter = cw + 1 + k;
-      sp.overflowList = last ? nullptr : dp.classList + (size_t)(k + 1) * dp.classStride;
+      sp.overflowList = last ? nullptr : lists + (size_t)(k + 1) * dp.classStride;
       sp.overflowCount = last ? nullptr : cw + 8 + k + 1;
       sp.arrayBytes = last ? spillBytes : h->classBytes[k];
       const int blocks = last ? spillBlocks : h->smCount * h->classBlocksPerSM[k];
-      seed_kernel(conf, k)<<<blocks, h->classThreads[k], last ? 0 : h->classBytes[k], s>>>(sp);
+      seed_kernel(conf, k)<<<blocks, h->classThreads[k], last ? 0 : h->classBytes[k], cs>>>(sp);
     }
-    CUDA_TRY(cudaEventRecord(h->evChunk[2 * c + 1], s));
+    CUDA_TRY(cudaEventRecord(h->evChunk[2 * c + 1], cs));
     launches += 1 + kNumSeedClasses;
+    if (c + 1 == nChunks) h->lastDoublets = dpc;
   }
+  if (overlap) {  // the caller's stream continues when both chunk streams are done
+    for (int a = 0; a < nStreams; ++a) {
+      CUDA_TRY(cudaEventRecord(h->evChunkEnd[a], h->chunkStream[a]));
+      CUDA_TRY(cudaStreamWaitEvent(s, h->evChunkEnd[a], 0));
+    }
+  }
+  if (nChunks == 0) h->lastDoublets = dp;
   CUDA_TRY(cudaGetLastError());
   sp.nWorkPtr = wp.workStart + nNavAll;
   h->launches = launches;
-  h->lastDoublets = dp;
   if (conf) {
     ConfParams& cf = h->confParams;
     cf = ConfParams{};
@@ -602,8 +629,9 @@ int finish(b200seed_handle* h, cudaStream_t s, b200seed_seeds* out) {
     h->stageMs[4] = cudaEventElapsedTime(&t, h->ev[2], h->evCount) == cudaSuccess ? t : 0.f;
     h->stageMs[5] = 0.f;
     h->stageMs[6] = 0.f;
-    for (uint32_t c = 0; c < h->chunksTimed; ++c) {
-      cudaEvent_t before = c == 0 ? h->evCount : h->evChunk[2 * c - 1];
+    const uint32_t lag = (h->chunkStreams > 1 && h->chunksTimed > 1) ? (uint32_t)h->chunkStreams : 1u;
+    for (uint32_t c = 0; c < h->chunksTimed; ++c) {  // with two chunk streams the sums overlap in time
+      cudaEvent_t before = c < lag ? h->evCount : h->evChunk[2 * (c - lag) + 1];
       if (cudaEventElapsedTime(&t, before, h->evChunk[2 * c]) == cudaSuccess) h->stageMs[5] += t;
       if (cudaEventElapsedTime(&t, h->evChunk[2 * c], h->evChunk[2 * c + 1]) == cudaSuccess) h->stageMs[6] += t;
     }
@@ -748,6 +776,12 @@ int b200seed_create(const b200seed_config* cfg, int device, b200seed_handle** ou
   h->exactTies = engineRelaxed ? 0 : (int)env_u32("B200SEED_EXACT_TIES", 1);
   h->arenaMaxBytes = (size_t)std::max<uint32_t>(env_u32("B200SEED_ARENA_MB", 2048), 64u) << 20;
   CREATE_TRY(cudaEventCreate(&h->evCount));
+  CREATE_TRY(cudaEventCreateWithFlags(&h->evPlan, cudaEventDisableTiming));
+  h->chunkStreams = env_u32("B200SEED_CHUNK_STREAMS", 2) >= 2 ? 2 : 1;
+  for (int a = 0; a < 2; ++a) {
+    CREATE_TRY(cudaStreamCreateWithFlags(&h->chunkStream[a], cudaStreamNonBlocking));
+    CREATE_TRY(cudaEventCreateWithFlags(&h->evChunkEnd[a], cudaEventDisableTiming));
+  }
   CREATE_TRY(cudaMallocHost(&h->hPlan, (8 + (size_t)kMaxChunks + 1 + 8) * 4));
   {
     // dynamic shared memory of every class: what is left of the SM for N resident blocks (1 KB per block is
@@ -819,7 +853,8 @@ void b200seed_destroy(b200seed_handle* h) {
                     &h->binStart, &h->binCursor, &h->tmpIdx, &h->pIdx, &h->pXY, &h->pZR, &h->pVar,
                     &h->sortScratch, &h->midLo, &h->midCount, &h->workStart, &h->workPos, &h->workEG,
                     &h->workCounter, &h->capB, &h->capT, &h->slotPrefix, &h->capTileSums, &h->capTilePrefix, &h->planDev,
-                    &h->hdr, &h->classList, &h->arenaRec, &h->arenaKey, &h->spillScratch, &h->zWinOffsets, &h->slotB, &h->slotM, &h->slotT, &h->slotQ, &h->slotZ, &h->slotCount,
+                    &h->hdr, &h->classList, &h->arenaRec[0], &h->arenaRec[1], &h->arenaKey[0], &h->arenaKey[1], &h->spillScratch,
+                    &h->zWinOffsets, &h->slotB, &h->slotM, &h->slotT, &h->slotQ, &h->slotZ, &h->slotCount,
                     &h->seedStart, &h->tileSums, &h->tilePrefix, &h->outB, &h->outM, &h->outT, &h->outQ,
                     &h->outZ, &h->seedOffsets, &h->counters, &h->status, &h->zWin, &h->rec, &h->recZ, &h->recBegin,
                     &h->recCount, &h->slot2B, &h->slot2M, &h->slot2T, &h->slot2Q, &h->slot2Z, &h->slot2Count,
@@ -829,6 +864,11 @@ void b200seed_destroy(b200seed_handle* h) {
   if (h->hConfState != nullptr) cudaFreeHost(h->hConfState);
   if (h->hPlan != nullptr) cudaFreeHost(h->hPlan);
   if (h->evCount != nullptr) cudaEventDestroy(h->evCount);
+  if (h->evPlan != nullptr) cudaEventDestroy(h->evPlan);
+  for (int a = 0; a < 2; ++a) {
+    if (h->chunkStream[a] != nullptr) { cudaStreamSynchronize(h->chunkStream[a]); cudaStreamDestroy(h->chunkStream[a]); }
+    if (h->evChunkEnd[a] != nullptr) cudaEventDestroy(h->evChunkEnd[a]);
+  }
   for (cudaEvent_t e : h->evChunk) cudaEventDestroy(e);
   for (int i = 0; i < 5; ++i) {
     if (h->ev[i] != nullptr) cudaEventDestroy(h->ev[i]);
@@ -1284,13 +1324,16 @@ int b200seed_debug_doublets(b200seed_handle* h, b200seed_doublets* out) {
     dp.workCounter = scratchCounters;
     dp.classCount = scratchCounters + 8;
     dp.counters = h->counters.as<unsigned long long>();  // scribbled on: the host copy of the last run is what counts
+    dp.rec = h->arenaRec[0].as<DoubletRecord>();
+    dp.key = h->arenaKey[0].as<float>();
+    dp.classList = h->classList.as<uint32_t>();
     k_doublets<true><<<h->smCount * h->doubletBlocksPerSM[1], kDoubletWarps * 32, 0, s>>>(dp);
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaGetLastError());
     uint64_t slots = 0;
     for (uint32_t w = w0; w < w1; ++w) slots = std::max<uint64_t>(slots, (uint64_t)hdr[w].offset + hdr[w].capB + capT[w]);
     rec.resize(std::max<uint64_t>(slots, 1));
-    if (slots > 0) CUDA_TRY(cudaMemcpy(rec.data(), h->arenaRec.ptr, slots * sizeof(DoubletRecord), cudaMemcpyDeviceToHost));
+    if (slots > 0) CUDA_TRY(cudaMemcpy(rec.data(), h->arenaRec[0].ptr, slots * sizeof(DoubletRecord), cudaMemcpyDeviceToHost));
     for (uint32_t w = w0; w < w1; ++w) {
       out->firstDoublet[w] = o;
       out->nBottom[w] = hdr[w].nB;

@@ -287,34 +287,90 @@ def run_gpu(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for i in range(args.warmup):
-        step_device(eng, i)
-    eng.sync()
+    # The timed region: K steps (batches) handed out to `value_streams` worker threads, each with its own handle on its
+    # own CUDA stream (the engine synchronises once per call to read its chunk plan; several handles keep the GPU
+    # busy across those gaps, like the Sequencer's worker threads do).  Timed with CUDA events: every worker stream
+    # waits for the start event, the end event waits for every worker stream.
+    n_val = max(1, args.value_streams)
+    val_engines = [eng] + [plugin.SeedingEngine(cfg, device=local) for _ in range(n_val - 1)]
+    val_streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(n_val - 1)]
+    # every worker needs its own output buffers (the batches' inputs are shared, read-only)
+    val_out = [[dict(d_out=[torch.empty_like(t) for t in b["d_out"]], d_soff=torch.zeros_like(b["d_soff"])) for b in batches]
+               for _ in range(n_val - 1)]
+
+    def step_on(t, i):
+        b = batches[i % n_batches]
+        o = b if t == 0 else val_out[t - 1][i % n_batches]
+        val_engines[t].run_batch_device(E, b["n_total"], b["d_off"].data_ptr(), [x.data_ptr() for x in b["d_cols"]],
+                                        o["d_soff"].data_ptr(), [x.data_ptr() for x in o["d_out"]], b["cap"],
+                                        stream=C.c_void_p(val_streams[t].cuda_stream))
+
+    def run_steps(first, count):
+        nxt = [first]
+        lock = threading.Lock()
+
+        def worker(t):
+            torch.cuda.set_device(local)
+            while True:
+                with lock:
+                    i = nxt[0]
+                    nxt[0] += 1
+                if i >= first + count:
+                    return
+                step_on(t, i)
+
+        ths = [threading.Thread(target=worker, args=(t,)) for t in range(n_val)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+
+    run_steps(0, max(args.warmup, n_val) * 1)
+    for e_ in val_engines:
+        e_.sync()
     launches_per_step = eng.counters()["nKernelLaunches"]
 
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         e0.record(stream)
-        for i in range(args.steps):
-            step_device(eng, args.warmup + i)
+        for st_ in val_streams[1:]:
+            st_.wait_event(e0)
+        run_steps(args.warmup, args.steps)
+        for st_ in val_streams[1:]:
+            done = torch.cuda.Event()
+            done.record(st_)
+            stream.wait_event(done)
         e1.record(stream)
         barrier()
     elapsed_ms = max_over_ranks(e0.elapsed_time(e1))
-    n_seeds_last = eng.sync()
+    n_seeds_last = 0
+    for e_ in val_engines:
+        n_seeds_last = e_.sync() or n_seeds_last
     cnt = eng.counters()
+    for e_ in val_engines[1:]:
+        e_.close()
+    del val_out
     value = world * E * args.steps / (elapsed_ms * 1e-3)
     # per-stage durations, measured live with the plugin's CUDA events (same stream) in a second, identically
     # shaped pass so that reading the events back does not put host syncs into the timed region above
+    # (the engine overlaps consecutive arena chunks on two internal streams; a second handle with
+    # B200SEED_CHUNK_STREAMS=1 runs them back to back so that every kernel's duration is its own)
+    os.environ["B200SEED_CHUNK_STREAMS"] = "1"
+    eng_serial = plugin.SeedingEngine(cfg, device=local)
+    del os.environ["B200SEED_CHUNK_STREAMS"]
     stage = {k: [] for k in ("grid", "seed", "doublet_count", "doublet_fill", "seed_middles")}
-    for i in range(min(args.steps, 8)):
-        step_device(eng, args.warmup + i)
-        eng.sync()
-        st = eng.stage_times_ms()
+    for i in range(2 + min(args.steps, 8)):
+        step_device(eng_serial, args.warmup + i)
+        eng_serial.sync()
+        if i < 2:
+            continue  # workspace allocation
+        st = eng_serial.stage_times_ms()
         for k in stage:
             stage[k].append(st[k])
     stage = {k: float(np.mean(v)) for k, v in stage.items()}
-    cnt_stage = eng.counters()  # counters of the last batch of the stage pass
+    cnt_stage = eng_serial.counters()  # counters of the last batch of the stage pass
+    eng_serial.close()
 
     # ---- end to end through the host C ABI, the reference's call pattern -----------------------------
     # The reference's execute() is entered by several Sequencer worker threads, ONE EVENT PER CALL
@@ -556,7 +612,8 @@ def run_gpu(args):
                    "l2_policy": f"inputs larger than L2: {n_batches} distinct resident batches "
                                 f"({n_batches * b0['n_total'] * 24 / 1e6:.0f} MB of columns) rotated; the doublet arena "
                                 f"(~{36 * n_dbl / 1e9:.0f} GB per step) streams through HBM",
-                   "parallelism": f"event sharding over {world} GPU(s), same event pool on every rank, no data-path collective"},
+                   "parallelism": f"event sharding over {world} GPU(s), same event pool on every rank, no data-path collective",
+                   "streams_per_gpu": n_val},
         "clocks": clk,
         "e2e": {"value": best_rate, "unit": UNIT, "h2d_bytes_per_step": int(h2d_ev), "d2h_bytes_per_step": int(d2h_ev),
                 "host_threads_per_gpu": best_t, "calls": n_calls, "threads_sweep": sweep,
@@ -605,6 +662,7 @@ def main():
     ap.add_argument("--events-per-step", type=int, default=EVENTS_PER_STEP)
     ap.add_argument("--distinct-events", type=int, default=N_DISTINCT_EVENTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--value-streams", type=int, default=3, help="handles (one CUDA stream each) that share the steps of the timed region")
     ap.add_argument("--e2e-threads", default="1,2,3,4,6", help="host worker threads (handles) per GPU swept by the e2e leg")
     ap.add_argument("--parity-events", type=int, default=4, help="timed events re-seeded by the reference and compared (0: skip)")
     ap.add_argument("--no-latency", dest="latency", action="store_false", help="skip the <mu>=300 latency block")
