@@ -19,6 +19,8 @@
 #define b200seed_create B200SEED_E(create)
 #define b200seed_destroy B200SEED_E(destroy)
 #define b200seed_last_error B200SEED_E(last_error)
+#define b200seed_alloc_pinned B200SEED_E(alloc_pinned)
+#define b200seed_free_pinned B200SEED_E(free_pinned)
 #define b200seed_get_info B200SEED_E(get_info)
 #define b200seed_get_counters B200SEED_E(get_counters)
 #define b200seed_run B200SEED_E(run)

@@ -22,6 +22,8 @@ extern "C" {
   int P##create(const b200seed_config*, int, P##handle**);                                                  \
   void P##destroy(P##handle*);                                                                              \
   const char* P##last_error(void);                                                                          \
+  void* P##alloc_pinned(size_t);                                                                            \
+  void P##free_pinned(void*);                                                                               \
   int P##get_info(const P##handle*, b200seed_info*);                                                        \
   int P##get_counters(const P##handle*, b200seed_counters*);                                                \
   int P##run(P##handle*, uint32_t, const float*, const float*, const float*, const float*, const float*,    \
@@ -97,6 +99,9 @@ const char* b200seed_last_error(void) {
   if (g_lastEngine == 2) return g_ownError;
   return g_lastEngine == 1 ? b200rx_last_error() : b200ex_last_error();
 }
+
+void* b200seed_alloc_pinned(size_t bytes) { return b200ex_alloc_pinned(bytes); }
+void b200seed_free_pinned(void* p) { b200ex_free_pinned(p); }
 
 int b200seed_config_init(b200seed_config* cfg) {
   g_lastEngine = 0;

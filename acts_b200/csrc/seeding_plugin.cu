@@ -668,6 +668,19 @@ extern "C" {
 
 const char* b200seed_last_error(void) { return g_lastError.c_str(); }
 
+void* b200seed_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes > 0 ? bytes : 1) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void b200seed_free_pinned(void* p) {
+  if (p != nullptr) cudaFreeHost(p);
+}
+
 int b200seed_config_init(b200seed_config* cfg) {
   if (cfg == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "cfg is NULL");
   config_defaults(*cfg);

@@ -13,13 +13,25 @@
 // body is what a Plugins/B200Seeding algorithm would contain, with the column
 // spans taken from SpacePointContainer::xColumn() etc..
 //
+// execute() is const and RE-ENTRANT like the reference's (the Sequencer enters it from several TBB worker
+// threads at once, one event each: Examples/Framework/src/Framework/Sequencer.cpp:472-525; the reference keeps
+// its per-thread scratch in a thread_local cache, GridTripletSeedingAlgorithm.cpp:337).  Here every call borrows
+// an engine slot -- a C-ABI handle (own CUDA stream and device workspaces) plus page-locked seed buffers that
+// are reused from call to call -- from a pool owned by the algorithm object; slots are created on demand up to
+// Config::maxConcurrentEvents, further callers wait for a free one.
+//
 // Header only; link against libacts_b200_seeding.so.  No CPU fallback.
 #pragma once
 
+#include <algorithm>
 #include <cmath>
+#include <condition_variable>
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 #include <limits>
+#include <memory>
+#include <mutex>
 #include <numbers>
 #include <span>
 #include <stdexcept>
@@ -113,6 +125,14 @@ class GridTripletSeedingAlgorithm final {
     std::uint32_t maxQualitySeedsPerSpMConf = 5;
     bool useDeltaRinsteadOfTopRadius = false;
     bool useExtraCuts = false;
+    /// Vertex-z constraint (reference: `inputVertices` names a whiteboard collection; a non-empty name enables the
+    /// cut for every event, GridTripletSeedingAlgorithm.hpp:239-243, .cpp:292-297).  Here the vertices are passed
+    /// to execute() directly; the name only switches the cut on.
+    std::string inputVertices;
+    double vertexZNSigma = 3.0;
+    double vertexZMargin = 0.0;
+    /// engine option: events seeded at the same time by one algorithm object (engine slots in the pool)
+    unsigned int maxConcurrentEvents = 4;
     /// engine option: CUDA device ordinal
     int device = 0;
     /// engine option: float fast path (FMA contraction, approximate division); seeds not guaranteed identical
@@ -120,7 +140,7 @@ class GridTripletSeedingAlgorithm final {
   };
 
   explicit GridTripletSeedingAlgorithm(const Config& cfg) : m_cfg(cfg) {
-    b200seed_config c{};
+    b200seed_config& c = m_abi;
     b200seed_config_init(&c);
     c.bFieldInZ = cfg.bFieldInZ; c.minPt = cfg.minPt; c.cotThetaMax = cfg.cotThetaMax; c.impactMax = cfg.impactMax;
     c.deltaRMin = cfg.deltaRMin; c.deltaRMax = cfg.deltaRMax;
@@ -134,7 +154,7 @@ class GridTripletSeedingAlgorithm final {
     c.zBinNeighborsTop = m_zTop.data(); c.nZBinNeighborsTop = static_cast<std::uint32_t>(cfg.zBinNeighborsTop.size());
     c.zBinNeighborsBottom = m_zBottom.data(); c.nZBinNeighborsBottom = static_cast<std::uint32_t>(cfg.zBinNeighborsBottom.size());
     c.numPhiNeighbors = cfg.numPhiNeighbors;
-    c.zBinEdges = cfg.zBinEdges.data(); c.nZBinEdges = static_cast<std::uint32_t>(cfg.zBinEdges.size());
+    c.zBinEdges = m_cfg.zBinEdges.data(); c.nZBinEdges = static_cast<std::uint32_t>(m_cfg.zBinEdges.size());
     for (std::size_t v : cfg.zBinsCustomLooping) m_looping.push_back(v);
     c.zBinsCustomLooping = m_looping.data(); c.nZBinsCustomLooping = static_cast<std::uint32_t>(m_looping.size());
     c.rMinMiddle = cfg.rMinMiddle; c.rMaxMiddle = cfg.rMaxMiddle;
@@ -159,39 +179,51 @@ class GridTripletSeedingAlgorithm final {
     c.maxSeedsPerSpMConf = cfg.maxSeedsPerSpMConf; c.maxQualitySeedsPerSpMConf = cfg.maxQualitySeedsPerSpMConf;
     c.useDeltaRinsteadOfTopRadius = cfg.useDeltaRinsteadOfTopRadius; c.useExtraCuts = cfg.useExtraCuts;
     c.relaxedFloat = cfg.relaxedFloat;
-    check(b200seed_create(&c, cfg.device, &m_handle));
+    c.useVertexZCuts = !cfg.inputVertices.empty();
+    c.vertexZNSigma = cfg.vertexZNSigma;
+    c.vertexZMargin = cfg.vertexZMargin;
+    if (cfg.maxConcurrentEvents == 0) throw std::invalid_argument("maxConcurrentEvents must be at least 1");
+    // the reference constructor chain throws here; so does this one (host-side validation, then the first slot)
+    b200seed_info info{};
+    check(b200seed_plan_info(&c, &info));
+    m_pool = std::make_unique<Pool>();
+    m_pool->slots.push_back(newSlot());
+    m_pool->free.push_back(m_pool->slots.back().get());
   }
-  ~GridTripletSeedingAlgorithm() { b200seed_destroy(m_handle); }
+  ~GridTripletSeedingAlgorithm() = default;
   GridTripletSeedingAlgorithm(const GridTripletSeedingAlgorithm&) = delete;
   GridTripletSeedingAlgorithm& operator=(const GridTripletSeedingAlgorithm&) = delete;
 
-  /// Run the seeding algorithm on one event (reference: execute(ctx), .cpp:180-402).
-  /// `zWindows` are the optional per-event vertex z-windows (VertexZCuts, .cpp:69-97).
-  SeedColumns execute(const SpacePointColumns& sp,
-                      std::span<const std::pair<float, float>> zWindows = {}) const {
-    const std::size_t n = sp.x.size();
-    if (sp.y.size() != n || sp.z.size() != n || sp.r.size() != n || sp.varianceZ.size() != n || sp.varianceR.size() != n) {
-      throw std::invalid_argument("space point columns differ in length");
-    }
+  /// Run the seeding algorithm on one event (reference: execute(ctx), .cpp:180-402).  Thread-safe and const.
+  /// `zWindows` are optional per-event vertex z-windows given directly (VertexZCuts, .cpp:69-97).
+  SeedColumns execute(const SpacePointColumns& sp, std::span<const std::pair<float, float>> zWindows = {}) const {
+    checkColumns(sp);
     std::vector<float> lo, hi;
     for (const auto& [a, b] : zWindows) { lo.push_back(a); hi.push_back(b); }
-    SeedColumns out;
-    std::size_t cap = std::max<std::size_t>(16, 2 * n);
-    for (;;) {
-      out.bottom.resize(cap); out.middle.resize(cap); out.top.resize(cap); out.quality.resize(cap); out.vertexZ.resize(cap);
-      b200seed_seeds s{out.bottom.data(), out.middle.data(), out.top.data(), out.quality.data(), out.vertexZ.data(), cap, 0};
-      const int rc = b200seed_run(m_handle, static_cast<std::uint32_t>(n), sp.x.data(), sp.y.data(), sp.z.data(), sp.r.data(),
-                                  sp.varianceZ.data(), sp.varianceR.data(), static_cast<std::uint32_t>(lo.size()), lo.data(),
-                                  hi.data(), &s);
-      if (rc == B200SEED_ERR_CAPACITY) { cap = s.size; continue; }
-      check(rc);
-      out.bottom.resize(s.size); out.middle.resize(s.size); out.top.resize(s.size); out.quality.resize(s.size); out.vertexZ.resize(s.size);
-      return out;
-    }
+    Lease lease(*m_pool, *this);
+    return run(*lease.slot, sp, [&](Slot& slot, b200seed_seeds* s) {
+      return b200seed_run(slot.handle, static_cast<std::uint32_t>(sp.x.size()), sp.x.data(), sp.y.data(), sp.z.data(), sp.r.data(),
+                          sp.varianceZ.data(), sp.varianceR.data(), static_cast<std::uint32_t>(lo.size()), lo.data(), hi.data(), s);
+    });
+  }
+
+  /// One event with its reconstructed vertices (reference: m_inputVertices(ctx), .cpp:187-206): z position and the
+  /// (2, 2) element of the covariance of every vertex.  Needs Config::inputVertices to be set, like the reference.
+  SeedColumns execute(const SpacePointColumns& sp, std::span<const double> vertexZ, std::span<const double> vertexVarZ) const {
+    checkColumns(sp);
+    if (m_cfg.inputVertices.empty()) throw std::invalid_argument("vertices given but Config::inputVertices is empty");
+    if (vertexZ.size() != vertexVarZ.size()) throw std::invalid_argument("vertex columns differ in length");
+    Lease lease(*m_pool, *this);
+    return run(*lease.slot, sp, [&](Slot& slot, b200seed_seeds* s) {
+      return b200seed_run_vertices(slot.handle, static_cast<std::uint32_t>(sp.x.size()), sp.x.data(), sp.y.data(), sp.z.data(),
+                                   sp.r.data(), sp.varianceZ.data(), sp.varianceR.data(), static_cast<std::uint32_t>(vertexZ.size()),
+                                   vertexZ.data(), vertexVarZ.data(), s);
+    });
   }
 
   const Config& config() const { return m_cfg; }
-  b200seed_counters counters() const { b200seed_counters c{}; b200seed_get_counters(m_handle, &c); return c; }
+  /// engine slots created so far (<= Config::maxConcurrentEvents)
+  std::size_t slotsInUse() const { std::lock_guard<std::mutex> g(m_pool->mutex); return m_pool->slots.size(); }
 
  private:
   static void copyRange(const SeedConfirmationRangeConfig& a, b200seed_seed_confirmation_range& b) {
@@ -211,11 +243,99 @@ class GridTripletSeedingAlgorithm final {
     }
   }
 
+  /// One engine slot: a handle (stream + device workspaces) and page-locked seed columns, reused from call to call.
+  struct Slot {
+    b200seed_handle* handle = nullptr;
+    void* pinned = nullptr;
+    std::size_t capacity = 0;  // seeds
+    ~Slot() {
+      if (pinned != nullptr) b200seed_free_pinned(pinned);
+      if (handle != nullptr) b200seed_destroy(handle);
+    }
+    void reserve(std::size_t seeds) {
+      if (seeds <= capacity) return;
+      if (pinned != nullptr) b200seed_free_pinned(pinned);
+      capacity = seeds + seeds / 4;
+      pinned = b200seed_alloc_pinned(capacity * 20);
+      if (pinned == nullptr) { capacity = 0; throw std::runtime_error("page-locked allocation failed"); }
+    }
+    b200seed_seeds columns() {
+      auto* base = static_cast<std::uint32_t*>(pinned);
+      return {base, base + capacity, base + 2 * capacity, reinterpret_cast<float*>(base + 3 * capacity),
+              reinterpret_cast<float*>(base + 4 * capacity), capacity, 0};
+    }
+  };
+  struct Pool {
+    std::mutex mutex;
+    std::condition_variable cv;
+    std::vector<std::unique_ptr<Slot>> slots;
+    std::vector<Slot*> free;
+  };
+  struct Lease {  // borrows a slot for the duration of one execute()
+    Pool& pool;
+    Slot* slot = nullptr;
+    Lease(Pool& p, const GridTripletSeedingAlgorithm& alg) : pool(p) {
+      std::unique_lock<std::mutex> lock(pool.mutex);
+      for (;;) {
+        if (!pool.free.empty()) { slot = pool.free.back(); pool.free.pop_back(); return; }
+        if (pool.slots.size() < alg.m_cfg.maxConcurrentEvents) {
+          pool.slots.push_back(nullptr);  // reserve the place, create outside the lock
+          const std::size_t at = pool.slots.size() - 1;
+          lock.unlock();
+          std::unique_ptr<Slot> fresh;
+          try { fresh = alg.newSlot(); } catch (...) { lock.lock(); pool.slots.erase(pool.slots.begin() + at); pool.cv.notify_one(); throw; }
+          lock.lock();
+          slot = fresh.get();
+          for (auto& sl : pool.slots) { if (sl == nullptr) { sl = std::move(fresh); break; } }
+          return;
+        }
+        pool.cv.wait(lock);
+      }
+    }
+    ~Lease() {
+      { std::lock_guard<std::mutex> g(pool.mutex); pool.free.push_back(slot); }
+      pool.cv.notify_one();
+    }
+  };
+
+  std::unique_ptr<Slot> newSlot() const {
+    auto slot = std::make_unique<Slot>();
+    check(b200seed_create(&m_abi, m_cfg.device, &slot->handle));
+    return slot;
+  }
+
+  static void checkColumns(const SpacePointColumns& sp) {
+    const std::size_t n = sp.x.size();
+    if (sp.y.size() != n || sp.z.size() != n || sp.r.size() != n || sp.varianceZ.size() != n || sp.varianceR.size() != n) {
+      throw std::invalid_argument("space point columns differ in length");
+    }
+  }
+
+  template <typename Call>
+  static SeedColumns run(Slot& slot, const SpacePointColumns& sp, Call&& call) {
+    slot.reserve(std::max<std::size_t>(16, 2 * sp.x.size()));
+    for (;;) {
+      b200seed_seeds s = slot.columns();
+      const int rc = call(slot, &s);
+      if (rc == B200SEED_ERR_CAPACITY) { slot.reserve(static_cast<std::size_t>(s.size)); continue; }
+      check(rc);
+      SeedColumns out;
+      const std::size_t n = static_cast<std::size_t>(s.size);
+      out.bottom.assign(s.bottom, s.bottom + n);
+      out.middle.assign(s.middle, s.middle + n);
+      out.top.assign(s.top, s.top + n);
+      out.quality.assign(s.quality, s.quality + n);
+      out.vertexZ.assign(s.vertexZ, s.vertexZ + n);
+      return out;
+    }
+  }
+
   Config m_cfg;
+  b200seed_config m_abi{};  // points into the vectors below
   std::vector<std::int32_t> m_zTop, m_zBottom;
   std::vector<std::uint64_t> m_looping;
   std::vector<float> m_rRange;
-  b200seed_handle* m_handle = nullptr;
+  std::unique_ptr<Pool> m_pool;  // mutable state behind the const interface, guarded by its mutex
 };
 
 }  // namespace ActsB200

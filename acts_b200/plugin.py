@@ -22,7 +22,8 @@ LIB_PATH = os.environ.get("B200SEED_LIB", os.path.join(_HERE, "libacts_b200_seed
 # every symbol include/acts_b200_seeding.h declares
 EXPORTED_SYMBOLS = [
     "b200seed_config_init", "b200seed_plan_info", "b200seed_plan_tables", "b200seed_create",
-    "b200seed_destroy", "b200seed_last_error", "b200seed_get_info", "b200seed_get_counters",
+    "b200seed_destroy", "b200seed_last_error", "b200seed_alloc_pinned", "b200seed_free_pinned",
+    "b200seed_get_info", "b200seed_get_counters",
     "b200seed_get_stage_times", "b200seed_get_stage_times_ex", "b200seed_set_phi_sector", "b200seed_estimate_params",
     "b200seed_run_vertices", "b200seed_vertex_windows", "b200seed_run_batch_windows",
     "b200seed_make_pixel_spacepoints", "b200seed_run_measurements",
@@ -50,6 +51,9 @@ def lib():
         L = C.CDLL(LIB_PATH)
         vp, u32, u64, f32p = C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p
         L.b200seed_last_error.restype = C.c_char_p
+        L.b200seed_alloc_pinned.restype = vp
+        L.b200seed_alloc_pinned.argtypes = [C.c_size_t]
+        L.b200seed_free_pinned.argtypes = [vp]
         L.b200seed_config_init.argtypes = [C.POINTER(Config)]
         L.b200seed_plan_info.argtypes = [C.POINTER(Config), C.POINTER(Info)]
         L.b200seed_plan_tables.argtypes = [C.POINTER(Config), vp, u64, vp, vp, vp, vp, vp, vp]

@@ -240,6 +240,11 @@ int b200seed_plan_tables(const b200seed_config* cfg, void* deviceConfig, uint64_
 int b200seed_create(const b200seed_config* cfg, int device, b200seed_handle** out);
 void b200seed_destroy(b200seed_handle* h);
 
+/* Page-locked host memory for the caller's column / seed buffers (cudaMallocHost / cudaFreeHost): copies from and
+ * to such buffers run at the full link rate and asynchronously.  NULL on failure. */
+void* b200seed_alloc_pinned(size_t bytes);
+void b200seed_free_pinned(void* p);
+
 /* Error text of the last failing call on this thread (never NULL). */
 const char* b200seed_last_error(void);
 

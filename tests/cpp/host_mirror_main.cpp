@@ -1,12 +1,20 @@
 // Exercises the C++ host mirror (acts_b200/host/GridTripletSeedingAlgorithm.hpp).
 //   host_mirror_main errors              -> exception mapping (no GPU needed beyond plan validation)
 //   host_mirror_main run <in.bin> <out.bin>  -> seeds one event read from a raw float file
+//   host_mirror_main mt <out.bin> <threads> <in0.bin> <in1.bin> ...
+//        -> ONE algorithm object, <threads> worker threads calling execute() concurrently (every thread seeds every
+//           event twice, in a different order, the way the Sequencer's workers enter execute()); all results of an
+//           event must be identical; the seeds of every event are written one after the other
+//   host_mirror_main runv <in.bin> <out.bin> <nSigma> <margin> z0 var0 z1 var1 ...  -> Config::inputVertices path
 // File format in: uint32 n, then x[n] y[n] z[n] r[n] varZ[n] varR[n] (float32).
 // File format out: uint64 nSeeds, then bottom, middle, top (uint32) and quality, vertexZ (float32).
+#include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <thread>
 #include <vector>
 
 #include "../../acts_b200/host/GridTripletSeedingAlgorithm.hpp"
@@ -36,7 +44,82 @@ static bool throwsAs(Alg::Config c) {
   return false;
 }
 
+using Columns = std::vector<std::vector<float>>;
+
+static Columns readEvent(const char* path) {
+  std::ifstream in(path, std::ios::binary);
+  std::uint32_t n = 0;
+  in.read(reinterpret_cast<char*>(&n), 4);
+  Columns col(6, std::vector<float>(n));
+  for (auto& v : col) in.read(reinterpret_cast<char*>(v.data()), 4ull * n);
+  return col;
+}
+
+static void writeSeeds(std::ofstream& out, const ActsB200::SeedColumns& seeds) {
+  const std::uint64_t ns = seeds.size();
+  out.write(reinterpret_cast<const char*>(&ns), 8);
+  out.write(reinterpret_cast<const char*>(seeds.bottom.data()), 4 * ns);
+  out.write(reinterpret_cast<const char*>(seeds.middle.data()), 4 * ns);
+  out.write(reinterpret_cast<const char*>(seeds.top.data()), 4 * ns);
+  out.write(reinterpret_cast<const char*>(seeds.quality.data()), 4 * ns);
+  out.write(reinterpret_cast<const char*>(seeds.vertexZ.data()), 4 * ns);
+}
+
+static bool sameSeeds(const ActsB200::SeedColumns& a, const ActsB200::SeedColumns& b) {
+  return a.bottom == b.bottom && a.middle == b.middle && a.top == b.top &&
+         a.size() == b.size() && std::memcmp(a.quality.data(), b.quality.data(), 4 * a.size()) == 0 &&
+         std::memcmp(a.vertexZ.data(), b.vertexZ.data(), 4 * a.size()) == 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc >= 5 && std::strcmp(argv[1], "mt") == 0) {
+    const int nThreads = std::atoi(argv[3]);
+    std::vector<Columns> evs;
+    for (int i = 4; i < argc; ++i) evs.push_back(readEvent(argv[i]));
+    const Alg alg(pu200());  // const: execute() is a const member, entered concurrently
+    std::vector<ActsB200::SeedColumns> first(evs.size());
+    for (std::size_t e = 0; e < evs.size(); ++e) {
+      first[e] = alg.execute({evs[e][0], evs[e][1], evs[e][2], evs[e][3], evs[e][4], evs[e][5]});
+    }
+    std::atomic<int> bad{0};
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nThreads; ++t) {
+      pool.emplace_back([&, t] {
+        try {
+          for (int rep = 0; rep < 2; ++rep) {
+            for (std::size_t k = 0; k < evs.size(); ++k) {
+              const std::size_t e = (k * 7 + static_cast<std::size_t>(t) * 3 + static_cast<std::size_t>(rep)) % evs.size();
+              const auto seeds = alg.execute({evs[e][0], evs[e][1], evs[e][2], evs[e][3], evs[e][4], evs[e][5]});
+              if (!sameSeeds(seeds, first[e])) ++bad;
+            }
+          }
+        } catch (const std::exception& ex) {
+          std::cerr << "thread " << t << ": " << ex.what() << "\n";
+          ++bad;
+        }
+      });
+    }
+    for (auto& th : pool) th.join();
+    std::ofstream out(argv[2], std::ios::binary);
+    for (const auto& s : first) writeSeeds(out, s);
+    std::printf("threads %d events %zu slots %zu mismatches %d\n", nThreads, evs.size(), alg.slotsInUse(), bad.load());
+    return bad.load() == 0 ? 0 : 1;
+  }
+  if (argc >= 6 && std::strcmp(argv[1], "runv") == 0) {
+    const Columns col = readEvent(argv[2]);
+    auto cfg = pu200();
+    cfg.inputVertices = "vertices";
+    cfg.vertexZNSigma = std::atof(argv[4]);
+    cfg.vertexZMargin = std::atof(argv[5]);
+    std::vector<double> vz, vv;
+    for (int i = 6; i + 1 < argc; i += 2) { vz.push_back(std::atof(argv[i])); vv.push_back(std::atof(argv[i + 1])); }
+    const Alg alg(cfg);
+    const auto seeds = alg.execute({col[0], col[1], col[2], col[3], col[4], col[5]}, vz, vv);
+    std::ofstream out(argv[3], std::ios::binary);
+    writeSeeds(out, seeds);
+    std::printf("seeds %zu\n", seeds.size());
+    return 0;
+  }
   if (argc >= 2 && std::strcmp(argv[1], "errors") == 0) {
     auto a = pu200(); a.minPt = 0.010f;                       // std::domain_error (phi binning)
     auto b = pu200(); b.phiMin = -4.f;                        // std::runtime_error (grid range)
