@@ -473,6 +473,34 @@ B2S_HD int classify_pair(const DeviceConfig& c, float rM, float varZM, float var
   float cu, im;
   return eval_pair_t<false>(c, rM, varZM, varRM, b, cotThetaT, erT, iDeltaRT, uT, &vT, cu, im);
 }
+// Branch-free classification for the scans: every term of eval_pair_t is evaluated unconditionally (the same
+// operations on the same inputs, so the same bits) and the class is selected at the end.  A warp of walkers takes
+// every path of the branchy version in almost every step anyway; straight-line code lets the independent chains
+// (first slope cut | conformal line A, S2, B | measured-pT slope cut | impact) overlap instead of waiting for one
+// another.  dU == 0 divides by zero (inf / NaN, discarded by the selection; IEEE division does not trap).
+B2S_HD int classify_pair_flat(const DeviceConfig& c, float rM, float varZM, float varRM,
+                              const BottomCtx& b, float cotThetaT, float erT, float iDeltaRT,
+                              float uT, float vT) {
+  const float cotThetaAvg2 = fmul(b.cotThetaB, cotThetaT);
+  const float corr = fmul(fmul(fmul(2.0f, fadd(fmul(cotThetaAvg2, varRM), varZM)), b.iDeltaRB), iDeltaRT);
+  const float error2 = fadd(fadd(erT, b.erB), corr);
+  const float deltaCotTheta = fsub(b.cotThetaB, cotThetaT);
+  const float deltaCotTheta2 = fmul(deltaCotTheta, deltaCotTheta);
+  const bool failA = deltaCotTheta2 > fadd(error2, b.scatteringInRegion2);
+  const float dU = fsub(uT, b.Ub);
+  const float A = fdiv(fsub(vT, b.Vb), dU);
+  const float S2 = fadd(1.0f, fmul(A, A));
+  const float B = fsub(b.Vb, fmul(A, b.Ub));
+  const float B2 = fmul(B, B);
+  const bool skipHelix = (dU == 0) | (S2 < fmul(B2, c.minHelixDiameter2));
+  const float iHelixDiameter2 = fdiv(B2, S2);
+  const float p2scatterSigma = fmul(iHelixDiameter2, b.sigmaSquaredPtDependent);
+  const bool failB = deltaCotTheta2 > fadd(error2, p2scatterSigma);
+  const float im = fabs_(fmul(fsub(A, fmul(B, rM)), rM));
+  const bool skipImpact = im > c.impactMax;
+  return failA ? kPairFailA : (skipHelix ? kPairSkip : (failB ? kPairFailB : (skipImpact ? kPairSkip : kPairEmit)));
+}
+
 // the scans: v of the top is read only when the pair gets past the first slope cut
 B2S_HD int classify_pair_lazy(const DeviceConfig& c, float rM, float varZM, float varRM,
                               const BottomCtx& b, float cotThetaT, float erT, float iDeltaRT,

@@ -33,6 +33,9 @@ namespace B200SEED_NS {
 #ifndef B200SEED_SPLIT_WALKERS
 #define B200SEED_SPLIT_WALKERS 0  // scans: 1 = separate backward / forward walkers per bottom, 0 = one merged walk
 #endif
+#ifndef B200SEED_CLASSIFY
+#define B200SEED_CLASSIFY classify_pair_flat  // or classify_pair (early exits)
+#endif
 #ifndef B200SEED_REFILL
 #define B200SEED_REFILL 12  // idle lanes of a warp that trigger a refill of the scan walkers
 #endif
@@ -670,7 +673,8 @@ struct __align__(16) MiddleHeader {
 static_assert(sizeof(MiddleHeader) == 32, "header is loaded as two 16-byte words");
 
 // Shared-memory classes of k_seed_middles: a middle goes to the smallest class its lists fit.
-constexpr int kNumSeedClasses = 6;  // 5 shared-memory classes + the spill class (lists in global memory)
+constexpr int kNumSeedClasses = 6;  // 5 shared-memory classes (6, 4, 3, 2, 1 resident blocks per SM) + the spill class (lists in global memory)
+constexpr int kChunkCounterWords = 32;  // per arena chunk: [0] fill ticket, [1 + k] ticket of class k, [16 + k] list length of class k
 constexpr int kSpillClass = kNumSeedClasses - 1;
 constexpr uint32_t kMaxListLength = 65534;  // 16-bit ranks
 constexpr uint32_t kMaxChunks = 4096;
@@ -1378,6 +1382,25 @@ __device__ __forceinline__ void block_fix_ties(uint32_t n, const float* cot, uin
 #ifndef B200SEED_SEED_REGS
 #define B200SEED_SEED_REGS 56  // 36 warps per SM; measured against 64 (32 warps) and 48 (42 warps, spills)
 #endif
+// Per-middle array inside the block's dynamic shared memory, addressed by a 32-bit byte offset from the shared
+// window (one register per array; the accesses are LDS / STS with the offset folded into the address), or, for the
+// spill class, a plain pointer into the block's global scratch.
+template <typename T, bool kSpill>
+struct Arr {
+  uint32_t off;
+  T* glob;
+  __device__ __forceinline__ Arr(unsigned char* base, uint32_t byteOffset) : off(byteOffset), glob(reinterpret_cast<T*>(base + byteOffset)) {}
+  __device__ __forceinline__ T* ptr() const {
+    if constexpr (kSpill) {
+      return glob;
+    } else {
+      extern __shared__ __align__(16) unsigned char smemRaw[];
+      return reinterpret_cast<T*>(smemRaw + off);
+    }
+  }
+  __device__ __forceinline__ T& operator[](uint32_t i) const { return ptr()[i]; }
+};
+
 // ---- TMA bulk copies (cp.async.bulk, 1-D, global -> shared) completing on an mbarrier ----------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -1451,22 +1474,20 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
       middle_info(mid);
     }
     const SeedCarve cv = seed_carve(nB, nT);
-    uint16_t* rankB = reinterpret_cast<uint16_t*>(base + cv.oRankB);
-    uint16_t* tstar = reinterpret_cast<uint16_t*>(base + cv.oTstar);
-    float4* sA = reinterpret_cast<float4*>(base + cv.oTops);  // sorted tops: {cotTheta, er, iDeltaR, u}, then v, then pos
-    float* sV = reinterpret_cast<float*>(sA + nT);
-    uint32_t* sPos = reinterpret_cast<uint32_t*>(sV + nT);
-    uint32_t* buckets = reinterpret_cast<uint32_t*>(base + cv.oBuckets);
-    float* keyB = reinterpret_cast<float*>(base + cv.oKeyB);
-    float* keyT = reinterpret_cast<float*>(base + cv.oKeyT);
-    uint16_t* rankT = reinterpret_cast<uint16_t*>(base + cv.oRankT);
-    TieItem* tieW = reinterpret_cast<TieItem*>(base + cv.oTie);
-    uint16_t* tieGrp = reinterpret_cast<uint16_t*>(base + cv.oTieGrp);
-    uint16_t* hval = reinterpret_cast<uint16_t*>(base + cv.oHval);
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(base + cv.oCnt);
+    const Arr<uint16_t, kSpill> rankB(base, cv.oRankB), tstar(base, cv.oTstar);
+    const Arr<float4, kSpill> sA(base, cv.oTops);  // sorted tops: {cotTheta, er, iDeltaR, u}, then v, then pos
+    const Arr<float, kSpill> sV(base, cv.oTops + 16u * nT);
+    const Arr<uint32_t, kSpill> sPos(base, cv.oTops + 20u * nT);
+    const Arr<uint32_t, kSpill> buckets(base, cv.oBuckets);
+    const Arr<float, kSpill> keyB(base, cv.oKeyB), keyT(base, cv.oKeyT);
+    const Arr<uint16_t, kSpill> rankT(base, cv.oRankT);
+    const Arr<TieItem, kSpill> tieW(base, cv.oTie);
+    const Arr<uint16_t, kSpill> tieGrp(base, cv.oTieGrp);
+    const Arr<uint16_t, kSpill> hval(base, cv.oHval);
+    const Arr<uint32_t, kSpill> cnt(base, cv.oCnt);
     const uint32_t poolCap = (p.arrayBytes - cv.oPool) / kPoolEntryBytes;
-    uint32_t* pool = reinterpret_cast<uint32_t*>(base + cv.oPool);
-    Cand* pool2 = reinterpret_cast<Cand*>(base + carve_align(cv.oPool + 4u * poolCap));
+    const Arr<uint32_t, kSpill> pool(base, cv.oPool);
+    const Arr<Cand, kSpill> pool2(base, carve_align(cv.oPool + 4u * poolCap));
 
     if (tid == 0) {
       sh.tie = 0; sh.tieB = 0; sh.tieT = 0; sh.heapSize = 0; sh.poolCount = 0; sh.nextBottom = 0; sh.heapSorted = 0;
@@ -1481,8 +1502,8 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
       if (tid == 0) {
         const uint32_t bytesB = ((nB + 3u) & ~3u) * 4u, bytesT = ((nT + 3u) & ~3u) * 4u;
         mbar_expect_tx(&keyBar, bytesB + bytesT);
-        tma_bulk_g2s(keyB, gKeyB, bytesB, &keyBar);
-        tma_bulk_g2s(keyT, gKeyT, bytesT, &keyBar);
+        tma_bulk_g2s(keyB.ptr(), gKeyB, bytesB, &keyBar);
+        tma_bulk_g2s(keyT.ptr(), gKeyT, bytesT, &keyBar);
       }
       mbar_wait(&keyBar, keyParity);
       keyParity ^= 1u;
@@ -1493,13 +1514,13 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
     }
 
     // ---- phase 2: order both lists like DoubletSeedFinder.hpp:94-104 -------
-    block_sort_both(nB, keyB, ordered_to_float(h1.x), ordered_to_float(h1.y), nT, keyT, ordered_to_float(h1.z),
-                    ordered_to_float(h1.w), rankB, rankT, buckets, cv.nBk, sh.scratch, &sh.tieB, &sh.tieT);
+    block_sort_both(nB, keyB.ptr(), ordered_to_float(h1.x), ordered_to_float(h1.y), nT, keyT.ptr(), ordered_to_float(h1.z),
+                    ordered_to_float(h1.w), rankB.ptr(), rankT.ptr(), buckets.ptr(), cv.nBk, sh.scratch, &sh.tieB, &sh.tieT);
     {
       const bool tieB = sh.tieB != 0, tieT = sh.tieT != 0;  // block-uniform (read after the sort's last barrier)
       if ((tieB || tieT) && tid == 0) sh.tie = 1;
-      if (tieB && p.exactTies && nB > 16) block_fix_ties(nB, keyB, rankB, tieW, tieGrp);
-      if (tieT && p.exactTies && nT > 16) block_fix_ties(nT, keyT, rankT, tieW, tieGrp);
+      if (tieB && p.exactTies && nB > 16) block_fix_ties(nB, keyB.ptr(), rankB.ptr(), tieW.ptr(), tieGrp.ptr());
+      if (tieT && p.exactTies && nT > 16) block_fix_ties(nT, keyT.ptr(), rankT.ptr(), tieW.ptr(), tieGrp.ptr());
     }
     // tops: full records in sorted order
     for (uint32_t t = tid; t < nT; t += THREADS) {
@@ -1531,7 +1552,10 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
       bottom_ctx(cfg, bc);
     };
     auto emit = [&](uint32_t j, uint32_t t) {
-      const uint32_t slot = atomicAdd(&sh.poolCount, 1u);
+      // a plain shared-memory atomic per candidate: they are rare (0.03 per pair test), the compiler's warp
+      // aggregation of atomicAdd costs more than it saves here
+      uint32_t slot;
+      asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(smem_u32(&sh.poolCount)) : "memory");
       if (slot < poolCap) pool[slot] = t | (j << 16);
     };
 #if B200SEED_SPLIT_WALKERS
@@ -1575,7 +1599,7 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
         if (active) {
           ++myTests;
           const float4 a = sA[t];
-          const int cls = classify_pair_lazy(cfg, mid.r, mid.varZ, mid.varR, bc, a.x, a.y, a.z, a.w, sV + t);
+          const int cls = B200SEED_CLASSIFY(cfg, mid.r, mid.varZ, mid.varR, bc, a.x, a.y, a.z, a.w, sV[t]);
           if (cls == kPairEmit) emit(j, (uint32_t)t);
           if (cls <= kPairFailB) {  // the walk ends at the first failing top
             if (step < 0) {
@@ -1632,7 +1656,7 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
         if (active) {
           ++myTests;
           const float4 a = sA[t];
-          const int cls = classify_pair_lazy(cfg, mid.r, mid.varZ, mid.varR, bc, a.x, a.y, a.z, a.w, sV + t);
+          const int cls = B200SEED_CLASSIFY(cfg, mid.r, mid.varZ, mid.varR, bc, a.x, a.y, a.z, a.w, sV[t]);
           if (cls == kPairEmit) emit(j, (uint32_t)t);
           const bool fail = cls <= kPairFailB;
           bool done = false;
@@ -1679,7 +1703,7 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
     // ---- phase 3c: pairs in [start_j, t*_j) that the scans did not touch --
     // few bottoms have such a gap: list them first, then one thread per listed bottom
     {
-      uint16_t* gapList = reinterpret_cast<uint16_t*>(pool2);  // pool2 is free until phase 3d
+      uint16_t* gapList = reinterpret_cast<uint16_t*>(pool2.ptr());  // pool2 is free until phase 3d
       if (tid == 0) sh.nSurv = 0;
       __syncthreads();
       for (uint32_t b0 = 0; b0 < nB; b0 += THREADS) {
@@ -1698,7 +1722,7 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
         for (uint32_t t = s; t < te; ++t) {
           ++myTests;
           const float4 a = sA[t];
-          const int cls = classify_pair_lazy(cfg, mid.r, mid.varZ, mid.varR, bc, a.x, a.y, a.z, a.w, sV + t);
+          const int cls = B200SEED_CLASSIFY(cfg, mid.r, mid.varZ, mid.varR, bc, a.x, a.y, a.z, a.w, sV[t]);
           if (cls == kPairEmit) emit(j, t);
         }
       }
@@ -1726,7 +1750,7 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
       if (t >= hval[j]) atomicAdd(&cnt[j], 1u);
     }
     __syncthreads();
-    const uint32_t nValid = block_scan_array(cnt, nB, sh.scratch);
+    const uint32_t nValid = block_scan_array(cnt.ptr(), nB, sh.scratch);
     for (uint32_t e = tid; e < poolCount; e += THREADS) {
       const uint32_t to = pool[e];
       const uint32_t j = to >> 16, t = to & 0xFFFFu;
@@ -1750,7 +1774,7 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
     for (uint32_t j = tid; j < nB; j += THREADS) {
       const uint32_t s = j == 0 ? 0u : cnt[j - 1], e = cnt[j];
       if (e - s < 2) continue;
-      Cand* grp = pool2 + s;
+      Cand* grp = pool2.ptr() + s;
       const int n = (int)(e - s);
       // the reference's input order is ascending top rank (emission order) ...
       for (int i = 1; i < n; ++i) {
@@ -1775,7 +1799,7 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
         const Cand c = pool2[i];
         const uint32_t j = c.tOwner >> 16;
         const uint32_t s = j == 0 ? 0u : cnt[j - 1], e = cnt[j];
-        const Cand* grp = pool2 + s;
+        const Cand* grp = pool2.ptr() + s;
         uint32_t nCompat;
         float wgt = filter_weight(
             cfg, (int)(e - s), (int)(i - s), c.impactOrWeight, [&](int q) { return grp[q].curv; },
@@ -1835,7 +1859,7 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
       const Cand c = pool2[i];
       const uint32_t j = c.tOwner >> 16;
       const uint32_t s = j == 0 ? 0u : cnt[j - 1], e = cnt[j];
-      const Cand* grp = pool2 + s;
+      const Cand* grp = pool2.ptr() + s;
       const float wgt = filter_weight(
           cfg, (int)(e - s), (int)(i - s), c.impactOrWeight, [&](int q) { return grp[q].curv; },
           [&](int q) { return grp[q].topR; });

@@ -85,9 +85,9 @@ struct b200seed_handle {
   int exactTies = 1;
   uint32_t phiFirst = 1, phiCount = 0xFFFFFFFFu;  // middle phi-bin sector (default: all)
   // shared-memory classes of the seeding kernel (seeding_kernels.cuh): blocks per SM, dynamic bytes per block
-  int classBlocksPerSM[kNumSeedClasses] = {1, 1, 1, 1, 1, 1};
-  int classThreads[kNumSeedClasses] = {32, 32, 32, 32, 32, 32};
-  uint32_t classBytes[kNumSeedClasses] = {0, 0, 0, 0, 0, 0};
+  int classBlocksPerSM[kNumSeedClasses] = {};
+  int classThreads[kNumSeedClasses] = {};
+  uint32_t classBytes[kNumSeedClasses] = {};
   int doubletBlocksPerSM[2] = {1, 1};  // count / fill
   size_t arenaMaxBytes = (size_t)2048 << 20;  // B200SEED_ARENA_MB: doublet arena per chunk of middles
   // constant tables
@@ -103,6 +103,11 @@ struct b200seed_handle {
   int chunkStreams = 2;
   cudaStream_t chunkStream[2] = {nullptr, nullptr};
   cudaEvent_t evPlan = nullptr, evChunkEnd[2] = {nullptr, nullptr};
+  // The seeding kernels of the shared-memory classes of one chunk are independent: each runs on its own stream, so
+  // the tail of one class overlaps the start of the next (B200SEED_CLASS_STREAMS=0: one after the other).
+  int classStreams = 1;
+  cudaStream_t classStream[2][kNumSeedClasses] = {};
+  cudaEvent_t evFill[2] = {nullptr, nullptr}, evClass[2][kNumSeedClasses] = {};
   uint32_t* hPlan = nullptr;  // pinned: planWords[8] + chunkBounds[kMaxChunks + 1]
   std::vector<uint32_t> lastChunkBounds;  // of the last call (debug_doublets)
   DevBuf slotB, slotM, slotT, slotQ, slotZ, slotCount, seedStart, tileSums, tilePrefix;
@@ -182,12 +187,12 @@ int ensure_workspace(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal) {
   CUDA_TRY(h->workStart.reserve((nNavAll + 1) * 4));
   CUDA_TRY(h->workPos.reserve(nT * 4));
   CUDA_TRY(h->workEG.reserve(nT * 4));
-  CUDA_TRY(h->workCounter.reserve(16 * 4 * ((size_t)kMaxChunks + 2)));
+  CUDA_TRY(h->workCounter.reserve(kChunkCounterWords * 4 * ((size_t)kMaxChunks + 2)));
   CUDA_TRY(h->capB.reserve(nT * 4));
   CUDA_TRY(h->capT.reserve(nT * 4));
   CUDA_TRY(h->slotPrefix.reserve((nT + 1) * 8));
   CUDA_TRY(h->hdr.reserve(nT * sizeof(MiddleHeader)));
-  CUDA_TRY(h->classList.reserve(nT * 4 * kNumSeedClasses * 2));
+  CUDA_TRY(h->classList.reserve(nT * 4 * (kNumSeedClasses + 1) * 2));
   CUDA_TRY(h->planDev.reserve(((size_t)kMaxChunks + 1 + 8) * 4));
   CUDA_TRY(h->slotB.reserve(nT * K * 4));
   CUDA_TRY(h->slotM.reserve(nT * K * 4));
@@ -228,6 +233,7 @@ int ensure_workspace(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal) {
 // whose dynamic shared memory holds its lists (exact sizes, SeedCarve); the last class keeps them in global memory.
 struct SeedClassShape { int threads, blocksPerSM; };
 // (56 registers per thread: 36 warps fit an SM; thread counts measured, tools/sweep_regs.sh)
+// Finer classes (9 ... 1 blocks per SM) were measured and lost: every class kernel has its own tail.
 constexpr SeedClassShape kSeedClassShape[kNumSeedClasses] = {{192, 6}, {288, 4}, {384, 3}, {576, 2}, {1024, 1}, {1024, 1}};
 
 using SeedKernel = void (*)(const SeedParams);
@@ -314,7 +320,7 @@ int enqueue(b200seed_handle* h) {
 
   CUDA_TRY(cudaMemsetAsync(h->binCount.ptr, 0, ((size_t)nBinsAll + 1) * 4, s));
   CUDA_TRY(cudaMemsetAsync(h->binCursor.ptr, 0, ((size_t)nBinsAll + 1) * 4, s));
-  CUDA_TRY(cudaMemsetAsync(h->workCounter.ptr, 0, 16 * 4 * ((size_t)kMaxChunks + 2), s));
+  CUDA_TRY(cudaMemsetAsync(h->workCounter.ptr, 0, kChunkCounterWords * 4 * ((size_t)kMaxChunks + 2), s));
   CUDA_TRY(cudaMemsetAsync(h->counters.ptr, 0, kCntSlots * 8, s));
   CUDA_TRY(cudaMemsetAsync(h->status.ptr, 0, 16, s));
 
@@ -508,13 +514,15 @@ int enqueue(b200seed_handle* h) {
   for (uint32_t c = 0; c < nChunks; ++c) {
     const int a = overlap ? (int)(c % (uint32_t)nStreams) : 0;
     cudaStream_t cs = overlap ? h->chunkStream[a] : s;
-    uint32_t* cw = wc + 16 * (c + 1);  // [0] fill ticket, [1 + k] ticket of class k, [8 + k] list length of class k
-    uint32_t* lists = dp.classList + (size_t)a * kNumSeedClasses * dp.classStride;
+    uint32_t* cw = wc + kChunkCounterWords * (c + 1);
+    // lists of the chunk: [k] class k (filled by the doublet pass), [kNumSeedClasses] middles whose candidate pool
+    // overflowed in a shared-memory class (re-run with the largest shared memory, then, if need be, by the spill class)
+    uint32_t* lists = dp.classList + (size_t)a * (kNumSeedClasses + 1) * dp.classStride;
     DoubletParams dpc = dp;
     dpc.itemFirst = bounds[c];
     dpc.itemEnd = bounds[c + 1];
     dpc.workCounter = cw;
-    dpc.classCount = cw + 8;
+    dpc.classCount = cw + 16;
     dpc.classList = lists;
     dpc.rec = h->arenaRec[a].as<DoubletRecord>();
     dpc.key = h->arenaKey[a].as<float>();
@@ -523,17 +531,32 @@ int enqueue(b200seed_handle* h) {
     sp.rec = dpc.rec;
     sp.key = dpc.key;
     sp.spillScratch = h->spillScratch.as<unsigned char>() + (size_t)a * spillBytes * (size_t)spillBlocks;
-    for (int k = 0; k < kNumSeedClasses; ++k) {
-      const bool last = k == kSpillClass;
-      sp.workList = lists + (size_t)k * dp.classStride;
-      sp.nWorkPtr = cw + 8 + k;
-      sp.workCounter = cw + 1 + k;
-      sp.overflowList = last ? nullptr : lists + (size_t)(k + 1) * dp.classStride;
-      sp.overflowCount = last ? nullptr : cw + 8 + k + 1;
-      sp.arrayBytes = last ? spillBytes : h->classBytes[k];
-      const int blocks = last ? spillBlocks : h->smCount * h->classBlocksPerSM[k];
-      seed_kernel(conf, k)<<<blocks, h->classThreads[k], last ? 0 : h->classBytes[k], cs>>>(sp);
+    const int kLargest = kSpillClass - 1;
+    auto launchClass = [&](int k, int list, int ticket, int overflowTo, cudaStream_t st) {
+      const bool spill = k == kSpillClass;
+      sp.workList = lists + (size_t)list * dp.classStride;
+      sp.nWorkPtr = cw + 16 + list;
+      sp.workCounter = cw + 1 + ticket;
+      sp.overflowList = overflowTo < 0 ? nullptr : lists + (size_t)overflowTo * dp.classStride;
+      sp.overflowCount = overflowTo < 0 ? nullptr : cw + 16 + overflowTo;
+      sp.arrayBytes = spill ? spillBytes : h->classBytes[k];
+      const int blocks = spill ? spillBlocks : h->smCount * h->classBlocksPerSM[k];
+      seed_kernel(conf, k)<<<blocks, h->classThreads[k], spill ? 0 : h->classBytes[k], st>>>(sp);
+    };
+    const bool fan = h->classStreams != 0;
+    if (fan) CUDA_TRY(cudaEventRecord(h->evFill[a], cs));
+    for (int k = 0; k <= kLargest; ++k) {  // the shared-memory classes, concurrently
+      cudaStream_t st = fan ? h->classStream[a][k] : cs;
+      if (fan) CUDA_TRY(cudaStreamWaitEvent(st, h->evFill[a], 0));
+      launchClass(k, k, k, k == kLargest ? kSpillClass : kNumSeedClasses, st);
+      if (fan) {
+        CUDA_TRY(cudaEventRecord(h->evClass[a][k], st));
+        CUDA_TRY(cudaStreamWaitEvent(cs, h->evClass[a][k], 0));
+      }
     }
+    launchClass(kLargest, kNumSeedClasses, kNumSeedClasses, kSpillClass, cs);  // the rare pool overflows
+    launchClass(kSpillClass, kSpillClass, kSpillClass, -1, cs);
+    launches += 1;  // (the re-run of the overflow list)
     CUDA_TRY(cudaEventRecord(h->evChunk[2 * c + 1], cs));
     launches += 1 + kNumSeedClasses;
     if (c + 1 == nChunks) h->lastDoublets = dpc;
@@ -791,6 +814,14 @@ int b200seed_create(const b200seed_config* cfg, int device, b200seed_handle** ou
   CREATE_TRY(cudaEventCreate(&h->evCount));
   CREATE_TRY(cudaEventCreateWithFlags(&h->evPlan, cudaEventDisableTiming));
   h->chunkStreams = env_u32("B200SEED_CHUNK_STREAMS", 2) >= 2 ? 2 : 1;
+  h->classStreams = env_u32("B200SEED_CLASS_STREAMS", 1) != 0 ? 1 : 0;
+  for (int a = 0; a < 2; ++a) {
+    CREATE_TRY(cudaEventCreateWithFlags(&h->evFill[a], cudaEventDisableTiming));
+    for (int k = 0; k < kNumSeedClasses; ++k) {
+      CREATE_TRY(cudaStreamCreateWithFlags(&h->classStream[a][k], cudaStreamNonBlocking));
+      CREATE_TRY(cudaEventCreateWithFlags(&h->evClass[a][k], cudaEventDisableTiming));
+    }
+  }
   for (int a = 0; a < 2; ++a) {
     CREATE_TRY(cudaStreamCreateWithFlags(&h->chunkStream[a], cudaStreamNonBlocking));
     CREATE_TRY(cudaEventCreateWithFlags(&h->evChunkEnd[a], cudaEventDisableTiming));
@@ -816,11 +847,14 @@ int b200seed_create(const b200seed_config* cfg, int device, b200seed_handle** ou
       h->classBytes[c] = bytes;
       h->classThreads[c] = kSeedClassShape[c].threads;
       if (const char* v = std::getenv("B200SEED_CLASS_THREADS")) {  // kernel experiments: "160,256,320,512,1024,1024"
-        int t[kNumSeedClasses] = {0};
-        if (std::sscanf(v, "%d,%d,%d,%d,%d,%d", &t[0], &t[1], &t[2], &t[3], &t[4], &t[5]) == kNumSeedClasses && t[c] >= 32 &&
-            t[c] <= 1024 && t[c] % 32 == 0) {
-          h->classThreads[c] = t[c];
+        std::vector<int> t;
+        for (const char* q = v; *q != 0;) {
+          t.push_back(std::atoi(q));
+          const char* comma = std::strchr(q, ',');
+          if (comma == nullptr) break;
+          q = comma + 1;
         }
+        if ((int)t.size() == kNumSeedClasses && t[c] >= 32 && t[c] <= 1024 && t[c] % 32 == 0) h->classThreads[c] = t[c];
       }
       int b = 0;
       CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k, h->classThreads[c], bytes));
@@ -881,6 +915,11 @@ void b200seed_destroy(b200seed_handle* h) {
   for (int a = 0; a < 2; ++a) {
     if (h->chunkStream[a] != nullptr) { cudaStreamSynchronize(h->chunkStream[a]); cudaStreamDestroy(h->chunkStream[a]); }
     if (h->evChunkEnd[a] != nullptr) cudaEventDestroy(h->evChunkEnd[a]);
+    if (h->evFill[a] != nullptr) cudaEventDestroy(h->evFill[a]);
+    for (int k = 0; k < kNumSeedClasses; ++k) {
+      if (h->classStream[a][k] != nullptr) cudaStreamDestroy(h->classStream[a][k]);
+      if (h->evClass[a][k] != nullptr) cudaEventDestroy(h->evClass[a][k]);
+    }
   }
   for (cudaEvent_t e : h->evChunk) cudaEventDestroy(e);
   for (int i = 0; i < 5; ++i) {
@@ -1327,15 +1366,15 @@ int b200seed_debug_doublets(b200seed_handle* h, b200seed_doublets* out) {
   if (out->middleCapacity < nWork || out->doubletCapacity < total) return fail(B200SEED_ERR_CAPACITY, "debug_doublets buffers too small");
   if (nWork > 0) CUDA_TRY(cudaMemcpy(out->middlePos, h->workPos.ptr, (size_t)nWork * 4, cudaMemcpyDeviceToHost));
   uint64_t o = 0;
-  uint32_t* scratchCounters = h->workCounter.as<uint32_t>() + 16 * ((size_t)kMaxChunks + 1);
+  uint32_t* scratchCounters = h->workCounter.as<uint32_t>() + kChunkCounterWords * ((size_t)kMaxChunks + 1);
   std::vector<DoubletRecord> rec;
   for (uint32_t c = 0; c < nChunks; ++c) {
     const uint32_t w0 = h->lastChunkBounds[c], w1 = h->lastChunkBounds[c + 1];
-    CUDA_TRY(cudaMemsetAsync(scratchCounters, 0, 16 * 4, s));
+    CUDA_TRY(cudaMemsetAsync(scratchCounters, 0, kChunkCounterWords * 4, s));
     dp.itemFirst = w0;
     dp.itemEnd = w1;
     dp.workCounter = scratchCounters;
-    dp.classCount = scratchCounters + 8;
+    dp.classCount = scratchCounters + 16;
     dp.counters = h->counters.as<unsigned long long>();  // scribbled on: the host copy of the last run is what counts
     dp.rec = h->arenaRec[0].as<DoubletRecord>();
     dp.key = h->arenaKey[0].as<float>();

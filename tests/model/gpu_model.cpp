@@ -773,4 +773,38 @@ int64_t model_check_atan2f(uint64_t seed, int64_t n) {
 
 uint64_t model_sizeof_device_config() { return sizeof(DeviceConfig); }
 
+// classify_pair_flat (branch-free, used by the device scans) against classify_pair (the reference's early exits)
+// on random pairs around realistic magnitudes, incl. dU == 0, equal slopes and values at the cut edges.
+int64_t model_check_flat_classify(uint64_t seed, int64_t n) {
+  std::mt19937_64 rng(seed);
+  std::uniform_real_distribution<float> U(-1.f, 1.f);
+  DeviceConfig c{};
+  c.minHelixDiameter2 = 2781625.5f;
+  c.impactMax = 3.0f;
+  int64_t bad = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    BottomCtx b{};
+    const float scale = std::pow(10.f, 4.f * U(rng));  // wide dynamic range of the slope windows
+    b.cotThetaB = 3.f * U(rng);
+    b.erB = 1e-6f * std::fabs(U(rng)) * scale;
+    b.iDeltaRB = 0.02f * std::fabs(U(rng)) + 0.003f;
+    b.Ub = 0.03f * U(rng);
+    b.Vb = 0.01f * U(rng);
+    b.sigmaSquaredPtDependent = (1.f + b.cotThetaB * b.cotThetaB) * 4283.94f;
+    b.scatteringInRegion2 = 1.54008687e-3f * (1.f + b.cotThetaB * b.cotThetaB);
+    const float rM = 60.f + 60.f * std::fabs(U(rng));
+    const float cotT = b.cotThetaB + 0.08f * U(rng) * U(rng);
+    const float erT = 1e-6f * std::fabs(U(rng)) * scale;
+    const float iDRT = 0.02f * std::fabs(U(rng)) + 0.003f;
+    float uT = b.Ub + 0.02f * U(rng) * U(rng) * U(rng);
+    float vT = b.Vb + 0.002f * U(rng) * U(rng);
+    if (i % 97 == 0) uT = b.Ub;        // dU == 0
+    if (i % 101 == 0) vT = b.Vb;       // A == 0
+    const int want = classify_pair(c, rM, 2e-4f, 4e-6f, b, cotT, erT, iDRT, uT, vT);
+    const int got = classify_pair_flat(c, rM, 2e-4f, 4e-6f, b, cotT, erT, iDRT, uT, vT);
+    bad += want != got;
+  }
+  return bad;
+}
+
 }  // extern "C"

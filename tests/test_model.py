@@ -111,3 +111,14 @@ def test_model_bin_index_equals_oracle(env):
         ref = np.array([orc.bin_index(float(O.lib().oracle_atan2f(float(y), float(x))), float(z), float(r))
                         for x, y, z, r in zip(ev["x"][:n], ev["y"][:n], ev["z"][:n], ev["r"][:n])])
         assert np.array_equal(got, ref)
+
+
+def test_branch_free_pair_classification_equals_the_early_exit_form():
+    """classify_pair_flat (device scans) evaluates every term of the triplet test unconditionally and selects the
+    class at the end: same class as the reference's early-exit order on 2e7 random pairs incl. dU == 0."""
+    from tests.model import model
+
+    L = model.lib()
+    L.model_check_flat_classify.restype = __import__("ctypes").c_int64
+    L.model_check_flat_classify.argtypes = [__import__("ctypes").c_uint64, __import__("ctypes").c_int64]
+    assert L.model_check_flat_classify(7, 20_000_000) == 0

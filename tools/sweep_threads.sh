@@ -1,3 +1,3 @@
-for t in "160,256,320,512,1024,1024" "128,256,320,512,1024,1024" "128,192,320,512,1024,1024" "160,192,288,512,1024,1024" "160,224,320,512,1024,1024" "96,128,192,384,1024,1024" "192,256,320,512,1024,1024"; do
-  echo "threads $t: $(B200SEED_CLASS_THREADS=$t python tools/stage_times.py 8 200 3 2>&1 | grep 'rep 2' | sed 's/.*seed \([0-9.]*\).*seed_middles \([0-9.]*\).*/seed \1 middles \2/')"
+for t in "128,128,160,192,224,288,384,576,1024,1024" "96,128,160,192,224,288,384,576,1024,1024" "128,128,128,192,224,288,384,576,1024,1024" "128,160,160,192,224,288,384,576,1024,1024"; do
+  echo "threads $t: $(B200SEED_CLASS_THREADS=$t B200SEED_CHUNK_STREAMS=1 python tools/stage_times.py 8 200 3 2>&1 | grep 'rep 2' | sed 's/.*seed \([0-9.]*\).*seed_middles \([0-9.]*\).*/seed \1 middles \2/')"
 done
