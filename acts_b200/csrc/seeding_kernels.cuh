@@ -697,7 +697,9 @@ struct SeedCarve {
   uint32_t oPool;     // u32[P] emission records, then Cand[P]
   uint32_t endA;
   uint32_t minBytes;  // with the smallest pool the class assignment guarantees
+  uint32_t pad;       // 16 words: stored per middle by the fill pass, loaded as four 16-byte words by the seeding kernel
 };
+static_assert(sizeof(SeedCarve) == 64, "four 16-byte words");
 
 B2S_HD uint32_t carve_align(uint32_t v) { return (v + 15u) & ~15u; }
 B2S_HD uint32_t seed_pool_min(uint32_t nB) { return nB / 2u + 32u; }  // candidates per middle: 0.29 nB on average at <mu>=200 (a middle whose pool overflows moves up one class)
@@ -727,6 +729,7 @@ B2S_HD SeedCarve seed_carve(uint32_t nB, uint32_t nT) {
   c.oPool = b;
   const uint32_t withPool = b + kPoolEntryBytes * seed_pool_min(nB);
   c.minBytes = a > withPool ? a : withPool;
+  c.pad = 0;
   return c;
 }
 
@@ -752,6 +755,7 @@ struct DoubletParams {
   DoubletRecord* rec;                    // arena of the chunk
   float* key;
   MiddleHeader* hdr;                     // [nWork]
+  SeedCarve* carve;                      // [nWork] shared-memory layout of the middle's arrays in k_seed_middles
   uint32_t* slotCount;                   // [nWork] seeds per middle (zeroed here for middles without triplet stage)
   uint32_t* classList;                   // [kNumSeedClasses][classStride]
   uint32_t* classCount;                  // [kNumSeedClasses]
@@ -1013,7 +1017,9 @@ __global__ void __launch_bounds__(kDoubletWarps * 32) k_doublets(const __grid_co
             h.nB = nB; h.nT = nT;
             h.cotMinB = float_to_ordered(mnB); h.cotMaxB = float_to_ordered(mxB);
             h.cotMinT = float_to_ordered(mnT); h.cotMaxT = float_to_ordered(mxT);
-            const uint32_t foot = seed_carve(nB, nT).minBytes;
+            const SeedCarve cv = seed_carve(nB, nT);
+            p.carve[w] = cv;
+            const uint32_t foot = cv.minBytes;
             int c = 0;
             while (c < kSpillClass && foot > p.classBytes[c]) ++c;
             p.classList[(size_t)c * p.classStride + atomicAdd(p.classCount + c, 1u)] = w;
@@ -1166,6 +1172,7 @@ struct SeedParams {
   const uint32_t* workPos;
   // the chunk's doublets
   const MiddleHeader* hdr;
+  const SeedCarve* carve;
   const DoubletRecord* rec;
   const float* key;
   // work list of this launch (one shared-memory class of one chunk)
@@ -1473,7 +1480,13 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
       mid.x = mxy.x; mid.y = mxy.y; mid.z = mzr.x; mid.r = mzr.y; mid.varZ = mvar.x; mid.varR = mvar.y;
       middle_info(mid);
     }
-    const SeedCarve cv = seed_carve(nB, nT);
+    SeedCarve cv;  // computed once per middle by the fill pass
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(p.carve + w);
+      uint4* dst = reinterpret_cast<uint4*>(&cv);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dst[q] = __ldg(src + q);
+    }
     const Arr<uint16_t, kSpill> rankB(base, cv.oRankB), tstar(base, cv.oTstar);
     const Arr<float4, kSpill> sA(base, cv.oTops);  // sorted tops: {cotTheta, er, iDeltaR, u}, then v, then pos
     const Arr<float, kSpill> sV(base, cv.oTops + 16u * nT);

@@ -97,7 +97,7 @@ struct b200seed_handle {
   DevBuf binOf, binCount, binStart, binCursor, tmpIdx, pIdx, pXY, pZR, pVar, sortScratch;
   DevBuf midLo, midCount, workStart, workPos, workEG, workCounter;
   // doublet stage: slot sizes and prefix, chunk plan, arena, per-middle headers, per-class work lists
-  DevBuf capB, capT, slotPrefix, capTileSums, capTilePrefix, planDev, hdr, classList, arenaRec[2], arenaKey[2], spillScratch;
+  DevBuf capB, capT, slotPrefix, capTileSums, capTilePrefix, planDev, hdr, carve, classList, arenaRec[2], arenaKey[2], spillScratch;
   // Consecutive chunks alternate between two internal streams (and two arena halves): the tail of one chunk's
   // seeding kernels overlaps the fill pass of the next.  B200SEED_CHUNK_STREAMS=1 serialises them (stage timing).
   int chunkStreams = 2;
@@ -192,6 +192,7 @@ int ensure_workspace(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal) {
   CUDA_TRY(h->capT.reserve(nT * 4));
   CUDA_TRY(h->slotPrefix.reserve((nT + 1) * 8));
   CUDA_TRY(h->hdr.reserve(nT * sizeof(MiddleHeader)));
+  CUDA_TRY(h->carve.reserve(nT * sizeof(SeedCarve)));
   CUDA_TRY(h->classList.reserve(nT * 4 * (kNumSeedClasses + 1) * 2));
   CUDA_TRY(h->planDev.reserve(((size_t)kMaxChunks + 1 + 8) * 4));
   CUDA_TRY(h->slotB.reserve(nT * K * 4));
@@ -408,6 +409,7 @@ int enqueue(b200seed_handle* h) {
   dp.planWords = planWords;
   dp.slotPrefix = h->slotPrefix.as<unsigned long long>();
   dp.hdr = h->hdr.as<MiddleHeader>();
+  dp.carve = h->carve.as<SeedCarve>();
   dp.slotCount = h->slotCount.as<uint32_t>();
   dp.classList = h->classList.as<uint32_t>();
   dp.classStride = nWorkMax;
@@ -481,6 +483,7 @@ int enqueue(b200seed_handle* h) {
   sp.pXY = gp.pXY; sp.pZR = gp.pZR; sp.pVar = gp.pVar;
   sp.workPos = wp.workPos;
   sp.hdr = dp.hdr;
+  sp.carve = dp.carve;
   sp.spillScratch = h->spillScratch.as<unsigned char>();
   sp.slotB = h->slotB.as<uint32_t>(); sp.slotM = h->slotM.as<uint32_t>(); sp.slotT = h->slotT.as<uint32_t>();
   sp.slotQ = h->slotQ.as<float>(); sp.slotZ = h->slotZ.as<float>();
@@ -900,7 +903,7 @@ void b200seed_destroy(b200seed_handle* h) {
                     &h->binStart, &h->binCursor, &h->tmpIdx, &h->pIdx, &h->pXY, &h->pZR, &h->pVar,
                     &h->sortScratch, &h->midLo, &h->midCount, &h->workStart, &h->workPos, &h->workEG,
                     &h->workCounter, &h->capB, &h->capT, &h->slotPrefix, &h->capTileSums, &h->capTilePrefix, &h->planDev,
-                    &h->hdr, &h->classList, &h->arenaRec[0], &h->arenaRec[1], &h->arenaKey[0], &h->arenaKey[1], &h->spillScratch,
+                    &h->hdr, &h->carve, &h->classList, &h->arenaRec[0], &h->arenaRec[1], &h->arenaKey[0], &h->arenaKey[1], &h->spillScratch,
                     &h->zWinOffsets, &h->slotB, &h->slotM, &h->slotT, &h->slotQ, &h->slotZ, &h->slotCount,
                     &h->seedStart, &h->tileSums, &h->tilePrefix, &h->outB, &h->outM, &h->outT, &h->outQ,
                     &h->outZ, &h->seedOffsets, &h->counters, &h->status, &h->zWin, &h->rec, &h->recZ, &h->recBegin,
