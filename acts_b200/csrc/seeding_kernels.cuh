@@ -33,6 +33,9 @@ namespace B200SEED_NS {
 #ifndef B200SEED_SPLIT_WALKERS
 #define B200SEED_SPLIT_WALKERS 0  // scans: 1 = separate backward / forward walkers per bottom, 0 = one merged walk
 #endif
+#ifndef B200SEED_PREFETCH_SLOT
+#define B200SEED_PREFETCH_SLOT 1  // L2 prefetch of the middle's arena slot at the top of the middle
+#endif
 #ifndef B200SEED_CLASSIFY
 #define B200SEED_CLASSIFY classify_pair_flat  // or classify_pair (early exits)
 #endif
@@ -1508,6 +1511,16 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
       sh.w = item < nWork ? p.workList[item] : 0xFFFFFFFFu;
     }
 
+#if B200SEED_PREFETCH_SLOT
+    // The records of the slot are gathered later (tops after the sort, bottoms one by one in the scans): ask the
+    // L2 for the whole slot now, one 128-byte line (4 records) per request.
+    {
+      const uint32_t nLines = (h0.z + nT + 3u) >> 2;  // bottoms [0, capB) and tops [capB, capB + nT)
+      for (uint32_t i = tid; i < nLines; i += THREADS) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(recB + 4u * i));
+      }
+    }
+#endif
     // ---- phase 1: keys ---------------------------------------------------------
     // Two TMA bulk copies stage the contiguous cotTheta key spans of the middle's arena slot in shared memory
     // (slots and list capacities are multiples of four records, so both spans are 16-byte aligned and padded).
@@ -1637,14 +1650,22 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
       // merged walk: down from |P_j| - 1 to the last failing top of the prefix (-> H_j, t*_j), then up from
       // |P_j| to the first failing top beyond it (brk_j).
       constexpr uint32_t kRefill = B200SEED_REFILL;
+      // the sorted tops are read through two pinned 32-bit shared-memory addresses (one LEA per load)
+      uint32_t aBase = 0, vBase = 0;
+      if constexpr (!kSpill) {
+        aBase = smem_u32(sA.ptr());
+        vBase = smem_u32(sV.ptr());
+        asm volatile("" : "+r"(aBase), "+r"(vBase));  // keep them in registers: no re-derivation from the carve-up in the loop
+      }
       bool active = false, exhausted = false;  // exhausted is warp-uniform
       uint32_t j = 0, H = 0, ts = 0;
       int t = 0, tUp = 0, step = 0;
       BottomCtx bc{};
       for (;;) {
-        const uint32_t idleMask = __ballot_sync(0xffffffffu, !active);
-        const uint32_t nIdle = (uint32_t)__popc(idleMask);
-        if (!exhausted && nIdle >= kRefill) {
+        const uint32_t actMask = __ballot_sync(0xffffffffu, active);
+        if (!exhausted && (uint32_t)__popc(actMask) <= 32u - kRefill) {
+          const uint32_t idleMask = ~actMask;
+          const uint32_t nIdle = (uint32_t)__popc(idleMask);
           uint32_t first = 0;
           if (lane == 0) first = atomicAdd(&sh.nextBottom, nIdle);
           first = __shfl_sync(0xffffffffu, first, 0);
@@ -1658,18 +1679,27 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
               H = 0; ts = 0;
               tUp = P;
               if (P > 0) { t = P - 1; step = -1; } else { t = 0; step = 1; }
-              active = t < (int)nT;  // nT > 0: always
+              active = true;  // nT > 0
+#ifdef B200SEED_ABLATE_SCAN  // timing experiment only: no pair is tested
+              active = false; hval[j] = 0; tstar[j] = 0;
+#endif
             }
           }
+          continue;  // re-vote with the new walkers
         }
-        if (__ballot_sync(0xffffffffu, active) == 0u) {
-          if (exhausted) break;
-          continue;
-        }
+        if (actMask == 0u) break;  // nothing walks and nothing is left to hand out
         if (active) {
           ++myTests;
-          const float4 a = sA[t];
-          const int cls = B200SEED_CLASSIFY(cfg, mid.r, mid.varZ, mid.varR, bc, a.x, a.y, a.z, a.w, sV[t]);
+          float4 a;
+          float vT;
+          if constexpr (!kSpill) {
+            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(aBase + 16u * (uint32_t)t));
+            asm("ld.shared.f32 %0, [%1];" : "=f"(vT) : "r"(vBase + 4u * (uint32_t)t));
+          } else {
+            a = sA[t];
+            vT = sV[t];
+          }
+          const int cls = B200SEED_CLASSIFY(cfg, mid.r, mid.varZ, mid.varR, bc, a.x, a.y, a.z, a.w, vT);
           if (cls == kPairEmit) emit(j, (uint32_t)t);
           const bool fail = cls <= kPairFailB;
           bool done = false;
