@@ -917,6 +917,7 @@ __device__ __forceinline__ uint32_t doublet_side(const DoubletParams& p, const M
   return nOut;
 }
 
+// (a register cap for the fill pass -- __launch_bounds__(256, 3 / 4 / 5) -- was measured: 19 - 20 ms instead of 14.4 ms)
 template <bool kFill>
 __global__ void __launch_bounds__(kDoubletWarps * 32) k_doublets(const __grid_constant__ DoubletParams p) {
   __shared__ WarpWindows sWin[kDoubletWarps];
