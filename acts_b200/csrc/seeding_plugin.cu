@@ -845,7 +845,11 @@ int b200seed_create(const b200seed_config* cfg, int device, b200seed_handle** ou
         size_t dyn = perBlock - 1024 - fa.sharedSizeBytes;
         dyn = std::min<size_t>(dyn, (size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes);
         bytes = (uint32_t)(dyn & ~(size_t)127);
-        CREATE_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        // The classes share one kernel function and the attribute is per function and process-wide: every
+        // handle sets the SAME value (the opt-in maximum), so a handle created while another thread launches
+        // the largest class can never lower the limit under that launch.
+        CREATE_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(((size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes) & ~(size_t)127)));
       }
       h->classBytes[c] = bytes;
       h->classThreads[c] = kSeedClassShape[c].threads;
