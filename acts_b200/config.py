@@ -309,4 +309,60 @@ def itk_conf_config(init) -> Config:
     return itk_like_config(init).update(**confirmation_overrides())
 
 
+def itk_pixel_config(init, z_neighbors: bool = True, high_occupancy: bool = False) -> Config:
+    """The reference's second published configuration VERBATIM: ``itkSeedingAlgConfig(PixelSpacePoints)``
+    (Python/Examples/python/itk.py:302-560) as ``addGridTripletSeeding`` hands it to
+    ``GridTripletSeedingAlgorithm::Config`` (Python/Examples/python/reconstruction.py:1001-1077): 13 non-uniform z
+    bins out to +-3 m, the rRangeMiddleSP table, zBinsCustomLooping, interactionPointCut, seedConfirmation with
+    both range blocks, useDeltaRinsteadOfTopRadius, deltaZMax = inf.
+
+    ``z_neighbors``: also set zBinNeighborsTop / zBinNeighborsBottom / numPhiNeighbors (itk.py:410-441,380);
+    ``addGridTripletSeeding`` itself does not forward them (the fields keep their defaults), the legacy
+    ``addStandardSeeding`` path does (reconstruction.py:966-968) -- both shapes are tested.
+    ``high_occupancy``: the highOccupancyConfig branch (itk.py:451-456,492-511) incl. useExtraCuts."""
+    cfg = Config()
+    init(C.byref(cfg))
+    r_range = [(40.0, 90.0), (40.0, 90.0), (40.0, 200.0), (46.0, 200.0), (46.0, 200.0), (46.0, 250.0), (46.0, 250.0),
+               (46.0, 250.0), (46.0, 200.0), (46.0, 200.0), (40.0, 200.0), (40.0, 90.0), (40.0, 90.0)]
+    looping = [2, 3, 4, 5, 12, 11, 10, 9, 7, 6, 8]
+    r_max, delta_r_max = 320.0, 280.0
+    min_pt, col_min, col_max, variable = 900 * MeV, -200.0, 200.0, 1
+    if high_occupancy:
+        r_max, delta_r_max = 250.0, 200.0
+        looping = [2, 10, 3, 9, 6, 4, 8, 5, 7]
+        min_pt, col_min, col_max, variable = 1000 * MeV, -150.0, 150.0, 0
+        r_range = [(40.0, 80.0), (40.0, 80.0), (40.0, 200.0), (70.0, 200.0), (70.0, 200.0), (70.0, 250.0), (70.0, 250.0),
+                   (70.0, 250.0), (70.0, 200.0), (70.0, 200.0), (40.0, 200.0), (40.0, 80.0), (40.0, 80.0)]
+    cfg.update(
+        bFieldInZ=2 * T, minPt=min_pt, cotThetaMax=27.2899, impactMax=2.0,
+        deltaRMin=20.0, deltaRMax=delta_r_max, deltaRMinTop=6.0, deltaRMaxTop=280.0, deltaRMinBottom=6.0, deltaRMaxBottom=150.0,
+        rMax=r_max, zMin=-3000.0, zMax=3000.0, phiMin=-math.pi, phiMax=math.pi,
+        phiBinDeflectionCoverage=3, maxPhiBins=200,
+        zBinEdges=[-3000.0, -2700.0, -2500.0, -1400.0, -925.0, -500.0, -250.0, 250.0, 500.0, 925.0, 1400.0, 2500.0, 2700.0, 3000.0],
+        zBinsCustomLooping=looping,
+        useVariableMiddleSPRange=variable, rRangeMiddleSP=r_range,
+        deltaRMiddleMinSPRange=10.0, deltaRMiddleMaxSPRange=10.0,
+        interactionPointCut=1, collisionRegionMin=col_min, collisionRegionMax=col_max,
+        sigmaScattering=2.0, radLengthPerSeed=0.0975,
+        compatSeedWeight=100.0, impactWeightFactor=100.0, zOriginWeightFactor=1.0,
+        maxSeedsPerSpM=4, compatSeedLimit=3, seedWeightIncrement=0.0, numSeedIncrement=100.0,
+        seedConfirmation=1,
+        centralSeedConfirmationRange=dict(zMinSeedConf=-500.0, zMaxSeedConf=500.0, rMaxSeedConf=140.0, nTopForLargeR=1,
+                                          nTopForSmallR=2, seedConfMinBottomRadius=60.0, seedConfMaxZOrigin=150.0,
+                                          minImpactSeedConf=1.0),
+        forwardSeedConfirmationRange=dict(zMinSeedConf=-3000.0, zMaxSeedConf=3000.0, rMaxSeedConf=140.0, nTopForLargeR=1,
+                                          nTopForSmallR=2, seedConfMinBottomRadius=60.0, seedConfMaxZOrigin=150.0,
+                                          minImpactSeedConf=1.0),
+        maxSeedsPerSpMConf=5, maxQualitySeedsPerSpMConf=5, useDeltaRinsteadOfTopRadius=1,
+        useExtraCuts=1 if high_occupancy else 0,
+    )
+    if z_neighbors:
+        cfg.update(
+            zBinNeighborsTop=[(0, 0), (-1, 0), (-2, 0), (-1, 0), (-1, 0), (-1, 0), (-1, 1), (0, 1), (0, 1), (0, 1), (0, 2), (0, 1), (0, 0)],
+            zBinNeighborsBottom=[(0, 0), (0, 1), (0, 1), (0, 1), (0, 1), (0, 1), (0, 0), (-1, 0), (-1, 0), (-1, 0), (-1, 0), (-1, 0), (0, 0)],
+            numPhiNeighbors=1,
+        )
+    return cfg
+
+
 NAN = math.nan

@@ -27,10 +27,23 @@ B_FIELD_T = 2.0
 PT_PER_RADIUS = B_FIELD_T * 0.000299792458  # GeV / mm
 
 
-def _helix_hits(rng, zv, pt, eta, phi0, q):
+GENERIC_LAYOUT = dict(barrel_r=BARREL_R, barrel_half_z=BARREL_HALF_Z, endcap_z=ENDCAP_Z, endcap_r=ENDCAP_R)
+# ITk-shaped pixel layout (five barrel layers, end-cap rings out to |z| = 2.85 m, r up to 315 mm): the shape the
+# reference's second published configuration is written for (Python/Examples/python/itk.py:302-560: zBinEdges out to
+# +-3000 mm, rMax 320 mm, collision region +-200 mm).  Not the real ITk geometry -- a layout with its extent, so that
+# every z bin of the ITk table, the rRangeMiddleSP rows and the forward seedConfirmation range are populated.
+ITK_LAYOUT = dict(barrel_r=np.array([34.0, 99.0, 160.0, 228.0, 291.0]), barrel_half_z=380.0,
+                  endcap_z=np.array([450.0, 550.0, 680.0, 840.0, 1040.0, 1280.0, 1560.0, 1900.0, 2300.0, 2650.0, 2850.0]),
+                  endcap_r=(33.0, 315.0))
+
+
+def _helix_hits(rng, zv, pt, eta, phi0, q, layout=None):
     """Intersections of helices from (0, 0, zv) with all layers (vectorised).
 
     Returns x, y, z (float64), is_barrel for every hit."""
+    layout = GENERIC_LAYOUT if layout is None else layout
+    BARREL_R, BARREL_HALF_Z = layout["barrel_r"], layout["barrel_half_z"]
+    ENDCAP_Z, ENDCAP_R = layout["endcap_z"], layout["endcap_r"]
     R = pt / PT_PER_RADIUS  # mm
     sinh_eta = np.sinh(eta)
     xs, ys, zs, barrel = [], [], [], []
@@ -68,7 +81,10 @@ def _helix_hits(rng, zv, pt, eta, phi0, q):
     return (np.concatenate(xs), np.concatenate(ys), np.concatenate(zs), np.concatenate(barrel))
 
 
-def _finish(rng, x, y, z, barrel, noise_fraction):
+def _finish(rng, x, y, z, barrel, noise_fraction, layout=None):
+    layout = GENERIC_LAYOUT if layout is None else layout
+    BARREL_R, BARREL_HALF_Z = layout["barrel_r"], layout["barrel_half_z"]
+    ENDCAP_Z, ENDCAP_R = layout["endcap_z"], layout["endcap_r"]
     n = x.size
     n_noise = int(round(noise_fraction * n))
     if n_noise > 0:
@@ -118,6 +134,22 @@ def pileup_event(event: int, mu: float = 200.0, sp_per_vertex: float = 500.0,
     q = rng.choice([-1.0, 1.0], size=n)
     x, y, z, barrel = _helix_hits(rng, zv, pt, eta, phi0, q)
     return _finish(rng, x, y, z, barrel, noise_fraction)
+
+
+def itk_pileup_event(event: int, mu: float = 60.0, sp_per_vertex: float = 500.0,
+                     noise_fraction: float = 0.10, seed: int = 42) -> dict:
+    """Pile-up event on the ITk-shaped pixel layout (|eta| < 4, beam spot sigma_z = 50 mm)."""
+    rng = np.random.Generator(np.random.Philox(key=seed + 100003 * 7 + event))
+    n_vtx = max(1, int(rng.poisson(mu)))
+    n_part = rng.poisson(sp_per_vertex / (1.0 + noise_fraction) / 5.5, size=n_vtx)
+    zv = np.repeat(rng.normal(0.0, 50.0, size=n_vtx), n_part)
+    n = zv.size
+    pt = 0.1 + rng.gamma(2.0, 0.45, size=n)
+    eta = rng.uniform(-4.0, 4.0, size=n)
+    phi0 = rng.uniform(-np.pi, np.pi, size=n)
+    q = rng.choice([-1.0, 1.0], size=n)
+    x, y, z, barrel = _helix_hits(rng, zv, pt, eta, phi0, q, ITK_LAYOUT)
+    return _finish(rng, x, y, z, barrel, noise_fraction, ITK_LAYOUT)
 
 
 def muon_gun_event(event: int, n_muons: int = 100, seed: int = 42) -> dict:

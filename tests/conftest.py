@@ -25,11 +25,16 @@ def built():
     return True
 
 
-CONFIGS = ("seeding_py", "pu200", "itk_like", "itk_conf")
+CONFIGS = ("seeding_py", "pu200", "itk_like", "itk_conf", "itk_pixel", "itk_pixel_grid", "itk_pixel_ho")
 
 
 def make_config(name, init):
     from acts_b200 import config
 
     return {"seeding_py": config.seeding_py_config, "pu200": config.pu200_config,
-            "itk_like": config.itk_like_config, "itk_conf": config.itk_conf_config}[name](init)
+            "itk_like": config.itk_like_config, "itk_conf": config.itk_conf_config,
+            # the verbatim ITk PIXEL configuration (itk.py:302-560): with the z-neighbour tables, as
+            # addGridTripletSeeding forwards it (without them), and the highOccupancyConfig branch
+            "itk_pixel": config.itk_pixel_config,
+            "itk_pixel_grid": lambda i: config.itk_pixel_config(i, z_neighbors=False),
+            "itk_pixel_ho": lambda i: config.itk_pixel_config(i, high_occupancy=True)}[name](init)

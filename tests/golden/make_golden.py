@@ -1,11 +1,11 @@
 """Generates the committed golden vectors in tests/golden/ from the CPU oracle.
 
-The reference (ACTS) cannot be built or imported in the build container (needs
-Eigen / Boost / TBB / ROOT) and holds no golden vector
-for this path, so these fixtures are produced by the oracle restatement
-(oracle/seeding_oracle.cpp) -- "parity unpinned", see DESIGN.md.  They pin the
-oracle itself against accidental changes and travel to the GPU box, where the
-CUDA path is compared with them without running the oracle.
+The reference holds no golden vector for this path, so these fixtures are produced
+by the oracle restatement (oracle/seeding_oracle.cpp).  Every one of them is
+reproduced bit for bit by the UNMODIFIED reference sources compiled under
+oracle/_ref (tests/test_reference_pin.py::test_golden_fixtures_match_reference),
+i.e. they are reference outputs.  They travel to the GPU box, where the CUDA path
+is compared with them without running the oracle or the reference.
 
     python tests/golden/make_golden.py
 """
@@ -28,16 +28,21 @@ CASES = [
     ("pu200_mu20_ev3", "pu200", "pileup", 3, 20.0),
     ("itk_like_mu10_ev1", "itk_like", "pileup", 1, 10.0),
     ("itk_conf_mu20_ev2", "itk_conf", "pileup", 2, 20.0),  # seedConfirmation = true
+    # the verbatim ITk PIXEL configuration (itk.py:302-560) on the ITk-shaped layout
+    ("itk_pixel_mu20_ev0", "itk_pixel", "itk", 0, 20.0),
+    ("itk_pixel_grid_mu10_ev1", "itk_pixel_grid", "itk", 1, 10.0),
+    ("itk_pixel_ho_mu20_ev2", "itk_pixel_ho", "itk", 2, 20.0),
 ]
 
-MAKE = {"seeding_py": config.seeding_py_config, "pu200": config.pu200_config, "itk_like": config.itk_like_config,
-        "itk_conf": config.itk_conf_config}
+from tests.conftest import make_config  # noqa: E402
+
 
 
 def main():
     for name, cfg_name, gen, eid, mu in CASES:
-        ev = events.muon_gun_event(eid) if gen == "muon" else events.pileup_event(eid, mu=mu)
-        res = O.Oracle(MAKE[cfg_name](O.config_init)).run(ev, want_grid=True)
+        ev = (events.muon_gun_event(eid) if gen == "muon" else
+              events.itk_pileup_event(eid, mu=mu) if gen == "itk" else events.pileup_event(eid, mu=mu))
+        res = O.Oracle(make_config(cfg_name, O.config_init)).run(ev, want_grid=True)
         np.savez_compressed(
             os.path.join(HERE, name + ".npz"), config=cfg_name,
             x=ev["x"], y=ev["y"], z=ev["z"], r=ev["r"], varZ=ev["varZ"], varR=ev["varR"],

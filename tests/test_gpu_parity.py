@@ -270,6 +270,35 @@ def test_seed_confirmation_host_decisions(plugin, O, monkeypatch):
     eng.close()
 
 
+@pytest.mark.parametrize("name,mu,ids", [
+    ("itk_pixel", 20, (0, 1)),
+    ("itk_pixel", 60, (2,)),
+    ("itk_pixel_grid", 60, (3,)),
+    ("itk_pixel_ho", 60, (4,)),
+    ("itk_pixel", 200, (5,)),       # ~1.1e5 space points out to |z| = 2.85 m
+    ("itk_pixel_ho", 200, (6,)),
+])
+def test_verbatim_itk_pixel_configuration(plugin, O, name, mu, ids):
+    """The reference's second published configuration, verbatim (Python/Examples/python/itk.py:302-560:
+    13 z bins, rRangeMiddleSP table, zBinsCustomLooping, interactionPointCut, seedConfirmation, deltaR
+    instead of the top radius), on ITk-shaped events; single events and one batch."""
+    from acts_b200 import events
+
+    eng = plugin.SeedingEngine(make_config(name, plugin.config_init))
+    orc = O.Oracle(make_config(name, O.config_init))
+    evs = [events.itk_pileup_event(i, mu=mu) for i in ids]
+    refs = [orc.run(ev) for ev in evs]
+    for ev, ref in zip(evs, refs):
+        got = eng.run(ev)
+        assert ref["quality"].size > 0
+        assert _same_bits(got, ref), f"{name} mu={mu}"
+    if len(evs) > 1:
+        cols, offsets = events.concat_events(evs)
+        for got, ref in zip(eng.run_batch(cols, offsets), refs):
+            assert _same_bits(got, ref)
+    eng.close()
+
+
 def test_full_size_event_mu200_seed_confirmation(plugin, O):
     """<mu>=200 with seedConfirmation = true: ~4.8e4 middles coupled through bestSeedQualityMap."""
     from acts_b200 import config as cm

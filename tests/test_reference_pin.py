@@ -62,6 +62,11 @@ def test_recipe_compiles_only_sources_under_the_reference_tree():
     ("itk_like", "pileup", 60, (0,)),
     ("itk_conf", "pileup", 20, (0, 2)),
     ("itk_conf", "pileup", 60, (1,)),
+    # the verbatim ITk PIXEL configuration (Python/Examples/python/itk.py:302-560) on ITk-shaped events
+    ("itk_pixel", "itk", 20, (0, 1)),
+    ("itk_pixel", "itk", 60, (2,)),
+    ("itk_pixel_grid", "itk", 60, (3,)),
+    ("itk_pixel_ho", "itk", 60, (4,)),
 ])
 def test_oracle_matches_reference(O, R, name, kind, mu, ids):
     from acts_b200 import events
@@ -69,7 +74,8 @@ def test_oracle_matches_reference(O, R, name, kind, mu, ids):
     orc = O.Oracle(make_config(name, O.config_init))
     ref = R.Reference(make_config(name, O.config_init))
     for i in ids:
-        ev = events.muon_gun_event(i) if kind == "muon" else events.pileup_event(i, mu=mu)
+        ev = (events.muon_gun_event(i) if kind == "muon" else
+              events.itk_pileup_event(i, mu=mu) if kind == "itk" else events.pileup_event(i, mu=mu))
         a, b = orc.run(ev), ref.run(ev)
         assert b["bottom"].size > 0
         assert _same_bits(a, b), f"{name} event {i}"
