@@ -42,6 +42,15 @@ namespace B200SEED_NS {
 #ifndef B200SEED_REFILL
 #define B200SEED_REFILL 12  // idle lanes of a warp that trigger a refill of the scan walkers
 #endif
+#ifndef B200SEED_FLAT_WALK
+#define B200SEED_FLAT_WALK 1  // scans: straight-line walker bookkeeping (selects) instead of the backward / forward branches
+#endif
+#ifndef B200SEED_MERGE_3B3C
+#define B200SEED_MERGE_3B3C 1  // window starts and the gap list in one pass (two block barriers and one sweep less)
+#endif
+#ifndef B200SEED_OPAQUE_EMIT
+#define B200SEED_OPAQUE_EMIT 1  // candidate emission: one shared-memory atomic per lane (no vote / leader / shuffle aggregation)
+#endif
 #ifndef B200SEED_WORK_CHUNK
 #define B200SEED_WORK_CHUNK 8  // consecutive work items a block takes at a time (1 = none)
 #endif
@@ -1582,7 +1591,14 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
       // a plain shared-memory atomic per candidate: they are rare (0.03 per pair test), the compiler's warp
       // aggregation of atomicAdd costs more than it saves here
       uint32_t slot;
+#if B200SEED_OPAQUE_EMIT
+      // the address carries a per-lane zero: ptxas cannot prove it warp-uniform and emits one ATOMS per lane
+      // instead of its vote / leader / popc / shuffle aggregation sequence
+      const uint32_t addr = smem_u32(&sh.poolCount) + (j >> 16);  // j < 65536: + 0, but per-lane in the compiler's eyes
+      asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(addr) : "memory");
+#else
       asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(smem_u32(&sh.poolCount)) : "memory");
+#endif
       if (slot < poolCap) pool[slot] = t | (j << 16);
     };
 #if B200SEED_SPLIT_WALKERS
@@ -1704,6 +1720,20 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
           if (cls == kPairEmit) emit(j, (uint32_t)t);
           const bool fail = cls <= kPairFailB;
           bool done = false;
+#if B200SEED_FLAT_WALK
+          {
+            // straight-line bookkeeping: backward and forward walkers of a warp take the same instructions
+            const bool bwd = step < 0;
+            const bool bf = bwd & fail;
+            H = bf ? (uint32_t)t + (cls == kPairFailA ? 1u : 0u) : H;
+            ts = bf ? (uint32_t)t : ts;
+            const bool turn = bwd & (fail | (t == 0));  // the prefix is done: turn around
+            const int tn = turn ? tUp : t + step;
+            step = turn ? 1 : step;
+            done = ((!bwd) & fail) | (tn >= (int)nT);
+            t = tn;
+          }
+#else
           if (step < 0) {
             if (fail) { H = (uint32_t)(cls == kPairFailA ? t + 1 : t); ts = (uint32_t)t; }
             if (fail || t == 0) {  // the prefix is done: turn around
@@ -1717,6 +1747,7 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
             ++t;
             done = fail || t >= (int)nT;
           }
+#endif
           if (done) {
             hval[j] = (uint16_t)H;
             tstar[j] = (uint16_t)ts;
@@ -1728,6 +1759,40 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
 #endif
     __syncthreads();
 
+#if B200SEED_MERGE_3B3C
+    // ---- phase 3b + 3c: window start = exclusive running max of H; the few bottoms with pairs in
+    // [start_j, t*_j) that the scans did not touch are listed while the starts are written back
+    {
+      uint16_t* gapList = reinterpret_cast<uint16_t*>(pool2.ptr());  // pool2 is free until phase 3d
+      if (tid == 0) sh.nSurv = 0;  // ordered before the appends below by the barriers of the block scan
+      const uint32_t chunk = (nB + THREADS - 1) / THREADS;
+      const uint32_t c0 = tid * chunk, c1 = (c0 + chunk < nB) ? c0 + chunk : nB;
+      uint32_t localMax = 0;
+      for (uint32_t j = c0; j < c1; ++j) localMax = localMax > hval[j] ? localMax : (uint32_t)hval[j];
+      uint32_t blockMax;
+      uint32_t run = block_scan_exclusive(localMax, sh.scratch, blockMax, OpMax());
+      for (uint32_t j = c0; j < c1; ++j) {
+        const uint32_t h = hval[j];
+        hval[j] = (uint16_t)run;
+        if (run < tstar[j]) gapList[atomicAdd(&sh.nSurv, 1u)] = (uint16_t)j;  // rare
+        run = run > h ? run : h;
+      }
+      __syncthreads();
+      const uint32_t nGap = sh.nSurv;
+      for (uint32_t q = tid; q < nGap; q += THREADS) {
+        const uint32_t j = gapList[q];
+        const uint32_t s = hval[j], te = tstar[j];
+        BottomCtx bc;
+        bottomCtx(j, bc);
+        for (uint32_t t = s; t < te; ++t) {
+          ++myTests;
+          const float4 a = sA[t];
+          const int cls = B200SEED_CLASSIFY(cfg, mid.r, mid.varZ, mid.varR, bc, a.x, a.y, a.z, a.w, sV[t]);
+          if (cls == kPairEmit) emit(j, t);
+        }
+      }
+    }
+#else
     // ---- phase 3b: window start = exclusive running max of H --------------
     {
       const uint32_t chunk = (nB + THREADS - 1) / THREADS;
@@ -1771,6 +1836,7 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
         }
       }
     }
+#endif
     for (uint32_t j = tid; j <= nB; j += THREADS) cnt[j] = 0;
     __syncthreads();
     const uint32_t poolCount = sh.poolCount;
