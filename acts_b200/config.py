@@ -143,6 +143,15 @@ class Config(C.Structure):
         return self
 
 
+class OrthogonalOptions(C.Structure):
+    """b200seed_orthogonal_options: the OrthogonalTripletSeedingAlgorithm::Config members the grid Config lacks."""
+    _fields_ = [
+        ("zOutermostLayersMin", C.c_float),
+        ("zOutermostLayersMax", C.c_float),
+        ("deltaPhiMax", C.c_float),
+    ]
+
+
 class Seeds(C.Structure):
     _fields_ = [
         ("bottom", C.c_void_p),
@@ -363,6 +372,26 @@ def itk_pixel_config(init, z_neighbors: bool = True, high_occupancy: bool = Fals
             numPhiNeighbors=1,
         )
     return cfg
+
+
+def orthogonal_config(init_orth, **overrides):
+    """(Config, OrthogonalOptions) with the reference defaults of OrthogonalTripletSeedingAlgorithm::Config
+    (hpp:38-186) and the <mu>=200 cut set of pu200_config on top (the same physics cuts through the other
+    candidate provider; addOrthogonalTripletSeeding forwards the same SeedFinderConfigArg fields,
+    Python/Examples/python/reconstruction.py:1080-1160).  ``init_orth`` is ``*_orthogonal_config_init``."""
+    cfg, opt = Config(), OrthogonalOptions()
+    init_orth(C.byref(cfg), C.byref(opt))
+    cfg.update(
+        rMax=200 * mm, deltaRMin=1 * mm, deltaRMax=300 * mm, deltaRMinTop=1 * mm, deltaRMaxTop=300 * mm,
+        deltaRMinBottom=1 * mm, deltaRMaxBottom=300 * mm, collisionRegionMin=-250 * mm, collisionRegionMax=250 * mm,
+        zMin=-2000 * mm, zMax=2000 * mm, maxSeedsPerSpM=1, sigmaScattering=5, radLengthPerSeed=0.1, minPt=500 * MeV,
+        impactMax=3 * mm, bFieldInZ=2 * T,
+    )
+    opt_over = {k: overrides.pop(k) for k in list(overrides) if k in ("zOutermostLayersMin", "zOutermostLayersMax", "deltaPhiMax")}
+    cfg.update(**overrides)
+    for k, v in opt_over.items():
+        setattr(opt, k, v)
+    return cfg, opt
 
 
 NAN = math.nan

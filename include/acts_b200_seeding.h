@@ -240,6 +240,26 @@ int b200seed_plan_tables(const b200seed_config* cfg, void* deviceConfig, uint64_
 int b200seed_create(const b200seed_config* cfg, int device, b200seed_handle** out);
 void b200seed_destroy(b200seed_handle* h);
 
+/* ---- OrthogonalTripletSeedingAlgorithm (the k-d-tree candidate provider feeding the same
+ * doublet / triplet / filter stages; Examples/Algorithms/TrackFinding/include/ActsExamples/
+ * TrackFinding/OrthogonalTripletSeedingAlgorithm.hpp:33-186, src/...cpp:62-317) -----------------
+ * Its Config is a subset of the grid algorithm's fields (same names, other defaults) plus the
+ * three below.  Grid-only members of b200seed_config (phiBinDeflectionCoverage, maxPhiBins,
+ * zBinNeighbors*, numPhiNeighbors, zBinEdges, zBinsCustomLooping, rRangeMiddleSP, vertex cuts)
+ * are ignored; seedConfirmation = true is not supported here (B200SEED_ERR_UNSUPPORTED).
+ * The handle is used with b200seed_run / b200seed_run_batch / b200seed_sync like a grid handle;
+ * seeds come in the reference's order (middles in k-d-tree order, the increasing-z group of a
+ * middle before its decreasing-z group). */
+typedef struct b200seed_orthogonal_options {
+  float zOutermostLayersMin; /* Config::zOutermostLayers.first  (hpp:102-103) */
+  float zOutermostLayersMax; /* Config::zOutermostLayers.second */
+  float deltaPhiMax;         /* Config::deltaPhiMax (hpp:110) */
+} b200seed_orthogonal_options;
+/* Reference defaults of OrthogonalTripletSeedingAlgorithm::Config (hpp:38-186). */
+int b200seed_orthogonal_config_init(b200seed_config* cfg, b200seed_orthogonal_options* opt);
+int b200seed_create_orthogonal(const b200seed_config* cfg, const b200seed_orthogonal_options* opt, int device,
+                               b200seed_handle** out);
+
 /* Page-locked host memory for the caller's column / seed buffers (cudaMallocHost / cudaFreeHost): copies from and
  * to such buffers run at the full link rate and asynchronously.  NULL on failure. */
 void* b200seed_alloc_pinned(size_t bytes);

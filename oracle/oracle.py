@@ -12,7 +12,7 @@ import subprocess
 
 import numpy as np
 
-from acts_b200.config import Config, Info
+from acts_b200.config import Config, Info, OrthogonalOptions
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libseeding_oracle.so")
@@ -82,12 +82,20 @@ def lib():
         L.oracle_vertex_windows.argtypes = [C.POINTER(Config), C.c_uint32] + [C.c_void_p] * 4
         L.oracle_run_many.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 7 + [C.c_int, C.c_uint32, C.c_void_p]
         L.oracle_run_many.restype = C.c_int64
+        L.oracle_orthogonal_config_init.argtypes = [C.POINTER(Config), C.POINTER(OrthogonalOptions)]
+        L.oracle_create_orthogonal.argtypes = [C.POINTER(Config), C.POINTER(OrthogonalOptions), C.POINTER(C.c_void_p)]
+        L.oracle_result_tree_order.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_result_tree_order.restype = C.c_uint64
         _lib = L
     return _lib
 
 
 def config_init(cfg_ref):
     lib().oracle_config_init(cfg_ref)
+
+
+def orthogonal_config_init(cfg_ref, opt_ref):
+    lib().oracle_orthogonal_config_init(cfg_ref, opt_ref)
 
 
 class OracleError(RuntimeError):
@@ -105,10 +113,15 @@ class Oracle:
 
     FAITHFUL, STABLE = 0, 1
 
-    def __init__(self, cfg: Config):
+    def __init__(self, cfg: Config, orthogonal: OrthogonalOptions | None = None):
+        """``orthogonal`` given: the restatement of OrthogonalTripletSeedingAlgorithm instead."""
         self._h = C.c_void_p()
         self._cfg = cfg
-        rc = lib().oracle_create(C.byref(cfg), C.byref(self._h))
+        self._orth = orthogonal
+        if orthogonal is not None:
+            rc = lib().oracle_create_orthogonal(C.byref(cfg), C.byref(orthogonal), C.byref(self._h))
+        else:
+            rc = lib().oracle_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
             raise OracleError(rc, lib().oracle_last_error().decode())
 
@@ -182,7 +195,17 @@ class Oracle:
             hist = np.zeros(96, np.uint64)
             lib().oracle_result_histograms(res, _p(hist))
             out["histograms"] = {"bottoms/128": hist[:32].copy(), "tops/128": hist[32:64].copy(), "candPerRound/32": hist[64:].copy()}
-            if want_grid or dump_doublets:
+            if self._orth is not None:
+                order = np.zeros(int(lib().oracle_result_tree_order(res, None)), np.uint32)
+                lib().oracle_result_tree_order(res, _p(order))
+                out["tree_order"] = order
+                ng = lib().oracle_result_grid_size(res)
+                core = {"copiedFromIndex": np.zeros(ng, np.uint32), "binBegin": np.zeros(0, np.uint32), "binEnd": np.zeros(0, np.uint32)}
+                for k in ("x", "y", "z", "r", "varZ", "varR"):
+                    core[k] = np.zeros(ng, np.float32)
+                lib().oracle_result_grid(res, *[_p(core[k]) for k in ("copiedFromIndex", "x", "y", "z", "r", "varZ", "varR", "binBegin", "binEnd")])
+                out["core"] = core
+            elif want_grid or dump_doublets:
                 ng = lib().oracle_result_grid_size(res)
                 nb = self.info().nGlobalBins
                 g = {"copiedFromIndex": np.zeros(ng, np.uint32)}

@@ -13,7 +13,7 @@ import subprocess
 
 import numpy as np
 
-from acts_b200.config import Config
+from acts_b200.config import Config, OrthogonalOptions
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_ref", "libseeding_ref.so")
@@ -44,6 +44,7 @@ def lib():
         L = C.CDLL(_LIB_PATH)
         L.ref_last_error.restype = C.c_char_p
         L.ref_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+        L.ref_create_orthogonal.argtypes = [C.POINTER(Config), C.POINTER(OrthogonalOptions), C.POINTER(C.c_void_p)]
         L.ref_destroy.argtypes = [C.c_void_p]
         L.ref_run.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 6 + [C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
         L.ref_result_num_seeds.argtypes = [C.c_void_p]
@@ -69,11 +70,15 @@ def _p(a):
 class Reference:
     """The reference algorithm object.  ``cfg.useVertexZCuts`` configures ``inputVertices``."""
 
-    def __init__(self, cfg: Config):
+    def __init__(self, cfg: Config, orthogonal: OrthogonalOptions | None = None):
+        """``orthogonal`` given: the reference's OrthogonalTripletSeedingAlgorithm instead."""
         self._h = C.c_void_p()
         self._cfg = cfg  # keeps the arrays the struct points to alive
-        self._with_vertices = bool(cfg.useVertexZCuts)
-        rc = lib().ref_create(C.byref(cfg), C.byref(self._h))
+        self._with_vertices = bool(cfg.useVertexZCuts) and orthogonal is None
+        if orthogonal is not None:
+            rc = lib().ref_create_orthogonal(C.byref(cfg), C.byref(orthogonal), C.byref(self._h))
+        else:
+            rc = lib().ref_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
             raise ReferenceError_(rc, lib().ref_last_error().decode())
 

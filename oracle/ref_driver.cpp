@@ -7,6 +7,8 @@
 // the reference's own translation units, compiled where they lie under
 // /root/reference, nothing copied:
 //   Examples/Algorithms/TrackFinding/src/GridTripletSeedingAlgorithm.cpp   (the boundary, execute())
+//   Examples/Algorithms/TrackFinding/src/OrthogonalTripletSeedingAlgorithm.cpp + Core/src/Seeding/
+//                     CylindricalSpacePointKDTree.cpp + Core/src/Geometry/Extent.cpp (the k-d-tree seeder)
 //   Core/src/Seeding/{DoubletSeedFinder,TripletSeedFinder,BroadTripletSeedFilter,TripletSeeder,
 //                     CylindricalSpacePointGrid}.cpp, Core/src/Seeding/detail/{CandidatesForMiddleSp,
 //                     SpacePointGridPhiBinning}.cpp
@@ -34,6 +36,7 @@
 #include "ActsExamples/Framework/IAlgorithm.hpp"
 #include "ActsExamples/Framework/WhiteBoard.hpp"
 #include "ActsExamples/TrackFinding/GridTripletSeedingAlgorithm.hpp"
+#include "ActsExamples/TrackFinding/OrthogonalTripletSeedingAlgorithm.hpp"
 
 #include <atomic>
 #include <cmath>
@@ -149,8 +152,64 @@ Algorithm::Config toConfig(const b200seed_config& c) {
   return o;
 }
 
+// OrthogonalTripletSeedingAlgorithm::Config from the shared b200seed_config fields + the three extra members
+ActsExamples::OrthogonalTripletSeedingAlgorithm::Config toOrthogonalConfig(const b200seed_config& c,
+                                                                           const b200seed_orthogonal_options& x) {
+  ActsExamples::OrthogonalTripletSeedingAlgorithm::Config o;
+  o.inputSpacePoints = "spacepoints";
+  o.outputSeeds = "seeds";
+  o.bFieldInZ = c.bFieldInZ;
+  o.minPt = c.minPt;
+  o.cotThetaMax = c.cotThetaMax;
+  o.impactMax = c.impactMax;
+  o.deltaRMin = c.deltaRMin;
+  o.deltaRMax = c.deltaRMax;
+  o.deltaRMinTop = c.deltaRMinTop;
+  o.deltaRMaxTop = c.deltaRMaxTop;
+  o.deltaRMinBottom = c.deltaRMinBottom;
+  o.deltaRMaxBottom = c.deltaRMaxBottom;
+  o.rMin = c.rMin;
+  o.rMax = c.rMax;
+  o.zMin = c.zMin;
+  o.zMax = c.zMax;
+  o.phiMin = c.phiMin;
+  o.phiMax = c.phiMax;
+  o.rMinMiddle = c.rMinMiddle;
+  o.rMaxMiddle = c.rMaxMiddle;
+  o.useVariableMiddleSPRange = c.useVariableMiddleSPRange != 0;
+  o.deltaRMiddleMinSPRange = c.deltaRMiddleMinSPRange;
+  o.deltaRMiddleMaxSPRange = c.deltaRMiddleMaxSPRange;
+  o.zOutermostLayers = {x.zOutermostLayersMin, x.zOutermostLayersMax};
+  o.deltaZMin = c.deltaZMin;
+  o.deltaZMax = c.deltaZMax;
+  o.deltaPhiMax = x.deltaPhiMax;
+  o.interactionPointCut = c.interactionPointCut != 0;
+  o.collisionRegionMin = c.collisionRegionMin;
+  o.collisionRegionMax = c.collisionRegionMax;
+  o.helixCutTolerance = c.helixCutTolerance;
+  o.sigmaScattering = c.sigmaScattering;
+  o.radLengthPerSeed = c.radLengthPerSeed;
+  o.toleranceParam = c.toleranceParam;
+  o.deltaInvHelixDiameter = c.deltaInvHelixDiameter;
+  o.compatSeedWeight = c.compatSeedWeight;
+  o.impactWeightFactor = c.impactWeightFactor;
+  o.zOriginWeightFactor = c.zOriginWeightFactor;
+  o.maxSeedsPerSpM = c.maxSeedsPerSpM;
+  o.compatSeedLimit = static_cast<std::size_t>(c.compatSeedLimit);
+  o.seedWeightIncrement = c.seedWeightIncrement;
+  o.numSeedIncrement = c.numSeedIncrement;
+  o.seedConfirmation = c.seedConfirmation != 0;
+  o.centralSeedConfirmationRange = toRange(c.centralSeedConfirmationRange);
+  o.forwardSeedConfirmationRange = toRange(c.forwardSeedConfirmationRange);
+  o.maxSeedsPerSpMConf = c.maxSeedsPerSpMConf;
+  o.maxQualitySeedsPerSpMConf = c.maxQualitySeedsPerSpMConf;
+  o.useDeltaRinsteadOfTopRadius = c.useDeltaRinsteadOfTopRadius != 0;
+  o.useExtraCuts = c.useExtraCuts != 0;
+  return o;
+}
+
 struct RefHandle {
-  std::unique_ptr<Algorithm> algorithm;
+  std::unique_ptr<ActsExamples::IAlgorithm> algorithm;
   std::unique_ptr<Harness> harness;
   bool withVertices = false;
 };
@@ -194,6 +253,19 @@ int ref_create(const b200seed_config* cfg, void** out) {
     h->algorithm = std::make_unique<Algorithm>(toConfig(*cfg),
                                                Acts::getDefaultLogger("GridTripletSeeding", Acts::Logging::WARNING));
     h->harness = std::make_unique<Harness>("spacepoints", h->withVertices ? "vertices" : "", "seeds");
+  });
+  if (rc == B200SEED_OK) *out = h.release();
+  return rc;
+}
+
+// The reference's OrthogonalTripletSeedingAlgorithm (k-d-tree candidate provider); used with ref_run like a grid handle.
+int ref_create_orthogonal(const b200seed_config* cfg, const b200seed_orthogonal_options* opt, void** out) {
+  *out = nullptr;
+  auto h = std::make_unique<RefHandle>();
+  const int rc = guarded([&] {
+    h->algorithm = std::make_unique<ActsExamples::OrthogonalTripletSeedingAlgorithm>(
+        toOrthogonalConfig(*cfg, *opt), Acts::getDefaultLogger("OrthogonalTripletSeeding", Acts::Logging::WARNING));
+    h->harness = std::make_unique<Harness>("spacepoints", "", "seeds");
   });
   if (rc == B200SEED_OK) *out = h.release();
   return rc;

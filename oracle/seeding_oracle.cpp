@@ -6,13 +6,13 @@
 // timed CPU baseline of bench.py; the product (acts_b200/csrc) never links,
 // imports or calls it.
 //
-// PARITY STATUS: *unpinned by reference fixtures*.  The reference holds no
-// golden vector / KAT for this path (only SHA hashes of ROOT files of a full
-// simulation chain, Python/Examples/tests/root_file_hashes.txt:6-9) and cannot
-// be compiled here (needs Eigen, Boost, TBB).  The restatement is
-// defended by line-by-line traceability (citations below, paths relative to the
-// ACTS tree), by the worked constants of the canonical configuration, by
-// hand-checkable micro cases and by self-consistency properties (tests/).
+// PARITY STATUS: *pinned to the reference itself*.  The reference holds no golden
+// vector / KAT for this path, but its unmodified sources compile in this container
+// against stand-in third-party headers (oracle/Makefile target `ref`, oracle/_ref);
+// tests/test_reference_pin.py runs the same inputs through the reference's own
+// execute() and through this restatement and demands bit-identical seeds in the same
+// order (canonical configurations, the verbatim ITk configuration, fuzzed
+// configurations, vertex windows, tie storms, full-size events, the orthogonal seeder).
 //
 // Arithmetic contract: every cut is IEEE binary32, evaluated in the reference's
 // operation order, compiled WITHOUT fma contraction and without -march (the
@@ -143,6 +143,35 @@ void completeNavigation(std::vector<std::size_t>& bins, std::size_t nBins,
   }
 }
 
+// derived constants of the doublet / triplet finders
+void deriveFinderConstants(Setup& s) {
+  const b200seed_config& c = s.cfg;
+  // DoubletSeedFinder.cpp:351-357
+  {
+    const float pTPerHelixRadius = c.bFieldInZ;
+    s.minHelixDiameter2Doublet =
+        squaref(c.minPt * 2 / pTPerHelixRadius) * c.helixCutTolerance;
+  }
+  // TripletSeedFinder.cpp:456-481
+  {
+    const double xOverX0 = c.radLengthPerSeed;
+    const double q2OverBeta2 = 1;
+    const double t = std::sqrt(xOverX0 * q2OverBeta2);
+    // 13.6_MeV: UnitConstants::MeV (double 1e-3) * 13.6L (Units.hpp:149,181-184)
+    const double e136 = static_cast<double>(1e-3 * 13.6L);
+    s.highland =
+        static_cast<float>(e136 * t * (1.0 + 0.038 * 2 * std::log(t)));
+    const float maxScatteringAngle = s.highland / c.minPt;
+    const float maxScatteringAngle2 = maxScatteringAngle * maxScatteringAngle;
+    const float pTPerHelixRadius = c.bFieldInZ;
+    s.minHelixDiameter2 =
+        squaref(c.minPt * 2 / pTPerHelixRadius) * c.helixCutTolerance;
+    const float pT2perRadius = squaref(s.highland / pTPerHelixRadius);
+    s.sigmapT2perRadius = pT2perRadius * squaref(2 * c.sigmaScattering);
+    s.multipleScattering2 = maxScatteringAngle2 * squaref(c.sigmaScattering);
+  }
+}
+
 Setup makeSetup(const b200seed_config& c) {
   Setup s;
   s.cfg = c;
@@ -245,30 +274,7 @@ Setup makeSetup(const b200seed_config& c) {
   s.dRMaxB = std::isnan(c.deltaRMaxBottom) ? c.deltaRMax : c.deltaRMaxBottom;
   s.dRMinT = std::isnan(c.deltaRMinTop) ? c.deltaRMin : c.deltaRMinTop;
   s.dRMaxT = std::isnan(c.deltaRMaxTop) ? c.deltaRMax : c.deltaRMaxTop;
-  // DoubletSeedFinder.cpp:351-357
-  {
-    const float pTPerHelixRadius = c.bFieldInZ;
-    s.minHelixDiameter2Doublet =
-        squaref(c.minPt * 2 / pTPerHelixRadius) * c.helixCutTolerance;
-  }
-  // TripletSeedFinder.cpp:456-481
-  {
-    const double xOverX0 = c.radLengthPerSeed;
-    const double q2OverBeta2 = 1;
-    const double t = std::sqrt(xOverX0 * q2OverBeta2);
-    // 13.6_MeV: UnitConstants::MeV (double 1e-3) * 13.6L (Units.hpp:149,181-184)
-    const double e136 = static_cast<double>(1e-3 * 13.6L);
-    s.highland =
-        static_cast<float>(e136 * t * (1.0 + 0.038 * 2 * std::log(t)));
-    const float maxScatteringAngle = s.highland / c.minPt;
-    const float maxScatteringAngle2 = maxScatteringAngle * maxScatteringAngle;
-    const float pTPerHelixRadius = c.bFieldInZ;
-    s.minHelixDiameter2 =
-        squaref(c.minPt * 2 / pTPerHelixRadius) * c.helixCutTolerance;
-    const float pT2perRadius = squaref(s.highland / pTPerHelixRadius);
-    s.sigmapT2perRadius = pT2perRadius * squaref(2 * c.sigmaScattering);
-    s.multipleScattering2 = maxScatteringAngle2 * squaref(c.sigmaScattering);
-  }
+  deriveFinderConstants(s);
   return s;
 }
 
@@ -619,6 +625,105 @@ bool doubletExperimentCut(const Event& ev, DoubletCuts kind, Index m, Index o,
   return false;
 }
 
+// One candidate of DoubletSeedFinder.cpp:41-273 after the deltaR window logic: the cuts of :137-271 and the
+// coordinate transform; appends to `out` when the candidate survives.
+template <bool isBottom>
+inline void doubletCandidate(Event& ev, DoubletCuts cuts, Index m, const MiddleInfo& mi, Index o,
+                             float deltaR, Doublets& out) {
+  const Setup& s = *ev.s;
+  const b200seed_config& c = s.cfg;
+  const Packed& p = ev.sp;
+  const float impactMax = isBottom ? -c.impactMax : c.impactMax;
+  const float xM = p.x[m];
+  const float yM = p.y[m];
+  const float zM = p.z[m];
+  const float rM = p.r[m];
+  const float varianceZM = p.varZ[m];
+  const float varianceRM = p.varR[m];
+  const float vIPAbs = impactMax * mi.uIP2;
+  const auto calculateError = [&](float varianceZO, float varianceRO,
+                                  float iDeltaR2, float cotTheta) {
+    return iDeltaR2 * ((varianceZM + varianceZO) +
+                       (cotTheta * cotTheta) * (varianceRM + varianceRO));
+  };
+  const float xO = p.x[o];
+  const float yO = p.y[o];
+  const float zO = p.z[o];
+  const float varianceZO = p.varZ[o];
+  const float varianceRO = p.varR[o];
+  ++ev.cnt.nPairTests;
+
+  float deltaZ = 0;
+  if constexpr (isBottom) {
+    deltaZ = zM - zO;
+  } else {
+    deltaZ = zO - zM;
+  }
+  if (outsideRange(deltaZ, c.deltaZMin, c.deltaZMax)) return;
+
+  const float zOriginTimesDeltaR = zM * deltaR - rM * deltaZ;
+  if (outsideRange(zOriginTimesDeltaR, c.collisionRegionMin * deltaR,
+                   c.collisionRegionMax * deltaR)) {
+    return;
+  }
+
+  if (!c.interactionPointCut) {
+    if (outsideRange(deltaZ, -c.cotThetaMax * deltaR, c.cotThetaMax * deltaR)) {
+      return;
+    }
+    const float deltaX = xO - xM;
+    const float deltaY = yO - yM;
+    const float xNewFrame = deltaX * mi.cosPhiM + deltaY * mi.sinPhiM;
+    const float yNewFrame = deltaY * mi.cosPhiM - deltaX * mi.sinPhiM;
+    const float deltaR2 = deltaX * deltaX + deltaY * deltaY;
+    const float iDeltaR2 = 1 / deltaR2;
+    const float uT = xNewFrame * iDeltaR2;
+    const float vT = yNewFrame * iDeltaR2;
+    const float iDeltaR = std::sqrt(iDeltaR2);
+    const float cotTheta = deltaZ * iDeltaR;
+    if (cuts != DoubletCuts::None) {
+      if (!doubletExperimentCut(ev, cuts, m, o, cotTheta, isBottom)) return;
+    }
+    const float er = calculateError(varianceZO, varianceRO, iDeltaR2, cotTheta);
+    out.sp.push_back(o); out.cotTheta.push_back(cotTheta);
+    out.er.push_back(er); out.iDeltaR.push_back(iDeltaR);
+    out.u.push_back(uT); out.v.push_back(vT);
+    out.x.push_back(xNewFrame); out.y.push_back(yNewFrame);
+    return;
+  }
+
+  // interactionPointCut == true, :205-271
+  const float deltaX = xO - xM;
+  const float deltaY = yO - yM;
+  const float xNewFrame = deltaX * mi.cosPhiM + deltaY * mi.sinPhiM;
+  const float yNewFrame = deltaY * mi.cosPhiM - deltaX * mi.sinPhiM;
+  const float deltaR2 = deltaX * deltaX + deltaY * deltaY;
+  const float iDeltaR2 = 1 / deltaR2;
+  const float uT = xNewFrame * iDeltaR2;
+  const float vT = yNewFrame * iDeltaR2;
+  if (std::abs(rM * yNewFrame) > impactMax * xNewFrame) {
+    const float vIP = (yNewFrame > 0) ? -vIPAbs : vIPAbs;
+    const float aCoef = (vT - vIP) / (uT - mi.uIP);
+    const float bCoef = vIP - aCoef * mi.uIP;
+    if ((bCoef * bCoef) * s.minHelixDiameter2Doublet > 1 + aCoef * aCoef) {
+      return;
+    }
+  }
+  if (outsideRange(deltaZ, -c.cotThetaMax * deltaR, c.cotThetaMax * deltaR)) {
+    return;
+  }
+  const float iDeltaR = std::sqrt(iDeltaR2);
+  const float cotTheta = deltaZ * iDeltaR;
+  if (cuts != DoubletCuts::None) {
+    if (!doubletExperimentCut(ev, cuts, m, o, cotTheta, isBottom)) return;
+  }
+  const float er = calculateError(varianceZO, varianceRO, iDeltaR2, cotTheta);
+  out.sp.push_back(o); out.cotTheta.push_back(cotTheta);
+  out.er.push_back(er); out.iDeltaR.push_back(iDeltaR);
+  out.u.push_back(uT); out.v.push_back(vT);
+  out.x.push_back(xNewFrame); out.y.push_back(yNewFrame);
+}
+
 // DoubletSeedFinder.cpp:41-273 for sortedByR = true.  [begin,end) is the
 // caller's persistent candidate range; begin is advanced like
 // `candidateSps = candidateSps.subrange(offset)`.
@@ -626,26 +731,10 @@ template <bool isBottom>
 void createDoublets(Event& ev, DoubletCuts cuts, Index m, const MiddleInfo& mi,
                     Index& begin, Index end, Doublets& out) {
   const Setup& s = *ev.s;
-  const b200seed_config& c = s.cfg;
   const Packed& p = ev.sp;
   const float cfgDeltaRMin = isBottom ? s.dRMinB : s.dRMinT;
   const float cfgDeltaRMax = isBottom ? s.dRMaxB : s.dRMaxT;
-  const float impactMax = isBottom ? -c.impactMax : c.impactMax;
-
-  const float xM = p.x[m];
-  const float yM = p.y[m];
-  const float zM = p.z[m];
   const float rM = p.r[m];
-  const float varianceZM = p.varZ[m];
-  const float varianceRM = p.varR[m];
-
-  const float vIPAbs = impactMax * mi.uIP2;
-
-  const auto calculateError = [&](float varianceZO, float varianceRO,
-                                  float iDeltaR2, float cotTheta) {
-    return iDeltaR2 * ((varianceZM + varianceZO) +
-                       (cotTheta * cotTheta) * (varianceRM + varianceRO));
-  };
 
   // :73-93
   {
@@ -662,13 +751,7 @@ void createDoublets(Event& ev, DoubletCuts cuts, Index m, const MiddleInfo& mi,
   }
 
   for (Index o = begin; o < end; ++o) {
-    const float xO = p.x[o];
-    const float yO = p.y[o];
-    const float zO = p.z[o];
     const float rO = p.r[o];
-    const float varianceZO = p.varZ[o];
-    const float varianceRO = p.varR[o];
-
     float deltaR = 0;
     if constexpr (isBottom) {
       deltaR = rM - rO;
@@ -677,77 +760,30 @@ void createDoublets(Event& ev, DoubletCuts cuts, Index m, const MiddleInfo& mi,
       deltaR = rO - rM;
       if (deltaR > cfgDeltaRMax) break;
     }
-    ++ev.cnt.nPairTests;
+    doubletCandidate<isBottom>(ev, cuts, m, mi, o, deltaR, out);
+  }
+}
 
-    float deltaZ = 0;
+// DoubletSeedFinder.cpp:41-273 for sortedByR = false (spacePointsSortedByRadius = false, the orthogonal
+// seeder): every candidate of the subset is tested, the deltaR window is an explicit cut (:126-130).
+template <bool isBottom>
+void createDoubletsUnsorted(Event& ev, DoubletCuts cuts, Index m, const MiddleInfo& mi,
+                            const std::vector<Index>& candidates, Doublets& out) {
+  const Setup& s = *ev.s;
+  const Packed& p = ev.sp;
+  const float cfgDeltaRMin = isBottom ? s.dRMinB : s.dRMinT;
+  const float cfgDeltaRMax = isBottom ? s.dRMaxB : s.dRMaxT;
+  const float rM = p.r[m];
+  for (Index o : candidates) {
+    const float rO = p.r[o];
+    float deltaR = 0;
     if constexpr (isBottom) {
-      deltaZ = zM - zO;
+      deltaR = rM - rO;
     } else {
-      deltaZ = zO - zM;
+      deltaR = rO - rM;
     }
-    if (outsideRange(deltaZ, c.deltaZMin, c.deltaZMax)) continue;
-
-    const float zOriginTimesDeltaR = zM * deltaR - rM * deltaZ;
-    if (outsideRange(zOriginTimesDeltaR, c.collisionRegionMin * deltaR,
-                     c.collisionRegionMax * deltaR)) {
-      continue;
-    }
-
-    if (!c.interactionPointCut) {
-      if (outsideRange(deltaZ, -c.cotThetaMax * deltaR, c.cotThetaMax * deltaR)) {
-        continue;
-      }
-      const float deltaX = xO - xM;
-      const float deltaY = yO - yM;
-      const float xNewFrame = deltaX * mi.cosPhiM + deltaY * mi.sinPhiM;
-      const float yNewFrame = deltaY * mi.cosPhiM - deltaX * mi.sinPhiM;
-      const float deltaR2 = deltaX * deltaX + deltaY * deltaY;
-      const float iDeltaR2 = 1 / deltaR2;
-      const float uT = xNewFrame * iDeltaR2;
-      const float vT = yNewFrame * iDeltaR2;
-      const float iDeltaR = std::sqrt(iDeltaR2);
-      const float cotTheta = deltaZ * iDeltaR;
-      if (cuts != DoubletCuts::None) {
-        if (!doubletExperimentCut(ev, cuts, m, o, cotTheta, isBottom)) continue;
-      }
-      const float er = calculateError(varianceZO, varianceRO, iDeltaR2, cotTheta);
-      out.sp.push_back(o); out.cotTheta.push_back(cotTheta);
-      out.er.push_back(er); out.iDeltaR.push_back(iDeltaR);
-      out.u.push_back(uT); out.v.push_back(vT);
-      out.x.push_back(xNewFrame); out.y.push_back(yNewFrame);
-      continue;
-    }
-
-    // interactionPointCut == true, :205-271
-    const float deltaX = xO - xM;
-    const float deltaY = yO - yM;
-    const float xNewFrame = deltaX * mi.cosPhiM + deltaY * mi.sinPhiM;
-    const float yNewFrame = deltaY * mi.cosPhiM - deltaX * mi.sinPhiM;
-    const float deltaR2 = deltaX * deltaX + deltaY * deltaY;
-    const float iDeltaR2 = 1 / deltaR2;
-    const float uT = xNewFrame * iDeltaR2;
-    const float vT = yNewFrame * iDeltaR2;
-    if (std::abs(rM * yNewFrame) > impactMax * xNewFrame) {
-      const float vIP = (yNewFrame > 0) ? -vIPAbs : vIPAbs;
-      const float aCoef = (vT - vIP) / (uT - mi.uIP);
-      const float bCoef = vIP - aCoef * mi.uIP;
-      if ((bCoef * bCoef) * s.minHelixDiameter2Doublet > 1 + aCoef * aCoef) {
-        continue;
-      }
-    }
-    if (outsideRange(deltaZ, -c.cotThetaMax * deltaR, c.cotThetaMax * deltaR)) {
-      continue;
-    }
-    const float iDeltaR = std::sqrt(iDeltaR2);
-    const float cotTheta = deltaZ * iDeltaR;
-    if (cuts != DoubletCuts::None) {
-      if (!doubletExperimentCut(ev, cuts, m, o, cotTheta, isBottom)) continue;
-    }
-    const float er = calculateError(varianceZO, varianceRO, iDeltaR2, cotTheta);
-    out.sp.push_back(o); out.cotTheta.push_back(cotTheta);
-    out.er.push_back(er); out.iDeltaR.push_back(iDeltaR);
-    out.u.push_back(uT); out.v.push_back(vT);
-    out.x.push_back(xNewFrame); out.y.push_back(yNewFrame);
+    if (outsideRange(deltaR, cfgDeltaRMin, cfgDeltaRMax)) continue;
+    doubletCandidate<isBottom>(ev, cuts, m, mi, o, deltaR, out);
   }
 }
 
@@ -1045,25 +1081,19 @@ void filterTripletsMiddleFixed(Event& ev) {
   }
 }
 
-// TripletSeeder.cpp:44-107 (+ createAndFilterTriplets :21-42)
-void seedsForMiddle(Event& ev, DoubletCuts cuts, Index m,
-                    std::vector<std::pair<Index, Index>>& bottomRanges,
-                    std::vector<std::pair<Index, Index>>& topRanges) {
+// TripletSeeder.cpp:44-107 (+ createAndFilterTriplets :21-42).  `makeTops` / `makeBottoms` fill the doublet
+// containers from the candidate groups of the caller (grid bins or k-d-tree subsets).
+template <typename MakeTops, typename MakeBottoms>
+void seedsForMiddleT(Event& ev, Index m, MakeTops&& makeTops, MakeBottoms&& makeBottoms) {
   const MiddleInfo mi = computeMiddleInfo(ev.sp, m);
   ++ev.cnt.nMiddles;
 
   ev.topDoublets.clear();
-  for (auto& rng : topRanges) {
-    createDoublets<false>(ev, cuts, m, mi, rng.first, rng.second, ev.topDoublets);
-  }
+  makeTops(mi, ev.topDoublets);
   if (ev.dump != nullptr) {
     // stage-level parity needs both lists even when the reference returns early
     ev.bottomDoublets.clear();
-    auto copy = bottomRanges;
-    for (auto& rng : copy) {
-      createDoublets<true>(ev, cuts, m, mi, rng.first, rng.second, ev.bottomDoublets);
-    }
-    ev.cnt.nPairTests -= 0;  // counters are not meaningful in dump mode
+    makeBottoms(mi, ev.bottomDoublets, true);
     DoubletDump& d = *ev.dump;
     d.middlePos.push_back(m);
     d.nBottom.push_back(static_cast<Index>(ev.bottomDoublets.size()));
@@ -1085,9 +1115,7 @@ void seedsForMiddle(Event& ev, DoubletCuts cuts, Index m,
   if (!sufficientTopDoublets(ev, m)) return;
 
   ev.bottomDoublets.clear();
-  for (auto& rng : bottomRanges) {
-    createDoublets<true>(ev, cuts, m, mi, rng.first, rng.second, ev.bottomDoublets);
-  }
+  makeBottoms(mi, ev.bottomDoublets, false);
   if (ev.bottomDoublets.empty()) return;
 
   ev.cnt.nBottomDoublets += ev.bottomDoublets.size();
@@ -1132,6 +1160,25 @@ void seedsForMiddle(Event& ev, DoubletCuts cuts, Index m,
   ev.cnt.maxCandidatesPerMiddle = std::max(ev.cnt.maxCandidatesPerMiddle, candThisMiddle);
   ev.cnt.histCandRound[std::min<std::uint64_t>(31, candThisRound / 32)]++;
   filterTripletsMiddleFixed(ev);
+}
+
+// the grid algorithm's groups: r-sorted bin ranges, advanced in place (DoubletSeedFinder.cpp:73-93)
+void seedsForMiddle(Event& ev, DoubletCuts cuts, Index m,
+                    std::vector<std::pair<Index, Index>>& bottomRanges,
+                    std::vector<std::pair<Index, Index>>& topRanges) {
+  seedsForMiddleT(
+      ev, m,
+      [&](const MiddleInfo& mi, Doublets& out) {
+        for (auto& rng : topRanges) createDoublets<false>(ev, cuts, m, mi, rng.first, rng.second, out);
+      },
+      [&](const MiddleInfo& mi, Doublets& out, bool forDump) {
+        if (forDump) {  // the dump must not advance the persistent ranges
+          auto copy = bottomRanges;
+          for (auto& rng : copy) createDoublets<true>(ev, cuts, m, mi, rng.first, rng.second, out);
+        } else {
+          for (auto& rng : bottomRanges) createDoublets<true>(ev, cuts, m, mi, rng.first, rng.second, out);
+        }
+      });
 }
 
 // GridTripletSeedingAlgorithm.cpp:404-421
@@ -1234,6 +1281,354 @@ void runEvent(Event& ev) {
   }
 }
 
+// ===========================================================================
+// OrthogonalTripletSeedingAlgorithm (Examples/Algorithms/TrackFinding/src/
+// OrthogonalTripletSeedingAlgorithm.cpp:62-317): the same doublet / triplet / filter
+// stages behind a k-d-tree candidate provider.
+// ===========================================================================
+namespace orth {
+
+constexpr std::size_t kDims = 3;      // CylindricalSpacePointKDTree.hpp:33-36 (phi, r, z)
+constexpr std::size_t kLeafSize = 4;  // CylindricalSpacePointKDTree.hpp:42
+enum Dim { DimPhi = 0, DimR = 1, DimZ = 2 };
+
+using Coord = std::array<float, kDims>;
+using Pair = std::pair<Coord, Index>;  // KDTree::pair_t
+
+// RangeXD<3, float> (Core/include/Acts/Utilities/RangeXD.hpp): semi-open [min, max) per dimension
+struct Range {
+  float mn[kDims], mx[kDims];
+  Range() {  // RangeXD():  lowest .. max
+    for (std::size_t i = 0; i < kDims; ++i) {
+      mn[i] = std::numeric_limits<float>::lowest();
+      mx[i] = std::numeric_limits<float>::max();
+    }
+  }
+  void shrinkMin(std::size_t i, float v) { mn[i] = std::max(mn[i], v); }
+  void shrinkMax(std::size_t i, float v) { mx[i] = std::min(mx[i], v); }
+  void shrink(std::size_t i, float lo, float hi) { shrinkMin(i, lo); shrinkMax(i, hi); }
+  bool degenerate() const {
+    for (std::size_t i = 0; i < kDims; ++i) if (mn[i] >= mx[i]) return true;
+    return false;
+  }
+  bool contains(const Coord& v) const {
+    for (std::size_t i = 0; i < kDims; ++i) if (!(mn[i] <= v[i] && v[i] < mx[i])) return false;
+    return true;
+  }
+  bool covers(const Range& o) const {  // operator>=
+    for (std::size_t i = 0; i < kDims; ++i) if (!(mn[i] <= o.mn[i] && mx[i] >= o.mx[i])) return false;
+    return true;
+  }
+  bool intersects(const Range& r) const {  // operator&&
+    for (std::size_t i = 0; i < kDims; ++i) if (!(mn[i] < r.mx[i] && r.mn[i] < mx[i])) return false;
+    return true;
+  }
+};
+
+// KDTree<3, SpacePointIndex, float, std::array, 4> (Core/include/Acts/Utilities/KDTree.hpp:40-503): nodes hold
+// [begin, end) of the one element vector, which the constructors permute in place.
+struct Node {
+  std::size_t begin = 0, end = 0;
+  bool internal = false;
+  Range range;
+  int lhs = -1, rhs = -1;
+};
+struct Tree {
+  std::vector<Pair> elems;
+  std::vector<Node> nodes;
+
+  static Range boundingBox(const std::vector<Pair>& e, std::size_t b, std::size_t en) {  // :236-264
+    Coord mn{}, mx{};
+    for (std::size_t i = 0; i < kDims; ++i) {
+      mn[i] = std::numeric_limits<float>::max();
+      mx[i] = std::numeric_limits<float>::lowest();
+    }
+    for (std::size_t i = b; i != en; ++i) {
+      for (std::size_t j = 0; j < kDims; ++j) {
+        mn[j] = std::min(mn[j], e[i].first[j]);
+        mx[j] = std::max(mx[j], e[i].first[j]);
+      }
+    }
+    Range r;
+    for (std::size_t j = 0; j < kDims; ++j) {
+      r.mn[j] = mn[j];
+      r.mx[j] = std::nextafter(mx[j], std::numeric_limits<float>::max());  // nextRepresentable, :222-234
+    }
+    return r;
+  }
+
+  // KDTreeNode constructor, :271-350
+  int build(std::size_t b, std::size_t e, bool internal, std::size_t d) {
+    const int id = static_cast<int>(nodes.size());
+    nodes.emplace_back();
+    nodes[id].begin = b;
+    nodes[id].end = e;
+    nodes[id].internal = internal;
+    nodes[id].range = boundingBox(elems, b, e);
+    if (!internal) return id;
+    constexpr std::size_t maxExactMedian = 128;
+    const auto first = elems.begin() + static_cast<std::ptrdiff_t>(b);
+    const auto last = elems.begin() + static_cast<std::ptrdiff_t>(e);
+    auto pivot = first;
+    if (e - b > maxExactMedian) {
+      const float mid = static_cast<float>(0.5) * (nodes[id].range.mx[d] + nodes[id].range.mn[d]);
+      pivot = std::partition(first, last, [=](const Pair& i) { return i.first[d] < mid; });
+    } else {
+      std::sort(first, last, [d](const Pair& a, const Pair& bb) { return a.first[d] < bb.first[d]; });
+      pivot = first + (std::distance(first, last) / 2);
+    }
+    if (pivot == first || pivot == std::prev(last)) {
+      pivot = std::next(first, kLeafSize);
+    }
+    const std::size_t p = static_cast<std::size_t>(pivot - elems.begin());
+    const std::size_t lhsSize = p - b, rhsSize = e - p;
+    const int l = build(b, p, lhsSize > kLeafSize, (d + 1) % kDims);
+    nodes[id].lhs = l;
+    const int r = build(p, e, rhsSize > kLeafSize, (d + 1) % kDims);
+    nodes[id].rhs = r;
+    return id;
+  }
+  void construct() {  // KDTree(vector_t&&), :66-80
+    nodes.clear();
+    nodes.reserve(elems.size());
+    build(0, elems.size(), elems.size() > kLeafSize, 0);
+  }
+
+  // KDTreeNode::rangeSearchMapDiscard, :352-396
+  void search(int id, const Range& r, std::vector<Index>& out) const {
+    const Node& n = nodes[static_cast<std::size_t>(id)];
+    const bool contained = r.covers(n.range);
+    if (n.internal) {
+      if (contained) {
+        for (std::size_t i = n.begin; i != n.end; ++i) out.push_back(elems[i].second);
+        return;
+      }
+      if (nodes[static_cast<std::size_t>(n.lhs)].range.intersects(r)) search(n.lhs, r, out);
+      if (nodes[static_cast<std::size_t>(n.rhs)].range.intersects(r)) search(n.rhs, r, out);
+    } else {
+      for (std::size_t i = n.begin; i != n.end; ++i) {
+        if (contained || r.contains(elems[i].first)) out.push_back(elems[i].second);
+      }
+    }
+  }
+};
+
+// CylindricalSpacePointKDTree::Options (hpp:45-70)
+struct Options {
+  float rMax, zMin, zMax, phiMin, phiMax, deltaRMin, deltaRMax, collisionRegionMin, collisionRegionMax, cotThetaMax,
+      deltaPhiMax;
+  float deltaZMax = std::numeric_limits<float>::infinity();  // hpp default; the algorithm never sets it
+};
+
+// CylindricalSpacePointKDTree.cpp:17-96
+Range validTupleOrthoRangeLH(const Options& o, float pL, float rL, float zL) {
+  const float colMin = o.collisionRegionMin;
+  const float colMax = o.collisionRegionMax;
+  Range res;
+  res.shrinkMin(DimPhi, o.phiMin);
+  res.shrinkMax(DimPhi, o.phiMax);
+  res.shrinkMax(DimR, o.rMax);
+  res.shrinkMin(DimZ, o.zMin);
+  res.shrinkMax(DimZ, o.zMax);
+  res.shrinkMin(DimR, rL + o.deltaRMin);
+  res.shrinkMax(DimR, rL + o.deltaRMax);
+  const float zMax = (res.mx[DimR] / rL) * (zL - colMin) + colMin;
+  const float zMin = colMax - (res.mx[DimR] / rL) * (colMax - zL);
+  if (zL > colMin) {
+    res.shrinkMax(DimZ, zMax);
+  } else if (zL < colMax) {
+    res.shrinkMin(DimZ, zMin);
+  }
+  res.shrinkMin(DimZ, zL - o.cotThetaMax * (res.mx[DimR] - rL));
+  res.shrinkMax(DimZ, zL + o.cotThetaMax * (res.mx[DimR] - rL));
+  res.shrinkMin(DimPhi, pL - o.deltaPhiMax);
+  res.shrinkMax(DimPhi, pL + o.deltaPhiMax);
+  res.shrinkMin(DimZ, zL - o.deltaZMax);
+  res.shrinkMax(DimZ, zL + o.deltaZMax);
+  return res;
+}
+
+// CylindricalSpacePointKDTree.cpp:98-157
+Range validTupleOrthoRangeHL(const Options& o, float pM, float rM, float zM) {
+  Range res;
+  res.shrinkMin(DimPhi, o.phiMin);
+  res.shrinkMax(DimPhi, o.phiMax);
+  res.shrinkMax(DimR, o.rMax);
+  res.shrinkMin(DimZ, o.zMin);
+  res.shrinkMax(DimZ, o.zMax);
+  res.shrinkMin(DimR, rM - o.deltaRMax);
+  res.shrinkMax(DimR, rM - o.deltaRMin);
+  const float fracR = res.mn[DimR] / rM;
+  const float zMin = (zM - o.collisionRegionMin) * fracR + o.collisionRegionMin;
+  const float zMax = (zM - o.collisionRegionMax) * fracR + o.collisionRegionMax;
+  res.shrinkMin(DimZ, std::min(zMin, zM));
+  res.shrinkMax(DimZ, std::max(zMax, zM));
+  res.shrinkMin(DimPhi, pM - o.deltaPhiMax);
+  res.shrinkMax(DimPhi, pM + o.deltaPhiMax);
+  res.shrinkMin(DimZ, zM - o.deltaZMax);
+  res.shrinkMax(DimZ, zM + o.deltaZMax);
+  return res;
+}
+
+struct Candidates {  // hpp:73-93
+  std::vector<Index> bottom_lh_v, bottom_hl_v, top_lh_v, top_hl_v;
+  void clear() { bottom_lh_v.clear(); bottom_hl_v.clear(); top_lh_v.clear(); top_hl_v.clear(); }
+};
+
+// the four search boxes of one middle (CylindricalSpacePointKDTree.cpp:159-217), shared with the tests
+struct Boxes {
+  Range bottom_lh, top_lh, bottom_hl, top_hl;
+};
+Boxes searchBoxes(const Options& lh, const Options& hl, float pM, float rM, float zM) {
+  const Range bottom_r = validTupleOrthoRangeHL(hl, pM, rM, zM);
+  const Range top_r = validTupleOrthoRangeLH(lh, pM, rM, zM);
+  const float cotTheta = std::max(std::abs(zM / rM), lh.cotThetaMax);
+  const float deltaRMaxTop = top_r.mx[DimR] - rM;
+  const float deltaRMaxBottom = rM - bottom_r.mn[DimR];
+  Boxes b;
+  b.bottom_lh = bottom_r;
+  b.bottom_lh.shrink(DimZ, zM - cotTheta * deltaRMaxBottom, zM);
+  b.top_lh = top_r;
+  b.top_lh.shrink(DimZ, zM, zM + cotTheta * deltaRMaxTop);
+  b.bottom_hl = bottom_r;
+  b.bottom_hl.shrink(DimZ, zM, zM + cotTheta * deltaRMaxBottom);
+  b.top_hl = top_r;
+  b.top_hl.shrink(DimZ, zM - cotTheta * deltaRMaxTop, zM);
+  return b;
+}
+
+// CylindricalSpacePointKDTree::validTuples, .cpp:159-263
+void validTuples(const Tree& tree, const Options& lh, const Options& hl, float pM, float rM, float zM,
+                 std::size_t nTopSeedConf, Candidates& c) {
+  const Boxes b = searchBoxes(lh, hl, pM, rM, zM);
+  if (!b.bottom_lh.degenerate() && !b.top_lh.degenerate()) tree.search(0, b.top_lh, c.top_lh_v);
+  if (!b.bottom_hl.degenerate() && !b.top_hl.degenerate()) tree.search(0, b.top_hl, c.top_hl_v);
+  const bool searchBotLh = c.top_lh_v.size() >= nTopSeedConf;
+  const bool searchBotHl = c.top_hl_v.size() >= nTopSeedConf;
+  if (!c.top_lh_v.empty() && searchBotLh) tree.search(0, b.bottom_lh, c.bottom_lh_v);
+  if (!c.top_hl_v.empty() && searchBotHl) tree.search(0, b.bottom_hl, c.bottom_hl_v);
+}
+
+struct OrthOptions {
+  float zOutermostLayersMin, zOutermostLayersMax, deltaPhiMax;
+};
+
+// what the tests read back about the tree
+struct TreeDump {
+  std::vector<Index> order;  // element order after construction (= middle iteration order), core indices
+};
+
+// OrthogonalTripletSeedingAlgorithm::execute, .cpp:101-317
+void runEvent(Event& ev, const OrthOptions& oo, TreeDump* dump) {
+  const Setup& s = *ev.s;
+  const b200seed_config& c = s.cfg;
+  Packed& p = ev.sp;
+  Tree tree;
+  std::vector<float> phi;
+  double extentRMin = std::numeric_limits<double>::max(), extentRMax = std::numeric_limits<double>::lowest();
+  bool extentSet = false;
+  for (Index i = 0; i < ev.n; ++i) {
+    if (c.useExtraCuts && !itkFastTrackingSPselect(ev.r[i], ev.z[i])) continue;  // :123-127
+    const Index newIndex = static_cast<Index>(p.copiedFrom.size());
+    p.copiedFrom.push_back(i);
+    p.x.push_back(ev.x[i]); p.y.push_back(ev.y[i]); p.z.push_back(ev.z[i]); p.r.push_back(ev.r[i]);
+    p.varZ.push_back(ev.varZ[i]); p.varR.push_back(ev.varR[i]);
+    const float ph = ev.phiOverride != nullptr ? ev.phiOverride[i] : std::atan2(ev.y[i], ev.x[i]);  // :136
+    phi.push_back(ph);
+    tree.elems.push_back({Coord{ph, ev.r[i], ev.z[i]}, newIndex});  // :140, insert(index, phi, r, z)
+    // Extent::extend (Core/src/Geometry/Extent.cpp:33-56): AxisR = VectorHelpers::perp of the double vector
+    const double xd = ev.x[i], yd = ev.y[i];
+    const double perp = std::sqrt(xd * xd + yd * yd);
+    if (!extentSet) { extentRMin = perp; extentRMax = perp; extentSet = true; }
+    extentRMin = std::min(extentRMin, perp);
+    extentRMax = std::max(extentRMax, perp);
+  }
+  ev.cnt.nInGrid = p.copiedFrom.size();
+  if (tree.elems.empty()) return;  // (KDTree of an empty vector: a single empty leaf, no middle)
+  tree.construct();
+  if (dump != nullptr) for (const Pair& e : tree.elems) dump->order.push_back(e.second);
+
+  // :152-171
+  Options lh{};
+  lh.rMax = c.rMax; lh.zMin = c.zMin; lh.zMax = c.zMax; lh.phiMin = c.phiMin; lh.phiMax = c.phiMax;
+  lh.deltaRMin = std::isnan(c.deltaRMinBottom) ? c.deltaRMin : c.deltaRMinBottom;
+  lh.deltaRMax = std::isnan(c.deltaRMaxBottom) ? c.deltaRMax : c.deltaRMaxBottom;
+  lh.collisionRegionMin = c.collisionRegionMin; lh.collisionRegionMax = c.collisionRegionMax;
+  lh.cotThetaMax = c.cotThetaMax; lh.deltaPhiMax = oo.deltaPhiMax;
+  Options hl = lh;
+  hl.deltaRMin = std::isnan(c.deltaRMinTop) ? c.deltaRMin : c.deltaRMinTop;
+  hl.deltaRMax = std::isnan(c.deltaRMaxTop) ? c.deltaRMax : c.deltaRMaxTop;
+
+  // :227-232 (double arithmetic, stored in a Range1D<float>)
+  const float rMiddleMin = static_cast<float>(std::floor(extentRMin / 2) * 2 + c.deltaRMiddleMinSPRange);
+  const float rMiddleMax = static_cast<float>(std::floor(extentRMax / 2) * 2 - c.deltaRMiddleMaxSPRange);
+
+  const DoubletCuts cuts = c.useExtraCuts ? DoubletCuts::Itk : DoubletCuts::None;  // :191-193
+  ev.collector.configure(c.maxSeedsPerSpMConf, c.maxQualitySeedsPerSpMConf);
+  ev.collector.clear();
+  ev.bestSeedQualityMap.clear();
+  ev.rMaxSeedConf = 0;
+
+  Candidates cand;
+  for (const Pair& middle : tree.elems) {  // :247
+    const Index m = middle.second;
+    const float rM = p.r[m];
+    if (c.useVariableMiddleSPRange) {
+      if (rM < rMiddleMin || rM > rMiddleMax) continue;
+    } else {
+      if (rM > c.rMaxMiddle || rM < c.rMinMiddle) continue;
+    }
+    const float zM = p.z[m];
+    if (zM < oo.zOutermostLayersMin || zM > oo.zOutermostLayersMax) continue;
+    const float phiM = phi[m];
+    if (phiM > c.phiMax || phiM < c.phiMin) continue;
+
+    std::size_t nTopSeedConf = 0;
+    if (c.seedConfirmation) {  // :276-288
+      const b200seed_seed_confirmation_range& rng =
+          (zM > c.centralSeedConfirmationRange.zMaxSeedConf || zM < c.centralSeedConfirmationRange.zMinSeedConf)
+              ? c.forwardSeedConfirmationRange
+              : c.centralSeedConfirmationRange;
+      nTopSeedConf = rM > rng.rMaxSeedConf ? rng.nTopForLargeR : rng.nTopForSmallR;
+    }
+    cand.clear();
+    validTuples(tree, lh, hl, phiM, rM, zM, nTopSeedConf, cand);
+    for (int group = 0; group < 2; ++group) {  // :294-306: increasing-z candidates, then decreasing-z
+      const std::vector<Index>& bottoms = group == 0 ? cand.bottom_lh_v : cand.bottom_hl_v;
+      const std::vector<Index>& tops = group == 0 ? cand.top_lh_v : cand.top_hl_v;
+      seedsForMiddleT(
+          ev, m,
+          [&](const MiddleInfo& mi, Doublets& out) { createDoubletsUnsorted<false>(ev, cuts, m, mi, tops, out); },
+          [&](const MiddleInfo& mi, Doublets& out, bool) { createDoubletsUnsorted<true>(ev, cuts, m, mi, bottoms, out); });
+    }
+  }
+  ev.cnt.nSeeds = ev.seeds.size();
+  for (Seed& sd : ev.seeds) {  // :310-314
+    sd.b = p.copiedFrom[sd.b];
+    sd.m = p.copiedFrom[sd.m];
+    sd.t = p.copiedFrom[sd.t];
+  }
+}
+
+// the derived constants of the three finders with the orthogonal algorithm's own deltaR resolution
+// (.cpp:173-205: note the isnan tests on deltaRMax{Bottom,Top} for BOTH bounds)
+Setup makeSetup(const b200seed_config& c) {
+  Setup s;
+  s.cfg = c;
+  s.cfg.zBinNeighborsTop = s.cfg.zBinNeighborsBottom = nullptr;
+  s.cfg.zBinEdges = nullptr;
+  s.cfg.zBinsCustomLooping = nullptr;
+  s.cfg.rRangeMiddleSP = nullptr;
+  s.dRMinB = std::isnan(c.deltaRMaxBottom) ? c.deltaRMin : c.deltaRMinBottom;
+  s.dRMaxB = std::isnan(c.deltaRMaxBottom) ? c.deltaRMax : c.deltaRMaxBottom;
+  s.dRMinT = std::isnan(c.deltaRMaxTop) ? c.deltaRMin : c.deltaRMinTop;
+  s.dRMaxT = std::isnan(c.deltaRMaxTop) ? c.deltaRMax : c.deltaRMaxTop;
+  deriveFinderConstants(s);
+  return s;
+}
+
+}  // namespace orth
+
 thread_local std::string g_error;
 
 int fail(int code, const std::string& msg) {
@@ -1257,6 +1652,8 @@ struct oracle_counters {
 
 struct oracle_handle {
   Setup setup;
+  bool orthogonal = false;
+  orth::OrthOptions orthOptions{};
 };
 
 const char* oracle_last_error() { return g_error.c_str(); }
@@ -1346,6 +1743,26 @@ int oracle_create(const b200seed_config* cfg, oracle_handle** out) {
 }
 void oracle_destroy(oracle_handle* h) { delete h; }
 
+// OrthogonalTripletSeedingAlgorithm::Config defaults (hpp:38-186): the shared fields have the grid
+// algorithm's defaults, plus zOutermostLayers and deltaPhiMax.
+void oracle_orthogonal_config_init(b200seed_config* c, b200seed_orthogonal_options* o) {
+  oracle_config_init(c);
+  o->zOutermostLayersMin = -2700;
+  o->zOutermostLayersMax = 2700;
+  o->deltaPhiMax = 0.085;
+}
+int oracle_create_orthogonal(const b200seed_config* cfg, const b200seed_orthogonal_options* opt, oracle_handle** out) {
+  try {
+    auto* h = new oracle_handle{orth::makeSetup(*cfg)};
+    h->orthogonal = true;
+    h->orthOptions = {opt->zOutermostLayersMin, opt->zOutermostLayersMax, opt->deltaPhiMax};
+    *out = h;
+    return B200SEED_OK;
+  } catch (const std::exception& e) {
+    return fail(B200SEED_ERR_RUNTIME, e.what());
+  }
+}
+
 int oracle_get_info(const oracle_handle* h, b200seed_info* info) {
   const Setup& s = h->setup;
   std::memset(info, 0, sizeof(*info));
@@ -1398,6 +1815,7 @@ float oracle_atan2f(float y, float x) { return std::atan2(y, x); }
 struct oracle_event_result {
   Event ev;
   DoubletDump dump;
+  orth::TreeDump treeDump;
 };
 
 // GridTripletSeedingAlgorithm.cpp:187-206: one z window per vertex,
@@ -1434,7 +1852,11 @@ int oracle_run(const oracle_handle* h, std::uint32_t n, const float* x, const fl
       res->dump.first.push_back(0);
       ev.dump = &res->dump;
     }
-    runEvent(ev);
+    if (h->orthogonal) {
+      orth::runEvent(ev, h->orthOptions, &res->treeDump);
+    } else {
+      runEvent(ev);
+    }
     *out = res;
     return B200SEED_OK;
   } catch (const std::exception& e) {
@@ -1442,6 +1864,11 @@ int oracle_run(const oracle_handle* h, std::uint32_t n, const float* x, const fl
   }
 }
 void oracle_result_free(oracle_event_result* r) { delete r; }
+// element order of the k-d tree after construction (core space point indices), orthogonal handles only
+std::uint64_t oracle_result_tree_order(const oracle_event_result* r, std::uint32_t* order) {
+  if (order != nullptr) std::copy(r->treeDump.order.begin(), r->treeDump.order.end(), order);
+  return r->treeDump.order.size();
+}
 
 std::uint64_t oracle_result_num_seeds(const oracle_event_result* r) { return r->ev.seeds.size(); }
 void oracle_result_seeds(const oracle_event_result* r, std::uint32_t* b, std::uint32_t* m,
@@ -1615,7 +2042,11 @@ std::int64_t oracle_run_many(const oracle_handle* h, std::uint32_t nEvents,
         ev.n = spOffsets[e + 1] - o;
         ev.navStride = navStride == 0 ? 1 : navStride;
         ev.navPhase = e % ev.navStride;
-        runEvent(ev);
+        if (h->orthogonal) {
+          orth::runEvent(ev, h->orthOptions, nullptr);
+        } else {
+          runEvent(ev);
+        }
         total += static_cast<std::int64_t>(ev.seeds.size());
         if (seedCounts != nullptr) seedCounts[e] = ev.seeds.size();
       } catch (...) {

@@ -187,3 +187,67 @@ def test_reference_entered_from_many_threads(R, O):
     counts = ref.run_many(cols, offsets, n_threads=8)
     single = [ref.run(ev)["bottom"].size for ev in evs]
     assert counts.tolist() == single
+
+
+ORTH_VARIANTS = [
+    dict(),
+    dict(interactionPointCut=1),
+    dict(useExtraCuts=1),
+    dict(useVariableMiddleSPRange=1, deltaRMiddleMinSPRange=25.0, deltaRMiddleMaxSPRange=40.0),
+    dict(deltaPhiMax=0.025, maxSeedsPerSpM=4, sigmaScattering=2.0),
+    dict(deltaPhiMax=0.2, zOutermostLayersMin=-650.0, zOutermostLayersMax=800.0, phiMin=-2.5, phiMax=2.0),
+    dict(deltaRMinTop=float("nan"), deltaRMaxTop=float("nan"), deltaRMinBottom=6.0, deltaRMaxBottom=150.0),  # the isnan quirk of .cpp:175-198
+    dict(deltaRMinTop=10.0, deltaRMaxTop=120.0, deltaRMinBottom=float("nan"), deltaRMaxBottom=float("nan")),
+    dict(collisionRegionMin=-80.0, collisionRegionMax=120.0, cotThetaMax=3.0, deltaZMin=-300.0, deltaZMax=250.0),
+    dict(useDeltaRinsteadOfTopRadius=1, compatSeedLimit=3, numSeedIncrement=100.0, impactWeightFactor=100.0),
+]
+
+
+@pytest.mark.parametrize("variant", range(len(ORTH_VARIANTS)))
+def test_orthogonal_oracle_matches_reference(O, R, variant):
+    """The k-d-tree seeder (OrthogonalTripletSeedingAlgorithm.cpp:101-317 + CylindricalSpacePointKDTree.cpp +
+    KDTree.hpp): tree construction order, the four search boxes, unsorted doublet search, both z-direction
+    groups per middle -- oracle against the reference's own execute(), bit-identical seeds in order."""
+    from acts_b200 import config, events
+
+    over = ORTH_VARIANTS[variant]
+    orc = O.Oracle(*config.orthogonal_config(O.orthogonal_config_init, **over))
+    ref = R.Reference(*config.orthogonal_config(O.orthogonal_config_init, **over))
+    evs = [events.muon_gun_event(variant), events.pileup_event(variant, mu=5), events.pileup_event(40 + variant, mu=30)]
+    if variant in (0, 2, 4):
+        evs.append(events.itk_pileup_event(variant, mu=10))
+    total = 0
+    for k, ev in enumerate(evs):
+        a, b = orc.run(ev), ref.run(ev)
+        total += b["bottom"].size
+        assert _same_bits(a, b), f"variant {variant} event {k}"
+    assert total > 0
+
+
+def test_orthogonal_with_seed_confirmation_and_ties(O, R):
+    """seedConfirmation through the k-d-tree seeder (one filter state across both groups of a middle and across
+    middles, .cpp:234-238) and quantised coordinates (equal keys in the tree's std::sort / std::partition)."""
+    from acts_b200 import config, events
+
+    over = dict(config.confirmation_overrides())
+    ev = events.pileup_event(5, mu=30)
+    a = O.Oracle(*config.orthogonal_config(O.orthogonal_config_init, **over)).run(ev)
+    b = R.Reference(*config.orthogonal_config(O.orthogonal_config_init, **over)).run(ev)
+    assert b["bottom"].size > 0 and _same_bits(a, b)
+    q = {k: (np.round(v * 4) / 4).astype(np.float32) if k in ("x", "y", "z") else v for k, v in ev.items()}
+    q["r"] = np.hypot(q["x"], q["y"]).astype(np.float32)
+    q["r"] = (np.round(q["r"] * 2) / 2).astype(np.float32)
+    a = O.Oracle(*config.orthogonal_config(O.orthogonal_config_init)).run(q)
+    b = R.Reference(*config.orthogonal_config(O.orthogonal_config_init)).run(q)
+    assert b["bottom"].size > 0 and _same_bits(a, b)
+
+
+def test_orthogonal_empty_and_tiny_inputs(O, R):
+    from acts_b200 import config, events
+
+    orc = O.Oracle(*config.orthogonal_config(O.orthogonal_config_init))
+    ref = R.Reference(*config.orthogonal_config(O.orthogonal_config_init))
+    ev = events.pileup_event(0, mu=5)
+    for n in (0, 1, 3, 4, 5, 9, 130):
+        sub = {k: v[:n] for k, v in ev.items()}
+        assert _same_bits(orc.run(sub), ref.run(sub)), n
