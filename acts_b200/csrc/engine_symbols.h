@@ -17,6 +17,8 @@
 #define b200seed_plan_info B200SEED_E(plan_info)
 #define b200seed_plan_tables B200SEED_E(plan_tables)
 #define b200seed_create B200SEED_E(create)
+#define b200seed_create_orthogonal B200SEED_E(create_orthogonal)
+#define b200seed_orthogonal_config_init B200SEED_E(orthogonal_config_init)
 #define b200seed_destroy B200SEED_E(destroy)
 #define b200seed_last_error B200SEED_E(last_error)
 #define b200seed_alloc_pinned B200SEED_E(alloc_pinned)

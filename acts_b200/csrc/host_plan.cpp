@@ -113,7 +113,9 @@ void completeNavigation(std::vector<std::size_t>& bins, std::size_t nBins, int a
   }
 }
 
-void build(const b200seed_config& c, HostPlan& plan) {
+void build(const b200seed_config& c, HostPlan& plan, const b200seed_orthogonal_options* orthOpt = nullptr) {
+  const bool orthogonal = orthOpt != nullptr;
+  plan.orthogonal = orthogonal;
   if (c.abi_version != B200SEED_ABI_VERSION || c.struct_size != sizeof(b200seed_config)) {
     throw Fail{B200SEED_ERR_INVALID_ARGUMENT,
                "b200seed_config: abi_version/struct_size mismatch (use b200seed_config_init)"};
@@ -123,6 +125,8 @@ void build(const b200seed_config& c, HostPlan& plan) {
       (c.nZBinsCustomLooping && !c.zBinsCustomLooping) || (c.nRRangeMiddleSP && !c.rRangeMiddleSP)) {
     throw Fail{B200SEED_ERR_INVALID_ARGUMENT, "b200seed_config: null array with non-zero count"};
   }
+  const float gridRMin = 0;
+  if (!orthogonal) {
   // GridTripletSeedingAlgorithm.cpp:117-126
   for (uint32_t i = 0; i < c.nZBinsCustomLooping; ++i) {
     if (c.zBinsCustomLooping[i] >= c.nZBinEdges) {
@@ -132,7 +136,6 @@ void build(const b200seed_config& c, HostPlan& plan) {
     }
   }
   // CylindricalSpacePointGrid.cpp:18-37; the algorithm forces the grid's rMin to 0
-  const float gridRMin = 0;
   if (c.phiMin < -kPiF || c.phiMax > kPiF) {
     throw Fail{B200SEED_ERR_RUNTIME,
                "CylindricalSpacePointGrid: phiMin (" + std::to_string(c.phiMin) +
@@ -150,8 +153,16 @@ void build(const b200seed_config& c, HostPlan& plan) {
     throw Fail{B200SEED_ERR_RUNTIME, "CylindricalSpacePointGrid: zMin is bigger than zMax"};
   }
 
+  }
   DeviceConfig& d = plan.dev;
   std::memset(&d, 0, sizeof(d));
+  plan.navBins.clear();
+  plan.botOffsets = {0};
+  plan.topOffsets = {0};
+  plan.botBins.clear();
+  plan.topBins.clear();
+  plan.maxNeighborBins = 0;
+  if (!orthogonal) {
   const int phiBins = phiBinCount(c);
 
   // phi axis, Axis.hpp:40-58
@@ -259,11 +270,34 @@ void build(const b200seed_config& c, HostPlan& plan) {
                "more than " + std::to_string(kMaxNeighborBins) + " neighbour bins per middle bin"};
   }
 
+  }
   // doublet finders, GridTripletSeedingAlgorithm.cpp:272-309
   d.dRMinB = std::isnan(c.deltaRMinBottom) ? c.deltaRMin : c.deltaRMinBottom;
   d.dRMaxB = std::isnan(c.deltaRMaxBottom) ? c.deltaRMax : c.deltaRMaxBottom;
   d.dRMinT = std::isnan(c.deltaRMinTop) ? c.deltaRMin : c.deltaRMinTop;
   d.dRMaxT = std::isnan(c.deltaRMaxTop) ? c.deltaRMax : c.deltaRMaxTop;
+  if (orthogonal) {
+    // OrthogonalTripletSeedingAlgorithm.cpp:176-199: the doublet finders test deltaRMax{Bottom,Top} for NaN to
+    // pick BOTH bounds; the tree options (.cpp:158-171) test each bound on its own, the "low-high" set with the
+    // Bottom values and the "high-low" set with the Top values
+    d.dRMinB = std::isnan(c.deltaRMaxBottom) ? c.deltaRMin : c.deltaRMinBottom;
+    d.dRMinT = std::isnan(c.deltaRMaxTop) ? c.deltaRMin : c.deltaRMinTop;
+    OrthDeviceConfig& o = plan.orth;
+    o.rMax = c.rMax; o.zMin = c.zMin; o.zMax = c.zMax; o.phiMin = c.phiMin; o.phiMax = c.phiMax;
+    o.lhDeltaRMin = std::isnan(c.deltaRMinBottom) ? c.deltaRMin : c.deltaRMinBottom;
+    o.lhDeltaRMax = std::isnan(c.deltaRMaxBottom) ? c.deltaRMax : c.deltaRMaxBottom;
+    o.hlDeltaRMin = std::isnan(c.deltaRMinTop) ? c.deltaRMin : c.deltaRMinTop;
+    o.hlDeltaRMax = std::isnan(c.deltaRMaxTop) ? c.deltaRMax : c.deltaRMaxTop;
+    o.collisionRegionMin = c.collisionRegionMin; o.collisionRegionMax = c.collisionRegionMax;
+    o.cotThetaMax = c.cotThetaMax;
+    o.deltaPhiMax = orthOpt->deltaPhiMax;
+    o.deltaZMax = std::numeric_limits<float>::infinity();  // Options::deltaZMax default, never set by the algorithm
+    o.zOutermostLayersMin = orthOpt->zOutermostLayersMin;
+    o.zOutermostLayersMax = orthOpt->zOutermostLayersMax;
+    if (c.seedConfirmation) {
+      throw Fail{B200SEED_ERR_UNSUPPORTED, "seedConfirmation with the orthogonal seeder is not supported"};
+    }
+  }
   d.deltaZMin = c.deltaZMin;
   d.deltaZMax = c.deltaZMax;
   d.collisionRegionMin = c.collisionRegionMin;
@@ -344,14 +378,14 @@ void build(const b200seed_config& c, HostPlan& plan) {
   d.rMaxMiddle = c.rMaxMiddle;
   d.deltaRMiddleMinSPRange = c.deltaRMiddleMinSPRange;
   d.deltaRMiddleMaxSPRange = c.deltaRMiddleMaxSPRange;
-  d.nRRangeMiddleSP = static_cast<int32_t>(c.nRRangeMiddleSP);
-  if (c.nRRangeMiddleSP > static_cast<uint32_t>(kMaxZEdges)) {
+  d.nRRangeMiddleSP = orthogonal ? 0 : static_cast<int32_t>(c.nRRangeMiddleSP);
+  if (!orthogonal && c.nRRangeMiddleSP > static_cast<uint32_t>(kMaxZEdges)) {
     throw Fail{B200SEED_ERR_UNSUPPORTED, "rRangeMiddleSP too long"};
   }
-  for (uint32_t i = 0; i < 2 * c.nRRangeMiddleSP; ++i) d.rRangeMiddleSP[i] = c.rRangeMiddleSP[i];
-  d.nZBinEdgesF = static_cast<int32_t>(c.nZBinEdges);
-  for (uint32_t i = 0; i < c.nZBinEdges; ++i) d.zBinEdgesF[i] = c.zBinEdges[i];
-  if (c.nRRangeMiddleSP != 0 && !c.useVariableMiddleSPRange) {
+  for (uint32_t i = 0; !orthogonal && i < 2 * c.nRRangeMiddleSP; ++i) d.rRangeMiddleSP[i] = c.rRangeMiddleSP[i];
+  d.nZBinEdgesF = orthogonal ? 0 : static_cast<int32_t>(c.nZBinEdges);
+  for (uint32_t i = 0; !orthogonal && i < c.nZBinEdges; ++i) d.zBinEdgesF[i] = c.zBinEdges[i];
+  if (!orthogonal && c.nRRangeMiddleSP != 0 && !c.useVariableMiddleSPRange) {
     // the reference indexes rRangeMiddleSP[zBin] unchecked (.cpp:415-420) with
     // zBin = max(lower_bound(zBinEdges, zM) - 1, 0) <= max(nZBinEdges, 1) - 1
     const uint32_t needed = c.nZBinEdges > 1 ? c.nZBinEdges - 1 : 1;
@@ -390,6 +424,17 @@ void build(const b200seed_config& c, HostPlan& plan) {
 bool make_host_plan(const b200seed_config& cfg, HostPlan& plan, PlanError& err) {
   try {
     build(cfg, plan);
+    return true;
+  } catch (const Fail& f) {
+    err.code = f.code;
+    err.message = f.msg;
+    return false;
+  }
+}
+
+bool make_orthogonal_plan(const b200seed_config& cfg, const b200seed_orthogonal_options& opt, HostPlan& plan, PlanError& err) {
+  try {
+    build(cfg, plan, &opt);
     return true;
   } catch (const Fail& f) {
     err.code = f.code;

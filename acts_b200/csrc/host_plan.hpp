@@ -38,6 +38,9 @@ struct HostPlan {
   // per-middle output slots: min(maxSeedsPerSpM + 1, maxSeedsPerSpMConf)
   uint32_t seedsPerMiddle = 0;
   bool relaxedFloat = false;
+  // OrthogonalTripletSeedingAlgorithm: no grid, the k-d-tree provider's search options instead
+  bool orthogonal = false;
+  OrthDeviceConfig orth{};
   // Config::inputVertices / vertexZNSigma / vertexZMargin (GridTripletSeedingAlgorithm.hpp:239-243)
   bool useVertexZCuts = false;
   double vertexZNSigma = 3.0, vertexZMargin = 0.0;
@@ -46,6 +49,10 @@ struct HostPlan {
 // Validates like the reference (same exception classes mapped to status codes)
 // and fills the plan.  Returns false and sets err on failure.
 bool make_host_plan(const b200seed_config& cfg, HostPlan& plan, PlanError& err);
+
+// The same for OrthogonalTripletSeedingAlgorithm (ctor .cpp:62-99, the option / finder set-up of execute()
+// .cpp:152-225): derived constants of the three finders and the two CylindricalSpacePointKDTree::Options.
+bool make_orthogonal_plan(const b200seed_config& cfg, const b200seed_orthogonal_options& opt, HostPlan& plan, PlanError& err);
 
 // Reference defaults (GridTripletSeedingAlgorithm.hpp:34-244).
 void config_defaults(b200seed_config& cfg);

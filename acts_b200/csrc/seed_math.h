@@ -267,6 +267,16 @@ struct DeviceConfig {
   float zBinEdgesF[kMaxZEdges];
 };
 
+// CylindricalSpacePointKDTree::Options of the orthogonal seeder (CylindricalSpacePointKDTree.hpp:45-70,
+// OrthogonalTripletSeedingAlgorithm.cpp:152-171): the "low-high" set (top search) and the "high-low" set (bottom
+// search) differ only in the deltaR window; + the middle selection of .cpp:268-275.
+struct OrthDeviceConfig {
+  float rMax, zMin, zMax, phiMin, phiMax;
+  float lhDeltaRMin, lhDeltaRMax, hlDeltaRMin, hlDeltaRMax;
+  float collisionRegionMin, collisionRegionMax, cotThetaMax, deltaPhiMax, deltaZMax;
+  float zOutermostLayersMin, zOutermostLayersMax;
+};
+
 // ---------------------------------------------------------------------------
 // Grid lookup: SpacePointGridBase.hpp:67-87, Axis.hpp:216-235,296,497-539,598-600,
 // MultiAxisHelper.hpp:230-245.  Returns -1 when the point is outside the grid.
@@ -409,6 +419,90 @@ B2S_HD bool doublet_finish(const DeviceConfig& c, const MiddleSp& m, float delta
   out.xNew = xNewFrame;
   out.yNew = yNewFrame;
   return true;
+}
+
+// ---------------------------------------------------------------------------
+// Orthogonal seeder: the search boxes of one middle space point
+// (CylindricalSpacePointKDTree.cpp:17-217).  RangeXD<3, float> is semi-open per dimension
+// (phi, r, z); shrinkMin / shrinkMax are std::max / std::min with the running bound first.
+// ---------------------------------------------------------------------------
+struct KdBox {
+  float mn[3], mx[3];  // phi, r, z
+};
+B2S_HD float std_max(float a, float b) { return (a < b) ? b : a; }  // std::max(a, b)
+B2S_HD float std_min(float a, float b) { return (b < a) ? b : a; }  // std::min(a, b)
+B2S_HD void kd_shrink_min(KdBox& b, int d, float v) { b.mn[d] = std_max(b.mn[d], v); }
+B2S_HD void kd_shrink_max(KdBox& b, int d, float v) { b.mx[d] = std_min(b.mx[d], v); }
+B2S_HD bool kd_degenerate(const KdBox& b) { return (b.mn[0] >= b.mx[0]) | (b.mn[1] >= b.mx[1]) | (b.mn[2] >= b.mx[2]); }
+B2S_HD void kd_box_init(KdBox& b) {
+  for (int d = 0; d < 3; ++d) { b.mn[d] = -3.402823466e+38f; b.mx[d] = 3.402823466e+38f; }
+}
+
+// validTupleOrthoRangeLH, .cpp:17-96 (the box of the TOP candidates, "low-high" options)
+B2S_HD void kd_range_lh(const OrthDeviceConfig& o, float pL, float rL, float zL, KdBox& res) {
+  const float colMin = o.collisionRegionMin, colMax = o.collisionRegionMax;
+  kd_box_init(res);
+  kd_shrink_min(res, 0, o.phiMin);
+  kd_shrink_max(res, 0, o.phiMax);
+  kd_shrink_max(res, 1, o.rMax);
+  kd_shrink_min(res, 2, o.zMin);
+  kd_shrink_max(res, 2, o.zMax);
+  kd_shrink_min(res, 1, fadd(rL, o.lhDeltaRMin));
+  kd_shrink_max(res, 1, fadd(rL, o.lhDeltaRMax));
+  const float zMax = fadd(fmul(fdiv(res.mx[1], rL), fsub(zL, colMin)), colMin);
+  const float zMin = fsub(colMax, fmul(fdiv(res.mx[1], rL), fsub(colMax, zL)));
+  if (zL > colMin) {
+    kd_shrink_max(res, 2, zMax);
+  } else if (zL < colMax) {
+    kd_shrink_min(res, 2, zMin);
+  }
+  kd_shrink_min(res, 2, fsub(zL, fmul(o.cotThetaMax, fsub(res.mx[1], rL))));
+  kd_shrink_max(res, 2, fadd(zL, fmul(o.cotThetaMax, fsub(res.mx[1], rL))));
+  kd_shrink_min(res, 0, fsub(pL, o.deltaPhiMax));
+  kd_shrink_max(res, 0, fadd(pL, o.deltaPhiMax));
+  kd_shrink_min(res, 2, fsub(zL, o.deltaZMax));
+  kd_shrink_max(res, 2, fadd(zL, o.deltaZMax));
+}
+
+// validTupleOrthoRangeHL, .cpp:98-157 (the box of the BOTTOM candidates, "high-low" options)
+B2S_HD void kd_range_hl(const OrthDeviceConfig& o, float pM, float rM, float zM, KdBox& res) {
+  kd_box_init(res);
+  kd_shrink_min(res, 0, o.phiMin);
+  kd_shrink_max(res, 0, o.phiMax);
+  kd_shrink_max(res, 1, o.rMax);
+  kd_shrink_min(res, 2, o.zMin);
+  kd_shrink_max(res, 2, o.zMax);
+  kd_shrink_min(res, 1, fsub(rM, o.hlDeltaRMax));
+  kd_shrink_max(res, 1, fsub(rM, o.hlDeltaRMin));
+  const float fracR = fdiv(res.mn[1], rM);
+  const float zMin = fadd(fmul(fsub(zM, o.collisionRegionMin), fracR), o.collisionRegionMin);
+  const float zMax = fadd(fmul(fsub(zM, o.collisionRegionMax), fracR), o.collisionRegionMax);
+  kd_shrink_min(res, 2, std_min(zMin, zM));
+  kd_shrink_max(res, 2, std_max(zMax, zM));
+  kd_shrink_min(res, 0, fsub(pM, o.deltaPhiMax));
+  kd_shrink_max(res, 0, fadd(pM, o.deltaPhiMax));
+  kd_shrink_min(res, 2, fsub(zM, o.deltaZMax));
+  kd_shrink_max(res, 2, fadd(zM, o.deltaZMax));
+}
+
+// validTuples, .cpp:159-217: dir 0 = monotonically increasing z ("lh" lists), dir 1 = decreasing z ("hl" lists)
+B2S_HD void kd_search_boxes(const OrthDeviceConfig& o, float pM, float rM, float zM, int dir, KdBox& bottom, KdBox& top) {
+  kd_range_hl(o, pM, rM, zM, bottom);
+  kd_range_lh(o, pM, rM, zM, top);
+  const float cotTheta = std_max(fabs_(fdiv(zM, rM)), o.cotThetaMax);
+  const float deltaRMaxTop = fsub(top.mx[1], rM);
+  const float deltaRMaxBottom = fsub(rM, bottom.mn[1]);
+  if (dir == 0) {
+    kd_shrink_min(bottom, 2, fsub(zM, fmul(cotTheta, deltaRMaxBottom)));
+    kd_shrink_max(bottom, 2, zM);
+    kd_shrink_min(top, 2, zM);
+    kd_shrink_max(top, 2, fadd(zM, fmul(cotTheta, deltaRMaxTop)));
+  } else {
+    kd_shrink_min(bottom, 2, zM);
+    kd_shrink_max(bottom, 2, fadd(zM, fmul(cotTheta, deltaRMaxBottom)));
+    kd_shrink_min(top, 2, fsub(zM, fmul(cotTheta, deltaRMaxTop)));
+    kd_shrink_max(top, 2, zM);
+  }
 }
 
 // ---------------------------------------------------------------------------

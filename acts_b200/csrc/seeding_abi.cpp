@@ -20,6 +20,8 @@ extern "C" {
   int P##plan_tables(const b200seed_config*, void*, uint64_t, uint32_t*, uint32_t*, uint32_t*, uint32_t*,   \
                      uint32_t*, uint64_t*);                                                                 \
   int P##create(const b200seed_config*, int, P##handle**);                                                  \
+  int P##create_orthogonal(const b200seed_config*, const b200seed_orthogonal_options*, int, P##handle**);   \
+  int P##orthogonal_config_init(b200seed_config*, b200seed_orthogonal_options*);                            \
   void P##destroy(P##handle*);                                                                              \
   const char* P##last_error(void);                                                                          \
   void* P##alloc_pinned(size_t);                                                                            \
@@ -134,6 +136,34 @@ int b200seed_create(const b200seed_config* cfg, int device, b200seed_handle** ou
   } else {
     g_lastEngine = 0;
     rc = b200ex_create(cfg, device, &h->exact);
+  }
+  if (rc != B200SEED_OK) {
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return B200SEED_OK;
+}
+
+int b200seed_orthogonal_config_init(b200seed_config* cfg, b200seed_orthogonal_options* opt) {
+  g_lastEngine = 0;
+  return b200ex_orthogonal_config_init(cfg, opt);
+}
+
+int b200seed_create_orthogonal(const b200seed_config* cfg, const b200seed_orthogonal_options* opt, int device,
+                               b200seed_handle** out) {
+  if (cfg == nullptr || opt == nullptr || out == nullptr) return own_error("NULL argument");
+  *out = nullptr;
+  b200seed_handle* h = new (std::nothrow) b200seed_handle;
+  if (h == nullptr) return own_error("out of memory");
+  int rc;
+  const bool relaxed = cfg->struct_size == sizeof(b200seed_config) && cfg->relaxedFloat != 0;
+  if (relaxed) {
+    g_lastEngine = 1;
+    rc = b200rx_create_orthogonal(cfg, opt, device, &h->relaxed);
+  } else {
+    g_lastEngine = 0;
+    rc = b200ex_create_orthogonal(cfg, opt, device, &h->exact);
   }
   if (rc != B200SEED_OK) {
     delete h;

@@ -130,6 +130,7 @@ struct CompactParams {
   unsigned long long outCapacity;
   unsigned long long* seedOffsets;  // [nEvents + 1]
   const uint32_t* workStart;
+  const uint32_t* eventFirstItem;  // NULL: event e starts at workStart[e * nNav]; else at workStart[eventFirstItem[e]]
   uint32_t* seedStart;  // [nWork + 1] exclusive scan of slotCount
   uint32_t nEvents, nNav;
   unsigned long long* counters;
@@ -2157,7 +2158,7 @@ __global__ void __launch_bounds__(256) k_compact_seeds(const __grid_constant__ C
 __global__ void k_event_offsets(const __grid_constant__ CompactParams p) {
   const uint32_t nWork = *p.nWorkPtr;
   for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e <= p.nEvents; e += gridDim.x * blockDim.x) {
-    const uint32_t w = e < p.nEvents ? p.workStart[(size_t)e * p.nNav] : nWork;
+    const uint32_t w = e < p.nEvents ? p.workStart[p.eventFirstItem != nullptr ? (size_t)p.eventFirstItem[e] : (size_t)e * p.nNav] : nWork;
     // seedStart[nWork] is only written when nWork > 0
     p.seedOffsets[e] = nWork == 0 ? 0ull : (unsigned long long)p.seedStart[w];
   }

@@ -15,7 +15,11 @@
 
 #include "../../include/acts_b200_seeding.h"
 #include "host_plan.hpp"
+#include <atomic>
+#include <thread>
+
 #include "seeding_kernels.cuh"
+#include "orthogonal_kernels.cuh"
 
 using namespace B200SEED_NS;
 
@@ -113,6 +117,9 @@ struct b200seed_handle {
   DevBuf slotB, slotM, slotT, slotQ, slotZ, slotCount, seedStart, tileSums, tilePrefix;
   DevBuf outB, outM, outT, outQ, outZ, seedOffsets;  // device outputs of the host API
   DevBuf counters, status, zWin, zWinOffsets;
+  // orthogonal seeder: the event trees built by the host layer (kd_tree_host.hpp)
+  DevBuf orthPosOrig, orthPosPhi, orthNodes, orthCoreOffsets, orthNodeOffsets, orthRRange;
+  uint32_t itemsMax = 0;  // upper bound of the work items of the last call (grid: space points, orthogonal: 2 x)
   uint32_t zWinCapacity = 1;  // windows per column of zWin (lo column, then hi column)
   DoubletParams lastDoublets{};  // of the last call (debug_doublets re-runs the fill pass chunk by chunk)
   // seedConfirmation: candidate records, second slot set, per-space-point seed lists, {record counter, changed[round]}
@@ -128,6 +135,8 @@ struct b200seed_handle {
     uint32_t nEvents = 0, nTotal = 0;
     const uint32_t* dOffsets = nullptr;
     const float *x = nullptr, *y = nullptr, *z = nullptr, *r = nullptr, *varZ = nullptr, *varR = nullptr, *dPhi = nullptr;
+    const float *hx = nullptr, *hy = nullptr, *hz = nullptr, *hr = nullptr;  // host copies of the columns, when the caller gave them
+    const uint32_t* hOffsets = nullptr;
     int nZWin = 0;
     bool vertexCuts = false;            // VertexZCuts connected (cfg.useVertexZCuts, or windows given)
     const uint32_t* dZWinOffsets = nullptr;  // per-event window ranges (NULL: all events share [0, nZWin))
@@ -170,7 +179,8 @@ int upload(DevBuf& buf, const std::vector<uint32_t>& v, cudaStream_t s) {
 int ensure_workspace(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal) {
   const size_t nBinsAll = (size_t)nEvents * (size_t)h->plan.dev.nGlobalBins;
   const size_t nNavAll = (size_t)nEvents * h->plan.navBins.size();
-  const size_t nT = std::max<size_t>(nTotal, 1);
+  // per work item arrays: one item per space point at most (grid), two per space point (orthogonal: both z directions)
+  const size_t nT = std::max<size_t>(h->plan.orthogonal ? 2 * (size_t)nTotal : (size_t)nTotal, 1);
   const size_t K = std::max<uint32_t>(h->plan.seedsPerMiddle, 1);
   CUDA_TRY(h->binOf.reserve(nT * 4));
   CUDA_TRY(h->binCount.reserve((nBinsAll + 1) * 4));
@@ -285,7 +295,7 @@ int enqueue_tail(b200seed_handle* h, cudaStream_t s) {
   const CompactParams& cp = h->compactParams;
   const uint32_t nEvents = h->last.nEvents;
   const uint32_t nBinsAll = nEvents * (uint32_t)h->plan.dev.nGlobalBins;
-  const uint32_t nTiles = std::max<uint32_t>(1, (h->last.nTotal + kTile - 1) / kTile);
+  const uint32_t nTiles = std::max<uint32_t>(1, (std::max(h->itemsMax, h->last.nTotal) + kTile - 1) / kTile);
   k_tile_sums<<<nTiles, 256, 0, s>>>(cp);
   k_scan<<<1, kScanThreads, 0, s>>>(cp.tileSums, cp.tilePrefix, nTiles);
   k_compact_seeds<<<nTiles, 256, 0, s>>>(cp);
@@ -300,6 +310,124 @@ int enqueue_tail(b200seed_handle* h, cudaStream_t s) {
   if (h->plan.dev.seedConfirmation) {
     CUDA_TRY(cudaMemcpyAsync(h->hConfState, h->confState.ptr, kConfStateWords * 4, cudaMemcpyDeviceToHost, s));
   }
+  return B200SEED_OK;
+}
+
+// Orthogonal seeder, front of the pipeline (replaces the grid stage and the bin-wise work list): the host layer
+// builds every event's k-d tree (kd_tree_host.hpp, one thread per event), the device gathers the packed copy in
+// element order and lists two work items per accepted middle.
+int orth_front(b200seed_handle* h, GridParams& gp, WorkParams& wp, KdDoubletParams& kdp, uint64_t& launches) {
+  const b200seed_handle::EnqueueArgs& a = h->last;
+  const uint32_t nEvents = a.nEvents, nTotal = a.nTotal;
+  cudaStream_t s = a.stream;
+  const HostPlan& plan = h->plan;
+  // host copies of x, y, z, r (the caller's, or read back when the inputs are device resident)
+  std::vector<float> back[4];
+  std::vector<uint32_t> backOffsets;
+  const float* hc[4] = {a.hx, a.hy, a.hz, a.hr};
+  const uint32_t* hOff = a.hOffsets;
+  if (hOff == nullptr || (nTotal > 0 && (hc[0] == nullptr || hc[1] == nullptr || hc[2] == nullptr || hc[3] == nullptr))) {
+    const float* dc[4] = {a.x, a.y, a.z, a.r};
+    backOffsets.resize((size_t)nEvents + 1);
+    CUDA_TRY(cudaMemcpyAsync(backOffsets.data(), a.dOffsets, ((size_t)nEvents + 1) * 4, cudaMemcpyDeviceToHost, s));
+    for (int k = 0; k < 4; ++k) {
+      back[k].resize(std::max<size_t>(nTotal, 1));
+      if (nTotal > 0) CUDA_TRY(cudaMemcpyAsync(back[k].data(), dc[k], (size_t)nTotal * 4, cudaMemcpyDeviceToHost, s));
+      hc[k] = back[k].data();
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    hOff = backOffsets.data();
+  }
+  std::vector<KdEventTree> trees(nEvents);
+  {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const uint32_t nThreads = std::min<uint32_t>(nEvents, std::min<unsigned>(hw, 32u));
+    std::atomic<uint32_t> next{0};
+    auto worker = [&] {
+      for (;;) {
+        const uint32_t e = next.fetch_add(1);
+        if (e >= nEvents) return;
+        const uint32_t b = hOff[e], n = hOff[e + 1] - b;
+        build_kd_event(plan.dev, n, hc[0] + b, hc[1] + b, hc[2] + b, hc[3] + b, trees[e]);
+      }
+    };
+    std::vector<std::thread> pool;
+    for (uint32_t t = 1; t < nThreads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
+  }
+  std::vector<uint32_t> coreOffsets(nEvents + 1, 0), nodeOffsets(nEvents + 1, 0);
+  for (uint32_t e = 0; e < nEvents; ++e) {
+    coreOffsets[e + 1] = coreOffsets[e] + (uint32_t)trees[e].posOrig.size();
+    nodeOffsets[e + 1] = nodeOffsets[e] + (uint32_t)trees[e].nodes.size();
+  }
+  const uint32_t nCore = coreOffsets[nEvents], nNodes = nodeOffsets[nEvents];
+  std::vector<uint32_t> posOrig(std::max<uint32_t>(nCore, 1));
+  std::vector<float> posPhi(std::max<uint32_t>(nCore, 1)), rRange(2 * (size_t)nEvents);
+  std::vector<KdNodeDev> nodes(std::max<uint32_t>(nNodes, 1));
+  for (uint32_t e = 0; e < nEvents; ++e) {
+    std::copy(trees[e].posOrig.begin(), trees[e].posOrig.end(), posOrig.begin() + coreOffsets[e]);
+    std::copy(trees[e].posPhi.begin(), trees[e].posPhi.end(), posPhi.begin() + coreOffsets[e]);
+    std::copy(trees[e].nodes.begin(), trees[e].nodes.end(), nodes.begin() + nodeOffsets[e]);
+    rRange[2 * e] = trees[e].rMiddleMin;
+    rRange[2 * e + 1] = trees[e].rMiddleMax;
+  }
+  CUDA_TRY(h->orthPosOrig.reserve(posOrig.size() * 4));
+  CUDA_TRY(h->orthPosPhi.reserve(posPhi.size() * 4));
+  CUDA_TRY(h->orthNodes.reserve(nodes.size() * sizeof(KdNodeDev)));
+  CUDA_TRY(h->orthCoreOffsets.reserve(coreOffsets.size() * 4));
+  CUDA_TRY(h->orthNodeOffsets.reserve(nodeOffsets.size() * 4));
+  CUDA_TRY(h->orthRRange.reserve(std::max<size_t>(rRange.size(), 1) * 4));
+  CUDA_TRY(h->midCount.reserve(((size_t)nCore + 1) * 4));
+  CUDA_TRY(h->workStart.reserve(((size_t)nCore + 2) * 4));
+  CUDA_TRY(cudaMemcpyAsync(h->orthPosOrig.ptr, posOrig.data(), posOrig.size() * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->orthPosPhi.ptr, posPhi.data(), posPhi.size() * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->orthNodes.ptr, nodes.data(), nodes.size() * sizeof(KdNodeDev), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->orthCoreOffsets.ptr, coreOffsets.data(), coreOffsets.size() * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->orthNodeOffsets.ptr, nodeOffsets.data(), nodeOffsets.size() * 4, cudaMemcpyHostToDevice, s));
+  if (!rRange.empty()) CUDA_TRY(cudaMemcpyAsync(h->orthRRange.ptr, rRange.data(), rRange.size() * 4, cudaMemcpyHostToDevice, s));
+  // the number of selected space points is what the grid path reports as nInGrid (read back from binStart[0])
+  CUDA_TRY(cudaMemcpyAsync(h->binStart.ptr, &coreOffsets[nEvents], 4, cudaMemcpyHostToDevice, s));
+
+  CUDA_TRY(cudaEventRecord(h->ev[1], s));
+  OrthParams op{};
+  op.cfg = plan.dev;
+  op.orth = plan.orth;
+  op.nEvents = nEvents; op.nCoreTotal = nCore;
+  op.spOffsets = a.dOffsets;
+  op.coreOffsets = h->orthCoreOffsets.as<uint32_t>();
+  op.nodeOffsets = h->orthNodeOffsets.as<uint32_t>();
+  op.rMiddleRange = h->orthRRange.as<float>();
+  op.posOrig = h->orthPosOrig.as<uint32_t>();
+  op.posPhi = h->orthPosPhi.as<float>();
+  op.nodes = h->orthNodes.as<KdNodeDev>();
+  op.x = a.x; op.y = a.y; op.z = a.z; op.r = a.r; op.varZ = a.varZ; op.varR = a.varR;
+  op.pIdx = gp.pIdx; op.pXY = gp.pXY; op.pZR = gp.pZR; op.pVar = gp.pVar;
+  op.itemCount = h->midCount.as<uint32_t>();
+  op.workStart = h->workStart.as<uint32_t>();
+  op.workPos = h->workPos.as<uint32_t>();
+  op.workEG = h->workEG.as<uint32_t>();
+  wp.workStart = op.workStart;
+  wp.workPos = op.workPos;
+  wp.workEG = op.workEG;
+  const int blocks = std::max(1, std::min<int>((int)((nCore + 255) / 256), h->smCount * 8));
+  if (nCore > 0) {
+    k_orth_gather<<<blocks, 256, 0, s>>>(op);
+    ++launches;
+  }
+  k_scan<<<1, kScanThreads, 0, s>>>(op.itemCount, op.workStart, nCore);
+  ++launches;
+  if (nCore > 0) {
+    k_orth_fill_work<<<blocks, 256, 0, s>>>(op);
+    ++launches;
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));  // the staging vectors go out of scope
+  kdp.orth = plan.orth;
+  kdp.coreOffsets = op.coreOffsets;
+  kdp.nodeOffsets = op.nodeOffsets;
+  kdp.nodes = op.nodes;
+  kdp.posPhi = op.posPhi;
+  kdp.d.nNav = nCore;  // read by enqueue(): the work-item total sits at workStart[nCore]
   return B200SEED_OK;
 }
 
@@ -347,6 +475,26 @@ int enqueue(b200seed_handle* h) {
   gp.status = h->status.as<int>();
   gp.counters = h->counters.as<unsigned long long>();
 
+  const bool orthogonal = plan.orthogonal;
+  const uint32_t itemsMax = orthogonal ? 2u * nTotal : nTotal;
+  h->itemsMax = itemsMax;
+  const uint32_t* nWorkPtr = nullptr;       // device: number of work items of this call
+  const uint32_t* eventFirstItem = nullptr;  // orthogonal: index into workStart of every event's first item
+  KdDoubletParams kdp{};
+  WorkParams wp{};
+  wp.cfg = plan.dev;
+  wp.nEvents = nEvents; wp.nBins = nBins; wp.nNav = nNav;
+  wp.binStart = gp.binStart;
+  wp.pZR = gp.pZR;
+  wp.navBins = h->navBins.as<uint32_t>();
+  wp.midLo = h->midLo.as<uint32_t>();
+  wp.midCount = h->midCount.as<uint32_t>();
+  wp.workStart = h->workStart.as<uint32_t>();
+  wp.workPos = h->workPos.as<uint32_t>();
+  wp.workEG = h->workEG.as<uint32_t>();
+  wp.phiFirst = h->phiFirst;
+  wp.phiCount = h->phiCount;
+  if (!orthogonal) {
   const int elemBlocks = std::max(1, std::min<int>((int)((nTotal + 255) / 256), h->smCount * 8));
   if (nTotal > 0) {
     k_bin_count<<<elemBlocks, 256, 0, s>>>(gp);
@@ -361,27 +509,21 @@ int enqueue(b200seed_handle* h) {
   }
 
   CUDA_TRY(cudaEventRecord(h->ev[1], s));
-  WorkParams wp{};
-  wp.cfg = plan.dev;
-  wp.nEvents = nEvents; wp.nBins = nBins; wp.nNav = nNav;
-  wp.binStart = gp.binStart;
-  wp.pZR = gp.pZR;
-  wp.navBins = h->navBins.as<uint32_t>();
-  wp.midLo = h->midLo.as<uint32_t>();
-  wp.midCount = h->midCount.as<uint32_t>();
-  wp.workStart = h->workStart.as<uint32_t>();
-  wp.workPos = h->workPos.as<uint32_t>();
-  wp.workEG = h->workEG.as<uint32_t>();
-  wp.phiFirst = h->phiFirst;
-  wp.phiCount = h->phiCount;
   k_middle_ranges<<<nEvents, 256, 0, s>>>(wp);
   k_scan<<<1, kScanThreads, 0, s>>>(wp.midCount, wp.workStart, nNavAll);
   k_fill_work<<<(nNavAll * 32 + 255) / 256, 256, 0, s>>>(wp);
   launches += 3;
 
+  nWorkPtr = wp.workStart + nNavAll;
+  } else {
+    rc = orth_front(h, gp, wp, kdp, launches);
+    if (rc != B200SEED_OK) return rc;
+    nWorkPtr = wp.workStart + kdp.d.nNav;  // (orth_front parks the element count there)
+    eventFirstItem = h->orthCoreOffsets.as<uint32_t>();
+  }
   CUDA_TRY(cudaEventRecord(h->ev[2], s));
   const bool conf = plan.dev.seedConfirmation != 0;
-  const uint32_t nWorkMax = std::max<uint32_t>(nTotal, 1);
+  const uint32_t nWorkMax = std::max<uint32_t>(itemsMax, 1);
   uint32_t* wc = h->workCounter.as<uint32_t>();  // 16 words per launch group: [0] count pass, [1 + c] chunk c
   uint32_t* planWords = h->planDev.as<uint32_t>();
   CUDA_TRY(cudaMemsetAsync(planWords, 0, 8 * 4, s));
@@ -398,7 +540,7 @@ int enqueue(b200seed_handle* h) {
   dp.topOffsets = h->topOffsets.as<uint32_t>();
   dp.topBins = h->topBins.as<uint32_t>();
   dp.workPos = wp.workPos; dp.workEG = wp.workEG;
-  dp.nWorkPtr = wp.workStart + nNavAll;
+  dp.nWorkPtr = nWorkPtr;
   dp.nNav = nNav; dp.nBins = nBins;
   dp.zWinLo = h->zWin.as<float>();
   dp.zWinHi = h->zWin.as<float>() + h->zWinCapacity;
@@ -417,11 +559,16 @@ int enqueue(b200seed_handle* h) {
   dp.conf = conf ? 1 : 0;
   dp.counters = gp.counters;
   dp.status = gp.status;
-  k_doublets<false><<<h->smCount * h->doubletBlocksPerSM[0], kDoubletWarps * 32, 0, s>>>(dp);
+  if (orthogonal) {
+    kdp.d = dp;
+    k_doublets_kd<false><<<h->smCount * h->doubletBlocksPerSM[0], kDoubletWarps * 32, 0, s>>>(kdp);
+  } else {
+    k_doublets<false><<<h->smCount * h->doubletBlocksPerSM[0], kDoubletWarps * 32, 0, s>>>(dp);
+  }
   ++launches;
 
   // ---- slot prefix, chunk plan; the host reads the plan (the one synchronisation inside a call) ---
-  const uint32_t nTiles = std::max<uint32_t>(1, (nTotal + kTile - 1) / kTile);
+  const uint32_t nTiles = std::max<uint32_t>(1, (itemsMax + kTile - 1) / kTile);
   const int nStreams = h->chunkStreams;
   const unsigned long long arenaRecordsMax =
       std::max<unsigned long long>(h->arenaMaxBytes / 36ull / (unsigned long long)nStreams, 4ull * kMaxListLength);
@@ -529,7 +676,13 @@ int enqueue(b200seed_handle* h) {
     dpc.classList = lists;
     dpc.rec = h->arenaRec[a].as<DoubletRecord>();
     dpc.key = h->arenaKey[a].as<float>();
-    k_doublets<true><<<h->smCount * h->doubletBlocksPerSM[1], kDoubletWarps * 32, 0, cs>>>(dpc);
+    if (orthogonal) {
+      KdDoubletParams kdc = kdp;
+      kdc.d = dpc;
+      k_doublets_kd<true><<<h->smCount * h->doubletBlocksPerSM[1], kDoubletWarps * 32, 0, cs>>>(kdc);
+    } else {
+      k_doublets<true><<<h->smCount * h->doubletBlocksPerSM[1], kDoubletWarps * 32, 0, cs>>>(dpc);
+    }
     CUDA_TRY(cudaEventRecord(h->evChunk[2 * c], cs));
     sp.rec = dpc.rec;
     sp.key = dpc.key;
@@ -572,7 +725,7 @@ int enqueue(b200seed_handle* h) {
   }
   if (nChunks == 0) h->lastDoublets = dp;
   CUDA_TRY(cudaGetLastError());
-  sp.nWorkPtr = wp.workStart + nNavAll;
+  sp.nWorkPtr = nWorkPtr;
   h->launches = launches;
   if (conf) {
     ConfParams& cf = h->confParams;
@@ -603,6 +756,7 @@ int enqueue(b200seed_handle* h) {
   cp.outCapacity = a.outCapacity;
   cp.seedOffsets = a.dSeedOffsets;
   cp.workStart = wp.workStart;
+  cp.eventFirstItem = eventFirstItem;
   cp.seedStart = h->seedStart.as<uint32_t>();
   cp.nEvents = nEvents; cp.nNav = nNav;
   cp.counters = gp.counters;
@@ -754,12 +908,33 @@ int b200seed_plan_tables(const b200seed_config* cfg, void* deviceConfig, uint64_
   return B200SEED_OK;
 }
 
+static int create_impl(const b200seed_config* cfg, const b200seed_orthogonal_options* orthOpt, int device, b200seed_handle** out);
+
 int b200seed_create(const b200seed_config* cfg, int device, b200seed_handle** out) {
+  return create_impl(cfg, nullptr, device, out);
+}
+
+int b200seed_orthogonal_config_init(b200seed_config* cfg, b200seed_orthogonal_options* opt) {
+  if (cfg == nullptr || opt == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL argument");
+  config_defaults(*cfg);  // the shared members have the grid algorithm's defaults (OrthogonalTripletSeedingAlgorithm.hpp:38-186)
+  opt->zOutermostLayersMin = -2700.f;
+  opt->zOutermostLayersMax = 2700.f;
+  opt->deltaPhiMax = 0.085f;
+  return B200SEED_OK;
+}
+
+int b200seed_create_orthogonal(const b200seed_config* cfg, const b200seed_orthogonal_options* opt, int device,
+                               b200seed_handle** out) {
+  if (opt == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL argument");
+  return create_impl(cfg, opt, device, out);
+}
+
+static int create_impl(const b200seed_config* cfg, const b200seed_orthogonal_options* orthOpt, int device, b200seed_handle** out) {
   if (cfg == nullptr || out == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL argument");
   *out = nullptr;
   auto* h = new b200seed_handle;
   PlanError err;
-  if (!make_host_plan(*cfg, h->plan, err)) {
+  if (!(orthOpt != nullptr ? make_orthogonal_plan(*cfg, *orthOpt, h->plan, err) : make_host_plan(*cfg, h->plan, err))) {
     delete h;
     return fail(err.code, err.message);
   }
@@ -912,7 +1087,8 @@ void b200seed_destroy(b200seed_handle* h) {
                     &h->seedStart, &h->tileSums, &h->tilePrefix, &h->outB, &h->outM, &h->outT, &h->outQ,
                     &h->outZ, &h->seedOffsets, &h->counters, &h->status, &h->zWin, &h->rec, &h->recZ, &h->recBegin,
                     &h->recCount, &h->slot2B, &h->slot2M, &h->slot2T, &h->slot2Q, &h->slot2Z, &h->slot2Count,
-                    &h->confHead, &h->confNext, &h->confState, &h->confDirty}) {
+                    &h->confHead, &h->confNext, &h->confState, &h->confDirty, &h->orthPosOrig, &h->orthPosPhi,
+                    &h->orthNodes, &h->orthCoreOffsets, &h->orthNodeOffsets, &h->orthRRange}) {
     b->release();
   }
   if (h->hConfState != nullptr) cudaFreeHost(h->hConfState);
@@ -1183,7 +1359,7 @@ static int run_host_batch(b200seed_handle* h, uint32_t nEvents, const uint32_t* 
     CUDA_TRY(cudaStreamSynchronize(s));  // the staging vectors go out of scope
   }
   const size_t K = std::max<uint32_t>(h->plan.seedsPerMiddle, 1);
-  const size_t maxSeeds = std::max<size_t>(1, (size_t)nTotal * K);
+  const size_t maxSeeds = std::max<size_t>(1, (size_t)nTotal * K * (h->plan.orthogonal ? 2 : 1));
   CUDA_TRY(h->outB.reserve(maxSeeds * 4));
   CUDA_TRY(h->outM.reserve(maxSeeds * 4));
   CUDA_TRY(h->outT.reserve(maxSeeds * 4));
@@ -1196,6 +1372,7 @@ static int run_host_batch(b200seed_handle* h, uint32_t nEvents, const uint32_t* 
     a.nEvents = nEvents; a.nTotal = nTotal; a.dOffsets = h->inOffsets.as<uint32_t>();
     a.x = h->inX.as<float>(); a.y = h->inY.as<float>(); a.z = h->inZ.as<float>(); a.r = h->inR.as<float>();
     a.varZ = h->inVarZ.as<float>(); a.varR = h->inVarR.as<float>(); a.dPhi = dPhi;
+    if (meas == nullptr) { a.hx = x; a.hy = y; a.hz = z; a.hr = r; a.hOffsets = spOffsets; }
     a.nZWin = (int)nMerged;
     a.dZWinOffsets = dWinOffsets;
     a.vertexCuts = h->plan.useVertexZCuts || nZWin > 0 || win.offsets != nullptr;

@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 from . import config as cfgmod
-from .config import Config, Counters, Doublets, Info, Seeds
+from .config import Config, Counters, Doublets, Info, OrthogonalOptions, Seeds
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200SEED_LIB", os.path.join(_HERE, "libacts_b200_seeding.so"))  # override: kernel experiments
@@ -22,6 +22,7 @@ LIB_PATH = os.environ.get("B200SEED_LIB", os.path.join(_HERE, "libacts_b200_seed
 # every symbol include/acts_b200_seeding.h declares
 EXPORTED_SYMBOLS = [
     "b200seed_config_init", "b200seed_plan_info", "b200seed_plan_tables", "b200seed_create",
+    "b200seed_orthogonal_config_init", "b200seed_create_orthogonal",
     "b200seed_destroy", "b200seed_last_error", "b200seed_alloc_pinned", "b200seed_free_pinned",
     "b200seed_get_info", "b200seed_get_counters",
     "b200seed_get_stage_times", "b200seed_get_stage_times_ex", "b200seed_set_phi_sector", "b200seed_estimate_params",
@@ -58,6 +59,8 @@ def lib():
         L.b200seed_plan_info.argtypes = [C.POINTER(Config), C.POINTER(Info)]
         L.b200seed_plan_tables.argtypes = [C.POINTER(Config), vp, u64, vp, vp, vp, vp, vp, vp]
         L.b200seed_create.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(vp)]
+        L.b200seed_orthogonal_config_init.argtypes = [C.POINTER(Config), C.POINTER(OrthogonalOptions)]
+        L.b200seed_create_orthogonal.argtypes = [C.POINTER(Config), C.POINTER(OrthogonalOptions), C.c_int, C.POINTER(vp)]
         L.b200seed_destroy.argtypes = [vp]
         L.b200seed_get_info.argtypes = [vp, C.POINTER(Info)]
         L.b200seed_get_counters.argtypes = [vp, C.POINTER(Counters)]
@@ -84,6 +87,10 @@ def lib():
 
 def config_init(cfg_ref):
     lib().b200seed_config_init(cfg_ref)
+
+
+def orthogonal_config_init(cfg_ref, opt_ref):
+    lib().b200seed_orthogonal_config_init(cfg_ref, opt_ref)
 
 
 def _check(rc: int):
@@ -127,10 +134,15 @@ def plan_tables(cfg: Config) -> dict:
 class SeedingEngine:
     """One handle = one device + one stream (see the header's threading contract)."""
 
-    def __init__(self, cfg: Config, device: int = 0):
+    def __init__(self, cfg: Config, device: int = 0, orthogonal: OrthogonalOptions | None = None):
+        """``orthogonal`` given: an OrthogonalTripletSeedingAlgorithm handle (k-d-tree candidate provider)."""
         self._h = C.c_void_p()
         self.cfg = cfg
-        _check(lib().b200seed_create(C.byref(cfg), device, C.byref(self._h)))
+        self.orthogonal = orthogonal
+        if orthogonal is not None:
+            _check(lib().b200seed_create_orthogonal(C.byref(cfg), C.byref(orthogonal), device, C.byref(self._h)))
+        else:
+            _check(lib().b200seed_create(C.byref(cfg), device, C.byref(self._h)))
         self.device = device
 
     def close(self):
@@ -236,7 +248,7 @@ class SeedingEngine:
         ``out`` may hold caller-owned (e.g. pinned) seed columns that are reused from call to call."""
         cols = self._cols(ev)
         n = cols[0].size
-        cap = capacity if capacity is not None else max(16, n * 6)
+        cap = capacity if capacity is not None else max(16, n * (12 if self.orthogonal is not None else 6))
         if out is not None:
             s = Seeds()
             s.bottom, s.middle, s.top = _p(out["bottom"]), _p(out["middle"]), _p(out["top"])
@@ -273,7 +285,7 @@ class SeedingEngine:
         arrs = self._cols(cols)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
         n_events = offsets.size - 1
-        cap = capacity if capacity is not None else max(16, int(offsets[-1]) * 6)
+        cap = capacity if capacity is not None else max(16, int(offsets[-1]) * (12 if self.orthogonal is not None else 6))
         if out is not None:
             cap = min(int(a.size) for a in out.values())
             s = Seeds()

@@ -770,3 +770,75 @@ def test_random_configurations_match_oracle(plugin, O):
         if done == 48:
             break
     assert done == 48
+
+
+ORTH_VARIANTS = [
+    dict(),
+    dict(interactionPointCut=1),
+    dict(useExtraCuts=1),
+    dict(useVariableMiddleSPRange=1, deltaRMiddleMinSPRange=25.0, deltaRMiddleMaxSPRange=40.0),
+    dict(deltaPhiMax=0.025, maxSeedsPerSpM=4, sigmaScattering=2.0),
+    dict(deltaPhiMax=0.2, zOutermostLayersMin=-650.0, zOutermostLayersMax=800.0, phiMin=-2.5, phiMax=2.0),
+    dict(deltaRMinTop=float("nan"), deltaRMaxTop=float("nan"), deltaRMinBottom=6.0, deltaRMaxBottom=150.0),
+    dict(deltaRMinTop=10.0, deltaRMaxTop=120.0, deltaRMinBottom=float("nan"), deltaRMaxBottom=float("nan")),
+    dict(collisionRegionMin=-80.0, collisionRegionMax=120.0, cotThetaMax=3.0, deltaZMin=-300.0, deltaZMax=250.0),
+    dict(useDeltaRinsteadOfTopRadius=1, compatSeedLimit=3, numSeedIncrement=100.0, impactWeightFactor=100.0),
+]
+
+
+@pytest.mark.parametrize("variant", range(len(ORTH_VARIANTS)))
+def test_orthogonal_seeder_matches_oracle(plugin, O, variant):
+    """OrthogonalTripletSeedingAlgorithm (k-d-tree candidate provider, both z-direction groups per middle) through
+    b200seed_create_orthogonal: seeds bit-identical to the oracle IN THE REFERENCE'S ORDER (the oracle is pinned to
+    the reference's own execute() on the same variants, tests/test_reference_pin.py)."""
+    from acts_b200 import config, events
+
+    over = ORTH_VARIANTS[variant]
+    cfg, opt = config.orthogonal_config(plugin.orthogonal_config_init, **over)
+    eng = plugin.SeedingEngine(cfg, orthogonal=opt)
+    orc = O.Oracle(*config.orthogonal_config(O.orthogonal_config_init, **over))
+    evs = [events.muon_gun_event(variant), events.pileup_event(variant, mu=5), events.pileup_event(40 + variant, mu=30)]
+    if variant in (0, 2, 4):
+        evs.append(events.itk_pileup_event(variant, mu=10))
+    refs = [orc.run(ev) for ev in evs]
+    assert sum(r["bottom"].size for r in refs) > 0
+    for k, (ev, ref) in enumerate(zip(evs, refs)):
+        got = eng.run(ev)
+        assert O.seed_set(got) == O.seed_set(ref), f"variant {variant} event {k}: seed set differs"
+        assert _same_bits(got, ref), f"variant {variant} event {k}: seed order differs"
+        cnt = eng.counters()
+        assert cnt["nMiddles"] == ref["counters"]["nMiddles"]
+        assert cnt["nBottomDoublets"] == ref["counters"]["nBottomDoublets"]
+        assert cnt["nTopDoublets"] == ref["counters"]["nTopDoublets"]
+    cols, offsets = events.concat_events(evs)
+    for got, ref in zip(eng.run_batch(cols, offsets), refs):
+        assert _same_bits(got, ref)
+    eng.close()
+
+
+def test_orthogonal_seeder_edge_cases_and_full_size(plugin, O):
+    """Empty / tiny events (the tree degenerates to a leaf), quantised coordinates (equal keys in the tree's
+    partition / sort and in the cotTheta sort), a <mu>=200 event, and the unsupported seedConfirmation mode."""
+    from acts_b200 import config, events
+
+    cfg, opt = config.orthogonal_config(plugin.orthogonal_config_init)
+    eng = plugin.SeedingEngine(cfg, orthogonal=opt)
+    orc = O.Oracle(*config.orthogonal_config(O.orthogonal_config_init))
+    ev = events.pileup_event(0, mu=5)
+    for n in (0, 1, 3, 4, 5, 9, 130):
+        sub = {k: v[:n] for k, v in ev.items()}
+        assert _same_bits(eng.run(sub), orc.run(sub)), n
+    ev = events.pileup_event(5, mu=30)
+    q = {k: (np.round(v * 4) / 4).astype(np.float32) if k in ("x", "y", "z") else v for k, v in ev.items()}
+    q["r"] = (np.round(np.hypot(q["x"], q["y"]) * 2) / 2).astype(np.float32)
+    ref = orc.run(q)
+    assert ref["bottom"].size > 0 and _same_bits(eng.run(q), ref)
+    big = events.pileup_event(3, mu=200)
+    ref = orc.run(big)
+    assert ref["bottom"].size > 50_000
+    assert _same_bits(eng.run(big), ref)
+    eng.close()
+    cfg, opt = config.orthogonal_config(plugin.orthogonal_config_init, **config.confirmation_overrides())
+    with pytest.raises(plugin.SeedingError) as exc:
+        plugin.SeedingEngine(cfg, orthogonal=opt)
+    assert exc.value.code == config.ERR_UNSUPPORTED
