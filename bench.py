@@ -555,6 +555,44 @@ def run_gpu(args):
                            "no tie replay); efficiency = exact seeds also found / exact seeds on one batch"}
         reng.close()
 
+    # ---- the other TripletSeeder caller: OrthogonalTripletSeedingAlgorithm (k-d-tree provider), reported separately ----
+    orthogonal = None
+    if args.orthogonal:
+        from oracle import ref as R
+        from oracle import oracle as O2
+
+        ocfg, oopt = config.orthogonal_config(plugin.orthogonal_config_init)
+        oeng = plugin.SeedingEngine(ocfg, device=local, orthogonal=oopt)
+        n_o = min(8, E)
+        ocols, ooff = events.concat_events(evs[:n_o])
+        oeng.run_batch(ocols, ooff)  # warm-up (workspaces)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            ores = oeng.run_batch(ocols, ooff)
+        o_s = (time.perf_counter() - t0) / reps
+        ost = oeng.stage_times_ms()
+        ocnt = oeng.counters()
+        orth_ref = None
+        if R.available() or R.build() is not None:
+            rr = R.Reference(*config.orthogonal_config(O2.orthogonal_config_init))
+            t0 = time.perf_counter()
+            rb = rr.run(evs[0])
+            ref_s = time.perf_counter() - t0
+            same = all(np.array_equal(ores[0][k].view(np.uint32), rb[k].view(np.uint32)) for k in ("bottom", "middle", "top", "quality", "vertexZ"))
+            orth_ref = {"seconds_per_event_one_core": ref_s, "identical_seeds_and_order": bool(same),
+                        "kind": "unmodified reference sources (oracle/_ref), one event, one host core"}
+            if not same:
+                sys.stderr.write("bench.py: PARITY FAILURE of the orthogonal seeder against the reference\n")
+        orthogonal = {"value": n_o / o_s, "unit": UNIT, "n_gpus": 1, "events_per_call": n_o, "ms_per_call": o_s * 1e3,
+                      "host_tree_build_and_upload_ms": ost.get("grid"), "doublet_count_ms": ost.get("doublet_count"),
+                      "doublet_fill_ms": ost.get("doublet_fill"), "seed_middles_ms": ost.get("seed_middles"),
+                      "seeds": int(sum(r_["bottom"].size for r_ in ores)), "doublets": int(ocnt["nBottomDoublets"] + ocnt["nTopDoublets"]),
+                      "reference": orth_ref,
+                      "note": "b200seed_create_orthogonal handle, host buffers in / seeds out through b200seed_run_batch "
+                              "(wall clock incl. the host-side k-d tree construction); same <mu>=200 events and cut set"}
+        oeng.close()
+
     # ---- roofline ------------------------------------------------------------------------------------------
     peak_gbs, peak_src, sm_max = load_peaks()
     b0 = batches[(args.warmup + min(args.steps, 8) - 1) % n_batches]
@@ -637,6 +675,7 @@ def run_gpu(args):
         "compute": fp32,
         "relaxed_float": relaxed,
         "latency": latency,
+        "orthogonal": orthogonal,
         "cpu_baseline": cpu,
         "counters_last_step": cnt,
         "seeds_last_step": int(n_seeds_last),
@@ -668,6 +707,7 @@ def main():
     ap.add_argument("--no-latency", dest="latency", action="store_false", help="skip the <mu>=300 latency block")
     ap.add_argument("--no-relaxed", dest="relaxed", action="store_false", help="skip the relaxedFloat fast-path report")
     ap.add_argument("--no-oracle-counters", dest="oracle_counters", action="store_false")
+    ap.add_argument("--no-orthogonal", dest="orthogonal", action="store_false", help="skip the OrthogonalTripletSeedingAlgorithm report")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
