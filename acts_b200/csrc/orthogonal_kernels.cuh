@@ -9,9 +9,9 @@
 //                       increasing-z group ("lh") and the decreasing-z group ("hl"), in that order (.cpp:294-306)
 //   k_orth_fill_work    work list from the exclusive scan of the per-position item counts
 //   k_doublets_kd<fill> the two-pass doublet stage of k_doublets with the r-sorted bin windows replaced by a
-//                       range search: one warp walks the event's tree (nodes in pre-order with skip indices, no
-//                       stack) and tests the elements of every reported node in element order; deltaR is an
-//                       explicit cut (DoubletSeedFinder.cpp:126-130, spacePointsSortedByRadius = false)
+//                       range search: one THREAD per work item walks the event's tree (nodes in pre-order with skip
+//                       indices, no stack) and tests the elements of every reported node in element order; deltaR
+//                       is an explicit cut (DoubletSeedFinder.cpp:126-130, spacePointsSortedByRadius = false)
 #pragma once
 
 #include "kd_tree_host.hpp"
@@ -95,53 +95,20 @@ struct KdDoubletParams {
   const float* posPhi;
 };
 
-// One side (bottom or top candidates) of one work item: the range search + the doublet cuts.  Count pass: returns
-// the number of survivors of the deltaR window and the (z, r) cuts (the slot size).  Fill pass: survivors are queued
-// and finished 32 at a time like doublet_side; returns the number of doublets written.
+// One side (bottom or top candidates) of one work item, walked by ONE THREAD: the range search + the doublet cuts.
+// Count pass: returns the number of survivors of the deltaR window and the (z, r) cuts (the slot size).  Fill pass:
+// every survivor is finished on the spot and written to the slot in emission order; returns the number of doublets.
+// The 32 work items of a warp are consecutive in the work list = neighbours in the tree's element order (both z
+// directions of a middle, then the next middle), so their walks visit nearly the same nodes (L1 hits) and have
+// similar lengths.
 template <bool kBottom, bool kFill>
 __device__ __forceinline__ uint32_t kd_side(const KdDoubletParams& p, const MiddleSp& mid, const KdBox& box,
-                                            uint32_t corePos0, const KdNodeDev* nodes, uint32_t nNodes, uint32_t* queue,
+                                            uint32_t corePos0, const KdNodeDev* nodes, uint32_t nNodes,
                                             DoubletRecord* recOut, float* keyOut, float& cotMin, float& cotMax) {
   const DeviceConfig& cfg = p.d.cfg;
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t ltMask = (1u << lane) - 1u;
   const float dRMin = kBottom ? cfg.dRMinB : cfg.dRMinT, dRMax = kBottom ? cfg.dRMaxB : cfg.dRMaxT;
-  uint32_t myCount = 0, qn = 0, nOut = 0;
+  uint32_t n = 0;
   float mn = 3.0e38f, mx = -3.0e38f;
-  auto drain = [&](uint32_t n) {  // finish the first n (<= 32) queued candidates, in order
-    bool ok = false;
-    DoubletRecord out;
-    if (lane < n) {
-      const uint32_t o = queue[lane];
-      const float2 zr = ldg2(p.d.pZR + o), xy = ldg2(p.d.pXY + o), var = ldg2(p.d.pVar + o);
-      float dR, dZ;
-      doublet_zr_cuts<kBottom>(cfg, mid, zr.x, zr.y, dR, dZ);
-      DoubletRec rec;
-      ok = doublet_finish<kBottom>(cfg, mid, dR, dZ, xy.x, xy.y, zr.y, var.x, var.y, nullptr, nullptr, 0, rec, true);
-      out.pos = o; out.cotTheta = rec.cotTheta; out.iDeltaR = rec.iDeltaR; out.er = rec.er;
-      out.u = rec.u; out.v = rec.v; out.xNew = rec.xNew; out.yNew = rec.yNew;
-    }
-    const uint32_t mask = __ballot_sync(0xffffffffu, ok);
-    if (ok) {
-      const uint32_t d = nOut + (uint32_t)__popc(mask & ltMask);
-      float4* dst = reinterpret_cast<float4*>(recOut + d);
-      dst[0] = make_float4(__uint_as_float(out.pos), out.cotTheta, out.iDeltaR, out.er);
-      dst[1] = make_float4(out.u, out.v, out.xNew, out.yNew);
-      keyOut[d] = out.cotTheta;
-      mn = fminf(mn, out.cotTheta);
-      mx = fmaxf(mx, out.cotTheta);
-    }
-    nOut += (uint32_t)__popc(mask);
-    const uint32_t rest = qn - n;
-    for (uint32_t base = 0; base < rest; base += 32u) {
-      const uint32_t i = base + lane;
-      const uint32_t carry = i < rest ? queue[i + n] : 0u;
-      __syncwarp();
-      if (i < rest) queue[i] = carry;
-      __syncwarp();
-    }
-    qn = rest;
-  };
   // KDTreeNode::rangeSearchMapDiscard as a pre-order scan: a node that does not overlap the box is skipped with
   // its subtree (the reference tests the overlap before it descends into a child, KDTree.hpp:377-385); a leaf,
   // or an internal node the box covers completely, reports its elements in element order (:363-374,386-395).
@@ -158,55 +125,45 @@ __device__ __forceinline__ uint32_t kd_side(const KdDoubletParams& p, const Midd
                            (box.mn[2] <= a.z) & (box.mx[2] >= b.y);
     if (c.y != 0u && !contained) { ++id; continue; }
     const uint32_t e0 = corePos0 + __float_as_uint(b.z), e1 = corePos0 + __float_as_uint(b.w);
-    for (uint32_t base = e0; base < e1; base += 32u) {
-      const uint32_t o = base + lane;
-      bool pass = false;
-      if (o < e1) {
-        const float2 zr = ldg2(p.d.pZR + o);
-        bool inside = contained;
-        if (!inside) {
-          const float phi = __ldg(p.posPhi + o);
-          inside = (box.mn[0] <= phi) & (phi < box.mx[0]) & (box.mn[1] <= zr.y) & (zr.y < box.mx[1]) &
-                   (box.mn[2] <= zr.x) & (zr.x < box.mx[2]);
-        }
-        if (inside) {
-          float dR, dZ;
-          const bool zrOk = doublet_zr_cuts<kBottom>(cfg, mid, zr.x, zr.y, dR, dZ);
-          pass = zrOk && !outside_range(dR, dRMin, dRMax);  // (deltaR first in the reference: both are pure rejections)
-        }
+    for (uint32_t o = e0; o < e1; ++o) {
+      const float2 zr = ldg2(p.d.pZR + o);
+      if (!contained) {
+        const float phi = __ldg(p.posPhi + o);
+        const bool inside = (box.mn[0] <= phi) & (phi < box.mx[0]) & (box.mn[1] <= zr.y) & (zr.y < box.mx[1]) &
+                            (box.mn[2] <= zr.x) & (zr.x < box.mx[2]);
+        if (!inside) continue;
       }
+      float dR, dZ;
+      if (!doublet_zr_cuts<kBottom>(cfg, mid, zr.x, zr.y, dR, dZ)) continue;
+      if (outside_range(dR, dRMin, dRMax)) continue;  // (first in the reference: both are pure rejections)
       if (!kFill) {
-        myCount += pass ? 1u : 0u;
+        ++n;
       } else {
-        const uint32_t mask = __ballot_sync(0xffffffffu, pass);
-        if (pass) queue[qn + (uint32_t)__popc(mask & ltMask)] = o;
-        qn += (uint32_t)__popc(mask);
-        __syncwarp();
-        while (qn >= 32u) drain(32u);  // qn < 32 + 32 before
+        const float2 xy = ldg2(p.d.pXY + o), var = ldg2(p.d.pVar + o);
+        DoubletRec rec;
+        if (!doublet_finish<kBottom>(cfg, mid, dR, dZ, xy.x, xy.y, zr.y, var.x, var.y, nullptr, nullptr, 0, rec, true)) continue;
+        float4* dst = reinterpret_cast<float4*>(recOut + n);
+        dst[0] = make_float4(__uint_as_float(o), rec.cotTheta, rec.iDeltaR, rec.er);
+        dst[1] = make_float4(rec.u, rec.v, rec.xNew, rec.yNew);
+        keyOut[n] = rec.cotTheta;
+        mn = fminf(mn, rec.cotTheta);
+        mx = fmaxf(mx, rec.cotTheta);
+        ++n;
       }
     }
     id = c.x;
   }
-  if (!kFill) {
-    for (int d = 16; d > 0; d >>= 1) myCount += __shfl_xor_sync(0xffffffffu, myCount, d);
-    return myCount;
-  }
-  if (qn > 0u) drain(qn);
-  for (int d = 16; d > 0; d >>= 1) {
-    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-  }
   cotMin = mn;
   cotMax = mx;
-  return nOut;
+  return n;
 }
 
+constexpr int kKdThreads = 128;
+
 template <bool kFill>
-__global__ void __launch_bounds__(kDoubletWarps * 32) k_doublets_kd(const __grid_constant__ KdDoubletParams kp) {
-  __shared__ uint32_t sQueue[kDoubletWarps][64];
+__global__ void __launch_bounds__(kKdThreads) k_doublets_kd(const __grid_constant__ KdDoubletParams kp) {
   const DoubletParams& p = kp.d;
-  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  uint32_t* queue = sQueue[wib];
+  const uint32_t lane = threadIdx.x & 31;
   const uint32_t itemFirst = kFill ? p.itemFirst : 0u;
   const uint32_t itemEnd = kFill ? p.itemEnd : *p.nWorkPtr;
   const uint32_t nItems = itemEnd - itemFirst;
@@ -214,91 +171,104 @@ __global__ void __launch_bounds__(kDoubletWarps * 32) k_doublets_kd(const __grid
   uint32_t maxFoot = 0, maxB = 0, maxT = 0;
   for (;;) {
     uint32_t it = 0;
-    if (lane == 0) it = atomicAdd(p.workCounter, 1u);
+    if (lane == 0) it = atomicAdd(p.workCounter, 32u);  // a warp takes 32 consecutive items
     it = __shfl_sync(0xffffffffu, it, 0);
     if (it >= nItems) break;
-    const uint32_t w = itemFirst + it;
-    uint32_t capT = 0, capB = 0;
-    if (kFill) {
-      capT = __ldg(p.capT + w);
-      capB = __ldg(p.capB + w);
-      if (capT == 0u || capB == 0u) {
-        if (lane == 0) {
+    it += lane;
+    if (it < nItems) {
+      const uint32_t w = itemFirst + it;
+      uint32_t capT = 0, capB = 0;
+      bool live = true;
+      if (kFill) {
+        capT = __ldg(p.capT + w);
+        capB = __ldg(p.capB + w);
+        if (capT == 0u || capB == 0u) {
           MiddleHeader h{};
           h.capB = capB;
           p.hdr[w] = h;
           p.slotCount[w] = 0;
+          live = false;
         }
-        continue;
       }
-    }
-    const uint32_t m = __ldg(p.workPos + w);
-    const uint32_t eg = __ldg(p.workEG + w);
-    const uint32_t ev = eg >> 1;
-    const int dir = (int)(eg & 1u);
-    const uint32_t corePos0 = __ldg(kp.coreOffsets + ev);
-    const uint32_t node0 = __ldg(kp.nodeOffsets + ev), nNodes = __ldg(kp.nodeOffsets + ev + 1) - node0;
-    const KdNodeDev* nodes = kp.nodes + node0;
-    MiddleSp mid;
-    {
-      const float2 mxy = ldg2(p.pXY + m), mzr = ldg2(p.pZR + m), mvar = ldg2(p.pVar + m);
-      mid.x = mxy.x; mid.y = mxy.y; mid.z = mzr.x; mid.r = mzr.y; mid.varZ = mvar.x; mid.varR = mvar.y;
-      middle_info(mid);
-    }
-    KdBox boxB, boxT;
-    kd_search_boxes(kp.orth, __ldg(kp.posPhi + m), mid.r, mid.z, dir, boxB, boxT);
-    const bool searchable = !kd_degenerate(boxB) && !kd_degenerate(boxT);  // CylindricalSpacePointKDTree.cpp:226,241
-    if (!kFill) {
-      ++cntMiddles;
-      float a, b;
-      if (searchable) {
-        capT = kd_side<false, false>(kp, mid, boxT, corePos0, nodes, nNodes, queue, nullptr, nullptr, a, b);
-        if (capT != 0u) capB = kd_side<true, false>(kp, mid, boxB, corePos0, nodes, nNodes, queue, nullptr, nullptr, a, b);
-      }
-      if (capB == 0u) capT = 0u;
-      if (capB > kMaxListLength || capT > kMaxListLength) {
-        if (lane == 0) atomicOr(p.status, kStatusOverflowDoublets);
-        capB = 0; capT = 0;
-      }
-      capB = (capB + 3u) & ~3u;
-      capT = (capT + 3u) & ~3u;
-      if (lane == 0) { p.capB[w] = capB; p.capT[w] = capT; }
-      if (capB != 0u) {
-        const uint32_t foot = seed_carve(capB, capT).minBytes;
-        maxFoot = foot > maxFoot ? foot : maxFoot;
-        maxB = capB > maxB ? capB : maxB;
-        maxT = capT > maxT ? capT : maxT;
-      }
-    } else {
-      const unsigned long long slot = p.slotPrefix[w] - p.slotPrefix[p.itemFirst];
-      DoubletRecord* recSlot = p.rec + slot;
-      float* keySlot = p.key + slot;
-      float mnT = 0.f, mxT = 0.f, mnB = 0.f, mxB = 0.f;
-      const uint32_t nT = kd_side<false, true>(kp, mid, boxT, corePos0, nodes, nNodes, queue, recSlot + capB, keySlot + capB, mnT, mxT);
-      uint32_t nB = 0;
-      if (nT != 0u) nB = kd_side<true, true>(kp, mid, boxB, corePos0, nodes, nNodes, queue, recSlot, keySlot, mnB, mxB);
-      const bool go = nT != 0u && nB != 0u;
-      if (lane == 0) {
-        MiddleHeader h{};
-        h.capB = capB;
-        h.offset = (uint32_t)slot;
-        if (go) {
-          h.nB = nB; h.nT = nT;
-          h.cotMinB = float_to_ordered(mnB); h.cotMaxB = float_to_ordered(mxB);
-          h.cotMinT = float_to_ordered(mnT); h.cotMaxT = float_to_ordered(mxT);
-          const SeedCarve cv = seed_carve(nB, nT);
-          p.carve[w] = cv;
-          const uint32_t foot = cv.minBytes;
-          int c = 0;
-          while (c < kSpillClass && foot > p.classBytes[c]) ++c;
-          p.classList[(size_t)c * p.classStride + atomicAdd(p.classCount + c, 1u)] = w;
+      if (live) {
+        const uint32_t m = __ldg(p.workPos + w);
+        const uint32_t eg = __ldg(p.workEG + w);
+        const uint32_t ev = eg >> 1;
+        const int dir = (int)(eg & 1u);
+        const uint32_t corePos0 = __ldg(kp.coreOffsets + ev);
+        const uint32_t node0 = __ldg(kp.nodeOffsets + ev), nNodes = __ldg(kp.nodeOffsets + ev + 1) - node0;
+        const KdNodeDev* nodes = kp.nodes + node0;
+        MiddleSp mid;
+        {
+          const float2 mxy = ldg2(p.pXY + m), mzr = ldg2(p.pZR + m), mvar = ldg2(p.pVar + m);
+          mid.x = mxy.x; mid.y = mxy.y; mid.z = mzr.x; mid.r = mzr.y; mid.varZ = mvar.x; mid.varR = mvar.y;
+          middle_info(mid);
+        }
+        KdBox boxB, boxT;
+        kd_search_boxes(kp.orth, __ldg(kp.posPhi + m), mid.r, mid.z, dir, boxB, boxT);
+        const bool searchable = !kd_degenerate(boxB) && !kd_degenerate(boxT);  // CylindricalSpacePointKDTree.cpp:226,241
+        if (!kFill) {
+          ++cntMiddles;
+          float a, b;
+          if (searchable) {
+            capT = kd_side<false, false>(kp, mid, boxT, corePos0, nodes, nNodes, nullptr, nullptr, a, b);
+            if (capT != 0u) capB = kd_side<true, false>(kp, mid, boxB, corePos0, nodes, nNodes, nullptr, nullptr, a, b);
+          }
+          if (capB == 0u) capT = 0u;
+          if (capB > kMaxListLength || capT > kMaxListLength) {
+            atomicOr(p.status, kStatusOverflowDoublets);
+            capB = 0; capT = 0;
+          }
+          capB = (capB + 3u) & ~3u;  // slots and their two halves start on 16-byte boundaries of the key array (TMA)
+          capT = (capT + 3u) & ~3u;
+          p.capB[w] = capB;
+          p.capT[w] = capT;
+          if (capB != 0u) {
+            const uint32_t foot = seed_carve(capB, capT).minBytes;
+            maxFoot = foot > maxFoot ? foot : maxFoot;
+            maxB = capB > maxB ? capB : maxB;
+            maxT = capT > maxT ? capT : maxT;
+          }
         } else {
-          p.slotCount[w] = 0;
+          const unsigned long long slot = p.slotPrefix[w] - p.slotPrefix[p.itemFirst];
+          DoubletRecord* recSlot = p.rec + slot;
+          float* keySlot = p.key + slot;
+          float mnT = 0.f, mxT = 0.f, mnB = 0.f, mxB = 0.f;
+          const uint32_t nT = kd_side<false, true>(kp, mid, boxT, corePos0, nodes, nNodes, recSlot + capB, keySlot + capB, mnT, mxT);
+          uint32_t nB = 0;
+          if (nT != 0u) nB = kd_side<true, true>(kp, mid, boxB, corePos0, nodes, nNodes, recSlot, keySlot, mnB, mxB);
+          const bool go = nT != 0u && nB != 0u;
+          MiddleHeader h{};
+          h.capB = capB;
+          h.offset = (uint32_t)slot;
+          if (go) {
+            h.nB = nB; h.nT = nT;
+            h.cotMinB = float_to_ordered(mnB); h.cotMaxB = float_to_ordered(mxB);
+            h.cotMinT = float_to_ordered(mnT); h.cotMaxT = float_to_ordered(mxT);
+            const SeedCarve cv = seed_carve(nB, nT);
+            p.carve[w] = cv;
+            const uint32_t foot = cv.minBytes;
+            int c = 0;
+            while (c < kSpillClass && foot > p.classBytes[c]) ++c;
+            p.classList[(size_t)c * p.classStride + atomicAdd(p.classCount + c, 1u)] = w;
+            cntB += nB;
+            cntT += nT;
+          } else {
+            p.slotCount[w] = 0;
+          }
+          p.hdr[w] = h;
         }
-        p.hdr[w] = h;
       }
-      if (go) { cntB += nB; cntT += nT; }
     }
+  }
+  // per-warp totals -> global counters
+  for (int d = 16; d > 0; d >>= 1) {
+    cntMiddles += __shfl_xor_sync(0xffffffffu, cntMiddles, d);
+    cntB += __shfl_xor_sync(0xffffffffu, cntB, d);
+    cntT += __shfl_xor_sync(0xffffffffu, cntT, d);
+    maxFoot = max(maxFoot, __shfl_xor_sync(0xffffffffu, maxFoot, d));
+    maxB = max(maxB, __shfl_xor_sync(0xffffffffu, maxB, d));
+    maxT = max(maxT, __shfl_xor_sync(0xffffffffu, maxT, d));
   }
   if (lane == 0) {
     if (!kFill) {

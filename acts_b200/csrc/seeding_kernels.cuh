@@ -462,25 +462,46 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_bins(const __grid_constan
       __syncthreads();
       if (threadIdx.x < 32) warp_sort_replay_ties(W, (int)n, bin_flagged);
       __syncthreads();
-      // tied element k (in replay order) of a group takes the group's k-th canonical slot
-      uint32_t myDest = 0xFFFFFFFFu, myIdx = 0;
-      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {  // few tied elements: at most one per thread in practice
-        const TieItem it = W[i];
-        if (!bin_flagged(it)) continue;
-        const uint32_t rank = it.val & 0x7fffffffu;
-        const uint32_t rb = __float_as_uint(it.key);
-        uint32_t g = rank;
-        while (g > 0 && (uint32_t)(keys[g - 1] >> 32) == rb) --g;
-        uint32_t before = 0;
-        for (uint32_t q = 0; q < i; ++q) before += (bin_flagged(W[q]) && __float_as_uint(W[q].key) == rb) ? 1u : 0u;
-        if (myDest != 0xFFFFFFFFu) {  // a thread owning several tied elements writes the earlier one now (distinct slots)
-          p.tmpIdx[b0 + myDest] = myIdx;
+      // Tied element k (in replay order) of a group takes the group's k-th canonical slot.  One warp walks W in
+      // order: the group of an element is the first canonical rank with its radius (lower bound over the sorted
+      // keys), its place inside the group comes from a ballot scan + a running member count per group (kept in
+      // binOf[b0 + g], free since k_scatter) -- linear in n however many elements tie.  The reassignments are
+      // staged in tmpIdx (free from here on), then patched into the keys.
+      uint32_t* grpCount = p.binOf + b0;
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) grpCount[i] = 0;
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        const uint32_t lane = threadIdx.x;
+        for (uint32_t base = 0; base < n; base += 32) {
+          const uint32_t i = base + lane;
+          TieItem it;
+          it.key = 0.f;
+          it.val = 0u;
+          if (i < n) it = W[i];
+          const bool flagged = i < n && bin_flagged(it);
+          const uint32_t rank = it.val & 0x7fffffffu;
+          const uint32_t rb = __float_as_uint(it.key);
+          uint32_t g = 0;
+          if (flagged) {
+            uint32_t lo = 0, hi = rank;
+            while (lo < hi) {
+              const uint32_t mid = (lo + hi) >> 1;
+              if ((uint32_t)(keys[mid] >> 32) < rb) lo = mid + 1; else hi = mid;
+            }
+            g = lo;
+          }
+          const uint32_t same = __match_any_sync(0xffffffffu, flagged ? g : 0x80000000u + lane);  // unflagged lanes match themselves only
+          const uint32_t before = (uint32_t)__popc(same & ((1u << lane) - 1u));
+          uint32_t carried = 0;
+          if (flagged && before == 0u) {  // first member of its group in this step: one lane per group
+            carried = grpCount[g];
+            grpCount[g] = carried + (uint32_t)__popc(same);
+          }
+          carried = __shfl_sync(0xffffffffu, carried, __ffs(same) - 1);
+          if (flagged) p.tmpIdx[b0 + g + carried + before] = (uint32_t)(keys[rank] & 0xffffffffull);
+          __syncwarp();
         }
-        myDest = g + before;
-        myIdx = (uint32_t)(keys[rank] & 0xffffffffull);
       }
-      // stage the reassignments in tmpIdx (free from here on), then patch keys
-      if (myDest != 0xFFFFFFFFu) p.tmpIdx[b0 + myDest] = myIdx;
       __syncthreads();
       for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
         const uint32_t rb = (uint32_t)(keys[i] >> 32);

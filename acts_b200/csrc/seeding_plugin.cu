@@ -93,7 +93,8 @@ struct b200seed_handle {
   int classThreads[kNumSeedClasses] = {};
   uint32_t classBytes[kNumSeedClasses] = {};
   int doubletBlocksPerSM[2] = {1, 1};  // count / fill
-  size_t arenaMaxBytes = (size_t)2048 << 20;  // B200SEED_ARENA_MB: doublet arena per chunk of middles
+  int kdBlocksPerSM[2] = {1, 1};       // orthogonal seeder: k_doublets_kd count / fill
+  size_t arenaMaxBytes = (size_t)8192 << 20;  // B200SEED_ARENA_MB: doublet arena per chunk of middles
   // constant tables
   DevBuf navBins, botOffsets, botBins, topOffsets, topBins;
   // per-batch workspaces
@@ -561,7 +562,7 @@ int enqueue(b200seed_handle* h) {
   dp.status = gp.status;
   if (orthogonal) {
     kdp.d = dp;
-    k_doublets_kd<false><<<h->smCount * h->doubletBlocksPerSM[0], kDoubletWarps * 32, 0, s>>>(kdp);
+    k_doublets_kd<false><<<h->smCount * h->kdBlocksPerSM[0], kKdThreads, 0, s>>>(kdp);
   } else {
     k_doublets<false><<<h->smCount * h->doubletBlocksPerSM[0], kDoubletWarps * 32, 0, s>>>(dp);
   }
@@ -679,7 +680,7 @@ int enqueue(b200seed_handle* h) {
     if (orthogonal) {
       KdDoubletParams kdc = kdp;
       kdc.d = dpc;
-      k_doublets_kd<true><<<h->smCount * h->doubletBlocksPerSM[1], kDoubletWarps * 32, 0, cs>>>(kdc);
+      k_doublets_kd<true><<<h->smCount * h->kdBlocksPerSM[1], kKdThreads, 0, cs>>>(kdc);
     } else {
       k_doublets<true><<<h->smCount * h->doubletBlocksPerSM[1], kDoubletWarps * 32, 0, cs>>>(dpc);
     }
@@ -988,7 +989,7 @@ static int create_impl(const b200seed_config* cfg, const b200seed_orthogonal_opt
   h->recPerSpacePoint = std::max<uint32_t>(env_u32("B200SEED_REC_PER_SP", 32), 1u);
   // the tie-order replay of the unstable sorts only makes sense when the keys are the reference's bit for bit
   h->exactTies = engineRelaxed ? 0 : (int)env_u32("B200SEED_EXACT_TIES", 1);
-  h->arenaMaxBytes = (size_t)std::max<uint32_t>(env_u32("B200SEED_ARENA_MB", 2048), 64u) << 20;
+  h->arenaMaxBytes = (size_t)std::max<uint32_t>(env_u32("B200SEED_ARENA_MB", 8192), 64u) << 20;
   CREATE_TRY(cudaEventCreate(&h->evCount));
   CREATE_TRY(cudaEventCreateWithFlags(&h->evPlan, cudaEventDisableTiming));
   h->chunkStreams = env_u32("B200SEED_CHUNK_STREAMS", 2) >= 2 ? 2 : 1;
@@ -1047,6 +1048,10 @@ static int create_impl(const b200seed_config* cfg, const b200seed_orthogonal_opt
     h->doubletBlocksPerSM[0] = std::max(1, b);
     CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_doublets<true>, kDoubletWarps * 32, 0));
     h->doubletBlocksPerSM[1] = std::max(1, b);
+    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_doublets_kd<false>, kKdThreads, 0));
+    h->kdBlocksPerSM[0] = std::max(1, b);
+    CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_doublets_kd<true>, kKdThreads, 0));
+    h->kdBlocksPerSM[1] = std::max(1, b);
   }
   CREATE_TRY(cudaFuncSetAttribute(k_sort_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->sortSmemCap * 16)));
   if (std::getenv("B200SEED_VERBOSE") != nullptr) {
