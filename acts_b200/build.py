@@ -43,7 +43,7 @@ def _stale(target, sources):
 
 def plugin_sources():
     names = ["seeding_plugin.cu", "host_plan.cpp", "seeding_abi.cpp", "engine_symbols.h", "seeding_kernels.cuh",
-             "seed_math.h", "host_plan.hpp"]
+             "orthogonal_kernels.cuh", "kd_tree_host.hpp", "seed_math.h", "host_plan.hpp"]
     return [os.path.join(CSRC, n) for n in names] + [os.path.join(ROOT, "include", "acts_b200_seeding.h")]
 
 
@@ -103,8 +103,9 @@ def build_host_mirror_test(force: bool = False) -> str:
     """C++20 driver of the host mirror class, linked against the plugin."""
     src = os.path.join(ROOT, "tests", "cpp", "host_mirror_main.cpp")
     hdr = os.path.join(ROOT, "acts_b200", "host", "GridTripletSeedingAlgorithm.hpp")
+    hdr2 = os.path.join(ROOT, "acts_b200", "host", "OrthogonalTripletSeedingAlgorithm.hpp")
     build_plugin()
-    if force or _stale(HOST_TEST_BIN, [src, hdr, PLUGIN_SO]):
+    if force or _stale(HOST_TEST_BIN, [src, hdr, hdr2, PLUGIN_SO]):
         cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=gnu++20", "-Wall", "-o", HOST_TEST_BIN, src,
                "-L" + os.path.dirname(PLUGIN_SO), "-lacts_b200_seeding", "-Wl,-rpath," + os.path.dirname(PLUGIN_SO)]
         res = subprocess.run(cmd, capture_output=True, text=True)

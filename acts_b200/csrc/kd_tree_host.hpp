@@ -12,8 +12,11 @@
 // calls, on the host, in the plugin's host layer -- construction is a sequential recursion over
 // in-place permutations; the per-middle range searches and everything after them run on the device.
 //
-// Output layout for the device: nodes in PRE-ORDER with a skip index (first node after the
-// subtree), so the range search is a stack-free scan `id = overlaps ? id + 1 : skip[id]`.
+// Output layout: nodes in PRE-ORDER with a skip index (first node after the subtree) and the left
+// child's index, local to the event; seeding_plugin.cu re-bases them into the batch-wide node array
+// of the device (node e = root of event e, ropes instead of skip indices), where the range search is
+// the stack-free scan `id = descend ? lhs[id] : rope[id]`.  This builder is the host-side twin of the
+// device construction (k_kd_split / k_kd_small) and is what B200SEED_KD_HOST=1 selects.
 #pragma once
 
 #include <algorithm>
@@ -28,12 +31,15 @@
 
 namespace B200SEED_NS {
 
+constexpr uint32_t kKdEnd = 0xFFFFFFFFu;  // rope of the last subtree: the search is over
+
 struct KdNodeDev {
   float mn[3], mx[3];    // bounding box (phi, r, z): [min, nextafter(max)) like KDTree::boundingBox
-  uint32_t begin, end;   // element positions inside the event
-  uint32_t skip;         // index (inside the event's node list) of the first node after this subtree
+  uint32_t begin, end;   // element positions (host builder: inside the event; on the device: packed, batch-wide)
+  uint32_t skip;         // rope: the node to continue with when this subtree is done or skipped (kKdEnd: none)
   uint32_t internal;     // 1: internal node, 0: leaf
-  uint32_t pad[2];
+  uint32_t lhs;          // internal nodes: left child; the right child is the left child's rope
+  uint32_t pad;
 };
 static_assert(sizeof(KdNodeDev) == 48, "three 16-byte words per node");
 
@@ -119,7 +125,8 @@ inline void build_kd_event(const DeviceConfig& cfg, uint32_t n, const float* x, 
         const std::size_t lhs = k + 1, rhs = lhs + size[lhs];
         size[k] = 1 + size[lhs] + size[rhs];
       }
-      out.nodes[k].skip = static_cast<uint32_t>(k) + size[k];
+      out.nodes[k].skip = static_cast<uint32_t>(k) + size[k];  // (== nodes.size(): end of the event's list)
+      out.nodes[k].lhs = static_cast<uint32_t>(k) + 1;
     }
   }
   out.posOrig.resize(elems.size());

@@ -25,7 +25,6 @@ struct OrthParams {
   uint32_t nEvents, nCoreTotal;
   const uint32_t* spOffsets;    // [nEvents + 1] the caller's events
   const uint32_t* coreOffsets;  // [nEvents + 1] selected space points (= tree elements) per event
-  const uint32_t* nodeOffsets;  // [nEvents + 1]
   const float* rMiddleRange;    // [2 * nEvents] variable middle range per event
   const uint32_t* posOrig;      // [nCoreTotal] element position -> index inside the caller's event
   const float* posPhi;          // [nCoreTotal]
@@ -89,9 +88,7 @@ __global__ void __launch_bounds__(256) k_orth_fill_work(const __grid_constant__ 
 struct KdDoubletParams {
   DoubletParams d;  // work list, slot sizes, arena, headers, class lists (binStart / nav tables unused)
   OrthDeviceConfig orth;
-  const uint32_t* coreOffsets;
-  const uint32_t* nodeOffsets;
-  const KdNodeDev* nodes;
+  const KdNodeDev* nodes;  // node e = root of event e
   const float* posPhi;
 };
 
@@ -103,7 +100,7 @@ struct KdDoubletParams {
 // similar lengths.
 template <bool kBottom, bool kFill>
 __device__ __forceinline__ uint32_t kd_side(const KdDoubletParams& p, const MiddleSp& mid, const KdBox& box,
-                                            uint32_t corePos0, const KdNodeDev* nodes, uint32_t nNodes,
+                                            const KdNodeDev* nodes, uint32_t rootNode,
                                             DoubletRecord* recOut, float* keyOut, float& cotMin, float& cotMax) {
   const DeviceConfig& cfg = p.d.cfg;
   const float dRMin = kBottom ? cfg.dRMinB : cfg.dRMinT, dRMax = kBottom ? cfg.dRMaxB : cfg.dRMaxT;
@@ -112,19 +109,19 @@ __device__ __forceinline__ uint32_t kd_side(const KdDoubletParams& p, const Midd
   // KDTreeNode::rangeSearchMapDiscard as a pre-order scan: a node that does not overlap the box is skipped with
   // its subtree (the reference tests the overlap before it descends into a child, KDTree.hpp:377-385); a leaf,
   // or an internal node the box covers completely, reports its elements in element order (:363-374,386-395).
-  uint32_t id = 0;
-  while (id < nNodes) {
+  uint32_t id = rootNode;
+  while (id != kKdEnd) {
     const float4* nd = reinterpret_cast<const float4*>(nodes + id);
     const float4 a = __ldg(nd), b = __ldg(nd + 1);
     const uint4 c = __ldg(reinterpret_cast<const uint4*>(nd + 2));
-    // a = {mnPhi, mnR, mnZ, mxPhi}, b = {mxR, mxZ, begin, end}, c = {skip, internal, -, -}
+    // a = {mnPhi, mnR, mnZ, mxPhi}, b = {mxR, mxZ, begin, end}, c = {skip, internal, lhs, -}
     const bool overlaps = (a.x < box.mx[0]) & (box.mn[0] < a.w) & (a.y < box.mx[1]) & (box.mn[1] < b.x) &
                           (a.z < box.mx[2]) & (box.mn[2] < b.y);
-    if (!overlaps) { id = c.x; continue; }
+    if (!overlaps) { id = c.x; continue; }  // rope: the next node outside this subtree (kKdEnd after the last)
     const bool contained = (box.mn[0] <= a.x) & (box.mx[0] >= a.w) & (box.mn[1] <= a.y) & (box.mx[1] >= b.x) &
                            (box.mn[2] <= a.z) & (box.mx[2] >= b.y);
-    if (c.y != 0u && !contained) { ++id; continue; }
-    const uint32_t e0 = corePos0 + __float_as_uint(b.z), e1 = corePos0 + __float_as_uint(b.w);
+    if (c.y != 0u && !contained) { id = c.z; continue; }  // descend: left child (the right one is the left one's rope)
+    const uint32_t e0 = __float_as_uint(b.z), e1 = __float_as_uint(b.w);  // packed positions (batch-wide)
     for (uint32_t o = e0; o < e1; ++o) {
       const float2 zr = ldg2(p.d.pZR + o);
       if (!contained) {
@@ -195,9 +192,8 @@ __global__ void __launch_bounds__(kKdThreads) k_doublets_kd(const __grid_constan
         const uint32_t eg = __ldg(p.workEG + w);
         const uint32_t ev = eg >> 1;
         const int dir = (int)(eg & 1u);
-        const uint32_t corePos0 = __ldg(kp.coreOffsets + ev);
-        const uint32_t node0 = __ldg(kp.nodeOffsets + ev), nNodes = __ldg(kp.nodeOffsets + ev + 1) - node0;
-        const KdNodeDev* nodes = kp.nodes + node0;
+        const KdNodeDev* nodes = kp.nodes;
+        const uint32_t rootNode = ev;  // node e is the root of event e
         MiddleSp mid;
         {
           const float2 mxy = ldg2(p.pXY + m), mzr = ldg2(p.pZR + m), mvar = ldg2(p.pVar + m);
@@ -211,8 +207,8 @@ __global__ void __launch_bounds__(kKdThreads) k_doublets_kd(const __grid_constan
           ++cntMiddles;
           float a, b;
           if (searchable) {
-            capT = kd_side<false, false>(kp, mid, boxT, corePos0, nodes, nNodes, nullptr, nullptr, a, b);
-            if (capT != 0u) capB = kd_side<true, false>(kp, mid, boxB, corePos0, nodes, nNodes, nullptr, nullptr, a, b);
+            capT = kd_side<false, false>(kp, mid, boxT, nodes, rootNode, nullptr, nullptr, a, b);
+            if (capT != 0u) capB = kd_side<true, false>(kp, mid, boxB, nodes, rootNode, nullptr, nullptr, a, b);
           }
           if (capB == 0u) capT = 0u;
           if (capB > kMaxListLength || capT > kMaxListLength) {
@@ -234,9 +230,9 @@ __global__ void __launch_bounds__(kKdThreads) k_doublets_kd(const __grid_constan
           DoubletRecord* recSlot = p.rec + slot;
           float* keySlot = p.key + slot;
           float mnT = 0.f, mxT = 0.f, mnB = 0.f, mxB = 0.f;
-          const uint32_t nT = kd_side<false, true>(kp, mid, boxT, corePos0, nodes, nNodes, recSlot + capB, keySlot + capB, mnT, mxT);
+          const uint32_t nT = kd_side<false, true>(kp, mid, boxT, nodes, rootNode, recSlot + capB, keySlot + capB, mnT, mxT);
           uint32_t nB = 0;
-          if (nT != 0u) nB = kd_side<true, true>(kp, mid, boxB, corePos0, nodes, nNodes, recSlot, keySlot, mnB, mxB);
+          if (nT != 0u) nB = kd_side<true, true>(kp, mid, boxB, nodes, rootNode, recSlot, keySlot, mnB, mxB);
           const bool go = nT != 0u && nB != 0u;
           MiddleHeader h{};
           h.capB = capB;

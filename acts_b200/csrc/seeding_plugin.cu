@@ -357,19 +357,36 @@ int orth_front(b200seed_handle* h, GridParams& gp, WorkParams& wp, KdDoubletPara
     worker();
     for (auto& t : pool) t.join();
   }
-  std::vector<uint32_t> coreOffsets(nEvents + 1, 0), nodeOffsets(nEvents + 1, 0);
+  // batch-wide node array: node e = root of event e, the other nodes of event e follow from base[e]
+  std::vector<uint32_t> coreOffsets(nEvents + 1, 0), nodeBase(nEvents + 1, nEvents);
   for (uint32_t e = 0; e < nEvents; ++e) {
     coreOffsets[e + 1] = coreOffsets[e] + (uint32_t)trees[e].posOrig.size();
-    nodeOffsets[e + 1] = nodeOffsets[e] + (uint32_t)trees[e].nodes.size();
+    nodeBase[e + 1] = nodeBase[e] + (uint32_t)std::max<size_t>(trees[e].nodes.size(), 1) - 1;
   }
-  const uint32_t nCore = coreOffsets[nEvents], nNodes = nodeOffsets[nEvents];
+  const uint32_t nCore = coreOffsets[nEvents], nNodes = nodeBase[nEvents];
   std::vector<uint32_t> posOrig(std::max<uint32_t>(nCore, 1));
   std::vector<float> posPhi(std::max<uint32_t>(nCore, 1)), rRange(2 * (size_t)nEvents);
   std::vector<KdNodeDev> nodes(std::max<uint32_t>(nNodes, 1));
   for (uint32_t e = 0; e < nEvents; ++e) {
     std::copy(trees[e].posOrig.begin(), trees[e].posOrig.end(), posOrig.begin() + coreOffsets[e]);
     std::copy(trees[e].posPhi.begin(), trees[e].posPhi.end(), posPhi.begin() + coreOffsets[e]);
-    std::copy(trees[e].nodes.begin(), trees[e].nodes.end(), nodes.begin() + nodeOffsets[e]);
+    const uint32_t nLocal = (uint32_t)trees[e].nodes.size();
+    auto global = [&](uint32_t local) { return local == 0 ? e : (local >= nLocal ? kKdEnd : nodeBase[e] + local - 1); };
+    if (nLocal == 0) {  // an event without selected space points: an empty leaf that overlaps no box
+      KdNodeDev leaf{};
+      for (int j = 0; j < 3; ++j) { leaf.mn[j] = std::numeric_limits<float>::max(); leaf.mx[j] = std::numeric_limits<float>::lowest(); }
+      leaf.begin = leaf.end = coreOffsets[e];
+      leaf.skip = kKdEnd;
+      nodes[e] = leaf;
+    }
+    for (uint32_t k = 0; k < nLocal; ++k) {
+      KdNodeDev nd = trees[e].nodes[k];
+      nd.begin += coreOffsets[e];
+      nd.end += coreOffsets[e];
+      nd.skip = global(nd.skip);
+      nd.lhs = nd.internal != 0u ? global(nd.lhs) : 0u;
+      nodes[global(k)] = nd;
+    }
     rRange[2 * e] = trees[e].rMiddleMin;
     rRange[2 * e + 1] = trees[e].rMiddleMax;
   }
@@ -377,7 +394,6 @@ int orth_front(b200seed_handle* h, GridParams& gp, WorkParams& wp, KdDoubletPara
   CUDA_TRY(h->orthPosPhi.reserve(posPhi.size() * 4));
   CUDA_TRY(h->orthNodes.reserve(nodes.size() * sizeof(KdNodeDev)));
   CUDA_TRY(h->orthCoreOffsets.reserve(coreOffsets.size() * 4));
-  CUDA_TRY(h->orthNodeOffsets.reserve(nodeOffsets.size() * 4));
   CUDA_TRY(h->orthRRange.reserve(std::max<size_t>(rRange.size(), 1) * 4));
   CUDA_TRY(h->midCount.reserve(((size_t)nCore + 1) * 4));
   CUDA_TRY(h->workStart.reserve(((size_t)nCore + 2) * 4));
@@ -385,7 +401,6 @@ int orth_front(b200seed_handle* h, GridParams& gp, WorkParams& wp, KdDoubletPara
   CUDA_TRY(cudaMemcpyAsync(h->orthPosPhi.ptr, posPhi.data(), posPhi.size() * 4, cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(h->orthNodes.ptr, nodes.data(), nodes.size() * sizeof(KdNodeDev), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(h->orthCoreOffsets.ptr, coreOffsets.data(), coreOffsets.size() * 4, cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync(h->orthNodeOffsets.ptr, nodeOffsets.data(), nodeOffsets.size() * 4, cudaMemcpyHostToDevice, s));
   if (!rRange.empty()) CUDA_TRY(cudaMemcpyAsync(h->orthRRange.ptr, rRange.data(), rRange.size() * 4, cudaMemcpyHostToDevice, s));
   // the number of selected space points is what the grid path reports as nInGrid (read back from binStart[0])
   CUDA_TRY(cudaMemcpyAsync(h->binStart.ptr, &coreOffsets[nEvents], 4, cudaMemcpyHostToDevice, s));
@@ -397,7 +412,6 @@ int orth_front(b200seed_handle* h, GridParams& gp, WorkParams& wp, KdDoubletPara
   op.nEvents = nEvents; op.nCoreTotal = nCore;
   op.spOffsets = a.dOffsets;
   op.coreOffsets = h->orthCoreOffsets.as<uint32_t>();
-  op.nodeOffsets = h->orthNodeOffsets.as<uint32_t>();
   op.rMiddleRange = h->orthRRange.as<float>();
   op.posOrig = h->orthPosOrig.as<uint32_t>();
   op.posPhi = h->orthPosPhi.as<float>();
@@ -424,8 +438,6 @@ int orth_front(b200seed_handle* h, GridParams& gp, WorkParams& wp, KdDoubletPara
   }
   CUDA_TRY(cudaStreamSynchronize(s));  // the staging vectors go out of scope
   kdp.orth = plan.orth;
-  kdp.coreOffsets = op.coreOffsets;
-  kdp.nodeOffsets = op.nodeOffsets;
   kdp.nodes = op.nodes;
   kdp.posPhi = op.posPhi;
   kdp.d.nNav = nCore;  // read by enqueue(): the work-item total sits at workStart[nCore]

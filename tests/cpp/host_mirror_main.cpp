@@ -6,6 +6,8 @@
 //           event twice, in a different order, the way the Sequencer's workers enter execute()); all results of an
 //           event must be identical; the seeds of every event are written one after the other
 //   host_mirror_main runv <in.bin> <out.bin> <nSigma> <margin> z0 var0 z1 var1 ...  -> Config::inputVertices path
+//   host_mirror_main orth <out.bin> <threads> <in0.bin> ...  -> ActsB200::OrthogonalTripletSeedingAlgorithm, one object,
+//        <threads> worker threads, every event seeded by every thread; seeds of every event written one after the other
 // File format in: uint32 n, then x[n] y[n] z[n] r[n] varZ[n] varR[n] (float32).
 // File format out: uint64 nSeeds, then bottom, middle, top (uint32) and quality, vertexZ (float32).
 #include <atomic>
@@ -18,6 +20,7 @@
 #include <vector>
 
 #include "../../acts_b200/host/GridTripletSeedingAlgorithm.hpp"
+#include "../../acts_b200/host/OrthogonalTripletSeedingAlgorithm.hpp"
 
 using Alg = ActsB200::GridTripletSeedingAlgorithm;
 
@@ -146,6 +149,48 @@ int main(int argc, char** argv) {
     out.write(reinterpret_cast<const char*>(seeds.vertexZ.data()), 4 * ns);
     std::printf("seeds %llu\n", static_cast<unsigned long long>(ns));
     return 0;
+  }
+  if (argc >= 5 && std::strcmp(argv[1], "orth") == 0) {
+    using Orth = ActsB200::OrthogonalTripletSeedingAlgorithm;
+    Orth::Config c;  // the <mu>=200 cut set on the orthogonal defaults (acts_b200/config.py: orthogonal_config)
+    c.rMax = 200; c.deltaRMin = 1; c.deltaRMax = 300; c.deltaRMinTop = 1; c.deltaRMaxTop = 300;
+    c.deltaRMinBottom = 1; c.deltaRMaxBottom = 300; c.collisionRegionMin = -250; c.collisionRegionMax = 250;
+    c.zMin = -2000; c.zMax = 2000; c.maxSeedsPerSpM = 1; c.sigmaScattering = 5; c.radLengthPerSeed = 0.1f;
+    c.minPt = 0.5f; c.impactMax = 3;
+    c.maxConcurrentEvents = 2;
+    bool confRejected = false;
+    try {
+      Orth::Config bad = c;
+      bad.seedConfirmation = true;
+      Orth rejected(bad);
+    } catch (const std::runtime_error&) {
+      confRejected = true;
+    }
+    const int nThreads = std::atoi(argv[3]);
+    std::vector<Columns> evs;
+    for (int i = 4; i < argc; ++i) evs.push_back(readEvent(argv[i]));
+    const Orth alg(c);
+    std::vector<ActsB200::SeedColumns> first(evs.size());
+    for (std::size_t e = 0; e < evs.size(); ++e) {
+      const auto& col = evs[e];
+      first[e] = alg.execute({col[0], col[1], col[2], col[3], col[4], col[5]});
+    }
+    std::atomic<int> mismatches{0};
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nThreads; ++t) {
+      pool.emplace_back([&, t] {
+        for (std::size_t k = 0; k < evs.size(); ++k) {
+          const std::size_t e = (k + static_cast<std::size_t>(t)) % evs.size();
+          const auto& col = evs[e];
+          if (!sameSeeds(alg.execute({col[0], col[1], col[2], col[3], col[4], col[5]}), first[e])) ++mismatches;
+        }
+      });
+    }
+    for (auto& th : pool) th.join();
+    std::ofstream out(argv[2], std::ios::binary);
+    for (const auto& s : first) writeSeeds(out, s);
+    std::printf("threads %d events %zu mismatches %d confirmation rejected %d\n", nThreads, evs.size(), mismatches.load(), confRejected ? 1 : 0);
+    return mismatches.load() == 0 && confRejected ? 0 : 1;
   }
   std::puts("usage: host_mirror_main errors | run <in.bin> <out.bin>");
   return 2;

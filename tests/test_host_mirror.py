@@ -103,3 +103,27 @@ def test_cpp_execute_with_vertices(built, tmp_path):
     assert ref["quality"].size > 0
     for k in ("bottom", "middle", "top", "quality", "vertexZ"):
         assert np.array_equal(got[k], ref[k].view(np.uint32)), k
+
+
+@pytest.mark.gpu
+def test_cpp_orthogonal_mirror(built, tmp_path):
+    """ActsB200::OrthogonalTripletSeedingAlgorithm (acts_b200/host/OrthogonalTripletSeedingAlgorithm.hpp): one object,
+    four threads, results identical across threads and equal to the oracle (which is pinned to the reference)."""
+    from acts_b200 import config, events
+    from oracle import oracle as O
+
+    evs = [events.pileup_event(60 + i, mu=mu) for i, mu in enumerate((15, 30, 8))]
+    files = []
+    for i, ev in enumerate(evs):
+        files.append(str(tmp_path / f"in{i}.bin"))
+        _write_event(files[-1], ev)
+    fout = tmp_path / "out.bin"
+    res = subprocess.run([BIN, "orth", str(fout), "4", *files], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "mismatches 0" in res.stdout and "confirmation rejected 1" in res.stdout
+    orc = O.Oracle(*config.orthogonal_config(O.orthogonal_config_init))
+    for ev, got in zip(evs, _read_seed_blocks(fout, len(evs))):
+        ref = orc.run(ev)
+        assert ref["bottom"].size > 0
+        for k in ("bottom", "middle", "top", "quality", "vertexZ"):
+            assert np.array_equal(got[k], ref[k].view(np.uint32)), k
