@@ -1,4 +1,6 @@
-// kd_tree_host.hpp -- host-side construction of the orthogonal seeder's k-d tree.
+// kd_tree_host.hpp -- host-side twin of the orthogonal seeder's k-d tree construction (the default path builds the
+// trees on the device: k_kd_select / k_kd_split / k_kd_small in orthogonal_kernels.cuh; B200SEED_KD_HOST=1 selects
+// this one, which the tests use as a cross-check).  Also defines the node record both builders produce.
 //
 // The reference builds one Acts::KDTree<3, SpacePointIndex, float, std::array, 4> per event over
 // (phi, r, z) of the selected space points (OrthogonalTripletSeedingAlgorithm.cpp:113-150,

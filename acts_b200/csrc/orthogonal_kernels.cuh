@@ -85,6 +85,317 @@ __global__ void __launch_bounds__(256) k_orth_fill_work(const __grid_constant__ 
   }
 }
 
+// ---------------------------------------------------------------------------
+// k-d tree construction on the device (Core/include/Acts/Utilities/KDTree.hpp:66-80,236-350): an in-place replay
+// of the reference's node-by-node std::partition / std::sort over the element arrays of the whole batch.
+//   k_kd_select   selection (.cpp:123-127), phi = replayed atan2f, extent of r (Extent::extend), element arrays in
+//                 insertion order (ordered compaction through the scan of the selection flags when a selector is on)
+//   k_kd_roots    one task per event; radius range of the middles (.cpp:227-232)
+//   k_kd_split    one block per node with more than 128 elements: bounding box, split value = middle of the box in
+//                 the node's dimension, std::partition replayed exactly -- libstdc++'s bidirectional partition swaps
+//                 the k-th misplaced element from the left with the k-th misplaced element from the right, so the
+//                 block ranks both kinds with a scan and performs the swaps in parallel --, child tasks.  One launch
+//                 per tree level (the host reads the number of tasks of the next level).
+//   k_kd_small    one warp per subtree of at most 128 elements, in shared memory: per sub-level every lane owns a node,
+//                 sorts it by the node's dimension with the libstdc++ introsort replay (std_sort, seed_math.h), splits
+//                 at the median and emits its children; leaves (at most 4 elements) are finished on the spot.
+// Nodes carry ropes (`skip`) and their left child, so the searches need neither a stack nor any node order.
+// ---------------------------------------------------------------------------
+struct KdTask {
+  uint32_t begin, end;  // packed element positions
+  uint32_t node;        // the node record to fill
+  uint32_t skip;        // its rope
+  uint32_t dim;         // split dimension (phi, r, z cycle)
+};
+constexpr uint32_t kKdExactMedian = 128, kKdLeaf = 4;
+constexpr int kKdSplitThreads = 1024;
+constexpr int kKdSmallWarps = 8;
+
+struct KdBuildParams {
+  DeviceConfig cfg;
+  uint32_t nEvents, nTotal;
+  const uint32_t* spOffsets;
+  const float *x, *y, *z, *r;
+  uint32_t* selFlag;      // [nTotal] (selector on)
+  uint32_t* selScan;      // [nTotal + 1] exclusive scan of selFlag
+  float* phiTmp;          // [nTotal] phi in the caller's order (selector on)
+  uint32_t* coreOffsets;  // [nEvents + 1]
+  float *ePhi, *eR, *eZ;  // element arrays
+  uint32_t* eIdx;         // element -> index inside the caller's event
+  unsigned long long* extent;  // [nEvents] min, then [nEvents] max of perp, as bits (non-negative doubles order like integers)
+  float* rMiddleRange;         // [2 * nEvents]
+  KdNodeDev* nodes;
+  uint32_t* counters;  // [0] nodes allocated, [1] small tasks, [2 + (level & 1)] tasks of the next level
+  KdTask *tasksIn, *tasksOut, *tasksSmall;
+  uint32_t nTasksIn, outSlot;
+  uint32_t *listL, *listR;  // [nTotal] positions of the misplaced elements of every node, by rank
+};
+
+__global__ void __launch_bounds__(256) k_kd_select(const __grid_constant__ KdBuildParams p) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const bool selector = p.cfg.useExtraCuts != 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.nTotal; i += stride) {
+    const uint32_t e = orth_event_of(p.spOffsets, p.nEvents, i);
+    const float x = __ldg(p.x + i), y = __ldg(p.y + i), z = __ldg(p.z + i), r = __ldg(p.r + i);
+    const bool sel = !(selector && !itk_sp_select(r, z));
+#ifdef B200SEED_RELAXED
+    const float phi = atan2f(y, x);
+#else
+    const float phi = glibc_atan2f(y, x);
+#endif
+    if (selector) {
+      p.selFlag[i] = sel ? 1u : 0u;
+      p.phiTmp[i] = phi;
+    } else {  // every space point is an element: insertion order = the caller's order
+      p.ePhi[i] = phi; p.eR[i] = r; p.eZ[i] = z;
+      p.eIdx[i] = i - __ldg(p.spOffsets + e);
+    }
+    if (sel) {
+      const double xd = (double)x, yd = (double)y;
+      const double perp = sqrt(dadd(dmul(xd, xd), dmul(yd, yd)));  // VectorHelpers::perp of the double vector
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(perp);
+      atomicMin(p.extent + e, bits);
+      atomicMax(p.extent + p.nEvents + e, bits);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_kd_compact(const __grid_constant__ KdBuildParams p) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.nTotal; i += stride) {
+    if (p.selFlag[i] == 0u) continue;
+    const uint32_t e = orth_event_of(p.spOffsets, p.nEvents, i);
+    const uint32_t q = p.selScan[i];
+    p.ePhi[q] = p.phiTmp[i]; p.eR[q] = __ldg(p.r + i); p.eZ[q] = __ldg(p.z + i);
+    p.eIdx[q] = i - __ldg(p.spOffsets + e);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_kd_roots(const __grid_constant__ KdBuildParams p) {
+  const bool selector = p.cfg.useExtraCuts != 0;
+  for (uint32_t e = threadIdx.x; e <= p.nEvents; e += blockDim.x) {
+    const uint32_t o = __ldg(p.spOffsets + e);
+    p.coreOffsets[e] = selector ? p.selScan[o] : o;
+  }
+  if (threadIdx.x == 0) p.counters[0] = p.nEvents;  // node e = root of event e
+  __syncthreads();
+  for (uint32_t e = threadIdx.x; e < p.nEvents; e += blockDim.x) {
+    KdTask t;
+    t.begin = p.coreOffsets[e];
+    t.end = p.coreOffsets[e + 1];
+    t.node = e;
+    t.skip = kKdEnd;
+    t.dim = 0;
+    if (t.end - t.begin > kKdExactMedian) {
+      p.tasksOut[atomicAdd(p.counters + 2 + p.outSlot, 1u)] = t;
+    } else {
+      p.tasksSmall[atomicAdd(p.counters + 1, 1u)] = t;
+    }
+    // .cpp:227-232 in double, stored as float (Range1D<float>)
+    const bool any = t.end != t.begin;
+    const double rLo = any ? __longlong_as_double((long long)p.extent[e]) : 0.0;
+    const double rHi = any ? __longlong_as_double((long long)p.extent[p.nEvents + e]) : 0.0;
+    p.rMiddleRange[2 * e] = (float)dadd(dmul(dfloor(ddiv(rLo, 2.0)), 2.0), (double)p.cfg.deltaRMiddleMinSPRange);
+    p.rMiddleRange[2 * e + 1] = (float)dsub(dmul(dfloor(ddiv(rHi, 2.0)), 2.0), (double)p.cfg.deltaRMiddleMaxSPRange);
+  }
+}
+
+__device__ __forceinline__ float kd_next_up(float v) { return nextafterf(v, 3.402823466e+38f); }  // KDTree::nextRepresentable
+
+__global__ void __launch_bounds__(kKdSplitThreads) k_kd_split(const __grid_constant__ KdBuildParams p) {
+  __shared__ float sMin[3][32], sMax[3][32];
+  __shared__ uint32_t scratch[34];
+  __shared__ uint32_t sLhs;
+  const KdTask t = p.tasksIn[blockIdx.x];
+  const uint32_t b = t.begin, e = t.end, d = t.dim;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* const key[3] = {p.ePhi, p.eR, p.eZ};
+  // bounding box (KDTree::boundingBox)
+  float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
+  float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+  for (uint32_t i = b + tid; i < e; i += blockDim.x) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float v = key[j][i];
+      mn[j] = std_min(mn[j], v);
+      mx[j] = std_max(mx[j], v);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    for (int s = 16; s > 0; s >>= 1) {
+      mn[j] = fminf(mn[j], __shfl_xor_sync(0xffffffffu, mn[j], s));
+      mx[j] = fmaxf(mx[j], __shfl_xor_sync(0xffffffffu, mx[j], s));
+    }
+    if (lane == 0) { sMin[j][warp] = mn[j]; sMax[j][warp] = mx[j]; }
+  }
+  __syncthreads();
+  const uint32_t nWarps = blockDim.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    float a = lane < nWarps ? sMin[j][lane] : 3.402823466e+38f, c = lane < nWarps ? sMax[j][lane] : -3.402823466e+38f;
+    for (int s = 16; s > 0; s >>= 1) {
+      a = fminf(a, __shfl_xor_sync(0xffffffffu, a, s));
+      c = fmaxf(c, __shfl_xor_sync(0xffffffffu, c, s));
+    }
+    mn[j] = a;
+    mx[j] = kd_next_up(c);
+  }
+  // split value: the middle of the box in this dimension (KDTree.hpp:299-305)
+  const float mid = fmul(0.5f, fadd(mx[d], mn[d]));
+  const float* kd = key[d];
+  uint32_t cnt = 0;
+  for (uint32_t i = b + tid; i < e; i += blockDim.x) cnt += kd[i] < mid ? 1u : 0u;
+  uint32_t nTrue;
+  block_scan_exclusive(cnt, scratch, nTrue, OpSum());
+  const uint32_t P = b + nTrue;  // std::partition's return value
+  // std::partition (bidirectional): the k-th element of [b, P) that fails the predicate is swapped with the k-th
+  // element from the right of [P, e) that satisfies it
+  uint32_t carryL = 0, carryR = 0;
+  for (uint32_t base = b; base < e; base += blockDim.x) {
+    const uint32_t i = base + tid;
+    const bool in = i < e;
+    const bool pred = in && kd[i] < mid;
+    const bool isL = in && i < P && !pred, isR = in && i >= P && pred;
+    uint32_t total;
+    const uint32_t excl = block_scan_exclusive((isL ? 1u : 0u) | (isR ? 0x10000u : 0u), scratch, total, OpSum());
+    if (isL) p.listL[b + carryL + (excl & 0xFFFFu)] = i;
+    if (isR) p.listR[b + carryR + (excl >> 16)] = i;
+    carryL += total & 0xFFFFu;
+    carryR += total >> 16;
+  }
+  __syncthreads();
+  const uint32_t nMis = carryL;  // == carryR
+  for (uint32_t k = tid; k < nMis; k += blockDim.x) {
+    const uint32_t i = p.listL[b + k], j = p.listR[b + nMis - 1u - k];
+    const float a0 = p.ePhi[i], a1 = p.eR[i], a2 = p.eZ[i];
+    const uint32_t a3 = p.eIdx[i];
+    p.ePhi[i] = p.ePhi[j]; p.eR[i] = p.eR[j]; p.eZ[i] = p.eZ[j]; p.eIdx[i] = p.eIdx[j];
+    p.ePhi[j] = a0; p.eR[j] = a1; p.eZ[j] = a2; p.eIdx[j] = a3;
+  }
+  if (tid == 0) {
+    uint32_t pivot = P;
+    if (pivot == b || pivot == e - 1u) pivot = b + kKdLeaf;  // KDTree.hpp:322-324
+    const uint32_t lhs = atomicAdd(p.counters + 0, 2u);
+    KdNodeDev nd{};
+    for (int j = 0; j < 3; ++j) { nd.mn[j] = mn[j]; nd.mx[j] = mx[j]; }
+    nd.begin = b; nd.end = e; nd.skip = t.skip; nd.internal = 1u; nd.lhs = lhs;
+    p.nodes[t.node] = nd;
+    KdTask c[2];
+    c[0].begin = b; c[0].end = pivot; c[0].node = lhs; c[0].skip = lhs + 1u; c[0].dim = (d + 1u) % 3u;
+    c[1].begin = pivot; c[1].end = e; c[1].node = lhs + 1u; c[1].skip = t.skip; c[1].dim = (d + 1u) % 3u;
+    for (int k = 0; k < 2; ++k) {
+      if (c[k].end - c[k].begin > kKdExactMedian) {
+        p.tasksOut[atomicAdd(p.counters + 2 + p.outSlot, 1u)] = c[k];
+      } else {
+        p.tasksSmall[atomicAdd(p.counters + 1, 1u)] = c[k];
+      }
+    }
+    sLhs = lhs;
+  }
+  (void)sLhs;
+}
+
+struct KdElem {
+  float c[3];
+  uint32_t idx;
+};
+
+__device__ __forceinline__ void kd_bbox_smem(const KdElem* el, uint32_t n, float* mn, float* mx) {
+  for (int j = 0; j < 3; ++j) { mn[j] = 3.402823466e+38f; mx[j] = -3.402823466e+38f; }
+  for (uint32_t i = 0; i < n; ++i) {
+    for (int j = 0; j < 3; ++j) {
+      mn[j] = std_min(mn[j], el[i].c[j]);
+      mx[j] = std_max(mx[j], el[i].c[j]);
+    }
+  }
+  for (int j = 0; j < 3; ++j) mx[j] = kd_next_up(mx[j]);
+}
+
+__global__ void __launch_bounds__(kKdSmallWarps * 32) k_kd_small(const __grid_constant__ KdBuildParams p) {
+  __shared__ KdElem sElem[kKdSmallWarps][kKdExactMedian];
+  __shared__ KdTask sTask[kKdSmallWarps][2][32];
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t nSmall = p.counters[1];
+  const uint32_t w = blockIdx.x * kKdSmallWarps + wib;
+  if (w >= nSmall) return;
+  const KdTask root = p.tasksSmall[w];
+  const uint32_t b0 = root.begin, n0 = root.end - root.begin;
+  KdElem* el = sElem[wib];
+  for (uint32_t i = lane; i < n0; i += 32) {
+    KdElem v;
+    v.c[0] = p.ePhi[b0 + i]; v.c[1] = p.eR[b0 + i]; v.c[2] = p.eZ[b0 + i]; v.idx = p.eIdx[b0 + i];
+    el[i] = v;
+  }
+  if (lane == 0) sTask[wib][0][0] = root;
+  __syncwarp();
+  uint32_t nCur = 1;
+  int cur = 0;
+  while (nCur > 0) {
+    const bool have = lane < nCur;
+    KdTask t{};
+    if (have) t = sTask[wib][cur][lane];
+    const uint32_t n = t.end - t.begin;
+    const bool internal = have && n > kKdLeaf;
+    float mn[3], mx[3];
+    uint32_t pivot = t.begin;
+    if (have) {
+      KdElem* mine = el + (t.begin - b0);
+      kd_bbox_smem(mine, n, mn, mx);
+      if (internal) {
+        const uint32_t d = t.dim;
+        std_sort(mine, (int)n, [d](const KdElem& a, const KdElem& c) { return a.c[d] < c.c[d]; });  // KDTree.hpp:310-316
+        pivot = t.begin + n / 2u;
+        if (pivot == t.begin || pivot == t.end - 1u) pivot = t.begin + kKdLeaf;
+      }
+    }
+    // node ids of the children: two per internal node
+    const uint32_t intMask = __ballot_sync(0xffffffffu, internal);
+    uint32_t base = 0;
+    if (lane == 0 && intMask != 0u) base = atomicAdd(p.counters + 0, 2u * (uint32_t)__popc(intMask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const uint32_t lhs = base + 2u * (uint32_t)__popc(intMask & ((1u << lane) - 1u));
+    if (have) {
+      KdNodeDev nd{};
+      for (int j = 0; j < 3; ++j) { nd.mn[j] = mn[j]; nd.mx[j] = mx[j]; }
+      nd.begin = t.begin; nd.end = t.end; nd.skip = t.skip; nd.internal = internal ? 1u : 0u; nd.lhs = internal ? lhs : 0u;
+      p.nodes[t.node] = nd;
+    }
+    // children: leaves are finished here, internal children go to the next sub-level
+    KdTask c[2];
+    bool next[2] = {false, false};
+    if (internal) {
+      c[0].begin = t.begin; c[0].end = pivot; c[0].node = lhs; c[0].skip = lhs + 1u; c[0].dim = (t.dim + 1u) % 3u;
+      c[1].begin = pivot; c[1].end = t.end; c[1].node = lhs + 1u; c[1].skip = t.skip; c[1].dim = (t.dim + 1u) % 3u;
+      for (int k = 0; k < 2; ++k) {
+        const uint32_t cn = c[k].end - c[k].begin;
+        if (cn > kKdLeaf) {
+          next[k] = true;
+        } else {
+          KdNodeDev leaf{};
+          float lmn[3], lmx[3];
+          kd_bbox_smem(el + (c[k].begin - b0), cn, lmn, lmx);
+          for (int j = 0; j < 3; ++j) { leaf.mn[j] = lmn[j]; leaf.mx[j] = lmx[j]; }
+          leaf.begin = c[k].begin; leaf.end = c[k].end; leaf.skip = c[k].skip; leaf.internal = 0u; leaf.lhs = 0u;
+          p.nodes[c[k].node] = leaf;
+        }
+      }
+    }
+    const uint32_t m0 = __ballot_sync(0xffffffffu, next[0]), m1 = __ballot_sync(0xffffffffu, next[1]);
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t before = (uint32_t)__popc(m0 & lt) + (uint32_t)__popc(m1 & lt);
+    if (next[0]) sTask[wib][cur ^ 1][before] = c[0];
+    if (next[1]) sTask[wib][cur ^ 1][before + (next[0] ? 1u : 0u)] = c[1];
+    nCur = (uint32_t)__popc(m0) + (uint32_t)__popc(m1);  // <= 32: a sub-level of a <= 128-element subtree with nodes of > 4 elements
+    cur ^= 1;
+    __syncwarp();
+  }
+  for (uint32_t i = lane; i < n0; i += 32) {
+    const KdElem v = el[i];
+    p.ePhi[b0 + i] = v.c[0]; p.eR[b0 + i] = v.c[1]; p.eZ[b0 + i] = v.c[2]; p.eIdx[b0 + i] = v.idx;
+  }
+}
+
 struct KdDoubletParams {
   DoubletParams d;  // work list, slot sizes, arena, headers, class lists (binStart / nav tables unused)
   OrthDeviceConfig orth;

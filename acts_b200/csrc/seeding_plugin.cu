@@ -120,6 +120,8 @@ struct b200seed_handle {
   DevBuf counters, status, zWin, zWinOffsets;
   // orthogonal seeder: the event trees built by the host layer (kd_tree_host.hpp)
   DevBuf orthPosOrig, orthPosPhi, orthNodes, orthCoreOffsets, orthNodeOffsets, orthRRange;
+  DevBuf orthElemR, orthElemZ, orthScratch, orthTasks, orthExtent;  // device construction of the trees
+  bool kdHostBuild = false;  // B200SEED_KD_HOST=1: build the trees in the host layer (kd_tree_host.hpp) instead
   uint32_t itemsMax = 0;  // upper bound of the work items of the last call (grid: space points, orthogonal: 2 x)
   uint32_t zWinCapacity = 1;  // windows per column of zWin (lo column, then hi column)
   DoubletParams lastDoublets{};  // of the last call (debug_doublets re-runs the fill pass chunk by chunk)
@@ -317,7 +319,109 @@ int enqueue_tail(b200seed_handle* h, cudaStream_t s) {
 // Orthogonal seeder, front of the pipeline (replaces the grid stage and the bin-wise work list): the host layer
 // builds every event's k-d tree (kd_tree_host.hpp, one thread per event), the device gathers the packed copy in
 // element order and lists two work items per accepted middle.
+// Tree construction on the device (k_kd_select / k_kd_roots / k_kd_split per level / k_kd_small).  Leaves the element
+// arrays (orthPosPhi = phi, orthPosOrig = index in the caller's event), the node array, coreOffsets and the middle
+// radius ranges on the device; returns the number of elements of the batch.
+int orth_build_device(b200seed_handle* h, uint64_t& launches, uint32_t& nCoreOut) {
+  const b200seed_handle::EnqueueArgs& a = h->last;
+  const uint32_t nEvents = a.nEvents, nTotal = a.nTotal;
+  cudaStream_t s = a.stream;
+  const size_t nT = std::max<size_t>(nTotal, 1);
+  const bool selector = h->plan.dev.useExtraCuts != 0;
+  const size_t maxActive = nT / 129 + nEvents + 2, maxSmall = nT / 2 + nEvents + 8;
+  CUDA_TRY(h->orthPosOrig.reserve(nT * 4));
+  CUDA_TRY(h->orthPosPhi.reserve(nT * 4));
+  CUDA_TRY(h->orthElemR.reserve(nT * 4));
+  CUDA_TRY(h->orthElemZ.reserve(nT * 4));
+  CUDA_TRY(h->orthScratch.reserve((nT + 1) * 4 * 5));
+  CUDA_TRY(h->orthNodes.reserve((2 * nT + nEvents + 2) * sizeof(KdNodeDev)));
+  CUDA_TRY(h->orthCoreOffsets.reserve(((size_t)nEvents + 1) * 4));
+  CUDA_TRY(h->orthRRange.reserve(std::max<size_t>(2 * (size_t)nEvents, 1) * 4));
+  CUDA_TRY(h->orthTasks.reserve((2 * maxActive + maxSmall) * sizeof(KdTask)));
+  CUDA_TRY(h->orthExtent.reserve(std::max<size_t>(2 * (size_t)nEvents, 1) * 8 + 64));
+  KdBuildParams bp{};
+  bp.cfg = h->plan.dev;
+  bp.nEvents = nEvents; bp.nTotal = nTotal;
+  bp.spOffsets = a.dOffsets;
+  bp.x = a.x; bp.y = a.y; bp.z = a.z; bp.r = a.r;
+  uint32_t* scratch = h->orthScratch.as<uint32_t>();
+  bp.selFlag = scratch;
+  bp.selScan = scratch + (nT + 1);
+  bp.phiTmp = reinterpret_cast<float*>(scratch + 2 * (nT + 1));
+  bp.listL = scratch + 3 * (nT + 1);
+  bp.listR = scratch + 4 * (nT + 1);
+  bp.coreOffsets = h->orthCoreOffsets.as<uint32_t>();
+  bp.ePhi = h->orthPosPhi.as<float>(); bp.eR = h->orthElemR.as<float>(); bp.eZ = h->orthElemZ.as<float>();
+  bp.eIdx = h->orthPosOrig.as<uint32_t>();
+  bp.extent = h->orthExtent.as<unsigned long long>();
+  bp.counters = reinterpret_cast<uint32_t*>(h->orthExtent.as<unsigned char>() + std::max<size_t>(2 * (size_t)nEvents, 1) * 8);
+  bp.rMiddleRange = h->orthRRange.as<float>();
+  bp.nodes = h->orthNodes.as<KdNodeDev>();
+  KdTask* lists[2] = {h->orthTasks.as<KdTask>(), h->orthTasks.as<KdTask>() + maxActive};
+  bp.tasksSmall = h->orthTasks.as<KdTask>() + 2 * maxActive;
+  CUDA_TRY(cudaMemsetAsync(bp.extent, 0xFF, (size_t)nEvents * 8, s));
+  CUDA_TRY(cudaMemsetAsync(bp.extent + nEvents, 0, (size_t)nEvents * 8, s));
+  CUDA_TRY(cudaMemsetAsync(bp.counters, 0, 16, s));
+  const int blocks = std::max(1, std::min<int>((int)((nTotal + 255) / 256), h->smCount * 8));
+  if (nTotal > 0) {
+    k_kd_select<<<blocks, 256, 0, s>>>(bp);
+    ++launches;
+    if (selector) {
+      k_scan<<<1, kScanThreads, 0, s>>>(bp.selFlag, bp.selScan, nTotal);
+      k_kd_compact<<<blocks, 256, 0, s>>>(bp);
+      launches += 2;
+    }
+  } else if (selector) {
+    CUDA_TRY(cudaMemsetAsync(bp.selScan, 0, 4, s));
+  }
+  int slot = 0;
+  bp.tasksOut = lists[slot];
+  bp.outSlot = (uint32_t)slot;
+  k_kd_roots<<<1, 256, 0, s>>>(bp);
+  ++launches;
+  uint32_t hc[4] = {0, 0, 0, 0};
+  std::vector<uint32_t> coreOffsets((size_t)nEvents + 1);
+  CUDA_TRY(cudaMemcpyAsync(hc, bp.counters, 16, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(coreOffsets.data(), bp.coreOffsets, coreOffsets.size() * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  uint32_t nActive = hc[2 + slot];
+  while (nActive > 0) {  // one launch per tree level that still has nodes of more than 128 elements
+    if (nActive > maxActive) return fail(B200SEED_ERR_RUNTIME, "k-d tree construction: task list overflow");
+    bp.tasksIn = lists[slot];
+    bp.nTasksIn = nActive;
+    bp.tasksOut = lists[slot ^ 1];
+    bp.outSlot = (uint32_t)(slot ^ 1);
+    CUDA_TRY(cudaMemsetAsync(bp.counters + 2 + (slot ^ 1), 0, 4, s));
+    k_kd_split<<<nActive, kKdSplitThreads, 0, s>>>(bp);
+    ++launches;
+    CUDA_TRY(cudaMemcpyAsync(hc, bp.counters, 16, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    slot ^= 1;
+    nActive = hc[2 + slot];
+  }
+  const uint32_t nSmall = hc[1];
+  if (nSmall > maxSmall) return fail(B200SEED_ERR_RUNTIME, "k-d tree construction: small-task list overflow");
+  if (nSmall > 0) {
+    k_kd_small<<<(nSmall + kKdSmallWarps - 1) / kKdSmallWarps, kKdSmallWarps * 32, 0, s>>>(bp);
+    ++launches;
+  }
+  CUDA_TRY(cudaGetLastError());
+  nCoreOut = coreOffsets[nEvents];
+  CUDA_TRY(cudaMemcpyAsync(h->binStart.ptr, bp.coreOffsets + nEvents, 4, cudaMemcpyDeviceToDevice, s));  // reported as nInGrid
+  return B200SEED_OK;
+}
+
+int orth_front_tail(b200seed_handle* h, GridParams& gp, WorkParams& wp, KdDoubletParams& kdp, uint64_t& launches, uint32_t nCore);
+
 int orth_front(b200seed_handle* h, GridParams& gp, WorkParams& wp, KdDoubletParams& kdp, uint64_t& launches) {
+  if (!h->kdHostBuild) {
+    uint32_t nCore = 0;
+    const int rc = orth_build_device(h, launches, nCore);
+    if (rc != B200SEED_OK) return rc;
+    CUDA_TRY(h->midCount.reserve(((size_t)nCore + 1) * 4));
+    CUDA_TRY(h->workStart.reserve(((size_t)nCore + 2) * 4));
+    return orth_front_tail(h, gp, wp, kdp, launches, nCore);
+  }
   const b200seed_handle::EnqueueArgs& a = h->last;
   const uint32_t nEvents = a.nEvents, nTotal = a.nTotal;
   cudaStream_t s = a.stream;
@@ -405,6 +509,16 @@ int orth_front(b200seed_handle* h, GridParams& gp, WorkParams& wp, KdDoubletPara
   // the number of selected space points is what the grid path reports as nInGrid (read back from binStart[0])
   CUDA_TRY(cudaMemcpyAsync(h->binStart.ptr, &coreOffsets[nEvents], 4, cudaMemcpyHostToDevice, s));
 
+  CUDA_TRY(cudaStreamSynchronize(s));  // the staging vectors go out of scope
+  return orth_front_tail(h, gp, wp, kdp, launches, nCore);
+}
+
+// gather in element order, middle selection, work list (two items per accepted middle)
+int orth_front_tail(b200seed_handle* h, GridParams& gp, WorkParams& wp, KdDoubletParams& kdp, uint64_t& launches, uint32_t nCore) {
+  const b200seed_handle::EnqueueArgs& a = h->last;
+  const uint32_t nEvents = a.nEvents;
+  cudaStream_t s = a.stream;
+  const HostPlan& plan = h->plan;
   CUDA_TRY(cudaEventRecord(h->ev[1], s));
   OrthParams op{};
   op.cfg = plan.dev;
@@ -436,7 +550,6 @@ int orth_front(b200seed_handle* h, GridParams& gp, WorkParams& wp, KdDoubletPara
     k_orth_fill_work<<<blocks, 256, 0, s>>>(op);
     ++launches;
   }
-  CUDA_TRY(cudaStreamSynchronize(s));  // the staging vectors go out of scope
   kdp.orth = plan.orth;
   kdp.nodes = op.nodes;
   kdp.posPhi = op.posPhi;
@@ -1005,6 +1118,7 @@ static int create_impl(const b200seed_config* cfg, const b200seed_orthogonal_opt
   CREATE_TRY(cudaEventCreate(&h->evCount));
   CREATE_TRY(cudaEventCreateWithFlags(&h->evPlan, cudaEventDisableTiming));
   h->chunkStreams = env_u32("B200SEED_CHUNK_STREAMS", 2) >= 2 ? 2 : 1;
+  h->kdHostBuild = env_u32("B200SEED_KD_HOST", 0) != 0;
   h->classStreams = env_u32("B200SEED_CLASS_STREAMS", 1) != 0 ? 1 : 0;
   for (int a = 0; a < 2; ++a) {
     CREATE_TRY(cudaEventCreateWithFlags(&h->evFill[a], cudaEventDisableTiming));
@@ -1105,7 +1219,8 @@ void b200seed_destroy(b200seed_handle* h) {
                     &h->outZ, &h->seedOffsets, &h->counters, &h->status, &h->zWin, &h->rec, &h->recZ, &h->recBegin,
                     &h->recCount, &h->slot2B, &h->slot2M, &h->slot2T, &h->slot2Q, &h->slot2Z, &h->slot2Count,
                     &h->confHead, &h->confNext, &h->confState, &h->confDirty, &h->orthPosOrig, &h->orthPosPhi,
-                    &h->orthNodes, &h->orthCoreOffsets, &h->orthNodeOffsets, &h->orthRRange}) {
+                    &h->orthNodes, &h->orthCoreOffsets, &h->orthNodeOffsets, &h->orthRRange, &h->orthElemR, &h->orthElemZ,
+                    &h->orthScratch, &h->orthTasks, &h->orthExtent}) {
     b->release();
   }
   if (h->hConfState != nullptr) cudaFreeHost(h->hConfState);
