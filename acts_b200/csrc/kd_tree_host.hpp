@@ -50,6 +50,7 @@ struct KdEventTree {
   std::vector<float> posPhi;      // element position -> phi
   std::vector<KdNodeDev> nodes;
   float rMiddleMin = 0.f, rMiddleMax = 0.f;  // useVariableMiddleSPRange (.cpp:227-232)
+  bool runaway = false;  // construction does not terminate (> 128 identical points: the reference recurses without end)
 };
 
 inline void build_kd_event(const DeviceConfig& cfg, uint32_t n, const float* x, const float* y, const float* z,
@@ -83,6 +84,10 @@ inline void build_kd_event(const DeviceConfig& cfg, uint32_t n, const float* x, 
     std::vector<Frame> todo;
     todo.push_back({0, elems.size(), elems.size() > kLeaf, 0});
     while (!todo.empty()) {
+      if (out.nodes.size() > 4 * elems.size() + 64) {  // a binary tree over n elements with non-empty leaves has < 2 n nodes
+        out.runaway = true;
+        break;
+      }
       const Frame f = todo.back();
       todo.pop_back();
       KdNodeDev node{};
@@ -119,6 +124,7 @@ inline void build_kd_event(const DeviceConfig& cfg, uint32_t n, const float* x, 
       todo.push_back({p, f.e, f.e - p > kLeaf, (d + 1) % 3});
       todo.push_back({f.b, p, p - f.b > kLeaf, (d + 1) % 3});
     }
+    if (out.runaway) return;
     // subtree sizes by a reverse sweep (children have larger indices than their parent)
     const std::size_t nn = out.nodes.size();
     std::vector<uint32_t> size(nn, 1);

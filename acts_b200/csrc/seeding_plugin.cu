@@ -385,8 +385,14 @@ int orth_build_device(b200seed_handle* h, uint64_t& launches, uint32_t& nCoreOut
   CUDA_TRY(cudaMemcpyAsync(coreOffsets.data(), bp.coreOffsets, coreOffsets.size() * 4, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   uint32_t nActive = hc[2 + slot];
+  uint32_t level = 0;
   while (nActive > 0) {  // one launch per tree level that still has nodes of more than 128 elements
     if (nActive > maxActive) return fail(B200SEED_ERR_RUNTIME, "k-d tree construction: task list overflow");
+    // A node of more than 128 points with identical (phi, r, z) never splits: the reference's constructor recurses
+    // without end on it (KDTree.hpp:299-324: the whole range becomes the left child again).  Refuse instead of looping.
+    if (++level > nTotal / 4 + 64) {
+      return fail(B200SEED_ERR_INVALID_ARGUMENT, "k-d tree construction does not terminate: more than 128 space points with identical (phi, r, z)");
+    }
     bp.tasksIn = lists[slot];
     bp.nTasksIn = nActive;
     bp.tasksOut = lists[slot ^ 1];
@@ -460,6 +466,11 @@ int orth_front(b200seed_handle* h, GridParams& gp, WorkParams& wp, KdDoubletPara
     for (uint32_t t = 1; t < nThreads; ++t) pool.emplace_back(worker);
     worker();
     for (auto& t : pool) t.join();
+  }
+  for (const KdEventTree& t : trees) {
+    if (t.runaway) {
+      return fail(B200SEED_ERR_INVALID_ARGUMENT, "k-d tree construction does not terminate: more than 128 space points with identical (phi, r, z)");
+    }
   }
   // batch-wide node array: node e = root of event e, the other nodes of event e follow from base[e]
   std::vector<uint32_t> coreOffsets(nEvents + 1, 0), nodeBase(nEvents + 1, nEvents);

@@ -842,3 +842,75 @@ def test_orthogonal_seeder_edge_cases_and_full_size(plugin, O):
     with pytest.raises(plugin.SeedingError) as exc:
         plugin.SeedingEngine(cfg, orthogonal=opt)
     assert exc.value.code == config.ERR_UNSUPPORTED
+
+
+def test_orthogonal_tree_construction_corner_cases(plugin, O, monkeypatch):
+    """The device replay of the reference's k-d tree construction (std::partition above 128 elements, std::sort
+    below) on inputs that stress it: event sizes around the 4 / 128 thresholds, identical points, one azimuth for
+    every point (degenerate phi splits: `pivot == end`, an empty right child), a selector that drops points
+    (ordered compaction), empty events inside a batch, <mu>=100; and the host-layer builder as a cross-check."""
+    from acts_b200 import config, events
+
+    base = events.pileup_event(7, mu=30)
+    n = base["x"].size
+    cases = [{k: v[:m] for k, v in base.items()} for m in (126, 127, 128, 129, 130, 133, 257, 1025)]
+    dup = {k: v.copy() for k, v in base.items()}
+    for k in dup:  # 100 copies of one space point in the middle of a normal event (more than 128 identical points
+        dup[k][1000:1100] = dup[k][999]  # make the reference itself recurse without end: KDTree.hpp:299-324)
+    cases.append(dup)
+    same_phi = {k: v.copy() for k, v in base.items()}
+    ang = np.float32(0.7)
+    same_phi["x"] = (same_phi["r"] * np.cos(ang)).astype(np.float32)  # one azimuth for everybody: the phi splits degenerate
+    same_phi["y"] = (same_phi["r"] * np.sin(ang)).astype(np.float32)
+    cases.append(same_phi)
+    cases.append(events.pileup_event(2, mu=100))
+    for over in (dict(), dict(useExtraCuts=1)):
+        cfg, opt = config.orthogonal_config(plugin.orthogonal_config_init, **over)
+        eng = plugin.SeedingEngine(cfg, orthogonal=opt)
+        orc = O.Oracle(*config.orthogonal_config(O.orthogonal_config_init, **over))
+        refs = [orc.run(ev) for ev in cases]
+        for i, (ev, ref) in enumerate(zip(cases, refs)):
+            assert _same_bits(eng.run(ev), ref), (over, i)
+        empty = {k: v[:0] for k, v in base.items()}
+        batch = [cases[3], empty, cases[8], empty, cases[0]]
+        cols, offsets = events.concat_events(batch)
+        got = eng.run_batch(cols, offsets)
+        for g, ev in zip(got, batch):
+            assert _same_bits(g, orc.run(ev))
+        eng.close()
+    monkeypatch.setenv("B200SEED_KD_HOST", "1")
+    cfg, opt = config.orthogonal_config(plugin.orthogonal_config_init)
+    eng = plugin.SeedingEngine(cfg, orthogonal=opt)
+    orc = O.Oracle(*config.orthogonal_config(O.orthogonal_config_init))
+    for ev in (cases[3], cases[8], cases[9]):
+        assert _same_bits(eng.run(ev), orc.run(ev))
+    eng.close()
+
+
+@pytest.mark.parametrize("host_build", [False, True])
+def test_orthogonal_refuses_the_input_the_reference_cannot_build(plugin, O, monkeypatch, host_build):
+    """More than 128 space points with identical (phi, r, z) whose three mantissas are odd: the middle of the
+    bounding box rounds up in every dimension, every point satisfies `x < mid`, the whole range becomes the left child
+    again and the reference's constructor recurses without end (KDTree.hpp:299-324).  The engine reports it
+    (INVALID_ARGUMENT) instead of looping; the same points with an even mantissa are peeled four at a time and work."""
+    from acts_b200 import config, events
+
+    if host_build:
+        monkeypatch.setenv("B200SEED_KD_HOST", "1")
+    ev = events.pileup_event(1, mu=5)
+    x, y = np.float32(40.0), np.float32(0.0)
+    for _ in range(10000):  # an azimuth with an odd mantissa (phi = atan2f(y, x) as the reference computes it)
+        y = np.nextafter(y, np.float32(1e9))
+        if int(np.float32(O.lib().oracle_atan2f(float(y), float(x))).view(np.uint32)) & 1:
+            break
+    odd = lambda v: (np.float32(v).view(np.uint32) | np.uint32(1)).view(np.float32)
+    bad = {k: v.copy() for k, v in ev.items()}
+    bad["x"][:200], bad["y"][:200] = x, y
+    bad["z"][:200], bad["r"][:200] = odd(12.5), odd(40.0)
+    cfg, opt = config.orthogonal_config(plugin.orthogonal_config_init)
+    eng = plugin.SeedingEngine(cfg, orthogonal=opt)
+    with pytest.raises(plugin.SeedingError) as exc:
+        eng.run(bad)
+    assert exc.value.code == config.ERR_INVALID_ARGUMENT
+    assert eng.run(ev)["bottom"].size == O.Oracle(*config.orthogonal_config(O.orthogonal_config_init)).run(ev)["bottom"].size
+    eng.close()
