@@ -294,9 +294,6 @@ void build(const b200seed_config& c, HostPlan& plan, const b200seed_orthogonal_o
     o.deltaZMax = std::numeric_limits<float>::infinity();  // Options::deltaZMax default, never set by the algorithm
     o.zOutermostLayersMin = orthOpt->zOutermostLayersMin;
     o.zOutermostLayersMax = orthOpt->zOutermostLayersMax;
-    if (c.seedConfirmation) {
-      throw Fail{B200SEED_ERR_UNSUPPORTED, "seedConfirmation with the orthogonal seeder is not supported"};
-    }
   }
   d.deltaZMin = c.deltaZMin;
   d.deltaZMax = c.deltaZMax;

@@ -471,6 +471,7 @@ constexpr int kKdThreads = 128;
 template <bool kFill>
 __global__ void __launch_bounds__(kKdThreads) k_doublets_kd(const __grid_constant__ KdDoubletParams kp) {
   const DoubletParams& p = kp.d;
+  const DeviceConfig& cfg = p.cfg;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t itemFirst = kFill ? p.itemFirst : 0u;
   const uint32_t itemEnd = kFill ? p.itemEnd : *p.nWorkPtr;
@@ -542,9 +543,13 @@ __global__ void __launch_bounds__(kKdThreads) k_doublets_kd(const __grid_constan
           float* keySlot = p.key + slot;
           float mnT = 0.f, mxT = 0.f, mnB = 0.f, mxB = 0.f;
           const uint32_t nT = kd_side<false, true>(kp, mid, boxT, nodes, rootNode, recSlot + capB, keySlot + capB, mnT, mxT);
+          bool go = nT != 0u;
+          // BroadTripletSeedFilter.cpp:63-94 (sufficientTopDoublets; it subsumes the candidate-count test of
+          // CylindricalSpacePointKDTree.cpp:245-246: doublets <= candidates)
+          if (go && p.conf) go = !(nT < conf_n_top(conf_range(cfg, mid.z), mid.r));
           uint32_t nB = 0;
-          if (nT != 0u) nB = kd_side<true, true>(kp, mid, boxB, nodes, rootNode, recSlot, keySlot, mnB, mxB);
-          const bool go = nT != 0u && nB != 0u;
+          if (go) nB = kd_side<true, true>(kp, mid, boxB, nodes, rootNode, recSlot, keySlot, mnB, mxB);
+          go = go && nB != 0u;
           MiddleHeader h{};
           h.capB = capB;
           h.offset = (uint32_t)slot;

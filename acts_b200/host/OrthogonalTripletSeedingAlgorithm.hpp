@@ -64,7 +64,7 @@ class OrthogonalTripletSeedingAlgorithm final {
     std::size_t compatSeedLimit = 2;
     float seedWeightIncrement = 0.f;
     float numSeedIncrement = std::numeric_limits<float>::infinity();
-    bool seedConfirmation = false;  // true: std::runtime_error at construction (not supported by the engine)
+    bool seedConfirmation = false;
     SeedConfirmationRangeConfig centralSeedConfirmationRange;
     SeedConfirmationRangeConfig forwardSeedConfirmationRange;
     std::uint32_t maxSeedsPerSpMConf = 5;
@@ -97,6 +97,8 @@ class OrthogonalTripletSeedingAlgorithm final {
     c.maxSeedsPerSpM = cfg.maxSeedsPerSpM; c.compatSeedLimit = cfg.compatSeedLimit;
     c.seedWeightIncrement = cfg.seedWeightIncrement; c.numSeedIncrement = cfg.numSeedIncrement;
     c.seedConfirmation = cfg.seedConfirmation;
+    copyRange(cfg.centralSeedConfirmationRange, c.centralSeedConfirmationRange);
+    copyRange(cfg.forwardSeedConfirmationRange, c.forwardSeedConfirmationRange);
     c.maxSeedsPerSpMConf = cfg.maxSeedsPerSpMConf; c.maxQualitySeedsPerSpMConf = cfg.maxQualitySeedsPerSpMConf;
     c.useDeltaRinsteadOfTopRadius = cfg.useDeltaRinsteadOfTopRadius; c.useExtraCuts = cfg.useExtraCuts;
     m_opt.zOutermostLayersMin = cfg.zOutermostLayers.first;
@@ -166,6 +168,12 @@ class OrthogonalTripletSeedingAlgorithm final {
               reinterpret_cast<float*>(base + 4 * capacity), capacity, 0};
     }
   };
+  static void copyRange(const SeedConfirmationRangeConfig& a, b200seed_seed_confirmation_range& b) {
+    b.zMinSeedConf = a.zMinSeedConf; b.zMaxSeedConf = a.zMaxSeedConf; b.rMaxSeedConf = a.rMaxSeedConf;
+    b.nTopForLargeR = a.nTopForLargeR; b.nTopForSmallR = a.nTopForSmallR;
+    b.seedConfMinBottomRadius = a.seedConfMinBottomRadius; b.seedConfMaxZOrigin = a.seedConfMaxZOrigin;
+    b.minImpactSeedConf = a.minImpactSeedConf;
+  }
   static void check(int rc) {
     if (rc == B200SEED_OK) return;
     const std::string msg = b200seed_last_error();

@@ -246,7 +246,8 @@ void b200seed_destroy(b200seed_handle* h);
  * Its Config is a subset of the grid algorithm's fields (same names, other defaults) plus the
  * three below.  Grid-only members of the config struct -- phiBinDeflectionCoverage, maxPhiBins,
  * zBinNeighbors*, numPhiNeighbors, zBinEdges, zBinsCustomLooping, rRangeMiddleSP, vertex cuts --
- * are ignored; seedConfirmation = true is not supported here (B200SEED_ERR_UNSUPPORTED).
+ * are ignored.  seedConfirmation = true is supported (one filter state across both groups of a middle and
+ * across middles, OrthogonalTripletSeedingAlgorithm.cpp:234-238).
  * The handle is used with b200seed_run / b200seed_run_batch / b200seed_sync like a grid handle;
  * seeds come in the reference's order (middles in k-d-tree order, the increasing-z group of a
  * middle before its decreasing-z group). */

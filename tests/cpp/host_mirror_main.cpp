@@ -189,8 +189,8 @@ int main(int argc, char** argv) {
     for (auto& th : pool) th.join();
     std::ofstream out(argv[2], std::ios::binary);
     for (const auto& s : first) writeSeeds(out, s);
-    std::printf("threads %d events %zu mismatches %d confirmation rejected %d\n", nThreads, evs.size(), mismatches.load(), confRejected ? 1 : 0);
-    return mismatches.load() == 0 && confRejected ? 0 : 1;
+    std::printf("threads %d events %zu mismatches %d\n", nThreads, evs.size(), mismatches.load());
+    return mismatches.load() == 0 ? 0 : 1;
   }
   std::puts("usage: host_mirror_main errors | run <in.bin> <out.bin>");
   return 2;

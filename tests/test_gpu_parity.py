@@ -818,7 +818,7 @@ def test_orthogonal_seeder_matches_oracle(plugin, O, variant):
 
 def test_orthogonal_seeder_edge_cases_and_full_size(plugin, O):
     """Empty / tiny events (the tree degenerates to a leaf), quantised coordinates (equal keys in the tree's
-    partition / sort and in the cotTheta sort), a <mu>=200 event, and the unsupported seedConfirmation mode."""
+    partition / sort and in the cotTheta sort), a <mu>=200 event, and seedConfirmation = true."""
     from acts_b200 import config, events
 
     cfg, opt = config.orthogonal_config(plugin.orthogonal_config_init)
@@ -838,10 +838,18 @@ def test_orthogonal_seeder_edge_cases_and_full_size(plugin, O):
     assert ref["bottom"].size > 50_000
     assert _same_bits(eng.run(big), ref)
     eng.close()
-    cfg, opt = config.orthogonal_config(plugin.orthogonal_config_init, **config.confirmation_overrides())
-    with pytest.raises(plugin.SeedingError) as exc:
-        plugin.SeedingEngine(cfg, orthogonal=opt)
-    assert exc.value.code == config.ERR_UNSUPPORTED
+    # seedConfirmation through the k-d-tree seeder: one filter state (bestSeedQualityMap) across both z-direction
+    # groups of a middle and across middles (.cpp:234-238) = the fixed-point replay over work items
+    over = config.confirmation_overrides()
+    cfg, opt = config.orthogonal_config(plugin.orthogonal_config_init, **over)
+    eng = plugin.SeedingEngine(cfg, orthogonal=opt)
+    orc = O.Oracle(*config.orthogonal_config(O.orthogonal_config_init, **over))
+    for ev in (events.pileup_event(5, mu=30), events.pileup_event(6, mu=60), events.itk_pileup_event(1, mu=20)):
+        ref = orc.run(ev)
+        assert ref["bottom"].size > 0
+        assert _same_bits(eng.run(ev), ref)
+    assert eng.counters()["nConfirmationRounds"] >= 2
+    eng.close()
 
 
 def test_orthogonal_tree_construction_corner_cases(plugin, O, monkeypatch):

@@ -120,7 +120,7 @@ def test_cpp_orthogonal_mirror(built, tmp_path):
     fout = tmp_path / "out.bin"
     res = subprocess.run([BIN, "orth", str(fout), "4", *files], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout + res.stderr
-    assert "mismatches 0" in res.stdout and "confirmation rejected 1" in res.stdout
+    assert "mismatches 0" in res.stdout
     orc = O.Oracle(*config.orthogonal_config(O.orthogonal_config_init))
     for ev, got in zip(evs, _read_seed_blocks(fout, len(evs))):
         ref = orc.run(ev)
