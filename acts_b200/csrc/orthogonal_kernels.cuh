@@ -9,9 +9,9 @@
 //                       increasing-z group ("lh") and the decreasing-z group ("hl"), in that order (.cpp:294-306)
 //   k_orth_fill_work    work list from the exclusive scan of the per-position item counts
 //   k_doublets_kd<fill> the two-pass doublet stage of k_doublets with the r-sorted bin windows replaced by a
-//                       range search: one THREAD per work item walks the event's tree (nodes in pre-order with skip
-//                       indices, no stack) and tests the elements of every reported node in element order; deltaR
-//                       is an explicit cut (DoubletSeedFinder.cpp:126-130, spacePointsSortedByRadius = false)
+//                       range search: every LANE is a walker with its own work item (rope walk, no stack; lane
+//                       refill) and tests the elements of every reported node in element order; deltaR is an
+//                       explicit cut (DoubletSeedFinder.cpp:126-130, spacePointsSortedByRadius = false)
 #pragma once
 
 #include "kd_tree_host.hpp"
@@ -403,172 +403,253 @@ struct KdDoubletParams {
   const float* posPhi;
 };
 
-// One side (bottom or top candidates) of one work item, walked by ONE THREAD: the range search + the doublet cuts.
-// Count pass: returns the number of survivors of the deltaR window and the (z, r) cuts (the slot size).  Fill pass:
-// every survivor is finished on the spot and written to the slot in emission order; returns the number of doublets.
-// The 32 work items of a warp are consecutive in the work list = neighbours in the tree's element order (both z
-// directions of a middle, then the next middle), so their walks visit nearly the same nodes (L1 hits) and have
-// similar lengths.
-template <bool kBottom, bool kFill>
-__device__ __forceinline__ uint32_t kd_side(const KdDoubletParams& p, const MiddleSp& mid, const KdBox& box,
-                                            const KdNodeDev* nodes, uint32_t rootNode,
-                                            DoubletRecord* recOut, float* keyOut, float& cotMin, float& cotMax) {
-  const DeviceConfig& cfg = p.d.cfg;
-  const float dRMin = kBottom ? cfg.dRMinB : cfg.dRMinT, dRMax = kBottom ? cfg.dRMaxB : cfg.dRMaxT;
-  uint32_t n = 0;
-  float mn = 3.0e38f, mx = -3.0e38f;
-  // KDTreeNode::rangeSearchMapDiscard as a pre-order scan: a node that does not overlap the box is skipped with
-  // its subtree (the reference tests the overlap before it descends into a child, KDTree.hpp:377-385); a leaf,
-  // or an internal node the box covers completely, reports its elements in element order (:363-374,386-395).
-  uint32_t id = rootNode;
-  while (id != kKdEnd) {
-    const float4* nd = reinterpret_cast<const float4*>(nodes + id);
-    const float4 a = __ldg(nd), b = __ldg(nd + 1);
-    const uint4 c = __ldg(reinterpret_cast<const uint4*>(nd + 2));
-    // a = {mnPhi, mnR, mnZ, mxPhi}, b = {mxR, mxZ, begin, end}, c = {skip, internal, lhs, -}
-    const bool overlaps = (a.x < box.mx[0]) & (box.mn[0] < a.w) & (a.y < box.mx[1]) & (box.mn[1] < b.x) &
-                          (a.z < box.mx[2]) & (box.mn[2] < b.y);
-    if (!overlaps) { id = c.x; continue; }  // rope: the next node outside this subtree (kKdEnd after the last)
-    const bool contained = (box.mn[0] <= a.x) & (box.mx[0] >= a.w) & (box.mn[1] <= a.y) & (box.mx[1] >= b.x) &
-                           (box.mn[2] <= a.z) & (box.mx[2] >= b.y);
-    if (c.y != 0u && !contained) { id = c.z; continue; }  // descend: left child (the right one is the left one's rope)
-    const uint32_t e0 = __float_as_uint(b.z), e1 = __float_as_uint(b.w);  // packed positions (batch-wide)
-    for (uint32_t o = e0; o < e1; ++o) {
-      const float2 zr = ldg2(p.d.pZR + o);
-      if (!contained) {
-        const float phi = __ldg(p.posPhi + o);
-        const bool inside = (box.mn[0] <= phi) & (phi < box.mx[0]) & (box.mn[1] <= zr.y) & (zr.y < box.mx[1]) &
-                            (box.mn[2] <= zr.x) & (zr.x < box.mx[2]);
-        if (!inside) continue;
-      }
-      float dR, dZ;
-      if (!doublet_zr_cuts<kBottom>(cfg, mid, zr.x, zr.y, dR, dZ)) continue;
-      if (outside_range(dR, dRMin, dRMax)) continue;  // (first in the reference: both are pure rejections)
-      if (!kFill) {
-        ++n;
-      } else {
-        const float2 xy = ldg2(p.d.pXY + o), var = ldg2(p.d.pVar + o);
-        DoubletRec rec;
-        if (!doublet_finish<kBottom>(cfg, mid, dR, dZ, xy.x, xy.y, zr.y, var.x, var.y, nullptr, nullptr, 0, rec, true)) continue;
-        float4* dst = reinterpret_cast<float4*>(recOut + n);
-        dst[0] = make_float4(__uint_as_float(o), rec.cotTheta, rec.iDeltaR, rec.er);
-        dst[1] = make_float4(rec.u, rec.v, rec.xNew, rec.yNew);
-        keyOut[n] = rec.cotTheta;
-        mn = fminf(mn, rec.cotTheta);
-        mx = fmaxf(mx, rec.cotTheta);
-        ++n;
-      }
-    }
-    id = c.x;
-  }
-  cotMin = mn;
-  cotMax = mx;
-  return n;
-}
-
+// The two-pass doublet stage of the orthogonal seeder.  Every LANE is a walker with its own work item: it runs the
+// range search of the item's top box, then (if tops were found) of its bottom box, one micro-step per loop iteration
+// -- either one node visit or one element test -- so that the 32 walkers of a warp reconverge after every step; a lane
+// whose item is finished takes the next unassigned item at once (lane refill), so warps stay full although the items
+// differ widely (the decreasing-z group of a forward middle is nearly empty, the increasing-z group is not).
+//   KDTreeNode::rangeSearchMapDiscard as a rope walk: a node that does not overlap the box is skipped with its
+//   subtree (the reference tests the overlap before it descends into a child, KDTree.hpp:377-385); a leaf, or an
+//   internal node the box covers completely, reports its elements in element order (:363-374,386-395).
+// Count pass: survivors of the deltaR window and the (z, r) cuts per side (the slot size).  Fill pass: every survivor
+// is finished on the spot and written to the item's slot in emission order.
 constexpr int kKdThreads = 128;
+#ifndef B200SEED_KD_SCAN_BELOW
+#define B200SEED_KD_SCAN_BELOW 16  // measured against 4 (the reference leaf size: nothing scanned), 32, 64: tools/ab_kd.sh
+#endif
+constexpr int kKdScanBelow = B200SEED_KD_SCAN_BELOW;
 
 template <bool kFill>
 __global__ void __launch_bounds__(kKdThreads) k_doublets_kd(const __grid_constant__ KdDoubletParams kp) {
   const DoubletParams& p = kp.d;
   const DeviceConfig& cfg = p.cfg;
   const uint32_t lane = threadIdx.x & 31;
+  const uint32_t ltMask = (1u << lane) - 1u;
   const uint32_t itemFirst = kFill ? p.itemFirst : 0u;
   const uint32_t itemEnd = kFill ? p.itemEnd : *p.nWorkPtr;
   const uint32_t nItems = itemEnd - itemFirst;
   unsigned long long cntMiddles = 0, cntB = 0, cntT = 0;
   uint32_t maxFoot = 0, maxB = 0, maxT = 0;
+  // walker state
+  int phase = 0;  // 0 idle, 1 top walk, 2 bottom walk, 3 retired
+  uint32_t w = 0, m = 0, rootNode = 0;
+  int dir = 0;
+  MiddleSp mid{};
+  KdBox box{};
+  float dRMin = 0.f, dRMax = 0.f;
+  uint32_t id = kKdEnd, o = 0, oEnd = 0;
+  bool contained = false;
+  uint32_t n = 0, nTop = 0, capT = 0, capB = 0;
+  float mn = 0.f, mx = 0.f, mnT = 0.f, mxT = 0.f;
+  DoubletRecord* recSlot = nullptr;
+  float* keySlot = nullptr;
+  DoubletRecord* recOut = nullptr;
+  float* keyOut = nullptr;
+  uint32_t slotLo = 0;
+  bool exhausted = false;  // warp-uniform: the work list has been handed out
+  const KdNodeDev* nodes = kp.nodes;
+
+  auto startWalk = [&](bool bottom) {
+    KdBox boxB, boxT;
+    kd_search_boxes(kp.orth, __ldg(kp.posPhi + m), mid.r, mid.z, dir, boxB, boxT);
+    box = bottom ? boxB : boxT;
+    dRMin = bottom ? cfg.dRMinB : cfg.dRMinT;
+    dRMax = bottom ? cfg.dRMaxB : cfg.dRMaxT;
+    id = rootNode; o = 0; oEnd = 0; contained = false;
+    n = 0; mn = 3.0e38f; mx = -3.0e38f;
+    phase = bottom ? 2 : 1;
+  };
+  auto finishCount = [&]() {  // count pass: slot sizes of the item
+    if (capB == 0u) capT = 0u;
+    if (capB > kMaxListLength || capT > kMaxListLength) {
+      atomicOr(p.status, kStatusOverflowDoublets);
+      capB = 0; capT = 0;
+    }
+    capB = (capB + 3u) & ~3u;  // slots and their two halves start on 16-byte boundaries of the key array (TMA)
+    capT = (capT + 3u) & ~3u;
+    p.capB[w] = capB;
+    p.capT[w] = capT;
+    if (capB != 0u) {
+      const uint32_t foot = seed_carve(capB, capT).minBytes;
+      maxFoot = foot > maxFoot ? foot : maxFoot;
+      maxB = capB > maxB ? capB : maxB;
+      maxT = capT > maxT ? capT : maxT;
+    }
+    phase = 0;
+  };
+  auto finishFill = [&](uint32_t nB, float mnB, float mxB) {  // fill pass: header, carve-up, class list
+    const bool go = nTop != 0u && nB != 0u;
+    MiddleHeader h{};
+    h.capB = capB;
+    h.offset = slotLo;
+    if (go) {
+      h.nB = nB; h.nT = nTop;
+      h.cotMinB = float_to_ordered(mnB); h.cotMaxB = float_to_ordered(mxB);
+      h.cotMinT = float_to_ordered(mnT); h.cotMaxT = float_to_ordered(mxT);
+      const SeedCarve cv = seed_carve(nB, nTop);
+      p.carve[w] = cv;
+      const uint32_t foot = cv.minBytes;
+      int c = 0;
+      while (c < kSpillClass && foot > p.classBytes[c]) ++c;
+      p.classList[(size_t)c * p.classStride + atomicAdd(p.classCount + c, 1u)] = w;
+      cntB += nB;
+      cntT += nTop;
+    } else {
+      p.slotCount[w] = 0;
+    }
+    p.hdr[w] = h;
+    phase = 0;
+  };
+
   for (;;) {
-    uint32_t it = 0;
-    if (lane == 0) it = atomicAdd(p.workCounter, 32u);  // a warp takes 32 consecutive items
-    it = __shfl_sync(0xffffffffu, it, 0);
-    if (it >= nItems) break;
-    it += lane;
-    if (it < nItems) {
-      const uint32_t w = itemFirst + it;
-      uint32_t capT = 0, capB = 0;
-      bool live = true;
-      if (kFill) {
-        capT = __ldg(p.capT + w);
-        capB = __ldg(p.capB + w);
-        if (capT == 0u || capB == 0u) {
-          MiddleHeader h{};
-          h.capB = capB;
-          p.hdr[w] = h;
-          p.slotCount[w] = 0;
-          live = false;
+    const uint32_t idle = __ballot_sync(0xffffffffu, phase == 0);
+    if (idle != 0u) {
+      if (!exhausted) {  // hand the next items to the idle lanes
+        const uint32_t nIdle = (uint32_t)__popc(idle);
+        const int leader = __ffs(idle) - 1;
+        uint32_t base = 0;
+        if ((int)lane == leader) base = atomicAdd(p.workCounter, nIdle);
+        base = __shfl_sync(0xffffffffu, base, leader);
+        exhausted = base + nIdle >= nItems;
+        if (phase == 0) {
+          const uint32_t it = base + (uint32_t)__popc(idle & ltMask);
+          if (it >= nItems) {
+            phase = 3;
+          } else {
+            w = itemFirst + it;
+            bool live = true;
+            capT = 0; capB = 0;
+            if (kFill) {
+              capT = __ldg(p.capT + w);
+              capB = __ldg(p.capB + w);
+              if (capT == 0u || capB == 0u) {
+                MiddleHeader h{};
+                h.capB = capB;
+                p.hdr[w] = h;
+                p.slotCount[w] = 0;
+                live = false;  // stays idle: takes another item in the next round
+              }
+            }
+            if (live) {
+              m = __ldg(p.workPos + w);
+              const uint32_t eg = __ldg(p.workEG + w);
+              rootNode = eg >> 1;  // node e is the root of event e
+              dir = (int)(eg & 1u);
+              const float2 mxy = ldg2(p.pXY + m), mzr = ldg2(p.pZR + m), mvar = ldg2(p.pVar + m);
+              mid.x = mxy.x; mid.y = mxy.y; mid.z = mzr.x; mid.r = mzr.y; mid.varZ = mvar.x; mid.varR = mvar.y;
+              middle_info(mid);
+              KdBox boxB, boxT;
+              kd_search_boxes(kp.orth, __ldg(kp.posPhi + m), mid.r, mid.z, dir, boxB, boxT);
+              const bool searchable = !kd_degenerate(boxB) && !kd_degenerate(boxT);  // CylindricalSpacePointKDTree.cpp:226,241
+              if (!kFill) {
+                ++cntMiddles;
+                if (searchable) {
+                  startWalk(false);
+                } else {
+                  finishCount();
+                }
+              } else {
+                const unsigned long long slot = p.slotPrefix[w] - p.slotPrefix[p.itemFirst];
+                slotLo = (uint32_t)slot;
+                recSlot = p.rec + slot;
+                keySlot = p.key + slot;
+                nTop = 0;
+                if (searchable) {
+                  startWalk(false);
+                  recOut = recSlot + capB;
+                  keyOut = keySlot + capB;
+                } else {
+                  finishFill(0u, 0.f, 0.f);
+                }
+              }
+            }
+          }
+        }
+        continue;
+      }
+      if (phase == 0) phase = 3;  // nothing left to hand out
+    }
+    const bool walking = phase == 1 || phase == 2;
+    if (__ballot_sync(0xffffffffu, walking) == 0u) break;
+    if (!walking) continue;
+    const bool bottom = phase == 2;
+    const bool elemStep = o < oEnd;
+    if (elemStep) {
+      const float2 zr = ldg2(p.pZR + o);
+      bool inside = contained;
+      if (!inside) {
+        const float phi = __ldg(kp.posPhi + o);
+        inside = (box.mn[0] <= phi) & (phi < box.mx[0]) & (box.mn[1] <= zr.y) & (zr.y < box.mx[1]) &
+                 (box.mn[2] <= zr.x) & (zr.x < box.mx[2]);
+      }
+      float dR, dZ;
+      // (deltaR is tested first in the reference, DoubletSeedFinder.cpp:126-130: both are pure rejections)
+      const bool pass = inside && doublet_zr_cuts_side(bottom, cfg, mid, zr.x, zr.y, dR, dZ) && !outside_range(dR, dRMin, dRMax);
+      if (pass) {
+        if (!kFill) {
+          ++n;
+        } else {
+          const float2 xy = ldg2(p.pXY + o), var = ldg2(p.pVar + o);
+          DoubletRec rec;
+          if (doublet_finish_side(bottom, cfg, mid, dR, dZ, xy.x, xy.y, zr.y, var.x, var.y, nullptr, nullptr, 0, rec, true)) {
+            float4* dst = reinterpret_cast<float4*>(recOut + n);
+            dst[0] = make_float4(__uint_as_float(o), rec.cotTheta, rec.iDeltaR, rec.er);
+            dst[1] = make_float4(rec.u, rec.v, rec.xNew, rec.yNew);
+            keyOut[n] = rec.cotTheta;
+            mn = fminf(mn, rec.cotTheta);
+            mx = fmaxf(mx, rec.cotTheta);
+            ++n;
+          }
         }
       }
-      if (live) {
-        const uint32_t m = __ldg(p.workPos + w);
-        const uint32_t eg = __ldg(p.workEG + w);
-        const uint32_t ev = eg >> 1;
-        const int dir = (int)(eg & 1u);
-        const KdNodeDev* nodes = kp.nodes;
-        const uint32_t rootNode = ev;  // node e is the root of event e
-        MiddleSp mid;
-        {
-          const float2 mxy = ldg2(p.pXY + m), mzr = ldg2(p.pZR + m), mvar = ldg2(p.pVar + m);
-          mid.x = mxy.x; mid.y = mxy.y; mid.z = mzr.x; mid.r = mzr.y; mid.varZ = mvar.x; mid.varR = mvar.y;
-          middle_info(mid);
-        }
-        KdBox boxB, boxT;
-        kd_search_boxes(kp.orth, __ldg(kp.posPhi + m), mid.r, mid.z, dir, boxB, boxT);
-        const bool searchable = !kd_degenerate(boxB) && !kd_degenerate(boxT);  // CylindricalSpacePointKDTree.cpp:226,241
+      ++o;
+    } else if (id != kKdEnd) {
+      const float4* nd = reinterpret_cast<const float4*>(nodes + id);
+      const float4 a = __ldg(nd), b = __ldg(nd + 1);
+      const uint4 c = __ldg(reinterpret_cast<const uint4*>(nd + 2));
+      // a = {mnPhi, mnR, mnZ, mxPhi}, b = {mxR, mxZ, begin, end}, c = {rope, internal, lhs, -}
+      const bool overlaps = (a.x < box.mx[0]) & (box.mn[0] < a.w) & (a.y < box.mx[1]) & (box.mn[1] < b.x) &
+                            (a.z < box.mx[2]) & (box.mn[2] < b.y);
+      const bool cont = (box.mn[0] <= a.x) & (box.mx[0] >= a.w) & (box.mn[1] <= a.y) & (box.mx[1] >= b.x) &
+                        (box.mn[2] <= a.z) & (box.mx[2] >= b.y);
+      // Descend only into nodes of more than kKdScanBelow elements: a smaller subtree is scanned element by
+      // element instead (every reported element passes the exact `contains` test of the reference's leaves, so
+      // the reported set and its order are the same; the walk trades node visits -- divergent, dependent loads --
+      // for element tests at consecutive addresses).
+      const uint32_t e0 = __float_as_uint(b.z), e1 = __float_as_uint(b.w);
+      const bool descend = overlaps & (c.y != 0u) & !cont & (e1 - e0 > (uint32_t)kKdScanBelow);  // left child; the right one is the left one's rope
+      id = descend ? c.z : c.x;
+      if (overlaps & !descend) {
+        o = e0;  // packed positions (batch-wide)
+        oEnd = e1;
+        contained = cont;
+      }
+    } else {  // the walk is over
+      if (!bottom) {
         if (!kFill) {
-          ++cntMiddles;
-          float a, b;
-          if (searchable) {
-            capT = kd_side<false, false>(kp, mid, boxT, nodes, rootNode, nullptr, nullptr, a, b);
-            if (capT != 0u) capB = kd_side<true, false>(kp, mid, boxB, nodes, rootNode, nullptr, nullptr, a, b);
-          }
-          if (capB == 0u) capT = 0u;
-          if (capB > kMaxListLength || capT > kMaxListLength) {
-            atomicOr(p.status, kStatusOverflowDoublets);
-            capB = 0; capT = 0;
-          }
-          capB = (capB + 3u) & ~3u;  // slots and their two halves start on 16-byte boundaries of the key array (TMA)
-          capT = (capT + 3u) & ~3u;
-          p.capB[w] = capB;
-          p.capT[w] = capT;
-          if (capB != 0u) {
-            const uint32_t foot = seed_carve(capB, capT).minBytes;
-            maxFoot = foot > maxFoot ? foot : maxFoot;
-            maxB = capB > maxB ? capB : maxB;
-            maxT = capT > maxT ? capT : maxT;
-          }
+          capT = n;
+          if (capT != 0u) startWalk(true); else finishCount();
         } else {
-          const unsigned long long slot = p.slotPrefix[w] - p.slotPrefix[p.itemFirst];
-          DoubletRecord* recSlot = p.rec + slot;
-          float* keySlot = p.key + slot;
-          float mnT = 0.f, mxT = 0.f, mnB = 0.f, mxB = 0.f;
-          const uint32_t nT = kd_side<false, true>(kp, mid, boxT, nodes, rootNode, recSlot + capB, keySlot + capB, mnT, mxT);
-          bool go = nT != 0u;
+          nTop = n; mnT = mn; mxT = mx;
+          bool go = nTop != 0u;
           // BroadTripletSeedFilter.cpp:63-94 (sufficientTopDoublets; it subsumes the candidate-count test of
           // CylindricalSpacePointKDTree.cpp:245-246: doublets <= candidates)
-          if (go && p.conf) go = !(nT < conf_n_top(conf_range(cfg, mid.z), mid.r));
-          uint32_t nB = 0;
-          if (go) nB = kd_side<true, true>(kp, mid, boxB, nodes, rootNode, recSlot, keySlot, mnB, mxB);
-          go = go && nB != 0u;
-          MiddleHeader h{};
-          h.capB = capB;
-          h.offset = (uint32_t)slot;
+          if (go && p.conf) go = !(nTop < conf_n_top(conf_range(cfg, mid.z), mid.r));
           if (go) {
-            h.nB = nB; h.nT = nT;
-            h.cotMinB = float_to_ordered(mnB); h.cotMaxB = float_to_ordered(mxB);
-            h.cotMinT = float_to_ordered(mnT); h.cotMaxT = float_to_ordered(mxT);
-            const SeedCarve cv = seed_carve(nB, nT);
-            p.carve[w] = cv;
-            const uint32_t foot = cv.minBytes;
-            int c = 0;
-            while (c < kSpillClass && foot > p.classBytes[c]) ++c;
-            p.classList[(size_t)c * p.classStride + atomicAdd(p.classCount + c, 1u)] = w;
-            cntB += nB;
-            cntT += nT;
+            startWalk(true);
+            recOut = recSlot;
+            keyOut = keySlot;
           } else {
-            p.slotCount[w] = 0;
+            nTop = 0;
+            finishFill(0u, 0.f, 0.f);
           }
-          p.hdr[w] = h;
+        }
+      } else {
+        if (!kFill) {
+          capB = n;
+          finishCount();
+        } else {
+          finishFill(n, mn, mx);
         }
       }
     }

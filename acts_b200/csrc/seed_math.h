@@ -332,11 +332,13 @@ B2S_HD bool outside_range(float v, float lo, float hi) { return (v < lo) | (v > 
 // interactionPointCut == false; the cotTheta cut moves after the IP cut when
 // it is true).  deltaR is assumed to be inside [deltaRMin, deltaRMax] already
 // (the r window is found by binary search).
-template <bool kBottom>
-B2S_HD bool doublet_zr_cuts(const DeviceConfig& c, const MiddleSp& m, float zO, float rO,
-                            float& deltaR, float& deltaZ) {
-  deltaR = kBottom ? fsub(m.r, rO) : fsub(rO, m.r);
-  deltaZ = kBottom ? fsub(m.z, zO) : fsub(zO, m.z);
+// (`kBottom`: the side as a value -- a compile-time constant in the grid kernels, a per-lane bool in the
+// orthogonal seeder's walkers, where the lanes of a warp work on different sides: operands are selected, the
+// operations are the same)
+B2S_HD bool doublet_zr_cuts_side(const bool kBottom, const DeviceConfig& c, const MiddleSp& m, float zO, float rO,
+                                 float& deltaR, float& deltaZ) {
+  deltaR = fsub(kBottom ? m.r : rO, kBottom ? rO : m.r);
+  deltaZ = fsub(kBottom ? m.z : zO, kBottom ? zO : m.z);
   if (outside_range(deltaZ, c.deltaZMin, c.deltaZMax)) return false;
   const float zOriginTimesDeltaR = fsub(fmul(m.z, deltaR), fmul(m.r, deltaZ));
   if (outside_range(zOriginTimesDeltaR, fmul(c.collisionRegionMin, deltaR),
@@ -350,6 +352,11 @@ B2S_HD bool doublet_zr_cuts(const DeviceConfig& c, const MiddleSp& m, float zO, 
   }
   return true;
 }
+template <bool kBottom>
+B2S_HD bool doublet_zr_cuts(const DeviceConfig& c, const MiddleSp& m, float zO, float rO,
+                            float& deltaR, float& deltaZ) {
+  return doublet_zr_cuts_side(kBottom, c, m, zO, rO, deltaR, deltaZ);
+}
 
 struct DoubletRec {
   float cotTheta, iDeltaR, er, u, v, xNew, yNew;
@@ -357,11 +364,10 @@ struct DoubletRec {
 
 // Second half (:168-201 resp. :205-271): coordinate transform, optional IP /
 // curvature cut, experiment cuts, error term.
-template <bool kBottom>
-B2S_HD bool doublet_finish(const DeviceConfig& c, const MiddleSp& m, float deltaR, float deltaZ,
-                           float xO, float yO, float rO, float varZO, float varRO,
-                           const float* zWinLo, const float* zWinHi, int nZWin,
-                           DoubletRec& out, bool sortedWindows = false) {
+B2S_HD bool doublet_finish_side(const bool kBottom, const DeviceConfig& c, const MiddleSp& m, float deltaR, float deltaZ,
+                                float xO, float yO, float rO, float varZO, float varRO,
+                                const float* zWinLo, const float* zWinHi, int nZWin,
+                                DoubletRec& out, bool sortedWindows = false) {
   const float deltaX = fsub(xO, m.x);
   const float deltaY = fsub(yO, m.y);
   const float xNewFrame = fadd(fmul(deltaX, m.cosPhiM), fmul(deltaY, m.sinPhiM));
@@ -419,6 +425,13 @@ B2S_HD bool doublet_finish(const DeviceConfig& c, const MiddleSp& m, float delta
   out.xNew = xNewFrame;
   out.yNew = yNewFrame;
   return true;
+}
+template <bool kBottom>
+B2S_HD bool doublet_finish(const DeviceConfig& c, const MiddleSp& m, float deltaR, float deltaZ,
+                           float xO, float yO, float rO, float varZO, float varRO,
+                           const float* zWinLo, const float* zWinHi, int nZWin,
+                           DoubletRec& out, bool sortedWindows = false) {
+  return doublet_finish_side(kBottom, c, m, deltaR, deltaZ, xO, yO, rO, varZO, varRO, zWinLo, zWinHi, nZWin, out, sortedWindows);
 }
 
 // ---------------------------------------------------------------------------
