@@ -1278,6 +1278,7 @@ int b200seed_get_counters(const b200seed_handle* h, b200seed_counters* c) {
 // outermost navigation axis, GridIterator.ipp:228-242).
 int b200seed_set_phi_sector(b200seed_handle* h, uint32_t firstPhiBin, uint32_t nPhiBins) {
   if (h == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL handle");
+  if (h->plan.orthogonal) return fail(B200SEED_ERR_UNSUPPORTED, "not available on an orthogonal-seeder handle (no grid, no vertex windows)");
   if (nPhiBins != 0 && h->plan.dev.seedConfirmation) {
     return fail(B200SEED_ERR_UNSUPPORTED,
                 "seedConfirmation couples the middles of an event through bestSeedQualityMap: no phi-sector split");
@@ -1402,6 +1403,9 @@ static int run_host_batch(b200seed_handle* h, uint32_t nEvents, const uint32_t* 
   }
   const uint32_t nZWin = win.nZWin;
   if (nZWin > 0 && (win.lo == nullptr || win.hi == nullptr)) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL z window column");
+  if (h->plan.orthogonal && (nZWin > 0 || win.offsets != nullptr || phi != nullptr)) {
+    return fail(B200SEED_ERR_UNSUPPORTED, "vertex z windows / a caller-supplied phi column are not part of the orthogonal seeder");
+  }
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
   const uint32_t nTotal = spOffsets[nEvents] - spOffsets[0];
@@ -1640,6 +1644,7 @@ int b200seed_debug_grid(b200seed_handle* h, uint64_t capacity, uint32_t* copiedF
                         float* z, float* r, float* varZ, float* varR, uint64_t binCapacity,
                         uint32_t* binBegin, uint32_t* binEnd) {
   if (h == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL handle");
+  if (h->plan.orthogonal) return fail(B200SEED_ERR_UNSUPPORTED, "not available on an orthogonal-seeder handle (no grid, no vertex windows)");
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaDeviceSynchronize());
   const size_t n = h->lastCounters.nInGrid;
@@ -1670,6 +1675,7 @@ int b200seed_debug_grid(b200seed_handle* h, uint64_t capacity, uint32_t* copiedF
 // like the reference, the engine does not search them (TripletSeeder.cpp:62-69).
 int b200seed_debug_doublets(b200seed_handle* h, b200seed_doublets* out) {
   if (h == nullptr || out == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (h->plan.orthogonal) return fail(B200SEED_ERR_UNSUPPORTED, "not available on an orthogonal-seeder handle (no grid, no vertex windows)");
   if (h->lastEvents == 0) return fail(B200SEED_ERR_INVALID_ARGUMENT, "no previous run on this handle");
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaDeviceSynchronize());
