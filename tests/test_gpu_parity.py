@@ -311,11 +311,6 @@ def test_full_size_event_mu200_seed_confirmation(plugin, O):
     assert ref["quality"].size > 10_000
     assert _same_bits(got, ref)
     assert eng.counters()["nConfirmationRounds"] >= 2
-    # grid-only entry points say so on an orthogonal handle
-    for call in (lambda: eng.debug_grid(), lambda: eng.run(events.pileup_event(5, mu=5), z_windows=[(-10.0, 10.0)])):
-        with pytest.raises(plugin.SeedingError) as exc:
-            call()
-        assert exc.value.code == config.ERR_UNSUPPORTED
     eng.close()
 
 
@@ -854,6 +849,11 @@ def test_orthogonal_seeder_edge_cases_and_full_size(plugin, O):
         assert ref["bottom"].size > 0
         assert _same_bits(eng.run(ev), ref)
     assert eng.counters()["nConfirmationRounds"] >= 2
+    # grid-only entry points say so on an orthogonal handle
+    for call in (lambda: eng.debug_grid(), lambda: eng.run(events.pileup_event(5, mu=5), z_windows=[(-10.0, 10.0)])):
+        with pytest.raises(plugin.SeedingError) as exc:
+            call()
+        assert exc.value.code == config.ERR_UNSUPPORTED
     eng.close()
 
 
