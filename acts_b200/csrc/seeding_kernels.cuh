@@ -1176,6 +1176,14 @@ __global__ void k_plan_chunks(const __grid_constant__ SlotScanParams p) {
   }
   p.planWords[3] = n;
   p.planWords[4] = nWork;
+  // records of the largest chunk (the arena the host reserves): read back with the plan, no second round trip
+  unsigned long long largest = 0;
+  for (uint32_t c = 0; c < n; ++c) {
+    const unsigned long long r = p.slotPrefix[p.chunkBounds[c + 1]] - p.slotPrefix[p.chunkBounds[c]];
+    largest = r > largest ? r : largest;
+  }
+  p.planWords[5] = (uint32_t)(largest & 0xFFFFFFFFull);
+  p.planWords[6] = (uint32_t)(largest >> 32);
 }
 
 // ---------------------------------------------------------------------------

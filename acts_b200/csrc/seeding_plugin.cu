@@ -740,15 +740,7 @@ int enqueue(b200seed_handle* h) {
   const uint32_t* bounds = h->hPlan + 8;
   h->lastChunkBounds.assign(bounds, bounds + nChunks + 1);
   // arena: the largest chunk (its slots are the prefix difference, read back below with the plan)
-  unsigned long long chunkRecordsMax = 0;
-  {
-    std::vector<unsigned long long> edge(nChunks + 1, 0ull);
-    for (uint32_t c = 0; c <= nChunks; ++c) {
-      CUDA_TRY(cudaMemcpyAsync(&edge[c], h->slotPrefix.as<unsigned long long>() + bounds[c], 8, cudaMemcpyDeviceToHost, s));
-    }
-    CUDA_TRY(cudaStreamSynchronize(s));
-    for (uint32_t c = 0; c < nChunks; ++c) chunkRecordsMax = std::max(chunkRecordsMax, edge[c + 1] - edge[c]);
-  }
+  const unsigned long long chunkRecordsMax = (unsigned long long)h->hPlan[5] | ((unsigned long long)h->hPlan[6] << 32);
   for (int a = 0; a < (nChunks > 1 ? nStreams : 1); ++a) {
     CUDA_TRY(h->arenaRec[a].reserve(std::max<size_t>(64, (size_t)chunkRecordsMax * sizeof(DoubletRecord))));
     CUDA_TRY(h->arenaKey[a].reserve(std::max<size_t>(64, (size_t)chunkRecordsMax * 4)));
