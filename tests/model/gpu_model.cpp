@@ -808,3 +808,47 @@ int64_t model_check_flat_classify(uint64_t seed, int64_t n) {
 }
 
 }  // extern "C"
+
+
+// ---------------------------------------------------------------------------
+// Orthogonal seeder, k-d tree construction on the device (acts_b200/csrc/orthogonal_kernels.cuh):
+//  * k_kd_split replays libstdc++'s bidirectional std::partition by RANKS -- the k-th element of [0, P) that fails the
+//    predicate is swapped with the k-th element from the right of [P, n) that satisfies it (P = number of elements
+//    that satisfy it) -- instead of walking two cursors towards each other;
+//  * the whole construction (boxes, mid-point split above 128 elements, std::sort + median below, the pivot repair)
+//    must leave the elements in the order Acts::KDTree leaves them in.
+// Both are checked here against the real library calls, without a GPU.
+// ---------------------------------------------------------------------------
+extern "C" {
+
+// std::partition vs the rank pairing on random keys (duplicates, all-true / all-false included); returns mismatches
+int64_t model_check_partition_pairing(uint64_t seed, int maxN, int trials) {
+  std::mt19937_64 rng(seed);
+  int64_t bad = 0;
+  for (int t = 0; t < trials; ++t) {
+    const int n = 1 + (int)(rng() % (uint64_t)maxN);
+    const int mode = (int)(rng() % 5);
+    std::vector<std::pair<float, uint32_t>> a(n);
+    for (int i = 0; i < n; ++i) a[i] = {(float)(rng() % (mode == 3 ? 3u : 1000u)), (uint32_t)i};
+    const float mid = mode == 0 ? -1.f : (mode == 1 ? 2000.f : (float)(rng() % 1000u));
+    auto pred = [mid](const std::pair<float, uint32_t>& v) { return v.first < mid; };
+    std::vector<std::pair<float, uint32_t>> ref = a;
+    const auto it = std::partition(ref.begin(), ref.end(), pred);
+    const int P = (int)(it - ref.begin());
+    // the device formulation
+    int nTrue = 0;
+    for (int i = 0; i < n; ++i) nTrue += pred(a[i]) ? 1 : 0;
+    std::vector<int> listL, listR;
+    for (int i = 0; i < n; ++i) {
+      if (i < nTrue && !pred(a[i])) listL.push_back(i);
+      if (i >= nTrue && pred(a[i])) listR.push_back(i);
+    }
+    if (nTrue != P || listL.size() != listR.size()) { ++bad; continue; }
+    const int nMis = (int)listL.size();
+    for (int k = 0; k < nMis; ++k) std::swap(a[listL[k]], a[listR[nMis - 1 - k]]);
+    for (int i = 0; i < n; ++i) bad += (a[i] != ref[i]) ? 1 : 0;
+  }
+  return bad;
+}
+
+}  // extern "C"

@@ -122,3 +122,14 @@ def test_branch_free_pair_classification_equals_the_early_exit_form():
     L.model_check_flat_classify.restype = __import__("ctypes").c_int64
     L.model_check_flat_classify.argtypes = [__import__("ctypes").c_uint64, __import__("ctypes").c_int64]
     assert L.model_check_flat_classify(7, 20_000_000) == 0
+
+
+def test_partition_rank_pairing_equals_std_partition(env):
+    """k_kd_split (orthogonal seeder, k-d tree construction on the device) replays libstdc++'s bidirectional
+    std::partition by ranks: k-th misplaced element from the left <-> k-th misplaced element from the right."""
+    L = env[3].lib()
+    L.model_check_partition_pairing.restype = __import__("ctypes").c_int64
+    L.model_check_partition_pairing.argtypes = [__import__("ctypes").c_uint64, __import__("ctypes").c_int, __import__("ctypes").c_int]
+    assert L.model_check_partition_pairing(1, 40, 20000) == 0
+    assert L.model_check_partition_pairing(2, 3000, 2000) == 0
+    assert L.model_check_partition_pairing(3, 200000, 20) == 0
