@@ -798,6 +798,14 @@ struct DoubletParams {
   int conf;                              // seedConfirmation: sufficientTopDoublets after the top search
   unsigned long long* counters;
   int* status;
+  // Hand-off from the count pass to the fill pass: the r windows of every neighbour bin of a middle and the survivor
+  // bit masks of the (z, r) cuts (one word per 32 candidates), so that the fill pass neither searches the windows
+  // nor loads and tests the candidates again.  Per middle: [2 * nWin window words][top mask words][bottom mask words]
+  // at maskOff[w] (0xFFFFFFFF: the arena was full -- that middle is recomputed by the fill pass).
+  uint32_t* maskArena;
+  uint32_t maskCapacity;  // words
+  uint32_t* maskCursor;
+  uint32_t* maskOff;      // [nWork]
 };
 
 // r windows of the neighbour bins of one middle, searched by one warp (TripletSeeder.cpp:157-195,
@@ -865,11 +873,14 @@ template <bool kBottom, bool kFill>
 __device__ __forceinline__ uint32_t doublet_side(const DoubletParams& p, const MiddleSp& mid, const uint32_t* winS,
                                                  const uint32_t* winE, uint32_t nWin, uint32_t* queue,
                                                  DoubletRecord* recOut, float* keyOut, float& cotMin, float& cotMax,
-                                                 const float* zLo, const float* zHi, int nZ) {
+                                                 const float* zLo, const float* zHi, int nZ, uint32_t* masks = nullptr) {
+  // `masks`: count pass -- where to write the survivor words (NULL: nowhere); fill pass -- where to read them from
+  // (NULL: load and test the candidates like the count pass did)
   const DeviceConfig& cfg = p.cfg;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t ltMask = (1u << lane) - 1u;
   uint32_t myCount = 0;  // count pass: per lane
+  uint32_t wi = 0;       // mask word index
   uint32_t qn = 0, nOut = 0;
   float mn = 3.0e38f, mx = -3.0e38f;
   auto drain = [&](uint32_t n) {  // finish the first n (<= 32) queued candidates
@@ -909,24 +920,46 @@ __device__ __forceinline__ uint32_t doublet_side(const DoubletParams& p, const M
   for (uint32_t k = 0; k < nWin; ++k) {
     const uint32_t s = winS[k], e = winE[k];
     for (uint32_t base = s; base < e; base += 128u) {
+      if (kFill && masks != nullptr) {  // the count pass left the survivor words: no candidate is loaded or tested again
+        const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(masks + wi));  // (4 words per step, 16-byte aligned)
+        wi += 4;
+        const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t mask = mw[u];
+          if ((mask >> lane) & 1u) queue[qn + (uint32_t)__popc(mask & ltMask)] = base + 32u * (uint32_t)u + lane;
+          qn += (uint32_t)__popc(mask);
+        }
+      } else {
       float2 zr[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const uint32_t o = base + 32u * (uint32_t)u + lane;
         zr[u] = o < e ? ldg2(p.pZR + o) : make_float2(0.f, 0.f);
       }
+      uint32_t mw[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const uint32_t o = base + 32u * (uint32_t)u + lane;
         float dR, dZ;
         const bool pass = o < e && doublet_zr_cuts<kBottom>(cfg, mid, zr[u].x, zr[u].y, dR, dZ);
         if (!kFill) {
-          myCount += pass ? 1u : 0u;
+          if (masks != nullptr) {
+            mw[u] = __ballot_sync(0xffffffffu, pass);
+            myCount += lane == 0 ? (uint32_t)__popc(mw[u]) : 0u;
+          } else {
+            myCount += pass ? 1u : 0u;
+          }
         } else {
           const uint32_t mask = __ballot_sync(0xffffffffu, pass);
           if (pass) queue[qn + (uint32_t)__popc(mask & ltMask)] = o;
           qn += (uint32_t)__popc(mask);
         }
+      }
+      if (!kFill && masks != nullptr) {
+        if (lane == 0) *reinterpret_cast<uint4*>(masks + wi) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+        wi += 4;
+      }
       }
       if (kFill) {
         __syncwarp();
@@ -1006,16 +1039,59 @@ __global__ void __launch_bounds__(kDoubletWarps * 32) k_doublets(const __grid_co
         mid.x = mxy.x; mid.y = mxy.y; mid.z = mzr.x; mid.r = mzr.y; mid.varZ = mvar.x; mid.varR = mvar.y;
         middle_info(mid);
       }
-      const float firstMiddleR = ldg2(p.pZR + bs[__ldg(p.navBins + g)]).y;
-      const bool near = eg == prevEG && w == prevW + 1u;
-      prevEG = eg;
-      prevW = w;
-      warp_windows(p, bs, botBeg, nBot, topBeg, nTop, mid.r, firstMiddleR, near, W);
+      const uint32_t nWin = nBot + nTop;
+      const uint32_t nWinWords = (2u * nWin + 3u) & ~3u;  // the mask words that follow stay 16-byte aligned
+      uint32_t moff = 0xFFFFFFFFu;
+      if (kFill && p.maskArena != nullptr) moff = __ldg(p.maskOff + w);
+      if (moff != 0xFFFFFFFFu) {
+        // the count pass left this middle's windows (and survivor masks) in the arena
+        for (uint32_t k = lane; k < nWin; k += 32u) {
+          const uint2 se = __ldg(reinterpret_cast<const uint2*>(p.maskArena + moff) + k);
+          W.s[k] = se.x;
+          W.e[k] = se.y;
+        }
+        __syncwarp();
+        prevEG = 0xFFFFFFFFu;  // (W.hi is not restored: the next searched middle starts from scratch)
+      } else {
+        const float firstMiddleR = ldg2(p.pZR + bs[__ldg(p.navBins + g)]).y;
+        const bool near = eg == prevEG && w == prevW + 1u;
+        prevEG = eg;
+        prevW = w;
+        warp_windows(p, bs, botBeg, nBot, topBeg, nTop, mid.r, firstMiddleR, near, W);
+      }
+      // 128-candidate steps of the top windows (= 4 mask words each): where the bottom masks start
+      uint32_t stepsT = 0, stepsB = 0;
+      if (p.maskArena != nullptr) {
+        for (uint32_t k = lane; k < nWin; k += 32u) {
+          const uint32_t st = (W.e[k] - W.s[k] + 127u) >> 7;
+          if (k < nBot) stepsB += st; else stepsT += st;
+        }
+        for (int d = 16; d > 0; d >>= 1) {
+          stepsT += __shfl_xor_sync(0xffffffffu, stepsT, d);
+          stepsB += __shfl_xor_sync(0xffffffffu, stepsB, d);
+        }
+      }
       if (!kFill) {
         ++cntMiddles;
         float a, b;
-        capT = doublet_side<false, false>(p, mid, W.s + nBot, W.e + nBot, nTop, queue, nullptr, nullptr, a, b, nullptr, nullptr, 0);
-        if (capT != 0u) capB = doublet_side<true, false>(p, mid, W.s, W.e, nBot, queue, nullptr, nullptr, a, b, nullptr, nullptr, 0);
+        uint32_t *maskT = nullptr, *maskB = nullptr;
+        if (p.maskArena != nullptr) {
+          const uint32_t words = nWinWords + 4u * (stepsT + stepsB);
+          uint32_t off = 0;
+          if (lane == 0) off = atomicAdd(p.maskCursor, words);
+          off = __shfl_sync(0xffffffffu, off, 0);
+          const bool fits = off <= p.maskCapacity && words <= p.maskCapacity - off;
+          if (fits) {
+            for (uint32_t k = lane; k < nWin; k += 32u) {
+              reinterpret_cast<uint2*>(p.maskArena + off)[k] = make_uint2(W.s[k], W.e[k]);
+            }
+            maskT = p.maskArena + off + nWinWords;
+            maskB = maskT + 4u * stepsT;
+          }
+          if (lane == 0) p.maskOff[w] = fits ? off : 0xFFFFFFFFu;
+        }
+        capT = doublet_side<false, false>(p, mid, W.s + nBot, W.e + nBot, nTop, queue, nullptr, nullptr, a, b, nullptr, nullptr, 0, maskT);
+        if (capT != 0u) capB = doublet_side<true, false>(p, mid, W.s, W.e, nBot, queue, nullptr, nullptr, a, b, nullptr, nullptr, 0, maskB);
         if (capB == 0u) capT = 0u;  // a middle without bottoms or without tops costs nothing later
         if (capB > kMaxListLength || capT > kMaxListLength) {
           if (lane == 0) atomicOr(p.status, kStatusOverflowDoublets);
@@ -1038,11 +1114,16 @@ __global__ void __launch_bounds__(kDoubletWarps * 32) k_doublets(const __grid_co
         const uint32_t zw0 = p.zWinOffsets != nullptr ? __ldg(p.zWinOffsets + ev) : 0u;
         const int nZ = p.zWinOffsets != nullptr ? (int)(__ldg(p.zWinOffsets + ev + 1) - zw0) : p.nZWin;
         const float *zLo = p.zWinLo + zw0, *zHi = p.zWinHi + zw0;
-        const uint32_t nT = doublet_side<false, true>(p, mid, W.s + nBot, W.e + nBot, nTop, queue, recSlot + capB, keySlot + capB, mnT, mxT, zLo, zHi, nZ);
+        uint32_t *maskT = nullptr, *maskB = nullptr;
+        if (moff != 0xFFFFFFFFu) {
+          maskT = p.maskArena + moff + nWinWords;
+          maskB = maskT + 4u * stepsT;
+        }
+        const uint32_t nT = doublet_side<false, true>(p, mid, W.s + nBot, W.e + nBot, nTop, queue, recSlot + capB, keySlot + capB, mnT, mxT, zLo, zHi, nZ, maskT);
         bool go = nT != 0u;
         if (go && p.conf) go = !(nT < conf_n_top(conf_range(cfg, mid.z), mid.r));  // BroadTripletSeedFilter.cpp:63-94
         uint32_t nB = 0;
-        if (go) nB = doublet_side<true, true>(p, mid, W.s, W.e, nBot, queue, recSlot, keySlot, mnB, mxB, zLo, zHi, nZ);
+        if (go) nB = doublet_side<true, true>(p, mid, W.s, W.e, nBot, queue, recSlot, keySlot, mnB, mxB, zLo, zHi, nZ, maskB);
         go = go && nB != 0u;
         if (lane == 0) {
           MiddleHeader h{};

@@ -103,6 +103,8 @@ struct b200seed_handle {
   DevBuf midLo, midCount, workStart, workPos, workEG, workCounter;
   // doublet stage: slot sizes and prefix, chunk plan, arena, per-middle headers, per-class work lists
   DevBuf capB, capT, slotPrefix, capTileSums, capTilePrefix, planDev, hdr, carve, classList, arenaRec[2], arenaKey[2], spillScratch;
+  DevBuf maskArena, maskOff;  // count pass -> fill pass: windows + survivor masks per middle (B200SEED_MASK_WORDS_PER_SP, 0 = off)
+  uint32_t maskWordsPerSp = 192;
   // Consecutive chunks alternate between two internal streams (and two arena halves): the tail of one chunk's
   // seeding kernels overlaps the fill pass of the next.  B200SEED_CHUNK_STREAMS=1 serialises them (stage timing).
   int chunkStreams = 2;
@@ -696,6 +698,15 @@ int enqueue(b200seed_handle* h) {
   dp.conf = conf ? 1 : 0;
   dp.counters = gp.counters;
   dp.status = gp.status;
+  if (!orthogonal && h->maskWordsPerSp != 0u) {
+    const size_t words = std::min<size_t>(std::max<size_t>((size_t)nTotal * h->maskWordsPerSp, 1u << 16), 0xFFFFFFF0u);
+    CUDA_TRY(h->maskArena.reserve(words * 4));
+    CUDA_TRY(h->maskOff.reserve((size_t)nWorkMax * 4));
+    dp.maskArena = h->maskArena.as<uint32_t>();
+    dp.maskCapacity = (uint32_t)words;
+    dp.maskCursor = planWords + 7;  // zeroed with the plan words
+    dp.maskOff = h->maskOff.as<uint32_t>();
+  }
   if (orthogonal) {
     kdp.d = dp;
     k_doublets_kd<false><<<h->smCount * h->kdBlocksPerSM[0], kKdThreads, 0, s>>>(kdp);
@@ -1122,6 +1133,7 @@ static int create_impl(const b200seed_config* cfg, const b200seed_orthogonal_opt
   CREATE_TRY(cudaEventCreateWithFlags(&h->evPlan, cudaEventDisableTiming));
   h->chunkStreams = env_u32("B200SEED_CHUNK_STREAMS", 2) >= 2 ? 2 : 1;
   h->kdHostBuild = env_u32("B200SEED_KD_HOST", 0) != 0;
+  h->maskWordsPerSp = env_u32("B200SEED_MASK_WORDS_PER_SP", 192);
   h->classStreams = env_u32("B200SEED_CLASS_STREAMS", 1) != 0 ? 1 : 0;
   for (int a = 0; a < 2; ++a) {
     CREATE_TRY(cudaEventCreateWithFlags(&h->evFill[a], cudaEventDisableTiming));
@@ -1216,7 +1228,7 @@ void b200seed_destroy(b200seed_handle* h) {
                     &h->binStart, &h->binCursor, &h->tmpIdx, &h->pIdx, &h->pXY, &h->pZR, &h->pVar,
                     &h->sortScratch, &h->midLo, &h->midCount, &h->workStart, &h->workPos, &h->workEG,
                     &h->workCounter, &h->capB, &h->capT, &h->slotPrefix, &h->capTileSums, &h->capTilePrefix, &h->planDev,
-                    &h->hdr, &h->carve, &h->classList, &h->arenaRec[0], &h->arenaRec[1], &h->arenaKey[0], &h->arenaKey[1], &h->spillScratch,
+                    &h->hdr, &h->carve, &h->classList, &h->maskArena, &h->maskOff, &h->arenaRec[0], &h->arenaRec[1], &h->arenaKey[0], &h->arenaKey[1], &h->spillScratch,
                     &h->zWinOffsets, &h->slotB, &h->slotM, &h->slotT, &h->slotQ, &h->slotZ, &h->slotCount,
                     &h->seedStart, &h->tileSums, &h->tilePrefix, &h->outB, &h->outM, &h->outT, &h->outQ,
                     &h->outZ, &h->seedOffsets, &h->counters, &h->status, &h->zWin, &h->rec, &h->recZ, &h->recBegin,

@@ -97,6 +97,25 @@ def test_seeds_match_oracle(plugin, O, name, kind, mu, ids):
     eng.close()
 
 
+@pytest.mark.parametrize("words", ["0", "3", "40"])
+def test_count_to_fill_hand_off_arena_full_or_off(plugin, O, monkeypatch, words):
+    """The count pass hands its r windows and survivor masks to the fill pass through an arena
+    (B200SEED_MASK_WORDS_PER_SP words per space point, read at create).  Off (0), nearly always full (3) and
+    partly full (40): a middle that did not fit is searched and tested again by the fill pass -- same seeds."""
+    monkeypatch.setenv("B200SEED_MASK_WORDS_PER_SP", words)
+    eng = plugin.SeedingEngine(make_config("pu200", plugin.config_init))
+    orc = O.Oracle(make_config("pu200", O.config_init))
+    for i, mu in ((0, 20), (1, 60)):
+        ev = _event("pileup", i, mu)
+        got = eng.run(ev)
+        ref = orc.run(ev)
+        assert _same_bits(got, ref), f"mask words {words}, event {i}"
+        cnt = eng.counters()
+        assert cnt["nBottomDoublets"] == ref["counters"]["nBottomDoublets"]
+        assert cnt["nTopDoublets"] == ref["counters"]["nTopDoublets"]
+    eng.close()
+
+
 def test_batch_equals_single_events(plugin, O):
     from acts_b200 import events
 
