@@ -217,3 +217,42 @@ def pixel_measurements(event: int, n: int = 20000, seed: int = 42) -> tuple[dict
     meas = {"surface": surface, "loc0": loc0, "loc1": loc1, "cov00": var[:, 0], "cov11": var[:, 1],
             "cov01": rho * np.sqrt(var[:, 0] * var[:, 1])}
     return meas, transforms
+
+
+def strip_details(ev: dict, seed: int = 0, half_length: float = 12.0, gap: float = 3.0, stereo: float = 0.02) -> np.ndarray:
+    """Synthetic outer-strip calibration details for every space point of ``ev``: (n, 12) float32 =
+    outerCenter, innerToOuterSeparation, outerHalfVector, innerHalfVector
+    (Core/include/Acts/EventData/StripSpacePointCalibrationDetails.hpp:16-29).
+
+    Every space point is taken as the crossing of a double-sided strip module: the outer strip passes through the
+    point, the inner strip through the point where the line from the origin pierces a plane ``gap`` mm closer to the
+    beam line; the two strips are rotated by +-``stereo`` rad about the module normal (radial in the barrel, along z
+    for |z| > 500 mm).  The crossing sits at a random place along both strips (|s| <= 0.9 half lengths), so a
+    straight track from the origin calibrates back to the space point and tracks from displaced vertices move along
+    the outer strip or leave the module (the tolerance cut of StripSpacePointCalibrationImpl.hpp:44-74)."""
+    rng = np.random.Generator(np.random.Philox(key=977 + seed))
+    p = np.stack([ev["x"], ev["y"], ev["z"]], axis=1).astype(np.float64)
+    n = p.shape[0]
+    r = np.hypot(p[:, 0], p[:, 1])
+    barrel = np.abs(p[:, 2]) <= 500.0
+    rs = np.where(r > 0, r, 1.0)
+    normal = np.where(barrel[:, None], np.stack([p[:, 0] / rs, p[:, 1] / rs, np.zeros(n)], axis=1),
+                      np.tile(np.array([0.0, 0.0, 1.0]), (n, 1)))
+    # strip axis without stereo: along z in the barrel, radial on the discs
+    axis = np.where(barrel[:, None], np.tile(np.array([0.0, 0.0, 1.0]), (n, 1)),
+                    np.stack([p[:, 0] / rs, p[:, 1] / rs, np.zeros(n)], axis=1))
+    side = np.cross(normal, axis)
+
+    def rotated(angle):
+        return axis * np.cos(angle) + side * np.sin(angle)
+
+    u_outer, u_inner = rotated(stereo), rotated(-stereo)
+    s_outer = rng.uniform(-0.9, 0.9, size=n)[:, None]
+    s_inner = rng.uniform(-0.9, 0.9, size=n)[:, None]
+    pn = np.sum(p * normal, axis=1)
+    pn = np.where(np.abs(pn) > 1e-6, pn, 1.0)
+    q = p * (1.0 - gap / pn)[:, None]  # origin -> p pierces the inner plane here
+    oc = p - s_outer * half_length * u_outer
+    ic = q - s_inner * half_length * u_inner
+    out = np.concatenate([oc, oc - ic, half_length * u_outer, half_length * u_inner], axis=1)
+    return np.ascontiguousarray(out, dtype=np.float32)

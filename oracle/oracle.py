@@ -62,6 +62,7 @@ def lib():
         L.oracle_atan2f.argtypes = [C.c_float, C.c_float]
         L.oracle_atan2f.restype = C.c_float
         L.oracle_run.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 6 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.oracle_run_strips.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 7 + [C.c_float, C.c_int, C.POINTER(C.c_void_p)]
         L.oracle_result_free.argtypes = [C.c_void_p]
         L.oracle_result_num_seeds.argtypes = [C.c_void_p]
         L.oracle_result_num_seeds.restype = C.c_uint64
@@ -164,9 +165,18 @@ class Oracle:
         return list(zip(lo.tolist(), hi.tolist()))
 
     def run(self, ev: dict, sort_mode: int = 0, dump_doublets: bool = False,
-            z_windows=None, phi_override=None, want_grid: bool = False, vertices=None) -> dict:
+            z_windows=None, phi_override=None, want_grid: bool = False, vertices=None,
+            strip_cot_theta_diff_max=None) -> dict:
+        """``strip_cot_theta_diff_max`` given (``float("inf")`` = the reference's default): the strip triplet path
+        (TripletSeedFinder.cpp:164-406) with ``ev["strip"]`` = (n, 12) outer-strip calibration details."""
         cols = [np.ascontiguousarray(ev[k], dtype=np.float32) for k in ("x", "y", "z", "r", "varZ", "varR")]
         n = cols[0].size
+        if strip_cot_theta_diff_max is not None:
+            strip = np.ascontiguousarray(ev["strip"], dtype=np.float32).reshape(n, 12)
+            res = C.c_void_p()
+            rc = lib().oracle_run_strips(self._h, n, *[_p(c) for c in cols], _p(strip), float(strip_cot_theta_diff_max),
+                                         sort_mode, C.byref(res))
+            return self._collect(rc, res, False, False)
         if vertices is not None:
             z_windows = self.vertex_windows(*vertices)
         lo = hi = None
@@ -179,6 +189,9 @@ class Oracle:
         res = C.c_void_p()
         rc = lib().oracle_run(self._h, n, *[_p(c) for c in cols], nzw, _p(lo), _p(hi),
                               sort_mode, int(dump_doublets), _p(phi), C.byref(res))
+        return self._collect(rc, res, want_grid, dump_doublets)
+
+    def _collect(self, rc, res, want_grid, dump_doublets) -> dict:
         if rc != 0:
             raise OracleError(rc, lib().oracle_last_error().decode())
         try:

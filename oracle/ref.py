@@ -47,6 +47,7 @@ def lib():
         L.ref_create_orthogonal.argtypes = [C.POINTER(Config), C.POINTER(OrthogonalOptions), C.POINTER(C.c_void_p)]
         L.ref_destroy.argtypes = [C.c_void_p]
         L.ref_run.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 6 + [C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.ref_run_strips.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 7 + [C.c_float, C.c_int, C.POINTER(C.c_void_p)]
         L.ref_result_num_seeds.argtypes = [C.c_void_p]
         L.ref_result_num_seeds.restype = C.c_uint64
         L.ref_result_seeds.argtypes = [C.c_void_p] * 6
@@ -105,6 +106,23 @@ class Reference:
             nv = vz.size
         res = C.c_void_p()
         rc = lib().ref_run(self._h, n, *[_p(c) for c in cols], nv, _p(vz), _p(vv), C.byref(res))
+        return self._collect(rc, res)
+
+    def run_strips(self, ev: dict, cot_theta_diff_max: float = float("inf"), use_strip_info: bool = True) -> dict:
+        """The strip triplet path (TripletSeedFinder.cpp:164-406) through ref_run_strips: the reference's Core objects
+        driven like execute() drives them, TripletSeedFinder created with ``useStripInfo`` and
+        ``cotThetaDiffMax``.  ``ev["strip"]``: (n, 12) float32 outer-strip calibration details.
+        ``use_strip_info=False``: the pixel path through the same glue (must equal ``run``)."""
+        cols = [np.ascontiguousarray(ev[k], dtype=np.float32) for k in ("x", "y", "z", "r", "varZ", "varR")]
+        n = cols[0].size
+        strip = np.ascontiguousarray(ev["strip"], dtype=np.float32).reshape(n, 12)
+        res = C.c_void_p()
+        rc = lib().ref_run_strips(self._h, n, *[_p(c) for c in cols], _p(strip), float(cot_theta_diff_max),
+                                  1 if use_strip_info else 0, C.byref(res))
+        return self._collect(rc, res)
+
+    @staticmethod
+    def _collect(rc, res) -> dict:
         if rc != 0:
             raise ReferenceError_(rc, lib().ref_last_error().decode())
         try:

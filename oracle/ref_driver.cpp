@@ -27,6 +27,11 @@
 
 #include "Acts/EventData/SeedContainer.hpp"
 #include "Acts/EventData/SpacePointContainer.hpp"
+#include "Acts/Seeding/BroadTripletSeedFilter.hpp"
+#include "Acts/Seeding/CylindricalSpacePointGrid.hpp"
+#include "Acts/Seeding/DoubletSeedFinder.hpp"
+#include "Acts/Seeding/TripletSeedFinder.hpp"
+#include "Acts/Seeding/TripletSeeder.hpp"
 #include "Acts/Utilities/Logger.hpp"
 #include "ActsExamples/EventData/Seed.hpp"
 #include "ActsExamples/EventData/SpacePoint.hpp"
@@ -35,7 +40,11 @@
 #include "ActsExamples/Framework/DataHandle.hpp"
 #include "ActsExamples/Framework/IAlgorithm.hpp"
 #include "ActsExamples/Framework/WhiteBoard.hpp"
+// ref_run_strips (bottom of this file) reads what the reference's constructor derived (m_gridConfig, m_filterConfig,
+// m_seedFinder, ...): the class is included with its private section opened.  Nothing else depends on it.
+#define private public
 #include "ActsExamples/TrackFinding/GridTripletSeedingAlgorithm.hpp"
+#undef private
 #include "ActsExamples/TrackFinding/OrthogonalTripletSeedingAlgorithm.hpp"
 
 #include <atomic>
@@ -375,6 +384,134 @@ int64_t ref_run_many(void* handle, uint32_t nEvents, const uint32_t* spOffsets, 
   int64_t total = 0;
   for (uint32_t e = 0; e < nEvents; ++e) total += static_cast<int64_t>(seedCounts[e]);
   return total;
+}
+
+// ---------------------------------------------------------------------------
+// Strip triplet path (Core/src/Seeding/TripletSeedFinder.cpp:164-406).
+// GridTripletSeedingAlgorithm::execute hard-wires TripletSeedFinder::Config::useStripInfo = false (.cpp:315) and
+// copies no strip column into its core container, so the unmodified execute() cannot reach that path.
+// ref_run_strips drives the same Core objects in the sequence execute() does -- the algorithm object's own grid /
+// filter configuration and TripletSeeder (built by the reference's constructor), CylindricalSpacePointGrid,
+// DoubletSeedFinder, BroadTripletSeedFilter, TripletSeeder::createSeedsFromGroups -- but with a TripletSeedFinder
+// created with useStripInfo = true (+ cotThetaDiffMax) and the StripCalibrationDetails column filled.
+// Everything that computes is the reference's; this function is the glue between its public Core interfaces.
+// strip: 12 floats per space point = outerCenter, innerToOuterSeparation, outerHalfVector, innerHalfVector
+// (StripSpacePointCalibrationDetails.hpp:16-29).  useStripInfo = 0 runs the pixel path through the same glue: the
+// result must then equal ref_run's (tests/test_reference_pin.py checks it).  Plain doublet cuts only (the ITk doublet cut and the vertex
+// windows are file-local to the algorithm's source).
+int ref_run_strips(void* handle, uint32_t n, const float* x, const float* y, const float* z, const float* r,
+                   const float* varZ, const float* varR, const float* strip, float cotThetaDiffMax, int useStripInfo,
+                   void** result) {
+  auto* h = static_cast<RefHandle*>(handle);
+  *result = nullptr;
+  auto res = std::make_unique<RefResult>();
+  const int rc = guarded([&] {
+    const auto* alg = dynamic_cast<const Algorithm*>(h->algorithm.get());
+    if (alg == nullptr) throw std::invalid_argument("ref_run_strips: not a grid handle");
+    const Algorithm::Config& c = alg->m_cfg;
+    if (c.useExtraCuts || !c.inputVertices.empty()) throw std::invalid_argument("ref_run_strips: plain doublet cuts only");
+
+    Acts::CylindricalSpacePointGrid grid(alg->m_gridConfig, Acts::getDefaultLogger("Grid", Acts::Logging::WARNING));
+    for (uint32_t i = 0; i < n; ++i) grid.insert(i, std::atan2(y[i], x[i]), z[i], r[i]);
+    for (std::size_t b = 0; b < grid.numberOfBins(); ++b) {
+      std::ranges::sort(grid.at(b), [&](const Acts::SpacePointIndex& p, const Acts::SpacePointIndex& q) { return r[p] < r[q]; });
+    }
+
+    Acts::SpacePointContainer core(Acts::SpacePointColumns::CopiedFromIndex | Acts::SpacePointColumns::PackedXY |
+                                   Acts::SpacePointColumns::PackedZR | Acts::SpacePointColumns::VarianceZ |
+                                   Acts::SpacePointColumns::VarianceR | Acts::SpacePointColumns::StripCalibrationDetails);
+    core.reserve(grid.numberOfSpacePoints());
+    std::vector<Acts::SpacePointIndexRange> ranges;
+    float rLow = std::numeric_limits<float>::max(), rHigh = std::numeric_limits<float>::lowest();
+    for (std::size_t b = 0; b < grid.numberOfBins(); ++b) {
+      const std::uint32_t first = core.size();
+      for (Acts::SpacePointIndex i : grid.at(b)) {
+        auto sp = core.createSpacePoint();
+        sp.copiedFromIndex() = i;
+        sp.xy() = std::array<float, 2>{x[i], y[i]};
+        sp.zr() = std::array<float, 2>{z[i], r[i]};
+        sp.varianceZ() = varZ[i];
+        sp.varianceR() = varR[i];
+        const float* d = strip + 12u * i;
+        Acts::OuterStripSpacePointCalibrationDetails det;
+        det.outerCenter = {d[0], d[1], d[2]};
+        det.innerToOuterSeparation = {d[3], d[4], d[5]};
+        det.outerHalfVector = {d[6], d[7], d[8]};
+        det.innerHalfVector = {d[9], d[10], d[11]};
+        sp.outerStripCalibrationDetails() = det;
+      }
+      const std::uint32_t last = core.size();
+      ranges.emplace_back(first, last);
+      if (first != last) {
+        rLow = std::min(rLow, core[first].zr()[1]);
+        rHigh = std::max(rHigh, core[last - 1].zr()[1]);
+      }
+    }
+
+    Acts::DoubletSeedFinder::Config dc;
+    dc.spacePointsSortedByRadius = true;
+    dc.candidateDirection = Acts::Direction::Backward();
+    dc.deltaRMin = std::isnan(c.deltaRMinBottom) ? c.deltaRMin : c.deltaRMinBottom;
+    dc.deltaRMax = std::isnan(c.deltaRMaxBottom) ? c.deltaRMax : c.deltaRMaxBottom;
+    dc.deltaZMin = c.deltaZMin;
+    dc.deltaZMax = c.deltaZMax;
+    dc.impactMax = c.impactMax;
+    dc.interactionPointCut = c.interactionPointCut;
+    dc.collisionRegionMin = c.collisionRegionMin;
+    dc.collisionRegionMax = c.collisionRegionMax;
+    dc.cotThetaMax = c.cotThetaMax;
+    dc.minPt = c.minPt;
+    dc.helixCutTolerance = c.helixCutTolerance;
+    auto bottomFinder = Acts::DoubletSeedFinder::create(Acts::DoubletSeedFinder::DerivedConfig(dc, c.bFieldInZ));
+    dc.candidateDirection = Acts::Direction::Forward();
+    dc.deltaRMin = std::isnan(c.deltaRMinTop) ? c.deltaRMin : c.deltaRMinTop;
+    dc.deltaRMax = std::isnan(c.deltaRMaxTop) ? c.deltaRMax : c.deltaRMaxTop;
+    auto topFinder = Acts::DoubletSeedFinder::create(Acts::DoubletSeedFinder::DerivedConfig(dc, c.bFieldInZ));
+
+    Acts::TripletSeedFinder::Config tc;
+    // the one switch execute() does not offer (0: the glue itself can be checked -- same seeds as ref_run)
+    tc.useStripInfo = useStripInfo != 0;
+    tc.sortedByCotTheta = true;
+    tc.minPt = c.minPt;
+    tc.sigmaScattering = c.sigmaScattering;
+    tc.radLengthPerSeed = c.radLengthPerSeed;
+    tc.impactMax = c.impactMax;
+    tc.helixCutTolerance = c.helixCutTolerance;
+    tc.toleranceParam = c.toleranceParam;
+    tc.cotThetaDiffMax = cotThetaDiffMax;
+    auto tripletFinder = Acts::TripletSeedFinder::create(Acts::TripletSeedFinder::DerivedConfig(tc, c.bFieldInZ));
+
+    const Acts::Range1D<float> variableRange = {std::floor(rLow / 2) * 2 + c.deltaRMiddleMinSPRange,
+                                                std::floor(rHigh / 2) * 2 - c.deltaRMiddleMaxSPRange};
+    Acts::BroadTripletSeedFilter::State filterState;
+    Acts::BroadTripletSeedFilter::Cache filterCache;
+    Acts::BroadTripletSeedFilter filter(alg->m_filterConfig, filterState, filterCache, *alg->m_filterLogger);
+    Acts::TripletSeeder::Cache cache;
+    Acts::SeedContainer seeds;
+    std::vector<Acts::SpacePointContainer::ConstRange> below, above;
+    for (const auto [bottomBins, middleBin, topBins] : grid.binnedGroup()) {
+      const auto middles = core.range(ranges.at(middleBin)).asConst();
+      if (middles.empty()) continue;
+      below.clear();
+      above.clear();
+      for (const auto b : bottomBins) below.push_back(core.range(ranges.at(b)).asConst());
+      for (const auto t : topBins) above.push_back(core.range(ranges.at(t)).asConst());
+      const auto rRangeMiddle = alg->retrieveRadiusRangeForMiddle(middles.front(), variableRange);
+      alg->m_seedFinder->createSeedsFromGroups(cache, *bottomFinder, *topFinder, *tripletFinder, filter, core, below, middles,
+                                               above, rRangeMiddle, seeds);
+    }
+    for (const auto& seed : seeds) {
+      const auto idx = seed.spacePointIndices();
+      if (idx.size() != 3) throw std::runtime_error("seed without three space points");
+      res->bottom.push_back(core.at(idx[0]).copiedFromIndex());
+      res->middle.push_back(core.at(idx[1]).copiedFromIndex());
+      res->top.push_back(core.at(idx[2]).copiedFromIndex());
+      res->quality.push_back(seed.quality());
+      res->vertexZ.push_back(seed.vertexZ());
+    }
+  });
+  if (rc == B200SEED_OK) *result = res.release();
+  return rc;
 }
 
 uint64_t ref_result_num_seeds(const void* r) { return static_cast<const RefResult*>(r)->bottom.size(); }

@@ -486,6 +486,11 @@ struct Event {
   ZWindows zw;
   int sortMode = kFaithful;
   const float* phiOverride = nullptr;  // optional precomputed phi (tests)
+  // strip triplet path (TripletSeedFinder::Config::useStripInfo = true): 12 floats per ORIGINAL space point =
+  // outerCenter, innerToOuterSeparation, outerHalfVector, innerHalfVector
+  // (StripSpacePointCalibrationDetails.hpp:16-29); NULL = pixel path
+  const float* strip = nullptr;
+  float cotThetaDiffMax = std::numeric_limits<float>::infinity();  // TripletSeedFinder.hpp:175
   // bounded sampling for the timed baseline: only navigation entries g with
   // g % navStride == navPhase are seeded (the grid is always built in full)
   std::uint32_t navStride = 1, navPhase = 0;
@@ -871,6 +876,172 @@ void createTripletTopCandidates(Event& ev, Index m, Index bottomDoublet,
   topBegin += topDoubletOffset;
 }
 
+// ---------------------------------------------------------------------------
+// Strip triplet path.
+// ---------------------------------------------------------------------------
+using Vec3 = std::array<float, 3>;
+// Utilities/detail/StdArrayLinalg.hpp:57-83
+inline float dot3(const Vec3& a, const Vec3& b) {
+  float result = 0;
+  for (std::size_t i = 0; i < 3; ++i) result += a[i] * b[i];
+  return result;
+}
+inline Vec3 cross3(const Vec3& a, const Vec3& b) {
+  return {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+}
+// StripSpacePointCalibrationDetails.hpp:33-49 + detail/StripSpacePointCalibrationImpl.hpp:22-42
+struct StripDerived {
+  Vec3 iosvCrossIhv, iosvCrossOhv, ihvCrossOhv, oc, ohv;
+};
+inline StripDerived deriveStrip(const float* d) {
+  const Vec3 oc{d[0], d[1], d[2]}, iosv{d[3], d[4], d[5]}, ohv{d[6], d[7], d[8]}, ihv{d[9], d[10], d[11]};
+  StripDerived out;
+  out.ihvCrossOhv = cross3(ihv, ohv);
+  out.iosvCrossOhv = cross3(iosv, ohv);
+  out.iosvCrossIhv = cross3(iosv, ihv);
+  out.oc = oc;
+  out.ohv = ohv;
+  return out;
+}
+// detail/StripSpacePointCalibrationImpl.hpp:44-85
+inline bool calibrateStrip(const Vec3& direction, const StripDerived& sp, Vec3& calibrated, float tolerance) {
+  const float scale = dot3(direction, sp.ihvCrossOhv);
+  const float sInner = dot3(direction, sp.iosvCrossOhv);
+  if (std::abs(sInner) > std::abs(scale) * tolerance) return false;
+  const float sOuter = dot3(direction, sp.iosvCrossIhv);
+  if (std::abs(sOuter) > std::abs(scale) * tolerance) return false;
+  const float sOuterNorm = sOuter / scale;
+  for (std::size_t i = 0; i < 3; ++i) calibrated[i] = sp.oc[i] + sp.ohv[i] * sOuterNorm;
+  return true;
+}
+
+// TripletSeedFinder.cpp:164-406 (strip path, sortedByCotTheta = true); window handling as above.
+void createStripTripletTopCandidates(Event& ev, Index m, Index bottomDoublet,
+                                     std::size_t& topBegin, std::size_t topEnd) {
+  const Setup& s = *ev.s;
+  const Packed& p = ev.sp;
+  const Doublets& B = ev.bottomDoublets;
+  const Doublets& T = ev.topDoublets;
+  TopCandidates& out = ev.topCandidates;
+
+  const float rM = p.r[m];
+  const float cosPhiM = p.x[m] / rM;
+  const float sinPhiM = p.y[m] / rM;
+  const float varianceZM = p.varZ[m];
+  const float varianceRM = p.varR[m];
+
+  const float cotThetaB0 = B.cotTheta[bottomDoublet];
+  const float erB = B.er[bottomDoublet];
+  const float iDeltaRB = B.iDeltaR[bottomDoublet];
+  const float Ub0 = B.u[bottomDoublet];
+  const float Vb0 = B.v[bottomDoublet];
+
+  const float iSinTheta2 = 1 + cotThetaB0 * cotThetaB0;
+  const float sigmaSquaredPtDependent = iSinTheta2 * s.sigmapT2perRadius;
+  const float scatteringInRegion2 = s.multipleScattering2 * iSinTheta2;
+
+  const float sinTheta = 1 / std::sqrt(iSinTheta2);
+  const float cosTheta = cotThetaB0 * sinTheta;
+  const std::array<float, 2> rot = {cosPhiM * sinTheta, sinPhiM * sinTheta};
+
+  const StripDerived calM = deriveStrip(ev.strip + 12u * p.copiedFrom[m]);
+  const StripDerived calB = deriveStrip(ev.strip + 12u * p.copiedFrom[B.sp[bottomDoublet]]);
+
+  std::size_t topDoubletOffset = 0;
+  for (std::size_t k = topBegin; k < topEnd; ++k) {
+    const std::size_t topDoubletIndex = k - topBegin;
+    const Index t = ev.sortedTops[k].index;
+    {  // :226-238
+      const float cotThetaT = T.cotTheta[t];
+      const float deltaCotTheta = cotThetaB0 - cotThetaT;
+      const float cotThetaDiffMax2 = ev.cotThetaDiffMax * ev.cotThetaDiffMax;
+      if (deltaCotTheta * deltaCotTheta > cotThetaDiffMax2) {
+        if (cotThetaB0 < cotThetaT) break;
+        topDoubletOffset = topDoubletIndex + 1;
+        continue;
+      }
+    }
+    ++ev.cnt.nTripletTests;
+    const float dU0 = T.u[t] - Ub0;
+    if (dU0 == 0) continue;
+    const float A0 = (T.v[t] - Vb0) / dU0;
+
+    const Vec3 directionMiddle = {rot[0] - rot[1] * A0, rot[0] * A0 + rot[1], cosTheta};
+    Vec3 rMTransf{};
+    if (!calibrateStrip(directionMiddle, calM, rMTransf, s.cfg.toleranceParam)) continue;
+
+    const float zDirectionMiddle = cosTheta * std::sqrt(1 + A0 * A0);
+
+    const float B0 = 2 * (Vb0 - A0 * Ub0);
+    const float Cb = 1 - B0 * B.y[bottomDoublet];
+    const float Sb = A0 + B0 * B.x[bottomDoublet];
+    const Vec3 directionBottom = {rot[0] * Cb - rot[1] * Sb, rot[0] * Sb + rot[1] * Cb, zDirectionMiddle};
+    Vec3 rBTransf{};
+    if (!calibrateStrip(directionBottom, calB, rBTransf, s.cfg.toleranceParam)) continue;
+
+    const float Ct = 1 - B0 * T.y[t];
+    const float St = A0 + B0 * T.x[t];
+    const Vec3 directionTop = {rot[0] * Ct - rot[1] * St, rot[0] * St + rot[1] * Ct, zDirectionMiddle};
+    const StripDerived calT = deriveStrip(ev.strip + 12u * p.copiedFrom[T.sp[t]]);
+    Vec3 rTTransf{};
+    if (!calibrateStrip(directionTop, calT, rTTransf, s.cfg.toleranceParam)) continue;
+
+    const float xB = rBTransf[0] - rMTransf[0];
+    const float yB = rBTransf[1] - rMTransf[1];
+    const float zB = rBTransf[2] - rMTransf[2];
+    const float xT = rTTransf[0] - rMTransf[0];
+    const float yT = rTTransf[1] - rMTransf[1];
+    const float zT = rTTransf[2] - rMTransf[2];
+
+    const float iDeltaRB2 = 1 / (xB * xB + yB * yB);
+    const float iDeltaRT2 = 1 / (xT * xT + yT * yT);
+
+    const float cotThetaB = -zB * std::sqrt(iDeltaRB2);
+    const float cotThetaT = zT * std::sqrt(iDeltaRT2);
+
+    const float averageCotTheta = 0.5f * (cotThetaB + cotThetaT);
+    const float cotThetaAvg2 = averageCotTheta * averageCotTheta;
+
+    const float error2 = T.er[t] + erB +
+                         2 * (cotThetaAvg2 * varianceRM + varianceZM) *
+                             iDeltaRB * T.iDeltaR[t];
+
+    const float deltaCotTheta = cotThetaB - cotThetaT;
+    const float deltaCotTheta2 = deltaCotTheta * deltaCotTheta;
+    if (deltaCotTheta2 > error2 + scatteringInRegion2) continue;
+
+    const float rMxy = std::sqrt(rMTransf[0] * rMTransf[0] + rMTransf[1] * rMTransf[1]);
+    const float irMxy = 1 / rMxy;
+    const float Ax = rMTransf[0] * irMxy;
+    const float Ay = rMTransf[1] * irMxy;
+
+    const float Ub = (xB * Ax + yB * Ay) * iDeltaRB2;
+    const float Vb = (yB * Ax - xB * Ay) * iDeltaRB2;
+    const float Ut = (xT * Ax + yT * Ay) * iDeltaRT2;
+    const float Vt = (yT * Ax - xT * Ay) * iDeltaRT2;
+
+    const float dU = Ut - Ub;
+    if (dU == 0) continue;
+    const float A = (Vt - Vb) / dU;
+    const float S2 = 1 + A * A;
+    const float Bc = Vb - A * Ub;
+    const float B2 = Bc * Bc;
+    if (S2 < B2 * s.minHelixDiameter2) continue;
+
+    const float iHelixDiameter2 = B2 / S2;
+    const float p2scatterSigma = iHelixDiameter2 * sigmaSquaredPtDependent;
+    if (deltaCotTheta2 > error2 + p2scatterSigma) continue;
+
+    const float im = std::abs((A - Bc * rMxy) * rMxy);
+    if (im > s.cfg.impactMax) continue;
+
+    out.top.push_back(T.sp[t]);
+    out.curvature.push_back(Bc / std::sqrt(S2));
+    out.impact.push_back(im);
+  }
+  topBegin += topDoubletOffset;
+}
+
 float getBestSeedQuality(const std::unordered_map<Index, float>& map, Index sp) {
   auto it = map.find(sp);
   if (it != map.end()) return it->second;
@@ -1149,7 +1320,11 @@ void seedsForMiddleT(Event& ev, Index m, MakeTops&& makeTops, MakeBottoms&& make
     ++bottomInRound;
     if (topBegin == topEnd) break;
     ev.topCandidates.clear();
-    createTripletTopCandidates(ev, m, b.index, topBegin, topEnd);
+    if (ev.strip != nullptr) {  // TripletSeedFinder.cpp:408-420: useStripInfo picks the strip implementation
+      createStripTripletTopCandidates(ev, m, b.index, topBegin, topEnd);
+    } else {
+      createTripletTopCandidates(ev, m, b.index, topBegin, topEnd);
+    }
     ev.cnt.nCandidates += ev.topCandidates.size();
     candThisMiddle += ev.topCandidates.size();
     candThisRound += ev.topCandidates.size();
@@ -1857,6 +2032,31 @@ int oracle_run(const oracle_handle* h, std::uint32_t n, const float* x, const fl
     } else {
       runEvent(ev);
     }
+    *out = res;
+    return B200SEED_OK;
+  } catch (const std::exception& e) {
+    return fail(B200SEED_ERR_RUNTIME, e.what());
+  }
+}
+// One event through the strip triplet path (TripletSeedFinder::Config::useStripInfo = true, cotThetaDiffMax):
+// strip = 12 floats per space point (outerCenter, innerToOuterSeparation, outerHalfVector, innerHalfVector).
+int oracle_run_strips(const oracle_handle* h, std::uint32_t n, const float* x, const float* y,
+                      const float* z, const float* r, const float* varZ, const float* varR,
+                      const float* strip, float cotThetaDiffMax, int sortMode, oracle_event_result** out) {
+  try {
+    if (h->orthogonal) return fail(B200SEED_ERR_UNSUPPORTED, "strip triplet path: grid handles only");
+    if (strip == nullptr && n != 0) return fail(B200SEED_ERR_INVALID_ARGUMENT, "strip details missing");
+    auto* res = new oracle_event_result;
+    Event& ev = res->ev;
+    ev.s = &h->setup;
+    ev.x = x; ev.y = y; ev.z = z; ev.r = r; ev.varZ = varZ; ev.varR = varR;
+    ev.n = n;
+    ev.zw = {nullptr, nullptr, 0};
+    ev.sortMode = sortMode;
+    static const float kNoStrip[12] = {};
+    ev.strip = strip != nullptr ? strip : kNoStrip;
+    ev.cotThetaDiffMax = cotThetaDiffMax;
+    runEvent(ev);
     *out = res;
     return B200SEED_OK;
   } catch (const std::exception& e) {
