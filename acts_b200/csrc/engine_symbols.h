@@ -34,6 +34,7 @@
 #define b200seed_get_stage_times B200SEED_E(get_stage_times)
 #define b200seed_get_stage_times_ex B200SEED_E(get_stage_times_ex)
 #define b200seed_run_vertices B200SEED_E(run_vertices)
+#define b200seed_run_strips B200SEED_E(run_strips)
 #define b200seed_vertex_windows B200SEED_E(vertex_windows)
 #define b200seed_run_batch_windows B200SEED_E(run_batch_windows)
 #define b200seed_estimate_params B200SEED_E(estimate_params)

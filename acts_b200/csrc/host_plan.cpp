@@ -399,6 +399,7 @@ void build(const b200seed_config& c, HostPlan& plan, const b200seed_orthogonal_o
   plan.useVertexZCuts = c.useVertexZCuts != 0;
   plan.vertexZNSigma = c.vertexZNSigma;
   plan.vertexZMargin = c.vertexZMargin;
+  plan.toleranceParam = c.toleranceParam;
 
   b200seed_info& info = plan.info;
   std::memset(&info, 0, sizeof(info));

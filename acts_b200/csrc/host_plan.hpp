@@ -44,6 +44,7 @@ struct HostPlan {
   // Config::inputVertices / vertexZNSigma / vertexZMargin (GridTripletSeedingAlgorithm.hpp:239-243)
   bool useVertexZCuts = false;
   double vertexZNSigma = 3.0, vertexZMargin = 0.0;
+  float toleranceParam = 1.1f;  // TripletSeedFinder::Config::toleranceParam (strip triplet path only)
 };
 
 // Validates like the reference (same exception classes mapped to status codes)

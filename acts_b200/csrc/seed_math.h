@@ -617,6 +617,130 @@ B2S_HD int classify_pair_lazy(const DeviceConfig& c, float rM, float varZM, floa
 }
 
 // ---------------------------------------------------------------------------
+// Triplets, strip path: TripletSeedFinder.cpp:164-406 (useStripInfo = true) with
+// detail/StripSpacePointCalibrationImpl.hpp:22-85.  A space point carries the
+// derived calibration details (three cross products, outer strip centre and half
+// vector) as one 64-byte record, computed once per event by k_gather_strips.
+// ---------------------------------------------------------------------------
+struct StripDerived {  // StripSpacePointCalibrationDetails.hpp:33-49
+  float ihvXohv[3];   // innerCrossOuterHalfVector
+  float iosvXohv[3];  // innerToOuterSeparationCrossOuterHalfVector
+  float iosvXihv[3];  // innerToOuterSeparationCrossInnerHalfVector
+  float oc[3], ohv[3];
+  float pad;
+};
+static_assert(sizeof(StripDerived) == 64, "four 16-byte words per space point");
+// Utilities/detail/StdArrayLinalg.hpp:70-83
+B2S_HD void strip_cross(const float* a, const float* b, float* out) {
+  out[0] = fsub(fmul(a[1], b[2]), fmul(a[2], b[1]));
+  out[1] = fsub(fmul(a[2], b[0]), fmul(a[0], b[2]));
+  out[2] = fsub(fmul(a[0], b[1]), fmul(a[1], b[0]));
+}
+// raw: outerCenter, innerToOuterSeparation, outerHalfVector, innerHalfVector (12 floats)
+B2S_HD void strip_derive(const float* raw, StripDerived& o) {  // StripSpacePointCalibrationImpl.hpp:22-42
+  const float* oc = raw;
+  const float* iosv = raw + 3;
+  const float* ohv = raw + 6;
+  const float* ihv = raw + 9;
+  strip_cross(ihv, ohv, o.ihvXohv);
+  strip_cross(iosv, ohv, o.iosvXohv);
+  strip_cross(iosv, ihv, o.iosvXihv);
+  for (int i = 0; i < 3; ++i) { o.oc[i] = oc[i]; o.ohv[i] = ohv[i]; }
+  o.pad = 0.0f;
+}
+// stdArrayDot: result = 0; result += a[i] * b[i] (StdArrayLinalg.hpp:60-67)
+B2S_HD float strip_dot(float dx, float dy, float dz, const float* b) {
+  return fadd(fadd(fadd(0.0f, fmul(dx, b[0])), fmul(dy, b[1])), fmul(dz, b[2]));
+}
+// calibrateOuterStripSpacePoint, StripSpacePointCalibrationImpl.hpp:44-85
+B2S_HD bool strip_calibrate(float dx, float dy, float dz, const StripDerived& sp, float tolerance, float* out) {
+  const float scale = strip_dot(dx, dy, dz, sp.ihvXohv);
+  const float limit = fmul(fabs_(scale), tolerance);
+  const float sInner = strip_dot(dx, dy, dz, sp.iosvXohv);
+  if (fabs_(sInner) > limit) return false;
+  const float sOuter = strip_dot(dx, dy, dz, sp.iosvXihv);
+  if (fabs_(sOuter) > limit) return false;
+  const float sOuterNorm = fdiv(sOuter, scale);
+  for (int i = 0; i < 3; ++i) out[i] = fadd(sp.oc[i], fmul(sp.ohv[i], sOuterNorm));
+  return true;
+}
+
+struct StripBottomCtx {  // loop invariants of one (middle, bottom doublet), :172-212
+  float cotThetaB0, erB, iDeltaRB, Ub0, Vb0, xB, yB;
+  float sigmaSquaredPtDependent, scatteringInRegion2;
+  float rot0, rot1, cosTheta;
+};
+B2S_HD void strip_bottom_ctx(const DeviceConfig& c, float cosPhiM, float sinPhiM, StripBottomCtx& b) {
+  const float iSinTheta2 = fadd(1.0f, fmul(b.cotThetaB0, b.cotThetaB0));
+  b.sigmaSquaredPtDependent = fmul(iSinTheta2, c.sigmapT2perRadius);
+  b.scatteringInRegion2 = fmul(c.multipleScattering2, iSinTheta2);
+  const float sinTheta = fdiv(1.0f, fsqrt(iSinTheta2));
+  b.cosTheta = fmul(b.cotThetaB0, sinTheta);
+  b.rot0 = fmul(cosPhiM, sinTheta);
+  b.rot1 = fmul(sinPhiM, sinTheta);
+}
+// the cot(theta) pre-filter of :226-238: true = the top is outside the window of this bottom
+B2S_HD bool strip_outside_window(float cotThetaB0, float cotThetaT, float cotThetaDiffMax2) {
+  const float deltaCotTheta = fsub(cotThetaB0, cotThetaT);
+  return fmul(deltaCotTheta, deltaCotTheta) > cotThetaDiffMax2;
+}
+// One (bottom, top) pair inside the window, :240-395.  true = candidate {top, curvature, impact}.
+B2S_HD bool eval_strip_pair(const DeviceConfig& c, float toleranceParam, float varZM, float varRM, const StripBottomCtx& b,
+                            const StripDerived& calM, const StripDerived& calB, const StripDerived& calT, float erT,
+                            float iDeltaRT, float uT, float vT, float xT, float yT, float& curvature, float& impact) {
+  const float dU0 = fsub(uT, b.Ub0);
+  if (dU0 == 0) return false;
+  const float A0 = fdiv(fsub(vT, b.Vb0), dU0);
+  float rM[3], rB[3], rT[3];
+  if (!strip_calibrate(fsub(b.rot0, fmul(b.rot1, A0)), fadd(fmul(b.rot0, A0), b.rot1), b.cosTheta, calM, toleranceParam, rM)) return false;
+  const float zDirectionMiddle = fmul(b.cosTheta, fsqrt(fadd(1.0f, fmul(A0, A0))));
+  const float B0 = fmul(2.0f, fsub(b.Vb0, fmul(A0, b.Ub0)));
+  const float Cb = fsub(1.0f, fmul(B0, b.yB));
+  const float Sb = fadd(A0, fmul(B0, b.xB));
+  if (!strip_calibrate(fsub(fmul(b.rot0, Cb), fmul(b.rot1, Sb)), fadd(fmul(b.rot0, Sb), fmul(b.rot1, Cb)), zDirectionMiddle, calB,
+                       toleranceParam, rB)) return false;
+  const float Ct = fsub(1.0f, fmul(B0, yT));
+  const float St = fadd(A0, fmul(B0, xT));
+  if (!strip_calibrate(fsub(fmul(b.rot0, Ct), fmul(b.rot1, St)), fadd(fmul(b.rot0, St), fmul(b.rot1, Ct)), zDirectionMiddle, calT,
+                       toleranceParam, rT)) return false;
+  const float xB = fsub(rB[0], rM[0]), yB = fsub(rB[1], rM[1]), zB = fsub(rB[2], rM[2]);
+  const float xTn = fsub(rT[0], rM[0]), yTn = fsub(rT[1], rM[1]), zT = fsub(rT[2], rM[2]);
+  const float iDeltaRB2 = fdiv(1.0f, fadd(fmul(xB, xB), fmul(yB, yB)));
+  const float iDeltaRT2 = fdiv(1.0f, fadd(fmul(xTn, xTn), fmul(yTn, yTn)));
+  const float cotThetaB = fmul(-zB, fsqrt(iDeltaRB2));
+  const float cotThetaT = fmul(zT, fsqrt(iDeltaRT2));
+  const float averageCotTheta = fmul(0.5f, fadd(cotThetaB, cotThetaT));
+  const float cotThetaAvg2 = fmul(averageCotTheta, averageCotTheta);
+  const float corr = fmul(fmul(fmul(2.0f, fadd(fmul(cotThetaAvg2, varRM), varZM)), b.iDeltaRB), iDeltaRT);
+  const float error2 = fadd(fadd(erT, b.erB), corr);
+  const float deltaCotTheta = fsub(cotThetaB, cotThetaT);
+  const float deltaCotTheta2 = fmul(deltaCotTheta, deltaCotTheta);
+  if (deltaCotTheta2 > fadd(error2, b.scatteringInRegion2)) return false;
+  const float rMxy = fsqrt(fadd(fmul(rM[0], rM[0]), fmul(rM[1], rM[1])));
+  const float irMxy = fdiv(1.0f, rMxy);
+  const float Ax = fmul(rM[0], irMxy), Ay = fmul(rM[1], irMxy);
+  const float Ub = fmul(fadd(fmul(xB, Ax), fmul(yB, Ay)), iDeltaRB2);
+  const float Vb = fmul(fsub(fmul(yB, Ax), fmul(xB, Ay)), iDeltaRB2);
+  const float Ut = fmul(fadd(fmul(xTn, Ax), fmul(yTn, Ay)), iDeltaRT2);
+  const float Vt = fmul(fsub(fmul(yTn, Ax), fmul(xTn, Ay)), iDeltaRT2);
+  const float dU = fsub(Ut, Ub);
+  if (dU == 0) return false;
+  const float A = fdiv(fsub(Vt, Vb), dU);
+  const float S2 = fadd(1.0f, fmul(A, A));
+  const float B = fsub(Vb, fmul(A, Ub));
+  const float B2 = fmul(B, B);
+  if (S2 < fmul(B2, c.minHelixDiameter2)) return false;
+  const float iHelixDiameter2 = fdiv(B2, S2);
+  const float p2scatterSigma = fmul(iHelixDiameter2, b.sigmaSquaredPtDependent);
+  if (deltaCotTheta2 > fadd(error2, p2scatterSigma)) return false;
+  const float im = fabs_(fmul(fsub(A, fmul(B, rMxy)), rMxy));
+  if (im > c.impactMax) return false;
+  curvature = fdiv(B, fsqrt(S2));
+  impact = im;
+  return true;
+}
+
+// ---------------------------------------------------------------------------
 // Seed filter: BroadTripletSeedFilter.cpp:96-322 (seedConfirmation == false).
 // The candidates of one (middle, bottom) pair are given in curvature-sorted
 // order (curv[], topR[], impact[] indexed by sorted rank).  The weight of

@@ -44,6 +44,8 @@ extern "C" {
   int P##run_vertices(P##handle*, uint32_t, const float*, const float*, const float*, const float*,         \
                       const float*, const float*, uint32_t, const double*, const double*, b200seed_seeds*); \
   int P##vertex_windows(const P##handle*, uint32_t, const double*, const double*, float*, float*);          \
+  int P##run_strips(P##handle*, uint32_t, const float*, const float*, const float*, const float*,           \
+                    const float*, const float*, const float*, float, b200seed_seeds*);                      \
   int P##run_batch_windows(P##handle*, uint32_t, const uint32_t*, const float*, const float*, const float*, \
                            const float*, const float*, const float*, const uint32_t*, const float*,         \
                            const float*, uint64_t*, b200seed_seeds*);                                       \
@@ -239,6 +241,13 @@ int b200seed_run_vertices(b200seed_handle* h, uint32_t nSpacePoints, const float
                           const double* vertexZ, const double* vertexVarZ, b200seed_seeds* out) {
   B200SEED_FORWARD(h, b200ex_run_vertices(h->exact, nSpacePoints, x, y, z, r, varZ, varR, nVertices, vertexZ, vertexVarZ, out),
                    b200rx_run_vertices(h->relaxed, nSpacePoints, x, y, z, r, varZ, varR, nVertices, vertexZ, vertexVarZ, out));
+}
+
+int b200seed_run_strips(b200seed_handle* h, uint32_t nSpacePoints, const float* x, const float* y, const float* z,
+                        const float* r, const float* varZ, const float* varR, const float* stripDetails,
+                        float cotThetaDiffMax, b200seed_seeds* out) {
+  B200SEED_FORWARD(h, b200ex_run_strips(h->exact, nSpacePoints, x, y, z, r, varZ, varR, stripDetails, cotThetaDiffMax, out),
+                   b200rx_run_strips(h->relaxed, nSpacePoints, x, y, z, r, varZ, varR, stripDetails, cotThetaDiffMax, out));
 }
 
 int b200seed_vertex_windows(const b200seed_handle* h, uint32_t nVertices, const double* vertexZ, const double* vertexVarZ,

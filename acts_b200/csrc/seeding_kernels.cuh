@@ -529,6 +529,31 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_bins(const __grid_constan
   }
 }
 
+// Strip triplet path: the derived calibration details of every space point of the packed copy
+// (deriveOuterStripSpacePointCalibrationDetails, StripSpacePointCalibrationImpl.hpp:22-42; the reference derives them
+// per (bottom, top) pair, TripletSeedFinder.cpp:205-213,282-286 -- same inputs, same operations, same bits).
+// raw: 12 floats per ORIGINAL space point of the (single) event.
+__global__ void __launch_bounds__(256) k_gather_strips(const uint32_t* __restrict__ pIdx, const uint32_t* __restrict__ nPackedPtr,
+                                                       const float* __restrict__ raw, StripDerived* __restrict__ out) {
+  const uint32_t nPacked = *nPackedPtr;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < nPacked; pos += stride) {
+    float d[12];
+    const float4* src = reinterpret_cast<const float4*>(raw + 12ull * pIdx[pos]);  // 48 bytes per point: 16-byte aligned
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const float4 v = __ldg(src + q);
+      d[4 * q] = v.x; d[4 * q + 1] = v.y; d[4 * q + 2] = v.z; d[4 * q + 3] = v.w;
+    }
+    StripDerived o;
+    strip_derive(d, o);
+    const uint4* w = reinterpret_cast<const uint4*>(&o);
+    uint4* dst = reinterpret_cast<uint4*>(out + pos);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q] = w[q];
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Middle work list
 // ---------------------------------------------------------------------------
@@ -1319,7 +1344,11 @@ struct SeedParams {
   float* recZ;           // zOrigin
   uint32_t *recBegin, *recCount;  // per work item
   uint32_t* recCounter;  // bump allocator (keeps counting past the capacity: tells the host what to reserve)
-  uint32_t recCapacity;
+  uint32_t recCapacity;  // strip triplet path only (TripletSeedFinder::Config::useStripInfo): derived calibration details per packed
+  // position, cotThetaDiffMax^2, toleranceParam
+  const StripDerived* pStrip;
+  float cotThetaDiffMax2;
+  float toleranceParam;
 };
 
 // meta word of a candidate record
@@ -1561,7 +1590,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // generic-proxy accesses to shared memory before, async-proxy (TMA) writes to the same bytes after
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <bool kConf, bool kSpill>
+// kStrip: the strip triplet path (TripletSeedFinder.cpp:164-406) in place of phases 3a-3c; everything else is shared.
+template <bool kConf, bool kSpill, bool kStrip = false>
 __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_constant__ SeedParams p) {
   const uint32_t THREADS = blockDim.x;
   extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -1673,12 +1703,14 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
     for (uint32_t t = tid; t < nT; t += THREADS) {
       const float4* src = reinterpret_cast<const float4*>(recT + rankT[t]);
       const float4 a = __ldg(src), b = __ldg(src + 1);
-      sPos[t] = __float_as_uint(a.x);
+      // (strip path: the index of the top in the arena slot instead -- its record holds the position AND x', y')
+      sPos[t] = kStrip ? (uint32_t)rankT[t] : __float_as_uint(a.x);
       sA[t] = make_float4(a.y, a.w, a.z, b.x);
       sV[t] = b.y;
     }
     __syncthreads();
     // |P_j|: tops with cotT <= cotB_j
+    if constexpr (!kStrip)
     for (uint32_t j = tid; j < nB; j += THREADS) {
       const float c = keyB[rankB[j]];
       uint32_t lo = 0, hi = nT;
@@ -1712,6 +1744,71 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
 #endif
       if (slot < poolCap) pool[slot] = t | (j << 16);
     };
+    // packed position of sorted top t
+    auto topPos = [&](uint32_t t) -> uint32_t {
+      if constexpr (kStrip) return __ldg(&recT[sPos[t]].pos); else return sPos[t];
+    };
+    // ---- strip path: phases 3a-3c are one plain scan ---------------------------------------------
+    // The window of a bottom is the run of sorted tops with (cotB - cotT)^2 <= cotThetaDiffMax^2 (:226-238: tops
+    // below the window are dropped for good, the loop ends at the first top above it; both tests are monotone in
+    // the sorted order, so the window does not depend on the bottoms before).  One thread per bottom.
+    float cosPhiM = 0.f, sinPhiM = 0.f;
+    auto stripBottom = [&](uint32_t j, StripBottomCtx& sb) -> uint32_t {
+      const float4* src = reinterpret_cast<const float4*>(recB + rankB[j]);
+      const float4 a = __ldg(src), b = __ldg(src + 1);
+      sb.cotThetaB0 = a.y; sb.iDeltaRB = a.z; sb.erB = a.w; sb.Ub0 = b.x; sb.Vb0 = b.y; sb.xB = b.z; sb.yB = b.w;
+      strip_bottom_ctx(cfg, cosPhiM, sinPhiM, sb);
+      return __float_as_uint(a.x);
+    };
+    auto stripEval = [&](const StripBottomCtx& sb, const StripDerived& calM, const StripDerived& calB, uint32_t t, float& curv,
+                         float& im) -> bool {
+      const DoubletRecord* rt = recT + sPos[t];
+      const float4 a = __ldg(reinterpret_cast<const float4*>(rt)), b = __ldg(reinterpret_cast<const float4*>(rt) + 1);
+      StripDerived calT;
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(p.pStrip + __float_as_uint(a.x));
+        uint4* dst = reinterpret_cast<uint4*>(&calT);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = __ldg(src + q);
+      }
+      return eval_strip_pair(cfg, p.toleranceParam, mid.varZ, mid.varR, sb, calM, calB, calT, a.w, a.z, b.x, b.y, b.z, b.w, curv, im);
+    };
+    auto loadStrip = [&](uint32_t pos, StripDerived& out) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.pStrip + pos);
+      uint4* dst = reinterpret_cast<uint4*>(&out);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dst[q] = __ldg(src + q);
+    };
+    if constexpr (kStrip) {
+      cosPhiM = fdiv(mid.x, mid.r);  // :171-172
+      sinPhiM = fdiv(mid.y, mid.r);
+      StripDerived calM;
+      loadStrip(m, calM);
+      for (uint32_t j = tid; j < nB; j += THREADS) {
+        StripBottomCtx sb;
+        const uint32_t posB = stripBottom(j, sb);
+        StripDerived calB;
+        loadStrip(posB, calB);
+        uint32_t lo = 0, hi = nT;  // first top that is not below the window
+        while (lo < hi) {
+          const uint32_t md = (lo + hi) >> 1;
+          const float cT = sA[md].x;
+          if (strip_outside_window(sb.cotThetaB0, cT, p.cotThetaDiffMax2) && !(sb.cotThetaB0 < cT)) lo = md + 1; else hi = md;
+        }
+        for (uint32_t t = lo; t < nT; ++t) {
+          const float cT = sA[t].x;
+          if (strip_outside_window(sb.cotThetaB0, cT, p.cotThetaDiffMax2)) {
+            if (sb.cotThetaB0 < cT) break;
+            continue;
+          }
+          ++myTests;
+          float cu, im;
+          if (stripEval(sb, calM, calB, t, cu, im)) emit(j, t);
+        }
+        hval[j] = 0;
+      }
+      __syncthreads();
+    } else {
 #if B200SEED_SPLIT_WALKERS
     {
       // Two walkers per bottom, one lane each: the backward one goes down from |P_j| - 1 to the last failing top
@@ -1948,6 +2045,7 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
       }
     }
 #endif
+    }  // !kStrip
     for (uint32_t j = tid; j <= nB; j += THREADS) cnt[j] = 0;
     __syncthreads();
     const uint32_t poolCount = sh.poolCount;
@@ -1977,12 +2075,21 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
       const uint32_t j = to >> 16, t = to & 0xFFFFu;
       if (t < hval[j]) continue;
       // the candidate's curvature and impact (TripletSeedFinder.cpp:148-155), one thread per candidate
-      BottomCtx bc;
-      bottomCtx(j, bc);
       Cand c;
-      const float4 a = sA[t];
-      eval_pair(cfg, mid.r, mid.varZ, mid.varR, bc, a.x, a.y, a.z, a.w, sV[t], c.curv, c.impactOrWeight);
-      const float2 tzr = ldg2(p.pZR + sPos[t]);
+      if constexpr (kStrip) {
+        StripBottomCtx sb;
+        const uint32_t posB = stripBottom(j, sb);
+        StripDerived calM, calB;
+        loadStrip(m, calM);
+        loadStrip(posB, calB);
+        stripEval(sb, calM, calB, t, c.curv, c.impactOrWeight);
+      } else {
+        BottomCtx bc;
+        bottomCtx(j, bc);
+        const float4 a = sA[t];
+        eval_pair(cfg, mid.r, mid.varZ, mid.varR, bc, a.x, a.y, a.z, a.w, sV[t], c.curv, c.impactOrWeight);
+      }
+      const float2 tzr = ldg2(p.pZR + topPos(t));
       c.topR = tzr.y;
       if (cfg.useDeltaRinsteadOfTopRadius) {
         const float dr = fsub(tzr.y, mid.r), dz = fsub(tzr.x, mid.z);
@@ -2066,7 +2173,7 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
             const uint32_t j = meta & kRecGroupMask;
             const size_t o = (size_t)recBase + rank;
             const float4 br = __ldg(reinterpret_cast<const float4*>(recB + rankB[j]));
-            p.rec4[o] = make_uint4(__float_as_uint(br.x), sPos[c.tOwner & 0xFFFFu], __float_as_uint(c.impactOrWeight), meta & ~kRecKeep);
+            p.rec4[o] = make_uint4(__float_as_uint(br.x), topPos(c.tOwner & 0xFFFFu), __float_as_uint(c.impactOrWeight), meta & ~kRecKeep);
             p.recZ[o] = fsub(mid.z, fmul(mid.r, br.y));
           }
         }
@@ -2188,7 +2295,7 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
         const size_t o = (size_t)w * p.seedsPerMiddle + lane;
         p.slotB[o] = __float_as_uint(br.x);
         p.slotM[o] = m;
-        p.slotT[o] = sPos[tRank];
+        p.slotT[o] = topPos(tRank);
         p.slotQ[o] = myW;
         p.slotZ[o] = fsub(mid.z, fmul(mid.r, br.y));  // zOrigin, BroadTripletSeedFilter.cpp:119
       }

@@ -103,6 +103,9 @@ struct b200seed_handle {
   DevBuf midLo, midCount, workStart, workPos, workEG, workCounter;
   // doublet stage: slot sizes and prefix, chunk plan, arena, per-middle headers, per-class work lists
   DevBuf capB, capT, slotPrefix, capTileSums, capTilePrefix, planDev, hdr, carve, classList, arenaRec[2], arenaKey[2], spillScratch;
+  DevBuf inStrip, pStrip;  // strip triplet path: raw details of the event (12 floats per point), derived details per packed position
+  const float* pendingStrip = nullptr;  // set by b200seed_run_strips around its run_host_batch call
+  float pendingCotThetaDiffMax = 0.f;
   DevBuf maskArena, maskOff;  // count pass -> fill pass: windows + survivor masks per middle (B200SEED_MASK_WORDS_PER_SP, 0 = off)
   uint32_t maskWordsPerSp = 192;
   // Consecutive chunks alternate between two internal streams (and two arena halves): the tail of one chunk's
@@ -144,6 +147,8 @@ struct b200seed_handle {
     const uint32_t* hOffsets = nullptr;
     int nZWin = 0;
     bool vertexCuts = false;            // VertexZCuts connected (cfg.useVertexZCuts, or windows given)
+    const float* dStrip = nullptr;      // strip triplet path: raw calibration details on the device (NULL: pixel path)
+    float cotThetaDiffMax = 0.f;
     const uint32_t* dZWinOffsets = nullptr;  // per-event window ranges (NULL: all events share [0, nZWin))
     uint32_t *outB = nullptr, *outM = nullptr, *outT = nullptr;
     float *outQ = nullptr, *outZ = nullptr;
@@ -253,11 +258,14 @@ struct SeedClassShape { int threads, blocksPerSM; };
 constexpr SeedClassShape kSeedClassShape[kNumSeedClasses] = {{192, 6}, {288, 4}, {384, 3}, {576, 2}, {1024, 1}, {1024, 1}};
 
 using SeedKernel = void (*)(const SeedParams);
-template <bool kConf>
+template <bool kConf, bool kStrip>
 SeedKernel seed_kernel(int c) {
-  return c == kSpillClass ? k_seed_middles<kConf, true> : k_seed_middles<kConf, false>;
+  return c == kSpillClass ? k_seed_middles<kConf, true, kStrip> : k_seed_middles<kConf, false, kStrip>;
 }
-SeedKernel seed_kernel(bool conf, int c) { return conf ? seed_kernel<true>(c) : seed_kernel<false>(c); }
+SeedKernel seed_kernel(bool conf, int c, bool strip = false) {
+  if (strip) return conf ? seed_kernel<true, true>(c) : seed_kernel<false, true>(c);
+  return conf ? seed_kernel<true, false>(c) : seed_kernel<false, false>(c);
+}
 
 // Rounds [first, first + count) of the seedConfirmation fixed point (seeding_kernels.cuh, k_conf_replay).
 // Round r reads the seeds of slot set (r + 1) & 1 and writes set r & 1.
@@ -646,6 +654,11 @@ int enqueue(b200seed_handle* h) {
     k_sort_bins<<<nBinsAll, kSortThreads, (size_t)h->sortSmemCap * 16, s>>>(gp);
     launches += 2;
   }
+  if (a.dStrip != nullptr && nTotal > 0) {  // strip triplet path: derived calibration details in packed order
+    CUDA_TRY(h->pStrip.reserve((size_t)nTotal * sizeof(StripDerived)));
+    k_gather_strips<<<elemBlocks, 256, 0, s>>>(gp.pIdx, gp.binStart + nBinsAll, a.dStrip, h->pStrip.as<StripDerived>());
+    ++launches;
+  }
 
   CUDA_TRY(cudaEventRecord(h->ev[1], s));
   k_middle_ranges<<<nEvents, 256, 0, s>>>(wp);
@@ -777,6 +790,10 @@ int enqueue(b200seed_handle* h) {
   sp.slotCount = h->slotCount.as<uint32_t>();
   sp.seedsPerMiddle = std::max<uint32_t>(plan.seedsPerMiddle, 1);
   sp.exactTies = h->exactTies;
+  const bool strip = a.dStrip != nullptr;
+  sp.pStrip = h->pStrip.as<StripDerived>();
+  sp.cotThetaDiffMax2 = a.cotThetaDiffMax * a.cotThetaDiffMax;  // :232-233 (binary32 product, also in the relaxed engine)
+  sp.toleranceParam = plan.toleranceParam;
   sp.counters = gp.counters;
   sp.status = gp.status;
   if (conf) {
@@ -837,7 +854,7 @@ int enqueue(b200seed_handle* h) {
       sp.overflowCount = overflowTo < 0 ? nullptr : cw + 16 + overflowTo;
       sp.arrayBytes = spill ? spillBytes : h->classBytes[k];
       const int blocks = spill ? spillBlocks : h->smCount * h->classBlocksPerSM[k];
-      seed_kernel(conf, k)<<<blocks, h->classThreads[k], spill ? 0 : h->classBytes[k], st>>>(sp);
+      seed_kernel(conf, k, strip)<<<blocks, h->classThreads[k], spill ? 0 : h->classBytes[k], st>>>(sp);
     };
     const bool fan = h->classStreams != 0;
     if (fan) CUDA_TRY(cudaEventRecord(h->evFill[a], cs));
@@ -1167,6 +1184,10 @@ static int create_impl(const b200seed_config* cfg, const b200seed_orthogonal_opt
         // the largest class can never lower the limit under that launch.
         CREATE_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(((size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes) & ~(size_t)127)));
+        if (!h->plan.orthogonal) {  // the strip variant of the class (same static shared memory, same limit)
+          CREATE_TRY(cudaFuncSetAttribute(seed_kernel(conf, c, true), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(((size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes) & ~(size_t)127)));
+        }
       }
       h->classBytes[c] = bytes;
       h->classThreads[c] = kSeedClassShape[c].threads;
@@ -1228,7 +1249,7 @@ void b200seed_destroy(b200seed_handle* h) {
                     &h->binStart, &h->binCursor, &h->tmpIdx, &h->pIdx, &h->pXY, &h->pZR, &h->pVar,
                     &h->sortScratch, &h->midLo, &h->midCount, &h->workStart, &h->workPos, &h->workEG,
                     &h->workCounter, &h->capB, &h->capT, &h->slotPrefix, &h->capTileSums, &h->capTilePrefix, &h->planDev,
-                    &h->hdr, &h->carve, &h->classList, &h->maskArena, &h->maskOff, &h->arenaRec[0], &h->arenaRec[1], &h->arenaKey[0], &h->arenaKey[1], &h->spillScratch,
+                    &h->hdr, &h->carve, &h->classList, &h->maskArena, &h->maskOff, &h->inStrip, &h->pStrip, &h->arenaRec[0], &h->arenaRec[1], &h->arenaKey[0], &h->arenaKey[1], &h->spillScratch,
                     &h->zWinOffsets, &h->slotB, &h->slotM, &h->slotT, &h->slotQ, &h->slotZ, &h->slotCount,
                     &h->seedStart, &h->tileSums, &h->tilePrefix, &h->outB, &h->outM, &h->outT, &h->outQ,
                     &h->outZ, &h->seedOffsets, &h->counters, &h->status, &h->zWin, &h->rec, &h->recZ, &h->recBegin,
@@ -1527,6 +1548,8 @@ static int run_host_batch(b200seed_handle* h, uint32_t nEvents, const uint32_t* 
     a.nZWin = (int)nMerged;
     a.dZWinOffsets = dWinOffsets;
     a.vertexCuts = h->plan.useVertexZCuts || nZWin > 0 || win.offsets != nullptr;
+    a.dStrip = h->pendingStrip;
+    a.cotThetaDiffMax = h->pendingCotThetaDiffMax;
     a.outB = h->outB.as<uint32_t>(); a.outM = h->outM.as<uint32_t>(); a.outT = h->outT.as<uint32_t>();
     a.outQ = h->outQ.as<float>(); a.outZ = h->outZ.as<float>();
     a.outCapacity = maxSeeds;
@@ -1579,6 +1602,30 @@ int b200seed_run(b200seed_handle* h, uint32_t nSpacePoints, const float* x, cons
   WindowSource win;
   win.nZWin = nZWindows; win.lo = zWindowLo; win.hi = zWindowHi;
   return run_host_batch(h, 1, offsets, x, y, z, r, varZ, varR, nullptr, win, nullptr, out);
+}
+
+// One event through the strip triplet path (TripletSeedFinder::Config::useStripInfo = true,
+// TripletSeedFinder.cpp:164-406): the raw calibration details are staged on the device, the grid stage gathers the
+// derived details into packed order (k_gather_strips) and the seeding kernel runs its strip variant.
+int b200seed_run_strips(b200seed_handle* h, uint32_t nSpacePoints, const float* x, const float* y, const float* z,
+                        const float* r, const float* varZ, const float* varR, const float* stripDetails,
+                        float cotThetaDiffMax, b200seed_seeds* out) {
+  if (h == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL handle");
+  if (h->plan.orthogonal) return fail(B200SEED_ERR_UNSUPPORTED, "strip triplet path: grid handles only");
+  if (nSpacePoints > 0 && stripDetails == nullptr) return fail(B200SEED_ERR_INVALID_ARGUMENT, "NULL strip details");
+  if (cotThetaDiffMax != cotThetaDiffMax) return fail(B200SEED_ERR_INVALID_ARGUMENT, "cotThetaDiffMax is NaN");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(h->inStrip.reserve(std::max<size_t>((size_t)nSpacePoints * 48, 16)));
+  if (nSpacePoints > 0) {
+    CUDA_TRY(cudaMemcpyAsync(h->inStrip.ptr, stripDetails, (size_t)nSpacePoints * 48, cudaMemcpyHostToDevice, h->stream));
+  }
+  const uint32_t offsets[2] = {0, nSpacePoints};
+  WindowSource win;
+  h->pendingStrip = h->inStrip.as<float>();
+  h->pendingCotThetaDiffMax = cotThetaDiffMax;
+  const int rc = run_host_batch(h, 1, offsets, x, y, z, r, varZ, varR, nullptr, win, nullptr, out);
+  h->pendingStrip = nullptr;
+  return rc;
 }
 
 // GridTripletSeedingAlgorithm.cpp:187-206: one z window per vertex, [z - half, z + half] with

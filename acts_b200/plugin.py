@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "b200seed_destroy", "b200seed_last_error", "b200seed_alloc_pinned", "b200seed_free_pinned",
     "b200seed_get_info", "b200seed_get_counters",
     "b200seed_get_stage_times", "b200seed_get_stage_times_ex", "b200seed_set_phi_sector", "b200seed_estimate_params",
-    "b200seed_run_vertices", "b200seed_vertex_windows", "b200seed_run_batch_windows",
+    "b200seed_run_vertices", "b200seed_vertex_windows", "b200seed_run_batch_windows", "b200seed_run_strips",
     "b200seed_make_pixel_spacepoints", "b200seed_run_measurements",
     "b200seed_run", "b200seed_run_with_phi", "b200seed_run_batch", "b200seed_run_batch_device",
     "b200seed_sync", "b200seed_debug_grid", "b200seed_debug_doublets", "b200seed_debug_atan2f",
@@ -67,6 +67,7 @@ def lib():
         L.b200seed_get_stage_times.argtypes = [vp, vp]
         L.b200seed_get_stage_times_ex.argtypes = [vp, vp, u32]
         L.b200seed_run_vertices.argtypes = [vp, u32] + [f32p] * 6 + [u32, vp, vp, C.POINTER(Seeds)]
+        L.b200seed_run_strips.argtypes = [vp, u32] + [f32p] * 7 + [C.c_float, C.POINTER(Seeds)]
         L.b200seed_vertex_windows.argtypes = [vp, u32, vp, vp, vp, vp]
         L.b200seed_run_batch_windows.argtypes = [vp, u32, vp] + [f32p] * 6 + [vp, f32p, f32p, vp, C.POINTER(Seeds)]
         L.b200seed_set_phi_sector.argtypes = [vp, u32, u32]
@@ -241,10 +242,12 @@ class SeedingEngine:
         s.capacity = capacity
         return out, s
 
-    def run(self, ev: dict, z_windows=None, phi=None, capacity=None, out=None, vertices=None) -> dict:
+    def run(self, ev: dict, z_windows=None, phi=None, capacity=None, out=None, vertices=None,
+            strip_cot_theta_diff_max=None) -> dict:
         """One event through ``b200seed_run`` (host buffers in, host seeds out).
 
         ``vertices`` = (z, var z) goes through ``b200seed_run_vertices`` (Config::inputVertices).
+        ``strip_cot_theta_diff_max`` given: ``b200seed_run_strips`` with ``ev["strip"]`` ((n, 12) float32).
         ``out`` may hold caller-owned (e.g. pinned) seed columns that are reused from call to call."""
         cols = self._cols(ev)
         n = cols[0].size
@@ -256,7 +259,10 @@ class SeedingEngine:
             s.capacity = min(int(a.size) for a in out.values())
         else:
             out, s = self._alloc(cap)
-        if vertices is not None:
+        if strip_cot_theta_diff_max is not None:
+            strip = np.ascontiguousarray(ev["strip"], dtype=np.float32).reshape(n, 12)
+            rc = lib().b200seed_run_strips(self._h, n, *[_p(c) for c in cols], _p(strip), float(strip_cot_theta_diff_max), C.byref(s))
+        elif vertices is not None:
             vz = np.ascontiguousarray(vertices[0], dtype=np.float64)
             vv = np.ascontiguousarray(vertices[1], dtype=np.float64)
             rc = lib().b200seed_run_vertices(self._h, n, *[_p(c) for c in cols], vz.size, _p(vz), _p(vv), C.byref(s))

@@ -293,6 +293,20 @@ int b200seed_run_vertices(b200seed_handle* h, uint32_t nSpacePoints, const float
                           const double* vertexZ, const double* vertexVarZ,
                           b200seed_seeds* out);
 
+/* The strip triplet path: TripletSeedFinder::Config::useStripInfo = true
+ * (Core/src/Seeding/TripletSeedFinder.cpp:164-406, createStripTripletTopCandidates; calibration
+ * Core/include/Acts/SpacePointFormation/detail/StripSpacePointCalibrationImpl.hpp:22-85).  One event whose space
+ * points carry the StripCalibrationDetails column (SpacePointContainer.hpp:249-256): stripDetails holds 12 floats per
+ * space point = outerCenter, innerToOuterSeparation, outerHalfVector, innerHalfVector
+ * (StripSpacePointCalibrationDetails.hpp:16-29).  cotThetaDiffMax is TripletSeedFinder::Config::cotThetaDiffMax
+ * (TripletSeedFinder.hpp:171-175; INFINITY = the reference's default: no pre-filter); the tolerance of the module
+ * check is the config's toleranceParam.  Grid handles only (B200SEED_ERR_UNSUPPORTED on an orthogonal handle); the
+ * doublet stage, the seed filter and the output order are those of b200seed_run. */
+int b200seed_run_strips(b200seed_handle* h, uint32_t nSpacePoints, const float* x,
+                        const float* y, const float* z, const float* r,
+                        const float* varZ, const float* varR, const float* stripDetails,
+                        float cotThetaDiffMax, b200seed_seeds* out);
+
 /* The window construction of b200seed_run_vertices on its own (for the batch entry below). */
 int b200seed_vertex_windows(const b200seed_handle* h, uint32_t nVertices,
                             const double* vertexZ, const double* vertexVarZ,

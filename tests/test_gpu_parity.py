@@ -946,3 +946,87 @@ def test_orthogonal_refuses_the_input_the_reference_cannot_build(plugin, O, monk
     assert exc.value.code == config.ERR_INVALID_ARGUMENT
     assert eng.run(ev)["bottom"].size == O.Oracle(*config.orthogonal_config(O.orthogonal_config_init)).run(ev)["bottom"].size
     eng.close()
+
+
+# ---------------------------------------------------------------------------
+# Strip triplet path (TripletSeedFinder::Config::useStripInfo = true, TripletSeedFinder.cpp:164-406) through
+# b200seed_run_strips; the oracle's restatement is pinned to the reference's own implementation in
+# tests/test_reference_pin.py.
+# ---------------------------------------------------------------------------
+def _strip_event(kind, i, mu):
+    from acts_b200 import events
+
+    ev = dict(_event(kind, i, mu))
+    ev["strip"] = events.strip_details(ev, seed=i)
+    return ev
+
+
+@pytest.mark.parametrize("name,kind,mu,ids,over", [
+    ("seeding_py", "muon", 0, (0, 1), {}),
+    ("pu200", "pileup", 5, (0, 1), {}),
+    ("pu200", "pileup", 20, (0, 1, 2), {}),
+    ("pu200", "pileup", 60, (3,), {}),
+    ("pu200", "pileup", 20, (4, 5), dict(seedConfirmation=1)),
+    ("pu200", "pileup", 20, (6,), dict(toleranceParam=0.6, interactionPointCut=1)),
+    ("itk_like", "pileup", 20, (7,), dict(toleranceParam=3.0, useDeltaRinsteadOfTopRadius=1)),
+    ("itk_conf", "pileup", 20, (8,), {}),
+])
+def test_strip_triplet_path_matches_oracle(plugin, O, name, kind, mu, ids, over):
+    eng = plugin.SeedingEngine(make_config(name, plugin.config_init).update(**over))
+    orc = O.Oracle(make_config(name, O.config_init).update(**over))
+    total = 0
+    for i in ids:
+        ev = _strip_event(kind, i, mu)
+        for diff in (float("inf"), 0.4, 0.06, 0.0):
+            if mu >= 60 and diff == float("inf"):
+                continue  # (every bottom x top pair of every middle: minutes on the CPU side)
+            got = eng.run(ev, strip_cot_theta_diff_max=diff)
+            ref = orc.run(ev, strip_cot_theta_diff_max=diff)
+            assert O.seed_set(got) == O.seed_set(ref), f"{name} event {i} cotThetaDiffMax {diff}: seed set differs"
+            assert _same_bits(got, ref), f"{name} event {i} cotThetaDiffMax {diff}: order differs"
+            cnt = eng.counters()
+            assert cnt["nTripletTests"] == ref["counters"]["nTripletTests"]
+            assert cnt["nCandidates"] == ref["counters"]["nCandidates"]
+            total += ref["bottom"].size
+        # the pixel path on the same handle afterwards is untouched by the strip call
+        assert _same_bits(eng.run(ev), orc.run(ev))
+    assert total > 0
+    eng.close()
+
+
+def test_strip_triplet_path_edge_cases(plugin, O):
+    """Empty event, three points, parallel strips, quantised coordinates (cotTheta ties), and the argument checks
+    of the entry point.  (All-zero details give 0 / 0 = NaN positions, curvatures and weights: the reference then
+    sorts and heaps NaNs, whose order is whatever libstdc++'s comparisons happen to leave -- the oracle reproduces
+    that on the CPU (tests/test_reference_pin.py), the device is only required not to fail on it.)"""
+    from acts_b200 import events
+
+    eng = plugin.SeedingEngine(make_config("pu200", plugin.config_init))
+    orc = O.Oracle(make_config("pu200", O.config_init))
+    ev = _strip_event("pileup", 11, 10)
+    empty = {k: np.zeros(0, np.float32) for k in ("x", "y", "z", "r", "varZ", "varR")}
+    empty["strip"] = np.zeros((0, 12), np.float32)
+    three = {k: (v[:3] if k != "strip" else v[:3]) for k, v in ev.items()}
+    zero = dict(ev, strip=np.zeros_like(ev["strip"]))
+    par = dict(ev, strip=ev["strip"].copy())
+    par["strip"][:, 9:12] = par["strip"][:, 6:9]
+    q = {k: (np.round(ev[k] * 4) / 4).astype(np.float32) if k in ("x", "y", "z") else ev[k] for k in ev}
+    q["r"] = np.hypot(q["x"].astype(np.float64), q["y"].astype(np.float64)).astype(np.float32)
+    for case in (empty, three, par, q):
+        for diff in (float("inf"), 0.1):
+            got = eng.run(case, strip_cot_theta_diff_max=diff)
+            ref = orc.run(case, strip_cot_theta_diff_max=diff)
+            assert _same_bits(got, ref)
+    got = eng.run(zero, strip_cot_theta_diff_max=0.1)
+    assert got["bottom"].size == orc.run(zero, strip_cot_theta_diff_max=0.1)["bottom"].size
+    with pytest.raises(plugin.SeedingError) as ei:
+        eng.run(ev, strip_cot_theta_diff_max=float("nan"))
+    assert ei.value.code != 0
+    eng.close()
+    from acts_b200 import config
+
+    ocfg, oopt = config.orthogonal_config(plugin.orthogonal_config_init)
+    oeng = plugin.SeedingEngine(ocfg, orthogonal=oopt)
+    with pytest.raises(plugin.SeedingError):
+        oeng.run(ev, strip_cot_theta_diff_max=1.0)
+    oeng.close()

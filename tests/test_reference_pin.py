@@ -251,3 +251,71 @@ def test_orthogonal_empty_and_tiny_inputs(O, R):
     for n in (0, 1, 3, 4, 5, 9, 130):
         sub = {k: v[:n] for k, v in ev.items()}
         assert _same_bits(orc.run(sub), ref.run(sub)), n
+
+
+# ---------------------------------------------------------------------------
+# Strip triplet path (TripletSeedFinder.cpp:164-406).  execute() hard-wires useStripInfo = false (.cpp:315), so the
+# reference side is ref_run_strips: the reference's own Core objects driven in execute()'s sequence (oracle/ref_driver.cpp).
+# ---------------------------------------------------------------------------
+def _strip_event(events, kind, i, mu):
+    ev = events.muon_gun_event(i) if kind == "muon" else events.pileup_event(i, mu=mu)
+    ev = dict(ev)
+    ev["strip"] = events.strip_details(ev, seed=i)
+    return ev
+
+
+def test_strip_driver_glue_equals_execute(O, R):
+    """ref_run_strips with useStripInfo = 0 takes the pixel path through the same glue: same seeds as execute()."""
+    from acts_b200 import events
+
+    for name, kind, mu, i in (("pu200", "pileup", 20, 0), ("seeding_py", "muon", 0, 1), ("pu200", "pileup", 60, 2)):
+        ref = R.Reference(make_config(name, O.config_init))
+        ev = _strip_event(events, kind, i, mu)
+        a, b = ref.run(ev), ref.run_strips(ev, use_strip_info=False)
+        assert a["bottom"].size > 0
+        assert _same_bits(a, b), f"{name} event {i}"
+
+
+@pytest.mark.parametrize("name,kind,mu,ids,over", [
+    ("seeding_py", "muon", 0, (0, 1), {}),
+    ("pu200", "pileup", 5, (0, 1), {}),
+    ("pu200", "pileup", 20, (0, 1, 2), {}),
+    ("pu200", "pileup", 40, (3,), {}),
+    ("pu200", "pileup", 20, (4, 5), dict(seedConfirmation=1)),
+    ("pu200", "pileup", 20, (6,), dict(toleranceParam=0.6, interactionPointCut=1)),
+    ("pu200", "pileup", 20, (7,), dict(toleranceParam=3.0, useDeltaRinsteadOfTopRadius=1)),
+])
+def test_strip_oracle_matches_reference(O, R, name, kind, mu, ids, over):
+    from acts_b200 import events
+
+    orc = O.Oracle(make_config(name, O.config_init).update(**over))
+    ref = R.Reference(make_config(name, O.config_init).update(**over))
+    total = 0
+    for i in ids:
+        ev = _strip_event(events, kind, i, mu)
+        for diff in (float("inf"), 0.4, 0.06, 0.0):
+            a, b = orc.run(ev, strip_cot_theta_diff_max=diff), ref.run_strips(ev, diff)
+            assert _same_bits(a, b), f"{name} event {i} cotThetaDiffMax {diff}"
+            total += b["bottom"].size
+        # and the strip result is not the pixel result (the calibration moves the points)
+        assert not _same_bits(orc.run(ev, strip_cot_theta_diff_max=float("inf")), orc.run(ev)) or ev["x"].size < 50
+    assert total > 0
+
+
+def test_strip_degenerate_details_match_reference(O, R):
+    """All-zero details (scale = 0: 0 / 0 in the calibration), parallel strips, huge tolerance, and coordinates
+    quantised so that cotTheta values tie."""
+    from acts_b200 import events
+
+    orc = O.Oracle(make_config("pu200", O.config_init))
+    ref = R.Reference(make_config("pu200", O.config_init))
+    ev = _strip_event(events, "pileup", 11, 10)
+    zero = dict(ev, strip=np.zeros_like(ev["strip"]))
+    par = dict(ev, strip=ev["strip"].copy())
+    par["strip"][:, 9:12] = par["strip"][:, 6:9]  # inner strip parallel to the outer one
+    q = {k: (np.round(ev[k] * 4) / 4).astype(np.float32) if k in ("x", "y", "z") else ev[k] for k in ev}
+    q["r"] = np.hypot(q["x"].astype(np.float64), q["y"].astype(np.float64)).astype(np.float32)
+    for case in (zero, par, q):
+        for diff in (float("inf"), 0.1):
+            a, b = orc.run(case, strip_cot_theta_diff_max=diff), ref.run_strips(case, diff)
+            assert _same_bits(a, b)
