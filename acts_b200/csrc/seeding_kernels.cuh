@@ -1006,7 +1006,11 @@ __device__ __forceinline__ uint32_t doublet_side(const DoubletParams& p, const M
   return nOut;
 }
 
-// (a register cap for the fill pass -- __launch_bounds__(256, 3 / 4 / 5) -- was measured: 19 - 20 ms instead of 14.4 ms)
+// Measured and not kept for the fill pass (16-event batch, 9.6 ms as it stands; profiles/README.md, session 4):
+//   register caps -- __launch_bounds__(256, 3 / 4 / 5): 13.3 / 11.9 / 13.1 ms; an explicit (256, 1) lets ptxas take 173 registers
+//   a ring queue instead of moving the left-over entries to the front + the mask words of 32 steps loaded by one
+//   coalesced request and broadcast by shuffles: 10.1 ms (108 registers), 10.7 / 11.4 ms capped to 80 / 96
+//   two queued candidates per lane and drain step (both gathers in flight before the first use): 15.1 ms (173 registers)
 template <bool kFill>
 __global__ void __launch_bounds__(kDoubletWarps * 32) k_doublets(const __grid_constant__ DoubletParams p) {
   __shared__ WarpWindows sWin[kDoubletWarps];

@@ -221,6 +221,21 @@ class GridTripletSeedingAlgorithm final {
     });
   }
 
+  /// The strip triplet path (Acts::TripletSeedFinder::Config::useStripInfo = true, TripletSeedFinder.cpp:164-406; the
+  /// reference algorithm hard-wires false, .cpp:315 -- this is the entry for callers that build their own finder).
+  /// `stripDetails`: 12 floats per space point = outerCenter, innerToOuterSeparation, outerHalfVector, innerHalfVector
+  /// (Acts::OuterStripSpacePointCalibrationDetails); `cotThetaDiffMax`: TripletSeedFinder::Config::cotThetaDiffMax.
+  SeedColumns executeStrips(const SpacePointColumns& sp, std::span<const float> stripDetails,
+                            float cotThetaDiffMax = std::numeric_limits<float>::infinity()) const {
+    checkColumns(sp);
+    if (stripDetails.size() != 12 * sp.x.size()) throw std::invalid_argument("stripDetails: 12 floats per space point");
+    Lease lease(*m_pool, *this);
+    return run(*lease.slot, sp, [&](Slot& slot, b200seed_seeds* s) {
+      return b200seed_run_strips(slot.handle, static_cast<std::uint32_t>(sp.x.size()), sp.x.data(), sp.y.data(), sp.z.data(),
+                                 sp.r.data(), sp.varianceZ.data(), sp.varianceR.data(), stripDetails.data(), cotThetaDiffMax, s);
+    });
+  }
+
   const Config& config() const { return m_cfg; }
   /// engine slots created so far (<= Config::maxConcurrentEvents)
   std::size_t slotsInUse() const { std::lock_guard<std::mutex> g(m_pool->mutex); return m_pool->slots.size(); }

@@ -593,6 +593,43 @@ def run_gpu(args):
                               "(wall clock; the k-d trees are built on the device); same <mu>=200 events and cut set"}
         oeng.close()
 
+    # ---- the strip triplet path (TripletSeedFinder useStripInfo = true), reported separately ---------------------
+    strips = None
+    if args.strips:
+        from oracle import ref as R
+
+        cot_diff = 0.05  # cotThetaDiffMax: the pre-filter of TripletSeedFinder.cpp:226-238 (inf = every bottom x top pair)
+        seng = plugin.SeedingEngine(config.pu200_config(plugin.config_init), device=local)
+        sev = dict(evs[0])
+        sev["strip"] = events.strip_details(sev, seed=0)
+        seng.run(sev, strip_cot_theta_diff_max=cot_diff)  # warm-up
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            sres = seng.run(sev, strip_cot_theta_diff_max=cot_diff)
+        s_s = (time.perf_counter() - t0) / reps
+        sst = seng.stage_times_ms()
+        scnt = seng.counters()
+        strip_ref = None
+        if R.available() or R.build() is not None:
+            from oracle import oracle as O3
+
+            rr = R.Reference(config.pu200_config(O3.config_init))
+            t0 = time.perf_counter()
+            rb = rr.run_strips(sev, cot_diff)
+            ref_s = time.perf_counter() - t0
+            same = all(np.array_equal(sres[k].view(np.uint32), rb[k].view(np.uint32)) for k in ("bottom", "middle", "top", "quality", "vertexZ"))
+            strip_ref = {"seconds_per_event_one_core": ref_s, "identical_seeds_and_order": bool(same),
+                         "kind": "unmodified reference Core sources driven by oracle/ref_driver.cpp:ref_run_strips, one event, one host core"}
+            if not same:
+                sys.stderr.write("bench.py: PARITY FAILURE of the strip triplet path against the reference\n")
+        strips = {"value": 1.0 / s_s, "unit": UNIT, "n_gpus": 1, "ms_per_event": s_s * 1e3, "cotThetaDiffMax": cot_diff,
+                  "seed_middles_ms": sst.get("seed_middles"), "triplet_tests": int(scnt["nTripletTests"]),
+                  "seeds": int(sres["bottom"].size), "reference": strip_ref,
+                  "note": "b200seed_run_strips, one <mu>=200 event with synthetic double-sided strip module details "
+                          "(acts_b200/events.py:strip_details), host buffers in / seeds out (wall clock)"}
+        seng.close()
+
     # ---- roofline ------------------------------------------------------------------------------------------
     peak_gbs, peak_src, sm_max = load_peaks()
     b0 = batches[(args.warmup + min(args.steps, 8) - 1) % n_batches]
@@ -676,6 +713,7 @@ def run_gpu(args):
         "relaxed_float": relaxed,
         "latency": latency,
         "orthogonal": orthogonal,
+        "strips": strips,
         "cpu_baseline": cpu,
         "counters_last_step": cnt,
         "seeds_last_step": int(n_seeds_last),
@@ -708,6 +746,7 @@ def main():
     ap.add_argument("--no-relaxed", dest="relaxed", action="store_false", help="skip the relaxedFloat fast-path report")
     ap.add_argument("--no-oracle-counters", dest="oracle_counters", action="store_false")
     ap.add_argument("--no-orthogonal", dest="orthogonal", action="store_false", help="skip the OrthogonalTripletSeedingAlgorithm report")
+    ap.add_argument("--no-strips", dest="strips", action="store_false", help="skip the strip triplet path report")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -123,6 +123,21 @@ int main(int argc, char** argv) {
     std::printf("seeds %zu\n", seeds.size());
     return 0;
   }
+  if (argc >= 5 && std::strcmp(argv[1], "strips") == 0) {  // strips <event> <out> <cotThetaDiffMax>: the event file carries 12 more floats per point
+    std::ifstream in(argv[2], std::ios::binary);
+    std::uint32_t n = 0;
+    in.read(reinterpret_cast<char*>(&n), 4);
+    Columns col(6, std::vector<float>(n));
+    for (auto& v : col) in.read(reinterpret_cast<char*>(v.data()), 4ull * n);
+    std::vector<float> details(12ull * n);
+    in.read(reinterpret_cast<char*>(details.data()), 48ull * n);
+    const Alg alg(pu200());
+    const auto seeds = alg.executeStrips({col[0], col[1], col[2], col[3], col[4], col[5]}, details, static_cast<float>(std::atof(argv[4])));
+    std::ofstream out(argv[3], std::ios::binary);
+    writeSeeds(out, seeds);
+    std::printf("seeds %zu\n", seeds.size());
+    return 0;
+  }
   if (argc >= 2 && std::strcmp(argv[1], "errors") == 0) {
     auto a = pu200(); a.minPt = 0.010f;                       // std::domain_error (phi binning)
     auto b = pu200(); b.phiMin = -4.f;                        // std::runtime_error (grid range)

@@ -106,6 +106,27 @@ def test_cpp_execute_with_vertices(built, tmp_path):
 
 
 @pytest.mark.gpu
+def test_cpp_execute_strips(built, tmp_path):
+    """The strip triplet path through the mirror class (executeStrips -> b200seed_run_strips)."""
+    from acts_b200 import config, events
+    from oracle import oracle as O
+
+    ev = dict(events.pileup_event(33, mu=20))
+    ev["strip"] = events.strip_details(ev, seed=33)
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    _write_event(fin, ev)
+    with open(fin, "ab") as f:
+        f.write(np.ascontiguousarray(ev["strip"], dtype=np.float32).tobytes())
+    res = subprocess.run([BIN, "strips", str(fin), str(fout), "0.3"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    got = _read_seed_blocks(fout, 1)[0]
+    ref = O.Oracle(config.pu200_config(O.config_init)).run(ev, strip_cot_theta_diff_max=0.3)
+    assert ref["quality"].size > 0
+    for k in ("bottom", "middle", "top", "quality", "vertexZ"):
+        assert np.array_equal(got[k], ref[k].view(np.uint32)), k
+
+
+@pytest.mark.gpu
 def test_cpp_orthogonal_mirror(built, tmp_path):
     """ActsB200::OrthogonalTripletSeedingAlgorithm (acts_b200/host/OrthogonalTripletSeedingAlgorithm.hpp): one object,
     four threads, results identical across threads and equal to the oracle (which is pinned to the reference)."""
