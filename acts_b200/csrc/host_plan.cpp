@@ -339,16 +339,24 @@ void build(const b200seed_config& c, HostPlan& plan, const b200seed_orthogonal_o
   }
   d.compatSeedLimit = static_cast<uint32_t>(c.compatSeedLimit);
   d.maxSeedsPerSpM = c.maxSeedsPerSpM;
-  if (c.maxSeedsPerSpMConf > static_cast<uint32_t>(kMaxHeap)) {
-    throw Fail{B200SEED_ERR_UNSUPPORTED, "maxSeedsPerSpMConf > " + std::to_string(kMaxHeap)};
+  if (c.maxSeedsPerSpMConf > static_cast<uint32_t>(kMaxHeapBig)) {
+    throw Fail{B200SEED_ERR_UNSUPPORTED, "maxSeedsPerSpMConf > " + std::to_string(kMaxHeapBig)};
+  }
+  // a middle returns at most min(collector capacity, maxSeedsPerSpM + 1) seeds (BroadTripletSeedFilter.cpp:336-348)
+  if (std::min<uint64_t>(c.maxSeedsPerSpMConf, static_cast<uint64_t>(c.maxSeedsPerSpM) + 1) > static_cast<uint64_t>(kMaxHeap)) {
+    throw Fail{B200SEED_ERR_UNSUPPORTED, "min(maxSeedsPerSpMConf, maxSeedsPerSpM + 1) > " + std::to_string(kMaxHeap)};
   }
   d.maxSeedsPerSpMConf = c.maxSeedsPerSpMConf;
   d.useDeltaRinsteadOfTopRadius = c.useDeltaRinsteadOfTopRadius ? 1 : 0;
   // seed confirmation, GridTripletSeedingAlgorithm.cpp:163-171
   d.seedConfirmation = c.seedConfirmation ? 1 : 0;
   d.zOriginWeightFactor = c.zOriginWeightFactor;
-  if (c.seedConfirmation && c.maxQualitySeedsPerSpMConf > static_cast<uint32_t>(kMaxHeap)) {
-    throw Fail{B200SEED_ERR_UNSUPPORTED, "maxQualitySeedsPerSpMConf > " + std::to_string(kMaxHeap)};
+  if (c.seedConfirmation && c.maxQualitySeedsPerSpMConf > static_cast<uint32_t>(kMaxHeapBig)) {
+    throw Fail{B200SEED_ERR_UNSUPPORTED, "maxQualitySeedsPerSpMConf > " + std::to_string(kMaxHeapBig)};
+  }
+  if (c.seedConfirmation && std::min<uint64_t>(static_cast<uint64_t>(c.maxSeedsPerSpMConf) + c.maxQualitySeedsPerSpMConf,
+                                               static_cast<uint64_t>(c.maxSeedsPerSpM) + 1) > 2u * static_cast<uint64_t>(kMaxHeap)) {
+    throw Fail{B200SEED_ERR_UNSUPPORTED, "seedConfirmation: more than " + std::to_string(2 * kMaxHeap) + " seeds per middle"};
   }
   d.maxQualitySeedsPerSpMConf = c.maxQualitySeedsPerSpMConf;
   {

@@ -216,7 +216,8 @@ B2S_HD float glibc_atan2f(float y, float x) {
 constexpr int kMaxZEdges = 64;        // z bins + 1 supported on the device
 constexpr int kMaxNeighborBins = 64;  // non-empty-able neighbour bins per side per middle bin
 constexpr int kMaxCompatSeedLimit = 8;
-constexpr int kMaxHeap = 16;          // maxSeedsPerSpMConf supported
+constexpr int kMaxHeap = 16;          // seeds a middle can return: min(maxSeedsPerSpMConf, maxSeedsPerSpM + 1) (one lane each)
+constexpr int kMaxHeapBig = 128;      // collector capacities supported (maxSeedsPerSpMConf, maxQualitySeedsPerSpMConf; itk.py:504-505 uses 100)
 
 enum DoubletCutKind : int { kCutsNone = 0, kCutsItk = 1, kCutsVertexZ = 2 };
 

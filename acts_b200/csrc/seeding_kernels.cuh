@@ -1353,6 +1353,9 @@ struct SeedParams {
   const StripDerived* pStrip;
   float cotThetaDiffMax2;
   float toleranceParam;
+  // maxSeedsPerSpMConf > kMaxHeap: the literal heap replay keeps its arrays (16 bytes per entry) in the dynamic shared
+  // memory behind the per-middle arrays (at arrayBytes; spill class: at 0) instead of SeedShared
+  uint32_t bigHeap;
 };
 
 // meta word of a candidate record
@@ -2208,7 +2211,18 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
     // result depends on the heap's history -- the literal heap replay runs.
     if (tid < 32) {
       const int nLow = (int)cfg.maxSeedsPerSpMConf;
-      const int keep = nLow + 1;  // <= kMaxHeap + 1 <= 32 lanes
+      // Only the first min(nLow, maxSeedsPerSpM + 1) = K entries of the sorted collector are used (:336-348).  They
+      // are the K largest weights in descending order whenever the K + 1 largest differ: an entry with fewer than
+      // K <= nLow others at or above its weight is never refused and never the evicted minimum.
+      const int nUse = cfg.maxSeedsPerSpM < (uint32_t)nLow ? (int)cfg.maxSeedsPerSpM + 1 : nLow;
+      const int keep = nUse + 1;  // <= kMaxHeap + 1 <= 32 lanes (host_plan.cpp)
+      WeightIndex* heapArr = sh.heap;
+      StoredSeed* storArr = sh.storage;
+      if (p.bigHeap != 0u) {
+        unsigned char* tail = smemRaw + (kSpill ? 0u : p.arrayBytes);
+        heapArr = reinterpret_cast<WeightIndex*>(tail);
+        storArr = reinterpret_cast<StoredSeed*>(tail + 8u * (uint32_t)nLow);
+      }
       float myW = -3.402823466e+38f;
       uint32_t myId = 0xFFFFFFFFu;
       int filled = 0;
@@ -2235,7 +2249,7 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
           if (filled < keep) ++filled;
         }
       }
-      // ties among the nLow + 1 largest -> the order / membership depends on the heap history
+      // ties among the K + 1 largest -> the order / membership depends on the heap history
       const float nextW = __shfl_down_sync(0xffffffffu, myW, 1);
       const bool tieHere = (int)lane + 1 < filled && myW == nextW;
       const bool anyTie = __any_sync(0xffffffffu, tieHere);
@@ -2262,30 +2276,30 @@ __global__ void __maxnreg__(B200SEED_SEED_REGS) k_seed_middles(const __grid_cons
               sd.weight = wq;
               if (sh.heapSize < nLow) {
                 const int slotI = sh.heapSize;
-                sh.storage[slotI] = sd;
-                sh.heap[slotI].weight = wq;
-                sh.heap[slotI].index = (uint32_t)slotI;
+                storArr[slotI] = sd;
+                heapArr[slotI].weight = wq;
+                heapArr[slotI].index = (uint32_t)slotI;
                 sh.heapSize = slotI + 1;
-                std_push_heap(sh.heap, sh.heapSize, heap_comp);
+                std_push_heap(heapArr, sh.heapSize, heap_comp);
               } else {
-                const WeightIndex smallest = sh.heap[0];
+                const WeightIndex smallest = heapArr[0];
                 if (wq <= smallest.weight) continue;
-                sh.storage[smallest.index] = sd;
-                std_pop_heap(sh.heap, sh.heapSize, heap_comp);
-                sh.heap[sh.heapSize - 1].weight = wq;
-                sh.heap[sh.heapSize - 1].index = smallest.index;
-                std_push_heap(sh.heap, sh.heapSize, heap_comp);
+                storArr[smallest.index] = sd;
+                std_pop_heap(heapArr, sh.heapSize, heap_comp);
+                heapArr[sh.heapSize - 1].weight = wq;
+                heapArr[sh.heapSize - 1].index = smallest.index;
+                std_push_heap(heapArr, sh.heapSize, heap_comp);
               }
-              sh.heapMin = sh.heap[0].weight;
+              sh.heapMin = heapArr[0].weight;
             }
           }
           __syncwarp();
         }
-        if (lane == 0) std_sort_heap(sh.heap, sh.heapSize, heap_comp);
+        if (lane == 0) std_sort_heap(heapArr, sh.heapSize, heap_comp);
         __syncwarp();
         inHeap = sh.heapSize;
         if ((int)lane < inHeap) {
-          const StoredSeed sd = sh.storage[sh.heap[lane].index];
+          const StoredSeed sd = storArr[heapArr[lane].index];
           myW = sd.weight;
           myId = sd.tOwner;
         }
@@ -2486,10 +2500,12 @@ __device__ __forceinline__ void conf_push(WeightIndex* heap, int& size, int nMax
 
 constexpr int kConfWarps = 4;
 
+// kCap: capacity of either collector heap (kMaxHeap for the usual 5 / 5, kMaxHeapBig for itk.py's strip block 100 / 100)
+template <int kCap>
 __global__ void __launch_bounds__(kConfWarps * 32) k_conf_replay(const __grid_constant__ ConfParams p) {
   if (conf_converged(p)) return;
-  __shared__ WeightIndex heapHigh[kConfWarps][kMaxHeap], heapLow[kConfWarps][kMaxHeap];
-  __shared__ ConfSeed storageAll[kConfWarps][2 * kMaxHeap];
+  __shared__ WeightIndex heapHigh[kConfWarps][kCap], heapLow[kConfWarps][kCap];
+  __shared__ ConfSeed storageAll[kConfWarps][2 * kCap];
   const DeviceConfig& cfg = p.cfg;
   const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   WeightIndex* hHigh = heapHigh[wib];

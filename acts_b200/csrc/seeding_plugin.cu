@@ -103,6 +103,7 @@ struct b200seed_handle {
   DevBuf midLo, midCount, workStart, workPos, workEG, workCounter;
   // doublet stage: slot sizes and prefix, chunk plan, arena, per-middle headers, per-class work lists
   DevBuf capB, capT, slotPrefix, capTileSums, capTilePrefix, planDev, hdr, carve, classList, arenaRec[2], arenaKey[2], spillScratch;
+  uint32_t heapBytes = 0;  // maxSeedsPerSpMConf > kMaxHeap: dynamic shared memory behind the per-middle arrays for the literal heap replay
   DevBuf inStrip, pStrip;  // strip triplet path: raw details of the event (12 floats per point), derived details per packed position
   const float* pendingStrip = nullptr;  // set by b200seed_run_strips around its run_host_batch call
   float pendingCotThetaDiffMax = 0.f;
@@ -296,7 +297,11 @@ int enqueue_conf_rounds(b200seed_handle* h, int first, int count, cudaStream_t s
       k_conf_link<<<linkBlocks, 256, 0, s>>>(cp);
       ++h->launches;
     }
-    k_conf_replay<<<replayBlocks, kConfWarps * 32, 0, s>>>(cp);
+    if (std::max(h->plan.dev.maxSeedsPerSpMConf, h->plan.dev.maxQualitySeedsPerSpMConf) > (uint32_t)kMaxHeap) {
+      k_conf_replay<kMaxHeapBig><<<replayBlocks, kConfWarps * 32, 0, s>>>(cp);
+    } else {
+      k_conf_replay<kMaxHeap><<<replayBlocks, kConfWarps * 32, 0, s>>>(cp);
+    }
     ++h->launches;
   }
   h->confRoundsLaunched = first + count;
@@ -794,6 +799,7 @@ int enqueue(b200seed_handle* h) {
   sp.pStrip = h->pStrip.as<StripDerived>();
   sp.cotThetaDiffMax2 = a.cotThetaDiffMax * a.cotThetaDiffMax;  // :232-233 (binary32 product, also in the relaxed engine)
   sp.toleranceParam = plan.toleranceParam;
+  sp.bigHeap = h->heapBytes != 0u ? 1u : 0u;
   sp.counters = gp.counters;
   sp.status = gp.status;
   if (conf) {
@@ -854,7 +860,7 @@ int enqueue(b200seed_handle* h) {
       sp.overflowCount = overflowTo < 0 ? nullptr : cw + 16 + overflowTo;
       sp.arrayBytes = spill ? spillBytes : h->classBytes[k];
       const int blocks = spill ? spillBlocks : h->smCount * h->classBlocksPerSM[k];
-      seed_kernel(conf, k, strip)<<<blocks, h->classThreads[k], spill ? 0 : h->classBytes[k], st>>>(sp);
+      seed_kernel(conf, k, strip)<<<blocks, h->classThreads[k], (spill ? 0 : h->classBytes[k]) + h->heapBytes, st>>>(sp);
     };
     const bool fan = h->classStreams != 0;
     if (fan) CUDA_TRY(cudaEventRecord(h->evFill[a], cs));
@@ -1169,6 +1175,8 @@ static int create_impl(const b200seed_config* cfg, const b200seed_orthogonal_opt
     // reserved by the system, the kernel's static shared memory comes on top)
     const bool conf = h->plan.dev.seedConfirmation != 0;
     if (conf) CREATE_TRY(cudaMallocHost(&h->hConfState, kConfStateWords * 4));
+    // (with seedConfirmation the collector lives in k_conf_replay, not in the seeding kernel)
+    h->heapBytes = (!conf && h->plan.dev.maxSeedsPerSpMConf > (uint32_t)kMaxHeap) ? ((16u * h->plan.dev.maxSeedsPerSpMConf + 127u) & ~127u) : 0u;
     for (int c = 0; c < kNumSeedClasses; ++c) {
       SeedKernel k = seed_kernel(conf, c);
       cudaFuncAttributes fa{};
@@ -1178,7 +1186,7 @@ static int create_impl(const b200seed_config* cfg, const b200seed_orthogonal_opt
         const size_t perBlock = (size_t)prop.sharedMemPerMultiprocessor / (size_t)kSeedClassShape[c].blocksPerSM;
         size_t dyn = perBlock - 1024 - fa.sharedSizeBytes;
         dyn = std::min<size_t>(dyn, (size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes);
-        bytes = (uint32_t)(dyn & ~(size_t)127);
+        bytes = (uint32_t)(dyn & ~(size_t)127) - h->heapBytes;
         // The classes share one kernel function and the attribute is per function and process-wide: every
         // handle sets the SAME value (the opt-in maximum), so a handle created while another thread launches
         // the largest class can never lower the limit under that launch.
@@ -1202,7 +1210,7 @@ static int create_impl(const b200seed_config* cfg, const b200seed_orthogonal_opt
         if ((int)t.size() == kNumSeedClasses && t[c] >= 32 && t[c] <= 1024 && t[c] % 32 == 0) h->classThreads[c] = t[c];
       }
       int b = 0;
-      CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k, h->classThreads[c], bytes));
+      CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k, h->classThreads[c], bytes + h->heapBytes));
       h->classBlocksPerSM[c] = std::max(1, b);
     }
     int b = 0;

@@ -17,7 +17,7 @@ def random_config(rng, init):
     o["deltaRMinBottom"], o["deltaRMaxBottom"] = float(rng.choice([1.0, 5.0, 10.0])), float(rng.choice([80.0, 150.0, 300.0]))
     o["collisionRegionMin"], o["collisionRegionMax"] = float(rng.choice([-250.0, -150.0, -50.0])), float(rng.choice([60.0, 150.0, 250.0]))
     o["maxSeedsPerSpM"] = int(rng.choice([0, 1, 2, 5]))
-    o["maxSeedsPerSpMConf"] = int(rng.choice([1, 3, 5, 16]))
+    o["maxSeedsPerSpMConf"] = int(rng.choice([1, 3, 5, 16, 40, 100]))
     o["compatSeedLimit"] = int(rng.choice([0, 1, 2, 3, 8]))
     o["compatSeedWeight"] = float(rng.choice([100.0, 200.0]))
     o["impactWeightFactor"] = float(rng.choice([1.0, 100.0]))
@@ -50,7 +50,7 @@ def random_config(rng, init):
         o["deltaRMiddleMinSPRange"], o["deltaRMiddleMaxSPRange"] = 10.0, float(rng.choice([10.0, 40.0]))
     if rng.integers(0, 2):
         conf = cm.confirmation_overrides()
-        conf["maxQualitySeedsPerSpMConf"] = int(rng.choice([0, 1, 5]))
+        conf["maxQualitySeedsPerSpMConf"] = int(rng.choice([0, 1, 5, 100]))
         conf["zOriginWeightFactor"] = float(rng.choice([0.0, 1.0]))
         conf["centralSeedConfirmationRange"]["nTopForSmallR"] = int(rng.choice([1, 2, 3]))
         conf["forwardSeedConfirmationRange"]["rMaxSeedConf"] = float(rng.choice([80.0, 140.0]))

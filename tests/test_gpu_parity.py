@@ -1030,3 +1030,39 @@ def test_strip_triplet_path_edge_cases(plugin, O):
     with pytest.raises(plugin.SeedingError):
         oeng.run(ev, strip_cot_theta_diff_max=1.0)
     oeng.close()
+
+
+ITK_STRIP_FILTER = dict(impactWeightFactor=1.0, compatSeedLimit=4, numSeedIncrement=1.0, seedWeightIncrement=10100.0,
+                        maxSeedsPerSpMConf=100, maxQualitySeedsPerSpMConf=100, maxSeedsPerSpM=4)
+
+
+@pytest.mark.parametrize("conf", [False, True])
+def test_itk_strip_filter_block_collectors_of_100(plugin, O, conf):
+    """The filter block of the ITk STRIP configuration (Python/Examples/python/itk.py:499-506: collector capacities
+    100 / 100 with maxSeedsPerSpM = 4), with and without seedConfirmation, on smeared and on lattice-quantised
+    events (equal weights inside the collector: the literal heap replay runs with 100-entry heaps), through the
+    pixel and the strip triplet path."""
+    from acts_b200 import config as cm
+    from acts_b200 import events
+
+    extra = dict(cm.confirmation_overrides(), **ITK_STRIP_FILTER) if conf else dict(ITK_STRIP_FILTER)
+    eng = plugin.SeedingEngine(make_config("pu200", plugin.config_init).update(**extra))
+    orc = O.Oracle(make_config("pu200", O.config_init).update(**extra))
+    ties = 0
+    for i, mu, step in ((0, 30, 0.0), (1, 60, 0.0), (2, 30, 0.5), (3, 60, 2.0)):
+        ev = dict(events.pileup_event(i, mu=mu))
+        if step > 0:
+            for k in ("x", "y", "z"):
+                ev[k] = (np.round(ev[k] / np.float32(step)) * np.float32(step)).astype(np.float32)
+            ev["r"] = np.sqrt(ev["x"].astype(np.float64) ** 2 + ev["y"].astype(np.float64) ** 2).astype(np.float32)
+            ev["varZ"] = np.full_like(ev["varZ"], 0.01)
+            ev["varR"] = np.full_like(ev["varR"], 0.01)
+        got, ref = eng.run(ev), orc.run(ev)
+        assert ref["quality"].size > 100
+        ties += ref["counters"]["nWeightTieMiddles"]
+        assert _same_bits(got, ref), (conf, i, "pixel path")
+        ev["strip"] = events.strip_details(ev, seed=i)
+        got, ref = eng.run(ev, strip_cot_theta_diff_max=0.2), orc.run(ev, strip_cot_theta_diff_max=0.2)
+        assert _same_bits(got, ref), (conf, i, "strip path")
+    assert ties > 0
+    eng.close()

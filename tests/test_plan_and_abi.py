@@ -100,7 +100,11 @@ def test_config_errors_map_to_reference_exceptions(plugin, O):
 def test_unsupported_configs_are_rejected_loudly(plugin):
     from acts_b200 import config as cm
 
-    for override in (dict(seedConfirmation=1, maxQualitySeedsPerSpMConf=17), dict(compatSeedLimit=9), dict(maxSeedsPerSpMConf=17)):
+    # collector capacities up to 128 are fine (itk.py:504-505 uses 100); a middle can return at most 16 seeds
+    for ok in (dict(maxSeedsPerSpMConf=100), dict(seedConfirmation=1, maxSeedsPerSpMConf=100, maxQualitySeedsPerSpMConf=100)):
+        plugin.plan_info(make_config("pu200", plugin.config_init).update(**ok))
+    for override in (dict(seedConfirmation=1, maxQualitySeedsPerSpMConf=129), dict(compatSeedLimit=9), dict(maxSeedsPerSpMConf=129),
+                     dict(maxSeedsPerSpMConf=17, maxSeedsPerSpM=16)):
         with pytest.raises(plugin.SeedingError) as ei:
             plugin.plan_info(make_config("pu200", plugin.config_init).update(**override))
         assert ei.value.code == cm.ERR_UNSUPPORTED

@@ -319,3 +319,25 @@ def test_strip_degenerate_details_match_reference(O, R):
         for diff in (float("inf"), 0.1):
             a, b = orc.run(case, strip_cot_theta_diff_max=diff), ref.run_strips(case, diff)
             assert _same_bits(a, b)
+
+
+@pytest.mark.parametrize("conf", [False, True])
+def test_itk_strip_filter_block_matches_reference(O, R, conf):
+    """Collector capacities 100 / 100 (itk.py:499-506) with and without seedConfirmation, smeared and quantised events."""
+    from acts_b200 import config as cm
+    from acts_b200 import events
+
+    block = dict(impactWeightFactor=1.0, compatSeedLimit=4, numSeedIncrement=1.0, seedWeightIncrement=10100.0,
+                 maxSeedsPerSpMConf=100, maxQualitySeedsPerSpMConf=100, maxSeedsPerSpM=4)
+    extra = dict(cm.confirmation_overrides(), **block) if conf else block
+    orc = O.Oracle(make_config("pu200", O.config_init).update(**extra))
+    ref = R.Reference(make_config("pu200", O.config_init).update(**extra))
+    for i, mu, step in ((0, 30, 0.0), (2, 30, 0.5)):
+        ev = dict(events.pileup_event(i, mu=mu))
+        if step > 0:
+            for k in ("x", "y", "z"):
+                ev[k] = (np.round(ev[k] / np.float32(step)) * np.float32(step)).astype(np.float32)
+            ev["r"] = np.sqrt(ev["x"].astype(np.float64) ** 2 + ev["y"].astype(np.float64) ** 2).astype(np.float32)
+        a, b = orc.run(ev), ref.run(ev)
+        assert b["bottom"].size > 100
+        assert _same_bits(a, b), (conf, i)
