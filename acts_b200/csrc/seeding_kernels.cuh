@@ -921,6 +921,7 @@ __device__ __forceinline__ uint32_t doublet_side(const DoubletParams& p, const M
       out.pos = o; out.cotTheta = rec.cotTheta; out.iDeltaR = rec.iDeltaR; out.er = rec.er;
       out.u = rec.u; out.v = rec.v; out.xNew = rec.xNew; out.yNew = rec.yNew;
     }
+    __syncwarp();  // the queue entries of this step are read: later steps (or the other side of the middle) may overwrite them
     const uint32_t mask = __ballot_sync(0xffffffffu, ok);
     if (ok) {
       const uint32_t d = nOut + (uint32_t)__popc(mask & ltMask);
