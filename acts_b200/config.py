@@ -374,6 +374,47 @@ def itk_pixel_config(init, z_neighbors: bool = True, high_occupancy: bool = Fals
     return cfg
 
 
+def itk_strip_config(init, z_neighbors: bool = True) -> Config:
+    """``itkSeedingAlgConfig(StripSpacePoints)`` VERBATIM (Python/Examples/python/itk.py:302-400,458-506) as
+    ``addGridTripletSeeding`` hands it to ``GridTripletSeedingAlgorithm::Config`` (reconstruction.py:1001-1077):
+    rMax 1200 mm, deltaR 20 - 600 mm with 20 - 300 mm per side, deltaZMax 900 mm, no interaction-point cut,
+    impactMax 20 mm, the strip z-bin looping and neighbour tables, variable middle range 30 / 150 mm,
+    seedConfirmation with collector capacities 100 / 100, seedWeightIncrement 10100, compatSeedLimit 4."""
+    cfg = Config()
+    init(C.byref(cfg))
+    r_range = [(40.0, 90.0), (40.0, 90.0), (40.0, 200.0), (46.0, 200.0), (46.0, 200.0), (46.0, 250.0), (46.0, 250.0),
+               (46.0, 250.0), (46.0, 200.0), (46.0, 200.0), (40.0, 200.0), (40.0, 90.0), (40.0, 90.0)]
+    conf = dict(rMaxSeedConf=140.0, nTopForLargeR=1, nTopForSmallR=2, seedConfMinBottomRadius=60.0,
+                seedConfMaxZOrigin=150.0, minImpactSeedConf=1.0)
+    cfg.update(
+        bFieldInZ=2 * T, minPt=900 * MeV, cotThetaMax=27.2899, impactMax=20.0,
+        deltaRMin=20.0, deltaRMax=600.0, deltaRMinTop=20.0, deltaRMaxTop=300.0, deltaRMinBottom=20.0, deltaRMaxBottom=300.0,
+        deltaZMax=900.0,
+        rMax=1200.0, zMin=-3000.0, zMax=3000.0, phiMin=-math.pi, phiMax=math.pi,
+        phiBinDeflectionCoverage=3, maxPhiBins=200,
+        zBinEdges=[-3000.0, -2700.0, -2500.0, -1400.0, -925.0, -500.0, -250.0, 250.0, 500.0, 925.0, 1400.0, 2500.0, 2700.0, 3000.0],
+        zBinsCustomLooping=[6, 7, 5, 8, 4, 9, 3, 10, 2, 11, 1],
+        useVariableMiddleSPRange=1, rRangeMiddleSP=r_range,
+        deltaRMiddleMinSPRange=30.0, deltaRMiddleMaxSPRange=150.0,
+        interactionPointCut=0, collisionRegionMin=-200.0, collisionRegionMax=200.0,
+        sigmaScattering=2.0, radLengthPerSeed=0.0975,
+        compatSeedWeight=100.0, impactWeightFactor=1.0, zOriginWeightFactor=1.0,
+        maxSeedsPerSpM=4, compatSeedLimit=4, seedWeightIncrement=10100.0, numSeedIncrement=1.0,
+        seedConfirmation=1,
+        centralSeedConfirmationRange=dict(zMinSeedConf=-500.0, zMaxSeedConf=500.0, **conf),
+        forwardSeedConfirmationRange=dict(zMinSeedConf=-3000.0, zMaxSeedConf=3000.0, **conf),
+        maxSeedsPerSpMConf=100, maxQualitySeedsPerSpMConf=100, useDeltaRinsteadOfTopRadius=0,
+        useExtraCuts=0,
+    )
+    if z_neighbors:
+        cfg.update(
+            zBinNeighborsTop=[(0, 0), (-1, 0), (-2, 0), (-1, 0), (-1, 0), (-1, 0), (-1, 1), (0, 1), (0, 1), (0, 1), (0, 2), (0, 1), (0, 0)],
+            zBinNeighborsBottom=[(0, 0), (0, 1), (0, 1), (0, 1), (0, 2), (0, 1), (0, 0), (-1, 0), (-2, 0), (-1, 0), (-1, 0), (-1, 0), (0, 0)],
+            numPhiNeighbors=1,
+        )
+    return cfg
+
+
 def orthogonal_config(init_orth, **overrides):
     """(Config, OrthogonalOptions) with the reference defaults of OrthogonalTripletSeedingAlgorithm::Config
     (hpp:38-186) and the <mu>=200 cut set of pu200_config on top (the same physics cuts through the other

@@ -37,6 +37,13 @@ ITK_LAYOUT = dict(barrel_r=np.array([34.0, 99.0, 160.0, 228.0, 291.0]), barrel_h
                   endcap_r=(33.0, 315.0))
 
 
+# ITk-STRIP-shaped layout: four double-sided barrel layers out to 1 m, six end-cap discs out to |z| = 2.85 m -- the
+# extent itk.py's StripSpacePoints block is written for (rMax 1000 / 1200 mm, deltaR up to 600 mm, deltaZMax 900 mm).
+ITK_STRIP_LAYOUT = dict(barrel_r=np.array([405.0, 562.0, 762.0, 1000.0]), barrel_half_z=1372.0,
+                        endcap_z=np.array([1512.0, 1702.0, 1952.0, 2252.0, 2602.0, 2852.0]),
+                        endcap_r=(385.0, 970.0))
+
+
 def _helix_hits(rng, zv, pt, eta, phi0, q, layout=None):
     """Intersections of helices from (0, 0, zv) with all layers (vectorised).
 
@@ -152,6 +159,25 @@ def itk_pileup_event(event: int, mu: float = 60.0, sp_per_vertex: float = 500.0,
     return _finish(rng, x, y, z, barrel, noise_fraction, ITK_LAYOUT)
 
 
+def itk_strip_event(event: int, mu: float = 60.0, sp_per_vertex: float = 300.0,
+                    noise_fraction: float = 0.10, seed: int = 42) -> dict:
+    """Pile-up event on the ITk-strip-shaped layout (|eta| < 2.7), with the strip calibration details of
+    ``strip_details`` under ``"strip"`` (the points are what a strip space-point builder would hand over)."""
+    rng = np.random.Generator(np.random.Philox(key=seed + 100003 * 11 + event))
+    n_vtx = max(1, int(rng.poisson(mu)))
+    n_part = rng.poisson(sp_per_vertex / (1.0 + noise_fraction) / 4.0, size=n_vtx)
+    zv = np.repeat(rng.normal(0.0, 50.0, size=n_vtx), n_part)
+    n = zv.size
+    pt = 0.4 + rng.gamma(2.0, 0.6, size=n)
+    eta = rng.uniform(-2.7, 2.7, size=n)
+    phi0 = rng.uniform(-np.pi, np.pi, size=n)
+    q = rng.choice([-1.0, 1.0], size=n)
+    x, y, z, barrel = _helix_hits(rng, zv, pt, eta, phi0, q, ITK_STRIP_LAYOUT)
+    ev = dict(_finish(rng, x, y, z, barrel, noise_fraction, ITK_STRIP_LAYOUT))
+    ev["strip"] = strip_details(ev, seed=event, half_length=24.0, gap=6.0, barrel_max_z=1400.0)
+    return ev
+
+
 def muon_gun_event(event: int, n_muons: int = 100, seed: int = 42) -> dict:
     """Config 1: particle gun, 100 muons/event, pT 1-10 GeV, |eta| < 2.5
     (Examples/Scripts/Python/seeding.py:76-92), single vertex, no noise."""
@@ -219,7 +245,8 @@ def pixel_measurements(event: int, n: int = 20000, seed: int = 42) -> tuple[dict
     return meas, transforms
 
 
-def strip_details(ev: dict, seed: int = 0, half_length: float = 12.0, gap: float = 3.0, stereo: float = 0.02) -> np.ndarray:
+def strip_details(ev: dict, seed: int = 0, half_length: float = 12.0, gap: float = 3.0, stereo: float = 0.02,
+                  barrel_max_z: float = 500.0) -> np.ndarray:
     """Synthetic outer-strip calibration details for every space point of ``ev``: (n, 12) float32 =
     outerCenter, innerToOuterSeparation, outerHalfVector, innerHalfVector
     (Core/include/Acts/EventData/StripSpacePointCalibrationDetails.hpp:16-29).
@@ -227,14 +254,14 @@ def strip_details(ev: dict, seed: int = 0, half_length: float = 12.0, gap: float
     Every space point is taken as the crossing of a double-sided strip module: the outer strip passes through the
     point, the inner strip through the point where the line from the origin pierces a plane ``gap`` mm closer to the
     beam line; the two strips are rotated by +-``stereo`` rad about the module normal (radial in the barrel, along z
-    for |z| > 500 mm).  The crossing sits at a random place along both strips (|s| <= 0.9 half lengths), so a
+    for |z| > ``barrel_max_z``).  The crossing sits at a random place along both strips (|s| <= 0.9 half lengths), so a
     straight track from the origin calibrates back to the space point and tracks from displaced vertices move along
     the outer strip or leave the module (the tolerance cut of StripSpacePointCalibrationImpl.hpp:44-74)."""
     rng = np.random.Generator(np.random.Philox(key=977 + seed))
     p = np.stack([ev["x"], ev["y"], ev["z"]], axis=1).astype(np.float64)
     n = p.shape[0]
     r = np.hypot(p[:, 0], p[:, 1])
-    barrel = np.abs(p[:, 2]) <= 500.0
+    barrel = np.abs(p[:, 2]) <= barrel_max_z
     rs = np.where(r > 0, r, 1.0)
     normal = np.where(barrel[:, None], np.stack([p[:, 0] / rs, p[:, 1] / rs, np.zeros(n)], axis=1),
                       np.tile(np.array([0.0, 0.0, 1.0]), (n, 1)))

@@ -37,4 +37,7 @@ def make_config(name, init):
             # addGridTripletSeeding forwards it (without them), and the highOccupancyConfig branch
             "itk_pixel": config.itk_pixel_config,
             "itk_pixel_grid": lambda i: config.itk_pixel_config(i, z_neighbors=False),
-            "itk_pixel_ho": lambda i: config.itk_pixel_config(i, high_occupancy=True)}[name](init)
+            "itk_pixel_ho": lambda i: config.itk_pixel_config(i, high_occupancy=True),
+            # the verbatim ITk STRIP configuration (itk.py:458-506: collectors of 100, seedConfirmation)
+            "itk_strip": config.itk_strip_config,
+            "itk_strip_grid": lambda i: config.itk_strip_config(i, z_neighbors=False)}[name](init)

@@ -32,7 +32,13 @@ CASES = [
     ("itk_pixel_mu20_ev0", "itk_pixel", "itk", 0, 20.0),
     ("itk_pixel_grid_mu10_ev1", "itk_pixel_grid", "itk", 1, 10.0),
     ("itk_pixel_ho_mu20_ev2", "itk_pixel_ho", "itk", 2, 20.0),
+    # the verbatim ITk STRIP configuration (itk.py:458-506: seedConfirmation, collectors of 100) on the strip-shaped
+    # layout; these fixtures also carry the strip calibration details and the seeds of the strip triplet path
+    # (TripletSeedFinder useStripInfo = true, cotThetaDiffMax = 0.1) under "strip" / "s_*"
+    ("itk_strip_mu40_ev0", "itk_strip", "itkstrip", 0, 40.0),
+    ("itk_strip_grid_mu20_ev1", "itk_strip_grid", "itkstrip", 1, 20.0),
 ]
+STRIP_COT_THETA_DIFF_MAX = 0.1
 
 from tests.conftest import make_config  # noqa: E402
 
@@ -41,15 +47,22 @@ from tests.conftest import make_config  # noqa: E402
 def main():
     for name, cfg_name, gen, eid, mu in CASES:
         ev = (events.muon_gun_event(eid) if gen == "muon" else
-              events.itk_pileup_event(eid, mu=mu) if gen == "itk" else events.pileup_event(eid, mu=mu))
+              events.itk_pileup_event(eid, mu=mu) if gen == "itk" else
+              events.itk_strip_event(eid, mu=mu) if gen == "itkstrip" else events.pileup_event(eid, mu=mu))
         res = O.Oracle(make_config(cfg_name, O.config_init)).run(ev, want_grid=True)
+        extra = {}
+        if "strip" in ev:
+            sres = O.Oracle(make_config(cfg_name, O.config_init)).run(ev, strip_cot_theta_diff_max=STRIP_COT_THETA_DIFF_MAX)
+            extra = dict(strip=ev["strip"], s_cotThetaDiffMax=np.float32(STRIP_COT_THETA_DIFF_MAX),
+                         **{"s_" + k: sres[k] for k in ("bottom", "middle", "top", "quality", "vertexZ")})
         np.savez_compressed(
             os.path.join(HERE, name + ".npz"), config=cfg_name,
             x=ev["x"], y=ev["y"], z=ev["z"], r=ev["r"], varZ=ev["varZ"], varR=ev["varR"],
             bottom=res["bottom"], middle=res["middle"], top=res["top"], quality=res["quality"],
             vertexZ=res["vertexZ"], grid_copiedFromIndex=res["grid"]["copiedFromIndex"],
             grid_binBegin=res["grid"]["binBegin"], grid_binEnd=res["grid"]["binEnd"],
-            counters=np.array([res["counters"][k] for k in ("nInGrid", "nMiddles", "nBottomDoublets", "nTopDoublets", "nCandidates", "nSeeds")], dtype=np.uint64))
+            counters=np.array([res["counters"][k] for k in ("nInGrid", "nMiddles", "nBottomDoublets", "nTopDoublets", "nCandidates", "nSeeds")], dtype=np.uint64),
+            **extra)
         print(name, ev["x"].size, "space points ->", res["quality"].size, "seeds")
 
 

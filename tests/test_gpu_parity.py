@@ -519,6 +519,11 @@ def test_gpu_reproduces_committed_golden_vectors(plugin):
         grid = eng.debug_grid()
         assert np.array_equal(grid["copiedFromIndex"], g["grid_copiedFromIndex"])
         assert np.array_equal(grid["binBegin"], g["grid_binBegin"]) and np.array_equal(grid["binEnd"], g["grid_binEnd"])
+        if "strip" in g.files:  # the strip triplet path on the same event
+            ev["strip"] = g["strip"]
+            got = eng.run(ev, strip_cot_theta_diff_max=float(g["s_cotThetaDiffMax"]))
+            for k in KEYS:
+                assert np.array_equal(got[k].view(np.uint32), g["s_" + k].view(np.uint32)), (f, "strip", k)
         eng.close()
 
 
@@ -1065,4 +1070,25 @@ def test_itk_strip_filter_block_collectors_of_100(plugin, O, conf):
         got, ref = eng.run(ev, strip_cot_theta_diff_max=0.2), orc.run(ev, strip_cot_theta_diff_max=0.2)
         assert _same_bits(got, ref), (conf, i, "strip path")
     assert ties > 0
+    eng.close()
+
+
+@pytest.mark.parametrize("name,mu,ids", [("itk_strip", 60, (0, 1)), ("itk_strip", 200, (2,)), ("itk_strip_grid", 200, (3,))])
+def test_verbatim_itk_strip_configuration(plugin, O, name, mu, ids):
+    """itkSeedingAlgConfig(StripSpacePoints) verbatim (Python/Examples/python/itk.py:458-506: rMax 1200 mm, deltaR up
+    to 600 mm, deltaZMax 900 mm, seedConfirmation with collectors of 100 / 100, seedWeightIncrement 10100) on
+    ITk-strip-shaped events: the pixel triplet path (what the reference's algorithm runs with this configuration)
+    and the strip triplet path on the same points."""
+    from acts_b200 import events
+
+    eng = plugin.SeedingEngine(make_config(name, plugin.config_init))
+    orc = O.Oracle(make_config(name, O.config_init))
+    for i in ids:
+        ev = events.itk_strip_event(i, mu=mu)
+        got, ref = eng.run(ev), orc.run(ev)
+        assert ref["quality"].size > 1000
+        assert _same_bits(got, ref), (name, i, "pixel path")
+        got, ref = eng.run(ev, strip_cot_theta_diff_max=0.1), orc.run(ev, strip_cot_theta_diff_max=0.1)
+        assert ref["quality"].size > 500
+        assert _same_bits(got, ref), (name, i, "strip path")
     eng.close()

@@ -178,6 +178,11 @@ def test_oracle_reproduces_committed_golden_vectors(O):
         for k in ("bottom", "middle", "top", "quality", "vertexZ"):
             assert np.array_equal(res[k].view(np.uint32), g[k].view(np.uint32)), (f, k)
         assert np.array_equal(res["grid"]["copiedFromIndex"], g["grid_copiedFromIndex"])
+        if "strip" in g.files:  # the strip triplet path on the same event
+            ev["strip"] = g["strip"]
+            res = O.Oracle(make_config(str(g["config"]), O.config_init)).run(ev, strip_cot_theta_diff_max=float(g["s_cotThetaDiffMax"]))
+            for k in ("bottom", "middle", "top", "quality", "vertexZ"):
+                assert np.array_equal(res[k].view(np.uint32), g["s_" + k].view(np.uint32)), (f, "strip", k)
 
 
 def test_empty_and_out_of_grid_inputs(O):

@@ -174,6 +174,10 @@ def test_golden_fixtures_match_reference(R, O):
         b = R.Reference(make_config(name, O.config_init)).run(ev)
         want = {k: g[k] for k in KEYS}
         assert _same_bits(want, b), os.path.basename(f)
+        if "strip" in g.files:  # the reference's own strip triplet path (ref_run_strips) on the same event
+            ev["strip"] = g["strip"]
+            b = R.Reference(make_config(name, O.config_init)).run_strips(ev, float(g["s_cotThetaDiffMax"]))
+            assert _same_bits({k: g["s_" + k] for k in KEYS}, b), os.path.basename(f) + " (strip path)"
 
 
 def test_reference_entered_from_many_threads(R, O):
