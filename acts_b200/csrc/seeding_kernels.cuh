@@ -890,6 +890,9 @@ __device__ __forceinline__ void warp_windows(const DoubletParams& p, const uint3
 }
 
 constexpr int kDoubletWarps = 8;
+#ifndef B200SEED_MASK_PREFETCH
+#define B200SEED_MASK_PREFETCH 0
+#endif
 constexpr int kDoubletQueue = 160;  // < 32 left over + up to 128 new survivors per step
 
 // One side of one middle.  Count pass: returns the number of (z, r) survivors.  Fill pass: survivors are
@@ -898,7 +901,8 @@ template <bool kBottom, bool kFill>
 __device__ __forceinline__ uint32_t doublet_side(const DoubletParams& p, const MiddleSp& mid, const uint32_t* winS,
                                                  const uint32_t* winE, uint32_t nWin, uint32_t* queue,
                                                  DoubletRecord* recOut, float* keyOut, float& cotMin, float& cotMax,
-                                                 const float* zLo, const float* zHi, int nZ, uint32_t* masks = nullptr) {
+                                                 const float* zLo, const float* zHi, int nZ, uint32_t* masks = nullptr,
+                                                 uint32_t nMaskWords = 0) {
   // `masks`: count pass -- where to write the survivor words (NULL: nowhere); fill pass -- where to read them from
   // (NULL: load and test the candidates like the count pass did)
   const DeviceConfig& cfg = p.cfg;
@@ -943,12 +947,22 @@ __device__ __forceinline__ uint32_t doublet_side(const DoubletParams& p, const M
     }
     qn = rest;
   };
+#if B200SEED_MASK_PREFETCH
+  uint4 mNext = make_uint4(0u, 0u, 0u, 0u);  // the survivor words of the next step, requested one step ahead
+  if (kFill && masks != nullptr && nMaskWords != 0u) mNext = __ldg(reinterpret_cast<const uint4*>(masks));
+#endif
   for (uint32_t k = 0; k < nWin; ++k) {
     const uint32_t s = winS[k], e = winE[k];
     for (uint32_t base = s; base < e; base += 128u) {
       if (kFill && masks != nullptr) {  // the count pass left the survivor words: no candidate is loaded or tested again
+#if B200SEED_MASK_PREFETCH
+        const uint4 m4 = mNext;
+        wi += 4;
+        if (wi < nMaskWords) mNext = __ldg(reinterpret_cast<const uint4*>(masks + wi));
+#else
         const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(masks + wi));  // (4 words per step, 16-byte aligned)
         wi += 4;
+#endif
         const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -1149,11 +1163,11 @@ __global__ void __launch_bounds__(kDoubletWarps * 32) k_doublets(const __grid_co
           maskT = p.maskArena + moff + nWinWords;
           maskB = maskT + 4u * stepsT;
         }
-        const uint32_t nT = doublet_side<false, true>(p, mid, W.s + nBot, W.e + nBot, nTop, queue, recSlot + capB, keySlot + capB, mnT, mxT, zLo, zHi, nZ, maskT);
+        const uint32_t nT = doublet_side<false, true>(p, mid, W.s + nBot, W.e + nBot, nTop, queue, recSlot + capB, keySlot + capB, mnT, mxT, zLo, zHi, nZ, maskT, 4u * stepsT);
         bool go = nT != 0u;
         if (go && p.conf) go = !(nT < conf_n_top(conf_range(cfg, mid.z), mid.r));  // BroadTripletSeedFilter.cpp:63-94
         uint32_t nB = 0;
-        if (go) nB = doublet_side<true, true>(p, mid, W.s, W.e, nBot, queue, recSlot, keySlot, mnB, mxB, zLo, zHi, nZ, maskB);
+        if (go) nB = doublet_side<true, true>(p, mid, W.s, W.e, nBot, queue, recSlot, keySlot, mnB, mxB, zLo, zHi, nZ, maskB, 4u * stepsB);
         go = go && nB != 0u;
         if (lane == 0) {
           MiddleHeader h{};

@@ -215,7 +215,10 @@ int ensure_workspace(b200seed_handle* h, uint32_t nEvents, uint32_t nTotal) {
   CUDA_TRY(h->hdr.reserve(nT * sizeof(MiddleHeader)));
   CUDA_TRY(h->carve.reserve(nT * sizeof(SeedCarve)));
   CUDA_TRY(h->classList.reserve(nT * 4 * (kNumSeedClasses + 1) * 2));
-  CUDA_TRY(h->planDev.reserve(((size_t)kMaxChunks + 1 + 8) * 4));
+  if (h->planDev.ptr == nullptr) {  // the whole plan buffer is copied to the host each call, the bounds beyond the last chunk unread: define them once
+    CUDA_TRY(h->planDev.reserve(((size_t)kMaxChunks + 1 + 8) * 4));
+    CUDA_TRY(cudaMemset(h->planDev.ptr, 0, h->planDev.bytes));
+  }
   CUDA_TRY(h->slotB.reserve(nT * K * 4));
   CUDA_TRY(h->slotM.reserve(nT * K * 4));
   CUDA_TRY(h->slotT.reserve(nT * K * 4));
