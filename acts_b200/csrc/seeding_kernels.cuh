@@ -180,6 +180,34 @@ __device__ __forceinline__ uint32_t block_scan_exclusive(uint32_t v, uint32_t* s
   return out;
 }
 
+// Exclusive scan (sum) of an array of n words in place; returns the total
+// (to every thread).  Every thread scans kItems consecutive words serially, one
+// block scan combines the per-thread sums: a single pass for n <= 8 * blockDim.x.
+__device__ __forceinline__ uint32_t block_scan_array(uint32_t* a, uint32_t n, uint32_t* scratch) {
+  constexpr uint32_t kItems = 8;
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < n; base += blockDim.x * kItems) {
+    const uint32_t i0 = base + threadIdx.x * kItems;
+    uint32_t v[kItems];
+    uint32_t sum = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < kItems; ++k) {
+      v[k] = (i0 + k) < n ? a[i0 + k] : 0u;
+      sum += v[k];
+    }
+    uint32_t total;
+    uint32_t run = block_scan_exclusive(sum, scratch, total, OpSum()) + carry;
+#pragma unroll
+    for (uint32_t k = 0; k < kItems; ++k) {
+      if ((i0 + k) < n) a[i0 + k] = run;
+      run += v[k];
+    }
+    carry += total;
+  }
+  __syncthreads();
+  return carry;
+}
+
 // Ordered warp-aggregated append: lanes with `pred` get consecutive slots.
 // Must be called by all 32 lanes of the warp.
 __device__ __forceinline__ uint32_t warp_append(uint32_t* counter, bool pred) {
@@ -374,25 +402,26 @@ __global__ void __launch_bounds__(256) k_scatter(const __grid_constant__ GridPar
   }
 }
 
-// In-place bitonic sort of n 64-bit keys stored in a buffer of `padded` (power
-// of two, >= n) entries; entries [n, padded) must hold ~0ull.
-__device__ __forceinline__ void block_bitonic_sort(unsigned long long* keys, uint32_t padded) {
-  for (uint32_t k = 2; k <= padded; k <<= 1) {
-    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-      for (uint32_t i = threadIdx.x; i < padded; i += blockDim.x) {
-        const uint32_t ixj = i ^ j;
-        if (ixj > i) {
-          const unsigned long long a = keys[i], b = keys[ixj];
-          const bool up = (i & k) == 0;
-          if ((a > b) == up) {
-            keys[i] = b;
-            keys[ixj] = a;
-          }
-        }
-      }
-      __syncthreads();
-    }
+// Bucket sort of the n entries of a bin (shared or global memory): `put(i, q)` stores entry i at position q,
+// `bucketOf(i)` is monotone non-decreasing in the sort key and < nBk, `sortBucket(s, e)` orders positions [s, e)
+// (entries of one bucket; one thread).  Replaces a 66-stage bitonic sort of 2048 padded keys by two atomic
+// passes, one scan and an insertion sort inside the buckets.
+constexpr uint32_t kSortBuckets = 2048;
+template <typename BucketOf, typename Put, typename SortBucket>
+__device__ __forceinline__ void block_bucket_sort(uint32_t n, uint32_t* buckets, uint32_t* scratch, BucketOf bucketOf, Put put,
+                                                  SortBucket sortBucket) {
+  for (uint32_t i = threadIdx.x; i <= kSortBuckets; i += blockDim.x) buckets[i] = 0;
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(buckets + bucketOf(i), 1u);
+  __syncthreads();
+  block_scan_array(buckets, kSortBuckets, scratch);
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) put(i, atomicAdd(buckets + bucketOf(i), 1u));
+  __syncthreads();  // buckets[b] is now the END of bucket b
+  for (uint32_t b = threadIdx.x; b < kSortBuckets; b += blockDim.x) {
+    const uint32_t s0 = b == 0 ? 0u : buckets[b - 1], e0 = buckets[b];
+    if (e0 - s0 >= 2u) sortBucket(s0, e0);
   }
+  __syncthreads();
 }
 
 __device__ __forceinline__ bool bin_flagged(const TieItem& a) { return (a.val >> 31) != 0u; }
@@ -411,54 +440,119 @@ __device__ __forceinline__ bool bin_flagged(const TieItem& a) { return (a.val >>
 // shared memory when they fit, else in the global scratch.
 __global__ void __launch_bounds__(kSortThreads) k_sort_bins(const __grid_constant__ GridParams p) {
   extern __shared__ unsigned long long smemKeys[];
-  __shared__ uint32_t sFlag;
+  __shared__ uint32_t sFlag, sMin, sMax;
+  __shared__ uint32_t sScratch[34];
   const uint32_t gb = blockIdx.x;
   const uint32_t b0 = p.binStart[gb], b1 = p.binStart[gb + 1];
   const uint32_t n = b1 - b0;
   if (n == 0) return;
   const uint32_t e = gb / p.nBins;
   const uint32_t evBase = __ldg(p.spOffsets + e);
-  uint32_t padded = 1;
-  while (padded < n) padded <<= 1;
-  const bool inSmem = padded <= p.sortSmemCap;
+  const uint32_t nEvent = __ldg(p.spOffsets + e + 1) - evBase;
+  // shared memory: keys[cap], work[cap], buckets[kSortBuckets + 1]; a bin beyond the capacity uses its 32 n bytes of
+  // the global scratch the same way
+  const bool inSmem = n <= p.sortSmemCap;
   unsigned long long* keys = inSmem ? smemKeys : p.sortScratch + 4ull * b0;
-  unsigned long long* work = inSmem ? smemKeys + p.sortSmemCap : p.sortScratch + 4ull * b0 + 2ull * n;
-  for (uint32_t i = threadIdx.x; i < padded; i += blockDim.x) {
-    unsigned long long k = ~0ull;
-    if (i < n) {
+  unsigned long long* work = inSmem ? smemKeys + p.sortSmemCap : p.sortScratch + 4ull * b0 + n;
+  uint32_t* buckets = inSmem ? reinterpret_cast<uint32_t*>(smemKeys + 2ull * p.sortSmemCap)
+                             : reinterpret_cast<uint32_t*>(p.sortScratch + 4ull * b0 + 2ull * n);
+  if (threadIdx.x == 0) { sFlag = 0; sMin = 0xFFFFFFFFu; sMax = 0u; }
+  __syncthreads();
+  {
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
       const uint32_t idx = p.tmpIdx[b0 + i];
       const float r = __ldg(p.r + evBase + idx);
-      const uint32_t rb = (r == 0.0f) ? 0u : __float_as_uint(r);  // r >= 0 inside the grid
-      k = ((unsigned long long)rb << 32) | idx;
+      const uint32_t rb = (r == 0.0f) ? 0u : __float_as_uint(r);  // r >= 0 inside the grid: the bit pattern orders like the value
+      work[i] = ((unsigned long long)rb << 32) | idx;
+      mn = mn < rb ? mn : rb;
+      mx = mx > rb ? mx : rb;
     }
-    keys[i] = k;
+    for (int d = 16; d > 0; d >>= 1) {
+      const uint32_t om = __shfl_xor_sync(0xffffffffu, mn, d), ox = __shfl_xor_sync(0xffffffffu, mx, d);
+      mn = mn < om ? mn : om;
+      mx = mx > ox ? mx : ox;
+    }
+    if ((threadIdx.x & 31u) == 0u) { atomicMin(&sMin, mn); atomicMax(&sMax, mx); }
   }
-  if (threadIdx.x == 0) sFlag = 0;
   __syncthreads();
-  block_bitonic_sort(keys, padded);
+  // 1. canonical order (r, original index): work -> keys
+  {
+    const float rMin = __uint_as_float(sMin), rMax = __uint_as_float(sMax);
+    const float scale = rMax > rMin ? (float)kSortBuckets / (rMax - rMin) : 0.0f;
+    block_bucket_sort(
+        n, buckets, sScratch,
+        [&](uint32_t i) {
+          float t = (__uint_as_float((uint32_t)(work[i] >> 32)) - rMin) * scale;  // monotone in r
+          if (!(t > 0.0f)) t = 0.0f;
+          const uint32_t b = (uint32_t)t;
+          return b < kSortBuckets ? b : kSortBuckets - 1u;
+        },
+        [&](uint32_t i, uint32_t q) { keys[q] = work[i]; },
+        [&](uint32_t s0, uint32_t e0) {
+          unsigned long long* a = keys + s0;
+          const uint32_t m = e0 - s0;
+          if (m <= 48u) {
+            for (uint32_t i = 1; i < m; ++i) {
+              const unsigned long long v = a[i];
+              uint32_t j = i;
+              while (j > 0 && a[j - 1] > v) { a[j] = a[j - 1]; --j; }
+              a[j] = v;
+            }
+          } else {  // many equal or nearly equal radii (quantised coordinates): heapsort, O(m log m) for any input
+            auto sift = [&](uint32_t root, uint32_t end) {
+              const unsigned long long v = a[root];
+              for (;;) {
+                uint32_t c = 2u * root + 1u;
+                if (c >= end) break;
+                if (c + 1u < end && a[c + 1u] > a[c]) ++c;
+                if (!(a[c] > v)) break;
+                a[root] = a[c];
+                root = c;
+              }
+              a[root] = v;
+            };
+            for (uint32_t i = m / 2u; i-- > 0u;) sift(i, m);
+            for (uint32_t end = m - 1u; end > 0u; --end) {
+              const unsigned long long t = a[0]; a[0] = a[end]; a[end] = t;
+              sift(0u, end);
+            }
+          }
+        });
+  }
   if (p.exactTies && n > 16) {
     bool t = false;
     for (uint32_t i = threadIdx.x + 1; i < n; i += blockDim.x) t |= (keys[i] >> 32) == (keys[i - 1] >> 32);
     if (t) sFlag = 1;
     __syncthreads();
     if (sFlag != 0) {  // block-uniform
-      // insertion order: sort (original index, canonical rank) by index
-      for (uint32_t i = threadIdx.x; i < padded; i += blockDim.x) {
-        work[i] = i < n ? (((keys[i] & 0xffffffffull) << 32) | i) : ~0ull;
-      }
-      __syncthreads();
-      block_bitonic_sort(work, padded);
+      // 2. insertion order (ascending original index): the replay items {r, canonical rank | tied flag} are scattered
+      // straight into that order (original indices are spread evenly over [0, nEvent))
       TieItem* W = reinterpret_cast<TieItem*>(work);
-      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint32_t rank = (uint32_t)(work[i] & 0xffffffffull);
-        const uint32_t rb = (uint32_t)(keys[rank] >> 32);
-        const bool tied = (rank > 0 && (uint32_t)(keys[rank - 1] >> 32) == rb) ||
-                          (rank + 1 < n && (uint32_t)(keys[rank + 1] >> 32) == rb);
-        TieItem it;
-        it.key = __uint_as_float(rb);
-        it.val = rank | (tied ? 0x80000000u : 0u);
-        W[i] = it;  // the same 8 bytes work[i] came from
-      }
+      auto idxOfItem = [&](const TieItem& it) { return (uint32_t)(keys[it.val & 0x7fffffffu] & 0xffffffffull); };
+      block_bucket_sort(
+          n, buckets, sScratch,
+          [&](uint32_t i) {
+            const uint32_t b = (uint32_t)(((keys[i] & 0xffffffffull) * kSortBuckets) / nEvent);
+            return b < kSortBuckets ? b : kSortBuckets - 1u;
+          },
+          [&](uint32_t i, uint32_t q) {
+            const uint32_t rb = (uint32_t)(keys[i] >> 32);
+            const bool tied = (i > 0 && (uint32_t)(keys[i - 1] >> 32) == rb) || (i + 1 < n && (uint32_t)(keys[i + 1] >> 32) == rb);
+            TieItem it;
+            it.key = __uint_as_float(rb);
+            it.val = i | (tied ? 0x80000000u : 0u);
+            W[q] = it;
+          },
+          [&](uint32_t s0, uint32_t e0) {
+            for (uint32_t i = s0 + 1; i < e0; ++i) {
+              const TieItem v = W[i];
+              const uint32_t vi = idxOfItem(v);
+              uint32_t j = i;
+              while (j > s0 && idxOfItem(W[j - 1]) > vi) { W[j] = W[j - 1]; --j; }
+              W[j] = v;
+            }
+          });
       __syncthreads();
       if (threadIdx.x < 32) warp_sort_replay_ties(W, (int)n, bin_flagged);
       __syncthreads();
@@ -1407,34 +1501,6 @@ struct SeedShared {
   float heapMin;
   unsigned long long cnt[kCntSlots];
 };
-
-// Exclusive scan (sum) of an array of n words in place; returns the total
-// (to every thread).  Every thread scans kItems consecutive words serially, one
-// block scan combines the per-thread sums: a single pass for n <= 8 * blockDim.x.
-__device__ __forceinline__ uint32_t block_scan_array(uint32_t* a, uint32_t n, uint32_t* scratch) {
-  constexpr uint32_t kItems = 8;
-  uint32_t carry = 0;
-  for (uint32_t base = 0; base < n; base += blockDim.x * kItems) {
-    const uint32_t i0 = base + threadIdx.x * kItems;
-    uint32_t v[kItems];
-    uint32_t sum = 0;
-#pragma unroll
-    for (uint32_t k = 0; k < kItems; ++k) {
-      v[k] = (i0 + k) < n ? a[i0 + k] : 0u;
-      sum += v[k];
-    }
-    uint32_t total;
-    uint32_t run = block_scan_exclusive(sum, scratch, total, OpSum()) + carry;
-#pragma unroll
-    for (uint32_t k = 0; k < kItems; ++k) {
-      if ((i0 + k) < n) a[i0 + k] = run;
-      run += v[k];
-    }
-    carry += total;
-  }
-  __syncthreads();
-  return carry;
-}
 
 // Combined bucket sort of the bottom and top doublet lists of one middle by
 // (cotTheta, emission index): the bottoms use buckets [0, nBk / 2), the tops

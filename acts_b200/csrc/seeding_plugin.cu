@@ -85,7 +85,7 @@ struct b200seed_handle {
   // per-middle shared-memory capacities are compile-time (seeding_kernels.cuh):
   // tier 0 takes every middle at 2 blocks per SM, middles that do not fit are
   // re-queued to tier 1 (1 block per SM)
-  uint32_t sortSmemCap = 4096;
+  uint32_t sortSmemCap = 2560;  // elements of a bin sorted in shared memory (16 bytes each + the bucket counters: 4 blocks per SM); larger bins use the global scratch
   int exactTies = 1;
   uint32_t phiFirst = 1, phiCount = 0xFFFFFFFFu;  // middle phi-bin sector (default: all)
   // shared-memory classes of the seeding kernel (seeding_kernels.cuh): blocks per SM, dynamic bytes per block
@@ -659,7 +659,7 @@ int enqueue(b200seed_handle* h) {
   ++launches;
   if (nTotal > 0) {
     k_scatter<<<elemBlocks, 256, 0, s>>>(gp);
-    k_sort_bins<<<nBinsAll, kSortThreads, (size_t)h->sortSmemCap * 16, s>>>(gp);
+    k_sort_bins<<<nBinsAll, kSortThreads, (size_t)h->sortSmemCap * 16 + ((size_t)kSortBuckets + 1) * 4, s>>>(gp);
     launches += 2;
   }
   if (a.dStrip != nullptr && nTotal > 0) {  // strip triplet path: derived calibration details in packed order
@@ -1226,7 +1226,8 @@ static int create_impl(const b200seed_config* cfg, const b200seed_orthogonal_opt
     CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_doublets_kd<true>, kKdThreads, 0));
     h->kdBlocksPerSM[1] = std::max(1, b);
   }
-  CREATE_TRY(cudaFuncSetAttribute(k_sort_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->sortSmemCap * 16)));
+  h->sortSmemCap = std::min<uint32_t>(std::max<uint32_t>(env_u32("B200SEED_SORT_CAP", 2560), 520), 8192);  // (>= 513: a larger bin's 32 n bytes of scratch also hold the bucket counters)
+  CREATE_TRY(cudaFuncSetAttribute(k_sort_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8192 * 16 + (kSortBuckets + 1) * 4)));
   if (std::getenv("B200SEED_VERBOSE") != nullptr) {
     for (int c = 0; c < kNumSeedClasses; ++c) {
       std::fprintf(stderr, "b200seed: seed class %d: %d threads, %u bytes of shared memory, %d blocks per SM\n", c,

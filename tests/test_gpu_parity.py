@@ -116,6 +116,29 @@ def test_count_to_fill_hand_off_arena_full_or_off(plugin, O, monkeypatch, words)
     eng.close()
 
 
+@pytest.mark.parametrize("cap", ["520", "800"])
+def test_bins_larger_than_the_sort_capacity_use_the_global_scratch(plugin, O, monkeypatch, cap):
+    """k_sort_bins orders a bin in shared memory up to B200SEED_SORT_CAP elements (default 2560) and in its slice
+    of the global scratch beyond: same packed copy (incl. the order inside bins with equal radii), same seeds."""
+    monkeypatch.setenv("B200SEED_SORT_CAP", cap)
+    eng = plugin.SeedingEngine(make_config("pu200", plugin.config_init))
+    orc = O.Oracle(make_config("pu200", O.config_init))
+    for i, mu, step in ((0, 100, 0.0), (1, 100, 1.0)):
+        ev = dict(_event("pileup", i, mu))
+        if step > 0:
+            for k in ("x", "y", "z"):
+                ev[k] = (np.round(ev[k] / np.float32(step)) * np.float32(step)).astype(np.float32)
+            ev["r"] = np.sqrt(ev["x"].astype(np.float64) ** 2 + ev["y"].astype(np.float64) ** 2).astype(np.float32)
+        got = eng.run(ev)
+        ref = orc.run(ev, want_grid=True)
+        assert ref["counters"]["maxBinSize"] > int(cap)
+        g = eng.debug_grid()
+        for k in ("copiedFromIndex", "binBegin", "binEnd"):
+            assert np.array_equal(g[k], ref["grid"][k]), f"grid {k}"
+        assert _same_bits(got, ref)
+    eng.close()
+
+
 def test_batch_equals_single_events(plugin, O):
     from acts_b200 import events
 
