@@ -398,6 +398,10 @@ def run_gpu(args):
 
         def worker(t, limit):
             torch.cuda.set_device(local)
+            if limit is None:  # warm-up: two calls on THIS thread's handle (the dynamic queue could starve a handle and leave its allocations to the timed region)
+                for j in range(2):
+                    engines[t].run(ev_pinned[(2 * t + j) % len(ev_pinned)], out=outs[t][1])
+                return
             while True:
                 with lock:  # dynamic event queue, like tbb::parallel_for over the events
                     i = nxt[0]
@@ -415,7 +419,7 @@ def run_gpu(args):
             for th in ths:
                 th.join()
 
-        run(2 * n_thr)  # warm-up: every handle allocates its workspaces
+        run(None)  # warm-up: every handle allocates its workspaces
         for k in range(n_thr):
             seeds_seen[k] = 0
         barrier()
