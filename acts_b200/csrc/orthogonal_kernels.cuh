@@ -401,7 +401,16 @@ struct KdDoubletParams {
   OrthDeviceConfig orth;
   const KdNodeDev* nodes;  // node e = root of event e
   const float* posPhi;
+  // Hand-off from the count pass to the fill pass: the positions of the survivors of every walk, in emission order,
+  // as a chain of 32-word pages (31 hits + the index of the next page; the list ends with kKdHitEnd).  hitHead[2 w]
+  // / [2 w + 1] = first page of the top / bottom walk of item w (kKdHitNone: arena full -- that walk is repeated by
+  // the fill pass).  The fill pass then reads positions instead of searching the tree a second time.
+  uint32_t* hitArena;
+  uint32_t hitPages;    // capacity in pages (0: no hand-off)
+  uint32_t* hitCursor;  // next free page
+  uint32_t* hitHead;    // [2 * items]
 };
+constexpr uint32_t kKdHitEnd = 0xFFFFFFFFu, kKdHitNone = 0xFFFFFFFFu;
 
 // The two-pass doublet stage of the orthogonal seeder.  Every LANE is a walker with its own work item: it runs the
 // range search of the item's top box, then (if tops were found) of its bottom box, one micro-step per loop iteration
@@ -448,6 +457,25 @@ __global__ void __launch_bounds__(kKdThreads) k_doublets_kd(const __grid_constan
   uint32_t slotLo = 0;
   bool exhausted = false;  // warp-uniform: the work list has been handed out
   const KdNodeDev* nodes = kp.nodes;
+  // hit list of the current walk: count pass -- page being written / words used / overflow; fill pass -- page being
+  // read / next word, listMode = this walk replays a list
+  uint32_t hitPage = kKdHitNone, hitFill = 0;
+  bool listMode = false;
+  auto hitAlloc = [&]() -> uint32_t {
+    const uint32_t pg = atomicAdd(kp.hitCursor, 1u);
+    return pg < kp.hitPages ? pg : kKdHitNone;
+  };
+  auto hitPut = [&](uint32_t v) {  // count pass: append one word to the current walk's list
+    if (hitPage == kKdHitNone) return;
+    if (hitFill == 31u) {
+      const uint32_t np = hitAlloc();
+      kp.hitArena[32ull * hitPage + 31u] = np;  // (kKdHitNone: the reader never gets here, the head is withdrawn below)
+      hitPage = np;
+      hitFill = 0;
+      if (np == kKdHitNone) return;
+    }
+    kp.hitArena[32ull * hitPage + hitFill++] = v;
+  };
 
   auto startWalk = [&](bool bottom) {
     KdBox boxB, boxT;
@@ -458,6 +486,24 @@ __global__ void __launch_bounds__(kKdThreads) k_doublets_kd(const __grid_constan
     id = rootNode; o = 0; oEnd = 0; contained = false;
     n = 0; mn = 3.0e38f; mx = -3.0e38f;
     phase = bottom ? 2 : 1;
+    listMode = false;
+    if (kp.hitPages != 0u) {
+      uint32_t* head = kp.hitHead + 2ull * w + (bottom ? 1u : 0u);
+      if (!kFill) {
+        hitPage = hitAlloc();
+        hitFill = 0;
+        *head = hitPage;
+      } else {
+        hitPage = *head;
+        hitFill = 0;
+        listMode = hitPage != kKdHitNone;
+      }
+    }
+  };
+  auto endList = [&](bool bottom) {  // count pass: close the list of the walk that just ended (or withdraw it)
+    if (kp.hitPages == 0u) return;
+    hitPut(kKdHitEnd);
+    if (hitPage == kKdHitNone) kp.hitHead[2ull * w + (bottom ? 1u : 0u)] = kKdHitNone;
   };
   auto finishCount = [&]() {  // count pass: slot sizes of the item
     if (capB == 0u) capT = 0u;
@@ -573,12 +619,26 @@ __global__ void __launch_bounds__(kKdThreads) k_doublets_kd(const __grid_constan
     if (__ballot_sync(0xffffffffu, walking) == 0u) break;
     if (!walking) continue;
     const bool bottom = phase == 2;
-    const bool elemStep = o < oEnd;
+    // fill pass, list mode: the next word of the count pass's hit list is either a survivor, a page link or the end
+    bool listEnd = false;
+    uint32_t eo = o;
+    bool elemStep = o < oEnd;
+    if (kFill && listMode) {
+      const uint32_t v = __ldg(kp.hitArena + 32ull * hitPage + hitFill);
+      elemStep = false;
+      if (hitFill == 31u) {
+        hitPage = v;
+        hitFill = 0;
+        continue;
+      }
+      ++hitFill;
+      if (v == kKdHitEnd) { listEnd = true; } else { eo = v; elemStep = true; }
+    }
     if (elemStep) {
-      const float2 zr = ldg2(p.pZR + o);
-      bool inside = contained;
+      const float2 zr = ldg2(p.pZR + eo);
+      bool inside = contained || (kFill && listMode);
       if (!inside) {
-        const float phi = __ldg(kp.posPhi + o);
+        const float phi = __ldg(kp.posPhi + eo);
         inside = (box.mn[0] <= phi) & (phi < box.mx[0]) & (box.mn[1] <= zr.y) & (zr.y < box.mx[1]) &
                  (box.mn[2] <= zr.x) & (zr.x < box.mx[2]);
       }
@@ -588,7 +648,9 @@ __global__ void __launch_bounds__(kKdThreads) k_doublets_kd(const __grid_constan
       if (pass) {
         if (!kFill) {
           ++n;
+          hitPut(eo);
         } else {
+          const uint32_t o = eo;  // (shadows the walker's position for the stores below)
           const float2 xy = ldg2(p.pXY + o), var = ldg2(p.pVar + o);
           DoubletRec rec;
           if (doublet_finish_side(bottom, cfg, mid, dR, dZ, xy.x, xy.y, zr.y, var.x, var.y, nullptr, nullptr, 0, rec, true)) {
@@ -602,8 +664,8 @@ __global__ void __launch_bounds__(kKdThreads) k_doublets_kd(const __grid_constan
           }
         }
       }
-      ++o;
-    } else if (id != kKdEnd) {
+      if (!(kFill && listMode)) ++o;
+    } else if (!listEnd && id != kKdEnd && !(kFill && listMode)) {
       const float4* nd = reinterpret_cast<const float4*>(nodes + id);
       const float4 a = __ldg(nd), b = __ldg(nd + 1);
       const uint4 c = __ldg(reinterpret_cast<const uint4*>(nd + 2));
@@ -625,6 +687,7 @@ __global__ void __launch_bounds__(kKdThreads) k_doublets_kd(const __grid_constan
         contained = cont;
       }
     } else {  // the walk is over
+      if (!kFill) endList(bottom);
       if (!bottom) {
         if (!kFill) {
           capT = n;

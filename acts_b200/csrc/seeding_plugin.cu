@@ -127,6 +127,8 @@ struct b200seed_handle {
   // orthogonal seeder: the event trees built by the host layer (kd_tree_host.hpp)
   DevBuf orthPosOrig, orthPosPhi, orthNodes, orthCoreOffsets, orthNodeOffsets, orthRRange;
   DevBuf orthElemR, orthElemZ, orthScratch, orthTasks, orthExtent;  // device construction of the trees
+  DevBuf kdHitArena, kdHitHead;  // count pass -> fill pass: survivor positions of every tree walk (B200SEED_KD_HIT_MB, 0 = off)
+  uint32_t kdHitMB = 4096;
   bool kdHostBuild = false;  // B200SEED_KD_HOST=1: build the trees in the host layer (kd_tree_host.hpp) instead
   uint32_t itemsMax = 0;  // upper bound of the work items of the last call (grid: space points, orthogonal: 2 x)
   uint32_t zWinCapacity = 1;  // windows per column of zWin (lo column, then hi column)
@@ -730,6 +732,15 @@ int enqueue(b200seed_handle* h) {
   }
   if (orthogonal) {
     kdp.d = dp;
+    if (h->kdHitMB != 0u) {
+      const size_t bytes = (size_t)h->kdHitMB << 20;
+      CUDA_TRY(h->kdHitArena.reserve(bytes));
+      CUDA_TRY(h->kdHitHead.reserve((size_t)nWorkMax * 8));
+      kdp.hitArena = h->kdHitArena.as<uint32_t>();
+      kdp.hitPages = (uint32_t)std::min<size_t>(bytes / 128, 0xFFFFFFF0u);
+      kdp.hitCursor = planWords + 7;  // zeroed with the plan words
+      kdp.hitHead = h->kdHitHead.as<uint32_t>();
+    }
     k_doublets_kd<false><<<h->smCount * h->kdBlocksPerSM[0], kKdThreads, 0, s>>>(kdp);
   } else {
     k_doublets<false><<<h->smCount * h->doubletBlocksPerSM[0], kDoubletWarps * 32, 0, s>>>(dp);
@@ -1159,6 +1170,7 @@ static int create_impl(const b200seed_config* cfg, const b200seed_orthogonal_opt
   CREATE_TRY(cudaEventCreateWithFlags(&h->evPlan, cudaEventDisableTiming));
   h->chunkStreams = env_u32("B200SEED_CHUNK_STREAMS", 2) >= 2 ? 2 : 1;
   h->kdHostBuild = env_u32("B200SEED_KD_HOST", 0) != 0;
+  h->kdHitMB = env_u32("B200SEED_KD_HIT_MB", 4096);
   h->maskWordsPerSp = env_u32("B200SEED_MASK_WORDS_PER_SP", 192);
   h->classStreams = env_u32("B200SEED_CLASS_STREAMS", 1) != 0 ? 1 : 0;
   for (int a = 0; a < 2; ++a) {
@@ -1261,7 +1273,7 @@ void b200seed_destroy(b200seed_handle* h) {
                     &h->binStart, &h->binCursor, &h->tmpIdx, &h->pIdx, &h->pXY, &h->pZR, &h->pVar,
                     &h->sortScratch, &h->midLo, &h->midCount, &h->workStart, &h->workPos, &h->workEG,
                     &h->workCounter, &h->capB, &h->capT, &h->slotPrefix, &h->capTileSums, &h->capTilePrefix, &h->planDev,
-                    &h->hdr, &h->carve, &h->classList, &h->maskArena, &h->maskOff, &h->inStrip, &h->pStrip, &h->arenaRec[0], &h->arenaRec[1], &h->arenaKey[0], &h->arenaKey[1], &h->spillScratch,
+                    &h->hdr, &h->carve, &h->classList, &h->maskArena, &h->maskOff, &h->inStrip, &h->pStrip, &h->kdHitArena, &h->kdHitHead, &h->arenaRec[0], &h->arenaRec[1], &h->arenaKey[0], &h->arenaKey[1], &h->spillScratch,
                     &h->zWinOffsets, &h->slotB, &h->slotM, &h->slotT, &h->slotQ, &h->slotZ, &h->slotCount,
                     &h->seedStart, &h->tileSums, &h->tilePrefix, &h->outB, &h->outM, &h->outT, &h->outQ,
                     &h->outZ, &h->seedOffsets, &h->counters, &h->status, &h->zWin, &h->rec, &h->recZ, &h->recBegin,

@@ -1115,3 +1115,23 @@ def test_verbatim_itk_strip_configuration(plugin, O, name, mu, ids):
         assert ref["quality"].size > 500
         assert _same_bits(got, ref), (name, i, "strip path")
     eng.close()
+
+
+@pytest.mark.parametrize("mb", ["0", "1"])
+def test_orthogonal_hit_list_arena_off_or_full(plugin, O, monkeypatch, mb):
+    """The count pass of the orthogonal seeder hands the survivor positions of every tree walk to the fill pass
+    (B200SEED_KD_HIT_MB, default 4096).  Off (0) and nearly always full (1 MB): a walk whose list did not fit is
+    searched again by the fill pass -- same seeds in the same order."""
+    from acts_b200 import config, events
+
+    monkeypatch.setenv("B200SEED_KD_HIT_MB", mb)
+    ocfg, oopt = config.orthogonal_config(plugin.orthogonal_config_init)
+    eng = plugin.SeedingEngine(ocfg, orthogonal=oopt)
+    orc = O.Oracle(*config.orthogonal_config(O.orthogonal_config_init))
+    evs = [events.pileup_event(i, mu=m) for i, m in ((0, 30), (1, 60))]
+    for ev in evs:
+        assert _same_bits(eng.run(ev), orc.run(ev))
+    cols, offsets = events.concat_events(evs)
+    for got, ev in zip(eng.run_batch(cols, offsets), evs):
+        assert _same_bits(got, orc.run(ev))
+    eng.close()
