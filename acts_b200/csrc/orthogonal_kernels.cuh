@@ -574,6 +574,8 @@ __global__ void __launch_bounds__(kKdThreads) k_doublets_kd(const __grid_constan
                 p.hdr[w] = h;
                 p.slotCount[w] = 0;
                 live = false;  // stays idle: takes another item in the next round
+              } else if (kp.hitPages != 0u && kp.hitHead[2ull * w] != kKdHitNone && kp.hitHead[2ull * w + 1u] != kKdHitNone) {
+                live = false;  // both walks left their hit lists: k_doublets_kd_lists fills this item
               }
             }
             if (live) {
@@ -738,6 +740,110 @@ __global__ void __launch_bounds__(kKdThreads) k_doublets_kd(const __grid_constan
       if (cntB != 0ull) atomicAdd(p.counters + kCntBottomDoublets, cntB);
       if (cntT != 0ull) atomicAdd(p.counters + kCntTopDoublets, cntT);
     }
+  }
+}
+
+// Fill pass of the items whose two tree walks left hit lists (KdDoubletParams::hitHead): one WARP per item reads a
+// page of the list with one coalesced request (31 positions + the link), gathers the space points, finishes the
+// doublets and writes the survivors compacted in list order -- the arena slot, header, carve-up and class list are
+// those of k_doublets_kd<true>, which keeps the items without lists.  ticket: a work counter of its own.
+constexpr int kKdListWarps = 8;
+__global__ void __launch_bounds__(kKdListWarps * 32) k_doublets_kd_lists(const __grid_constant__ KdDoubletParams kp, uint32_t* ticket) {
+  const DoubletParams& p = kp.d;
+  const DeviceConfig& cfg = p.cfg;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t ltMask = (1u << lane) - 1u;
+  const uint32_t nItems = p.itemEnd - p.itemFirst;
+  unsigned long long cntB = 0, cntT = 0;  // lane 0
+  auto side = [&](bool bottom, const MiddleSp& mid, uint32_t page, DoubletRecord* recOut, float* keyOut, float& cotMin, float& cotMax) -> uint32_t {
+    uint32_t n = 0;
+    float mn = 3.0e38f, mx = -3.0e38f;
+    for (;;) {
+      const uint32_t v = __ldg(kp.hitArena + 32ull * page + lane);
+      const uint32_t link = __shfl_sync(0xffffffffu, v, 31);
+      const uint32_t endMask = __ballot_sync(0xffffffffu, lane < 31u && v == kKdHitEnd);
+      const uint32_t nValid = endMask != 0u ? (uint32_t)(__ffs(endMask) - 1) : 31u;
+      bool ok = false;
+      DoubletRec rec;
+      if (lane < nValid) {
+        const float2 zr = ldg2(p.pZR + v), xy = ldg2(p.pXY + v), var = ldg2(p.pVar + v);
+        float dR, dZ;
+        doublet_zr_cuts_side(bottom, cfg, mid, zr.x, zr.y, dR, dZ);  // (a hit passed them in the count pass: dR, dZ)
+        ok = doublet_finish_side(bottom, cfg, mid, dR, dZ, xy.x, xy.y, zr.y, var.x, var.y, nullptr, nullptr, 0, rec, true);
+      }
+      const uint32_t mask = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const uint32_t d = n + (uint32_t)__popc(mask & ltMask);
+        float4* dst = reinterpret_cast<float4*>(recOut + d);
+        dst[0] = make_float4(__uint_as_float(v), rec.cotTheta, rec.iDeltaR, rec.er);
+        dst[1] = make_float4(rec.u, rec.v, rec.xNew, rec.yNew);
+        keyOut[d] = rec.cotTheta;
+        mn = fminf(mn, rec.cotTheta);
+        mx = fmaxf(mx, rec.cotTheta);
+      }
+      n += (uint32_t)__popc(mask);
+      if (endMask != 0u) break;
+      page = link;
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    }
+    cotMin = mn;
+    cotMax = mx;
+    return n;
+  };
+  for (;;) {
+    uint32_t it = 0;
+    if (lane == 0) it = atomicAdd(ticket, 1u);
+    it = __shfl_sync(0xffffffffu, it, 0);
+    if (it >= nItems) break;
+    const uint32_t w = p.itemFirst + it;
+    const uint32_t capT = __ldg(p.capT + w), capB = __ldg(p.capB + w);
+    if (capT == 0u || capB == 0u) continue;  // (k_doublets_kd<true> writes the empty header)
+    const uint32_t headT = kp.hitHead[2ull * w], headB = kp.hitHead[2ull * w + 1u];
+    if (headT == kKdHitNone || headB == kKdHitNone) continue;  // (k_doublets_kd<true> walks the tree again)
+    const uint32_t m = __ldg(p.workPos + w);
+    MiddleSp mid;
+    {
+      const float2 mxy = ldg2(p.pXY + m), mzr = ldg2(p.pZR + m), mvar = ldg2(p.pVar + m);
+      mid.x = mxy.x; mid.y = mxy.y; mid.z = mzr.x; mid.r = mzr.y; mid.varZ = mvar.x; mid.varR = mvar.y;
+      middle_info(mid);
+    }
+    const unsigned long long slot = p.slotPrefix[w] - p.slotPrefix[p.itemFirst];
+    DoubletRecord* recSlot = p.rec + slot;
+    float* keySlot = p.key + slot;
+    float mnT, mxT, mnB = 0.f, mxB = 0.f;
+    uint32_t nTop = side(false, mid, headT, recSlot + capB, keySlot + capB, mnT, mxT);
+    bool go = nTop != 0u;
+    if (go && p.conf) go = !(nTop < conf_n_top(conf_range(cfg, mid.z), mid.r));  // BroadTripletSeedFilter.cpp:63-94
+    uint32_t nB = 0;
+    if (go) nB = side(true, mid, headB, recSlot, keySlot, mnB, mxB);
+    go = go && nB != 0u;
+    if (lane == 0) {  // header, carve-up, class list: as k_doublets_kd<true>::finishFill
+      MiddleHeader h{};
+      h.capB = capB;
+      h.offset = (uint32_t)slot;
+      if (go) {
+        h.nB = nB; h.nT = nTop;
+        h.cotMinB = float_to_ordered(mnB); h.cotMaxB = float_to_ordered(mxB);
+        h.cotMinT = float_to_ordered(mnT); h.cotMaxT = float_to_ordered(mxT);
+        const SeedCarve cv = seed_carve(nB, nTop);
+        p.carve[w] = cv;
+        int c = 0;
+        while (c < kSpillClass && cv.minBytes > p.classBytes[c]) ++c;
+        p.classList[(size_t)c * p.classStride + atomicAdd(p.classCount + c, 1u)] = w;
+        cntB += nB;
+        cntT += nTop;
+      } else {
+        p.slotCount[w] = 0;
+      }
+      p.hdr[w] = h;
+    }
+  }
+  if (lane == 0) {
+    if (cntB != 0ull) atomicAdd(p.counters + kCntBottomDoublets, cntB);
+    if (cntT != 0ull) atomicAdd(p.counters + kCntTopDoublets, cntT);
   }
 }
 

@@ -856,6 +856,10 @@ int enqueue(b200seed_handle* h) {
     if (orthogonal) {
       KdDoubletParams kdc = kdp;
       kdc.d = dpc;
+      if (kdc.hitPages != 0u) {  // items whose walks left hit lists: one warp per item, no tree walk (cw[8]: its ticket)
+        k_doublets_kd_lists<<<h->smCount * 4, kKdListWarps * 32, 0, cs>>>(kdc, cw + 8);
+        ++launches;
+      }
       k_doublets_kd<true><<<h->smCount * h->kdBlocksPerSM[1], kKdThreads, 0, cs>>>(kdc);
     } else {
       k_doublets<true><<<h->smCount * h->doubletBlocksPerSM[1], kDoubletWarps * 32, 0, cs>>>(dpc);
