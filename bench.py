@@ -389,6 +389,8 @@ def run_gpu(args):
     cap_ev = max(ev["x"].size for ev in evs) * K
     h2d_ev = int(np.mean([ev["x"].size for ev in evs])) * 24
 
+    largest = sorted(range(len(ev_pinned)), key=lambda i: -ev_pinned[i]["x"].size)
+
     def e2e_per_event(n_thr, n_calls):
         engines = [plugin.SeedingEngine(cfg, device=local) for _ in range(n_thr)]
         outs = [pinned_seed_columns(cap_ev) for _ in range(n_thr)]
@@ -398,9 +400,11 @@ def run_gpu(args):
 
         def worker(t, limit):
             torch.cuda.set_device(local)
-            if limit is None:  # warm-up: two calls on THIS thread's handle (the dynamic queue could starve a handle and leave its allocations to the timed region)
-                for j in range(2):
-                    engines[t].run(ev_pinned[(2 * t + j) % len(ev_pinned)], out=outs[t][1])
+            if limit is None:
+                # warm-up: THIS thread's handle seeds the two largest events (the dynamic queue could starve a handle and
+                # leave its allocations to the timed region; workspaces grow with the largest event seen)
+                for i in largest[:2]:
+                    engines[t].run(ev_pinned[i], out=outs[t][1])
                 return
             while True:
                 with lock:  # dynamic event queue, like tbb::parallel_for over the events
