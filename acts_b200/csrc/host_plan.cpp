@@ -25,37 +25,30 @@ float sq(float v) { return v * v; }
 // Acts::fastCathetus(h, 1) with an int argument (MathHelpers.hpp:86-103,177-180)
 float cathetusOne(float h) { return std::sqrt((h - 1) * (h + 1)); }
 
-// SpacePointGridPhiBinning.cpp:20-95
+// Number of phi bins of the grid: the arithmetic of SpacePointGridPhiBinning.cpp:20-95 (same operations, same
+// float / double types), condensed -- the azimuth a minimum-pT helix sweeps between (rMax - deltaRMax) and rMax plus
+// the spread an impact parameter of impactMax adds, divided by phiBinDeflectionCoverage, is one bin width.
 int phiBinCount(const b200seed_config& c) {
-  if (c.bFieldInZ == 0) {
-    return c.maxPhiBins;
+  if (c.bFieldInZ == 0) return c.maxPhiBins;
+  const float helixR = c.minPt / c.bFieldInZ;
+  if (helixR < c.rMax * 0.5) {
+    throw Fail{B200SEED_ERR_DOMAIN, "phi binning: the minimum-pT helix (minPt / bFieldInZ) does not reach rMax"};
   }
-  const float minHelixRadius = c.minPt / c.bFieldInZ;
-  if (minHelixRadius < c.rMax * 0.5) {
-    throw Fail{B200SEED_ERR_DOMAIN,
-               "The value of minHelixRadius cannot be smaller than rMax / 2. "
-               "Please check the configuration of bFieldInZ and minPt"};
-  }
-  const float outerAngle = std::atan(1.f / cathetusOne(2 * minHelixRadius / c.rMax));
-  float innerAngle = 0;
-  float rMin = c.rMax;
+  auto sweep = [&](float radius) { return std::atan(1.f / cathetusOne(2 * helixR / radius)); };
+  const float sweepOuter = sweep(c.rMax);
+  float sweepInner = 0;
+  float innerR = c.rMax;
   if (c.rMax > c.deltaRMax) {
-    const float innerCircleR = c.rMax - c.deltaRMax;
-    rMin = innerCircleR;
-    innerAngle = std::atan(1.f / cathetusOne(2 * minHelixRadius / innerCircleR));
+    const float r0 = c.rMax - c.deltaRMax;
+    innerR = r0;
+    sweepInner = sweep(r0);
   }
-  const float sinInner = std::min(1.f, c.impactMax / rMin);
-  const float sinOuter = std::min(1.f, c.impactMax / c.rMax);
-  const float deltaAngleWithMaxD0 = std::abs(std::asin(sinInner) - std::asin(sinOuter));
-  const float deltaPhi =
-      (outerAngle - innerAngle + deltaAngleWithMaxD0) / c.phiBinDeflectionCoverage;
-  if (deltaPhi <= 0.f) {
-    throw Fail{B200SEED_ERR_DOMAIN,
-               "Delta phi value is equal to or less than zero, leading to an "
-               "impossible number of bins (negative or infinite)"};
+  const float impactSpread = std::abs(std::asin(std::min(1.f, c.impactMax / innerR)) - std::asin(std::min(1.f, c.impactMax / c.rMax)));
+  const float binWidth = (sweepOuter - sweepInner + impactSpread) / c.phiBinDeflectionCoverage;
+  if (binWidth <= 0.f) {
+    throw Fail{B200SEED_ERR_DOMAIN, "phi binning: non-positive bin width (check rMax, deltaRMax, impactMax, phiBinDeflectionCoverage)"};
   }
-  const int phiBins = static_cast<int>(std::ceil(2 * std::numbers::pi / deltaPhi));
-  return std::min(phiBins, c.maxPhiBins);
+  return std::min(static_cast<int>(std::ceil(2 * std::numbers::pi / binWidth)), c.maxPhiBins);
 }
 
 int wrapClosed(int bin, int w) { return 1 + (w + ((bin - 1) % w)) % w; }

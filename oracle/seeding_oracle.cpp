@@ -89,8 +89,7 @@ int computePhiBins(float minPt, float bFieldInZ, float rMax, float deltaRMax,
   const float minHelixRadius = minPt / bFieldInZ;
   if (minHelixRadius < rMax * 0.5) {
     throw std::domain_error(
-        "The value of minHelixRadius cannot be smaller than rMax / 2. Please "
-        "check the configuration of bFieldInZ and minPt");
+        "phi binning: minimum-pT helix radius below rMax / 2");
   }
   const float outerAngle =
       std::atan(1.f / fastCathetusOne(2 * minHelixRadius / rMax));
@@ -110,8 +109,7 @@ int computePhiBins(float minPt, float bFieldInZ, float rMax, float deltaRMax,
                          phiBinDeflectionCoverage;
   if (deltaPhi <= 0.f) {
     throw std::domain_error(
-        "Delta phi value is equal to or less than zero, leading to an "
-        "impossible number of bins (negative or infinite)");
+        "phi binning: bin width <= 0");
   }
   const int phiBins =
       static_cast<int>(std::ceil(2 * std::numbers::pi / deltaPhi));
