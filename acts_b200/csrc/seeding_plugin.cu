@@ -734,7 +734,11 @@ int enqueue(b200seed_handle* h) {
     kdp.d = dp;
     if (h->kdHitMB != 0u) {
       const size_t bytes = (size_t)h->kdHitMB << 20;
-      CUDA_TRY(h->kdHitArena.reserve(bytes));
+      if (h->kdHitArena.bytes < bytes) {
+        // (zeroed once: the list kernel reads whole pages, i.e. also the words behind the end mark of a walk's last page)
+        CUDA_TRY(h->kdHitArena.reserve(bytes));
+        CUDA_TRY(cudaMemsetAsync(h->kdHitArena.ptr, 0, h->kdHitArena.bytes, s));
+      }
       CUDA_TRY(h->kdHitHead.reserve((size_t)nWorkMax * 8));
       kdp.hitArena = h->kdHitArena.as<uint32_t>();
       kdp.hitPages = (uint32_t)std::min<size_t>(bytes / 128, 0xFFFFFFF0u);
