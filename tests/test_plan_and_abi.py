@@ -56,6 +56,38 @@ def test_plan_matches_oracle_derivation(plugin, O, name):
         assert getattr(pi, f) == getattr(oi, f), f
 
 
+def test_plan_matches_oracle_on_random_cut_sets(plugin, O):
+    """The host plan (phi bin count of SpacePointGridPhiBinning.cpp:20-95, derived finder constants) against the
+    oracle's derivation over random minPt / bField / rMax / deltaRMax / impactMax / coverage -- including the
+    combinations both refuse, with the same status code."""
+    from acts_b200 import config as cm
+
+    rng = np.random.default_rng(424242)
+    accepted = refused = 0
+    for _ in range(400):
+        over = dict(minPt=float(rng.choice([0.1, 0.4, 0.5, 0.9, 2.0, 10.0])), bFieldInZ=float(rng.choice([0.0, 1.0, 2.0, 3.8])) * cm.T,
+                    rMax=float(rng.choice([100.0, 200.0, 320.0, 1200.0])), deltaRMax=float(rng.choice([60.0, 150.0, 280.0, 600.0])),
+                    impactMax=float(rng.choice([0.5, 3.0, 20.0, 150.0])), phiBinDeflectionCoverage=int(rng.choice([1, 2, 3, 5])),
+                    maxPhiBins=int(rng.choice([20, 200, 10000])), sigmaScattering=float(rng.choice([2.0, 5.0])),
+                    radLengthPerSeed=float(rng.choice([0.05, 0.1])))
+        try:
+            want = O.Oracle(make_config("pu200", O.config_init).update(**over)).info()
+        except O.OracleError as e:
+            with pytest.raises(plugin.SeedingError) as ei:
+                plugin.plan_info(make_config("pu200", plugin.config_init).update(**over))
+            assert ei.value.code == e.code, over
+            refused += 1
+            continue
+        got = plugin.plan_info(make_config("pu200", plugin.config_init).update(**over))
+        for f in ("phiBins", "zBins", "rBins", "nGlobalBins"):
+            assert getattr(got, f) == getattr(want, f), (f, over)
+        for f in ("minHelixDiameter2", "highland", "sigmapT2perRadius", "multipleScattering2"):
+            a, b = np.float32(getattr(got, f)), np.float32(getattr(want, f))
+            assert a.view(np.uint32) == b.view(np.uint32) or (np.isnan(a) and np.isnan(b)), (f, over)
+        accepted += 1
+    assert accepted > 100 and refused > 10
+
+
 @pytest.mark.parametrize("name", CONFIGS)
 def test_neighbour_tables_match_oracle(plugin, O, name):
     cfg = make_config(name, plugin.config_init)
