@@ -73,6 +73,10 @@ struct ConfMiddle {
   std::vector<ConfRecord> rec;
 };
 
+// Strip triplet path (k_seed_middles<..., kStrip>): set by model_set_strips, NULL = pixel path
+static const float* gStrip = nullptr;  // 12 floats per ORIGINAL space point
+static float gCotThetaDiffMax2 = 0.f, gToleranceParam = 1.1f;
+
 // One middle space point, restructured algorithm.  tieMode: 0 canonical
 // (key, seq) order, 1 replay libstdc++ std::sort from the emission order.
 void processMiddle(const DeviceConfig& c, const Packed& p, uint32_t m, uint32_t firstMiddleInBin,
@@ -228,6 +232,26 @@ void processMiddle(const DeviceConfig& c, const Packed& p, uint32_t m, uint32_t 
       run = std::max(run, H[j]);
     }
   }
+  // --- strip path: the window of a bottom is the run of tops inside the cot(theta) pre-filter (device: kStrip scan)
+  StripDerived calM{};
+  float cosPhiM = 0.f, sinPhiM = 0.f;
+  if (gStrip != nullptr) {
+    strip_derive(gStrip + 12ull * p.copiedFrom[m], calM);
+    cosPhiM = fdiv(mid.x, mid.r);
+    sinPhiM = fdiv(mid.y, mid.r);
+    for (int j = 0; j < nB; ++j) {
+      const float cB = bottoms[j].rec.cotTheta;
+      int lo = 0, hi = nT;
+      while (lo < hi) {
+        const int md = (lo + hi) >> 1;
+        if (strip_outside_window(cB, tops[md].rec.cotTheta, gCotThetaDiffMax2) && !(cB < tops[md].rec.cotTheta)) lo = md + 1; else hi = md;
+      }
+      int k = lo;
+      while (k < nT && !(strip_outside_window(cB, tops[k].rec.cotTheta, gCotThetaDiffMax2) && cB < tops[k].rec.cotTheta)) ++k;
+      start[j] = lo;
+      brk[j] = k;
+    }
+  }
 
   // --- candidates, filter, bounded heap -------------------------------------
   if (c.seedConfirmation) conf->push_back({m, {}});
@@ -244,9 +268,22 @@ void processMiddle(const DeviceConfig& c, const Packed& p, uint32_t m, uint32_t 
     for (int t = start[j]; t < brk[j]; ++t) {
       const DoubletRec& T = tops[t].rec;
       float cu, im;
+      if (gStrip != nullptr) {
+        if (strip_outside_window(bottoms[j].rec.cotTheta, T.cotTheta, gCotThetaDiffMax2)) continue;  // (cannot happen inside the window)
+        stats[2]++;
+        StripBottomCtx sb;
+        const DoubletRec& Br = bottoms[j].rec;
+        sb.cotThetaB0 = Br.cotTheta; sb.iDeltaRB = Br.iDeltaR; sb.erB = Br.er; sb.Ub0 = Br.u; sb.Vb0 = Br.v; sb.xB = Br.xNew; sb.yB = Br.yNew;
+        strip_bottom_ctx(c, cosPhiM, sinPhiM, sb);
+        StripDerived calB, calT;
+        strip_derive(gStrip + 12ull * p.copiedFrom[bottoms[j].pos], calB);
+        strip_derive(gStrip + 12ull * p.copiedFrom[tops[t].pos], calT);
+        if (!eval_strip_pair(c, gToleranceParam, mid.varZ, mid.varR, sb, calM, calB, calT, T.er, T.iDeltaR, T.u, T.v, T.xNew, T.yNew, cu, im)) continue;
+      } else {
       stats[2]++;
       const int cls = eval_pair(c, mid.r, mid.varZ, mid.varR, b, T.cotTheta, T.er, T.iDeltaR, T.u, T.v, cu, im);
       if (cls != kPairEmit) continue;
+      }
       const uint32_t tp = tops[t].pos;
       float topR = p.r[tp];
       if (c.useDeltaRinsteadOfTopRadius) {
@@ -485,6 +522,13 @@ int64_t model_run(const DeviceConfig* cfg, const uint32_t* copiedFrom, const flo
     }
   }
   return (int64_t)out.size();
+}
+
+// strip triplet path for the next model_run calls (strip = NULL: back to the pixel path)
+void model_set_strips(const float* strip, float cotThetaDiffMax, float toleranceParam) {
+  gStrip = strip;
+  gCotThetaDiffMax2 = cotThetaDiffMax * cotThetaDiffMax;
+  gToleranceParam = toleranceParam;
 }
 
 // grid stage of the model: bin index with the replayed atan2f, per-SP
@@ -847,6 +891,69 @@ int64_t model_check_partition_pairing(uint64_t seed, int maxN, int trials) {
     const int nMis = (int)listL.size();
     for (int k = 0; k < nMis; ++k) std::swap(a[listL[k]], a[listR[nMis - 1 - k]]);
     for (int i = 0; i < n; ++i) bad += (a[i] != ref[i]) ? 1 : 0;
+  }
+  return bad;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Strip triplet path (k_seed_middles<..., kStrip>): the device evaluates, for every bottom on its own, the run of
+// sorted tops that starts at the first top which is not "outside the cot(theta) window and at or below the bottom"
+// (binary search) and ends before the first top that is outside and above.  The reference
+// (TripletSeedFinder.cpp:214-238,397-403) walks the tops sequentially, drops the tops below the window for all later
+// bottoms (subrange) and stops the loop of a bottom at the first top above it.  Both must enumerate the same
+// (bottom, top) pairs in the same order -- checked here on random sorted lists (ties, +-inf windows, empty lists).
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int64_t model_check_strip_window(uint64_t seed, int maxN, int trials) {
+  std::mt19937_64 rng(seed);
+  int64_t bad = 0;
+  for (int t = 0; t < trials; ++t) {
+    const int nB = (int)(rng() % (uint64_t)(maxN + 1)), nT = (int)(rng() % (uint64_t)(maxN + 1));
+    const int mode = (int)(rng() % 4);
+    auto draw = [&]() { return mode == 2 ? (float)(rng() % 7u) * 0.25f : (float)((double)(rng() % 2000001u) * 1e-5 - 10.0); };
+    std::vector<float> cotB(nB), cotT(nT);
+    for (float& v : cotB) v = draw();
+    for (float& v : cotT) v = draw();
+    std::sort(cotB.begin(), cotB.end());
+    std::sort(cotT.begin(), cotT.end());
+    const float diffMax = mode == 0 ? std::numeric_limits<float>::infinity() : (mode == 1 ? 0.0f : (float)(rng() % 400u) * 0.01f);
+    const float diffMax2 = diffMax * diffMax;
+    // the reference's sequential form
+    std::vector<std::pair<int, int>> ref, dev;
+    std::size_t begin = 0;
+    for (int j = 0; j < nB; ++j) {
+      if (begin == (std::size_t)nT) break;  // TripletSeeder.cpp:29-31
+      std::size_t offset = 0;
+      for (std::size_t k = begin; k < (std::size_t)nT; ++k) {
+        const float d = cotB[j] - cotT[k];
+        if (d * d > diffMax2) {
+          if (cotB[j] < cotT[k]) break;
+          offset = k - begin + 1;
+          continue;
+        }
+        ref.emplace_back(j, (int)k);
+      }
+      begin += offset;
+    }
+    // the device form (seeding_kernels.cuh, kStrip scan; strip_outside_window of seed_math.h)
+    for (int j = 0; j < nB; ++j) {
+      uint32_t lo = 0, hi = (uint32_t)nT;
+      while (lo < hi) {
+        const uint32_t md = (lo + hi) >> 1;
+        if (strip_outside_window(cotB[j], cotT[md], diffMax2) && !(cotB[j] < cotT[md])) lo = md + 1; else hi = md;
+      }
+      for (uint32_t k = lo; k < (uint32_t)nT; ++k) {
+        if (strip_outside_window(cotB[j], cotT[k], diffMax2)) {
+          if (cotB[j] < cotT[k]) break;
+          continue;
+        }
+        dev.emplace_back(j, (int)k);
+      }
+    }
+    bad += ref == dev ? 0 : 1;
   }
   return bad;
 }

@@ -35,6 +35,8 @@ def lib():
         L.model_check_atan2f.argtypes = [C.c_uint64, C.c_int64]
         L.model_check_atan2f.restype = C.c_int64
         L.model_sizeof_device_config.restype = C.c_uint64
+        L.model_set_strips.argtypes = [vp, C.c_float, C.c_float]
+        L.model_set_strips.restype = None
         _lib = L
     return _lib
 
@@ -74,8 +76,9 @@ def radius_ranges(cfg, tables, grid):
     return lo, hi
 
 
-def run(cfg, grid: dict, tie_mode: int = 0, z_windows=None) -> dict:
-    """Run the restructured algorithm on a packed grid (dict like Oracle.run()['grid'])."""
+def run(cfg, grid: dict, tie_mode: int = 0, z_windows=None, strip=None, cot_theta_diff_max=float("inf")) -> dict:
+    """Run the restructured algorithm on a packed grid (dict like Oracle.run()['grid']).
+    ``strip`` ((n, 12) float32, per ORIGINAL space point): the strip triplet path with ``cot_theta_diff_max``."""
     t = plugin.plan_tables(cfg)
     dc = t["deviceConfig"].copy()
     assert dc.size == lib().model_sizeof_device_config()
@@ -87,11 +90,16 @@ def run(cfg, grid: dict, tie_mode: int = 0, z_windows=None) -> dict:
     ob, om, ot = (np.zeros(cap, np.uint32) for _ in range(3))
     oq, oz = (np.zeros(cap, np.float32) for _ in range(2))
     stats = np.zeros(8, np.uint64)
+    if strip is not None:
+        strip = np.ascontiguousarray(strip, dtype=np.float32)
+        lib().model_set_strips(_p(strip), float(cot_theta_diff_max), float(cfg.toleranceParam))
     n = lib().model_run(_p(dc), _p(grid["copiedFromIndex"]), _p(grid["x"]), _p(grid["y"]), _p(grid["z"]), _p(grid["r"]),
                         _p(grid["varZ"]), _p(grid["varR"]), _p(grid["binBegin"]), _p(grid["binEnd"]),
                         t["navBins"].size, _p(t["navBins"]), _p(lo), _p(hi), _p(t["botOffsets"]), _p(t["botBins"]),
                         _p(t["topOffsets"]), _p(t["topBins"]), 0, None, None, tie_mode, cap,
                         _p(ob), _p(om), _p(ot), _p(oq), _p(oz), _p(stats))
+    if strip is not None:
+        lib().model_set_strips(None, 0.0, 1.1)
     assert 0 <= n <= cap
     return {"bottom": ob[:n], "middle": om[:n], "top": ot[:n], "quality": oq[:n], "vertexZ": oz[:n],
             "stats": {"nBottomDoublets": int(stats[0]), "nTopDoublets": int(stats[1]),

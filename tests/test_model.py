@@ -133,3 +133,38 @@ def test_partition_rank_pairing_equals_std_partition(env):
     assert L.model_check_partition_pairing(1, 40, 20000) == 0
     assert L.model_check_partition_pairing(2, 3000, 2000) == 0
     assert L.model_check_partition_pairing(3, 200000, 20) == 0
+
+
+def test_strip_window_per_bottom_equals_the_sequential_subrange_walk(env):
+    """Strip triplet path: the device finds every bottom's cot(theta) window on its own (binary search + scan); the
+    reference advances one shared subrange through the bottoms (TripletSeedFinder.cpp:226-238,397-403).  Same pairs,
+    same order -- random sorted lists with ties, cotThetaDiffMax = inf / 0 / finite."""
+    import ctypes as C
+
+    L = env[3].lib()
+    L.model_check_strip_window.restype = C.c_int64
+    L.model_check_strip_window.argtypes = [C.c_uint64, C.c_int, C.c_int]
+    assert L.model_check_strip_window(1, 12, 200000) == 0
+    assert L.model_check_strip_window(2, 300, 3000) == 0
+
+
+@pytest.mark.parametrize("name,over", [("pu200", {}), ("seeding_py", {}), ("pu200", dict(toleranceParam=0.6)),
+                                       ("itk_conf", {})])
+def test_model_strip_triplet_path_equals_oracle(env, name, over):
+    """The device formulation of the strip triplet path -- per-bottom cot(theta) windows, eval_strip_pair /
+    strip_calibrate / strip_derive of seed_math.h compiled for the host -- against the oracle's restatement of
+    createStripTripletTopCandidates (itself pinned to the reference, tests/test_reference_pin.py)."""
+    events, plugin, O, M = env
+    cfg = make_config(name, plugin.config_init).update(**over)
+    orc = O.Oracle(make_config(name, O.config_init).update(**over))
+    for i, mu in ((0, 10), (2, 30)):
+        ev = dict(events.muon_gun_event(i) if name == "seeding_py" else events.pileup_event(i, mu=mu))
+        ev["strip"] = events.strip_details(ev, seed=i)
+        grid = orc.run(ev, want_grid=True)["grid"]
+        for diff in (float("inf"), 0.3, 0.05):
+            ref = orc.run(ev, strip_cot_theta_diff_max=diff)
+            got = M.run(cfg, grid, tie_mode=2, strip=ev["strip"], cot_theta_diff_max=diff)
+            for k in KEYS:
+                assert np.array_equal(got[k].view(np.uint32), ref[k].view(np.uint32)), (name, i, diff, k)
+            assert got["stats"]["nTripletTests"] == ref["counters"]["nTripletTests"]
+            assert got["stats"]["nCandidates"] == ref["counters"]["nCandidates"]
