@@ -959,3 +959,57 @@ int64_t model_check_strip_window(uint64_t seed, int maxN, int trials) {
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Phase 3f of k_seed_middles keeps only the nUse + 1 = min(nLow, maxSeedsPerSpM + 1) + 1 largest weights in registers and
+// replays the literal bounded heap (capacity nLow, CandidatesForMiddleSp.cpp:44-93) only when two of them are equal.
+// Claim checked here: whenever the nUse + 1 largest weights differ, the first nUse entries of the sort_heap'ed
+// collector are the nUse largest weights in descending order -- for any nLow >= nUse, any push order, any ties below.
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int64_t model_check_topk_claim(uint64_t seed, int trials) {
+  std::mt19937_64 rng(seed);
+  int64_t bad = 0, exercised = 0;
+  for (int t = 0; t < trials; ++t) {
+    const int n = (int)(rng() % 400u);
+    const int nLow = 1 + (int)(rng() % 128u);
+    const int maxSeeds = (int)(rng() % 8u);
+    const int nUse = std::min(nLow, maxSeeds + 1);
+    const uint32_t levels = 1u + (uint32_t)(rng() % (t % 3 == 0 ? 12u : 100000u));  // few levels: many equal weights
+    std::vector<float> w(n);
+    for (float& v : w) v = (float)(rng() % levels) * 0.5f;
+    // literal collector
+    std::vector<WeightIndex> heap;
+    std::vector<float> storage;
+    for (int i = 0; i < n; ++i) {
+      if ((int)heap.size() < nLow) {
+        storage.push_back(w[i]);
+        heap.push_back({w[i], (uint32_t)storage.size() - 1});
+        std_push_heap(heap.data(), (int)heap.size(), heap_comp);
+        continue;
+      }
+      const WeightIndex smallest = heap[0];
+      if (w[i] <= smallest.weight) continue;
+      storage[smallest.index] = w[i];
+      std_pop_heap(heap.data(), (int)heap.size(), heap_comp);
+      heap.back() = {w[i], smallest.index};
+      std_push_heap(heap.data(), (int)heap.size(), heap_comp);
+    }
+    std_sort_heap(heap.data(), (int)heap.size(), heap_comp);
+    // the register selection: nUse + 1 largest, stable in arrival order
+    std::vector<float> top(w);
+    std::stable_sort(top.begin(), top.end(), [](float a, float b) { return a > b; });
+    const int keep = std::min<int>(nUse + 1, n);
+    bool distinct = true;
+    for (int i = 0; i + 1 < keep; ++i) distinct &= top[i] != top[i + 1];
+    if (!distinct) continue;  // the device runs the literal replay here
+    ++exercised;
+    const int nOut = std::min<int>((int)heap.size(), maxSeeds + 1);
+    if (nOut != std::min(n, nUse)) { ++bad; continue; }
+    for (int i = 0; i < nOut; ++i) bad += heap[i].weight != top[i] ? 1 : 0;
+  }
+  return exercised > trials / 10 ? bad : -1;
+}
+
+}  // extern "C"

@@ -168,3 +168,14 @@ def test_model_strip_triplet_path_equals_oracle(env, name, over):
                 assert np.array_equal(got[k].view(np.uint32), ref[k].view(np.uint32)), (name, i, diff, k)
             assert got["stats"]["nTripletTests"] == ref["counters"]["nTripletTests"]
             assert got["stats"]["nCandidates"] == ref["counters"]["nCandidates"]
+
+
+def test_top_k_selection_claim_against_the_literal_collector(env):
+    """k_seed_middles keeps min(nLow, maxSeedsPerSpM + 1) + 1 weights and trusts them when they differ: the literal
+    bounded heap of any capacity nLow then returns the same first entries (random weights, heavy ties, nLow up to 128)."""
+    import ctypes as C
+
+    L = env[3].lib()
+    L.model_check_topk_claim.restype = C.c_int64
+    L.model_check_topk_claim.argtypes = [C.c_uint64, C.c_int]
+    assert L.model_check_topk_claim(5, 200000) == 0
