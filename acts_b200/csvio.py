@@ -77,7 +77,49 @@ def read_spacepoints(path: str) -> dict:
         raise ValueError(f"{path}: neither the SpacePointData nor the SpacePointData2 layout")
     if r is None or (n and not np.any(r)):
         r = np.sqrt(x.astype(np.float64) ** 2 + y.astype(np.float64) ** 2).astype(np.float32)
-    return {"x": x, "y": y, "z": z, "r": r, "varZ": var_z, "varR": var_r, "measurement_id": mid}
+    out = {"x": x, "y": y, "z": z, "r": r, "varZ": var_z, "varR": var_r, "measurement_id": mid}
+    if "sp_topStripCenterPosition_0" in col:
+        # the strip columns of the reader layout -> the StripCalibrationDetails column exactly like
+        # CsvSpacePointReader.cpp:80-110 (extendCollection): float columns, the half vectors formed in double
+        # (Acts::Vector3 * float) and narrowed to float
+        def vec(prefix):
+            return np.stack([column("%s_%d" % (prefix, k), np.float32) for k in range(3)], axis=1).astype(np.float64) \
+                if n else np.zeros((0, 3), np.float64)
+
+        top_len = column("sp_topHalfStripLength", np.float32).astype(np.float64)
+        bot_len = column("sp_bottomHalfStripLength", np.float32).astype(np.float64)
+        outer_center = vec("sp_topStripCenterPosition")
+        separation = vec("sp_stripCenterDistance")
+        outer_half = vec("sp_topStripDirection") * top_len[:, None]
+        inner_half = vec("sp_bottomStripDirection") * bot_len[:, None]
+        out["strip"] = np.ascontiguousarray(np.concatenate([outer_center, separation, outer_half, inner_half], axis=1), dtype=np.float32)
+    return out
+
+
+STRIP_READER_COLUMNS = ("measurement_id", "sp_x", "sp_y", "sp_z", "sp_radius", "sp_covr", "sp_covz",
+                        "sp_topHalfStripLength", "sp_bottomHalfStripLength",
+                        "sp_topStripDirection_0", "sp_topStripDirection_1", "sp_topStripDirection_2",
+                        "sp_bottomStripDirection_0", "sp_bottomStripDirection_1", "sp_bottomStripDirection_2",
+                        "sp_stripCenterDistance_0", "sp_stripCenterDistance_1", "sp_stripCenterDistance_2",
+                        "sp_topStripCenterPosition_0", "sp_topStripCenterPosition_1", "sp_topStripCenterPosition_2")
+
+
+def write_strip_spacepoints(path: str, sp: dict, measurement_id=None) -> None:
+    """Write one event of strip space points in the reader layout ``SpacePointData`` (CsvOutputData.hpp:347-383):
+    ``sp["strip"]`` ((n, 12): outerCenter, innerToOuterSeparation, outerHalfVector, innerHalfVector) goes out as
+    half lengths + unit directions + separation + outer centre, the columns CsvSpacePointReader.cpp:80-97 reads."""
+    n = sp["x"].size
+    ids = np.arange(n, dtype=np.uint64) if measurement_id is None else np.asarray(measurement_id, np.uint64)
+    d = np.asarray(sp["strip"], np.float32).reshape(n, 12).astype(np.float64)
+    with open(path, "w", newline="") as fh:
+        fh.write(",".join(STRIP_READER_COLUMNS) + "\n")
+        for i in range(n):
+            oc, sep, oh, ih = d[i, 0:3], d[i, 3:6], d[i, 6:9], d[i, 9:12]
+            lt, lb = float(np.linalg.norm(oh)), float(np.linalg.norm(ih))
+            dt = oh / lt if lt > 0 else oh
+            db = ih / lb if lb > 0 else ih
+            vals = [sp["x"][i], sp["y"][i], sp["z"][i], sp["r"][i], sp["varR"][i], sp["varZ"][i], lt, lb, *dt, *db, *sep, *oc]
+            fh.write("%d,%s\n" % (int(ids[i]), ",".join(_f32(v) for v in vals)))
 
 
 def write_spacepoints(path: str, sp: dict, measurement_id=None) -> None:

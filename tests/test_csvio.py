@@ -57,3 +57,29 @@ def test_seed_layout_round_trip(tmp_path):
         assert np.array_equal(back[k], seeds[k])
     for k in ("quality", "vertexZ"):
         assert np.array_equal(back[k].view(np.uint32), seeds[k].view(np.uint32))
+
+
+def test_strip_columns_round_trip_like_the_reference_reader(tmp_path):
+    """The strip columns of the reader layout (CsvOutputData.hpp:354-373) -> the StripCalibrationDetails column the
+    way CsvSpacePointReader.cpp:80-110 fills it: half length x unit direction (double) narrowed to float."""
+    from acts_b200 import csvio, events
+
+    ev = events.itk_strip_event(0, mu=3)
+    path = tmp_path / "event000000000-spacepoint_strip.csv"
+    csvio.write_strip_spacepoints(str(path), ev)
+    back = csvio.read_spacepoints(str(path))
+    n = ev["x"].size
+    assert back["x"].size == n and back["strip"].shape == (n, 12) and back["strip"].dtype == np.float32
+    for k in ("x", "y", "z", "r", "varZ", "varR"):
+        assert np.array_equal(back[k].view(np.uint32), ev[k].view(np.uint32)), k
+    # centre and separation are exact; the half vectors go through (length, unit direction): a few ulp
+    assert np.array_equal(back["strip"][:, :6].view(np.uint32), ev["strip"][:, :6].view(np.uint32))
+    assert np.allclose(back["strip"][:, 6:], ev["strip"][:, 6:], rtol=3e-7, atol=1e-9)
+    # a hand-made row: direction (0, 0.6, 0.8), half length 10 -> half vector (0, 6, 8)
+    with open(path, "w") as fh:
+        fh.write(",".join(csvio.STRIP_READER_COLUMNS) + "\n")
+        fh.write("7,1,2,3,2.236068,0.01,0.02,10,5,0,0.6,0.8,1,0,0,0.5,0.25,0.125,100,200,300\n")
+    one = csvio.read_spacepoints(str(path))
+    want = np.array([[100, 200, 300, 0.5, 0.25, 0.125, 0, 6, 8, 5, 0, 0]], np.float32)
+    assert np.allclose(one["strip"], want, rtol=1e-7)
+    assert one["measurement_id"][0] == 7

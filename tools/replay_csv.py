@@ -22,7 +22,9 @@ from acts_b200 import config, csvio, plugin  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--input-dir", required=True)
 ap.add_argument("--output-dir", required=True)
-ap.add_argument("--config", default="pu200", choices=("seeding_py", "pu200", "itk_like", "itk_conf"))
+ap.add_argument("--config", default="pu200", choices=("seeding_py", "pu200", "itk_like", "itk_conf", "itk_pixel", "itk_strip"))
+ap.add_argument("--strips", type=float, default=None, metavar="COT_THETA_DIFF_MAX",
+                help="strip triplet path (TripletSeedFinder useStripInfo = true) on files that carry the strip columns of the reader layout")
 ap.add_argument("--stem", default="spacepoint.csv")
 ap.add_argument("--compare", action="store_true")
 a = ap.parse_args()
@@ -37,7 +39,12 @@ bad = 0
 for path in files:
     event = int(re.search(r"event(\d+)-", os.path.basename(path)).group(1))
     sp = csvio.read_spacepoints(path)
-    seeds = eng.run(sp)
+    if a.strips is not None:
+        if "strip" not in sp:
+            sys.exit("%s: no strip columns (CsvOutputData.hpp:354-373)" % path)
+        seeds = eng.run(sp, strip_cot_theta_diff_max=a.strips)
+    else:
+        seeds = eng.run(sp)
     params = eng.estimate_params(seeds, sp, b_field=(0.0, 0.0, float(cfg.bFieldInZ)))
     out = csvio.per_event_filepath(a.output_dir, "seed.csv", event)
     csvio.write_seeds(out, seeds, sp, free_params=params, measurement_id=sp["measurement_id"])
